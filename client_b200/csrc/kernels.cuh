@@ -1,0 +1,87 @@
+// kernels.cuh -- launch interface between runtime.cu (contexts, regions, ABI)
+// and kernels.cu (the sm_100a kernels).  Internal; the public surface is
+// include/tb200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tb200.h"
+
+namespace tb200 {
+
+// ---- fill ---------------------------------------------------------------------
+constexpr int kFillThreads = 256;
+constexpr int kFillUnroll = 4;                                    // groups per thread per tile
+constexpr uint32_t kFillTileBytes = kFillThreads * kFillUnroll * 16;  // 16 KiB
+
+struct FillLaunch {
+  const tb200_fill_job* jobs;   // device
+  const uint32_t* tile_prefix;  // device, njobs+1 entries; unused when uniform
+  const uint64_t* dev_epoch;    // device or nullptr
+  uint64_t seed;
+  uint64_t epoch;
+  uint32_t njobs;
+  uint32_t total_tiles;
+  uint32_t uniform_tiles;       // >0: every job has exactly this many tiles
+};
+cudaError_t launch_fill(const FillLaunch& l, int sm_count, cudaStream_t s);
+
+// ---- pack / cast ----------------------------------------------------------------
+struct ImagePack {
+  void* dst;
+  const uint8_t* src;
+  uint32_t dst_dtype;  // FP16 / FP32 / BF16
+  uint32_t layout;     // TB200_NCHW / TB200_NHWC
+  uint32_t scaling;
+  int n, h, w, c;
+};
+// returns cudaErrorInvalidValue for unsupported combinations
+cudaError_t launch_pack_image(const ImagePack& p, int sm_count, cudaStream_t s,
+                              int* launches);
+
+cudaError_t launch_cast(void* dst, uint32_t dst_dtype, const void* src,
+                        uint32_t src_dtype, uint64_t nelem, int sm_count,
+                        cudaStream_t s);
+bool cast_supported(uint32_t src_dtype, uint32_t dst_dtype);
+
+struct StridedPack {
+  void* dst;
+  const void* src;
+  uint32_t elem_size;
+  int ndim;
+  int64_t shape[TB200_MAX_DIMS];
+  int64_t strides[TB200_MAX_DIMS];  // bytes
+  uint64_t nelem;
+};
+cudaError_t launch_pack_strided(const StridedPack& p, int sm_count, cudaStream_t s);
+
+constexpr uint32_t kCopyTileBytes = 16384;
+struct CopyLaunch {
+  const tb200_copy_job* jobs;   // device
+  const uint32_t* tile_prefix;  // device, njobs+1
+  uint32_t njobs;
+  uint32_t total_tiles;
+};
+cudaError_t launch_concat(const CopyLaunch& l, int sm_count, cudaStream_t s);
+
+// ---- check ----------------------------------------------------------------------
+struct CheckAccum {  // device scratch, one per job, zeroed before the launch
+  unsigned long long mismatches;
+  unsigned long long sum;
+  unsigned long long best;  // (orderable fp32 key << 32) | (0xFFFFFFFF - index)
+  unsigned int xor32;
+  unsigned int pad;
+};
+constexpr uint32_t kCheckChunkBytes = 1u << 20;  // one CTA per MiB of a job
+struct CheckLaunch {
+  const tb200_check_job* jobs;  // device
+  CheckAccum* accum;            // device, njobs entries
+  tb200_check_result* results;  // device or mapped host
+  uint32_t njobs;
+  uint32_t max_chunks;          // grid.x
+};
+cudaError_t launch_check(const CheckLaunch& l, cudaStream_t s);
+
+cudaError_t launch_epoch_bump(uint64_t* dev_epoch, uint64_t delta, cudaStream_t s);
+
+}  // namespace tb200

@@ -1,0 +1,941 @@
+// runtime.cu -- contexts, CUDA-IPC regions, staging pipelines, graphs and the
+// extern "C" surface declared in include/tb200.h.
+//
+// Reference behaviour this file restates (paths under the reference root,
+// PY = src/python/library/tritonclient):
+//   PY/utils/cuda_shared_memory/__init__.py:107-149  region create (cudaMalloc + IPC handle)
+//   PY/utils/cuda_shared_memory/__init__.py:173-239  host arrays -> region (H2D + sync)
+//   PY/utils/cuda_shared_memory/__init__.py:242-325  region -> host
+//   PY/utils/cuda_shared_memory/_utils.py:67-121     region / stream lifetime
+// The device work itself lives in kernels.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define TB200_CUDA(expr)                                                              \
+  do {                                                                                \
+    cudaError_t e__ = (expr);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      return fail(TB200_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));   \
+    }                                                                                 \
+  } while (0)
+
+// switch to a device for the duration of a call and switch back (the reference
+// does the same around every runtime call, cuda_shared_memory/__init__.py:128-147)
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
+    if (prev_ != dev) {
+      err_ = cudaSetDevice(dev);
+      switched_ = (err_ == cudaSuccess);
+    }
+  }
+  ~DeviceGuard() {
+    if (switched_ && prev_ >= 0) cudaSetDevice(prev_);
+  }
+  cudaError_t error() const { return err_; }
+
+ private:
+  int prev_ = -1;
+  bool switched_ = false;
+  cudaError_t err_ = cudaSuccess;
+};
+
+// ---- a tiny fork/join pool for the host side of the staging pipeline ----------
+class CopyPool {
+ public:
+  static CopyPool& instance() {
+    static CopyPool pool;
+    return pool;
+  }
+  int threads() const { return static_cast<int>(workers_.size()) + 1; }
+  // split [0, n) into contiguous pieces and memcpy them in parallel
+  void parallel_memcpy(void* dst, const void* src, size_t n) {
+    const int parts = (n < (1u << 20)) ? 1 : std::min<int>(threads(), static_cast<int>(n >> 19));
+    if (parts <= 1) {
+      memcpy(dst, src, n);
+      return;
+    }
+    const size_t piece = ((n / parts) + 63) & ~static_cast<size_t>(63);
+    std::unique_lock<std::mutex> lk(mu_);
+    pending_ = 0;
+    for (int p = 1; p < parts; ++p) {
+      const size_t off = piece * p;
+      if (off >= n) break;
+      const size_t len = std::min(piece, n - off);
+      tasks_.push_back({static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len});
+      ++pending_;
+    }
+    lk.unlock();
+    cv_.notify_all();
+    memcpy(dst, src, std::min(piece, n));
+    lk.lock();
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+  }
+
+ private:
+  struct Task {
+    char* dst;
+    const char* src;
+    size_t len;
+  };
+  CopyPool() {
+    int n = 4;
+    if (const char* env = getenv("TB200_COPY_THREADS")) n = atoi(env);
+    else {
+      const unsigned hc = std::thread::hardware_concurrency();
+      n = static_cast<int>(std::max(1u, std::min(8u, hc / 2)));
+    }
+    n = std::max(1, std::min(n, 64));
+    for (int i = 1; i < n; ++i) workers_.emplace_back([this] { run(); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void run() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      cv_.wait(lk, [&] { return stop_ || !tasks_.empty(); });
+      if (stop_) return;
+      Task t = tasks_.back();
+      tasks_.pop_back();
+      lk.unlock();
+      memcpy(t.dst, t.src, t.len);
+      lk.lock();
+      if (--pending_ == 0) done_cv_.notify_all();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<Task> tasks_;
+  std::vector<std::thread> workers_;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+
+constexpr size_t kStageBytes = 4u << 20;  // one pinned staging buffer
+constexpr int kStageCount = 4;            // in flight per context
+constexpr size_t kJobSlotBytes = 64u << 10;
+constexpr int kJobSlots = 32;
+constexpr size_t kFlushBytes = 256u << 20;  // > 126 MB L2
+
+}  // namespace
+
+struct tb200_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int device = 0;
+  uint64_t kernels_per_launch = 0;
+  std::vector<void*> device_allocs;  // job tables owned by the graph
+};
+
+struct tb200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  uint64_t launches = 0;
+  // pinned staging ring for host <-> region copies
+  void* stage[kStageCount] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[kStageCount] = {nullptr, nullptr, nullptr, nullptr};
+  int stage_next = 0;
+  // job-table upload ring (pinned host mirror + device copy)
+  char* job_host = nullptr;
+  char* job_dev = nullptr;
+  cudaEvent_t job_ev[kJobSlots];
+  bool job_ev_valid[kJobSlots];
+  int job_next = 0;
+  // check scratch
+  tb200::CheckAccum* accum = nullptr;
+  uint32_t accum_cap = 0;
+  // epoch + flush scratch
+  uint64_t* dev_epoch = nullptr;
+  void* flush_buf = nullptr;
+  // capture state
+  tb200_graph* capture = nullptr;
+  uint64_t capture_launches0 = 0;
+};
+
+struct tb200_timer {
+  tb200_ctx* ctx = nullptr;
+  cudaEvent_t start = nullptr, stop = nullptr;
+};
+
+struct tb200_region {
+  std::string name;
+  void* base = nullptr;
+  uint64_t size = 0;
+  int device = 0;
+  bool opened = false;  // mapped from another process's handle
+  cudaIpcMemHandle_t handle;
+};
+
+namespace {
+
+int ensure_stage(tb200_ctx* ctx) {
+  if (ctx->stage[0] != nullptr) return TB200_OK;
+  for (int i = 0; i < kStageCount; ++i) {
+    TB200_CUDA(cudaHostAlloc(&ctx->stage[i], kStageBytes, cudaHostAllocDefault));
+    TB200_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+  }
+  return TB200_OK;
+}
+
+int ensure_jobs(tb200_ctx* ctx) {
+  if (ctx->job_host != nullptr) return TB200_OK;
+  void* h = nullptr;
+  void* d = nullptr;
+  TB200_CUDA(cudaHostAlloc(&h, kJobSlotBytes * kJobSlots, cudaHostAllocDefault));
+  TB200_CUDA(cudaMalloc(&d, kJobSlotBytes * kJobSlots));
+  ctx->job_host = static_cast<char*>(h);
+  ctx->job_dev = static_cast<char*>(d);
+  for (int i = 0; i < kJobSlots; ++i) {
+    TB200_CUDA(cudaEventCreateWithFlags(&ctx->job_ev[i], cudaEventDisableTiming));
+    ctx->job_ev_valid[i] = false;
+  }
+  return TB200_OK;
+}
+
+// Make `bytes` of host data available on the device for the next kernel on the
+// context's stream.  Outside capture: pinned ring slot + async H2D.  During
+// capture: a dedicated device buffer owned by the graph, filled synchronously now
+// (job tables are constants of the graph, replays upload nothing).
+int upload(tb200_ctx* ctx, const void* host, size_t bytes, const void** dev_out) {
+  if (bytes > kJobSlotBytes) return fail(TB200_ERR_INVALID, "job table of %zu bytes exceeds %zu", bytes, kJobSlotBytes);
+  if (ctx->capture != nullptr) {
+    void* d = nullptr;
+    TB200_CUDA(cudaMalloc(&d, bytes == 0 ? 16 : bytes));
+    ctx->capture->device_allocs.push_back(d);
+    TB200_CUDA(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+    *dev_out = d;
+    return TB200_OK;
+  }
+  int rc = ensure_jobs(ctx);
+  if (rc != TB200_OK) return rc;
+  const int slot = ctx->job_next;
+  ctx->job_next = (slot + 1) % kJobSlots;
+  if (ctx->job_ev_valid[slot]) TB200_CUDA(cudaEventSynchronize(ctx->job_ev[slot]));
+  char* h = ctx->job_host + slot * kJobSlotBytes;
+  char* d = ctx->job_dev + slot * kJobSlotBytes;
+  memcpy(h, host, bytes);
+  TB200_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TB200_CUDA(cudaEventRecord(ctx->job_ev[slot], ctx->stream));
+  ctx->job_ev_valid[slot] = true;
+  *dev_out = d;
+  return TB200_OK;
+}
+
+int check_range(const tb200_region* r, uint64_t offset, uint64_t nbytes) {
+  if (offset > r->size || nbytes > r->size - offset) {
+    return fail(TB200_ERR_RANGE, "range [%llu, +%llu) outside region '%s' of %llu bytes",
+                static_cast<unsigned long long>(offset), static_cast<unsigned long long>(nbytes),
+                r->name.c_str(), static_cast<unsigned long long>(r->size));
+  }
+  return TB200_OK;
+}
+
+// host -> device through the pinned ring; does not synchronise at the end
+int staged_h2d(tb200_ctx* ctx, char* dst, const char* src, uint64_t nbytes) {
+  int rc = ensure_stage(ctx);
+  if (rc != TB200_OK) return rc;
+  uint64_t done = 0;
+  while (done < nbytes) {
+    const size_t n = static_cast<size_t>(std::min<uint64_t>(kStageBytes, nbytes - done));
+    const int b = ctx->stage_next;
+    ctx->stage_next = (b + 1) % kStageCount;
+    TB200_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));  // buffer free again?
+    CopyPool::instance().parallel_memcpy(ctx->stage[b], src + done, n);
+    TB200_CUDA(cudaMemcpyAsync(dst + done, ctx->stage[b], n, cudaMemcpyHostToDevice, ctx->stream));
+    TB200_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+    done += n;
+  }
+  return TB200_OK;
+}
+
+}  // namespace
+
+using namespace tb200;
+
+extern "C" {
+
+// ---------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------
+uint32_t tb200_dtype_size(uint32_t dtype) {
+  switch (dtype) {
+    case TB200_BOOL: case TB200_UINT8: case TB200_INT8: return 1;
+    case TB200_UINT16: case TB200_INT16: case TB200_FP16: case TB200_BF16: return 2;
+    case TB200_UINT32: case TB200_INT32: case TB200_FP32: return 4;
+    case TB200_UINT64: case TB200_INT64: case TB200_FP64: return 8;
+    default: return 0;
+  }
+}
+
+static const char* const kDtypeNames[] = {"",      "BOOL",  "UINT8", "UINT16", "UINT32",
+                                          "UINT64", "INT8",  "INT16", "INT32",  "INT64",
+                                          "FP16",  "FP32",  "FP64",  "BYTES",  "BF16"};
+
+uint32_t tb200_dtype_from_name(const char* name) {
+  if (name == nullptr) return TB200_INVALID;
+  for (uint32_t i = 1; i <= TB200_BF16; ++i) {
+    if (strcmp(name, kDtypeNames[i]) == 0) return i;
+  }
+  return TB200_INVALID;
+}
+const char* tb200_dtype_name(uint32_t dtype) {
+  return (dtype >= 1 && dtype <= TB200_BF16) ? kDtypeNames[dtype] : "";
+}
+
+int tb200_abi_version(void) { return TB200_ABI_VERSION; }
+const char* tb200_last_error(void) { return g_last_error.c_str(); }
+
+int tb200_device_count(int* count) {
+  if (count == nullptr) return fail(TB200_ERR_INVALID, "count is NULL");
+  *count = 0;
+  TB200_CUDA(cudaGetDeviceCount(count));
+  return TB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// contexts
+// ---------------------------------------------------------------------------
+int tb200_ctx_create(int device_id, tb200_ctx** out) {
+  if (out == nullptr) return fail(TB200_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  TB200_CUDA(cudaGetDeviceCount(&n));
+  if (device_id < 0 || device_id >= n) return fail(TB200_ERR_INVALID, "device %d not in [0,%d)", device_id, n);
+  DeviceGuard g(device_id);
+  TB200_CUDA(g.error());
+  tb200_ctx* ctx = new tb200_ctx();
+  ctx->device = device_id;
+  cudaError_t e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  void* ep = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc(&ep, sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMemset(ep, 0, sizeof(uint64_t));
+  if (e != cudaSuccess) {
+    delete ctx;
+    return fail(TB200_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+  }
+  ctx->dev_epoch = static_cast<uint64_t*>(ep);
+  *out = ctx;
+  return TB200_OK;
+}
+
+int tb200_ctx_destroy(tb200_ctx* ctx) {
+  if (ctx == nullptr) return TB200_OK;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < kStageCount; ++i) {
+    if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+    if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+  }
+  if (ctx->job_host) {
+    cudaFreeHost(ctx->job_host);
+    cudaFree(ctx->job_dev);
+    for (int i = 0; i < kJobSlots; ++i) cudaEventDestroy(ctx->job_ev[i]);
+  }
+  if (ctx->accum) cudaFree(ctx->accum);
+  if (ctx->dev_epoch) cudaFree(ctx->dev_epoch);
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return TB200_OK;
+}
+
+int tb200_ctx_set_stream(tb200_ctx* ctx, void* cuda_stream) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  return TB200_OK;
+}
+void* tb200_ctx_stream(tb200_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+int tb200_ctx_device(tb200_ctx* ctx) { return ctx ? ctx->device : -1; }
+int tb200_ctx_sm_count(tb200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t tb200_ctx_launch_count(tb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int tb200_ctx_sync(tb200_ctx* ctx) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TB200_OK;
+}
+
+int tb200_timer_create(tb200_ctx* ctx, tb200_timer** out) {
+  if (ctx == nullptr || out == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
+  DeviceGuard g(ctx->device);
+  tb200_timer* t = new tb200_timer();
+  t->ctx = ctx;
+  cudaError_t e = cudaEventCreate(&t->start);
+  if (e == cudaSuccess) e = cudaEventCreate(&t->stop);
+  if (e != cudaSuccess) {
+    delete t;
+    return fail(TB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e));
+  }
+  *out = t;
+  return TB200_OK;
+}
+int tb200_timer_start(tb200_timer* t) {
+  if (t == nullptr) return fail(TB200_ERR_INVALID, "timer is NULL");
+  DeviceGuard g(t->ctx->device);
+  TB200_CUDA(cudaEventRecord(t->start, t->ctx->stream));
+  return TB200_OK;
+}
+int tb200_timer_stop(tb200_timer* t) {
+  if (t == nullptr) return fail(TB200_ERR_INVALID, "timer is NULL");
+  DeviceGuard g(t->ctx->device);
+  TB200_CUDA(cudaEventRecord(t->stop, t->ctx->stream));
+  return TB200_OK;
+}
+int tb200_timer_elapsed_ms(tb200_timer* t, float* ms) {
+  if (t == nullptr || ms == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
+  DeviceGuard g(t->ctx->device);
+  TB200_CUDA(cudaEventSynchronize(t->stop));
+  TB200_CUDA(cudaEventElapsedTime(ms, t->start, t->stop));
+  return TB200_OK;
+}
+int tb200_timer_destroy(tb200_timer* t) {
+  if (t == nullptr) return TB200_OK;
+  DeviceGuard g(t->ctx->device);
+  cudaEventDestroy(t->start);
+  cudaEventDestroy(t->stop);
+  delete t;
+  return TB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// regions
+// ---------------------------------------------------------------------------
+int tb200_region_create(const char* name, uint64_t byte_size, int device_id, tb200_region** out) {
+  if (out == nullptr) return fail(TB200_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  TB200_CUDA(cudaGetDeviceCount(&n));
+  if (device_id < 0 || device_id >= n) return fail(TB200_ERR_INVALID, "device %d not in [0,%d)", device_id, n);
+  DeviceGuard g(device_id);
+  TB200_CUDA(g.error());
+  tb200_region* r = new tb200_region();
+  r->name = name ? name : "";
+  r->size = byte_size;
+  r->device = device_id;
+  // cudaMalloc(0) yields no allocation to export; keep one granule so that an
+  // empty region still has a valid handle (the reference would fail here)
+  cudaError_t e = cudaMalloc(&r->base, byte_size == 0 ? 256 : byte_size);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&r->handle, r->base);
+  if (e != cudaSuccess) {
+    if (r->base) cudaFree(r->base);
+    delete r;
+    return fail(TB200_ERR_CUDA, "unable to create cuda shared memory handle: %s", cudaGetErrorString(e));
+  }
+  *out = r;
+  return TB200_OK;
+}
+
+int tb200_region_open(const uint8_t ipc_handle[TB200_IPC_HANDLE_BYTES], uint64_t byte_size,
+                      int device_id, tb200_region** out) {
+  if (out == nullptr || ipc_handle == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  static_assert(sizeof(cudaIpcMemHandle_t) == TB200_IPC_HANDLE_BYTES, "IPC handle size");
+  DeviceGuard g(device_id);
+  TB200_CUDA(g.error());
+  tb200_region* r = new tb200_region();
+  r->size = byte_size;
+  r->device = device_id;
+  r->opened = true;
+  memcpy(&r->handle, ipc_handle, TB200_IPC_HANDLE_BYTES);
+  cudaError_t e = cudaIpcOpenMemHandle(&r->base, r->handle, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    delete r;
+    return fail(TB200_ERR_CUDA, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+  }
+  *out = r;
+  return TB200_OK;
+}
+
+int tb200_region_destroy(tb200_region* r) {
+  if (r == nullptr) return TB200_OK;
+  DeviceGuard g(r->device);
+  cudaError_t e = r->opened ? cudaIpcCloseMemHandle(r->base) : cudaFree(r->base);
+  delete r;
+  if (e != cudaSuccess) return fail(TB200_ERR_CUDA, "region release failed: %s", cudaGetErrorString(e));
+  return TB200_OK;
+}
+
+int tb200_region_ipc_handle(const tb200_region* r, uint8_t out[TB200_IPC_HANDLE_BYTES]) {
+  if (r == nullptr || out == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
+  memcpy(out, &r->handle, TB200_IPC_HANDLE_BYTES);
+  return TB200_OK;
+}
+uint64_t tb200_region_base(const tb200_region* r) { return r ? reinterpret_cast<uint64_t>(r->base) : 0; }
+uint64_t tb200_region_size(const tb200_region* r) { return r ? r->size : 0; }
+int tb200_region_device(const tb200_region* r) { return r ? r->device : -1; }
+const char* tb200_region_name(const tb200_region* r) { return r ? r->name.c_str() : ""; }
+
+int tb200_region_write_host_gather(tb200_ctx* ctx, tb200_region* r, uint64_t offset, int nchunks,
+                                   const void* const* srcs, const uint64_t* sizes) {
+  if (ctx == nullptr || r == nullptr || nchunks < 0 || (nchunks > 0 && (srcs == nullptr || sizes == nullptr))) {
+    return fail(TB200_ERR_INVALID, "bad argument");
+  }
+  if (ctx->device != r->device) return fail(TB200_ERR_INVALID, "context on device %d, region on %d", ctx->device, r->device);
+  uint64_t total = 0;
+  for (int i = 0; i < nchunks; ++i) total += sizes[i];
+  int rc = check_range(r, offset, total);
+  if (rc != TB200_OK) return rc;
+  DeviceGuard g(ctx->device);
+  char* dst = static_cast<char*>(r->base) + offset;
+  for (int i = 0; i < nchunks; ++i) {
+    if (sizes[i] == 0) continue;
+    if (srcs[i] == nullptr) return fail(TB200_ERR_INVALID, "chunk %d is NULL", i);
+    rc = staged_h2d(ctx, dst, static_cast<const char*>(srcs[i]), sizes[i]);
+    if (rc != TB200_OK) return rc;
+    dst += sizes[i];
+  }
+  TB200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TB200_OK;
+}
+
+int tb200_region_write_host(tb200_ctx* ctx, tb200_region* r, uint64_t offset, const void* src, uint64_t nbytes) {
+  const void* srcs[1] = {src};
+  const uint64_t sizes[1] = {nbytes};
+  return tb200_region_write_host_gather(ctx, r, offset, 1, srcs, sizes);
+}
+
+int tb200_region_read_host(tb200_ctx* ctx, const tb200_region* r, uint64_t offset, void* dst, uint64_t nbytes) {
+  if (ctx == nullptr || r == nullptr || (dst == nullptr && nbytes != 0)) return fail(TB200_ERR_INVALID, "bad argument");
+  if (ctx->device != r->device) return fail(TB200_ERR_INVALID, "context on device %d, region on %d", ctx->device, r->device);
+  int rc = check_range(r, offset, nbytes);
+  if (rc != TB200_OK) return rc;
+  if (nbytes == 0) return TB200_OK;
+  DeviceGuard g(ctx->device);
+  rc = ensure_stage(ctx);
+  if (rc != TB200_OK) return rc;
+  const char* src = static_cast<const char*>(r->base) + offset;
+  char* out = static_cast<char*>(dst);
+  // two-deep pipeline: D2H of chunk k+1 overlaps the host memcpy of chunk k
+  uint64_t issued = 0, copied = 0;
+  int qb[kStageCount];
+  size_t qn[kStageCount];
+  int qhead = 0, qlen = 0;
+  while (copied < nbytes) {
+    while (issued < nbytes && qlen < kStageCount) {
+      const size_t n = static_cast<size_t>(std::min<uint64_t>(kStageBytes, nbytes - issued));
+      const int b = ctx->stage_next;
+      ctx->stage_next = (b + 1) % kStageCount;
+      TB200_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));
+      TB200_CUDA(cudaMemcpyAsync(ctx->stage[b], src + issued, n, cudaMemcpyDeviceToHost, ctx->stream));
+      TB200_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+      qb[(qhead + qlen) % kStageCount] = b;
+      qn[(qhead + qlen) % kStageCount] = n;
+      ++qlen;
+      issued += n;
+    }
+    const int b = qb[qhead];
+    const size_t n = qn[qhead];
+    qhead = (qhead + 1) % kStageCount;
+    --qlen;
+    TB200_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));
+    CopyPool::instance().parallel_memcpy(out + copied, ctx->stage[b], n);
+    copied += n;
+  }
+  return TB200_OK;
+}
+
+int tb200_region_write_ptr(tb200_ctx* ctx, tb200_region* r, uint64_t offset, const void* src, uint64_t nbytes) {
+  if (ctx == nullptr || r == nullptr || (src == nullptr && nbytes != 0)) return fail(TB200_ERR_INVALID, "bad argument");
+  int rc = check_range(r, offset, nbytes);
+  if (rc != TB200_OK) return rc;
+  if (nbytes == 0) return TB200_OK;
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(cudaMemcpyAsync(static_cast<char*>(r->base) + offset, src, nbytes, cudaMemcpyDefault, ctx->stream));
+  TB200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TB200_OK;
+}
+
+int tb200_host_alloc(uint64_t nbytes, void** host_ptr, void** device_ptr) {
+  if (host_ptr == nullptr) return fail(TB200_ERR_INVALID, "host_ptr is NULL");
+  void* h = nullptr;
+  TB200_CUDA(cudaHostAlloc(&h, nbytes == 0 ? 16 : nbytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  *host_ptr = h;
+  if (device_ptr != nullptr) {
+    void* d = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&d, h, 0);
+    if (e != cudaSuccess) {
+      cudaFreeHost(h);
+      return fail(TB200_ERR_CUDA, "cudaHostGetDevicePointer failed: %s", cudaGetErrorString(e));
+    }
+    *device_ptr = d;
+  }
+  return TB200_OK;
+}
+int tb200_host_free(void* host_ptr) {
+  if (host_ptr == nullptr) return TB200_OK;
+  TB200_CUDA(cudaFreeHost(host_ptr));
+  return TB200_OK;
+}
+int tb200_device_alloc(int device_id, uint64_t nbytes, void** device_ptr) {
+  if (device_ptr == nullptr) return fail(TB200_ERR_INVALID, "device_ptr is NULL");
+  DeviceGuard g(device_id);
+  TB200_CUDA(g.error());
+  TB200_CUDA(cudaMalloc(device_ptr, nbytes == 0 ? 16 : nbytes));
+  return TB200_OK;
+}
+int tb200_device_free(int device_id, void* device_ptr) {
+  if (device_ptr == nullptr) return TB200_OK;
+  DeviceGuard g(device_id);
+  TB200_CUDA(cudaFree(device_ptr));
+  return TB200_OK;
+}
+int tb200_memcpy_h2d_async(tb200_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  return TB200_OK;
+}
+int tb200_memcpy_d2h_async(tb200_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return TB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fill
+// ---------------------------------------------------------------------------
+static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint64_t seed,
+                     uint64_t epoch, bool use_dev_epoch) {
+  if (ctx == nullptr || njobs < 0 || (njobs > 0 && jobs == nullptr)) return fail(TB200_ERR_INVALID, "bad argument");
+  if (njobs == 0) return TB200_OK;
+  DeviceGuard g(ctx->device);
+  const int max_jobs = static_cast<int>(kJobSlotBytes / sizeof(tb200_fill_job)) / 2;  // jobs + prefix share a slot
+  for (int base = 0; base < njobs; base += max_jobs) {
+    const int n = std::min(max_jobs, njobs - base);
+    std::vector<uint32_t> prefix(n + 1, 0);
+    bool uniform = true;
+    uint64_t total = 0;
+    for (int i = 0; i < n; ++i) {
+      const tb200_fill_job& jb = jobs[base + i];
+      const uint32_t es = tb200_dtype_size(jb.dtype);
+      if (es == 0) return fail(TB200_ERR_INVALID, "job %d: dtype %u cannot be filled", base + i, jb.dtype);
+      if (jb.mode > TB200_FILL_BYTE) return fail(TB200_ERR_INVALID, "job %d: unknown fill mode %u", base + i, jb.mode);
+      if (jb.nbytes != 0 && jb.dst == 0) return fail(TB200_ERR_INVALID, "job %d: dst is NULL", base + i);
+      if (jb.mode == TB200_FILL_RANDOM) {
+        const uint64_t lim = es == 1 ? 256ull : (es == 2 ? 65536ull : (es == 4 ? (1ull << 32) : 0ull));
+        const bool is_int = jb.dtype != TB200_FP16 && jb.dtype != TB200_FP32 && jb.dtype != TB200_FP64 &&
+                            jb.dtype != TB200_BF16 && jb.dtype != TB200_BOOL;
+        if (is_int && lim != 0 && jb.irange > lim) {
+          return fail(TB200_ERR_INVALID, "job %d: irange %llu exceeds the %u-byte element range", base + i,
+                      static_cast<unsigned long long>(jb.irange), es);
+        }
+      }
+      const uint64_t tiles = (jb.nbytes + kFillTileBytes - 1) / kFillTileBytes;
+      total += tiles;
+      if (total > 0xFFFFFFF0ull) return fail(TB200_ERR_INVALID, "fill launch too large");
+      prefix[i + 1] = static_cast<uint32_t>(total);
+      if (tiles != (jobs[base].nbytes + kFillTileBytes - 1) / kFillTileBytes) uniform = false;
+    }
+    if (total == 0) continue;
+    // one upload: [jobs | prefix]
+    const size_t jbytes = sizeof(tb200_fill_job) * n;
+    const size_t pbytes = sizeof(uint32_t) * (n + 1);
+    std::vector<char> blob(jbytes + pbytes);
+    memcpy(blob.data(), jobs + base, jbytes);
+    memcpy(blob.data() + jbytes, prefix.data(), pbytes);
+    const void* dev = nullptr;
+    int rc = upload(ctx, blob.data(), blob.size(), &dev);
+    if (rc != TB200_OK) return rc;
+    FillLaunch L;
+    L.jobs = static_cast<const tb200_fill_job*>(dev);
+    L.tile_prefix = reinterpret_cast<const uint32_t*>(static_cast<const char*>(dev) + jbytes);
+    L.dev_epoch = use_dev_epoch ? ctx->dev_epoch : nullptr;
+    L.seed = seed;
+    L.epoch = epoch;
+    L.njobs = static_cast<uint32_t>(n);
+    L.total_tiles = static_cast<uint32_t>(total);
+    L.uniform_tiles = uniform ? prefix[1] : 0;
+    TB200_CUDA(launch_fill(L, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+  }
+  return TB200_OK;
+}
+
+int tb200_fill_async(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint64_t seed, uint64_t stream_epoch) {
+  return fill_impl(ctx, jobs, njobs, seed, stream_epoch, false);
+}
+int tb200_fill_epoch_async(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint64_t seed) {
+  return fill_impl(ctx, jobs, njobs, seed, 0, true);
+}
+
+int tb200_ctx_epoch_set(tb200_ctx* ctx, uint64_t value) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(cudaStreamSynchronize(ctx->stream));
+  TB200_CUDA(cudaMemcpy(ctx->dev_epoch, &value, sizeof(value), cudaMemcpyHostToDevice));
+  return TB200_OK;
+}
+int tb200_ctx_epoch_bump_async(tb200_ctx* ctx, uint64_t delta) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(launch_epoch_bump(ctx->dev_epoch, delta, ctx->stream));
+  ctx->launches += 1;
+  return TB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pack / cast
+// ---------------------------------------------------------------------------
+int tb200_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype, uint32_t dst_layout,
+                           const void* src_u8_nhwc, int n, int h, int w, int c, uint32_t scaling) {
+  if (ctx == nullptr || dst == nullptr || src_u8_nhwc == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
+  if (dst_layout != TB200_NCHW && dst_layout != TB200_NHWC) return fail(TB200_ERR_INVALID, "unknown layout %u", dst_layout);
+  DeviceGuard g(ctx->device);
+  ImagePack p;
+  p.dst = dst;
+  p.src = static_cast<const uint8_t*>(src_u8_nhwc);
+  p.dst_dtype = dst_dtype;
+  p.layout = dst_layout;
+  p.scaling = scaling;
+  p.n = n; p.h = h; p.w = w; p.c = c;
+  int launches = 0;
+  cudaError_t e = launch_pack_image(p, ctx->sm_count, ctx->stream, &launches);
+  if (e == cudaErrorInvalidValue) {
+    return fail(TB200_ERR_INVALID, "pack_image: unsupported combination (dtype %u, n=%d h=%d w=%d c=%d, scaling %u)",
+                dst_dtype, n, h, w, c, scaling);
+  }
+  TB200_CUDA(e);
+  ctx->launches += launches;
+  return TB200_OK;
+}
+
+int tb200_cast_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype, const void* src, uint32_t src_dtype, uint64_t nelem) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  if (nelem == 0) return TB200_OK;
+  if (dst == nullptr || src == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
+  if (!cast_supported(src_dtype, dst_dtype)) {
+    return fail(TB200_ERR_INVALID, "cast %s -> %s is not supported", tb200_dtype_name(src_dtype), tb200_dtype_name(dst_dtype));
+  }
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(launch_cast(dst, dst_dtype, src, src_dtype, nelem, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  return TB200_OK;
+}
+
+int tb200_pack_strided_async(tb200_ctx* ctx, void* dst, const void* src, uint32_t elem_size, int ndim,
+                             const int64_t* shape, const int64_t* src_strides) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  if (ndim < 0 || ndim > TB200_MAX_DIMS) return fail(TB200_ERR_INVALID, "ndim %d not in [0,%d]", ndim, TB200_MAX_DIMS);
+  if (elem_size != 1 && elem_size != 2 && elem_size != 4 && elem_size != 8) return fail(TB200_ERR_INVALID, "elem_size %u", elem_size);
+  if (ndim > 0 && (shape == nullptr || src_strides == nullptr)) return fail(TB200_ERR_INVALID, "NULL shape/strides");
+  StridedPack p;
+  memset(&p, 0, sizeof(p));
+  p.dst = dst;
+  p.src = src;
+  p.elem_size = elem_size;
+  p.ndim = ndim;
+  p.nelem = 1;
+  for (int d = 0; d < ndim; ++d) {
+    if (shape[d] < 0) return fail(TB200_ERR_INVALID, "negative extent");
+    p.shape[d] = shape[d];
+    p.strides[d] = src_strides[d];
+    p.nelem *= static_cast<uint64_t>(shape[d]);
+  }
+  if (p.nelem == 0) return TB200_OK;
+  if (dst == nullptr || src == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(launch_pack_strided(p, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  return TB200_OK;
+}
+
+int tb200_concat_async(tb200_ctx* ctx, const tb200_copy_job* jobs, int njobs) {
+  if (ctx == nullptr || njobs < 0 || (njobs > 0 && jobs == nullptr)) return fail(TB200_ERR_INVALID, "bad argument");
+  if (njobs == 0) return TB200_OK;
+  DeviceGuard g(ctx->device);
+  const int max_jobs = static_cast<int>(kJobSlotBytes / (sizeof(tb200_copy_job) + sizeof(uint32_t))) - 1;
+  for (int base = 0; base < njobs; base += max_jobs) {
+    const int n = std::min(max_jobs, njobs - base);
+    std::vector<uint32_t> prefix(n + 1, 0);
+    uint64_t total = 0;
+    for (int i = 0; i < n; ++i) {
+      const tb200_copy_job& jb = jobs[base + i];
+      if (jb.nbytes != 0 && (jb.dst == 0 || jb.src == 0)) return fail(TB200_ERR_INVALID, "job %d: NULL pointer", base + i);
+      total += (jb.nbytes + kCopyTileBytes - 1) / kCopyTileBytes;
+      if (total > 0xFFFFFFF0ull) return fail(TB200_ERR_INVALID, "concat launch too large");
+      prefix[i + 1] = static_cast<uint32_t>(total);
+    }
+    if (total == 0) continue;
+    const size_t jbytes = sizeof(tb200_copy_job) * n;
+    const size_t pbytes = sizeof(uint32_t) * (n + 1);
+    std::vector<char> blob(jbytes + pbytes);
+    memcpy(blob.data(), jobs + base, jbytes);
+    memcpy(blob.data() + jbytes, prefix.data(), pbytes);
+    const void* dev = nullptr;
+    int rc = upload(ctx, blob.data(), blob.size(), &dev);
+    if (rc != TB200_OK) return rc;
+    CopyLaunch L;
+    L.jobs = static_cast<const tb200_copy_job*>(dev);
+    L.tile_prefix = reinterpret_cast<const uint32_t*>(static_cast<const char*>(dev) + jbytes);
+    L.njobs = static_cast<uint32_t>(n);
+    L.total_tiles = static_cast<uint32_t>(total);
+    TB200_CUDA(launch_concat(L, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+  }
+  return TB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// check
+// ---------------------------------------------------------------------------
+int tb200_check_async(tb200_ctx* ctx, const tb200_check_job* jobs, int njobs, tb200_check_result* results) {
+  if (ctx == nullptr || njobs < 0 || (njobs > 0 && (jobs == nullptr || results == nullptr))) return fail(TB200_ERR_INVALID, "bad argument");
+  if (njobs == 0) return TB200_OK;
+  DeviceGuard g(ctx->device);
+  const int max_jobs = std::min<int>(static_cast<int>(kJobSlotBytes / sizeof(tb200_check_job)), 65535);
+  if (ctx->capture == nullptr && ctx->accum_cap < static_cast<uint32_t>(std::min(njobs, max_jobs))) {
+    TB200_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->accum) cudaFree(ctx->accum);
+    ctx->accum = nullptr;
+    ctx->accum_cap = 0;
+    const uint32_t cap = std::max<uint32_t>(1024, static_cast<uint32_t>(std::min(njobs, max_jobs)));
+    void* p = nullptr;
+    TB200_CUDA(cudaMalloc(&p, sizeof(CheckAccum) * cap));
+    ctx->accum = static_cast<CheckAccum*>(p);
+    ctx->accum_cap = cap;
+  }
+  for (int base = 0; base < njobs; base += max_jobs) {
+    const int n = std::min(max_jobs, njobs - base);
+    uint64_t max_bytes = 0;
+    for (int i = 0; i < n; ++i) {
+      const tb200_check_job& jb = jobs[base + i];
+      if (jb.kind > TB200_CHECK_TOP1) return fail(TB200_ERR_INVALID, "job %d: unknown check kind %u", base + i, jb.kind);
+      if (jb.nbytes != 0 && jb.a == 0) return fail(TB200_ERR_INVALID, "job %d: a is NULL", base + i);
+      if ((jb.kind == TB200_CHECK_EQUAL || jb.kind == TB200_CHECK_ADDSUB) && jb.nbytes != 0 && jb.b == 0) return fail(TB200_ERR_INVALID, "job %d: b is NULL", base + i);
+      if (jb.kind == TB200_CHECK_ADDSUB && jb.nbytes != 0 && (jb.c == 0 || jb.d == 0)) return fail(TB200_ERR_INVALID, "job %d: c/d is NULL", base + i);
+      if ((jb.kind == TB200_CHECK_ADDSUB || jb.kind == TB200_CHECK_TOP1) && (jb.nbytes % 4) != 0) return fail(TB200_ERR_INVALID, "job %d: nbytes must be a multiple of 4", base + i);
+      max_bytes = std::max(max_bytes, jb.nbytes);
+    }
+    const void* dev = nullptr;
+    int rc = upload(ctx, jobs + base, sizeof(tb200_check_job) * n, &dev);
+    if (rc != TB200_OK) return rc;
+    CheckAccum* accum = ctx->accum;
+    if (ctx->capture != nullptr) {  // graph-owned scratch
+      void* p = nullptr;
+      TB200_CUDA(cudaMalloc(&p, sizeof(CheckAccum) * n));
+      ctx->capture->device_allocs.push_back(p);
+      accum = static_cast<CheckAccum*>(p);
+    }
+    TB200_CUDA(cudaMemsetAsync(accum, 0, sizeof(CheckAccum) * n, ctx->stream));
+    CheckLaunch L;
+    L.jobs = static_cast<const tb200_check_job*>(dev);
+    L.accum = accum;
+    L.results = results + base;
+    L.njobs = static_cast<uint32_t>(n);
+    L.max_chunks = static_cast<uint32_t>((max_bytes + kCheckChunkBytes - 1) / kCheckChunkBytes);
+    if (L.max_chunks > 65535u * 32u) return fail(TB200_ERR_INVALID, "check job too large");
+    TB200_CUDA(launch_check(L, ctx->stream));
+    ctx->launches += 2;
+  }
+  return TB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// graphs
+// ---------------------------------------------------------------------------
+int tb200_graph_begin(tb200_ctx* ctx) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  if (ctx->capture != nullptr) return fail(TB200_ERR_STATE, "capture already in progress");
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(cudaStreamSynchronize(ctx->stream));
+  tb200_graph* gr = new tb200_graph();
+  gr->device = ctx->device;
+  cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) {
+    delete gr;
+    return fail(TB200_ERR_CUDA, "cudaStreamBeginCapture failed: %s", cudaGetErrorString(e));
+  }
+  ctx->capture = gr;
+  ctx->capture_launches0 = ctx->launches;
+  return TB200_OK;
+}
+
+int tb200_graph_end(tb200_ctx* ctx, tb200_graph** out) {
+  if (ctx == nullptr || out == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
+  if (ctx->capture == nullptr) return fail(TB200_ERR_STATE, "no capture in progress");
+  DeviceGuard g(ctx->device);
+  tb200_graph* gr = ctx->capture;
+  ctx->capture = nullptr;
+  gr->kernels_per_launch = ctx->launches - ctx->capture_launches0;
+  ctx->launches = ctx->capture_launches0;  // captured kernels did not run yet
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &gr->graph);
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&gr->exec, gr->graph, 0);
+  if (e != cudaSuccess) {
+    tb200_graph_destroy(gr);
+    return fail(TB200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  }
+  *out = gr;
+  return TB200_OK;
+}
+
+int tb200_graph_launch(tb200_ctx* ctx, tb200_graph* gr) {
+  if (ctx == nullptr || gr == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(cudaGraphLaunch(gr->exec, ctx->stream));
+  ctx->launches += gr->kernels_per_launch;
+  return TB200_OK;
+}
+
+int tb200_graph_destroy(tb200_graph* gr) {
+  if (gr == nullptr) return TB200_OK;
+  DeviceGuard g(gr->device);
+  if (gr->exec) cudaGraphExecDestroy(gr->exec);
+  if (gr->graph) cudaGraphDestroy(gr->graph);
+  for (void* p : gr->device_allocs) cudaFree(p);
+  delete gr;
+  return TB200_OK;
+}
+
+int tb200_l2_flush_async(tb200_ctx* ctx) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  DeviceGuard g(ctx->device);
+  if (ctx->flush_buf == nullptr) TB200_CUDA(cudaMalloc(&ctx->flush_buf, kFlushBytes));
+  TB200_CUDA(cudaMemsetAsync(ctx->flush_buf, 0, kFlushBytes, ctx->stream));
+  return TB200_OK;
+}
+
+}  // extern "C"

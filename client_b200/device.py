@@ -1,0 +1,307 @@
+"""Python face of the libtb200 kernels: job builders and thin launch wrappers.
+
+Everything here is plumbing over the C ABI (include/tb200.h): argument
+marshalling into the job structs, buffer lifetimes, error translation.  No
+tensor arithmetic happens in Python.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _native
+from ._native import CheckJob, CheckResult, CopyJob, FillJob
+
+_FLOAT_TYPES = ("FP16", "FP32", "FP64", "BF16")
+_KINDS = {"sum": _native.CHECK_SUM, "equal": _native.CHECK_EQUAL,
+          "addsub": _native.CHECK_ADDSUB, "top1": _native.CHECK_TOP1}
+
+
+def make_fill_job(dst, nbytes, datatype, stream_id=0, mode="random", low=0.0, high=None):
+    """Build a tb200_fill_job.
+
+    Floats: uniform in [low, high); ``high=None`` -> the unit interval (``low``
+    must be 0).  Integers: uniform in [low, high); ``high=None`` -> raw bits.
+    ``mode`` "zero" writes zeros, "byte" writes ``low`` as a repeated byte.
+    """
+    code = _native.DTYPE_CODES.get(datatype)
+    if code is None or datatype == "BYTES":
+        raise ValueError("datatype '%s' cannot be generated" % datatype)
+    job = FillJob()
+    job.dst = int(dst)
+    job.nbytes = int(nbytes)
+    job.stream = int(stream_id) & 0xFFFFFFFFFFFFFFFF
+    job.dtype = code
+    if mode == "zero":
+        job.mode = _native.FILL_ZERO
+        return job
+    if mode == "byte":
+        job.mode = _native.FILL_BYTE
+        job.ilo = int(low)
+        return job
+    if mode != "random":
+        raise ValueError("unknown fill mode '%s'" % mode)
+    job.mode = _native.FILL_RANDOM
+    if datatype in _FLOAT_TYPES:
+        if high is None:
+            if float(low) != 0.0:
+                raise ValueError("low must be 0 for the unit interval; pass high as well")
+            job.lo, job.span = 0.0, 0.0
+        else:
+            span = float(high) - float(low)
+            if not span > 0.0:
+                raise ValueError("high must be greater than low")
+            job.lo, job.span = float(low), span
+    elif datatype != "BOOL":
+        if high is None:
+            job.ilo, job.irange = 0, 0
+        else:
+            rng = int(high) - int(low)
+            if rng <= 0:
+                raise ValueError("high must be greater than low")
+            job.ilo, job.irange = int(low), rng
+    return job
+
+
+class HostBuffer:
+    """Pinned, device-mapped host memory (tb200_host_alloc): where the kernels
+    emit HTTP binary bodies / gRPC raw_input_contents and small results."""
+
+    def __init__(self, nbytes):
+        self._lib = _native.load()
+        hp, dp = ctypes.c_void_p(), ctypes.c_void_p()
+        _native.check(self._lib.tb200_host_alloc(int(nbytes), ctypes.byref(hp), ctypes.byref(dp)))
+        self.nbytes = int(nbytes)
+        self.host_ptr = hp.value
+        self.device_ptr = dp.value
+        self._ctype = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.host_ptr)
+
+    def array(self, dtype=np.uint8, count=None, offset=0):
+        """numpy view (no copy) over the pinned bytes."""
+        dt = np.dtype(dtype)
+        n = (self.nbytes - offset) // dt.itemsize if count is None else count
+        return np.frombuffer(self._ctype, dtype=dt, count=n, offset=offset)
+
+    def view(self, offset=0, nbytes=None):
+        end = self.nbytes if nbytes is None else offset + nbytes
+        return memoryview(self._ctype)[offset:end]
+
+    def close(self):
+        if getattr(self, "host_ptr", None):
+            self._ctype = None
+            self._lib.tb200_host_free(ctypes.c_void_p(self.host_ptr))
+            self.host_ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceBuffer:
+    """Plain device memory owned by the caller (tb200_device_alloc)."""
+
+    def __init__(self, device_id, nbytes):
+        self._lib = _native.load()
+        p = ctypes.c_void_p()
+        _native.check(self._lib.tb200_device_alloc(int(device_id), int(nbytes), ctypes.byref(p)))
+        self.ptr = p.value
+        self.nbytes = int(nbytes)
+        self.device_id = int(device_id)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self._lib.tb200_device_free(self.device_id, ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Graph:
+    """A captured sequence of libtb200 launches (tb200_graph)."""
+
+    def __init__(self, ops, handle):
+        self._ops = ops
+        self._h = handle
+
+    def launch(self):
+        _native.check(self._ops._lib.tb200_graph_launch(self._ops._ctx.handle, self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._ops._lib.tb200_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceOps:
+    """Launch wrappers bound to one context (device + stream)."""
+
+    def __init__(self, ctx=None, device_id=0):
+        self._lib = _native.load()
+        self._ctx = ctx if ctx is not None else _native.default_context(device_id)
+
+    @property
+    def ctx(self):
+        return self._ctx
+
+    @property
+    def device_id(self):
+        return self._ctx.device_id
+
+    def sync(self):
+        self._ctx.sync()
+
+    # -- raw copies -------------------------------------------------------------
+    def h2d(self, dst_ptr, src_host_ptr, nbytes):
+        _native.check(self._lib.tb200_memcpy_h2d_async(self._ctx.handle, dst_ptr, src_host_ptr, int(nbytes)))
+
+    def d2h(self, dst_host_ptr, src_ptr, nbytes):
+        _native.check(self._lib.tb200_memcpy_d2h_async(self._ctx.handle, dst_host_ptr, src_ptr, int(nbytes)))
+
+    def upload(self, array):
+        """Blocking convenience: numpy array -> new DeviceBuffer."""
+        arr = np.ascontiguousarray(array)
+        buf = DeviceBuffer(self.device_id, max(arr.nbytes, 16))
+        if arr.nbytes:
+            self.h2d(buf.ptr, arr.ctypes.data, arr.nbytes)
+            self.sync()
+        return buf
+
+    def download(self, ptr, nbytes, dtype=np.uint8):
+        """Blocking convenience: device bytes -> numpy array."""
+        out = np.empty(int(nbytes), dtype=np.uint8)
+        if nbytes:
+            self.d2h(out.ctypes.data, ptr, nbytes)
+            self.sync()
+        return out.view(dtype)
+
+    # -- kernels ------------------------------------------------------------------
+    @staticmethod
+    def job_array(jobs, ctype):
+        if isinstance(jobs, ctypes.Array):
+            return jobs, len(jobs)
+        arr = (ctype * max(len(jobs), 1))(*jobs)
+        return arr, len(jobs)
+
+    def fill(self, jobs, seed=0, epoch=0):
+        arr, n = self.job_array(jobs, FillJob)
+        _native.check(self._lib.tb200_fill_async(self._ctx.handle, arr, n, int(seed), int(epoch)))
+
+    def fill_epoch(self, jobs, seed=0):
+        arr, n = self.job_array(jobs, FillJob)
+        _native.check(self._lib.tb200_fill_epoch_async(self._ctx.handle, arr, n, int(seed)))
+
+    def epoch_set(self, value):
+        _native.check(self._lib.tb200_ctx_epoch_set(self._ctx.handle, int(value)))
+
+    def epoch_bump(self, delta=1):
+        _native.check(self._lib.tb200_ctx_epoch_bump_async(self._ctx.handle, int(delta)))
+
+    def pack_image(self, dst_ptr, datatype, layout, src_ptr, n, h, w, c, scaling="NONE"):
+        _native.check(
+            self._lib.tb200_pack_image_async(
+                self._ctx.handle, dst_ptr, _native.DTYPE_CODES[datatype],
+                _native.NCHW if layout == "NCHW" else _native.NHWC,
+                src_ptr, int(n), int(h), int(w), int(c), _native.SCALING_CODES[scaling],
+            )
+        )
+
+    def pack_image_from_host(self, dst_ptr, datatype, layout, images_u8_nhwc, scaling="NONE"):
+        """Stage uint8 NHWC host images on the device, then pack into dst."""
+        arr = np.ascontiguousarray(images_u8_nhwc, dtype=np.uint8)
+        n, h, w, c = arr.shape
+        staging = self._scratch(arr.nbytes)
+        self.h2d(staging.ptr, arr.ctypes.data, arr.nbytes)
+        self.pack_image(dst_ptr, datatype, layout, staging.ptr, n, h, w, c, scaling)
+        self.sync()  # arr must stay alive until the H2D completed
+
+    def _scratch(self, nbytes):
+        cur = getattr(self, "_scratch_buf", None)
+        if cur is None or cur.nbytes < nbytes:
+            self.sync()
+            self._scratch_buf = DeviceBuffer(self.device_id, max(int(nbytes), 1 << 20))
+        return self._scratch_buf
+
+    def cast(self, dst_ptr, dst_type, src_ptr, src_type, nelem):
+        _native.check(
+            self._lib.tb200_cast_async(
+                self._ctx.handle, dst_ptr, _native.DTYPE_CODES[dst_type], src_ptr,
+                _native.DTYPE_CODES[src_type], int(nelem),
+            )
+        )
+
+    def pack_strided(self, dst_ptr, src_ptr, elem_size, shape, strides_bytes):
+        nd = len(shape)
+        c_shape = (ctypes.c_int64 * max(nd, 1))(*[int(s) for s in shape])
+        c_strides = (ctypes.c_int64 * max(nd, 1))(*[int(s) for s in strides_bytes])
+        _native.check(
+            self._lib.tb200_pack_strided_async(
+                self._ctx.handle, dst_ptr, src_ptr, int(elem_size), nd, c_shape, c_strides
+            )
+        )
+
+    def concat(self, jobs):
+        arr, n = self.job_array(jobs, CopyJob)
+        _native.check(self._lib.tb200_concat_async(self._ctx.handle, arr, n))
+
+    def check(self, jobs, results_ptr):
+        arr, n = self.job_array(jobs, CheckJob)
+        _native.check(self._lib.tb200_check_async(self._ctx.handle, arr, n, results_ptr))
+
+    def check_one(self, kind, a, nbytes, b=0, c=0, d=0):
+        """Blocking convenience: run one check job, return its result as a dict."""
+        job = CheckJob(a=int(a), b=int(b), c=int(c), d=int(d), nbytes=int(nbytes), kind=_KINDS[kind], pad=0)
+        res = self._result_buf()
+        self.check([job], res.device_ptr)
+        self.sync()
+        return result_dict(res.array(np.uint8, ctypes.sizeof(CheckResult)).tobytes())
+
+    def _result_buf(self):
+        cur = getattr(self, "_res_buf", None)
+        if cur is None:
+            self._res_buf = HostBuffer(4096)
+        return self._res_buf
+
+    def l2_flush(self):
+        _native.check(self._lib.tb200_l2_flush_async(self._ctx.handle))
+
+    # -- graphs ---------------------------------------------------------------------
+    def graph_begin(self):
+        _native.check(self._lib.tb200_graph_begin(self._ctx.handle))
+
+    def graph_end(self):
+        h = ctypes.c_void_p()
+        _native.check(self._lib.tb200_graph_end(self._ctx.handle, ctypes.byref(h)))
+        return Graph(self, h)
+
+
+def result_dict(raw):
+    """Decode one tb200_check_result (32 bytes)."""
+    r = CheckResult.from_buffer_copy(raw)
+    return {
+        "mismatches": int(r.mismatches),
+        "sum": int(r.sum),
+        "xor32": int(r.xor32),
+        "argmax": int(r.argmax),
+        "max_value": float(r.max_value),
+    }
+
+
+def results_array(host_buffer, count):
+    """Structured numpy view over an array of tb200_check_result in pinned memory."""
+    dt = np.dtype(
+        [("mismatches", "<u8"), ("sum", "<u8"), ("xor32", "<u4"), ("argmax", "<u4"),
+         ("max_value", "<f4"), ("pad", "<u4")]
+    )
+    return host_buffer.array(dt, count)

@@ -1,0 +1,310 @@
+/*
+ * tb200.h -- C ABI of libtb200.so, the B200-native data plane behind the
+ * tritonclient-compatible Python package `client_b200`.
+ *
+ * Every entry point is plain C: pointers, sizes, opaque handles.  No torch,
+ * numpy or Python types cross this boundary.  The Python drop-in modules
+ * (client_b200/utils/cuda_shared_memory, client_b200/perf) bind it with
+ * ctypes; INTEGRATION.md shows the stub a tritonclient maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative tb200_status on
+ *     failure; tb200_last_error() returns the message of the calling thread's
+ *     last failure (the Python layer turns it into CudaSharedMemoryException /
+ *     InferenceServerException with the reference's message texts).
+ *   - all device work of a context is issued on that context's stream; calls
+ *     whose name ends in _async return before the work completed.
+ *   - the library never falls back to host code for device work: without a
+ *     usable CUDA device the calls fail with TB200_ERR_CUDA.
+ *
+ * Each block cites the reference interface it replaces
+ * (paths relative to the reference root, PY = src/python/library/tritonclient).
+ */
+#ifndef TB200_H_
+#define TB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB200_ABI_VERSION 1
+
+typedef enum tb200_status {
+  TB200_OK = 0,
+  TB200_ERR_INVALID = -1,  /* bad argument */
+  TB200_ERR_CUDA = -2,     /* CUDA runtime/driver failure (message has it) */
+  TB200_ERR_RANGE = -3,    /* offset/size outside the region */
+  TB200_ERR_NOMEM = -4,
+  TB200_ERR_STATE = -5,    /* call not valid in the object's current state */
+  TB200_ERR_IO = -6        /* socket / transport failure (load generator) */
+} tb200_status;
+
+/* Triton/KServe datatypes. Names and element sizes follow
+ * PY/utils/__init__.py:148-205 (np_to_triton_dtype / triton_to_np_dtype) and
+ * PY/utils/_dlpack.py:170-216.  BYTES is variable length and never reaches a
+ * kernel as an element type. */
+typedef enum tb200_dtype {
+  TB200_INVALID = 0,
+  TB200_BOOL = 1,
+  TB200_UINT8 = 2,
+  TB200_UINT16 = 3,
+  TB200_UINT32 = 4,
+  TB200_UINT64 = 5,
+  TB200_INT8 = 6,
+  TB200_INT16 = 7,
+  TB200_INT32 = 8,
+  TB200_INT64 = 9,
+  TB200_FP16 = 10,
+  TB200_FP32 = 11,
+  TB200_FP64 = 12,
+  TB200_BYTES = 13,
+  TB200_BF16 = 14
+} tb200_dtype;
+
+/* size in bytes of one element, 0 for BYTES/invalid */
+uint32_t tb200_dtype_size(uint32_t dtype);
+/* "FP32" -> TB200_FP32 ; unknown -> TB200_INVALID */
+uint32_t tb200_dtype_from_name(const char* triton_name);
+const char* tb200_dtype_name(uint32_t dtype);
+
+int tb200_abi_version(void);
+const char* tb200_last_error(void);
+/* number of visible CUDA devices (0 and TB200_ERR_CUDA when there is none) */
+int tb200_device_count(int* count);
+
+/* ------------------------------------------------------------------------
+ * Context: one device + one stream + scratch (job tables, pinned staging).
+ * Replaces the module-global per-device stream cache of
+ * PY/utils/cuda_shared_memory/__init__.py:57-70 and _utils.py:103-121.
+ * ---------------------------------------------------------------------- */
+typedef struct tb200_ctx tb200_ctx;
+
+int tb200_ctx_create(int device_id, tb200_ctx** out);
+int tb200_ctx_destroy(tb200_ctx* ctx);
+/* use an externally owned cudaStream_t (e.g. torch's current stream) */
+int tb200_ctx_set_stream(tb200_ctx* ctx, void* cuda_stream);
+void* tb200_ctx_stream(tb200_ctx* ctx);
+int tb200_ctx_device(tb200_ctx* ctx);
+int tb200_ctx_sync(tb200_ctx* ctx);
+/* kernels launched by this context since creation (bench.py gpu_launches) */
+uint64_t tb200_ctx_launch_count(tb200_ctx* ctx);
+int tb200_ctx_sm_count(tb200_ctx* ctx);
+
+/* CUDA-event stopwatch on the context's stream (bench.py times kernels with
+ * these because torch.cuda.Event only sees torch's own stream). */
+typedef struct tb200_timer tb200_timer;
+int tb200_timer_create(tb200_ctx* ctx, tb200_timer** out);
+int tb200_timer_start(tb200_timer* t);
+int tb200_timer_stop(tb200_timer* t);
+/* blocks until the stop event completed; milliseconds between start/stop */
+int tb200_timer_elapsed_ms(tb200_timer* t, float* ms);
+int tb200_timer_destroy(tb200_timer* t);
+
+/* ------------------------------------------------------------------------
+ * CUDA-IPC regions.
+ * Replaces PY/utils/cuda_shared_memory/__init__.py:
+ *   create_shared_memory_region :107-149   -> tb200_region_create
+ *   get_raw_handle              :152-170   -> tb200_region_ipc_handle
+ *   set_shared_memory_region    :173-239   -> tb200_region_write_host(+_gather)
+ *   get_contents_as_numpy       :242-325   -> tb200_region_read_host
+ *   set_..._from_dlpack         :328-388   -> tb200_region_write_ptr
+ *   destroy_shared_memory_region:414-429 / _utils.py:88-100 (cudaFree in
+ *   __del__)                               -> tb200_region_destroy
+ * and, for the server side of the loop (the process that receives the
+ * register call of PY/http/_client.py:1129-1175), tb200_region_open.
+ * ---------------------------------------------------------------------- */
+typedef struct tb200_region tb200_region;
+
+#define TB200_IPC_HANDLE_BYTES 64
+
+int tb200_region_create(const char* name, uint64_t byte_size, int device_id,
+                        tb200_region** out);
+/* map a region exported by another process (cudaIpcOpenMemHandle) */
+int tb200_region_open(const uint8_t ipc_handle[TB200_IPC_HANDLE_BYTES],
+                      uint64_t byte_size, int device_id, tb200_region** out);
+int tb200_region_destroy(tb200_region* r);
+int tb200_region_ipc_handle(const tb200_region* r,
+                            uint8_t out[TB200_IPC_HANDLE_BYTES]);
+uint64_t tb200_region_base(const tb200_region* r); /* device address */
+uint64_t tb200_region_size(const tb200_region* r);
+int tb200_region_device(const tb200_region* r);
+const char* tb200_region_name(const tb200_region* r);
+
+/* host -> region: multi-threaded pinned staging + async H2D, returns after the
+ * bytes are visible on the device (same blocking contract as the reference's
+ * cudaMemcpyAsync + cudaStreamSynchronize at :222-231). */
+int tb200_region_write_host(tb200_ctx* ctx, tb200_region* r, uint64_t offset,
+                            const void* src, uint64_t nbytes);
+/* N host chunks packed back to back from `offset` (the per-array loop of
+ * :203-230) with one synchronisation at the end */
+int tb200_region_write_host_gather(tb200_ctx* ctx, tb200_region* r,
+                                   uint64_t offset, int nchunks,
+                                   const void* const* srcs,
+                                   const uint64_t* sizes);
+/* region -> host, only the requested bytes (the reference copies the whole
+ * region, :266-276) */
+int tb200_region_read_host(tb200_ctx* ctx, const tb200_region* r,
+                           uint64_t offset, void* dst, uint64_t nbytes);
+/* any UVA pointer (device, pinned, pageable) -> region, cudaMemcpyDefault */
+int tb200_region_write_ptr(tb200_ctx* ctx, tb200_region* r, uint64_t offset,
+                           const void* src, uint64_t nbytes);
+
+/* pinned, device-mapped host memory: the staging the HTTP binary body and the
+ * gRPC raw_input_contents are emitted into by the kernels below. */
+int tb200_host_alloc(uint64_t nbytes, void** host_ptr, void** device_ptr);
+int tb200_host_free(void* host_ptr);
+/* plain device memory for sources / scratch owned by the caller */
+int tb200_device_alloc(int device_id, uint64_t nbytes, void** device_ptr);
+int tb200_device_free(int device_id, void* device_ptr);
+int tb200_memcpy_h2d_async(tb200_ctx* ctx, void* dst, const void* src,
+                           uint64_t nbytes);
+int tb200_memcpy_d2h_async(tb200_ctx* ctx, void* dst, const void* src,
+                           uint64_t nbytes);
+
+/* ------------------------------------------------------------------------
+ * Kernel 1: synthetic-input fill (Philox4x32-10, one coalesced 16-byte store
+ * per lane per call).  perf_analyzer's random / zero input generation is NOT
+ * in the reference; the contract is defined in DESIGN.md and
+ * restated on the CPU in oracle/ (parity with perf_analyzer values: unpinned).
+ *
+ * Tensor bytes are cut into 16-byte groups; group g of a job is
+ *   philox4x32_10(ctr = {g.lo, g.hi, stream.lo, stream.hi}, key = seed)
+ * mapped to elements by dtype (DESIGN.md "fill contract").
+ * ---------------------------------------------------------------------- */
+typedef enum tb200_fill_mode {
+  TB200_FILL_RANDOM = 0, /* uniform: floats in [lo, lo+span), ints in
+                            [ilo, ilo+irange) or raw bits when irange == 0 */
+  TB200_FILL_ZERO = 1,
+  TB200_FILL_BYTE = 2    /* every byte = (uint8_t)ilo */
+} tb200_fill_mode;
+
+typedef struct tb200_fill_job {
+  uint64_t dst;     /* device (or mapped-host) address of the tensor bytes   */
+  uint64_t nbytes;  /* tensor byte size                                      */
+  uint64_t stream;  /* Philox stream id: (request, input) -> distinct data   */
+  uint32_t dtype;   /* tb200_dtype                                           */
+  uint32_t mode;    /* tb200_fill_mode                                       */
+  double lo;        /* float dtypes: lower bound                             */
+  double span;      /* float dtypes: width; 0 -> unit interval [0,1)         */
+  int64_t ilo;      /* integer dtypes: lower bound / fill byte               */
+  uint64_t irange;  /* integer dtypes: number of values, 0 -> raw bits       */
+} tb200_fill_job;   /* 64 bytes */
+
+/* One launch covers all jobs (one job = one input tensor of one concurrency
+ * slot). `stream_epoch` is added to every job's stream id; when
+ * `device_epoch` is non-NULL the kernel adds *device_epoch as well (used by
+ * captured graphs so that every replay produces fresh data). */
+int tb200_fill_async(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs,
+                     uint64_t seed, uint64_t stream_epoch);
+
+/* ------------------------------------------------------------------------
+ * Kernel 2: cast + layout pack.
+ *  - tb200_pack_image_async: uint8 HWC images -> {FP16,FP32,BF16} CHW (or HWC)
+ *    with NONE / INCEPTION / VGG scaling; restates the numpy arithmetic of
+ *    src/python/examples/image_client.py:154-193 (preprocess).  Source tiles
+ *    are staged in shared memory with TMA bulk copies (cp.async.bulk).
+ *  - tb200_cast_async: contiguous element-wise dtype conversion with numpy
+ *    astype semantics; FP32->BF16 truncates like serialize_bf16_tensor
+ *    (PY/utils/__init__.py:294-335).
+ *  - tb200_pack_strided_async: ndarray.tobytes() of a strided source
+ *    (PY/http/_infer_input.py:212, PY/grpc/_infer_input.py:173).
+ *  - tb200_concat_async: b"".join of N tensors into one wire body
+ *    (PY/http/_utils.py:141-151) or into one region
+ *    (PY/utils/cuda_shared_memory/__init__.py:203-230).
+ * ---------------------------------------------------------------------- */
+typedef enum tb200_scaling {
+  TB200_SCALE_NONE = 0,
+  TB200_SCALE_INCEPTION = 1, /* (x / 127.5) - 1 */
+  TB200_SCALE_VGG = 2        /* x - (123, 117, 104)   (c == 1: x - 128) */
+} tb200_scaling;
+
+typedef enum tb200_layout { TB200_NCHW = 0, TB200_NHWC = 1 } tb200_layout;
+
+int tb200_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
+                           uint32_t dst_layout, const void* src_u8_nhwc,
+                           int n, int h, int w, int c, uint32_t scaling);
+
+int tb200_cast_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
+                     const void* src, uint32_t src_dtype, uint64_t nelem);
+
+#define TB200_MAX_DIMS 8
+/* dst is C-contiguous; src_strides are in BYTES (numpy convention) and may be
+ * negative or zero */
+int tb200_pack_strided_async(tb200_ctx* ctx, void* dst, const void* src,
+                             uint32_t elem_size, int ndim,
+                             const int64_t* shape, const int64_t* src_strides);
+
+typedef struct tb200_copy_job {
+  uint64_t dst;
+  uint64_t src;
+  uint64_t nbytes;
+} tb200_copy_job;
+int tb200_concat_async(tb200_ctx* ctx, const tb200_copy_job* jobs, int njobs);
+
+/* ------------------------------------------------------------------------
+ * Kernel 3: on-device output unpack / validation.  Replaces the whole-region
+ * D2H + numpy compare of the examples
+ * (src/python/examples/simple_http_cudashm_client.py:164-195,
+ *  PY/utils/cuda_shared_memory/__init__.py:266-304).
+ * Every job produces one tb200_check_result; the array is written to
+ * `results` (device or mapped-host memory).
+ * ---------------------------------------------------------------------- */
+typedef enum tb200_check_kind {
+  TB200_CHECK_SUM = 0,     /* checksum only                                  */
+  TB200_CHECK_EQUAL = 1,   /* a[i] == b[i] bytewise                          */
+  TB200_CHECK_ADDSUB = 2,  /* int32: a == c + d and b == c - d               */
+  TB200_CHECK_TOP1 = 3     /* fp32 vector: checksum, argmax, non-finite count */
+} tb200_check_kind;
+
+typedef struct tb200_check_job {
+  uint64_t a;      /* primary buffer (the output tensor; ADDSUB: OUTPUT0)    */
+  uint64_t b;      /* EQUAL: expected bytes ; ADDSUB: OUTPUT1                */
+  uint64_t c;      /* ADDSUB: INPUT0                                         */
+  uint64_t d;      /* ADDSUB: INPUT1                                         */
+  uint64_t nbytes; /* bytes of `a`                                           */
+  uint32_t kind;
+  uint32_t pad;
+} tb200_check_job; /* 48 bytes */
+
+typedef struct tb200_check_result {
+  uint64_t mismatches; /* EQUAL / ADDSUB: elements (bytes for EQUAL) that
+                          differ; TOP1: count of non-finite values           */
+  uint64_t sum;        /* sum of the little-endian u32 words of `a` mod 2^64
+                          (trailing bytes zero-extended)                      */
+  uint32_t xor32;      /* xor of the same words                              */
+  uint32_t argmax;     /* TOP1: index of the maximum (lowest index on ties)  */
+  float max_value;     /* TOP1                                               */
+  uint32_t pad;
+} tb200_check_result;  /* 32 bytes */
+
+int tb200_check_async(tb200_ctx* ctx, const tb200_check_job* jobs, int njobs,
+                      tb200_check_result* results);
+
+/* ------------------------------------------------------------------------
+ * Issue loop building blocks: capture any sequence of the *_async calls above
+ * into a CUDA graph and replay it per measurement step / concurrency slot.
+ * The concurrency loop itself (the absent perf_analyzer ConcurrencyManager /
+ * ConcurrencyWorker) is restated natively in loadgen.h.
+ * ---------------------------------------------------------------------- */
+typedef struct tb200_graph tb200_graph;
+int tb200_graph_begin(tb200_ctx* ctx);
+int tb200_graph_end(tb200_ctx* ctx, tb200_graph** out);
+int tb200_graph_launch(tb200_ctx* ctx, tb200_graph* g);
+int tb200_graph_destroy(tb200_graph* g);
+/* device-resident epoch counter added to Philox stream ids inside graphs */
+int tb200_ctx_epoch_set(tb200_ctx* ctx, uint64_t value);
+int tb200_ctx_epoch_bump_async(tb200_ctx* ctx, uint64_t delta);
+/* fill variant that reads the context's device epoch (graph friendly) */
+int tb200_fill_epoch_async(tb200_ctx* ctx, const tb200_fill_job* jobs,
+                           int njobs, uint64_t seed);
+
+/* write > L2-size bytes so the next timed kernel starts with a cold L2 */
+int tb200_l2_flush_async(tb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TB200_H_ */
