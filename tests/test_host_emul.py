@@ -1,0 +1,88 @@
+"""client_b200/csrc/philox.cuh (the math the kernels inline) compiled for the host
+and compared with the oracle: every dtype of the fill contract, all 256 pixel values
+of every scaling mode, and the software fp16 conversions.  A test aid: the host build
+is never part of libtb200.so."""
+
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import cref, image
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emul", "emul.cc")
+LIB = os.path.join(HERE, "host_emul", "libemul.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    hdr = os.path.join(HERE, "..", "client_b200", "csrc", "philox.cuh")
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", LIB, SRC], check=True)
+    L = ctypes.CDLL(LIB)
+    L.emul_fill.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
+                            ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64]
+    for f in (L.emul_scale_f32_bits, L.emul_scale_f16_bits):
+        f.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
+        f.restype = ctypes.c_uint32
+    for f in (L.emul_f32_to_f16, L.emul_f16_to_f32):
+        f.argtypes = [ctypes.c_uint32]
+        f.restype = ctypes.c_uint32
+    return L
+
+
+TYPES = ["FP32", "FP16", "BF16", "FP64", "INT64", "UINT64", "INT32", "UINT32", "INT16", "UINT16", "INT8", "UINT8", "BOOL"]
+
+
+@pytest.mark.parametrize("dt", TYPES)
+def test_fill_contract_header_vs_oracle(emul, dt):
+    is_float = dt in ("FP32", "FP16", "BF16", "FP64")
+    cases = [dict()]
+    if is_float:
+        cases += [dict(lo=-1.0, span=2.0), dict(lo=0.5, span=1e-3), dict(lo=0.0, span=255.0)]
+    elif dt != "BOOL":
+        top = {"INT8": 200, "UINT8": 256, "INT16": 60000, "UINT16": 65536}.get(dt, 128256)
+        cases += [dict(ilo=-5, irange=top), dict(ilo=0, irange=2), dict(ilo=7, irange=1)]
+    for kw in cases:
+        n = 4099
+        out = np.zeros(n, np.uint8)
+        emul.emul_fill(out.ctypes.data, n, cref.DT[dt], 0xABCDEF0123456789, (9 << 32) | 77,
+                       kw.get("lo", 0.0), kw.get("span", 0.0), kw.get("ilo", 0), kw.get("irange", 0))
+        ref = cref.fill(n, dt, seed=0xABCDEF0123456789, stream=(9 << 32) | 77, **kw)
+        assert np.array_equal(out, ref), (dt, kw)
+
+
+def test_scaling_all_256_values(emul):
+    for code, name in ((0, "NONE"), (1, "INCEPTION"), (2, "VGG")):
+        for c in (1, 3):
+            for ch in range(c):
+                px = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(c, axis=2)
+                r32 = image.preprocess_pixels(px, np.float32, name, False)[0, :, ch].view(np.uint32)
+                r16 = image.preprocess_pixels(px, np.float16, name, False)[0, :, ch].view(np.uint16)
+                m32 = np.array([emul.emul_scale_f32_bits(i, code, c, ch) for i in range(256)], dtype=np.uint32)
+                m16 = np.array([emul.emul_scale_f16_bits(i, code, c, ch) for i in range(256)], dtype=np.uint16)
+                assert np.array_equal(r32, m32) and np.array_equal(r16, m16), (name, c, ch)
+
+
+def test_software_half_conversions(emul):
+    allh = np.arange(65536, dtype=np.uint16)
+    want = allh.view(np.float16).astype(np.float32).view(np.uint32)
+    got = np.array([emul.emul_f16_to_f32(int(h)) for h in allh], dtype=np.uint32)
+    ok = ~np.isnan(allh.view(np.float16))
+    assert np.array_equal(want[ok], got[ok])
+    rng = np.random.default_rng(1)
+    bits = rng.integers(0, 2**32, 50000, dtype=np.uint64).astype(np.uint32)
+    edge = np.array([0x477FE000, 0x477FEFFF, 0x477FF000, 0x38800000, 0x387FFFFF, 0x33000000, 0x33000001, 0x32FFFFFF,
+                     0x3F801000, 0x3F803000, 0x3F802000, 0x7F800000, 0xFF800000, 0, 0x80000000], dtype=np.uint32)
+    bits = np.concatenate([bits, edge])
+    with np.errstate(over="ignore"):
+        want = bits.view(np.float32).astype(np.float16).view(np.uint16)
+    got = np.array([emul.emul_f32_to_f16(int(b)) for b in bits], dtype=np.uint16)
+    ok = ~np.isnan(bits.view(np.float32))
+    assert np.array_equal(want[ok], got[ok])

@@ -1,0 +1,389 @@
+"""GPU parity tests: every kernel, through the C ABI, against the CPU oracle.
+
+Integer / byte / index work is compared bit-exactly.  Floating-point random fill
+is bit-exact against the C oracle (which uses fmaf like the kernel); against the
+numpy oracle the stated tolerance is 1 ulp for scaled ranges (oracle/fill.py).
+"""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import cref
+from oracle import fill as ofill
+from oracle import image as oimage
+
+pytestmark = pytest.mark.gpu
+
+FLOATS = ("FP32", "FP16", "BF16", "FP64")
+ALL_FILL_TYPES = ["FP32", "FP16", "BF16", "FP64", "INT64", "UINT64", "INT32", "UINT32",
+                  "INT16", "UINT16", "INT8", "UINT8", "BOOL"]
+
+
+def _fill_device(ops, nbytes, dt, seed, stream, offset=0, **kw):
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    buf = DeviceBuffer(0, nbytes + offset + 64)
+    guard = np.full(nbytes + offset + 64, 0xA5, np.uint8)
+    ops.h2d(buf.ptr, guard.ctypes.data, guard.size)
+    job = make_fill_job(buf.ptr + offset, nbytes, dt, stream, **kw)
+    ops.fill([job], seed=seed)
+    out = ops.download(buf.ptr, nbytes + offset + 64)
+    assert (out[:offset] == 0xA5).all() and (out[offset + nbytes:] == 0xA5).all(), "fill wrote outside its tensor"
+    return out[offset:offset + nbytes].copy()
+
+
+def _oracle_kwargs(dt, low, high):
+    if dt in FLOATS:
+        return dict(lo=0.0 if high is None else low, span=0.0 if high is None else high - low)
+    if dt == "BOOL" or high is None:
+        return {}
+    return dict(ilo=low, irange=high - low)
+
+
+@pytest.mark.parametrize("dt", ALL_FILL_TYPES)
+@pytest.mark.parametrize("nbytes", [0, 1, 15, 16, 17, 4096, 16384, 16400, 602112 + 7, 3 * 16384])
+def test_fill_default_range_bit_exact(gpu_ops, dt, nbytes):
+    es = {"FP64": 8, "INT64": 8, "UINT64": 8, "FP32": 4, "INT32": 4, "UINT32": 4}.get(dt, 2 if dt in ("FP16", "BF16", "INT16", "UINT16") else 1)
+    nbytes -= nbytes % es
+    got = _fill_device(gpu_ops, nbytes, dt, seed=0x1234567890ABCDEF, stream=(5 << 32) | 17)
+    ref = cref.fill(nbytes, dt, seed=0x1234567890ABCDEF, stream=(5 << 32) | 17)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("dt,low,high", [
+    ("FP32", -1.0, 1.0), ("FP32", 0.0, 255.0), ("FP16", -1.0, 1.0), ("BF16", -4.0, 4.0), ("FP64", -1.0, 3.0),
+    ("INT64", 0, 30522), ("INT64", -7, 1 << 40), ("UINT64", 5, 1 << 63), ("INT32", 0, 128256), ("INT32", -100, 100),
+    ("UINT32", 0, 1 << 32), ("INT16", -300, 300), ("UINT16", 0, 65536), ("INT8", -128, 128), ("UINT8", 0, 200),
+])
+def test_fill_ranges_vs_both_oracles(gpu_ops, dt, low, high):
+    nbytes = 100000 - (100000 % 16) + 8
+    got = _fill_device(gpu_ops, nbytes, dt, seed=42, stream=7, low=low, high=high)
+    kw = _oracle_kwargs(dt, low, high)
+    ref_c = cref.fill(nbytes, dt, seed=42, stream=7, **kw)
+    assert np.array_equal(got, ref_c), "kernel differs from the C oracle"
+    ref_np = ofill.fill_bytes(nbytes, dt, seed=42, stream=7, **kw)
+    if dt in ("FP32", "FP64"):
+        # stated tolerance vs the numpy oracle (no true fma in numpy): 1 ulp
+        vt = np.float32 if dt == "FP32" else np.float64
+        it = np.int32 if dt == "FP32" else np.int64
+        a = got[: nbytes - nbytes % 8].view(vt).view(it).astype(np.int64)
+        b = ref_np[: nbytes - nbytes % 8].view(vt).view(it).astype(np.int64)
+        assert np.abs(a - b).max() <= 1
+        v = got[: nbytes - nbytes % 8].view(vt)
+        assert v.min() >= low and v.max() < high
+    else:
+        assert np.array_equal(got, ref_np)
+    if dt.startswith(("INT", "UINT")):
+        es = int(dt[-2:].replace("T", "")) // 8 if dt[-2:].isdigit() else 1
+        npdt = {"INT64": np.int64, "UINT64": np.uint64, "INT32": np.int32, "UINT32": np.uint32,
+                "INT16": np.int16, "UINT16": np.uint16, "INT8": np.int8, "UINT8": np.uint8}[dt]
+        v = got[: nbytes - nbytes % 8].view(npdt)
+        assert int(v.min()) >= low and int(v.max()) < high
+
+
+def test_fill_unaligned_destination(gpu_ops):
+    for off in (1, 3, 4, 8, 12):
+        got = _fill_device(gpu_ops, 5000, "UINT8", seed=9, stream=1, offset=off)
+        assert np.array_equal(got, cref.fill(5000, "UINT8", seed=9, stream=1))
+
+
+def test_fill_zero_and_byte(gpu_ops):
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    buf = DeviceBuffer(0, 70000)
+    gpu_ops.fill([make_fill_job(buf.ptr, 70000, "FP32", mode="byte", low=0x5A)])
+    assert (gpu_ops.download(buf.ptr, 70000) == 0x5A).all()
+    gpu_ops.fill([make_fill_job(buf.ptr + 16, 69000, "FP32", mode="zero")])
+    out = gpu_ops.download(buf.ptr, 70000)
+    assert (out[:16] == 0x5A).all() and (out[16:69016] == 0).all() and (out[69016:] == 0x5A).all()
+
+
+def test_fill_many_jobs_one_launch(gpu_ops):
+    """One launch, many slots: uniform (64 x 602112 B, config C2) and ragged mixes."""
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    sizes = [602112] * 8 + [3072, 3072, 0, 16384, 5, 100000]
+    dts = ["FP32"] * 8 + ["INT64", "INT64", "FP32", "INT32", "UINT8", "FP16"]
+    offs = np.concatenate([[0], np.cumsum([(s + 255) // 256 * 256 for s in sizes])])
+    buf = DeviceBuffer(0, int(offs[-1]) + 256)
+    launches0 = gpu_ops.ctx.launch_count
+    jobs = []
+    for i, (s, dt) in enumerate(zip(sizes, dts)):
+        hi = 30522 if dt == "INT64" else (128256 if dt == "INT32" else None)
+        jobs.append(make_fill_job(buf.ptr + int(offs[i]), s, dt, stream_id=1000 + i, low=0 if hi else 0.0, high=hi))
+    gpu_ops.fill(jobs, seed=77, epoch=5)
+    gpu_ops.sync()
+    assert gpu_ops.ctx.launch_count - launches0 == 1
+    out = gpu_ops.download(buf.ptr, int(offs[-1]))
+    for i, (s, dt) in enumerate(zip(sizes, dts)):
+        kw = dict(ilo=0, irange=30522) if dt == "INT64" else (dict(ilo=0, irange=128256) if dt == "INT32" else {})
+        ref = cref.fill(s, dt, seed=77, stream=1000 + i + 5, **kw)
+        assert np.array_equal(out[int(offs[i]):int(offs[i]) + s], ref), (i, dt, s)
+    # uniform fast path
+    jobs = [make_fill_job(buf.ptr + i * 602112, 602112, "FP32", stream_id=i) for i in range(8)]
+    gpu_ops.fill(jobs, seed=1)
+    out = gpu_ops.download(buf.ptr, 8 * 602112)
+    for i in range(8):
+        assert np.array_equal(out[i * 602112:(i + 1) * 602112], cref.fill(602112, "FP32", seed=1, stream=i))
+
+
+def test_fill_full_size_checksum(gpu_ops):
+    """C3 size (38,535,168 B FP16): checksum of the device tensor, computed on the
+    device, equals the oracle's checksum of the oracle's tensor."""
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    n = 38535168
+    buf = DeviceBuffer(0, n)
+    gpu_ops.fill([make_fill_job(buf.ptr, n, "FP16", stream_id=3)], seed=2024)
+    res = gpu_ops.check_one("sum", buf.ptr, n)
+    ref = cref.fill(n, "FP16", seed=2024, stream=3)
+    s, x = cref.checksum(ref)
+    assert (res["sum"], res["xor32"]) == (s, x)
+    # and a sampled exact comparison of the tail
+    tail = gpu_ops.download(buf.ptr + n - 65536, 65536)
+    assert np.array_equal(tail, ref[-65536:])
+
+
+@pytest.mark.parametrize("dt", ["FP16", "FP32", "BF16"])
+@pytest.mark.parametrize("scaling", ["NONE", "INCEPTION", "VGG"])
+@pytest.mark.parametrize("shape", [(2, 224, 224, 3), (1, 16, 16, 3), (3, 20, 24, 3), (2, 7, 9, 3), (2, 32, 32, 1), (1, 5, 5, 4)])
+@pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
+def test_pack_image_bit_exact(gpu_ops, dt, scaling, shape, layout):
+    from client_b200.device import DeviceBuffer
+
+    if scaling == "VGG" and shape[3] == 4:
+        pytest.skip("VGG means are defined for 1 or 3 channels")
+    rng = np.random.default_rng(hash((dt, scaling, shape, layout)) & 0xFFFF)
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    src = gpu_ops.upload(img)
+    es = 4 if dt == "FP32" else 2
+    dst = DeviceBuffer(0, img.size * es + 32)
+    n, h, w, c = shape
+    gpu_ops.pack_image(dst.ptr, dt, layout, src.ptr, n, h, w, c, scaling)
+    got = gpu_ops.download(dst.ptr, img.size * es)
+    assert np.array_equal(got, cref.pack_image(img, dt, layout, scaling))
+    assert np.array_equal(got, oimage.pack_batch(img, dt, layout, scaling))
+
+
+def test_pack_image_all_256_values(gpu_ops):
+    """Every uint8 value through every scaling/dtype: the arithmetic has only 256
+    inputs per channel, so this is exhaustive."""
+    from client_b200.device import DeviceBuffer
+
+    img = np.arange(256, dtype=np.uint8).reshape(1, 16, 16, 1).repeat(3, axis=3)
+    img = np.concatenate([img, img[:, ::-1]], axis=0)
+    src = gpu_ops.upload(img)
+    for dt in ("FP16", "FP32", "BF16"):
+        for scaling in ("NONE", "INCEPTION", "VGG"):
+            es = 4 if dt == "FP32" else 2
+            dst = DeviceBuffer(0, img.size * es)
+            gpu_ops.pack_image(dst.ptr, dt, "NCHW", src.ptr, 2, 16, 16, 3, scaling)
+            got = gpu_ops.download(dst.ptr, img.size * es)
+            assert np.array_equal(got, oimage.pack_batch(img, dt, "NCHW", scaling)), (dt, scaling)
+
+
+def test_pack_image_full_size_checksum(gpu_ops):
+    """C3(ii): 128 x 224 x 224 x 3 uint8 -> FP16 CHW INCEPTION, compared in full."""
+    from client_b200.device import DeviceBuffer
+
+    img = np.random.default_rng(3).integers(0, 256, (128, 224, 224, 3), dtype=np.uint8)
+    src = gpu_ops.upload(img)
+    dst = DeviceBuffer(0, img.size * 2)
+    gpu_ops.pack_image(dst.ptr, "FP16", "NCHW", src.ptr, 128, 224, 224, 3, "INCEPTION")
+    res = gpu_ops.check_one("sum", dst.ptr, img.size * 2)
+    ref = cref.pack_image(img, "FP16", "NCHW", "INCEPTION")
+    assert (res["sum"], res["xor32"]) == cref.checksum(ref)
+    assert np.array_equal(gpu_ops.download(dst.ptr, img.size * 2), ref)
+
+
+CASTS = [("UINT8", "FP32"), ("UINT8", "FP16"), ("UINT8", "BF16"), ("INT8", "FP32"), ("INT16", "FP16"),
+         ("UINT16", "FP32"), ("INT32", "FP32"), ("INT32", "FP64"), ("INT32", "INT64"), ("UINT32", "INT64"),
+         ("INT64", "INT32"), ("INT64", "FP32"), ("INT64", "FP64"), ("FP16", "FP32"), ("BF16", "FP32"),
+         ("FP32", "FP16"), ("FP32", "BF16"), ("FP32", "FP64"), ("FP64", "FP32"), ("FP64", "FP16"),
+         ("BOOL", "FP32"), ("FP32", "FP32"), ("INT64", "INT64"), ("UINT8", "UINT8")]
+NP = {"BOOL": np.bool_, "UINT8": np.uint8, "INT8": np.int8, "UINT16": np.uint16, "INT16": np.int16,
+      "UINT32": np.uint32, "INT32": np.int32, "UINT64": np.uint64, "INT64": np.int64,
+      "FP16": np.float16, "FP32": np.float32, "FP64": np.float64}
+
+
+def _random_values(dt, n, rng):
+    if dt == "BF16":
+        return (rng.integers(0, 1 << 16, n, dtype=np.uint32).astype(np.uint16))
+    if dt == "BOOL":
+        return rng.integers(0, 2, n).astype(np.bool_)
+    if dt.startswith("FP"):
+        bits = {"FP16": 16, "FP32": 32, "FP64": 64}[dt]
+        raw = rng.integers(0, 1 << 62, n, dtype=np.uint64).astype({16: np.uint16, 32: np.uint32, 64: np.uint64}[bits])
+        v = raw.view(NP[dt])
+        special = np.array([0.0, -0.0, 1.0, -2.5, 65504.0, 65520.0, 1e-8, 6e-8, 5.96e-8, np.inf, -np.inf, 3.0e38, 1e-40], dtype=np.float64).astype(NP[dt])
+        v = v.copy()
+        v[: special.size] = special
+        v[np.isnan(v)] = 1.5  # NaN payload propagation is not part of the contract
+        return v
+    info = np.iinfo(NP[dt])
+    v = rng.integers(info.min, info.max, n, dtype=np.int64 if info.min < 0 else np.uint64, endpoint=True).astype(NP[dt])
+    v[:4] = np.array([info.min, info.max, 0, 1]).astype(NP[dt])
+    return v
+
+
+@pytest.mark.parametrize("src_t,dst_t", CASTS)
+@pytest.mark.parametrize("n", [0, 1, 7, 4096, 100003])
+def test_cast_matches_numpy_astype(gpu_ops, src_t, dst_t, n):
+    from client_b200.device import DeviceBuffer
+
+    rng = np.random.default_rng(n + len(src_t) * 13 + len(dst_t))
+    v = _random_values(src_t, n, rng)
+    if src_t == "BF16":
+        as_f32 = (v.astype(np.uint32) << 16).view(np.float32)
+        as_f32 = np.where(np.isnan(as_f32), np.float32(1.5), as_f32)
+        v = (as_f32.view(np.uint32) >> 16).astype(np.uint16)
+        src_vals = (v.astype(np.uint32) << 16).view(np.float32)
+    else:
+        src_vals = v
+    with np.errstate(all="ignore"):
+        if dst_t == "BF16":
+            ref = (src_vals.astype(np.float32).view(np.uint32) >> 16).astype(np.uint16)
+        else:
+            ref = src_vals.astype(NP[dst_t])
+    src = gpu_ops.upload(v) if n else DeviceBuffer(0, 16)
+    dst = DeviceBuffer(0, max(ref.nbytes, 16))
+    gpu_ops.cast(dst.ptr, dst_t, src.ptr, src_t, n)
+    got = gpu_ops.download(dst.ptr, ref.nbytes)
+    assert np.array_equal(got, np.ascontiguousarray(ref).view(np.uint8).reshape(-1)), (src_t, dst_t)
+
+
+def test_cast_unsupported_pair_fails_loudly(gpu_ops):
+    from client_b200 import _native
+    from client_b200.device import DeviceBuffer
+
+    a = DeviceBuffer(0, 64)
+    with pytest.raises(_native.NativeError):
+        gpu_ops.cast(a.ptr, "UINT8", a.ptr, "FP32", 4)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.float32, np.int64])
+def test_pack_strided_equals_tobytes(gpu_ops, dtype):
+    from client_b200.device import DeviceBuffer
+
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 100, (6, 10, 14, 9)).astype(dtype)
+    src = gpu_ops.upload(base)
+    views = [base.transpose(0, 3, 1, 2), base[:, ::2, 1:13:3, ::-1], base[2:5, :, :, 4], base.T,
+             base[::-1, ::-1], np.broadcast_to(base[:1, :1], (3, 4, 14, 9)), base[1, 2, 3, 4:5], base[:, :0]]
+    for v in views:
+        nbytes = v.size * v.itemsize
+        dst = DeviceBuffer(0, nbytes + 32)
+        off = v.__array_interface__["data"][0] - base.__array_interface__["data"][0]
+        gpu_ops.pack_strided(dst.ptr, src.ptr + off, v.itemsize, v.shape, v.strides)
+        assert np.array_equal(gpu_ops.download(dst.ptr, nbytes), np.frombuffer(v.tobytes(), np.uint8))
+
+
+def test_concat_equals_bytes_join(gpu_ops):
+    from client_b200._native import CopyJob
+    from client_b200.device import DeviceBuffer
+
+    rng = np.random.default_rng(11)
+    parts = [rng.integers(0, 256, n, dtype=np.uint8) for n in (319, 64, 0, 16384, 100001, 7, 602112)]
+    srcs = [gpu_ops.upload(p) if p.size else DeviceBuffer(0, 16) for p in parts]
+    total = sum(p.size for p in parts)
+    dst = DeviceBuffer(0, total + 16)
+    jobs, off = [], 0
+    for p, s in zip(parts, srcs):
+        jobs.append(CopyJob(dst=dst.ptr + off, src=s.ptr, nbytes=p.size))
+        off += p.size
+    gpu_ops.concat(jobs)
+    assert gpu_ops.download(dst.ptr, total).tobytes() == b"".join(p.tobytes() for p in parts)
+
+
+def test_check_kinds(gpu_ops):
+    from client_b200._native import CheckJob
+    from client_b200.device import HostBuffer, results_array
+
+    rng = np.random.default_rng(2)
+    a = rng.integers(-1000, 1000, (1, 16), dtype=np.int32)
+    b = rng.integers(-1000, 1000, (1, 16), dtype=np.int32)
+    in0, in1 = gpu_ops.upload(a), gpu_ops.upload(b)
+    good0, good1 = gpu_ops.upload(a + b), gpu_ops.upload(a - b)
+    bad = (a + b).copy()
+    bad[0, 3] += 1
+    bad0 = gpu_ops.upload(bad)
+    logits = rng.standard_normal(1000).astype(np.float32)
+    logits[17] = np.nan
+    logits[500] = np.inf
+    logits[600] = -np.inf
+    lg = gpu_ops.upload(logits)
+    blob = rng.integers(0, 256, 3 * (1 << 20) + 13, dtype=np.uint8)
+    blob2 = blob.copy()
+    blob2[[5, 1 << 20, blob.size - 1]] ^= 0xFF
+    d1, d2 = gpu_ops.upload(blob), gpu_ops.upload(blob2)
+    jobs = [
+        CheckJob(a=good0.ptr, b=good1.ptr, c=in0.ptr, d=in1.ptr, nbytes=64, kind=2),
+        CheckJob(a=bad0.ptr, b=good1.ptr, c=in0.ptr, d=in1.ptr, nbytes=64, kind=2),
+        CheckJob(a=lg.ptr, nbytes=4000, kind=3),
+        CheckJob(a=d1.ptr, b=d2.ptr, nbytes=blob.size, kind=1),
+        CheckJob(a=d1.ptr + 1, nbytes=blob.size - 1, kind=0),  # unaligned checksum
+        CheckJob(a=d1.ptr, nbytes=0, kind=0),
+    ]
+    res = HostBuffer(4096)
+    gpu_ops.check(jobs, res.device_ptr)
+    gpu_ops.sync()
+    r = results_array(res, len(jobs))
+    assert r[0]["mismatches"] == 0 and r[1]["mismatches"] == 1
+    assert cref.addsub_mismatches(bad, a - b, a, b) == 1
+    assert (int(r[0]["sum"]), int(r[0]["xor32"])) == cref.checksum(a + b)
+    idx, mv, nonfinite = cref.top1(logits)
+    assert int(r[2]["argmax"]) == idx == 500 and int(r[2]["mismatches"]) == nonfinite == 3
+    assert np.isinf(r[2]["max_value"])
+    assert int(r[3]["mismatches"]) == cref.count_diff_bytes(blob, blob2) == 3
+    assert (int(r[3]["sum"]), int(r[3]["xor32"])) == cref.checksum(blob)
+    assert (int(r[4]["sum"]), int(r[4]["xor32"])) == cref.checksum(blob[1:])
+    assert int(r[5]["sum"]) == 0 and int(r[5]["mismatches"]) == 0
+    # finite logits: argmax equals numpy's
+    logits2 = rng.standard_normal(1000).astype(np.float32)
+    out = gpu_ops.check_one("top1", gpu_ops.upload(logits2).ptr, 4000)
+    assert out["argmax"] == int(np.argmax(logits2)) and out["max_value"] == float(logits2.max())
+
+
+def test_graph_replay_advances_epoch(gpu_ops):
+    """A captured fill produces fresh data on every replay (device epoch), and
+    equals the oracle for stream = slot + epoch."""
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    n = 65536 + 48
+    buf = DeviceBuffer(0, 2 * n)
+    jobs = [make_fill_job(buf.ptr, n, "FP32", stream_id=10), make_fill_job(buf.ptr + n, n, "INT32", stream_id=11, low=0, high=1000)]
+    gpu_ops.epoch_set(100)
+    gpu_ops.graph_begin()
+    gpu_ops.fill_epoch(jobs, seed=5)
+    gpu_ops.epoch_bump(2)
+    g = gpu_ops.graph_end()
+    for it in range(3):
+        g.launch()
+        out = gpu_ops.download(buf.ptr, 2 * n)
+        e = 100 + 2 * it
+        assert np.array_equal(out[:n], cref.fill(n, "FP32", seed=5, stream=10 + e))
+        assert np.array_equal(out[n:], cref.fill(n, "INT32", seed=5, stream=11 + e, ilo=0, irange=1000))
+    g.close()
+
+
+def test_fill_into_pinned_host_wire_buffer(gpu_ops):
+    """C4 shape: 2 x INT64[1,384] per request written by the kernel straight into
+    mapped host memory (the gRPC raw_input_contents staging), 256 slots, one launch."""
+    from client_b200.device import HostBuffer, make_fill_job
+
+    slots, per = 256, 3072
+    hb = HostBuffer(slots * 2 * per)
+    jobs = []
+    for s in range(slots):
+        jobs.append(make_fill_job(hb.device_ptr + (2 * s) * per, per, "INT64", stream_id=2 * s, low=0, high=30522))
+        jobs.append(make_fill_job(hb.device_ptr + (2 * s + 1) * per, per, "INT64", stream_id=2 * s + 1, low=0, high=2))
+    gpu_ops.fill(jobs, seed=3)
+    gpu_ops.sync()
+    host = hb.array(np.uint8)
+    for s in (0, 1, 100, 255):
+        assert np.array_equal(host[(2 * s) * per:(2 * s + 1) * per], cref.fill(per, "INT64", seed=3, stream=2 * s, ilo=0, irange=30522))
+        assert np.array_equal(host[(2 * s + 1) * per:(2 * s + 2) * per], cref.fill(per, "INT64", seed=3, stream=2 * s + 1, ilo=0, irange=2))
+    ids = host[:per].view(np.int64)
+    assert ids.min() >= 0 and ids.max() < 30522
