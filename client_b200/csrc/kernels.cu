@@ -193,6 +193,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -201,6 +202,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+    // a copy that never lands is a bug: fail the launch instead of hanging the GPU
+    if (!done && ++spins > (1u << 26)) __trap();
   } while (!done);
 }
 // TMA bulk copy global -> shared, completion signalled on the mbarrier
