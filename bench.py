@@ -159,14 +159,15 @@ def run_b200(args):
             CheckJob(a=out_regions[s]._base_addr + k * OUT_BYTES, nbytes=OUT_BYTES, kind=_native.CHECK_TOP1) for k in range(SLOTS)]))
     ops.sync()
 
-    # --- value: one CUDA graph per set = fill(64 slots) + epoch bump + validate(64 outputs)
+    # --- value: one CUDA graph per set = fill(64 slots, epoch advanced in-kernel) || validate(64 outputs)
     graphs = []
     ops.epoch_set(0)
     for s in range(SETS):
         ops.graph_begin()
-        ops.fill_epoch(fill_jobs[s], seed=SEED)
-        ops.epoch_bump(SLOTS)
+        ops.fork()   # validate the 64 output regions on a parallel branch ...
         ops.check(check_jobs[s], results.device_ptr + s * SLOTS * 32)
+        ops.join()
+        ops.fill_epoch(fill_jobs[s], seed=SEED, bump=SLOTS)  # ... while the 64 inputs are generated
         graphs.append(ops.graph_end())
 
     sampler = ClockSampler(local)

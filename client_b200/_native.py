@@ -94,6 +94,8 @@ SIGNATURES = {
     "tb200_ctx_stream": (c_vp, [c_vp]),
     "tb200_ctx_device": (c_int, [c_vp]),
     "tb200_ctx_sync": (c_int, [c_vp]),
+    "tb200_ctx_fork": (c_int, [c_vp]),
+    "tb200_ctx_join": (c_int, [c_vp]),
     "tb200_ctx_launch_count": (c_u64, [c_vp]),
     "tb200_ctx_sm_count": (c_int, [c_vp]),
     "tb200_timer_create": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
@@ -120,7 +122,7 @@ SIGNATURES = {
     "tb200_memcpy_h2d_async": (c_int, [c_vp, c_vp, c_vp, c_u64]),
     "tb200_memcpy_d2h_async": (c_int, [c_vp, c_vp, c_vp, c_u64]),
     "tb200_fill_async": (c_int, [c_vp, ctypes.POINTER(FillJob), c_int, c_u64, c_u64]),
-    "tb200_fill_epoch_async": (c_int, [c_vp, ctypes.POINTER(FillJob), c_int, c_u64]),
+    "tb200_fill_epoch_async": (c_int, [c_vp, ctypes.POINTER(FillJob), c_int, c_u64, c_u64]),
     "tb200_pack_image_async": (c_int, [c_vp, c_vp, c_u32, c_u32, c_vp, c_int, c_int, c_int, c_int, c_u32]),
     "tb200_cast_async": (c_int, [c_vp, c_vp, c_u32, c_vp, c_u32, c_u64]),
     "tb200_pack_strided_async": (c_int, [c_vp, c_vp, c_vp, c_u32, c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),

@@ -56,82 +56,83 @@ __device__ __forceinline__ uint32_t find_job(const uint32_t* __restrict__ prefix
 // =============================================================================
 // Kernel 1: fill
 // =============================================================================
+// One span = up to kFillSpanGroups consecutive 16-byte groups of one job, processed by
+// one CTA.  `count` groups exist in the span (the last may be partial), the first `full`
+// of them can be written with one aligned 16-byte store.
 template <uint32_t DT>
-__device__ __forceinline__ void fill_tile_random(uint8_t* __restrict__ dst, uint64_t nbytes,
-                                                 uint64_t group0, const FillParams& p,
-                                                 uint32_t s_lo, uint32_t s_hi, uint32_t k0,
-                                                 uint32_t k1, bool fast) {
-  if (fast) {
-    // whole tile in range and 16-byte aligned: four independent Philox chains per
-    // thread, each ending in one fully coalesced 512-byte-per-warp store
-    U32x4 o[kFillUnroll];
-#pragma unroll
-    for (int k = 0; k < kFillUnroll; ++k) {
-      const uint64_t g = group0 + static_cast<uint64_t>(k) * kFillThreads + threadIdx.x;
-      const U32x4 r = philox4x32<10>(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32),
-                                     s_lo, s_hi, k0, k1);
-      o[k] = fill_group(DT, r, p);
-    }
-#pragma unroll
-    for (int k = 0; k < kFillUnroll; ++k) {
-      const uint64_t g = group0 + static_cast<uint64_t>(k) * kFillThreads + threadIdx.x;
-      st_cs_v4(dst + g * 16, o[k]);
-    }
-    return;
+__device__ __forceinline__ void fill_span_random(uint8_t* __restrict__ dst, uint64_t nbytes,
+                                                 uint64_t g_first, uint32_t count, uint32_t full,
+                                                 const FillParams& p, uint32_t s_lo, uint32_t s_hi,
+                                                 const RoundKeys& rk) {
+  uint32_t i = threadIdx.x;
+  // two independent Philox chains per thread per iteration; every store instruction of a
+  // warp covers 512 contiguous bytes
+  for (; i + kFillThreads < full; i += 2 * kFillThreads) {
+    const uint64_t ga = g_first + i, gb = ga + kFillThreads;
+    const U32x4 ra = philox4x32_10_rk(static_cast<uint32_t>(ga), static_cast<uint32_t>(ga >> 32), s_lo, s_hi, rk);
+    const U32x4 rb = philox4x32_10_rk(static_cast<uint32_t>(gb), static_cast<uint32_t>(gb >> 32), s_lo, s_hi, rk);
+    const U32x4 oa = fill_group(DT, ra, p);
+    const U32x4 ob = fill_group(DT, rb, p);
+    st_cs_v4(dst + ga * 16, oa);
+    st_cs_v4(dst + gb * 16, ob);
   }
-  const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
-#pragma unroll 1
-  for (int k = 0; k < kFillUnroll; ++k) {
-    const uint64_t g = group0 + static_cast<uint64_t>(k) * kFillThreads + threadIdx.x;
-    const uint64_t off = g * 16;
-    if (off >= nbytes) continue;
-    const U32x4 r = philox4x32<10>(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32),
-                                   s_lo, s_hi, k0, k1);
+  for (; i < count; i += kFillThreads) {
+    const uint64_t g = g_first + i;
+    const U32x4 r = philox4x32_10_rk(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), s_lo, s_hi, rk);
     const U32x4 o = fill_group(DT, r, p);
-    const uint64_t left = nbytes - off;
-    if (left >= 16 && aligned) st_cs_v4(dst + off, o);
-    else store_bytes(dst + off, o, left >= 16 ? 16u : static_cast<uint32_t>(left));
+    if (i < full) {
+      st_cs_v4(dst + g * 16, o);
+    } else {
+      const uint64_t left = nbytes - g * 16;
+      store_bytes(dst + g * 16, o, left >= 16 ? 16u : static_cast<uint32_t>(left));
+    }
   }
 }
 
-__device__ __forceinline__ void fill_tile_const(uint8_t* __restrict__ dst, uint64_t nbytes,
-                                                uint64_t group0, uint32_t word) {
-  const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+__device__ __forceinline__ void fill_span_const(uint8_t* __restrict__ dst, uint64_t nbytes,
+                                                uint64_t g_first, uint32_t count, uint32_t full,
+                                                uint32_t word) {
   const U32x4 o{word, word, word, word};
-#pragma unroll
-  for (int k = 0; k < kFillUnroll; ++k) {
-    const uint64_t g = group0 + static_cast<uint64_t>(k) * kFillThreads + threadIdx.x;
-    const uint64_t off = g * 16;
-    if (off >= nbytes) continue;
-    const uint64_t left = nbytes - off;
-    if (left >= 16 && aligned) st_cs_v4(dst + off, o);
-    else store_bytes(dst + off, o, left >= 16 ? 16u : static_cast<uint32_t>(left));
+  for (uint32_t i = threadIdx.x; i < count; i += kFillThreads) {
+    const uint64_t g = g_first + i;
+    if (i < full) {
+      st_cs_v4(dst + g * 16, o);
+    } else {
+      const uint64_t left = nbytes - g * 16;
+      store_bytes(dst + g * 16, o, left >= 16 ? 16u : static_cast<uint32_t>(left));
+    }
   }
 }
 
 __global__ void __launch_bounds__(kFillThreads) fill_kernel(const FillLaunch L) {
-  const uint32_t k0 = static_cast<uint32_t>(L.seed);
-  const uint32_t k1 = static_cast<uint32_t>(L.seed >> 32);
   uint64_t epoch = L.epoch;
   if (L.dev_epoch != nullptr) epoch += *L.dev_epoch;
 
-  for (uint32_t tile = blockIdx.x; tile < L.total_tiles; tile += gridDim.x) {
-    uint32_t j, lt;
-    if (L.uniform_tiles != 0) {
-      j = tile / L.uniform_tiles;
-      lt = tile - j * L.uniform_tiles;
+  for (uint32_t span = blockIdx.x; span < L.total_spans; span += gridDim.x) {
+    uint32_t j, ls;
+    if (L.uniform_spans != 0) {
+      j = span / L.uniform_spans;
+      ls = span - j * L.uniform_spans;
     } else {
-      j = find_job(L.tile_prefix, L.njobs, tile);
-      lt = tile - __ldg(L.tile_prefix + j);
+      j = find_job(L.span_prefix, L.njobs, span);
+      ls = span - __ldg(L.span_prefix + j);
     }
     const tb200_fill_job jb = L.jobs[j];
     uint8_t* dst = reinterpret_cast<uint8_t*>(jb.dst);
-    const uint64_t group0 = static_cast<uint64_t>(lt) * (kFillThreads * kFillUnroll);
+    const uint64_t g_first = static_cast<uint64_t>(ls) * kFillSpanGroups;
+    const uint64_t bytes_left = jb.nbytes - g_first * 16;  // > 0 by construction of the span table
+    const uint64_t groups_left = (bytes_left + 15) / 16;
+    const uint32_t count = groups_left < kFillSpanGroups ? static_cast<uint32_t>(groups_left) : kFillSpanGroups;
+    uint32_t full = 0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      const uint64_t whole = bytes_left / 16;
+      full = whole < kFillSpanGroups ? static_cast<uint32_t>(whole) : kFillSpanGroups;
+    }
 
     if (jb.mode != TB200_FILL_RANDOM) {
       uint32_t word = 0;
       if (jb.mode == TB200_FILL_BYTE) word = (static_cast<uint32_t>(jb.ilo) & 0xFFu) * 0x01010101u;
-      fill_tile_const(dst, jb.nbytes, group0, word);
+      fill_span_const(dst, jb.nbytes, g_first, count, full, word);
       continue;
     }
     FillParams p;
@@ -145,32 +146,42 @@ __global__ void __launch_bounds__(kFillThreads) fill_kernel(const FillLaunch L) 
     const uint64_t stream = jb.stream + epoch;
     const uint32_t s_lo = static_cast<uint32_t>(stream);
     const uint32_t s_hi = static_cast<uint32_t>(stream >> 32);
-    const bool fast = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                      (group0 * 16 + kFillTileBytes <= jb.nbytes);
+#define TB200_FILL_CASE(DT) fill_span_random<DT>(dst, jb.nbytes, g_first, count, full, p, s_lo, s_hi, L.rk); break
     switch (jb.dtype) {
-      case kF32: fill_tile_random<kF32>(dst, jb.nbytes, group0, p, s_lo, s_hi, k0, k1, fast); break;
-      case kF16: fill_tile_random<kF16>(dst, jb.nbytes, group0, p, s_lo, s_hi, k0, k1, fast); break;
-      case kBF16: fill_tile_random<kBF16>(dst, jb.nbytes, group0, p, s_lo, s_hi, k0, k1, fast); break;
-      case kF64: fill_tile_random<kF64>(dst, jb.nbytes, group0, p, s_lo, s_hi, k0, k1, fast); break;
-      case kI64: case kU64:
-        fill_tile_random<kI64>(dst, jb.nbytes, group0, p, s_lo, s_hi, k0, k1, fast); break;
-      case kI32: case kU32:
-        fill_tile_random<kI32>(dst, jb.nbytes, group0, p, s_lo, s_hi, k0, k1, fast); break;
-      case kI16: case kU16:
-        fill_tile_random<kI16>(dst, jb.nbytes, group0, p, s_lo, s_hi, k0, k1, fast); break;
-      case kI8: case kU8:
-        fill_tile_random<kI8>(dst, jb.nbytes, group0, p, s_lo, s_hi, k0, k1, fast); break;
-      default:
-        fill_tile_random<kBool>(dst, jb.nbytes, group0, p, s_lo, s_hi, k0, k1, fast); break;
+      case kF32: TB200_FILL_CASE(kF32);
+      case kF16: TB200_FILL_CASE(kF16);
+      case kBF16: TB200_FILL_CASE(kBF16);
+      case kF64: TB200_FILL_CASE(kF64);
+      case kI64: case kU64: TB200_FILL_CASE(kI64);
+      case kI32: case kU32: TB200_FILL_CASE(kI32);
+      case kI16: case kU16: TB200_FILL_CASE(kI16);
+      case kI8: case kU8: TB200_FILL_CASE(kI8);
+      default: TB200_FILL_CASE(kBool);
     }
+#undef TB200_FILL_CASE
+  }
+
+  // graph replays: the last CTA to finish advances the device epoch, so the next replay
+  // generates fresh data without any host involvement (every CTA read the epoch above)
+  if (L.bump != 0 && threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicInc(L.done_counter, gridDim.x - 1);
+    if (prev == gridDim.x - 1) *L.dev_epoch += L.bump;
   }
 }
 
 cudaError_t launch_fill(const FillLaunch& l, int sm_count, cudaStream_t s) {
-  if (l.total_tiles == 0) return cudaSuccess;
-  // 8 resident CTAs of 256 threads fill an SM; the grid-stride loop covers the rest
-  uint32_t grid = static_cast<uint32_t>(sm_count) * 8u;
-  if (grid > l.total_tiles) grid = l.total_tiles;
+  if (l.total_spans == 0) return cudaSuccess;
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel, kFillThreads, 0) != cudaSuccess || n < 1) n = 4;
+    blocks_per_sm = n;
+  }
+  // all CTAs resident at once, every CTA the same number of spans (+-1)
+  const uint32_t max_grid = static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(blocks_per_sm);
+  const uint32_t rounds = (l.total_spans + max_grid - 1) / max_grid;
+  const uint32_t grid = (l.total_spans + rounds - 1) / rounds;
   fill_kernel<<<grid, kFillThreads, 0, s>>>(l);
   return cudaGetLastError();
 }
@@ -749,8 +760,8 @@ __global__ void __launch_bounds__(256) check_kernel(const CheckLaunch L) {
   const uint32_t j = blockIdx.y;
   const tb200_check_job jb = L.jobs[j];
   const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * kCheckChunkBytes;
-  if (begin >= jb.nbytes) return;
-  const uint64_t end = (begin + kCheckChunkBytes < jb.nbytes) ? begin + kCheckChunkBytes : jb.nbytes;
+  if (begin >= jb.nbytes && !(jb.nbytes == 0 && blockIdx.x == 0)) return;
+  const uint64_t end = (jb.nbytes == 0) ? begin : ((begin + kCheckChunkBytes < jb.nbytes) ? begin + kCheckChunkBytes : jb.nbytes);
   const uint8_t* a = reinterpret_cast<const uint8_t*>(jb.a);
   const uint8_t* b = reinterpret_cast<const uint8_t*>(jb.b);
   const uint8_t* c = reinterpret_cast<const uint8_t*>(jb.c);
@@ -792,7 +803,7 @@ __global__ void __launch_bounds__(256) check_kernel(const CheckLaunch L) {
     check_word(acc, kind, wa, wb, wc, wd, off / 4);
   }
 
-  // block reduction: warp shuffles, then one atomic per warp-leader via shared memory
+  // block reduction: warp shuffles, then the warp leaders through shared memory
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     acc.mism += __shfl_xor_sync(0xFFFFFFFFu, acc.mism, o);
@@ -808,38 +819,43 @@ __global__ void __launch_bounds__(256) check_kernel(const CheckLaunch L) {
     s_m[warp] = acc.mism; s_s[warp] = acc.sum; s_b[warp] = acc.best; s_x[warp] = acc.x;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long m = 0, sm = 0, bst = 0;
-    uint32_t x = 0;
+  if (threadIdx.x != 0) return;
+  unsigned long long m = 0, sm = 0, bst = 0;
+  uint32_t x = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      m += s_m[k]; sm += s_s[k]; x ^= s_x[k];
-      if (s_b[k] > bst) bst = s_b[k];
-    }
+  for (int k = 0; k < 8; ++k) {
+    m += s_m[k]; sm += s_s[k]; x ^= s_x[k];
+    if (s_b[k] > bst) bst = s_b[k];
+  }
+  const uint32_t nchunks = static_cast<uint32_t>((jb.nbytes + kCheckChunkBytes - 1) / kCheckChunkBytes);
+  if (nchunks > 1) {
+    // several CTAs share the job: combine through the accumulator, the last one finalizes
+    // and leaves the accumulator zeroed for the next launch
     CheckAccum* ac = L.accum + j;
     if (m) atomicAdd(&ac->mismatches, m);
     atomicAdd(&ac->sum, sm);
     atomicXor(&ac->xor32, x);
     if (bst) atomicMax(&ac->best, bst);
+    __threadfence();
+    if (atomicInc(&ac->done, nchunks - 1) != nchunks - 1) return;
+    __threadfence();
+    m = atomicExch(&ac->mismatches, 0ull);
+    sm = atomicExch(&ac->sum, 0ull);
+    bst = atomicExch(&ac->best, 0ull);
+    x = atomicExch(&ac->xor32, 0u);
   }
-}
-
-__global__ void check_finalize_kernel(const CheckLaunch L) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= L.njobs) return;
-  const CheckAccum ac = L.accum[j];
   tb200_check_result r;
-  r.mismatches = ac.mismatches;
-  r.sum = ac.sum;
-  r.xor32 = ac.xor32;
+  r.mismatches = m;
+  r.sum = sm;
+  r.xor32 = x;
   r.pad = 0;
-  if (ac.best == 0) {
+  if (bst == 0) {
     r.argmax = 0xFFFFFFFFu;
     r.max_value = 0.0f;
   } else {
-    const uint32_t key = static_cast<uint32_t>(ac.best >> 32);
+    const uint32_t key = static_cast<uint32_t>(bst >> 32);
     const uint32_t bits = (key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key;
-    r.argmax = 0xFFFFFFFFu - static_cast<uint32_t>(ac.best & 0xFFFFFFFFull);
+    r.argmax = 0xFFFFFFFFu - static_cast<uint32_t>(bst & 0xFFFFFFFFull);
     r.max_value = bits_f32(bits);
   }
   L.results[j] = r;
@@ -850,9 +866,6 @@ cudaError_t launch_check(const CheckLaunch& l, cudaStream_t s) {
   if (l.njobs == 0) return cudaSuccess;
   dim3 grid(l.max_chunks == 0 ? 1 : l.max_chunks, l.njobs);
   check_kernel<<<grid, 256, 0, s>>>(l);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  check_finalize_kernel<<<(l.njobs + 127) / 128, 128, 0, s>>>(l);
   return cudaGetLastError();
 }
 

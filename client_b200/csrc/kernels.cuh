@@ -6,23 +6,27 @@
 #include <stdint.h>
 
 #include "../../include/tb200.h"
+#include "philox.cuh"
 
 namespace tb200 {
 
 // ---- fill ---------------------------------------------------------------------
 constexpr int kFillThreads = 256;
-constexpr int kFillUnroll = 4;                                    // groups per thread per tile
-constexpr uint32_t kFillTileBytes = kFillThreads * kFillUnroll * 16;  // 16 KiB
+constexpr uint32_t kFillSpanGroups = 2048;                     // 16-byte groups per span
+constexpr uint32_t kFillSpanBytes = kFillSpanGroups * 16;      // 32 KiB: unit of work of one CTA
 
 struct FillLaunch {
   const tb200_fill_job* jobs;   // device
-  const uint32_t* tile_prefix;  // device, njobs+1 entries; unused when uniform
-  const uint64_t* dev_epoch;    // device or nullptr
+  const uint32_t* span_prefix;  // device, njobs+1 entries; unused when uniform
+  uint64_t* dev_epoch;          // device or nullptr: added to every stream id
+  unsigned int* done_counter;   // device: CTAs finished (wraps), used when bump != 0
   uint64_t seed;
   uint64_t epoch;
+  uint64_t bump;                // != 0: the last CTA adds this to *dev_epoch
   uint32_t njobs;
-  uint32_t total_tiles;
-  uint32_t uniform_tiles;       // >0: every job has exactly this many tiles
+  uint32_t total_spans;
+  uint32_t uniform_spans;       // >0: every job has exactly this many spans
+  RoundKeys rk;                 // Philox key schedule of `seed`
 };
 cudaError_t launch_fill(const FillLaunch& l, int sm_count, cudaStream_t s);
 
@@ -65,12 +69,12 @@ struct CopyLaunch {
 cudaError_t launch_concat(const CopyLaunch& l, int sm_count, cudaStream_t s);
 
 // ---- check ----------------------------------------------------------------------
-struct CheckAccum {  // device scratch, one per job, zeroed before the launch
+struct CheckAccum {  // device scratch, one per job; all-zero between launches (self-cleaning)
   unsigned long long mismatches;
   unsigned long long sum;
   unsigned long long best;  // (orderable fp32 key << 32) | (0xFFFFFFFF - index)
   unsigned int xor32;
-  unsigned int pad;
+  unsigned int done;        // chunks of the job finished so far (wraps to 0)
 };
 constexpr uint32_t kCheckChunkBytes = 1u << 20;  // one CTA per MiB of a job
 struct CheckLaunch {

@@ -50,6 +50,37 @@ TB200_HD U32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
   return U32x4{c0, c1, c2, c3};
 }
 
+// Same block function with the key schedule precomputed (rk[2r], rk[2r+1] are the
+// round-r keys).  The kernel passes rk in the launch parameters so every xor3 takes
+// its key from the constant bank and the 18 per-call key additions disappear.
+struct RoundKeys {
+  uint32_t k[20];
+};
+inline void make_round_keys(uint64_t seed, RoundKeys* out) {
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    out->k[2 * r] = k0;
+    out->k[2 * r + 1] = k1;
+    k0 += kPhiloxW0;
+    k1 += kPhiloxW1;
+  }
+}
+TB200_HD U32x4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                const RoundKeys& rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(kPhiloxM0) * c0;
+    const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ rk.k[2 * r];
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ rk.k[2 * r + 1];
+    c1 = static_cast<uint32_t>(p1);
+    c3 = static_cast<uint32_t>(p0);
+    c0 = n0;
+    c2 = n2;
+  }
+  return U32x4{c0, c1, c2, c3};
+}
+
 // ---- float <-> bit helpers that behave identically on host and device ------
 TB200_HD uint32_t f32_bits(float f) {
 #if defined(__CUDA_ARCH__)
@@ -194,18 +225,33 @@ struct FillParams {
   uint32_t unit;    // 1 -> floats are the unit interval, skip the fma
 };
 
-TB200_HD float unit_f32(uint32_t w) {  // 24-bit uniform in [0,1)
-  return static_cast<float>(w >> 8) * 5.9604644775390625e-8f;  // 2^-24
+// Uniform values in [0,1) by mantissa insertion: the top mantissa-width bits of the
+// random field become the fraction of a float in [1,2), then 1 is subtracted (exact).
+//   fp32: (w   >> 9 ) * 2^-23      fp16: (x16 >> 6) * 2^-10
+//   bf16: (x16 >> 9 ) * 2^-7       fp64: (x64 >> 12) * 2^-52
+// One shift/or + one add per value and no I2F conversions (those run on a slow pipe).
+TB200_HD float unit_f32(uint32_t w) {
+  return bits_f32(0x3F800000u | (w >> 9)) - 1.0f;
 }
-TB200_HD float unit_f16(uint32_t x16) {  // 11-bit uniform in [0,1), exact in fp16
-  return static_cast<float>(x16 >> 5) * 4.8828125e-4f;  // 2^-11
+TB200_HD float unit_f16(uint32_t x16) {  // 10 random bits, exactly representable in fp16
+  return bits_f32(0x3F800000u | ((x16 >> 6) << 13)) - 1.0f;
 }
-TB200_HD float unit_bf16(uint32_t x16) {  // 8-bit uniform in [0,1), exact in bf16
-  return static_cast<float>(x16 >> 8) * 3.90625e-3f;  // 2^-8
+TB200_HD float unit_bf16(uint32_t x16) {  // 7 random bits, exactly representable in bf16
+  return bits_f32(0x3F800000u | ((x16 >> 9) << 16)) - 1.0f;
 }
-TB200_HD double unit_f64(uint32_t lo, uint32_t hi) {  // 53-bit uniform in [0,1)
-  const uint64_t m = (static_cast<uint64_t>(hi >> 5) << 26) | (lo >> 6);
-  return static_cast<double>(m) * 1.1102230246251565e-16;  // 2^-53
+TB200_HD double unit_f64(uint32_t lo, uint32_t hi) {  // 52 random bits
+  const uint64_t x = (static_cast<uint64_t>(hi) << 32) | lo;
+  const uint64_t bits = 0x3FF0000000000000ull | (x >> 12);
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(static_cast<long long>(bits)) - 1.0;
+#else
+  union {
+    uint64_t u;
+    double d;
+  } v;
+  v.u = bits;
+  return v.d - 1.0;
+#endif
 }
 
 TB200_HD uint32_t fill_word_f32(uint32_t w, const FillParams& p) {
@@ -214,12 +260,20 @@ TB200_HD uint32_t fill_word_f32(uint32_t w, const FillParams& p) {
   return f32_bits(u);
 }
 TB200_HD uint32_t fill_word_f16(uint32_t w, const FillParams& p) {
-  float a = unit_f16(w & 0xFFFFu);
-  float b = unit_f16(w >> 16);
-  if (!p.unit) {
-    a = fma_f32(a, p.span_f, p.lo_f);
-    b = fma_f32(b, p.span_f, p.lo_f);
+  if (p.unit) {
+    // both halves at once: 0x3C00 | (x16 >> 6) is a half in [1,2); minus 1 is exact
+    const uint32_t one_plus = 0x3C003C00u | ((w >> 6) & 0x03FF03FFu);
+#if defined(__CUDA_ARCH__)
+    const __half2 v = __hsub2(*reinterpret_cast<const __half2*>(&one_plus), __float2half2_rn(1.0f));
+    return *reinterpret_cast<const uint32_t*>(&v);
+#else
+    const float a = f16_bits_to_f32(static_cast<uint16_t>(one_plus & 0xFFFFu)) - 1.0f;
+    const float b = f16_bits_to_f32(static_cast<uint16_t>(one_plus >> 16)) - 1.0f;
+    return static_cast<uint32_t>(f32_to_f16_bits(a)) | (static_cast<uint32_t>(f32_to_f16_bits(b)) << 16);
+#endif
   }
+  const float a = fma_f32(unit_f16(w & 0xFFFFu), p.span_f, p.lo_f);
+  const float b = fma_f32(unit_f16(w >> 16), p.span_f, p.lo_f);
   return static_cast<uint32_t>(f32_to_f16_bits(a)) |
          (static_cast<uint32_t>(f32_to_f16_bits(b)) << 16);
 }

@@ -165,7 +165,10 @@ struct tb200_graph {
 struct tb200_ctx {
   int device = 0;
   int sm_count = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // main stream
+  cudaStream_t cur = nullptr;      // stream launches go to (main, or side between fork/join)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool own_stream = true;
   uint64_t launches = 0;
   // pinned staging ring for host <-> region copies
@@ -182,7 +185,7 @@ struct tb200_ctx {
   tb200::CheckAccum* accum = nullptr;
   uint32_t accum_cap = 0;
   // epoch + flush scratch
-  uint64_t* dev_epoch = nullptr;
+  uint64_t* dev_epoch = nullptr;       // [0] epoch, [1] CTA-done counter of the fill kernel
   void* flush_buf = nullptr;
   // capture state
   tb200_graph* capture = nullptr;
@@ -251,8 +254,8 @@ int upload(tb200_ctx* ctx, const void* host, size_t bytes, const void** dev_out)
   char* h = ctx->job_host + slot * kJobSlotBytes;
   char* d = ctx->job_dev + slot * kJobSlotBytes;
   memcpy(h, host, bytes);
-  TB200_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  TB200_CUDA(cudaEventRecord(ctx->job_ev[slot], ctx->stream));
+  TB200_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->cur));
+  TB200_CUDA(cudaEventRecord(ctx->job_ev[slot], ctx->cur));
   ctx->job_ev_valid[slot] = true;
   *dev_out = d;
   return TB200_OK;
@@ -278,8 +281,8 @@ int staged_h2d(tb200_ctx* ctx, char* dst, const char* src, uint64_t nbytes) {
     ctx->stage_next = (b + 1) % kStageCount;
     TB200_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));  // buffer free again?
     CopyPool::instance().parallel_memcpy(ctx->stage[b], src + done, n);
-    TB200_CUDA(cudaMemcpyAsync(dst + done, ctx->stage[b], n, cudaMemcpyHostToDevice, ctx->stream));
-    TB200_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+    TB200_CUDA(cudaMemcpyAsync(dst + done, ctx->stage[b], n, cudaMemcpyHostToDevice, ctx->cur));
+    TB200_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->cur));
     done += n;
   }
   return TB200_OK;
@@ -345,13 +348,14 @@ int tb200_ctx_create(int device_id, tb200_ctx** out) {
   cudaError_t e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   void* ep = nullptr;
-  if (e == cudaSuccess) e = cudaMalloc(&ep, sizeof(uint64_t));
-  if (e == cudaSuccess) e = cudaMemset(ep, 0, sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&ep, 2 * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMemset(ep, 0, 2 * sizeof(uint64_t));
   if (e != cudaSuccess) {
     delete ctx;
     return fail(TB200_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
   }
   ctx->dev_epoch = static_cast<uint64_t*>(ep);
+  ctx->cur = ctx->stream;
   *out = ctx;
   return TB200_OK;
 }
@@ -372,6 +376,9 @@ int tb200_ctx_destroy(tb200_ctx* ctx) {
   if (ctx->accum) cudaFree(ctx->accum);
   if (ctx->dev_epoch) cudaFree(ctx->dev_epoch);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return TB200_OK;
@@ -383,6 +390,7 @@ int tb200_ctx_set_stream(tb200_ctx* ctx, void* cuda_stream) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->cur = ctx->stream;
   ctx->own_stream = false;
   return TB200_OK;
 }
@@ -395,6 +403,34 @@ int tb200_ctx_sync(tb200_ctx* ctx) {
   if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
   DeviceGuard g(ctx->device);
   TB200_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->side != nullptr && ctx->capture == nullptr) TB200_CUDA(cudaStreamSynchronize(ctx->side));
+  return TB200_OK;
+}
+
+// fork: later launches go to a side stream that starts after everything issued so far;
+// join: the main stream waits for the side stream.  Works eagerly and inside a graph
+// capture (it becomes a parallel branch of the graph).
+int tb200_ctx_fork(tb200_ctx* ctx) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  if (ctx->cur != ctx->stream) return fail(TB200_ERR_STATE, "already forked");
+  DeviceGuard g(ctx->device);
+  if (ctx->side == nullptr) {
+    TB200_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    TB200_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    TB200_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  TB200_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  TB200_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  ctx->cur = ctx->side;
+  return TB200_OK;
+}
+int tb200_ctx_join(tb200_ctx* ctx) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  if (ctx->cur == ctx->stream) return fail(TB200_ERR_STATE, "not forked");
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  TB200_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  ctx->cur = ctx->stream;
   return TB200_OK;
 }
 
@@ -527,7 +563,7 @@ int tb200_region_write_host_gather(tb200_ctx* ctx, tb200_region* r, uint64_t off
     if (rc != TB200_OK) return rc;
     dst += sizes[i];
   }
-  TB200_CUDA(cudaStreamSynchronize(ctx->stream));
+  TB200_CUDA(cudaStreamSynchronize(ctx->cur));
   return TB200_OK;
 }
 
@@ -559,8 +595,8 @@ int tb200_region_read_host(tb200_ctx* ctx, const tb200_region* r, uint64_t offse
       const int b = ctx->stage_next;
       ctx->stage_next = (b + 1) % kStageCount;
       TB200_CUDA(cudaEventSynchronize(ctx->stage_ev[b]));
-      TB200_CUDA(cudaMemcpyAsync(ctx->stage[b], src + issued, n, cudaMemcpyDeviceToHost, ctx->stream));
-      TB200_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+      TB200_CUDA(cudaMemcpyAsync(ctx->stage[b], src + issued, n, cudaMemcpyDeviceToHost, ctx->cur));
+      TB200_CUDA(cudaEventRecord(ctx->stage_ev[b], ctx->cur));
       qb[(qhead + qlen) % kStageCount] = b;
       qn[(qhead + qlen) % kStageCount] = n;
       ++qlen;
@@ -583,8 +619,8 @@ int tb200_region_write_ptr(tb200_ctx* ctx, tb200_region* r, uint64_t offset, con
   if (rc != TB200_OK) return rc;
   if (nbytes == 0) return TB200_OK;
   DeviceGuard g(ctx->device);
-  TB200_CUDA(cudaMemcpyAsync(static_cast<char*>(r->base) + offset, src, nbytes, cudaMemcpyDefault, ctx->stream));
-  TB200_CUDA(cudaStreamSynchronize(ctx->stream));
+  TB200_CUDA(cudaMemcpyAsync(static_cast<char*>(r->base) + offset, src, nbytes, cudaMemcpyDefault, ctx->cur));
+  TB200_CUDA(cudaStreamSynchronize(ctx->cur));
   return TB200_OK;
 }
 
@@ -625,13 +661,13 @@ int tb200_device_free(int device_id, void* device_ptr) {
 int tb200_memcpy_h2d_async(tb200_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
   if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
   DeviceGuard g(ctx->device);
-  TB200_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  TB200_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->cur));
   return TB200_OK;
 }
 int tb200_memcpy_d2h_async(tb200_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
   if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
   DeviceGuard g(ctx->device);
-  TB200_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TB200_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->cur));
   return TB200_OK;
 }
 
@@ -639,13 +675,16 @@ int tb200_memcpy_d2h_async(tb200_ctx* ctx, void* dst, const void* src, uint64_t 
 // fill
 // ---------------------------------------------------------------------------
 static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint64_t seed,
-                     uint64_t epoch, bool use_dev_epoch) {
+                     uint64_t epoch, bool use_dev_epoch, uint64_t bump) {
   if (ctx == nullptr || njobs < 0 || (njobs > 0 && jobs == nullptr)) return fail(TB200_ERR_INVALID, "bad argument");
   if (njobs == 0) return TB200_OK;
   DeviceGuard g(ctx->device);
-  const int max_jobs = static_cast<int>(kJobSlotBytes / sizeof(tb200_fill_job)) / 2;  // jobs + prefix share a slot
+  const int max_jobs = static_cast<int>(kJobSlotBytes / (sizeof(tb200_fill_job) + sizeof(uint32_t))) - 1;
+  RoundKeys rk;
+  make_round_keys(seed, &rk);
   for (int base = 0; base < njobs; base += max_jobs) {
     const int n = std::min(max_jobs, njobs - base);
+    const bool last = base + n >= njobs;
     std::vector<uint32_t> prefix(n + 1, 0);
     bool uniform = true;
     uint64_t total = 0;
@@ -664,13 +703,13 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
                       static_cast<unsigned long long>(jb.irange), es);
         }
       }
-      const uint64_t tiles = (jb.nbytes + kFillTileBytes - 1) / kFillTileBytes;
-      total += tiles;
+      const uint64_t spans = (jb.nbytes + kFillSpanBytes - 1) / kFillSpanBytes;
+      total += spans;
       if (total > 0xFFFFFFF0ull) return fail(TB200_ERR_INVALID, "fill launch too large");
       prefix[i + 1] = static_cast<uint32_t>(total);
-      if (tiles != (jobs[base].nbytes + kFillTileBytes - 1) / kFillTileBytes) uniform = false;
+      if (spans != (jobs[base].nbytes + kFillSpanBytes - 1) / kFillSpanBytes) uniform = false;
     }
-    if (total == 0) continue;
+    if (total == 0 && !(last && bump != 0)) continue;
     // one upload: [jobs | prefix]
     const size_t jbytes = sizeof(tb200_fill_job) * n;
     const size_t pbytes = sizeof(uint32_t) * (n + 1);
@@ -682,24 +721,31 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
     if (rc != TB200_OK) return rc;
     FillLaunch L;
     L.jobs = static_cast<const tb200_fill_job*>(dev);
-    L.tile_prefix = reinterpret_cast<const uint32_t*>(static_cast<const char*>(dev) + jbytes);
+    L.span_prefix = reinterpret_cast<const uint32_t*>(static_cast<const char*>(dev) + jbytes);
     L.dev_epoch = use_dev_epoch ? ctx->dev_epoch : nullptr;
+    L.done_counter = reinterpret_cast<unsigned int*>(ctx->dev_epoch + 1);
     L.seed = seed;
     L.epoch = epoch;
+    L.bump = (last && use_dev_epoch) ? bump : 0;
     L.njobs = static_cast<uint32_t>(n);
-    L.total_tiles = static_cast<uint32_t>(total);
-    L.uniform_tiles = uniform ? prefix[1] : 0;
-    TB200_CUDA(launch_fill(L, ctx->sm_count, ctx->stream));
+    L.total_spans = static_cast<uint32_t>(total);
+    L.uniform_spans = uniform ? prefix[1] : 0;
+    L.rk = rk;
+    if (total == 0) {  // nothing to write but the epoch must still advance
+      TB200_CUDA(launch_epoch_bump(ctx->dev_epoch, bump, ctx->cur));
+    } else {
+      TB200_CUDA(launch_fill(L, ctx->sm_count, ctx->cur));
+    }
     ctx->launches += 1;
   }
   return TB200_OK;
 }
 
 int tb200_fill_async(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint64_t seed, uint64_t stream_epoch) {
-  return fill_impl(ctx, jobs, njobs, seed, stream_epoch, false);
+  return fill_impl(ctx, jobs, njobs, seed, stream_epoch, false, 0);
 }
-int tb200_fill_epoch_async(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint64_t seed) {
-  return fill_impl(ctx, jobs, njobs, seed, 0, true);
+int tb200_fill_epoch_async(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint64_t seed, uint64_t bump) {
+  return fill_impl(ctx, jobs, njobs, seed, 0, true, bump);
 }
 
 int tb200_ctx_epoch_set(tb200_ctx* ctx, uint64_t value) {
@@ -712,7 +758,7 @@ int tb200_ctx_epoch_set(tb200_ctx* ctx, uint64_t value) {
 int tb200_ctx_epoch_bump_async(tb200_ctx* ctx, uint64_t delta) {
   if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
   DeviceGuard g(ctx->device);
-  TB200_CUDA(launch_epoch_bump(ctx->dev_epoch, delta, ctx->stream));
+  TB200_CUDA(launch_epoch_bump(ctx->dev_epoch, delta, ctx->cur));
   ctx->launches += 1;
   return TB200_OK;
 }
@@ -733,7 +779,7 @@ int tb200_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype, uint32
   p.scaling = scaling;
   p.n = n; p.h = h; p.w = w; p.c = c;
   int launches = 0;
-  cudaError_t e = launch_pack_image(p, ctx->sm_count, ctx->stream, &launches);
+  cudaError_t e = launch_pack_image(p, ctx->sm_count, ctx->cur, &launches);
   if (e == cudaErrorInvalidValue) {
     return fail(TB200_ERR_INVALID, "pack_image: unsupported combination (dtype %u, n=%d h=%d w=%d c=%d, scaling %u)",
                 dst_dtype, n, h, w, c, scaling);
@@ -751,7 +797,7 @@ int tb200_cast_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype, const void* 
     return fail(TB200_ERR_INVALID, "cast %s -> %s is not supported", tb200_dtype_name(src_dtype), tb200_dtype_name(dst_dtype));
   }
   DeviceGuard g(ctx->device);
-  TB200_CUDA(launch_cast(dst, dst_dtype, src, src_dtype, nelem, ctx->sm_count, ctx->stream));
+  TB200_CUDA(launch_cast(dst, dst_dtype, src, src_dtype, nelem, ctx->sm_count, ctx->cur));
   ctx->launches += 1;
   return TB200_OK;
 }
@@ -778,7 +824,7 @@ int tb200_pack_strided_async(tb200_ctx* ctx, void* dst, const void* src, uint32_
   if (p.nelem == 0) return TB200_OK;
   if (dst == nullptr || src == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
   DeviceGuard g(ctx->device);
-  TB200_CUDA(launch_pack_strided(p, ctx->sm_count, ctx->stream));
+  TB200_CUDA(launch_pack_strided(p, ctx->sm_count, ctx->cur));
   ctx->launches += 1;
   return TB200_OK;
 }
@@ -813,7 +859,7 @@ int tb200_concat_async(tb200_ctx* ctx, const tb200_copy_job* jobs, int njobs) {
     L.tile_prefix = reinterpret_cast<const uint32_t*>(static_cast<const char*>(dev) + jbytes);
     L.njobs = static_cast<uint32_t>(n);
     L.total_tiles = static_cast<uint32_t>(total);
-    TB200_CUDA(launch_concat(L, ctx->sm_count, ctx->stream));
+    TB200_CUDA(launch_concat(L, ctx->sm_count, ctx->cur));
     ctx->launches += 1;
   }
   return TB200_OK;
@@ -828,13 +874,14 @@ int tb200_check_async(tb200_ctx* ctx, const tb200_check_job* jobs, int njobs, tb
   DeviceGuard g(ctx->device);
   const int max_jobs = std::min<int>(static_cast<int>(kJobSlotBytes / sizeof(tb200_check_job)), 65535);
   if (ctx->capture == nullptr && ctx->accum_cap < static_cast<uint32_t>(std::min(njobs, max_jobs))) {
-    TB200_CUDA(cudaStreamSynchronize(ctx->stream));
+    TB200_CUDA(cudaStreamSynchronize(ctx->cur));
     if (ctx->accum) cudaFree(ctx->accum);
     ctx->accum = nullptr;
     ctx->accum_cap = 0;
     const uint32_t cap = std::max<uint32_t>(1024, static_cast<uint32_t>(std::min(njobs, max_jobs)));
     void* p = nullptr;
     TB200_CUDA(cudaMalloc(&p, sizeof(CheckAccum) * cap));
+    TB200_CUDA(cudaMemset(p, 0, sizeof(CheckAccum) * cap));  // kept zero by the kernel itself
     ctx->accum = static_cast<CheckAccum*>(p);
     ctx->accum_cap = cap;
   }
@@ -857,10 +904,10 @@ int tb200_check_async(tb200_ctx* ctx, const tb200_check_job* jobs, int njobs, tb
     if (ctx->capture != nullptr) {  // graph-owned scratch
       void* p = nullptr;
       TB200_CUDA(cudaMalloc(&p, sizeof(CheckAccum) * n));
+      TB200_CUDA(cudaMemset(p, 0, sizeof(CheckAccum) * n));
       ctx->capture->device_allocs.push_back(p);
       accum = static_cast<CheckAccum*>(p);
     }
-    TB200_CUDA(cudaMemsetAsync(accum, 0, sizeof(CheckAccum) * n, ctx->stream));
     CheckLaunch L;
     L.jobs = static_cast<const tb200_check_job*>(dev);
     L.accum = accum;
@@ -868,8 +915,8 @@ int tb200_check_async(tb200_ctx* ctx, const tb200_check_job* jobs, int njobs, tb
     L.njobs = static_cast<uint32_t>(n);
     L.max_chunks = static_cast<uint32_t>((max_bytes + kCheckChunkBytes - 1) / kCheckChunkBytes);
     if (L.max_chunks > 65535u * 32u) return fail(TB200_ERR_INVALID, "check job too large");
-    TB200_CUDA(launch_check(L, ctx->stream));
-    ctx->launches += 2;
+    TB200_CUDA(launch_check(L, ctx->cur));
+    ctx->launches += 1;
   }
   return TB200_OK;
 }
@@ -880,6 +927,7 @@ int tb200_check_async(tb200_ctx* ctx, const tb200_check_job* jobs, int njobs, tb
 int tb200_graph_begin(tb200_ctx* ctx) {
   if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
   if (ctx->capture != nullptr) return fail(TB200_ERR_STATE, "capture already in progress");
+  if (ctx->cur != ctx->stream) return fail(TB200_ERR_STATE, "join the side stream before capturing");
   DeviceGuard g(ctx->device);
   TB200_CUDA(cudaStreamSynchronize(ctx->stream));
   tb200_graph* gr = new tb200_graph();
@@ -897,6 +945,7 @@ int tb200_graph_begin(tb200_ctx* ctx) {
 int tb200_graph_end(tb200_ctx* ctx, tb200_graph** out) {
   if (ctx == nullptr || out == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
   if (ctx->capture == nullptr) return fail(TB200_ERR_STATE, "no capture in progress");
+  if (ctx->cur != ctx->stream) return fail(TB200_ERR_STATE, "join the side stream before ending the capture");
   DeviceGuard g(ctx->device);
   tb200_graph* gr = ctx->capture;
   ctx->capture = nullptr;
@@ -934,7 +983,7 @@ int tb200_l2_flush_async(tb200_ctx* ctx) {
   if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
   DeviceGuard g(ctx->device);
   if (ctx->flush_buf == nullptr) TB200_CUDA(cudaMalloc(&ctx->flush_buf, kFlushBytes));
-  TB200_CUDA(cudaMemsetAsync(ctx->flush_buf, 0, kFlushBytes, ctx->stream));
+  TB200_CUDA(cudaMemsetAsync(ctx->flush_buf, 0, kFlushBytes, ctx->cur));
   return TB200_OK;
 }
 

@@ -198,9 +198,18 @@ class DeviceOps:
         arr, n = self.job_array(jobs, FillJob)
         _native.check(self._lib.tb200_fill_async(self._ctx.handle, arr, n, int(seed), int(epoch)))
 
-    def fill_epoch(self, jobs, seed=0):
+    def fill_epoch(self, jobs, seed=0, bump=0):
+        """Fill with the device epoch added to every stream id; ``bump`` advances the
+        epoch inside the same kernel (graph replays then never repeat data)."""
         arr, n = self.job_array(jobs, FillJob)
-        _native.check(self._lib.tb200_fill_epoch_async(self._ctx.handle, arr, n, int(seed)))
+        _native.check(self._lib.tb200_fill_epoch_async(self._ctx.handle, arr, n, int(seed), int(bump)))
+
+    def fork(self):
+        """Later launches run on a side stream, concurrently with the main stream."""
+        _native.check(self._lib.tb200_ctx_fork(self._ctx.handle))
+
+    def join(self):
+        _native.check(self._lib.tb200_ctx_join(self._ctx.handle))
 
     def epoch_set(self, value):
         _native.check(self._lib.tb200_ctx_epoch_set(self._ctx.handle, int(value)))

@@ -89,6 +89,11 @@ int tb200_ctx_set_stream(tb200_ctx* ctx, void* cuda_stream);
 void* tb200_ctx_stream(tb200_ctx* ctx);
 int tb200_ctx_device(tb200_ctx* ctx);
 int tb200_ctx_sync(tb200_ctx* ctx);
+/* fork: subsequent launches go to a side stream ordered after everything issued so
+ * far; join: the main stream waits for it.  Inside a graph capture this builds two
+ * parallel branches (e.g. fill the inputs while the outputs are validated). */
+int tb200_ctx_fork(tb200_ctx* ctx);
+int tb200_ctx_join(tb200_ctx* ctx);
 /* kernels launched by this context since creation (bench.py gpu_launches) */
 uint64_t tb200_ctx_launch_count(tb200_ctx* ctx);
 int tb200_ctx_sm_count(tb200_ctx* ctx);
@@ -297,9 +302,11 @@ int tb200_graph_destroy(tb200_graph* g);
 /* device-resident epoch counter added to Philox stream ids inside graphs */
 int tb200_ctx_epoch_set(tb200_ctx* ctx, uint64_t value);
 int tb200_ctx_epoch_bump_async(tb200_ctx* ctx, uint64_t delta);
-/* fill variant that reads the context's device epoch (graph friendly) */
+/* fill variant that adds the context's device epoch to every stream id (graph
+ * friendly); when bump != 0 the kernel itself advances the device epoch by `bump`
+ * after its last CTA finished, so each replay produces fresh data */
 int tb200_fill_epoch_async(tb200_ctx* ctx, const tb200_fill_job* jobs,
-                           int njobs, uint64_t seed);
+                           int njobs, uint64_t seed, uint64_t bump);
 
 /* write > L2-size bytes so the next timed kernel starts with a cold L2 */
 int tb200_l2_flush_async(tb200_ctx* ctx);

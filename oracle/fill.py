@@ -56,16 +56,16 @@ def fill_bytes(nbytes, datatype, seed=0, stream=0, lo=0.0, span=0.0, ilo=0, iran
     w = group_words(ngroups, seed, stream)  # [G,4] uint32
     unit = span == 0.0
     if datatype == "FP32":
-        u = (w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+        u = (w >> np.uint32(9)).astype(np.float32) * np.float32(2.0 ** -23)
         if not unit:
             u = _fma32(u, span, lo)
         raw = u.astype("<f4").tobytes()
     elif datatype in ("FP16", "BF16"):
         x16 = np.stack([w & np.uint32(0xFFFF), w >> np.uint32(16)], axis=2).reshape(ngroups, 8)
         if datatype == "FP16":
-            u = (x16 >> np.uint32(5)).astype(np.float32) * np.float32(2.0 ** -11)
+            u = (x16 >> np.uint32(6)).astype(np.float32) * np.float32(2.0 ** -10)
         else:
-            u = (x16 >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -8)
+            u = (x16 >> np.uint32(9)).astype(np.float32) * np.float32(2.0 ** -7)
         if not unit:
             u = _fma32(u, span, lo)
         if datatype == "FP16":
@@ -75,8 +75,8 @@ def fill_bytes(nbytes, datatype, seed=0, stream=0, lo=0.0, span=0.0, ilo=0, iran
     elif datatype == "FP64":
         lo_w = w[:, 0::2].astype(np.uint64)
         hi_w = w[:, 1::2].astype(np.uint64)
-        m = ((hi_w >> np.uint64(5)) << np.uint64(26)) | (lo_w >> np.uint64(6))
-        u = m.astype(np.float64) * (2.0 ** -53)
+        m = ((hi_w << np.uint64(32)) | lo_w) >> np.uint64(12)
+        u = m.astype(np.float64) * (2.0 ** -52)
         if not unit:
             u = u * span + lo  # callers compare with a 1-ulp tolerance
         raw = u.astype("<f8").tobytes()

@@ -72,7 +72,7 @@ static void group_bytes(uint32_t dtype, const uint32_t w[4], double lo, double s
   switch (dtype) {
     case DT_F32:
       for (int i = 0; i < 4; ++i) {
-        float u = (float)(w[i] >> 8) * 0x1p-24f;
+        float u = (float)(w[i] >> 9) * 0x1p-23f; /* 23 random bits */
         if (!unit) u = fmaf(u, span_f, lo_f);
         memcpy(out + 4 * i, &u, 4);
       }
@@ -81,7 +81,7 @@ static void group_bytes(uint32_t dtype, const uint32_t w[4], double lo, double s
     case DT_BF16:
       for (int i = 0; i < 8; ++i) {
         uint32_t x16 = (w[i / 2] >> (16 * (i & 1))) & 0xFFFFu;
-        float u = (dtype == DT_F16) ? (float)(x16 >> 5) * 0x1p-11f : (float)(x16 >> 8) * 0x1p-8f;
+        float u = (dtype == DT_F16) ? (float)(x16 >> 6) * 0x1p-10f : (float)(x16 >> 9) * 0x1p-7f;
         if (!unit) u = fmaf(u, span_f, lo_f);
         uint16_t b = (dtype == DT_F16) ? half_bits(u) : (uint16_t)(float_bits(u) >> 16);
         memcpy(out + 2 * i, &b, 2);
@@ -89,8 +89,8 @@ static void group_bytes(uint32_t dtype, const uint32_t w[4], double lo, double s
       break;
     case DT_F64:
       for (int i = 0; i < 2; ++i) {
-        uint64_t m = ((uint64_t)(w[2 * i + 1] >> 5) << 26) | (w[2 * i] >> 6);
-        double u = (double)m * 0x1p-53;
+        uint64_t x = ((uint64_t)w[2 * i + 1] << 32) | w[2 * i];
+        double u = (double)(x >> 12) * 0x1p-52; /* 52 random bits */
         if (!unit) u = fma(u, span, lo);
         memcpy(out + 8 * i, &u, 8);
       }

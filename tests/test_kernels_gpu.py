@@ -46,7 +46,7 @@ def _oracle_kwargs(dt, low, high):
 @pytest.mark.parametrize("nbytes", [0, 1, 15, 16, 17, 4096, 16384, 16400, 602112 + 7, 3 * 16384])
 def test_fill_default_range_bit_exact(gpu_ops, dt, nbytes):
     es = {"FP64": 8, "INT64": 8, "UINT64": 8, "FP32": 4, "INT32": 4, "UINT32": 4}.get(dt, 2 if dt in ("FP16", "BF16", "INT16", "UINT16") else 1)
-    nbytes -= nbytes % es
+    nbytes -= nbytes % es  # whole elements
     got = _fill_device(gpu_ops, nbytes, dt, seed=0x1234567890ABCDEF, stream=(5 << 32) | 17)
     ref = cref.fill(nbytes, dt, seed=0x1234567890ABCDEF, stream=(5 << 32) | 17)
     assert np.array_equal(got, ref)
@@ -76,7 +76,6 @@ def test_fill_ranges_vs_both_oracles(gpu_ops, dt, low, high):
     else:
         assert np.array_equal(got, ref_np)
     if dt.startswith(("INT", "UINT")):
-        es = int(dt[-2:].replace("T", "")) // 8 if dt[-2:].isdigit() else 1
         npdt = {"INT64": np.int64, "UINT64": np.uint64, "INT32": np.int32, "UINT32": np.uint32,
                 "INT16": np.int16, "UINT16": np.uint16, "INT8": np.int8, "UINT8": np.uint8}[dt]
         v = got[: nbytes - nbytes % 8].view(npdt)
@@ -219,12 +218,14 @@ def _random_values(dt, n, rng):
         v = raw.view(NP[dt])
         special = np.array([0.0, -0.0, 1.0, -2.5, 65504.0, 65520.0, 1e-8, 6e-8, 5.96e-8, np.inf, -np.inf, 3.0e38, 1e-40], dtype=np.float64).astype(NP[dt])
         v = v.copy()
-        v[: special.size] = special
+        k = min(n, special.size)
+        v[:k] = special[:k]
         v[np.isnan(v)] = 1.5  # NaN payload propagation is not part of the contract
         return v
     info = np.iinfo(NP[dt])
     v = rng.integers(info.min, info.max, n, dtype=np.int64 if info.min < 0 else np.uint64, endpoint=True).astype(NP[dt])
-    v[:4] = np.array([info.min, info.max, 0, 1]).astype(NP[dt])
+    edge = np.array([info.min, info.max, 0, 1]).astype(NP[dt])
+    v[: min(n, 4)] = edge[: min(n, 4)]
     return v
 
 
@@ -366,6 +367,48 @@ def test_graph_replay_advances_epoch(gpu_ops):
         assert np.array_equal(out[:n], cref.fill(n, "FP32", seed=5, stream=10 + e))
         assert np.array_equal(out[n:], cref.fill(n, "INT32", seed=5, stream=11 + e, ilo=0, irange=1000))
     g.close()
+
+
+def test_graph_with_folded_bump_and_parallel_validate(gpu_ops):
+    """The bench step: fill (advancing the epoch inside the kernel) on the main branch,
+    validation of the output regions on a parallel branch of the same graph."""
+    from client_b200._native import CheckJob
+    from client_b200.device import DeviceBuffer, HostBuffer, make_fill_job, results_array
+
+    slots, n = 6, 602112
+    buf = DeviceBuffer(0, slots * n)
+    logits = np.random.default_rng(4).standard_normal((slots, 1000)).astype(np.float32)
+    outs = gpu_ops.upload(logits)
+    res = HostBuffer(slots * 32)
+    jobs = [make_fill_job(buf.ptr + k * n, n, "FP32", stream_id=k) for k in range(slots)]
+    checks = [CheckJob(a=outs.ptr + k * 4000, nbytes=4000, kind=3) for k in range(slots)]
+    gpu_ops.epoch_set(7)
+    launches0 = gpu_ops.ctx.launch_count
+    gpu_ops.graph_begin()
+    gpu_ops.fork()
+    gpu_ops.check(checks, res.device_ptr)
+    gpu_ops.join()
+    gpu_ops.fill_epoch(jobs, seed=99, bump=slots)
+    g = gpu_ops.graph_end()
+    assert gpu_ops.ctx.launch_count == launches0  # captured, not run
+    for it in range(4):
+        g.launch()
+        gpu_ops.sync()
+        e = 7 + slots * it
+        got = gpu_ops.download(buf.ptr, slots * n)
+        for k in (0, slots - 1):
+            assert np.array_equal(got[k * n:(k + 1) * n], cref.fill(n, "FP32", seed=99, stream=k + e)), (it, k)
+        r = results_array(res, slots)
+        assert [int(x) for x in r["argmax"]] == [int(np.argmax(row)) for row in logits]
+    assert gpu_ops.ctx.launch_count - launches0 == 4 * 2
+    g.close()
+    # eager fork/join as well
+    gpu_ops.fork()
+    gpu_ops.check(checks, res.device_ptr)
+    gpu_ops.join()
+    gpu_ops.fill(jobs, seed=1)
+    gpu_ops.sync()
+    assert np.array_equal(gpu_ops.download(buf.ptr, n), cref.fill(n, "FP32", seed=1, stream=0))
 
 
 def test_fill_into_pinned_host_wire_buffer(gpu_ops):
