@@ -1,0 +1,41 @@
+"""The load generator on the GPU: CUDA shared memory slots filled and validated on the
+device, requests that only name regions, mock server in its own process (C2 / C4 / C5
+shapes at small concurrency)."""
+
+import pytest
+
+from client_b200.perf import cli
+from test_loopback import start_server
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def server():
+    proc, http_port, grpc_port = start_server()
+    yield {"http": "127.0.0.1:%d" % http_port, "grpc": "127.0.0.1:%d" % grpc_port}
+    proc.terminate()
+    proc.wait(10)
+
+
+def test_densenet_cuda_shm_http(server):
+    rows = cli.main(["-m", "densenet_onnx", "-u", server["http"], "-i", "http", "--shared-memory", "cuda",
+                     "--concurrency-range", "1:4:2x", "-p", "300", "-r", "3", "--json"])
+    assert [r["concurrency"] for r in rows] == [1, 2, 4]
+    for r in rows:
+        assert r["count"] > 3 and r["failed"] == 0 and r["nonfinite"] == 0 and r["input_bytes"] == 602112, r
+
+
+def test_bert_wire_grpc_and_simple_system(server):
+    rows = cli.main(["-m", "bert_large", "-u", server["grpc"], "-i", "grpc", "--shared-memory", "none",
+                     "--concurrency-range", "4", "-p", "300", "-r", "3", "--json"])
+    assert rows[0]["count"] > 3 and rows[0]["failed"] == 0 and rows[0]["input_bytes"] == 6144
+    rows = cli.main(["-m", "simple", "-u", server["http"], "--shared-memory", "system", "--concurrency-range", "2",
+                     "-p", "300", "-r", "3", "--input-data-mode", "once", "--json"])
+    assert rows[0]["count"] > 3 and rows[0]["failed"] == 0
+
+
+def test_llama_stream_ttft(server):
+    rows = cli.main(["-m", "llama3_8b", "-u", server["grpc"], "-i", "grpc", "--streaming", "--shape", "input_ids:1,4096",
+                     "--concurrency-range", "2", "-p", "300", "-r", "3", "--json"])
+    assert rows[0]["count"] > 2 and "ttft_p50_us" in rows[0]
