@@ -1,0 +1,3 @@
+from ..._auth import BasicAuth
+
+__all__ = ["BasicAuth"]
