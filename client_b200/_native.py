@@ -135,6 +135,7 @@ SIGNATURES = {
     "tb200_ctx_epoch_set": (c_int, [c_vp, c_u64]),
     "tb200_ctx_epoch_bump_async": (c_int, [c_vp, c_u64]),
     "tb200_l2_flush_async": (c_int, [c_vp]),
+    "tb200_tune": (c_int, [ctypes.c_char_p, c_int]),
 }
 
 _lib = None

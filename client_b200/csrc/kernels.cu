@@ -56,29 +56,40 @@ __device__ __forceinline__ uint32_t find_job(const uint32_t* __restrict__ prefix
 // =============================================================================
 // Kernel 1: fill
 // =============================================================================
-// One span = up to kFillSpanGroups consecutive 16-byte groups of one job, processed by
-// one CTA.  `count` groups exist in the span (the last may be partial), the first `full`
-// of them can be written with one aligned 16-byte store.
-template <uint32_t DT>
-__device__ __forceinline__ void fill_span_random(uint8_t* __restrict__ dst, uint64_t nbytes,
-                                                 uint64_t g_first, uint32_t count, uint32_t full,
-                                                 const FillParams& p, uint32_t s_lo, uint32_t s_hi,
-                                                 const RoundKeys& rk) {
-  uint32_t i = threadIdx.x;
-  // two independent Philox chains per thread per iteration; every store instruction of a
-  // warp covers 512 contiguous bytes
-  for (; i + kFillThreads < full; i += 2 * kFillThreads) {
-    const uint64_t ga = g_first + i, gb = ga + kFillThreads;
-    const U32x4 ra = philox4x32_10_rk(static_cast<uint32_t>(ga), static_cast<uint32_t>(ga >> 32), s_lo, s_hi, rk);
-    const U32x4 rb = philox4x32_10_rk(static_cast<uint32_t>(gb), static_cast<uint32_t>(gb >> 32), s_lo, s_hi, rk);
-    const U32x4 oa = fill_group(DT, ra, p);
-    const U32x4 ob = fill_group(DT, rb, p);
-    st_cs_v4(dst + ga * 16, oa);
-    st_cs_v4(dst + gb * 16, ob);
+// largest j in [0, n) with prefix[j] <= g (64-bit prefix)
+__device__ __forceinline__ uint32_t find_job64(const uint64_t* __restrict__ prefix, uint32_t n, uint64_t g) {
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(prefix + mid) <= g) lo = mid; else hi = mid;
   }
-  for (; i < count; i += kFillThreads) {
-    const uint64_t g = g_first + i;
-    const U32x4 r = philox4x32_10_rk(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), s_lo, s_hi, rk);
+  return lo;
+}
+
+// Groups [g0, g0 + count) of one job; the first `full` of them can be written with one
+// aligned 16-byte store, the rest (at most the job's last, partial group or an unaligned
+// destination) byte-wise.  UNROLL independent Philox chains per thread per iteration;
+// every store instruction of a warp covers 512 contiguous bytes.
+template <uint32_t DT, int THREADS, int UNROLL, int ROUNDS>
+__device__ __forceinline__ void fill_segment_random(uint8_t* __restrict__ dst, uint64_t nbytes,
+                                                    uint64_t g0, uint32_t count, uint32_t full,
+                                                    const FillParams& p, uint32_t s_lo, uint32_t s_hi,
+                                                    const RoundKeys& rk) {
+  uint32_t i = threadIdx.x;
+  for (; i + (UNROLL - 1) * THREADS < full; i += UNROLL * THREADS) {
+    U32x4 o[UNROLL];
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) {
+      const uint64_t g = g0 + i + k * THREADS;
+      const U32x4 r = philox4x32_10_rk<ROUNDS>(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), s_lo, s_hi, rk);
+      o[k] = fill_group(DT, r, p);
+    }
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) st_cs_v4(dst + (g0 + i + k * THREADS) * 16, o[k]);
+  }
+  for (; i < count; i += THREADS) {
+    const uint64_t g = g0 + i;
+    const U32x4 r = philox4x32_10_rk<ROUNDS>(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), s_lo, s_hi, rk);
     const U32x4 o = fill_group(DT, r, p);
     if (i < full) {
       st_cs_v4(dst + g * 16, o);
@@ -89,12 +100,13 @@ __device__ __forceinline__ void fill_span_random(uint8_t* __restrict__ dst, uint
   }
 }
 
-__device__ __forceinline__ void fill_span_const(uint8_t* __restrict__ dst, uint64_t nbytes,
-                                                uint64_t g_first, uint32_t count, uint32_t full,
-                                                uint32_t word) {
+template <int THREADS>
+__device__ __forceinline__ void fill_segment_const(uint8_t* __restrict__ dst, uint64_t nbytes,
+                                                   uint64_t g0, uint32_t count, uint32_t full,
+                                                   uint32_t word) {
   const U32x4 o{word, word, word, word};
-  for (uint32_t i = threadIdx.x; i < count; i += kFillThreads) {
-    const uint64_t g = g_first + i;
+  for (uint32_t i = threadIdx.x; i < count; i += THREADS) {
+    const uint64_t g = g0 + i;
     if (i < full) {
       st_cs_v4(dst + g * 16, o);
     } else {
@@ -104,61 +116,70 @@ __device__ __forceinline__ void fill_span_const(uint8_t* __restrict__ dst, uint6
   }
 }
 
-__global__ void __launch_bounds__(kFillThreads) fill_kernel(const FillLaunch L) {
+// The launch's groups (all jobs back to back) are split evenly over the CTAs: CTA b owns
+// [T*b/P, T*(b+1)/P) and walks across job boundaries, so the load is balanced to one
+// group for any mix of tensor sizes and every CTA is resident from the start.
+template <int THREADS, int UNROLL, int MINB, int ROUNDS>
+__global__ void __launch_bounds__(THREADS, MINB) fill_kernel(const FillLaunch L) {
   uint64_t epoch = L.epoch;
   if (L.dev_epoch != nullptr) epoch += *L.dev_epoch;
 
-  for (uint32_t span = blockIdx.x; span < L.total_spans; span += gridDim.x) {
-    uint32_t j, ls;
-    if (L.uniform_spans != 0) {
-      j = span / L.uniform_spans;
-      ls = span - j * L.uniform_spans;
-    } else {
-      j = find_job(L.span_prefix, L.njobs, span);
-      ls = span - __ldg(L.span_prefix + j);
+  uint64_t lo = (L.total_groups * blockIdx.x) / gridDim.x;
+  const uint64_t hi = (L.total_groups * (blockIdx.x + 1ull)) / gridDim.x;
+  uint32_t j = 0;
+  if (lo < hi) {
+    j = L.uniform_groups != 0 ? static_cast<uint32_t>(lo / L.uniform_groups) : find_job64(L.group_prefix, L.njobs, lo);
+  }
+  while (lo < hi) {
+    const uint64_t job_begin = L.uniform_groups != 0 ? L.uniform_groups * j : __ldg(L.group_prefix + j);
+    const uint64_t job_end = L.uniform_groups != 0 ? job_begin + L.uniform_groups : __ldg(L.group_prefix + j + 1);
+    if (job_end <= lo) {  // empty job
+      ++j;
+      continue;
     }
+    const uint64_t seg_hi = hi < job_end ? hi : job_end;
     const tb200_fill_job jb = L.jobs[j];
     uint8_t* dst = reinterpret_cast<uint8_t*>(jb.dst);
-    const uint64_t g_first = static_cast<uint64_t>(ls) * kFillSpanGroups;
-    const uint64_t bytes_left = jb.nbytes - g_first * 16;  // > 0 by construction of the span table
-    const uint64_t groups_left = (bytes_left + 15) / 16;
-    const uint32_t count = groups_left < kFillSpanGroups ? static_cast<uint32_t>(groups_left) : kFillSpanGroups;
+    const uint64_t g0 = lo - job_begin;
+    const uint32_t count = static_cast<uint32_t>(seg_hi - lo);
     uint32_t full = 0;
     if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      const uint64_t whole = bytes_left / 16;
-      full = whole < kFillSpanGroups ? static_cast<uint32_t>(whole) : kFillSpanGroups;
+      const uint64_t whole = jb.nbytes / 16;
+      if (whole > g0) full = (whole - g0) < count ? static_cast<uint32_t>(whole - g0) : count;
     }
-
     if (jb.mode != TB200_FILL_RANDOM) {
       uint32_t word = 0;
       if (jb.mode == TB200_FILL_BYTE) word = (static_cast<uint32_t>(jb.ilo) & 0xFFu) * 0x01010101u;
-      fill_span_const(dst, jb.nbytes, g_first, count, full, word);
-      continue;
-    }
-    FillParams p;
-    p.lo_f = static_cast<float>(jb.lo);
-    p.span_f = static_cast<float>(jb.span);
-    p.lo_d = jb.lo;
-    p.span_d = jb.span;
-    p.ilo = jb.ilo;
-    p.irange = jb.irange;
-    p.unit = (jb.span == 0.0) ? 1u : 0u;
-    const uint64_t stream = jb.stream + epoch;
-    const uint32_t s_lo = static_cast<uint32_t>(stream);
-    const uint32_t s_hi = static_cast<uint32_t>(stream >> 32);
-#define TB200_FILL_CASE(DT) fill_span_random<DT>(dst, jb.nbytes, g_first, count, full, p, s_lo, s_hi, L.rk); break
-    switch (jb.dtype) {
-      case kF32: TB200_FILL_CASE(kF32);
-      case kF16: TB200_FILL_CASE(kF16);
-      case kBF16: TB200_FILL_CASE(kBF16);
-      case kF64: TB200_FILL_CASE(kF64);
-      case kI64: case kU64: TB200_FILL_CASE(kI64);
-      case kI32: case kU32: TB200_FILL_CASE(kI32);
-      case kI16: case kU16: TB200_FILL_CASE(kI16);
-      case kI8: case kU8: TB200_FILL_CASE(kI8);
-      default: TB200_FILL_CASE(kBool);
-    }
+      fill_segment_const<THREADS>(dst, jb.nbytes, g0, count, full, word);
+    } else {
+      FillParams p;
+      p.lo_f = static_cast<float>(jb.lo);
+      p.span_f = static_cast<float>(jb.span);
+      p.lo_d = jb.lo;
+      p.span_d = jb.span;
+      p.ilo = jb.ilo;
+      p.irange = jb.irange;
+      p.unit = (jb.span == 0.0) ? 1u : 0u;
+      const uint64_t stream = jb.stream + epoch;
+      const uint32_t s_lo = static_cast<uint32_t>(stream);
+      const uint32_t s_hi = static_cast<uint32_t>(stream >> 32);
+#define TB200_FILL_CASE(DT) \
+  fill_segment_random<DT, THREADS, UNROLL, ROUNDS>(dst, jb.nbytes, g0, count, full, p, s_lo, s_hi, L.rk); break
+      switch (jb.dtype) {
+        case kF32: TB200_FILL_CASE(kF32);
+        case kF16: TB200_FILL_CASE(kF16);
+        case kBF16: TB200_FILL_CASE(kBF16);
+        case kF64: TB200_FILL_CASE(kF64);
+        case kI64: case kU64: TB200_FILL_CASE(kI64);
+        case kI32: case kU32: TB200_FILL_CASE(kI32);
+        case kI16: case kU16: TB200_FILL_CASE(kI16);
+        case kI8: case kU8: TB200_FILL_CASE(kI8);
+        default: TB200_FILL_CASE(kBool);
+      }
 #undef TB200_FILL_CASE
+    }
+    lo = seg_hi;
+    ++j;
   }
 
   // graph replays: the last CTA to finish advances the device epoch, so the next replay
@@ -170,20 +191,45 @@ __global__ void __launch_bounds__(kFillThreads) fill_kernel(const FillLaunch L) 
   }
 }
 
-cudaError_t launch_fill(const FillLaunch& l, int sm_count, cudaStream_t s) {
-  if (l.total_spans == 0) return cudaSuccess;
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
+static int g_fill_variant = 0;
+void set_fill_variant(int v) { g_fill_variant = v; }
+
+template <int THREADS, int UNROLL, int MINB, int ROUNDS>
+static cudaError_t launch_fill_t(const FillLaunch& l, int sm_count, cudaStream_t s, int ctas_per_sm) {
+  static int occ = 0;
+  if (occ == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel, kFillThreads, 0) != cudaSuccess || n < 1) n = 4;
-    blocks_per_sm = n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<THREADS, UNROLL, MINB, ROUNDS>, THREADS, 0) != cudaSuccess || n < 1) n = 1;
+    occ = n;
   }
-  // all CTAs resident at once, every CTA the same number of spans (+-1)
-  const uint32_t max_grid = static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(blocks_per_sm);
-  const uint32_t rounds = (l.total_spans + max_grid - 1) / max_grid;
-  const uint32_t grid = (l.total_spans + rounds - 1) / rounds;
-  fill_kernel<<<grid, kFillThreads, 0, s>>>(l);
+  int per_sm = (ctas_per_sm > 0 && ctas_per_sm < occ) ? ctas_per_sm : occ;
+  uint64_t grid = static_cast<uint64_t>(sm_count) * per_sm;
+  // no point in CTAs with less than one iteration of work
+  const uint64_t max_useful = (l.total_groups + THREADS * UNROLL - 1) / (THREADS * UNROLL);
+  if (grid > max_useful) grid = max_useful;
+  if (grid == 0) grid = 1;
+  fill_kernel<THREADS, UNROLL, MINB, ROUNDS><<<static_cast<uint32_t>(grid), THREADS, 0, s>>>(l);
   return cudaGetLastError();
+}
+
+cudaError_t launch_fill(const FillLaunch& l, int sm_count, cudaStream_t s) {
+  if (l.total_groups == 0 && l.bump == 0) return cudaSuccess;
+  switch (g_fill_variant) {
+    // experiment matrix (scripts/fill_sweep.py): threads, unroll, min CTAs/SM, rounds
+    case 1: return launch_fill_t<256, 2, 1, 10>(l, sm_count, s, 0);
+    case 2: return launch_fill_t<256, 4, 1, 10>(l, sm_count, s, 0);
+    case 3: return launch_fill_t<256, 2, 8, 10>(l, sm_count, s, 0);
+    case 4: return launch_fill_t<128, 2, 1, 10>(l, sm_count, s, 0);
+    case 5: return launch_fill_t<128, 4, 1, 10>(l, sm_count, s, 0);
+    case 6: return launch_fill_t<512, 2, 1, 10>(l, sm_count, s, 0);
+    case 7: return launch_fill_t<256, 1, 8, 10>(l, sm_count, s, 0);
+    case 8: return launch_fill_t<256, 2, 4, 10>(l, sm_count, s, 4);
+    case 9: return launch_fill_t<256, 2, 1, 7>(l, sm_count, s, 0);   // NOT the contract: sensitivity only
+    case 10: return launch_fill_t<256, 2, 1, 1>(l, sm_count, s, 0);  // NOT the contract: store ceiling
+    case 11: return launch_fill_t<256, 3, 1, 10>(l, sm_count, s, 0);
+    case 12: return launch_fill_t<128, 2, 12, 10>(l, sm_count, s, 0);
+    default: return launch_fill_t<256, 2, 1, 10>(l, sm_count, s, 0);
+  }
 }
 
 // =============================================================================

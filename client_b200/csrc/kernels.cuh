@@ -11,24 +11,22 @@
 namespace tb200 {
 
 // ---- fill ---------------------------------------------------------------------
-constexpr int kFillThreads = 256;
-constexpr uint32_t kFillSpanGroups = 2048;                     // 16-byte groups per span
-constexpr uint32_t kFillSpanBytes = kFillSpanGroups * 16;      // 32 KiB: unit of work of one CTA
-
 struct FillLaunch {
-  const tb200_fill_job* jobs;   // device
-  const uint32_t* span_prefix;  // device, njobs+1 entries; unused when uniform
-  uint64_t* dev_epoch;          // device or nullptr: added to every stream id
-  unsigned int* done_counter;   // device: CTAs finished (wraps), used when bump != 0
+  const tb200_fill_job* jobs;    // device
+  const uint64_t* group_prefix;  // device, njobs+1 entries (16-byte groups before job j); unused when uniform
+  uint64_t* dev_epoch;           // device or nullptr: added to every stream id
+  unsigned int* done_counter;    // device: CTAs finished (wraps), used when bump != 0
   uint64_t seed;
   uint64_t epoch;
-  uint64_t bump;                // != 0: the last CTA adds this to *dev_epoch
+  uint64_t bump;                 // != 0: the last CTA adds this to *dev_epoch
+  uint64_t total_groups;
+  uint64_t uniform_groups;       // >0: every job has exactly this many groups
   uint32_t njobs;
-  uint32_t total_spans;
-  uint32_t uniform_spans;       // >0: every job has exactly this many spans
-  RoundKeys rk;                 // Philox key schedule of `seed`
+  RoundKeys rk;                  // Philox key schedule of `seed`
 };
 cudaError_t launch_fill(const FillLaunch& l, int sm_count, cudaStream_t s);
+// tuning knob for experiments (scripts/fill_sweep.py); 0 = default configuration
+void set_fill_variant(int v);
 
 // ---- pack / cast ----------------------------------------------------------------
 struct ImagePack {

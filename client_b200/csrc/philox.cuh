@@ -65,10 +65,11 @@ inline void make_round_keys(uint64_t seed, RoundKeys* out) {
     k1 += kPhiloxW1;
   }
 }
+template <int R = 10>
 TB200_HD U32x4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                 const RoundKeys& rk) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < R; ++r) {
     const uint64_t p0 = static_cast<uint64_t>(kPhiloxM0) * c0;
     const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;
     const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ rk.k[2 * r];

@@ -679,13 +679,13 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
   if (ctx == nullptr || njobs < 0 || (njobs > 0 && jobs == nullptr)) return fail(TB200_ERR_INVALID, "bad argument");
   if (njobs == 0) return TB200_OK;
   DeviceGuard g(ctx->device);
-  const int max_jobs = static_cast<int>(kJobSlotBytes / (sizeof(tb200_fill_job) + sizeof(uint32_t))) - 1;
+  const int max_jobs = static_cast<int>(kJobSlotBytes / (sizeof(tb200_fill_job) + sizeof(uint64_t))) - 1;
   RoundKeys rk;
   make_round_keys(seed, &rk);
   for (int base = 0; base < njobs; base += max_jobs) {
     const int n = std::min(max_jobs, njobs - base);
     const bool last = base + n >= njobs;
-    std::vector<uint32_t> prefix(n + 1, 0);
+    std::vector<uint64_t> prefix(n + 1, 0);
     bool uniform = true;
     uint64_t total = 0;
     for (int i = 0; i < n; ++i) {
@@ -703,16 +703,16 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
                       static_cast<unsigned long long>(jb.irange), es);
         }
       }
-      const uint64_t spans = (jb.nbytes + kFillSpanBytes - 1) / kFillSpanBytes;
-      total += spans;
-      if (total > 0xFFFFFFF0ull) return fail(TB200_ERR_INVALID, "fill launch too large");
-      prefix[i + 1] = static_cast<uint32_t>(total);
-      if (spans != (jobs[base].nbytes + kFillSpanBytes - 1) / kFillSpanBytes) uniform = false;
+      const uint64_t groups = (jb.nbytes + 15) / 16;
+      total += groups;
+      if (total > (1ull << 44)) return fail(TB200_ERR_INVALID, "fill launch too large");
+      prefix[i + 1] = total;
+      if (groups != (jobs[base].nbytes + 15) / 16) uniform = false;
     }
-    if (total == 0 && !(last && bump != 0)) continue;
+    if (total == 0 && !(last && bump != 0 && use_dev_epoch)) continue;
     // one upload: [jobs | prefix]
     const size_t jbytes = sizeof(tb200_fill_job) * n;
-    const size_t pbytes = sizeof(uint32_t) * (n + 1);
+    const size_t pbytes = sizeof(uint64_t) * (n + 1);
     std::vector<char> blob(jbytes + pbytes);
     memcpy(blob.data(), jobs + base, jbytes);
     memcpy(blob.data() + jbytes, prefix.data(), pbytes);
@@ -721,21 +721,17 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
     if (rc != TB200_OK) return rc;
     FillLaunch L;
     L.jobs = static_cast<const tb200_fill_job*>(dev);
-    L.span_prefix = reinterpret_cast<const uint32_t*>(static_cast<const char*>(dev) + jbytes);
+    L.group_prefix = reinterpret_cast<const uint64_t*>(static_cast<const char*>(dev) + jbytes);
     L.dev_epoch = use_dev_epoch ? ctx->dev_epoch : nullptr;
     L.done_counter = reinterpret_cast<unsigned int*>(ctx->dev_epoch + 1);
     L.seed = seed;
     L.epoch = epoch;
     L.bump = (last && use_dev_epoch) ? bump : 0;
     L.njobs = static_cast<uint32_t>(n);
-    L.total_spans = static_cast<uint32_t>(total);
-    L.uniform_spans = uniform ? prefix[1] : 0;
+    L.total_groups = total;
+    L.uniform_groups = (uniform && total != 0) ? prefix[1] : 0;
     L.rk = rk;
-    if (total == 0) {  // nothing to write but the epoch must still advance
-      TB200_CUDA(launch_epoch_bump(ctx->dev_epoch, bump, ctx->cur));
-    } else {
-      TB200_CUDA(launch_fill(L, ctx->sm_count, ctx->cur));
-    }
+    TB200_CUDA(launch_fill(L, ctx->sm_count, ctx->cur));
     ctx->launches += 1;
   }
   return TB200_OK;
@@ -977,6 +973,14 @@ int tb200_graph_destroy(tb200_graph* gr) {
   for (void* p : gr->device_allocs) cudaFree(p);
   delete gr;
   return TB200_OK;
+}
+
+int tb200_tune(const char* key, int value) {
+  if (key != nullptr && strcmp(key, "fill_variant") == 0) {
+    set_fill_variant(value);
+    return TB200_OK;
+  }
+  return fail(TB200_ERR_INVALID, "unknown tuning key");
 }
 
 int tb200_l2_flush_async(tb200_ctx* ctx) {

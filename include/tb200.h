@@ -308,6 +308,9 @@ int tb200_ctx_epoch_bump_async(tb200_ctx* ctx, uint64_t delta);
 int tb200_fill_epoch_async(tb200_ctx* ctx, const tb200_fill_job* jobs,
                            int njobs, uint64_t seed, uint64_t bump);
 
+/* experiment knobs (scripts/fill_sweep.py); key "fill_variant", 0 = default */
+int tb200_tune(const char* key, int value);
+
 /* write > L2-size bytes so the next timed kernel starts with a cold L2 */
 int tb200_l2_flush_async(tb200_ctx* ctx);
 
