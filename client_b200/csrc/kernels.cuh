@@ -21,7 +21,11 @@ struct FillLaunch {
   uint64_t bump;                 // != 0: the last CTA adds this to *dev_epoch
   uint64_t total_groups;
   uint64_t uniform_groups;       // >0: every job has exactly this many groups
+  uint64_t div_magic;            // floor(2^64 / uniform_groups) + 1 (homogeneous launches)
   uint32_t njobs;
+  uint32_t dtype0;               // dtype of job 0 (the dtype of a homogeneous launch)
+  uint32_t homogeneous;          // 1: uniform sizes, one dtype/range, random mode, every tensor a
+                                 //    16-byte-aligned multiple of 16 bytes -> grid-stride kernel
   RoundKeys rk;                  // Philox key schedule of `seed`
 };
 cudaError_t launch_fill(const FillLaunch& l, int sm_count, cudaStream_t s);

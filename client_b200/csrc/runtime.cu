@@ -687,6 +687,7 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
     const bool last = base + n >= njobs;
     std::vector<uint64_t> prefix(n + 1, 0);
     bool uniform = true;
+    bool homogeneous = true;
     uint64_t total = 0;
     for (int i = 0; i < n; ++i) {
       const tb200_fill_job& jb = jobs[base + i];
@@ -704,6 +705,11 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
         }
       }
       const uint64_t groups = (jb.nbytes + 15) / 16;
+      const tb200_fill_job& f = jobs[base];
+      if (jb.mode != TB200_FILL_RANDOM || jb.dtype != f.dtype || jb.lo != f.lo || jb.span != f.span ||
+          jb.ilo != f.ilo || jb.irange != f.irange || (jb.nbytes & 15) != 0 || (jb.dst & 15) != 0) {
+        homogeneous = false;
+      }
       total += groups;
       if (total > (1ull << 44)) return fail(TB200_ERR_INVALID, "fill launch too large");
       prefix[i + 1] = total;
@@ -730,6 +736,16 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
     L.njobs = static_cast<uint32_t>(n);
     L.total_groups = total;
     L.uniform_groups = (uniform && total != 0) ? prefix[1] : 0;
+    L.homogeneous = (homogeneous && L.uniform_groups != 0) ? 1u : 0u;
+    L.div_magic = 0;
+    L.dtype0 = jobs[base].dtype;
+    // exact g / d by multiply-high needs g * d < 2^64
+    if (L.homogeneous && (L.uniform_groups < 2 || static_cast<unsigned __int128>(total) * L.uniform_groups >= (static_cast<unsigned __int128>(1) << 63))) {
+      L.homogeneous = 0;
+    }
+    if (L.homogeneous) {
+      L.div_magic = static_cast<uint64_t>((static_cast<unsigned __int128>(1) << 64) / L.uniform_groups) + 1;
+    }
     L.rk = rk;
     TB200_CUDA(launch_fill(L, ctx->sm_count, ctx->cur));
     ctx->launches += 1;

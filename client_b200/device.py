@@ -84,7 +84,7 @@ class HostBuffer:
 
     def view(self, offset=0, nbytes=None):
         end = self.nbytes if nbytes is None else offset + nbytes
-        return memoryview(self._ctype)[offset:end]
+        return memoryview(self._ctype).cast("B")[offset:end]
 
     def close(self):
         if getattr(self, "host_ptr", None):
