@@ -100,46 +100,17 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def dist_setup(n_gpus):
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_mod
-
-        torch.cuda.set_device(local)
-        dist_mod.init_process_group("nccl")
-        dist = dist_mod
-    return world, rank, local, dist
-
-
-def barrier(dist, local):
-    if dist is not None:
-        import torch
-
-        dist.barrier()
-        torch.cuda.synchronize(local)
-
-
-def max_over_ranks(dist, local, value):
-    if dist is None:
-        return value
-    import torch
-
-    t = torch.tensor([value], dtype=torch.float64, device="cuda:%d" % local)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
-
-
 def run_b200(args):
     from client_b200 import _native
     from client_b200._native import CheckJob
     from client_b200.device import DeviceBuffer, DeviceOps, HostBuffer, make_fill_job, results_array
     import client_b200.utils.cuda_shared_memory as cudashm
 
-    world, rank, local, dist = dist_setup(args.gpus)
+    from client_b200.perf.replicas import Replicas
+
+    rep = Replicas()
+    world, rank, local = rep.world, rep.rank, rep.local_rank
+    stream0 = rep.stream_base(SLOTS)  # disjoint Philox streams per replica
     ctx = _native.Context(local)
     ops = DeviceOps(ctx)
     steps, warmup = args.steps, max(args.warmup, 3)
@@ -154,7 +125,7 @@ def run_b200(args):
     fill_jobs, check_jobs = [], []
     for s in range(SETS):
         fill_jobs.append((_native.FillJob * SLOTS)(*[
-            make_fill_job(in_regions[s]._base_addr + k * IN_BYTES, IN_BYTES, "FP32", stream_id=k) for k in range(SLOTS)]))
+            make_fill_job(in_regions[s]._base_addr + k * IN_BYTES, IN_BYTES, "FP32", stream_id=stream0 + k) for k in range(SLOTS)]))
         check_jobs.append((CheckJob * SLOTS)(*[
             CheckJob(a=out_regions[s]._base_addr + k * OUT_BYTES, nbytes=OUT_BYTES, kind=_native.CHECK_TOP1) for k in range(SLOTS)]))
     ops.sync()
@@ -176,15 +147,15 @@ def run_b200(args):
     for i in range(warmup):
         graphs[i % SETS].launch()
     ops.sync()
-    barrier(dist, local)
+    rep.barrier()
     launches0 = ctx.launch_count
     timer.start()
     for i in range(steps):
         graphs[i % SETS].launch()
     timer.stop()
     ops.sync()
-    barrier(dist, local)
-    ms_value = max_over_ranks(dist, local, timer.elapsed_ms())
+    rep.barrier()
+    ms_value = rep.max(timer.elapsed_ms())
     gpu_launches = ctx.launch_count - launches0
     res = results_array(results, SETS * SLOTS)
     assert int(res["mismatches"].sum()) == 0, "non-finite logits reported by the validate kernel"
@@ -217,7 +188,7 @@ def run_b200(args):
         ops.fill(fill_jobs[i % SETS], seed=SEED, epoch=i * SLOTS)
         ops.check(check_jobs[i % SETS], results.device_ptr + (i % SETS) * SLOTS * 32)
     ops.sync()
-    barrier(dist, local)
+    rep.barrier()
     t0 = time.perf_counter()
     timer.start()
     bad = 0
@@ -230,8 +201,8 @@ def run_b200(args):
     timer.stop()
     ops.sync()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    barrier(dist, local)
-    e2e_ms = max_over_ranks(dist, local, max(timer.elapsed_ms(), e2e_wall_ms))
+    rep.barrier()
+    e2e_ms = rep.max(max(timer.elapsed_ms(), e2e_wall_ms))
     assert bad == 0
     e2e_value = world * SLOTS * e2e_steps / (e2e_ms / 1e3)
     h2d_step = SLOTS * 64 + (SLOTS + 1) * 4 + SLOTS * 48
@@ -254,7 +225,7 @@ def run_b200(args):
         ops.check(check_jobs[s], results.device_ptr + s * SLOTS * 32)
         ops.sync()
     img_ms = (time.perf_counter() - t0) * 1e3
-    img_value = world * SLOTS * img_steps / (max_over_ranks(dist, local, img_ms) / 1e3)
+    img_value = world * SLOTS * img_steps / (rep.max(img_ms) / 1e3)
 
     # --- pack kernel alone (device-resident uint8 source), C3(ii)-style R+W roofline
     ops.graph_begin()
@@ -303,8 +274,7 @@ def run_b200(args):
         line["cpu_baseline"] = cpu_baseline_port()
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    rep.close()
 
 
 def cpu_baseline_port(seconds=12.0):
