@@ -130,28 +130,38 @@ def run_b200(args):
             CheckJob(a=out_regions[s]._base_addr + k * OUT_BYTES, nbytes=OUT_BYTES, kind=_native.CHECK_TOP1) for k in range(SLOTS)]))
     ops.sync()
 
-    # --- value: one CUDA graph per set = fill(64 slots, epoch advanced in-kernel) || validate(64 outputs)
-    graphs = []
-    ops.epoch_set(0)
-    for s in range(SETS):
+    # --- value: CUDA graphs of GRAPH_STEPS steps; a step = fill(64 slots, epoch advanced in-kernel)
+    #     on the main branch || validate(64 outputs) on a parallel branch, rotating over the sets
+    def capture(step_sets):
         ops.graph_begin()
-        ops.fork()   # validate the 64 output regions on a parallel branch ...
-        ops.check(check_jobs[s], results.device_ptr + s * SLOTS * 32)
-        ops.join()
-        ops.fill_epoch(fill_jobs[s], seed=SEED, bump=SLOTS)  # ... while the 64 inputs are generated
-        graphs.append(ops.graph_end())
+        for s in step_sets:
+            ops.fork()
+            ops.check(check_jobs[s], results.device_ptr + s * SLOTS * 32)   # side branch
+            ops.select(False)
+            ops.fill_epoch(fill_jobs[s], seed=SEED, bump=SLOTS)             # main branch
+            ops.join()
+        return ops.graph_end()
+
+    GRAPH_STEPS = 16
+    ops.epoch_set(0)
+    graph_many = capture([i % SETS for i in range(GRAPH_STEPS)])
+    graphs_one = [capture([s]) for s in range(SETS)]
+
+    def run_steps(n):
+        for _ in range(n // GRAPH_STEPS):
+            graph_many.launch()
+        for i in range(n % GRAPH_STEPS):
+            graphs_one[i % SETS].launch()
 
     sampler = ClockSampler(local)
     sampler.start()
     timer = _native.Timer(ctx)
-    for i in range(warmup):
-        graphs[i % SETS].launch()
+    run_steps(max(warmup, GRAPH_STEPS))
     ops.sync()
     rep.barrier()
     launches0 = ctx.launch_count
     timer.start()
-    for i in range(steps):
-        graphs[i % SETS].launch()
+    run_steps(steps)
     timer.stop()
     ops.sync()
     rep.barrier()

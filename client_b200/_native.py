@@ -96,6 +96,7 @@ SIGNATURES = {
     "tb200_ctx_sync": (c_int, [c_vp]),
     "tb200_ctx_fork": (c_int, [c_vp]),
     "tb200_ctx_join": (c_int, [c_vp]),
+    "tb200_ctx_select": (c_int, [c_vp, c_int]),
     "tb200_ctx_launch_count": (c_u64, [c_vp]),
     "tb200_ctx_sm_count": (c_int, [c_vp]),
     "tb200_timer_create": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
@@ -171,12 +172,9 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the symbol is missing
             fn.restype = restype
             fn.argtypes = argtypes
-        try:
-            from . import _native_loadgen
+        from . import _native_loadgen
 
-            _native_loadgen.declare(lib)
-        except ImportError:
-            pass
+        _native_loadgen.declare(lib)
         if lib.tb200_abi_version() != 1:
             raise RuntimeError("libtb200 ABI version mismatch")
         _lib = lib

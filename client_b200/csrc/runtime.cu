@@ -170,6 +170,7 @@ struct tb200_ctx {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool own_stream = true;
+  bool forked = false;
   uint64_t launches = 0;
   // pinned staging ring for host <-> region copies
   void* stage[kStageCount] = {nullptr, nullptr, nullptr, nullptr};
@@ -292,6 +293,10 @@ int staged_h2d(tb200_ctx* ctx, char* dst, const char* src, uint64_t nbytes) {
 
 using namespace tb200;
 
+namespace tb200 {
+void set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }
+}  // namespace tb200
+
 extern "C" {
 
 // ---------------------------------------------------------------------------
@@ -412,7 +417,7 @@ int tb200_ctx_sync(tb200_ctx* ctx) {
 // capture (it becomes a parallel branch of the graph).
 int tb200_ctx_fork(tb200_ctx* ctx) {
   if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
-  if (ctx->cur != ctx->stream) return fail(TB200_ERR_STATE, "already forked");
+  if (ctx->forked) return fail(TB200_ERR_STATE, "already forked");
   DeviceGuard g(ctx->device);
   if (ctx->side == nullptr) {
     TB200_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
@@ -421,15 +426,23 @@ int tb200_ctx_fork(tb200_ctx* ctx) {
   }
   TB200_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
   TB200_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  ctx->forked = true;
   ctx->cur = ctx->side;
+  return TB200_OK;
+}
+int tb200_ctx_select(tb200_ctx* ctx, int side) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  if (!ctx->forked) return fail(TB200_ERR_STATE, "not forked");
+  ctx->cur = side ? ctx->side : ctx->stream;
   return TB200_OK;
 }
 int tb200_ctx_join(tb200_ctx* ctx) {
   if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
-  if (ctx->cur == ctx->stream) return fail(TB200_ERR_STATE, "not forked");
+  if (!ctx->forked) return fail(TB200_ERR_STATE, "not forked");
   DeviceGuard g(ctx->device);
   TB200_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   TB200_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  ctx->forked = false;
   ctx->cur = ctx->stream;
   return TB200_OK;
 }
@@ -939,7 +952,7 @@ int tb200_check_async(tb200_ctx* ctx, const tb200_check_job* jobs, int njobs, tb
 int tb200_graph_begin(tb200_ctx* ctx) {
   if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
   if (ctx->capture != nullptr) return fail(TB200_ERR_STATE, "capture already in progress");
-  if (ctx->cur != ctx->stream) return fail(TB200_ERR_STATE, "join the side stream before capturing");
+  if (ctx->forked) return fail(TB200_ERR_STATE, "join the side stream before capturing");
   DeviceGuard g(ctx->device);
   TB200_CUDA(cudaStreamSynchronize(ctx->stream));
   tb200_graph* gr = new tb200_graph();
@@ -957,7 +970,7 @@ int tb200_graph_begin(tb200_ctx* ctx) {
 int tb200_graph_end(tb200_ctx* ctx, tb200_graph** out) {
   if (ctx == nullptr || out == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
   if (ctx->capture == nullptr) return fail(TB200_ERR_STATE, "no capture in progress");
-  if (ctx->cur != ctx->stream) return fail(TB200_ERR_STATE, "join the side stream before ending the capture");
+  if (ctx->forked) return fail(TB200_ERR_STATE, "join the side stream before ending the capture");
   DeviceGuard g(ctx->device);
   tb200_graph* gr = ctx->capture;
   ctx->capture = nullptr;

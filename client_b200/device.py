@@ -208,6 +208,10 @@ class DeviceOps:
         """Later launches run on a side stream, concurrently with the main stream."""
         _native.check(self._lib.tb200_ctx_fork(self._ctx.handle))
 
+    def select(self, side):
+        """While forked: route the following launches to the main (False) or side (True) stream."""
+        _native.check(self._lib.tb200_ctx_select(self._ctx.handle, 1 if side else 0))
+
     def join(self):
         _native.check(self._lib.tb200_ctx_join(self._ctx.handle))
 

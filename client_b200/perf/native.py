@@ -1,0 +1,145 @@
+"""Driver of the native load generator (include/tb200_loadgen.h): builds the per-slot
+HTTP requests with the drop-in request model, hands them plus the device job tables to
+libtb200 and reads back windowed statistics.  HTTP, synchronous closed loop."""
+
+import ctypes
+
+from .. import _native
+from .._native_loadgen import LoadgenConfig, LoadgenStats
+from ..http import InferenceServerClient, InferInput, InferRequestedOutput
+
+
+def frame_http_request(host, port, uri, body, json_size, head_only_bytes=None):
+    """A complete HTTP/1.1 POST.  ``head_only_bytes``: when given, ``body`` holds only the
+    JSON header and that many tensor bytes follow from the pinned tail."""
+    total = len(body) + (head_only_bytes or 0)
+    lines = ["POST /%s HTTP/1.1" % uri.lstrip("/"), "Host: %s:%d" % (host, port), "Content-Length: %d" % total]
+    if json_size is not None:
+        lines.append("Inference-Header-Content-Length: %d" % json_size)
+        lines.append("Content-Type: application/octet-stream")
+    else:
+        lines.append("Content-Type: application/json")
+    return ("\r\n".join(lines) + "\r\n\r\n").encode("ascii") + body
+
+
+class NativeLoadGenerator:
+    """One tb200_loadgen instance over a SlotSet (cuda shm or wire mode)."""
+
+    def __init__(self, url, model_name, model_version, slotset, concurrency, regenerate=True, validate=True):
+        self._lib = _native.load()
+        host, _, port = url.partition(":")
+        self.host, self.port = host, int(port or 80)
+        ss = slotset
+        self.slotset = ss
+        uri = InferenceServerClient._model_uri(model_name, model_version, "/infer")
+        self._keep = []
+        reqs, tails = [], []
+        for slot in range(concurrency):
+            inputs, outputs = [], []
+            for i, t in enumerate(ss.inputs):
+                inp = InferInput(t.name, t.shape, t.datatype)
+                if ss.shared_memory in ("cuda", "system"):
+                    inp.set_shared_memory(ss.prefix + "_in", t.nbytes, offset=ss.input_offset(slot, i))
+                else:
+                    inp._parameters["binary_data_size"] = t.nbytes  # bytes follow from the pinned tail
+                    inp._raw_data = b""
+                inputs.append(inp)
+            for i, t in enumerate(ss.outputs):
+                out = InferRequestedOutput(t.name)
+                if ss.shared_memory in ("cuda", "system"):
+                    out.set_shared_memory(ss.prefix + "_out", t.nbytes, offset=ss.output_offset(slot, i))
+                outputs.append(out)
+            body, json_size = InferenceServerClient.generate_request_body(inputs, outputs=outputs)
+            if ss.shared_memory == "none":
+                json_size = len(body)
+                reqs.append(frame_http_request(self.host, self.port, uri, body, json_size, head_only_bytes=ss.in_bytes))
+                tails.append((ss._wire.host_ptr + slot * ss.in_bytes, ss.in_bytes))
+            else:
+                reqs.append(frame_http_request(self.host, self.port, uri, body, json_size))
+        n = concurrency
+        bufs = [ctypes.create_string_buffer(r, len(r)) for r in reqs]
+        self._keep.append(bufs)
+        cfg = LoadgenConfig()
+        cfg.host = self.host.encode("ascii")
+        cfg.port = self.port
+        cfg.concurrency = n
+        cfg.requests = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
+        cfg.request_sizes = (ctypes.c_uint64 * n)(*[len(r) for r in reqs])
+        if tails:
+            cfg.tails = (ctypes.c_void_p * n)(*[p for p, _ in tails])
+            cfg.tail_sizes = (ctypes.c_uint64 * n)(*[s for _, s in tails])
+        if ss._ops is not None:
+            cfg.ctx = ss._ops.ctx.handle
+            fills = ss._fill_jobs(list(range(n)))
+            per = len(ss.inputs)
+            cfg.fill_jobs = (_native.FillJob * len(fills))(*fills)
+            cfg.fill_jobs_per_slot = per
+            cfg.seed = ss.seed
+            cfg.regenerate = 1 if regenerate else 0
+            if validate and ss.shared_memory == "cuda" and ss.outputs:
+                from ..device import HostBuffer
+
+                checks = []
+                for s in range(n):
+                    for i, t in enumerate(ss.outputs):
+                        kind = _native.CHECK_TOP1 if t.datatype == "FP32" else _native.CHECK_SUM
+                        checks.append(_native.CheckJob(a=ss.out_base + ss.output_offset(s, i), nbytes=t.nbytes, kind=kind))
+                self._results = HostBuffer(len(checks) * 32)
+                cfg.check_jobs = (_native.CheckJob * len(checks))(*checks)
+                cfg.check_jobs_per_slot = len(ss.outputs)
+                cfg.results = self._results.device_ptr
+        self._keep.append(cfg)
+        h = ctypes.c_void_p()
+        _native.check(self._lib.tb200_loadgen_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+
+    def start(self):
+        _native.check(self._lib.tb200_loadgen_start(self._h))
+
+    def window(self, seconds):
+        st = LoadgenStats()
+        _native.check(self._lib.tb200_loadgen_window(self._h, float(seconds), ctypes.byref(st)))
+        n = st.completed_request_count
+        return {
+            "count": int(n), "failed": int(st.failed_request_count),
+            "throughput": n / st.window_seconds if st.window_seconds > 0 else 0.0,
+            "avg_us": st.cumulative_total_request_time_ns / n / 1e3 if n else 0.0,
+            "send_us": st.cumulative_send_time_ns / n / 1e3 if n else 0.0,
+            "recv_us": st.cumulative_receive_time_ns / n / 1e3 if n else 0.0,
+            "p50_us": st.p50_ns / 1e3, "p90_us": st.p90_ns / 1e3, "p95_us": st.p95_ns / 1e3, "p99_us": st.p99_ns / 1e3,
+            "min_us": st.min_ns / 1e3, "max_us": st.max_ns / 1e3,
+            "device_batches": int(st.device_batches), "device_slots": int(st.device_slots),
+            "nonfinite": int(st.nonfinite_outputs), "mismatches": int(st.check_mismatches),
+        }
+
+    def stop(self):
+        if getattr(self, "_h", None):
+            self._lib.tb200_loadgen_stop(self._h)
+            self._lib.tb200_loadgen_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.stop()
+        except Exception:
+            pass
+
+
+class StubServer:
+    """tb200_stub_server: canned 200 responses, for measuring the generator itself."""
+
+    def __init__(self, body='{"model_name":"stub","outputs":[]}', host="127.0.0.1", port=0):
+        self._lib = _native.load()
+        p = ctypes.c_int(port)
+        h = ctypes.c_void_p()
+        _native.check(self._lib.tb200_stub_server_start(host.encode(), ctypes.byref(p), body.encode(), ctypes.byref(h)))
+        self._h, self.host, self.port = h, host, p.value
+
+    @property
+    def url(self):
+        return "%s:%d" % (self.host, self.port)
+
+    def stop(self):
+        if getattr(self, "_h", None):
+            self._lib.tb200_stub_server_stop(self._h)
+            self._h = None

@@ -92,7 +92,8 @@ int tb200_ctx_sync(tb200_ctx* ctx);
 /* fork: subsequent launches go to a side stream ordered after everything issued so
  * far; join: the main stream waits for it.  Inside a graph capture this builds two
  * parallel branches (e.g. fill the inputs while the outputs are validated). */
-int tb200_ctx_fork(tb200_ctx* ctx);
+int tb200_ctx_fork(tb200_ctx* ctx);            /* launches now go to the side stream   */
+int tb200_ctx_select(tb200_ctx* ctx, int side); /* while forked: 0 = main, 1 = side      */
 int tb200_ctx_join(tb200_ctx* ctx);
 /* kernels launched by this context since creation (bench.py gpu_launches) */
 uint64_t tb200_ctx_launch_count(tb200_ctx* ctx);

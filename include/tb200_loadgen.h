@@ -1,0 +1,87 @@
+/*
+ * tb200_loadgen.h -- C ABI of the native closed-loop load generator in libtb200.so.
+ *
+ * What it restates: perf_analyzer's ConcurrencyManager / ConcurrencyWorker loop --
+ * NOT part of the reference; its only traces there are
+ * the friend hooks in src/c++/library/common.h:42-47,358-360,462-464.  The per-request
+ * timestamps and the cumulative statistics follow the reference's C++ client types
+ * RequestTimers (src/c++/library/common.h:568-648) and InferStat (:93-114, folded by
+ * UpdateInferStat, src/c++/library/common.cc:56-106).
+ *
+ * Shape: `concurrency` worker threads each own one keep-alive HTTP/1.1 connection and
+ * keep one request in flight (closed loop).  A request is a pre-formed byte string per
+ * concurrency slot (with shared memory it only names regions, golden "A" of SURVEY.md
+ * 9.4).  One device thread serves all slots: slots whose responses came back are
+ * validated (tb200_check_async) and regenerated (tb200_fill_async) in ONE launch each,
+ * then handed back to the workers -- the transport threads never touch tensor bytes.
+ */
+#ifndef TB200_LOADGEN_H_
+#define TB200_LOADGEN_H_
+
+#include "tb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tb200_loadgen tb200_loadgen;
+
+typedef struct tb200_loadgen_config {
+  const char* host;              /* numeric IPv4 address, e.g. "127.0.0.1" */
+  int port;
+  int concurrency;               /* requests in flight = worker threads = slots */
+  const uint8_t* const* requests; /* [concurrency] complete HTTP requests (headers + body) */
+  const uint64_t* request_sizes;  /* [concurrency] */
+  /* optional binary tails sent right after requests[s] and NOT copied: they point into
+   * pinned staging that the fill kernel rewrites before every send (HTTP binary-tensor
+   * body in --shared-memory none mode); NULL when the request is self-contained */
+  const uint8_t* const* tails;
+  const uint64_t* tail_sizes;
+  /* device side (all optional: ctx == NULL -> transport only) */
+  tb200_ctx* ctx;
+  const tb200_fill_job* fill_jobs;   /* [concurrency * fill_jobs_per_slot], slot-major */
+  int fill_jobs_per_slot;
+  uint64_t seed;
+  int regenerate;                    /* 1: refill a slot's inputs before every request */
+  const tb200_check_job* check_jobs; /* [concurrency * check_jobs_per_slot] */
+  int check_jobs_per_slot;
+  tb200_check_result* results;       /* device-visible (mapped host), same count as check_jobs */
+} tb200_loadgen_config;
+
+typedef struct tb200_loadgen_stats {
+  /* InferStat (reference common.h:93-114) over the window */
+  uint64_t completed_request_count;
+  uint64_t failed_request_count;
+  uint64_t cumulative_total_request_time_ns; /* REQUEST_START -> REQUEST_END */
+  uint64_t cumulative_send_time_ns;          /* SEND_START -> SEND_END       */
+  uint64_t cumulative_receive_time_ns;       /* RECV_START -> RECV_END       */
+  /* latency distribution over the window (ns) */
+  uint64_t p50_ns, p90_ns, p95_ns, p99_ns, min_ns, max_ns;
+  double window_seconds;
+  /* device thread */
+  uint64_t device_batches;    /* fill(+check) passes                                  */
+  uint64_t device_slots;      /* slots served by them (device_slots / device_batches = */
+                              /* requests covered per launch)                          */
+  uint64_t nonfinite_outputs; /* from TOP1 checks                                      */
+  uint64_t check_mismatches;  /* from EQUAL / ADDSUB checks                            */
+} tb200_loadgen_stats;
+
+int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out);
+int tb200_loadgen_start(tb200_loadgen* lg);
+/* sleep `seconds`, then report and reset the statistics gathered meanwhile */
+int tb200_loadgen_window(tb200_loadgen* lg, double seconds, tb200_loadgen_stats* out);
+int tb200_loadgen_stop(tb200_loadgen* lg);
+int tb200_loadgen_destroy(tb200_loadgen* lg);
+
+/* A canned-response HTTP server for measuring the generator itself (every POST gets
+ * `200` + the given body; GET /v2/health/* gets 200).  Test/bench tooling: it does not
+ * open shared memory.  Returns the bound port through *port (pass 0 to pick one). */
+typedef struct tb200_stub_server tb200_stub_server;
+int tb200_stub_server_start(const char* host, int* port, const char* response_body,
+                            tb200_stub_server** out);
+int tb200_stub_server_stop(tb200_stub_server* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TB200_LOADGEN_H_ */

@@ -1,0 +1,105 @@
+"""Turn the ncu captures in gpurun_out/ into the tracked summaries under profiles/.
+
+  python scripts/summarize_profiles.py r01
+writes profiles/<tag>_launches.csv (kernel, count, avg us, share of the step),
+profiles/<tag>_<kernel>_full.txt (key metrics of the --set full capture) and copies the
+bench JSON lines.  Needs the ncu CLI (reads .ncu-rep files, no GPU).
+"""
+
+import collections
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+DST = os.path.join(ROOT, "profiles")
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_op_write.sum", "lts__t_sectors_op_read.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "sm__cycles_elapsed.avg", "sm__cycles_active.avg",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers",
+    "launch__shared_mem_per_block_static", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+]
+
+
+def launches(tag):
+    path = os.path.join(OUT, "launches.csv")
+    if not os.path.exists(path):
+        return
+    rows = list(csv.reader(open(path)))
+    start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[start]
+    ki, mi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[start + 1:]:
+        if len(r) > mi:
+            try:
+                agg.setdefault(r[ki].split("(")[0], []).append(float(r[mi].replace(",", "")))
+            except ValueError:
+                pass
+    total = sum(sum(v) for v in agg.values())
+    with open(os.path.join(DST, tag + "_launches.csv"), "w") as fh:
+        fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 24 --warmup 3\n")
+        fh.write("# per-launch times under ncu are cold-cache and serialised: compare the SHARES\n")
+        fh.write("kernel,launches,avg_us,min_us,max_us,share_pct\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            fh.write("%s,%d,%.2f,%.2f,%.2f,%.1f\n" % (k, len(v), sum(v) / len(v) / 1e3, min(v) / 1e3, max(v) / 1e3, 100 * sum(v) / total))
+
+
+def full(tag, rep, label):
+    path = os.path.join(OUT, rep)
+    if not os.path.exists(path):
+        return
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    if len(rows) < 3:
+        return
+    hdr, units = rows[0], rows[1]
+    with open(os.path.join(DST, "%s_%s_full.txt" % (tag, label)), "w") as fh:
+        fh.write("# ncu --set full --clock-control none --import-source on (from gpurun_out/%s)\n" % rep)
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")]
+            fh.write("\n== %s\n" % name)
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    fh.write("%-85s %s %s\n" % (k, r[i], units[i]))
+            rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", "")) if "dram__bytes_read.sum" in hdr else 0
+            fh.write("# traffic = dram read + write per launch, unit as above\n")
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    os.makedirs(DST, exist_ok=True)
+    launches(tag)
+    full(tag, "prof_fill.ncu-rep", "fill_kernel")
+    full(tag, "prof_pack.ncu-rep", "pack_image_kernel")
+    full(tag, "prof_check.ncu-rep", "check_kernel")
+    for src, dst in (("bench.json", "bench_b200.json"), ("bench_ref.json", "bench_reference.json"),
+                     ("fill_sweep.txt", "fill_sweep.txt"), ("store_bench.txt", "store_bench.txt"),
+                     ("nvidia_smi.txt", "nvidia_smi.txt")):
+        p = os.path.join(OUT, src)
+        if os.path.exists(p) and os.path.getsize(p):
+            shutil.copy(p, os.path.join(DST, tag + "_" + dst))
+    print(sorted(os.listdir(DST)))
+
+
+if __name__ == "__main__":
+    main()

@@ -386,9 +386,10 @@ def test_graph_with_folded_bump_and_parallel_validate(gpu_ops):
     launches0 = gpu_ops.ctx.launch_count
     gpu_ops.graph_begin()
     gpu_ops.fork()
-    gpu_ops.check(checks, res.device_ptr)
+    gpu_ops.check(checks, res.device_ptr)           # side branch
+    gpu_ops.select(False)
+    gpu_ops.fill_epoch(jobs, seed=99, bump=slots)   # main branch, concurrent with the check
     gpu_ops.join()
-    gpu_ops.fill_epoch(jobs, seed=99, bump=slots)
     g = gpu_ops.graph_end()
     assert gpu_ops.ctx.launch_count == launches0  # captured, not run
     for it in range(4):

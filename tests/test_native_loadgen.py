@@ -1,0 +1,84 @@
+"""The native load generator's transport on the CPU box: closed loop against the
+canned-response server and against the Python mock server (system shm, no device work)."""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+from client_b200 import _native
+from client_b200._native_loadgen import LoadgenConfig, LoadgenStats
+from client_b200.perf.native import StubServer, frame_http_request
+from test_loopback import start_server
+
+
+def _run(host, port, reqs, seconds=0.5):
+    lib = _native.load()
+    n = len(reqs)
+    bufs = [ctypes.create_string_buffer(r, len(r)) for r in reqs]
+    cfg = LoadgenConfig()
+    cfg.host, cfg.port, cfg.concurrency = host.encode(), port, n
+    cfg.requests = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
+    cfg.request_sizes = (ctypes.c_uint64 * n)(*[len(r) for r in reqs])
+    h = ctypes.c_void_p()
+    _native.check(lib.tb200_loadgen_create(ctypes.byref(cfg), ctypes.byref(h)))
+    _native.check(lib.tb200_loadgen_start(h))
+    st = LoadgenStats()
+    _native.check(lib.tb200_loadgen_window(h, 0.2, ctypes.byref(st)))  # warm-up window
+    _native.check(lib.tb200_loadgen_window(h, seconds, ctypes.byref(st)))
+    lib.tb200_loadgen_stop(h)
+    lib.tb200_loadgen_destroy(h)
+    return st
+
+
+def test_closed_loop_against_stub_server():
+    srv = StubServer()
+    try:
+        body = b'{"inputs":[{"name":"INPUT0","shape":[1,16],"datatype":"INT32","parameters":{"shared_memory_region":"r","shared_memory_byte_size":64}}]}'
+        req = frame_http_request(srv.host, srv.port, "v2/models/simple/infer", body, None)
+        st = _run(srv.host, srv.port, [req] * 4)
+        assert st.failed_request_count == 0 and st.completed_request_count > 200
+        assert 0 < st.min_ns <= st.p50_ns <= st.p99_ns <= st.max_ns
+        avg = st.cumulative_total_request_time_ns / st.completed_request_count
+        assert st.cumulative_send_time_ns + st.cumulative_receive_time_ns <= st.cumulative_total_request_time_ns
+        assert abs(st.completed_request_count / st.window_seconds - 4 / (avg * 1e-9)) / (4 / (avg * 1e-9)) < 0.5  # Little's law, roughly
+    finally:
+        srv.stop()
+
+
+def test_closed_loop_against_mock_server_system_shm():
+    """Requests that only name system-shm regions; the mock server computes add/sub."""
+    import client_b200.http as httpclient
+    import client_b200.utils.shared_memory as shm
+
+    proc, http_port, _ = start_server()
+    try:
+        a = np.arange(16, dtype=np.int32)
+        b = np.ones(16, dtype=np.int32)
+        ip = shm.create_shared_memory_region("lg_in", "/tb200_lg_in", 128)
+        op = shm.create_shared_memory_region("lg_out", "/tb200_lg_out", 128)
+        shm.set_shared_memory_region(ip, [a, b])
+        with httpclient.InferenceServerClient("127.0.0.1:%d" % http_port) as client:
+            client.register_system_shared_memory("lg_in", "/tb200_lg_in", 128)
+            client.register_system_shared_memory("lg_out", "/tb200_lg_out", 128)
+            inputs = [httpclient.InferInput("INPUT0", [1, 16], "INT32").set_shared_memory("lg_in", 64),
+                      httpclient.InferInput("INPUT1", [1, 16], "INT32").set_shared_memory("lg_in", 64, offset=64)]
+            outputs = [httpclient.InferRequestedOutput("OUTPUT0"), httpclient.InferRequestedOutput("OUTPUT1")]
+            outputs[0].set_shared_memory("lg_out", 64)
+            outputs[1].set_shared_memory("lg_out", 64, offset=64)
+            body, js = client.generate_request_body(inputs, outputs=outputs)
+            req = frame_http_request("127.0.0.1", http_port, "v2/models/simple/infer", body, js)
+            st = _run("127.0.0.1", http_port, [req, req], seconds=0.5)
+            assert st.failed_request_count == 0 and st.completed_request_count > 10
+            got = shm.get_contents_as_numpy(op, np.int32, [2, 16])
+            assert np.array_equal(got[0], a + b) and np.array_equal(got[1], a - b)
+            del got
+            bad = frame_http_request("127.0.0.1", http_port, "v2/models/nope/infer", body, js)
+            st = _run("127.0.0.1", http_port, [bad], seconds=0.2)
+            assert st.completed_request_count == 0 and st.failed_request_count > 0
+            client.unregister_system_shared_memory()
+        shm.destroy_shared_memory_region(ip)
+        shm.destroy_shared_memory_region(op)
+    finally:
+        proc.terminate()
+        proc.wait(10)
