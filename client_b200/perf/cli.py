@@ -60,6 +60,8 @@ def build_parser():
     ap.add_argument("--device-id", type=int, default=0)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--no-validate", action="store_true")
+    ap.add_argument("--engine", default="python", choices=["python", "native"],
+                    help="python: threads over the drop-in clients; native: libtb200's C++ workers (HTTP, sync)")
     ap.add_argument("--json", action="store_true")
     return ap
 
@@ -116,6 +118,26 @@ def run_instance(args, device_id, prefix, out_queue=None, staging_factory=None):
                           args.random_seed + 1000003 * device_id, token_range, name_prefix="%s_c%d" % (prefix, level),
                           staging=staging_factory() if staging_factory else None)
         slotset.register(control)
+        if args.engine == "native":
+            if protocol != "http" or args.streaming:
+                raise SystemExit("--engine native drives HTTP synchronous requests only")
+            from .native import NativeLoadGenerator
+
+            gen = NativeLoadGenerator(url, args.model_name, args.model_version, slotset, level,
+                                      regenerate=args.input_data_mode == "per-request", validate=not args.no_validate)
+            gen.start()
+            try:
+                res = measure_native(gen, args.measurement_interval, args.stability_percentage, args.max_trials, args.percentile)
+            finally:
+                gen.stop()
+                slotset.unregister(control)
+                slotset.close()
+            res.update(concurrency=level, device=device_id, errors=[], input_bytes=slotset.in_bytes, engine="native",
+                       launches_per_request=(2.0 * res["device_batches"] / max(1, res["device_slots"])) if res.get("device_batches") else 0.0)
+            rows.append(res)
+            if out_queue is None:
+                _report(args, res)
+            continue
         mgr = ConcurrencyManager(make_client, protocol, args.model_name, args.model_version, slotset, level,
                                  per_request_data=args.input_data_mode == "per-request", validate=not args.no_validate,
                                  streaming=args.streaming, request_parameters=params or None)
@@ -136,6 +158,33 @@ def run_instance(args, device_id, prefix, out_queue=None, staging_factory=None):
     if out_queue is not None:
         out_queue.put(rows)
     return rows
+
+
+def measure_native(gen, interval_ms, stability_pct, max_trials, percentile, min_windows=3):
+    """Same window / stability rule as loadgen.measure, over the native generator."""
+    gen.window(0.2)  # discard the ramp-up
+    windows = []
+    for _ in range(max_trials):
+        w = gen.window(interval_ms / 1e3)
+        w["latency_us"] = w["p%d_us" % percentile] if percentile in (50, 90, 95, 99) else w["avg_us"]
+        windows.append(w)
+        if len(windows) >= min_windows:
+            last = windows[-min_windows:]
+            thr = [x["throughput"] for x in last]
+            lat = [x["latency_us"] for x in last]
+            if min(thr) > 0 and (max(thr) - min(thr)) / max(thr) <= stability_pct / 100.0 and \
+                    (max(lat) == 0 or (max(lat) - min(lat)) / max(lat) <= stability_pct / 100.0):
+                break
+    last = windows[-min_windows:] if len(windows) >= min_windows else windows
+    merged = dict(last[-1])
+    merged["throughput"] = sum(x["throughput"] for x in last) / len(last)
+    merged["count"] = sum(x["count"] for x in last)
+    merged["failed"] = sum(x["failed"] for x in last)
+    merged["nonfinite"] = sum(x["nonfinite"] for x in last)
+    merged["device_batches"] = sum(x["device_batches"] for x in last)
+    merged["device_slots"] = sum(x["device_slots"] for x in last)
+    merged["windows"] = len(windows)
+    return merged
 
 
 def _report(args, res):

@@ -39,3 +39,35 @@ def test_llama_stream_ttft(server):
     rows = cli.main(["-m", "llama3_8b", "-u", server["grpc"], "-i", "grpc", "--streaming", "--shape", "input_ids:1,4096",
                      "--concurrency-range", "2", "-p", "300", "-r", "3", "--json"])
     assert rows[0]["count"] > 2 and "ttft_p50_us" in rows[0]
+
+
+def test_native_engine_cuda_shm(server):
+    """The C++ load generator: worker threads send pre-formed requests that name the
+    CUDA-IPC slots, the device thread validates and regenerates returned slots in batches."""
+    rows = cli.main(["-m", "densenet_onnx", "-u", server["http"], "--shared-memory", "cuda", "--engine", "native",
+                     "--concurrency-range", "4:8:2x", "-p", "300", "-r", "3", "--json"])
+    assert [r["concurrency"] for r in rows] == [4, 8]
+    for r in rows:
+        assert r["count"] > 5 and r["failed"] == 0 and r["nonfinite"] == 0 and r["device_slots"] >= r["count"] - 16, r
+
+
+def test_native_engine_wire_mode_and_stub_capacity(server):
+    rows = cli.main(["-m", "densenet_onnx", "-u", server["http"], "--shared-memory", "none", "--engine", "native",
+                     "--concurrency-range", "2", "-p", "300", "-r", "3", "--json"])
+    assert rows[0]["count"] > 3 and rows[0]["failed"] == 0
+    # pure generator capacity against the canned-response server (requests name regions only)
+    from client_b200.perf.loadgen import SlotSet, TensorSpec
+    from client_b200.perf.native import NativeLoadGenerator, StubServer
+
+    stub = StubServer()
+    try:
+        ss = SlotSet([TensorSpec("data_0", "FP32", [3, 224, 224])], [TensorSpec("fc6_1", "FP32", [1000])], 16, "cuda", 0, "random", 1, name_prefix="stubcap")
+        gen = NativeLoadGenerator(stub.url, "densenet_onnx", "", ss, 16, regenerate=True, validate=False)
+        gen.start()
+        gen.window(0.2)
+        w = gen.window(0.5)
+        gen.stop()
+        ss.close()
+        assert w["failed"] == 0 and w["throughput"] > 2000 and w["device_slots"] > 0, w
+    finally:
+        stub.stop()
