@@ -267,14 +267,18 @@ class Timer:
             pass
 
 
-_contexts = {}
+_contexts = threading.local()
 
 
 def default_context(device_id):
-    """Process-wide context per device (the analogue of the reference's
-    ``_dlpack_stream`` dict)."""
-    ctx = _contexts.get(device_id)
+    """Per-thread context per device (the analogue of the reference's ``_dlpack_stream``
+    dict, made thread-local so that the module-level shared memory functions can be
+    called from several threads)."""
+    table = getattr(_contexts, "table", None)
+    if table is None:
+        table = _contexts.table = {}
+    ctx = table.get(device_id)
     if ctx is None:
         ctx = Context(device_id)
-        _contexts[device_id] = ctx
+        table[device_id] = ctx
     return ctx

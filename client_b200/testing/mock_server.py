@@ -58,6 +58,7 @@ class _CudaRegions:
         self._regions = {}
         self._ctx = {}
         self._lock = threading.Lock()
+        self._io_lock = threading.Lock()
 
     def _native(self):
         from .. import _native
@@ -104,7 +105,8 @@ class _CudaRegions:
         if offset + nbytes > size:
             raise ServerError("shared memory region '%s' is too small" % name)
         out = np.empty(nbytes, np.uint8)
-        nat.check(nat.load().tb200_region_read_host(self._ctx[dev].handle, h, offset, out.ctypes.data, nbytes))
+        with self._io_lock:  # a context (stream + staging ring) serves one thread at a time
+            nat.check(nat.load().tb200_region_read_host(self._ctx[dev].handle, h, offset, out.ctypes.data, nbytes))
         return out.tobytes()
 
     def write(self, name, offset, data):
@@ -113,7 +115,8 @@ class _CudaRegions:
         if offset + len(data) > size:
             raise ServerError("shared memory region '%s' is too small for the output" % name)
         buf = np.frombuffer(data, np.uint8)
-        nat.check(nat.load().tb200_region_write_host(self._ctx[dev].handle, h, offset, buf.ctypes.data, len(data)))
+        with self._io_lock:
+            nat.check(nat.load().tb200_region_write_host(self._ctx[dev].handle, h, offset, buf.ctypes.data, len(data)))
 
 
 class _SystemRegions:
@@ -322,6 +325,16 @@ class MockCore:
 def _http_handler(core, verbose=False):
     class Handler(BaseHTTPRequestHandler):
         protocol_version = "HTTP/1.1"
+        wbufsize = 1 << 16  # headers + body leave in one segment (no Nagle / delayed-ACK stall)
+
+        def setup(self):
+            super().setup()
+            try:
+                import socket
+
+                self.connection.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+            except OSError:
+                pass
 
         def log_message(self, fmt, *args):
             if verbose:
@@ -337,6 +350,7 @@ def _http_handler(core, verbose=False):
             self.end_headers()
             if body:
                 self.wfile.write(body)
+            self.wfile.flush()
 
         def _json(self, obj, status=200):
             self._send(status, json.dumps(obj, separators=(",", ":")).encode())
