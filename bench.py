@@ -204,9 +204,7 @@ def run_b200(args):
     bad = 0
     for i in range(e2e_steps):
         s = i % SETS
-        ops.fill(fill_jobs[s], seed=SEED, epoch=i * SLOTS)
-        ops.check(check_jobs[s], results.device_ptr + s * SLOTS * 32)
-        ops.sync()
+        ops.step(fill_jobs[s], check_jobs[s], results.device_ptr + s * SLOTS * 32, seed=SEED, epoch=i * SLOTS)
         bad += int(res["mismatches"][s * SLOTS:(s + 1) * SLOTS].sum())
     timer.stop()
     ops.sync()
@@ -252,6 +250,37 @@ def run_b200(args):
     ops.sync()
     pack_ms = timer.elapsed_ms() / (50 * SETS)
     pack_bytes = SLOTS * (224 * 224 * 3) * (1 + 4)
+    # --- C3 extras (BASELINE configs[2]): one FP16[128,3,224,224] request = 38,535,168 B
+    c3_fill = [[make_fill_job(in_regions[s]._base_addr, SLOTS * IN_BYTES, "FP16", stream_id=stream0 + 7000 + s)] for s in range(SETS)]
+    ops.graph_begin()
+    for s in range(SETS):
+        ops.fill_epoch(c3_fill[s], seed=SEED)
+    gc3 = ops.graph_end()
+    for _ in range(3):
+        gc3.launch()
+    ops.sync()
+    timer.start()
+    for _ in range(50):
+        gc3.launch()
+    timer.stop()
+    ops.sync()
+    c3_fill_ms = timer.elapsed_ms() / (50 * SETS)
+    c3_src = DeviceBuffer(local, 128 * 224 * 224 * 3)
+    ops.fill([make_fill_job(c3_src.ptr, 128 * 224 * 224 * 3, "UINT8", stream_id=stream0 + 7100)], seed=SEED)
+    ops.graph_begin()
+    for s in range(SETS):
+        ops.pack_image(in_regions[s]._base_addr, "FP16", "NCHW", c3_src.ptr, 128, 224, 224, 3, "INCEPTION")
+    gc3p = ops.graph_end()
+    for _ in range(3):
+        gc3p.launch()
+    ops.sync()
+    timer.start()
+    for _ in range(50):
+        gc3p.launch()
+    timer.stop()
+    ops.sync()
+    c3_pack_ms = timer.elapsed_ms() / (50 * SETS)
+    c3_pack_bytes = 128 * 224 * 224 * 3 * (1 + 2)
     clocks = sampler.stop()
 
     line = {
@@ -265,7 +294,7 @@ def run_b200(args):
         "input_pack_gbps": round(world * SLOTS * IN_BYTES * steps / (ms_value / 1e3) / 1e9, 1),
         "e2e": {"value": round(e2e_value, 1), "unit": "infer/s", "h2d_bytes_per_step": h2d_step,
                 "d2h_bytes_per_step": d2h_step, "steps": e2e_steps,
-                "what": "client_b200.device API per step: job tables H2D from pinned memory, fill + validate, results D2H, sync"},
+                "what": "client_b200.device.DeviceOps.step() per step: job tables H2D from pinned memory, fill || validate, results D2H into mapped host memory, sync, host reads the 64 results"},
         "e2e_host_images": {"value": round(img_value, 1), "unit": "infer/s", "h2d_bytes_per_step": SLOTS * 224 * 224 * 3,
                             "d2h_bytes_per_step": d2h_step, "steps": img_steps,
                             "what": "64 uint8 HWC host images (pinned) -> H2D -> INCEPTION cast + CHW pack into the IPC slots -> validate"},
@@ -278,6 +307,12 @@ def run_b200(args):
                           "achieved": round(pack_bytes / (pack_ms / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                           "frac": round(pack_bytes / (pack_ms / 1e3) / 1e9 / peak, 4),
                           "algorithmic_bytes_per_launch": pack_bytes, "ms_per_launch": round(pack_ms, 6)},
+        "c3_resnet50_b128_fp16": {
+            "fill": {"achieved_gbps": round(SLOTS * IN_BYTES / (c3_fill_ms / 1e3) / 1e9, 1), "ms_per_request": round(c3_fill_ms, 6),
+                     "frac": round(SLOTS * IN_BYTES / (c3_fill_ms / 1e3) / 1e9 / peak, 4), "algorithmic_bytes": SLOTS * IN_BYTES},
+            "pack_u8_hwc_to_fp16_chw": {"achieved_gbps": round(c3_pack_bytes / (c3_pack_ms / 1e3) / 1e9, 1), "ms_per_request": round(c3_pack_ms, 6),
+                                         "frac": round(c3_pack_bytes / (c3_pack_ms / 1e3) / 1e9 / peak, 4), "algorithmic_bytes": c3_pack_bytes},
+        },
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

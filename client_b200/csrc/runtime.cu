@@ -1004,6 +1004,31 @@ int tb200_graph_destroy(tb200_graph* gr) {
   return TB200_OK;
 }
 
+int tb200_step_sync(tb200_ctx* ctx, const tb200_fill_job* fill_jobs, int nfill, uint64_t seed,
+                    uint64_t stream_epoch, const tb200_check_job* check_jobs, int ncheck,
+                    tb200_check_result* results) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  if (ctx->forked || ctx->capture != nullptr) return fail(TB200_ERR_STATE, "step inside a fork / capture");
+  int rc = TB200_OK;
+  if (ncheck > 0) {
+    // validation of the previous responses runs beside the generation of the next inputs
+    rc = tb200_ctx_fork(ctx);
+    if (rc == TB200_OK) rc = tb200_check_async(ctx, check_jobs, ncheck, results);
+    if (rc == TB200_OK) rc = tb200_ctx_select(ctx, 0);
+    if (rc != TB200_OK) {
+      if (ctx->forked) tb200_ctx_join(ctx);
+      return rc;
+    }
+  }
+  rc = tb200_fill_async(ctx, fill_jobs, nfill, seed, stream_epoch);
+  if (ctx->forked) {
+    const int rj = tb200_ctx_join(ctx);
+    if (rc == TB200_OK) rc = rj;
+  }
+  if (rc != TB200_OK) return rc;
+  return tb200_ctx_sync(ctx);
+}
+
 int tb200_tune(const char* key, int value) {
   if (key != nullptr && strcmp(key, "fill_variant") == 0) {
     set_fill_variant(value);

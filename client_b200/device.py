@@ -286,6 +286,12 @@ class DeviceOps:
             self._res_buf = HostBuffer(4096)
         return self._res_buf
 
+    def step(self, fill_jobs, check_jobs, results_ptr, seed=0, epoch=0):
+        """One closed-loop step (tb200_step_sync): generate inputs || validate outputs, wait."""
+        fa, nf = self.job_array(fill_jobs, FillJob)
+        ca, nc = self.job_array(check_jobs, CheckJob)
+        _native.check(self._lib.tb200_step_sync(self._ctx.handle, fa, nf, int(seed), int(epoch), ca, nc, results_ptr))
+
     def l2_flush(self):
         _native.check(self._lib.tb200_l2_flush_async(self._ctx.handle))
 

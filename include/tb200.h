@@ -309,6 +309,13 @@ int tb200_ctx_epoch_bump_async(tb200_ctx* ctx, uint64_t delta);
 int tb200_fill_epoch_async(tb200_ctx* ctx, const tb200_fill_job* jobs,
                            int njobs, uint64_t seed, uint64_t bump);
 
+/* One closed-loop step in a single call: generate the inputs of `nfill` jobs, validate
+ * `ncheck` outputs, wait for both.  The results land in `results` (mapped host memory);
+ * the job tables are copied host->device from the pinned ring inside the call. */
+int tb200_step_sync(tb200_ctx* ctx, const tb200_fill_job* fill_jobs, int nfill, uint64_t seed,
+                    uint64_t stream_epoch, const tb200_check_job* check_jobs, int ncheck,
+                    tb200_check_result* results);
+
 /* experiment knobs (scripts/fill_sweep.py); key "fill_variant", 0 = default */
 int tb200_tune(const char* key, int value);
 

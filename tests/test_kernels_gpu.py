@@ -431,3 +431,24 @@ def test_fill_into_pinned_host_wire_buffer(gpu_ops):
         assert np.array_equal(host[(2 * s + 1) * per:(2 * s + 2) * per], cref.fill(per, "INT64", seed=3, stream=2 * s + 1, ilo=0, irange=2))
     ids = host[:per].view(np.int64)
     assert ids.min() >= 0 and ids.max() < 30522
+
+
+def test_step_sync_call(gpu_ops):
+    """tb200_step_sync: one call = generate inputs || validate outputs, both complete on return."""
+    from client_b200._native import CheckJob
+    from client_b200.device import DeviceBuffer, HostBuffer, make_fill_job, results_array
+
+    n = 602112
+    buf = DeviceBuffer(0, 2 * n)
+    logits = np.random.default_rng(8).standard_normal((2, 1000)).astype(np.float32)
+    outs = gpu_ops.upload(logits)
+    res = HostBuffer(64)
+    jobs = [make_fill_job(buf.ptr + k * n, n, "FP32", stream_id=k) for k in range(2)]
+    checks = [CheckJob(a=outs.ptr + k * 4000, nbytes=4000, kind=3) for k in range(2)]
+    gpu_ops.step(jobs, checks, res.device_ptr, seed=3, epoch=9)
+    r = results_array(res, 2)
+    assert [int(x) for x in r["argmax"]] == [int(np.argmax(row)) for row in logits]
+    got = gpu_ops.download(buf.ptr, 2 * n)
+    assert np.array_equal(got[n:], cref.fill(n, "FP32", seed=3, stream=1 + 9))
+    gpu_ops.step(jobs, [], res.device_ptr, seed=4)  # no validation this time
+    assert np.array_equal(gpu_ops.download(buf.ptr, n), cref.fill(n, "FP32", seed=4, stream=0))
