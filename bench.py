@@ -235,10 +235,13 @@ def run_b200(args):
     img_ms = (time.perf_counter() - t0) * 1e3
     img_value = world * SLOTS * img_steps / (rep.max(img_ms) / 1e3)
 
-    # --- pack kernel alone (device-resident uint8 source), C3(ii)-style R+W roofline
+    # --- pack kernel alone (device-resident uint8 sources, one per set so that neither the
+    #     sources nor the destinations of consecutive launches are L2 hits), R+W roofline
+    pack_src = [DeviceBuffer(local, SLOTS * 224 * 224 * 3) for _ in range(SETS)]
+    ops.fill([make_fill_job(b.ptr, SLOTS * 224 * 224 * 3, "UINT8", stream_id=stream0 + 7200 + i) for i, b in enumerate(pack_src)], seed=SEED)
     ops.graph_begin()
     for s in range(SETS):
-        ops.pack_image(in_regions[s]._base_addr, "FP32", "NCHW", staging.ptr, SLOTS, 224, 224, 3, "INCEPTION")
+        ops.pack_image(in_regions[s]._base_addr, "FP32", "NCHW", pack_src[s].ptr, SLOTS, 224, 224, 3, "INCEPTION")
     gpack = ops.graph_end()
     for _ in range(3):
         gpack.launch()
@@ -265,11 +268,11 @@ def run_b200(args):
     timer.stop()
     ops.sync()
     c3_fill_ms = timer.elapsed_ms() / (50 * SETS)
-    c3_src = DeviceBuffer(local, 128 * 224 * 224 * 3)
-    ops.fill([make_fill_job(c3_src.ptr, 128 * 224 * 224 * 3, "UINT8", stream_id=stream0 + 7100)], seed=SEED)
+    c3_src = [DeviceBuffer(local, 128 * 224 * 224 * 3) for _ in range(SETS)]
+    ops.fill([make_fill_job(b.ptr, 128 * 224 * 224 * 3, "UINT8", stream_id=stream0 + 7100 + i) for i, b in enumerate(c3_src)], seed=SEED)
     ops.graph_begin()
     for s in range(SETS):
-        ops.pack_image(in_regions[s]._base_addr, "FP16", "NCHW", c3_src.ptr, 128, 224, 224, 3, "INCEPTION")
+        ops.pack_image(in_regions[s]._base_addr, "FP16", "NCHW", c3_src[s].ptr, 128, 224, 224, 3, "INCEPTION")
     gc3p = ops.graph_end()
     for _ in range(3):
         gc3p.launch()
