@@ -232,7 +232,12 @@ struct FillParams {
 //   bf16: (x16 >> 9 ) * 2^-7       fp64: (x64 >> 12) * 2^-52
 // One shift/or + one add per value and no I2F conversions (those run on a slow pipe).
 TB200_HD float unit_f32(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+  // one funnel shift: ({0x7F : w} >> 9) = (w >> 9) | 0x3F800000
+  return __uint_as_float(__funnelshift_r(w, 0x7Fu, 9)) - 1.0f;
+#else
   return bits_f32(0x3F800000u | (w >> 9)) - 1.0f;
+#endif
 }
 TB200_HD float unit_f16(uint32_t x16) {  // 10 random bits, exactly representable in fp16
   return bits_f32(0x3F800000u | ((x16 >> 6) << 13)) - 1.0f;
@@ -244,7 +249,11 @@ TB200_HD double unit_f64(uint32_t lo, uint32_t hi) {  // 52 random bits
   const uint64_t x = (static_cast<uint64_t>(hi) << 32) | lo;
   const uint64_t bits = 0x3FF0000000000000ull | (x >> 12);
 #if defined(__CUDA_ARCH__)
-  return __longlong_as_double(static_cast<long long>(bits)) - 1.0;
+  // two funnel shifts build 0x3FF0000000000000 | (x >> 12)
+  const uint32_t blo = __funnelshift_r(lo, hi, 12);
+  const uint32_t bhi = __funnelshift_r(hi, 0x3FFu, 12);
+  (void)bits;
+  return __hiloint2double(static_cast<int>(bhi), static_cast<int>(blo)) - 1.0;
 #else
   union {
     uint64_t u;
