@@ -390,11 +390,12 @@ def run_reference(args):
     # the path is memory-bound: more processes are not always faster, so give the
     # reference its best process count (probed on untimed steps)
     best = None
-    for nproc in sorted({1, max(1, cores // 4), max(1, cores // 2), cores}):
-        per = split(min(nproc, SLOTS))
+    candidates = sorted({n for n in (1, 2, 4, 8, 16, 32, 64, cores // 4, cores // 2, cores) if 1 <= n <= min(cores, SLOTS)})
+    for nproc in candidates:
+        per = split(nproc)
         with mp.get_context("fork").Pool(len(per)) as pool:
-            run_steps(pool, per, 1, 0)
-            dt_probe = run_steps(pool, per, 2, 10)
+            run_steps(pool, per, 2, 0)
+            dt_probe = min(run_steps(pool, per, 3, 10), run_steps(pool, per, 3, 20))
         if best is None or dt_probe < best[0]:
             best = (dt_probe, per)
     per = best[1]
