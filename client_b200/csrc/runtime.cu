@@ -79,7 +79,7 @@ class CopyPool {
   int threads() const { return static_cast<int>(workers_.size()) + 1; }
   // split [0, n) into contiguous pieces and memcpy them in parallel
   void parallel_memcpy(void* dst, const void* src, size_t n) {
-    const int parts = (n < (1u << 20)) ? 1 : std::min<int>(threads(), static_cast<int>(n >> 19));
+    const int parts = (n < (1u << 20)) ? 1 : std::min<int>(threads(), static_cast<int>(n >> 18));
     if (parts <= 1) {
       memcpy(dst, src, n);
       return;
@@ -112,7 +112,7 @@ class CopyPool {
     if (const char* env = getenv("TB200_COPY_THREADS")) n = atoi(env);
     else {
       const unsigned hc = std::thread::hardware_concurrency();
-      n = static_cast<int>(std::max(1u, std::min(8u, hc / 2)));
+      n = static_cast<int>(std::max(1u, std::min(16u, hc / 2)));
     }
     n = std::max(1, std::min(n, 64));
     for (int i = 1; i < n; ++i) workers_.emplace_back([this] { run(); });
@@ -146,7 +146,8 @@ class CopyPool {
   bool stop_ = false;
 };
 
-constexpr size_t kStageBytes = 4u << 20;  // one pinned staging buffer
+constexpr size_t kStageBytes = 8u << 20;  // one pinned staging buffer
+constexpr size_t kDirectBytes = 64u << 10; // below this the driver's own staging is faster
 constexpr int kStageCount = 4;            // in flight per context
 constexpr size_t kJobSlotBytes = 64u << 10;
 constexpr int kJobSlots = 32;
@@ -273,6 +274,12 @@ int check_range(const tb200_region* r, uint64_t offset, uint64_t nbytes) {
 
 // host -> device through the pinned ring; does not synchronise at the end
 int staged_h2d(tb200_ctx* ctx, char* dst, const char* src, uint64_t nbytes) {
+  if (nbytes <= kDirectBytes) {
+    // small tensors (C1 / C4 / C5): the copy from pageable memory is staged by the driver
+    // before cudaMemcpyAsync returns; nothing to gain from our own ring
+    TB200_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->cur));
+    return TB200_OK;
+  }
   int rc = ensure_stage(ctx);
   if (rc != TB200_OK) return rc;
   uint64_t done = 0;
@@ -593,6 +600,11 @@ int tb200_region_read_host(tb200_ctx* ctx, const tb200_region* r, uint64_t offse
   if (rc != TB200_OK) return rc;
   if (nbytes == 0) return TB200_OK;
   DeviceGuard g(ctx->device);
+  if (nbytes <= kDirectBytes) {
+    TB200_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(r->base) + offset, nbytes, cudaMemcpyDeviceToHost, ctx->cur));
+    TB200_CUDA(cudaStreamSynchronize(ctx->cur));
+    return TB200_OK;
+  }
   rc = ensure_stage(ctx);
   if (rc != TB200_OK) return rc;
   const char* src = static_cast<const char*>(r->base) + offset;
