@@ -41,6 +41,10 @@ LOADGEN_SIGNATURES = {
     "tb200_loadgen_destroy": (c_int, [c_vp]),
     "tb200_stub_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "tb200_stub_server_stop": (c_int, [c_vp]),
+    "tb200_mock_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_vp)]),
+    "tb200_mock_server_requests": (ctypes.c_uint64, [c_vp]),
+    "tb200_mock_server_batches": (ctypes.c_uint64, [c_vp]),
+    "tb200_mock_server_stop": (c_int, [c_vp]),
 }
 
 

@@ -240,32 +240,38 @@ void device_main(tb200_loadgen* lg) {
     lg->returned.drain(batch);
     if (lg->ctx != nullptr) {
       uint64_t bad = 0, mism = 0;
-      if (lg->check_per_slot > 0) {
-        checks.clear();
+      const bool do_check = lg->check_per_slot > 0;
+      const bool do_fill = lg->regenerate && lg->fill_per_slot > 0;
+      checks.clear();
+      fills.clear();
+      if (do_check) {
         for (int s : batch) {
           for (int k = 0; k < lg->check_per_slot; ++k) checks.push_back(lg->check_jobs[s * lg->check_per_slot + k]);
         }
-        if (tb200_check_async(lg->ctx, checks.data(), static_cast<int>(checks.size()), lg->results) != 0 ||
-            tb200_ctx_sync(lg->ctx) != 0) {
-          std::lock_guard<std::mutex> lk(lg->dev_mu);
-          lg->error = tb200_last_error();
-        } else {
-          for (size_t k = 0; k < checks.size(); ++k) {
-            if (checks[k].kind == TB200_CHECK_TOP1) bad += lg->results[k].mismatches;
-            else if (checks[k].kind != TB200_CHECK_SUM) mism += lg->results[k].mismatches;
-          }
-        }
       }
-      if (lg->regenerate && lg->fill_per_slot > 0) {
-        fills.clear();
+      if (do_fill) {
         for (int s : batch) {
           for (int k = 0; k < lg->fill_per_slot; ++k) fills.push_back(lg->fill_jobs[s * lg->fill_per_slot + k]);
         }
         lg->epoch += 1ull << 20;  // fresh Philox streams for every generation
-        if (tb200_fill_async(lg->ctx, fills.data(), static_cast<int>(fills.size()), lg->seed, lg->epoch) != 0 ||
-            tb200_ctx_sync(lg->ctx) != 0) {
-          std::lock_guard<std::mutex> lk(lg->dev_mu);
-          lg->error = tb200_last_error();
+      }
+      // validation of the returned outputs and generation of the next inputs run as
+      // parallel branches under ONE synchronisation (tb200_step_sync)
+      int rc = TB200_OK;
+      if (do_fill) {
+        rc = tb200_step_sync(lg->ctx, fills.data(), static_cast<int>(fills.size()), lg->seed, lg->epoch,
+                             checks.data(), static_cast<int>(checks.size()), lg->results);
+      } else if (do_check) {
+        rc = tb200_check_async(lg->ctx, checks.data(), static_cast<int>(checks.size()), lg->results);
+        if (rc == TB200_OK) rc = tb200_ctx_sync(lg->ctx);
+      }
+      if (rc != TB200_OK) {
+        std::lock_guard<std::mutex> lk(lg->dev_mu);
+        lg->error = tb200_last_error();
+      } else {
+        for (size_t k = 0; k < checks.size(); ++k) {
+          if (checks[k].kind == TB200_CHECK_TOP1) bad += lg->results[k].mismatches;
+          else if (checks[k].kind != TB200_CHECK_SUM) mism += lg->results[k].mismatches;
         }
       }
       std::lock_guard<std::mutex> lk(lg->dev_mu);

@@ -81,6 +81,18 @@ int tb200_stub_server_start(const char* host, int* port, const char* response_bo
                             tb200_stub_server** out);
 int tb200_stub_server_stop(tb200_stub_server* s);
 
+/* A native KServe-v2 stand-in server for loopback load runs over CUDA shared memory
+ * (csrc/mock_server.cu; tooling -- the reference has no server).  It opens
+ * the client's cudaIpcMemHandle_t from the register call (protocol of
+ * src/python/library/tritonclient/http/_client.py:1153-1207), so it must live in ANOTHER
+ * process than the client, and runs models `densenet_onnx` / `simple` as CUDA kernels
+ * on the mapped regions. */
+typedef struct tb200_mock_server tb200_mock_server;
+int tb200_mock_server_start(const char* host, int* port, int device_id, tb200_mock_server** out);
+uint64_t tb200_mock_server_requests(tb200_mock_server* s);
+uint64_t tb200_mock_server_batches(tb200_mock_server* s); /* kernel launches that served them */
+int tb200_mock_server_stop(tb200_mock_server* s);
+
 #ifdef __cplusplus
 }
 #endif
