@@ -127,6 +127,15 @@ def set_shared_memory_region(cuda_shm_handle, input_values):
                 "input_values must be specified as a list/tuple of numpy arrays"
             )
     try:
+        if len(input_values) == 1 and input_values[0].dtype != np.object_ and input_values[0].flags.c_contiguous:
+            # one plain array: no gather table
+            arr = input_values[0]
+            _native.check(
+                _native.load().tb200_region_write_host(
+                    _ctx(cuda_shm_handle._device_id).handle, cuda_shm_handle._native, 0, arr.ctypes.data, arr.nbytes
+                )
+            )
+            return
         keep, ptrs, sizes = _host_chunks(input_values)
         n = len(ptrs)
         c_ptrs = (ctypes.c_void_p * max(n, 1))(*ptrs)
