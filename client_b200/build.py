@@ -63,5 +63,24 @@ def build_native(force=False, verbose=False):
     return LIB
 
 
+CLIENT_LIB = os.path.join(LIBDIR, "libtb200client.so")
+
+
+def build_cpp_client(force=False, verbose=False):
+    """The C++ front end (client_b200/cpp): plain g++, linked against libtb200.so."""
+    cpp = os.path.join(HERE, "cpp")
+    src = os.path.join(cpp, "tb200_client.cc")
+    deps = [src, os.path.join(cpp, "tb200_client.h"), os.path.join(cpp, "json.h"), os.path.join(ROOT, "include", "tb200.h"), LIB]
+    if force or _newer(CLIENT_LIB, deps):
+        gxx = shutil.which("g++") or "g++"
+        cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", CLIENT_LIB, src,
+               "-L" + LIBDIR, "-ltb200", "-Wl,-rpath,$ORIGIN", "-lpthread"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    return CLIENT_LIB
+
+
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose=True))
+    print(build_cpp_client(force="--force" in sys.argv, verbose=True))
