@@ -75,6 +75,19 @@ class CheckResult(ctypes.Structure):
     ]
 
 
+class TopkJob(ctypes.Structure):
+    """tb200_topk_job (24 bytes)."""
+
+    _fields_ = [("src", c_u64), ("count", c_u64), ("dtype", c_u32), ("pad", c_u32)]
+
+
+class TopkEntry(ctypes.Structure):
+    """tb200_topk_entry."""
+
+    _fields_ = [("value", ctypes.c_float), ("index", c_u32)]
+
+
+assert ctypes.sizeof(TopkJob) == 24 and ctypes.sizeof(TopkEntry) == 8
 assert ctypes.sizeof(FillJob) == 64
 assert ctypes.sizeof(CopyJob) == 24
 assert ctypes.sizeof(CheckJob) == 48
@@ -129,6 +142,7 @@ SIGNATURES = {
     "tb200_pack_strided_async": (c_int, [c_vp, c_vp, c_vp, c_u32, c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "tb200_concat_async": (c_int, [c_vp, ctypes.POINTER(CopyJob), c_int]),
     "tb200_check_async": (c_int, [c_vp, ctypes.POINTER(CheckJob), c_int, c_vp]),
+    "tb200_topk_async": (c_int, [c_vp, ctypes.POINTER(TopkJob), c_int, c_int, c_vp]),
     "tb200_graph_begin": (c_int, [c_vp]),
     "tb200_graph_end": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "tb200_graph_launch": (c_int, [c_vp, c_vp]),

@@ -1039,6 +1039,72 @@ cudaError_t launch_check(const CheckLaunch& l, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// ---- top-k ---------------------------------------------------------------------------
+// One CTA per vector; pass r selects the best element strictly after pass r-1's pick in the
+// total order (value desc, index asc): composite = order_key(value) << 32 | ~index, larger
+// is better, NaN has key 0.  k passes over a vector that sits in L1/L2 after the first.
+__device__ __forceinline__ float topk_load(const void* src, uint32_t dtype, uint32_t i) {
+  if (dtype == TB200_FP32) return static_cast<const float*>(src)[i];
+  const uint16_t h = static_cast<const uint16_t*>(src)[i];
+  if (dtype == TB200_FP16) return f16_bits_to_f32(h);
+  return __uint_as_float(static_cast<uint32_t>(h) << 16);  // BF16
+}
+__device__ __forceinline__ unsigned long long topk_composite(float v, uint32_t i) {
+  uint32_t key = 0;
+  if (v == v) key = f32_order_key(v == 0.0f ? 0u : __float_as_uint(v));
+  return (static_cast<unsigned long long>(key) << 32) | (0xFFFFFFFFu - i);
+}
+
+__global__ void __launch_bounds__(256) topk_kernel(const tb200_topk_job* __restrict__ jobs, uint32_t k,
+                                                   tb200_topk_entry* __restrict__ out) {
+  __shared__ unsigned long long warp_best[8];
+  __shared__ unsigned long long picked;
+  const tb200_topk_job job = jobs[blockIdx.x];
+  const void* src = reinterpret_cast<const void*>(job.src);
+  const uint32_t n = static_cast<uint32_t>(job.count);
+  tb200_topk_entry* dst = out + static_cast<size_t>(blockIdx.x) * k;
+  unsigned long long prev = ~0ull;
+  for (uint32_t r = 0; r < k; ++r) {
+    unsigned long long best = 0;
+    if (prev != 0) {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long c = topk_composite(topk_load(src, job.dtype, i), i);
+        if (c < prev && c > best) best = c;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+      best = o > best ? o : best;
+    }
+    if ((threadIdx.x & 31) == 0) warp_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long b = warp_best[0];
+      for (int w = 1; w < 8; ++w) b = warp_best[w] > b ? warp_best[w] : b;
+      picked = b;
+      tb200_topk_entry e;
+      if (b != 0) {
+        e.index = 0xFFFFFFFFu - static_cast<uint32_t>(b);
+        e.value = topk_load(src, job.dtype, e.index);
+      } else {
+        e.index = 0xFFFFFFFFu;
+        e.value = 0.0f;
+      }
+      dst[r] = e;
+    }
+    __syncthreads();
+    prev = picked;  // rewritten only after the next pass's barrier
+  }
+  if (threadIdx.x == 0) __threadfence_system();  // out may live in mapped host memory
+}
+
+cudaError_t launch_topk(const tb200_topk_job* jobs, uint32_t njobs, uint32_t k, tb200_topk_entry* out, cudaStream_t s) {
+  if (njobs == 0) return cudaSuccess;
+  topk_kernel<<<njobs, 256, 0, s>>>(jobs, k, out);
+  return cudaGetLastError();
+}
+
 __global__ void epoch_bump_kernel(uint64_t* e, uint64_t delta) { *e += delta; }
 cudaError_t launch_epoch_bump(uint64_t* dev_epoch, uint64_t delta, cudaStream_t s) {
   epoch_bump_kernel<<<1, 1, 0, s>>>(dev_epoch, delta);

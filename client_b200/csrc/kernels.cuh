@@ -88,6 +88,8 @@ struct CheckLaunch {
 };
 cudaError_t launch_check(const CheckLaunch& l, cudaStream_t s);
 
+cudaError_t launch_topk(const tb200_topk_job* jobs, uint32_t njobs, uint32_t k, tb200_topk_entry* out, cudaStream_t s);
+
 cudaError_t launch_epoch_bump(uint64_t* dev_epoch, uint64_t delta, cudaStream_t s);
 
 }  // namespace tb200

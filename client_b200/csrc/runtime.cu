@@ -958,6 +958,32 @@ int tb200_check_async(tb200_ctx* ctx, const tb200_check_job* jobs, int njobs, tb
   return TB200_OK;
 }
 
+int tb200_topk_async(tb200_ctx* ctx, const tb200_topk_job* jobs, int njobs, int k, tb200_topk_entry* out) {
+  if (ctx == nullptr || njobs < 0 || (njobs > 0 && (jobs == nullptr || out == nullptr))) return fail(TB200_ERR_INVALID, "bad argument");
+  if (k < 1 || k > 1024) return fail(TB200_ERR_INVALID, "k must be in [1, 1024], got %d", k);
+  if (njobs == 0) return TB200_OK;
+  DeviceGuard g(ctx->device);
+  const int max_jobs = static_cast<int>(kJobSlotBytes / sizeof(tb200_topk_job));
+  for (int base = 0; base < njobs; base += max_jobs) {
+    const int n = std::min(max_jobs, njobs - base);
+    for (int i = 0; i < n; ++i) {
+      const tb200_topk_job& jb = jobs[base + i];
+      if (jb.dtype != TB200_FP32 && jb.dtype != TB200_FP16 && jb.dtype != TB200_BF16) {
+        return fail(TB200_ERR_INVALID, "job %d: top-k takes FP32, FP16 or BF16 vectors", base + i);
+      }
+      if (jb.count >= 0xFFFFFFFFull) return fail(TB200_ERR_INVALID, "job %d: vector too long", base + i);
+      if (jb.count != 0 && jb.src == 0) return fail(TB200_ERR_INVALID, "job %d: src is NULL", base + i);
+    }
+    const void* dev = nullptr;
+    int rc = upload(ctx, jobs + base, sizeof(tb200_topk_job) * n, &dev);
+    if (rc != TB200_OK) return rc;
+    TB200_CUDA(launch_topk(static_cast<const tb200_topk_job*>(dev), static_cast<uint32_t>(n), static_cast<uint32_t>(k),
+                           out + static_cast<size_t>(base) * k, ctx->cur));
+    ctx->launches += 1;
+  }
+  return TB200_OK;
+}
+
 // ---------------------------------------------------------------------------
 // graphs
 // ---------------------------------------------------------------------------

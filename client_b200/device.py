@@ -280,6 +280,26 @@ class DeviceOps:
         self.sync()
         return result_dict(res.array(np.uint8, ctypes.sizeof(CheckResult)).tobytes())
 
+    def topk(self, vectors, k):
+        """Blocking top-k of device vectors (tb200_topk_async).
+
+        vectors: [(device_address, element_count, "FP32" | "FP16" | "BF16"), ...];
+        returns (values float32 [n, k], indices uint32 [n, k]); slots past a vector's
+        length carry index 0xFFFFFFFF.  Only 8*k bytes per vector leave the device."""
+        from ._native import TopkJob
+
+        jobs = [TopkJob(src=int(a), count=int(n), dtype=_native.DTYPE_CODES[dt], pad=0) for a, n, dt in vectors]
+        arr, n = self.job_array(jobs, TopkJob)
+        k = int(k)
+        need = max(1, n * k * 8)
+        buf = getattr(self, "_topk_buf", None)
+        if buf is None or buf.nbytes < need:
+            buf = self._topk_buf = HostBuffer(max(need, 1 << 16))
+        _native.check(self._lib.tb200_topk_async(self._ctx.handle, arr, n, k, buf.device_ptr))
+        self.sync()
+        ent = buf.array(np.dtype([("value", "<f4"), ("index", "<u4")]), n * k).reshape(n, k)
+        return ent["value"].copy(), ent["index"].copy()
+
     def _result_buf(self):
         cur = getattr(self, "_res_buf", None)
         if cur is None:

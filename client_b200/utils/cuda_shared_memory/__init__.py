@@ -333,3 +333,45 @@ def check_shared_memory_region(cuda_shm_handle, kind="sum", byte_size=None, offs
     ops = DeviceOps(_ctx(cuda_shm_handle._device_id))
     b = expected._base_addr if expected is not None else 0
     return ops.check_one(kind, cuda_shm_handle._base_addr + offset, nbytes, b=b)
+
+
+def classify_shared_memory_region(cuda_shm_handle, datatype, shape, class_count, offset=0, labels=None):
+    """Top-``class_count`` classification of an output that stayed in CUDA shared memory.
+
+    The server refuses ``class_count`` on shared-memory outputs
+    (http/_requested_output.py:84-85), so this does on the device what the server's
+    classification extension does for inline outputs: the last axis of ``shape`` is the
+    class axis, every leading index is one batch item.  Returns a ``np.object_`` array of
+    shape ``shape[:-1] + [class_count]`` holding ``b"<value>:<index>[:<label>]"`` — the
+    form ``InferResult.as_numpy`` gives for a classification output and
+    src/python/examples/image_client.py:196-216 parses.  Only 8 bytes per class leave the GPU.
+    """
+    from ...device import DeviceOps
+    from ... import _native as nat
+
+    if datatype not in ("FP32", "FP16", "BF16"):
+        raise CudaSharedMemoryException("classification needs an FP32, FP16 or BF16 tensor")
+    shape = [int(d) for d in shape]
+    classes = shape[-1]
+    batch = int(np.prod(shape[:-1])) if len(shape) > 1 else 1
+    es = nat.DTYPE_SIZES[datatype]
+    if offset + batch * classes * es > cuda_shm_handle._byte_size:
+        raise CudaSharedMemoryException(
+            "The size of the shared memory region is insufficient to provide numpy array with requested size"
+        )
+    ops = DeviceOps(_ctx(cuda_shm_handle._device_id))
+    base = cuda_shm_handle._base_addr + offset
+    values, indices = ops.topk([(base + i * classes * es, classes, datatype) for i in range(batch)], class_count)
+    out = np.empty((batch, class_count), dtype=np.object_)
+    for i in range(batch):
+        for j in range(class_count):
+            idx = int(indices[i, j])
+            if idx == 0xFFFFFFFF:
+                out[i, j] = b""
+                continue
+            text = "%f:%d" % (float(values[i, j]), idx)
+            if labels is not None:
+                text += ":" + str(labels[idx])
+            out[i, j] = text.encode()
+    return out.reshape(shape[:-1] + [class_count])
+

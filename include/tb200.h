@@ -290,6 +290,31 @@ int tb200_check_async(tb200_ctx* ctx, const tb200_check_job* jobs, int njobs,
                       tb200_check_result* results);
 
 /* ------------------------------------------------------------------------
+ * Kernel 3b: classification of outputs that stay in shared memory.  The server refuses
+ * `classification` on a shared-memory output ("shared memory can't be set on
+ * classification output", PY/http/_requested_output.py:84-85), so the examples'
+ * top-k post-processing (src/python/examples/image_client.py:196-216) would need the
+ * whole tensor on the host; here only k (value, index) pairs per tensor leave the device.
+ * Order: value descending, lower index first on ties, -0.0 == +0.0, NaN after every
+ * number (numpy.argsort(-x, kind="stable")).  Entries past `count` get index 0xFFFFFFFF.
+ * ---------------------------------------------------------------------- */
+typedef struct tb200_topk_job {
+  uint64_t src;    /* device address of the vector                          */
+  uint64_t count;  /* elements (< 2^32 - 1)                                 */
+  uint32_t dtype;  /* TB200_FP32 | TB200_FP16 | TB200_BF16                  */
+  uint32_t pad;
+} tb200_topk_job;  /* 24 bytes */
+
+typedef struct tb200_topk_entry {
+  float value;
+  uint32_t index;
+} tb200_topk_entry;
+
+/* out: njobs * k entries, job-major (device or mapped-host memory); 1 <= k <= 1024 */
+int tb200_topk_async(tb200_ctx* ctx, const tb200_topk_job* jobs, int njobs, int k,
+                     tb200_topk_entry* out);
+
+/* ------------------------------------------------------------------------
  * Issue loop building blocks: capture any sequence of the *_async calls above
  * into a CUDA graph and replay it per measurement step / concurrency slot.
  * The concurrency loop itself (the absent perf_analyzer ConcurrencyManager /

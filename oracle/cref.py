@@ -33,6 +33,8 @@ def lib():
         L.oracle_addsub_mismatches.restype = u64
         L.oracle_top1.argtypes = [vp, u64, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(u64)]
         L.oracle_top1.restype = u32
+        L.oracle_topk.argtypes = [vp, u64, u32, vp, vp]
+        L.oracle_topk.restype = None
         L.oracle_marshal_http.argtypes = [vp, vp, u64, vp, vp, u64]
         L.oracle_marshal_http.restype = None
         _lib = L
@@ -89,3 +91,13 @@ def top1(values):
     mv, bad = ctypes.c_float(), ctypes.c_uint64()
     idx = lib().oracle_top1(v.ctypes.data, v.size, ctypes.byref(mv), ctypes.byref(bad))
     return int(idx), float(mv.value), int(bad.value)
+
+
+def topk(values, k):
+    """(values float32[k], indices uint32[k]) in numpy.argsort(-x, kind="stable") order."""
+    v = np.ascontiguousarray(values, dtype=np.float32).reshape(-1)
+    vals = np.zeros(k, dtype=np.float32)
+    idx = np.zeros(k, dtype=np.uint32)
+    lib().oracle_topk(v.ctypes.data, v.size, int(k), vals.ctypes.data, idx.ctypes.data)
+    return vals, idx
+

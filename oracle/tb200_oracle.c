@@ -250,6 +250,46 @@ uint32_t oracle_top1(const float* v, uint64_t n, float* max_value, uint64_t* non
   return best;
 }
 
+/* top-k in the order of numpy.argsort(-x, kind="stable"): value descending, lower index
+ * first on ties (-0.0 == +0.0), NaN after every number in index order.  Restates what
+ * the server's classification extension returns and image_client.postprocess
+ * (src/python/examples/image_client.py:196-216) consumes.  Selection sort, O(k*n). */
+void oracle_topk(const float* v, uint64_t n, uint32_t k, float* values, uint32_t* indices) {
+  uint64_t taken_prev = (uint64_t)-1; /* index of the previous pick */
+  int prev_nan = 0;
+  float prev_v = 0.0f;
+  for (uint32_t r = 0; r < k; ++r) {
+    uint64_t best = (uint64_t)-1;
+    for (uint64_t i = 0; i < n; ++i) {
+      /* candidate must come strictly after the previous pick in the order */
+      if (taken_prev != (uint64_t)-1) {
+        const int cn = isnan(v[i]);
+        int after;
+        if (prev_nan) after = cn && i > taken_prev;
+        else if (cn) after = 1;
+        else after = (v[i] < prev_v) || (v[i] == prev_v && i > taken_prev);
+        if (!after) continue;
+      }
+      if (best == (uint64_t)-1) { best = i; continue; }
+      const int bn = isnan(v[best]), cn = isnan(v[i]);
+      if (bn && !cn) best = i;
+      else if (!bn && !cn && v[i] > v[best]) best = i;
+    }
+    if (best == (uint64_t)-1) {
+      values[r] = 0.0f;
+      indices[r] = 0xFFFFFFFFu;
+      taken_prev = n; /* nothing comes after */
+      prev_nan = 1;
+      continue;
+    }
+    values[r] = v[best];
+    indices[r] = (uint32_t)best;
+    taken_prev = best;
+    prev_nan = isnan(v[best]);
+    prev_v = v[best];
+  }
+}
+
 /* ---- CPU baseline of the reference marshalling for bench.py (a1/a3 of SURVEY
  * section 8): ndarray.tobytes() then b"".join([json] + raw) == two memcpys.
  * PY/http/_infer_input.py:212 and PY/http/_utils.py:141-151. */

@@ -180,3 +180,77 @@ def test_device_side_producers(cudashm):
     ref = ((img.astype(np.float32) / 127.5) - 1).transpose(2, 0, 1)
     assert np.array_equal(got, ref)
     cudashm.destroy_shared_memory_region(h)
+
+
+@pytest.mark.parametrize("datatype", ["FP32", "FP16", "BF16"])
+def test_topk_on_device_matches_oracle(cudashm, datatype):
+    """tb200_topk_async vs the oracle (numpy stable argsort order): ties, signed zeros,
+    NaN, +-inf, k larger than the vector, several vectors per launch."""
+    from client_b200 import _native
+    from client_b200.device import DeviceOps
+    from client_b200.utils import serialize_bf16_tensor
+    from oracle import cref
+
+    rng = np.random.default_rng(5)
+    ops = DeviceOps(_native.default_context(0))
+    lengths = [1, 7, 1000, 1000, 4096, 33]
+    vecs = []
+    for n in lengths:
+        x = rng.standard_normal(n).astype(np.float32)
+        x[rng.random(n) < 0.2] = np.float32(0.5)      # ties
+        x[rng.random(n) < 0.05] = np.nan
+        x[rng.random(n) < 0.05] = -0.0
+        x[rng.random(n) < 0.02] = np.inf
+        x[rng.random(n) < 0.02] = -np.inf
+        if datatype == "FP16":
+            x = x.astype(np.float16).astype(np.float32)
+        elif datatype == "BF16":
+            x = (x.view(np.uint32) & 0xFFFF0000).view(np.float32)
+        vecs.append(x)
+    es = 4 if datatype == "FP32" else 2
+    h = cudashm.create_shared_memory_region("topk_data", sum(lengths) * 4, 0)
+    jobs, off, keep = [], 0, []
+    for x in vecs:
+        if datatype == "FP32":
+            raw = x
+        elif datatype == "FP16":
+            raw = x.astype(np.float16)
+        else:
+            raw = np.frombuffer(serialize_bf16_tensor(x).item(), dtype=np.uint16)
+        raw = np.ascontiguousarray(raw)
+        keep.append(raw)
+        ops.h2d(h._base_addr + off, raw.ctypes.data, raw.nbytes)
+        jobs.append((h._base_addr + off, x.size, datatype))
+        off += (x.size * es + 15) // 16 * 16
+    ops.sync()
+    for k in (1, 5, 40):
+        values, indices = ops.topk(jobs, k)
+        for j, x in enumerate(vecs):
+            want_v, want_i = cref.topk(x, k)
+            assert np.array_equal(indices[j], want_i), (datatype, k, j)
+            assert np.array_equal(values[j], want_v, equal_nan=True)
+    cudashm.destroy_shared_memory_region(h)
+
+
+def test_classify_shared_memory_region(cudashm):
+    """Client-side stand-in for the server's classification extension on outputs that stay
+    in shared memory: b"<value>:<index>[:<label>]" like InferResult.as_numpy returns."""
+    logits = np.zeros((2, 1000), dtype=np.float32)
+    logits[0, [3, 500, 999]] = [2.5, 9.25, 2.5]
+    logits[1, [7, 8]] = [-1.0, 4.0]
+    h = cudashm.create_shared_memory_region("cls_data", logits.nbytes, 0)
+    cudashm.set_shared_memory_region(h, [logits])
+    got = cudashm.classify_shared_memory_region(h, "FP32", [2, 1000], 3)
+    assert got.shape == (2, 3) and got.dtype == np.object_
+    assert [g.decode() for g in got[0]] == ["9.250000:500", "2.500000:3", "2.500000:999"]
+    assert [g.decode() for g in got[1]] == ["4.000000:8", "0.000000:0", "0.000000:1"]
+    labels = ["c%d" % i for i in range(1000)]
+    got = cudashm.classify_shared_memory_region(h, "FP32", [2, 1000], 1, labels=labels)
+    assert got[0, 0] == b"9.250000:500:c500"
+    cls = got[1, 0].decode().split(":")           # image_client.postprocess parsing
+    assert (float(cls[0]), int(cls[1]), cls[2]) == (4.0, 8, "c8")
+    with pytest.raises(cudashm.CudaSharedMemoryException):
+        cudashm.classify_shared_memory_region(h, "INT32", [2, 1000], 1)
+    with pytest.raises(cudashm.CudaSharedMemoryException):
+        cudashm.classify_shared_memory_region(h, "FP32", [3, 1000], 1)
+    cudashm.destroy_shared_memory_region(h)

@@ -217,3 +217,22 @@ def test_check_oracles():
     s, x = cref.checksum(np.frombuffer(b"\x01\x00\x00\x00\xff", np.uint8))
     assert (s, x) == (1 + 0xFF, 1 ^ 0xFF)
     assert cref.top1(np.array([0.1, np.nan, 3.0, 3.0, -np.inf], np.float32)) == (2, 3.0, 2)
+
+
+def test_topk_oracle_is_numpy_stable_argsort():
+    """oracle_topk == numpy.argsort(-x, kind='stable')[:k]: value descending, lower index
+    first on ties (-0.0 == +0.0), NaN after every number, 0xFFFFFFFF past the end."""
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        n, k = int(rng.integers(1, 80)), int(rng.integers(1, 12))
+        x = rng.integers(-3, 4, n).astype(np.float32)
+        x[rng.random(n) < 0.15] = np.nan
+        x[rng.random(n) < 0.10] = -0.0
+        x[rng.random(n) < 0.05] = np.inf
+        x[rng.random(n) < 0.05] = -np.inf
+        vals, idx = cref.topk(x, k)
+        order = np.argsort(-x, kind="stable")[:k]
+        m = min(k, n)
+        assert np.array_equal(idx[:m], order.astype(np.uint32)[:m])
+        assert np.array_equal(vals[:m], x[order[:m]], equal_nan=True)
+        assert (idx[m:] == 0xFFFFFFFF).all()
