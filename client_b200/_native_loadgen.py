@@ -17,6 +17,7 @@ class LoadgenConfig(ctypes.Structure):
         ("ctx", c_vp), ("fill_jobs", ctypes.POINTER(FillJob)), ("fill_jobs_per_slot", c_int),
         ("seed", c_u64), ("regenerate", c_int),
         ("check_jobs", ctypes.POINTER(CheckJob)), ("check_jobs_per_slot", c_int), ("results", c_vp),
+        ("device_window_us", ctypes.c_uint32),
     ]
 
 

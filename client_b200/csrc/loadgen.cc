@@ -17,6 +17,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -129,6 +130,14 @@ struct SlotQueue {
     q.pop_front();
     return s;
   }
+  // -1 on timeout
+  int pop_ns(uint64_t ns) {
+    std::unique_lock<std::mutex> lk(mu);
+    if (!cv.wait_for(lk, std::chrono::nanoseconds(ns), [&] { return !q.empty(); })) return -1;
+    int s = q.front();
+    q.pop_front();
+    return s;
+  }
   size_t drain(std::vector<int>& out) {
     std::lock_guard<std::mutex> lk(mu);
     const size_t n = q.size();
@@ -159,6 +168,7 @@ struct tb200_loadgen {
   int fill_per_slot = 0;
   uint64_t seed = 0;
   bool regenerate = false;
+  uint64_t device_window_ns = 0;
   std::vector<tb200_check_job> check_jobs;
   int check_per_slot = 0;
   tb200_check_result* results = nullptr;
@@ -238,6 +248,21 @@ void device_main(tb200_loadgen* lg) {
     if (first < 0) continue;
     batch.push_back(first);
     lg->returned.drain(batch);
+    // Accumulation window (cfg.device_window_us): without MPS client and server are two CUDA
+    // contexts time-sliced on one GPU and every hand-over costs ~100 us, so a pass should then
+    // cover the slots that are about to return anyway.  Ends at once when all are back.
+    const uint64_t window_ns = lg->device_window_ns;
+    if (window_ns != 0 && lg->ctx != nullptr) {
+      const uint64_t t0 = now_ns();
+      while (batch.size() < static_cast<size_t>(lg->concurrency)) {
+        const uint64_t el = now_ns() - t0;
+        if (el >= window_ns) break;
+        const int s = lg->returned.pop_ns(window_ns - el);
+        if (s < 0) break;
+        batch.push_back(s);
+        lg->returned.drain(batch);
+      }
+    }
     if (lg->ctx != nullptr) {
       uint64_t bad = 0, mism = 0;
       const bool do_check = lg->check_per_slot > 0;
@@ -255,15 +280,23 @@ void device_main(tb200_loadgen* lg) {
         }
         lg->epoch += 1ull << 20;  // fresh Philox streams for every generation
       }
-      // validation of the returned outputs and generation of the next inputs run as
-      // parallel branches under ONE synchronisation (tb200_step_sync)
+      // validation of the returned outputs + generation of the next inputs: parallel branches
+      // under one sync (tb200_step_sync).  TB200_LOADGEN_DEVICE_MODE (experiments only):
+      // 1 = check, sync, fill, sync; 2 = one stream, one sync
+      static const int mode = getenv("TB200_LOADGEN_DEVICE_MODE") ? atoi(getenv("TB200_LOADGEN_DEVICE_MODE")) : 0;
       int rc = TB200_OK;
-      if (do_fill) {
+      if (do_fill && mode == 0) {
         rc = tb200_step_sync(lg->ctx, fills.data(), static_cast<int>(fills.size()), lg->seed, lg->epoch,
                              checks.data(), static_cast<int>(checks.size()), lg->results);
-      } else if (do_check) {
-        rc = tb200_check_async(lg->ctx, checks.data(), static_cast<int>(checks.size()), lg->results);
-        if (rc == TB200_OK) rc = tb200_ctx_sync(lg->ctx);
+      } else {
+        if (do_check) {
+          rc = tb200_check_async(lg->ctx, checks.data(), static_cast<int>(checks.size()), lg->results);
+          if (rc == TB200_OK && (mode == 1 || !do_fill)) rc = tb200_ctx_sync(lg->ctx);
+        }
+        if (rc == TB200_OK && do_fill) {
+          rc = tb200_fill_async(lg->ctx, fills.data(), static_cast<int>(fills.size()), lg->seed, lg->epoch);
+          if (rc == TB200_OK) rc = tb200_ctx_sync(lg->ctx);
+        }
       }
       if (rc != TB200_OK) {
         std::lock_guard<std::mutex> lk(lg->dev_mu);
@@ -315,6 +348,7 @@ int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out) {
   lg->ctx = cfg->ctx;
   lg->seed = cfg->seed;
   lg->regenerate = cfg->regenerate != 0;
+  lg->device_window_ns = 1000ull * cfg->device_window_us;
   if (cfg->ctx != nullptr && cfg->fill_jobs != nullptr && cfg->fill_jobs_per_slot > 0) {
     lg->fill_per_slot = cfg->fill_jobs_per_slot;
     lg->fill_jobs.assign(cfg->fill_jobs, cfg->fill_jobs + static_cast<size_t>(cfg->concurrency) * cfg->fill_jobs_per_slot);

@@ -62,6 +62,9 @@ def build_parser():
     ap.add_argument("--no-validate", action="store_true")
     ap.add_argument("--engine", default="python", choices=["python", "native"],
                     help="python: threads over the drop-in clients; native: libtb200's C++ workers (HTTP, sync)")
+    ap.add_argument("--device-window-us", type=int, default=0,
+                    help="native engine: wait up to this long for more returned slots before a device pass "
+                         "(~150 helps when client and server are time-sliced CUDA contexts, i.e. no MPS)")
     ap.add_argument("--json", action="store_true")
     return ap
 
@@ -124,7 +127,8 @@ def run_instance(args, device_id, prefix, out_queue=None, staging_factory=None):
             from .native import NativeLoadGenerator
 
             gen = NativeLoadGenerator(url, args.model_name, args.model_version, slotset, level,
-                                      regenerate=args.input_data_mode == "per-request", validate=not args.no_validate)
+                                      regenerate=args.input_data_mode == "per-request", validate=not args.no_validate,
+                                      device_window_us=args.device_window_us)
             gen.start()
             try:
                 res = measure_native(gen, args.measurement_interval, args.stability_percentage, args.max_trials, args.percentile)

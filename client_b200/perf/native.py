@@ -25,7 +25,8 @@ def frame_http_request(host, port, uri, body, json_size, head_only_bytes=None):
 class NativeLoadGenerator:
     """One tb200_loadgen instance over a SlotSet (cuda shm or wire mode)."""
 
-    def __init__(self, url, model_name, model_version, slotset, concurrency, regenerate=True, validate=True):
+    def __init__(self, url, model_name, model_version, slotset, concurrency, regenerate=True, validate=True,
+                 device_window_us=0):
         self._lib = _native.load()
         host, _, port = url.partition(":")
         self.host, self.port = host, int(port or 80)
@@ -88,6 +89,7 @@ class NativeLoadGenerator:
                 cfg.check_jobs = (_native.CheckJob * len(checks))(*checks)
                 cfg.check_jobs_per_slot = len(ss.outputs)
                 cfg.results = self._results.device_ptr
+        cfg.device_window_us = int(device_window_us)
         self._keep.append(cfg)
         h = ctypes.c_void_p()
         _native.check(self._lib.tb200_loadgen_create(ctypes.byref(cfg), ctypes.byref(h)))

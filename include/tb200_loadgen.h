@@ -46,6 +46,11 @@ typedef struct tb200_loadgen_config {
   const tb200_check_job* check_jobs; /* [concurrency * check_jobs_per_slot] */
   int check_jobs_per_slot;
   tb200_check_result* results;       /* device-visible (mapped host), same count as check_jobs */
+  /* the device thread waits up to this long for further returned slots before a pass
+   * (ends early once every slot in flight is back); 0 = take what is there.  Worth ~150
+   * when client and server are time-sliced CUDA contexts (no MPS): each GPU hand-over
+   * between the processes costs ~100 us, so passes should be few and full */
+  uint32_t device_window_us;
 } tb200_loadgen_config;
 
 typedef struct tb200_loadgen_stats {

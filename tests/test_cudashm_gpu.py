@@ -208,7 +208,7 @@ def test_topk_on_device_matches_oracle(cudashm, datatype):
             x = (x.view(np.uint32) & 0xFFFF0000).view(np.float32)
         vecs.append(x)
     es = 4 if datatype == "FP32" else 2
-    h = cudashm.create_shared_memory_region("topk_data", sum(lengths) * 4, 0)
+    h = cudashm.create_shared_memory_region("topk_data", sum(lengths) * 4 + 16 * len(lengths), 0)
     jobs, off, keep = [], 0, []
     for x in vecs:
         if datatype == "FP32":
