@@ -320,9 +320,93 @@ def run_b200(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_port()
+    if rank == 0 and world == 1 and not args.no_loopback:
+        try:
+            line["loopback"] = loopback_extra(local)
+        except Exception as ex:  # the extra must never cost the bench line
+            line["loopback"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     rep.close()
+
+
+def loopback_extra(device, seconds=1.5):
+    """The north star's first metric as the user sees it: sustained inferences/sec against a
+    local CUDA-shared-memory server.  The native stand-in server runs as its own process (it
+    opens our IPC handles); requests only name regions; every request's FP32[3,224,224] input is
+    regenerated and its output validated on the device by the native load generator.  Beside it,
+    the reference-style CPU client loop (numpy tensor -> set_shared_memory_region -> infer ->
+    get_contents_as_numpy), one thread, same server.  Client and server are time-sliced CUDA
+    contexts here (no MPS): see profiles/ for the MPS numbers."""
+    import socket
+
+    import client_b200.http as httpclient
+    from client_b200.perf.loadgen import SlotSet, TensorSpec
+    from client_b200.perf.native import NativeLoadGenerator
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    srv = subprocess.Popen([sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(device)],
+                           cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    out = {"server": "client_b200.testing.native_server (own process, CUDA IPC, batched model kernel)", "mps": False, "levels": []}
+    try:
+        if "listening" not in srv.stdout.readline():
+            raise RuntimeError("native server did not start")
+        url = "127.0.0.1:%d" % port
+        control = httpclient.InferenceServerClient(url)
+        for conc, window in ((1, 0), (64, 150), (256, 150)):
+            ss = SlotSet([TensorSpec("data_0", "FP32", [3, 224, 224])], [TensorSpec("fc6_1", "FP32", [1000])], conc, "cuda", device,
+                         "random", SEED, name_prefix="bench_lb%d" % conc)
+            ss.register(control)
+            gen = NativeLoadGenerator(url, "densenet_onnx", "", ss, conc, regenerate=True, validate=True, device_window_us=window)
+            gen.start()
+            try:
+                gen.window(0.5)
+                w = gen.window(seconds)
+            finally:
+                gen.stop()
+                ss.unregister(control)
+                ss.close()
+            out["levels"].append({"concurrency": conc, "infer_per_s": round(w["throughput"], 1), "p50_us": round(w["p50_us"], 1),
+                                  "p99_us": round(w["p99_us"], 1), "failed": int(w["failed"]), "nonfinite": int(w["nonfinite"]),
+                                  "slots_per_device_pass": round(w["device_slots"] / max(1, w["device_batches"]), 1),
+                                  "device_window_us": window})
+        # reference-style CPU client loop, one thread
+        import client_b200.utils.cuda_shared_memory as cudashm
+
+        rng = np.random.default_rng(0)
+        in_h = cudashm.create_shared_memory_region("bench_cpu_in", IN_BYTES, device)
+        out_h = cudashm.create_shared_memory_region("bench_cpu_out", OUT_BYTES, device)
+        control.register_cuda_shared_memory("bench_cpu_in", cudashm.get_raw_handle(in_h), device, IN_BYTES)
+        control.register_cuda_shared_memory("bench_cpu_out", cudashm.get_raw_handle(out_h), device, OUT_BYTES)
+        inp = httpclient.InferInput("data_0", [3, 224, 224], "FP32").set_shared_memory("bench_cpu_in", IN_BYTES)
+        o = httpclient.InferRequestedOutput("fc6_1")
+        o.set_shared_memory("bench_cpu_out", OUT_BYTES)
+        lat, t_end = [], time.perf_counter() + seconds
+        t0 = time.perf_counter()
+        while time.perf_counter() < t_end:
+            t1 = time.perf_counter_ns()
+            x = rng.random((3, 224, 224), dtype=np.float32)
+            cudashm.set_shared_memory_region(in_h, [x])
+            control.infer("densenet_onnx", [inp], outputs=[o])
+            y = cudashm.get_contents_as_numpy(out_h, np.float32, [1000])
+            assert np.isfinite(y).all()
+            lat.append(time.perf_counter_ns() - t1)
+        dt = time.perf_counter() - t0
+        out["cpu_client_loop"] = {"concurrency": 1, "infer_per_s": round(len(lat) / dt, 1), "p50_us": round(float(np.percentile(lat, 50)) / 1e3, 1),
+                                  "what": "numpy Generator.random -> set_shared_memory_region (H2D + sync) -> infer -> get_contents_as_numpy (D2H), one thread"}
+        control.unregister_cuda_shared_memory()
+        cudashm.destroy_shared_memory_region(in_h)
+        cudashm.destroy_shared_memory_region(out_h)
+        control.close()
+    finally:
+        srv.terminate()
+        try:
+            srv.wait(10)
+        except Exception:
+            srv.kill()
+    return out
 
 
 def cpu_baseline_port(seconds=12.0):
@@ -423,6 +507,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-loopback", action="store_true", help="skip the loopback extra (native server in its own process)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

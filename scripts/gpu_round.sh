@@ -17,15 +17,15 @@ timeout -s KILL 600 python bench.py --impl reference --steps 100 > gpurun_out/be
 echo "ref rc=$?"; cat gpurun_out/bench_ref.json
 if [ -z "$SKIP_NCU" ]; then
 timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 24 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+    python bench.py --steps 24 --warmup 3 --no-cpu-baseline --no-loopback > gpurun_out/bench_under_ncu.log 2>&1
 echo "ncu list rc=$?"
 timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:fill_kernel -s 3 -c 2 -f -o gpurun_out/prof_fill \
-    python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_fill.log 2>&1
+    python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-loopback > gpurun_out/ncu_fill.log 2>&1
 echo "ncu fill rc=$?"
 timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:pack_image_chw -s 1 -c 2 -f -o gpurun_out/prof_pack \
-    python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_pack.log 2>&1
+    python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-loopback > gpurun_out/ncu_pack.log 2>&1
 echo "ncu pack rc=$?"
 timeout -s KILL 600 ncu --set full --clock-control none -k regex:check_kernel -s 1 -c 1 -f -o gpurun_out/prof_check \
-    python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_check.log 2>&1
+    python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-loopback > gpurun_out/ncu_check.log 2>&1
 fi
 ls -la gpurun_out
