@@ -6,10 +6,20 @@
 // is plain HTTP/1.1 over POSIX sockets: the reference's libcurl path
 // (src/c++/library/http_client.cc:1767-1830) cannot be built here and is not needed to
 // send a pre-formed request and read a Content-Length response.
+//
+// Threads: a few epoll-driven transport threads, each owning the keep-alive connections of
+// a share of the slots (slot s <-> connection s, thread s % T), plus one device thread.
+// A request is one non-blocking sendmsg of the pre-formed bytes (+ the borrowed tail); the
+// hand-over between transport and device thread is batched (one eventfd write per thread
+// and pass), so the host cost per request is a send, a recv and no thread wake-up.
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
+#include <fcntl.h>
+#include <sys/epoll.h>
+#include <sys/eventfd.h>
 #include <sys/socket.h>
+#include <sys/uio.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -20,12 +30,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/tb200_loadgen.h"
+#include "http_server.h"
 
 namespace {
 
@@ -51,16 +63,6 @@ int connect_to(const char* host, int port) {
   return fd;
 }
 
-bool send_all(int fd, const uint8_t* p, size_t n) {
-  while (n > 0) {
-    ssize_t k = send(fd, p, n, MSG_NOSIGNAL);
-    if (k <= 0) return false;
-    p += k;
-    n -= static_cast<size_t>(k);
-  }
-  return true;
-}
-
 // case-insensitive search of "content-length:" in the header block
 long content_length(const char* hdr, size_t len) {
   static const char key[] = "content-length:";
@@ -70,45 +72,6 @@ long content_length(const char* hdr, size_t len) {
     if (k == sizeof(key) - 1 && (i == 0 || hdr[i - 1] == '\n')) return strtol(hdr + i + k, nullptr, 10);
   }
   return 0;
-}
-
-// Read one HTTP response; returns the status code (0 on transport error).  *first_byte_ns
-// receives the time the first byte arrived (RECV_START).
-int read_response(int fd, std::vector<char>& buf, uint64_t* first_byte_ns) {
-  buf.clear();
-  size_t header_end = 0;
-  bool first = true;
-  char tmp[4096];
-  for (;;) {
-    ssize_t k = recv(fd, tmp, sizeof(tmp), 0);
-    if (k <= 0) return 0;
-    if (first) {
-      *first_byte_ns = now_ns();
-      first = false;
-    }
-    buf.insert(buf.end(), tmp, tmp + k);
-    if (buf.size() >= 4) {
-      const size_t from = buf.size() > static_cast<size_t>(k) + 3 ? buf.size() - k - 3 : 0;
-      for (size_t i = from; i + 3 < buf.size(); ++i) {
-        if (buf[i] == '\r' && buf[i + 1] == '\n' && buf[i + 2] == '\r' && buf[i + 3] == '\n') {
-          header_end = i + 4;
-          break;
-        }
-      }
-    }
-    if (header_end) break;
-    if (buf.size() > (1u << 20)) return 0;
-  }
-  const long body = content_length(buf.data(), header_end);
-  size_t have = buf.size() - header_end;
-  while (static_cast<long>(have) < body) {
-    ssize_t k = recv(fd, tmp, sizeof(tmp), 0);
-    if (k <= 0) return 0;
-    have += static_cast<size_t>(k);
-  }
-  int status = 0;
-  if (buf.size() > 12 && memcmp(buf.data(), "HTTP/1.", 7) == 0) status = atoi(buf.data() + 9);
-  return status;
 }
 
 struct SlotQueue {
@@ -153,6 +116,28 @@ struct WorkerStats {
   uint64_t completed = 0, failed = 0, total_ns = 0, send_ns = 0, recv_ns = 0;
 };
 
+// one keep-alive connection = one concurrency slot
+struct Conn {
+  int fd = -1;
+  int slot = 0;
+  size_t send_off = 0;     // bytes of request + tail already sent
+  bool want_out = false;   // EPOLLOUT armed
+  bool in_flight = false;
+  int attempts = 0;
+  std::vector<char> buf;   // response bytes so far
+  size_t header_end = 0;
+  long body = 0;
+  uint64_t t_start = 0, t_send_end = 0, t_recv_start = 0;
+};
+
+struct Transport {
+  int epfd = -1, evfd = -1;
+  std::mutex mu;
+  std::vector<int> ready;   // slots released by the device thread (guarded by mu)
+  std::vector<Conn> conns;  // the slots this thread owns
+  WorkerStats stats;
+};
+
 }  // namespace
 
 struct tb200_loadgen {
@@ -175,9 +160,9 @@ struct tb200_loadgen {
 
   std::atomic<bool> stop{false};
   bool started = false;
-  SlotQueue ready, returned;
+  SlotQueue returned;                          // transport threads -> device thread
+  std::vector<std::unique_ptr<Transport>> transports;
   std::vector<std::thread> threads;
-  std::vector<WorkerStats> stats;
   // device thread counters (guarded by dev_mu)
   std::mutex dev_mu;
   uint64_t device_batches = 0, device_slots = 0, nonfinite = 0, mismatches = 0, epoch = 0;
@@ -187,54 +172,220 @@ struct tb200_loadgen {
 
 namespace {
 
-void worker_main(tb200_loadgen* lg, int index) {
-  WorkerStats& st = lg->stats[index];
-  int fd = connect_to(lg->host.c_str(), lg->port);
-  std::vector<char> buf;
-  buf.reserve(8192);
-  while (!lg->stop.load(std::memory_order_relaxed)) {
-    const int slot = lg->passthrough ? index : lg->ready.pop(50);
-    if (slot < 0) continue;
-    const std::vector<uint8_t>& req = lg->requests[slot];
-    const uint8_t* tail = lg->tails.empty() ? nullptr : lg->tails[slot];
-    const uint64_t tail_size = lg->tails.empty() ? 0 : lg->tail_sizes[slot];
-    bool ok = false;
-    uint64_t t_start = now_ns(), t_send_end = t_start, t_recv_start = t_start, t_end = t_start;
-    for (int attempt = 0; attempt < 2 && !ok; ++attempt) {
-      if (fd < 0) fd = connect_to(lg->host.c_str(), lg->port);
-      if (fd < 0) break;
-      t_start = now_ns();  // REQUEST_START == SEND_START (the request is pre-formed)
-      if (!send_all(fd, req.data(), req.size()) || (tail_size != 0 && !send_all(fd, tail, tail_size))) {
-        close(fd);
-        fd = -1;
-        continue;
-      }
-      t_send_end = now_ns();
-      const int status = read_response(fd, buf, &t_recv_start);
-      t_end = now_ns();
-      if (status == 0) {  // connection dropped: reconnect once
-        close(fd);
-        fd = -1;
-        continue;
-      }
-      ok = (status == 200);
-      break;
-    }
-    {
-      std::lock_guard<std::mutex> lk(st.mu);
-      if (ok) {
-        st.completed += 1;
-        st.total_ns += t_end - t_start;
-        st.send_ns += t_send_end - t_start;
-        st.recv_ns += t_end - t_recv_start;
-        st.latencies.push_back(t_end - t_start);
-      } else {
-        st.failed += 1;
-      }
-    }
-    if (!lg->passthrough) lg->returned.push(slot);
+constexpr uint32_t kEvTag = 0xFFFFFFFFu;
+
+void conn_close(Transport* t, Conn& c) {
+  if (c.fd >= 0) {
+    epoll_ctl(t->epfd, EPOLL_CTL_DEL, c.fd, nullptr);
+    close(c.fd);
   }
-  if (fd >= 0) close(fd);
+  c.fd = -1;
+  c.want_out = false;
+}
+
+bool conn_open(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
+  c.fd = connect_to(lg->host.c_str(), lg->port);
+  if (c.fd < 0) return false;
+  fcntl(c.fd, F_SETFL, fcntl(c.fd, F_GETFL, 0) | O_NONBLOCK);
+  epoll_event ev{};
+  ev.events = EPOLLIN;
+  ev.data.u32 = index;
+  epoll_ctl(t->epfd, EPOLL_CTL_ADD, c.fd, &ev);
+  return true;
+}
+
+void conn_arm(Transport* t, Conn& c, uint32_t index, bool want_out) {
+  if (c.want_out == want_out) return;
+  epoll_event ev{};
+  ev.events = EPOLLIN | (want_out ? EPOLLOUT : 0);
+  ev.data.u32 = index;
+  epoll_ctl(t->epfd, EPOLL_CTL_MOD, c.fd, &ev);
+  c.want_out = want_out;
+}
+
+void request_done(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool ok, uint64_t t_end);
+
+// push the rest of request + tail; false on a dead connection
+bool conn_send(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
+  const std::vector<uint8_t>& req = lg->requests[c.slot];
+  const uint8_t* tail = lg->tails.empty() ? nullptr : lg->tails[c.slot];
+  const size_t tail_size = lg->tails.empty() ? 0 : static_cast<size_t>(lg->tail_sizes[c.slot]);
+  const size_t total = req.size() + tail_size;
+  while (c.send_off < total) {
+    iovec iov[2];
+    int n = 0;
+    if (c.send_off < req.size()) {
+      iov[n++] = iovec{const_cast<uint8_t*>(req.data()) + c.send_off, req.size() - c.send_off};
+      if (tail_size) iov[n++] = iovec{const_cast<uint8_t*>(tail), tail_size};
+    } else {
+      const size_t off = c.send_off - req.size();
+      iov[n++] = iovec{const_cast<uint8_t*>(tail) + off, tail_size - off};
+    }
+    msghdr msg{};
+    msg.msg_iov = iov;
+    msg.msg_iovlen = static_cast<size_t>(n);
+    const ssize_t k = sendmsg(c.fd, &msg, MSG_NOSIGNAL | MSG_DONTWAIT);
+    if (k < 0) {
+      if (errno == EINTR) continue;
+      if (errno == EAGAIN || errno == EWOULDBLOCK) {
+        conn_arm(t, c, index, true);
+        return true;
+      }
+      return false;
+    }
+    c.send_off += static_cast<size_t>(k);
+  }
+  c.t_send_end = now_ns();
+  conn_arm(t, c, index, false);
+  return true;
+}
+
+void request_start(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool retry) {
+  if (!retry) c.attempts = 0;
+  for (;;) {
+    if (c.fd < 0 && !conn_open(lg, t, c, index)) break;
+    c.in_flight = true;
+    c.send_off = 0;
+    c.buf.clear();
+    c.header_end = 0;
+    c.t_recv_start = 0;
+    c.t_start = now_ns();  // REQUEST_START == SEND_START (the request is pre-formed)
+    c.t_send_end = c.t_start;
+    if (conn_send(lg, t, c, index)) return;
+    conn_close(t, c);  // keep-alive connection the server dropped: reconnect once
+    if (++c.attempts >= 2) break;
+  }
+  request_done(lg, t, c, index, false, now_ns());
+}
+
+void request_done(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool ok, uint64_t t_end) {
+  c.in_flight = false;
+  {
+    std::lock_guard<std::mutex> lk(t->stats.mu);
+    if (ok) {
+      t->stats.completed += 1;
+      t->stats.total_ns += t_end - c.t_start;
+      t->stats.send_ns += c.t_send_end - c.t_start;
+      t->stats.recv_ns += t_end - c.t_recv_start;
+      t->stats.latencies.push_back(t_end - c.t_start);
+    } else {
+      t->stats.failed += 1;
+    }
+  }
+  if (lg->passthrough) {
+    if (lg->stop.load(std::memory_order_relaxed)) return;
+    if (ok) {
+      request_start(lg, t, c, index, false);
+    } else {
+      // do not spin (or recurse) on a dead server: retry from the event loop a little later
+      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+      {
+        std::lock_guard<std::mutex> lk(t->mu);
+        t->ready.push_back(c.slot);
+      }
+      const uint64_t one = 1;
+      if (write(t->evfd, &one, sizeof(one)) < 0) return;
+    }
+  } else {
+    lg->returned.push(c.slot);
+  }
+}
+
+void conn_readable(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
+  char tmp[16384];
+  for (;;) {
+    const ssize_t k = recv(c.fd, tmp, sizeof(tmp), MSG_DONTWAIT);
+    if (k < 0) {
+      if (errno == EINTR) continue;
+      if (errno == EAGAIN || errno == EWOULDBLOCK) return;
+    }
+    if (k <= 0) {  // dropped
+      conn_close(t, c);
+      if (!c.in_flight) return;
+      if (++c.attempts < 2) request_start(lg, t, c, index, true);
+      else request_done(lg, t, c, index, false, now_ns());
+      return;
+    }
+    if (!c.in_flight) continue;  // stray bytes
+    if (c.t_recv_start == 0) c.t_recv_start = now_ns();
+    const size_t old = c.buf.size();
+    c.buf.insert(c.buf.end(), tmp, tmp + k);
+    if (c.header_end == 0) {
+      for (size_t i = old > 3 ? old - 3 : 0; i + 3 < c.buf.size(); ++i) {
+        if (c.buf[i] == '\r' && c.buf[i + 1] == '\n' && c.buf[i + 2] == '\r' && c.buf[i + 3] == '\n') {
+          c.header_end = i + 4;
+          c.body = content_length(c.buf.data(), c.header_end);
+          break;
+        }
+      }
+      if (c.header_end == 0 && c.buf.size() > (1u << 20)) {
+        conn_close(t, c);
+        request_done(lg, t, c, index, false, now_ns());
+        return;
+      }
+    }
+    if (c.header_end != 0 && c.buf.size() >= c.header_end + static_cast<size_t>(c.body)) {
+      const uint64_t t_end = now_ns();
+      int status = 0;
+      if (c.buf.size() > 12 && memcmp(c.buf.data(), "HTTP/1.", 7) == 0) status = atoi(c.buf.data() + 9);
+      request_done(lg, t, c, index, status == 200, t_end);
+      return;  // one response per request; level-triggered epoll reports anything left
+    }
+  }
+}
+
+void transport_main(tb200_loadgen* lg, Transport* t) {
+  if (lg->passthrough) {
+    for (uint32_t i = 0; i < t->conns.size(); ++i) request_start(lg, t, t->conns[i], i, false);
+  }
+  std::vector<int> ready;
+  epoll_event events[64];
+  while (!lg->stop.load(std::memory_order_relaxed)) {
+    const int n = epoll_wait(t->epfd, events, 64, 50);
+    for (int e = 0; e < n; ++e) {
+      const uint32_t tag = events[e].data.u32;
+      if (tag == kEvTag) {
+        uint64_t count;
+        if (read(t->evfd, &count, sizeof(count)) < 0) continue;
+        {
+          std::lock_guard<std::mutex> lk(t->mu);
+          ready.swap(t->ready);
+        }
+        for (int slot : ready) {
+          const uint32_t i = static_cast<uint32_t>(slot / static_cast<int>(lg->transports.size()));
+          request_start(lg, t, t->conns[i], i, false);
+        }
+        ready.clear();
+        continue;
+      }
+      Conn& c = t->conns[tag];
+      if (c.fd < 0) continue;
+      if ((events[e].events & EPOLLOUT) && c.in_flight && !conn_send(lg, t, c, tag)) {
+        conn_close(t, c);
+        if (++c.attempts < 2) request_start(lg, t, c, tag, true);
+        else request_done(lg, t, c, tag, false, now_ns());
+        continue;
+      }
+      if (events[e].events & (EPOLLIN | EPOLLERR | EPOLLHUP)) conn_readable(lg, t, c, tag);
+    }
+  }
+  for (Conn& c : t->conns) conn_close(t, c);
+}
+
+// hand slots to the transport threads that own them: one eventfd write per thread
+void release_slots(tb200_loadgen* lg, const std::vector<int>& slots) {
+  const int T = static_cast<int>(lg->transports.size());
+  std::vector<char> touched(static_cast<size_t>(T), 0);
+  for (int s : slots) {
+    Transport* t = lg->transports[static_cast<size_t>(s % T)].get();
+    std::lock_guard<std::mutex> lk(t->mu);
+    t->ready.push_back(s);
+    touched[static_cast<size_t>(s % T)] = 1;
+  }
+  const uint64_t one = 1;
+  for (int i = 0; i < T; ++i) {
+    if (touched[static_cast<size_t>(i)] && write(lg->transports[static_cast<size_t>(i)]->evfd, &one, sizeof(one)) < 0) continue;
+  }
 }
 
 // validate + regenerate the slots that came back, one launch each, then release them
@@ -313,7 +464,7 @@ void device_main(tb200_loadgen* lg) {
       lg->nonfinite += bad;
       lg->mismatches += mism;
     }
-    for (int s : batch) lg->ready.push(s);
+    release_slots(lg, batch);
   }
 }
 
@@ -363,7 +514,6 @@ int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out) {
     lg->tail_sizes.assign(cfg->tail_sizes, cfg->tail_sizes + cfg->concurrency);
   }
   lg->passthrough = lg->ctx == nullptr || (lg->check_per_slot == 0 && !(lg->regenerate && lg->fill_per_slot > 0));
-  lg->stats = std::vector<WorkerStats>(cfg->concurrency);
   *out = lg;
   return TB200_OK;
 }
@@ -379,11 +529,34 @@ int tb200_loadgen_start(tb200_loadgen* lg) {
   }
   lg->started = true;
   lg->window_start_ns = now_ns();
+  // transport threads: ~8 connections each, at most 32 threads (and half the host's cores)
+  const int hw = static_cast<int>(std::max(2u, std::thread::hardware_concurrency()));
+  const int T = std::max(1, std::min({(lg->concurrency + 7) / 8, 32, hw / 2}));
+  lg->transports.clear();
+  for (int i = 0; i < T; ++i) {
+    std::unique_ptr<Transport> t(new Transport());
+    t->epfd = epoll_create1(0);
+    t->evfd = eventfd(0, EFD_NONBLOCK);
+    if (t->epfd < 0 || t->evfd < 0) return lg_fail(TB200_ERR_IO, "epoll / eventfd setup failed");
+    epoll_event ev{};
+    ev.events = EPOLLIN;
+    ev.data.u32 = kEvTag;
+    epoll_ctl(t->epfd, EPOLL_CTL_ADD, t->evfd, &ev);
+    lg->transports.push_back(std::move(t));
+  }
+  for (int s = 0; s < lg->concurrency; ++s) {  // slot s -> thread s % T, connection s / T
+    Conn c;
+    c.slot = s;
+    c.buf.reserve(4096);
+    lg->transports[static_cast<size_t>(s % T)]->conns.push_back(std::move(c));
+  }
   if (!lg->passthrough) {
-    for (int s = 0; s < lg->concurrency; ++s) lg->ready.push(s);
+    std::vector<int> all(static_cast<size_t>(lg->concurrency));
+    for (int s = 0; s < lg->concurrency; ++s) all[static_cast<size_t>(s)] = s;
+    release_slots(lg, all);
     lg->threads.emplace_back(device_main, lg);
   }
-  for (int i = 0; i < lg->concurrency; ++i) lg->threads.emplace_back(worker_main, lg, i);
+  for (auto& t : lg->transports) lg->threads.emplace_back(transport_main, lg, t.get());
   return TB200_OK;
 }
 
@@ -392,7 +565,8 @@ int tb200_loadgen_window(tb200_loadgen* lg, double seconds, tb200_loadgen_stats*
   if (seconds > 0) std::this_thread::sleep_for(std::chrono::duration<double>(seconds));
   memset(out, 0, sizeof(*out));
   std::vector<uint64_t> lat;
-  for (WorkerStats& st : lg->stats) {
+  for (auto& tr : lg->transports) {
+    WorkerStats& st = tr->stats;
     std::lock_guard<std::mutex> lk(st.mu);
     out->completed_request_count += st.completed;
     out->failed_request_count += st.failed;
@@ -435,6 +609,12 @@ int tb200_loadgen_stop(tb200_loadgen* lg) {
     if (t.joinable()) t.join();
   }
   lg->threads.clear();
+  for (auto& t : lg->transports) {
+    if (t->evfd >= 0) close(t->evfd);
+    if (t->epfd >= 0) close(t->epfd);
+  }
+  lg->transports.clear();
+  lg->stop.store(false);
   lg->started = false;
   return TB200_OK;
 }
@@ -452,102 +632,32 @@ int tb200_loadgen_destroy(tb200_loadgen* lg) {
 // canned-response server (tooling for measuring the generator)
 // ---------------------------------------------------------------------------------------
 struct tb200_stub_server {
-  int listen_fd = -1;
-  std::atomic<bool> stop{false};
+  tb200::EpollHttpServer http;
   std::string response;
-  std::thread acceptor;
-  std::mutex mu;
-  std::vector<std::thread> conns;
-  std::vector<int> fds;
 };
-
-namespace {
-
-void stub_conn(tb200_stub_server* s, int fd) {
-  std::vector<char> buf;
-  char tmp[8192];
-  for (;;) {
-    // read one request: headers, then Content-Length bytes of body
-    buf.clear();
-    size_t header_end = 0;
-    while (!header_end) {
-      ssize_t k = recv(fd, tmp, sizeof(tmp), 0);
-      if (k <= 0) return;  // the fd is closed by tb200_stub_server_stop
-      buf.insert(buf.end(), tmp, tmp + k);
-      for (size_t i = 0; i + 3 < buf.size(); ++i) {
-        if (buf[i] == '\r' && buf[i + 1] == '\n' && buf[i + 2] == '\r' && buf[i + 3] == '\n') {
-          header_end = i + 4;
-          break;
-        }
-      }
-    }
-    long body = content_length(buf.data(), header_end);
-    long have = static_cast<long>(buf.size() - header_end);
-    while (have < body) {
-      ssize_t k = recv(fd, tmp, sizeof(tmp), 0);
-      if (k <= 0) return;
-      have += k;
-    }
-    if (!send_all(fd, reinterpret_cast<const uint8_t*>(s->response.data()), s->response.size())) return;
-  }
-}
-
-void stub_accept(tb200_stub_server* s) {
-  while (!s->stop.load()) {
-    int fd = accept(s->listen_fd, nullptr, nullptr);
-    if (fd < 0) break;
-    int one = 1;
-    setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
-    std::lock_guard<std::mutex> lk(s->mu);
-    s->fds.push_back(fd);
-    s->conns.emplace_back(stub_conn, s, fd);
-  }
-}
-
-}  // namespace
 
 extern "C" {
 
 int tb200_stub_server_start(const char* host, int* port, const char* response_body, tb200_stub_server** out) {
   if (host == nullptr || port == nullptr || out == nullptr) return lg_fail(TB200_ERR_INVALID, "NULL argument");
   tb200_stub_server* s = new tb200_stub_server();
-  const std::string body = response_body ? response_body : "{}";
-  s->response = "HTTP/1.1 200 OK\r\nContent-Type: application/json\r\nContent-Length: " + std::to_string(body.size()) +
-                "\r\n\r\n" + body;
-  s->listen_fd = socket(AF_INET, SOCK_STREAM, 0);
-  int one = 1;
-  setsockopt(s->listen_fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
-  sockaddr_in addr{};
-  addr.sin_family = AF_INET;
-  addr.sin_port = htons(static_cast<uint16_t>(*port));
-  if (s->listen_fd < 0 || inet_pton(AF_INET, host, &addr.sin_addr) != 1 ||
-      bind(s->listen_fd, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) != 0 || listen(s->listen_fd, 1024) != 0) {
-    if (s->listen_fd >= 0) close(s->listen_fd);
+  s->response = tb200::EpollHttpServer::Response(200, response_body ? response_body : "{}");
+  const int hw = static_cast<int>(std::max(2u, std::thread::hardware_concurrency()));
+  const std::string* canned = &s->response;
+  if (!s->http.Start(host, port, std::min(16, hw / 2), [canned](uint64_t, const tb200::HttpRequest&, std::string* resp) {
+        *resp = *canned;
+        return true;
+      })) {
     delete s;
     return lg_fail(TB200_ERR_IO, "cannot bind the stub server");
   }
-  socklen_t len = sizeof(addr);
-  getsockname(s->listen_fd, reinterpret_cast<sockaddr*>(&addr), &len);
-  *port = ntohs(addr.sin_port);
-  s->acceptor = std::thread(stub_accept, s);
   *out = s;
   return TB200_OK;
 }
 
 int tb200_stub_server_stop(tb200_stub_server* s) {
   if (s == nullptr) return TB200_OK;
-  s->stop.store(true);
-  shutdown(s->listen_fd, SHUT_RDWR);
-  close(s->listen_fd);
-  if (s->acceptor.joinable()) s->acceptor.join();
-  {
-    std::lock_guard<std::mutex> lk(s->mu);
-    for (int fd : s->fds) shutdown(fd, SHUT_RDWR);
-  }
-  for (std::thread& t : s->conns) {
-    if (t.joinable()) t.join();
-  }
-  for (int fd : s->fds) close(fd);
+  s->http.Stop();
   delete s;
   return TB200_OK;
 }
