@@ -302,7 +302,7 @@ void conn_readable(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
     if (k <= 0) {  // dropped
       conn_close(t, c);
       if (!c.in_flight) return;
-      if (++c.attempts < 2) request_start(lg, t, c, index, true);
+      if (++c.attempts < 2 && !lg->stop.load(std::memory_order_relaxed)) request_start(lg, t, c, index, true);
       else request_done(lg, t, c, index, false, now_ns());
       return;
     }
@@ -340,7 +340,16 @@ void transport_main(tb200_loadgen* lg, Transport* t) {
   }
   std::vector<int> ready;
   epoll_event events[64];
-  while (!lg->stop.load(std::memory_order_relaxed)) {
+  uint64_t drain_deadline = 0;
+  for (;;) {
+    if (lg->stop.load(std::memory_order_relaxed)) {
+      // stopping: issue nothing new, but let the requests in flight complete (the server is
+      // still reading the regions they name) -- for at most two seconds
+      bool busy = false;
+      for (const Conn& c : t->conns) busy = busy || c.in_flight;
+      if (drain_deadline == 0) drain_deadline = now_ns() + 2000000000ull;
+      if (!busy || now_ns() > drain_deadline) break;
+    }
     const int n = epoll_wait(t->epfd, events, 64, 50);
     for (int e = 0; e < n; ++e) {
       const uint32_t tag = events[e].data.u32;
@@ -352,6 +361,7 @@ void transport_main(tb200_loadgen* lg, Transport* t) {
           ready.swap(t->ready);
         }
         for (int slot : ready) {
+          if (lg->stop.load(std::memory_order_relaxed)) break;
           const uint32_t i = static_cast<uint32_t>(slot / static_cast<int>(lg->transports.size()));
           request_start(lg, t, t->conns[i], i, false);
         }
