@@ -8,12 +8,13 @@
  * RequestTimers (src/c++/library/common.h:568-648) and InferStat (:93-114, folded by
  * UpdateInferStat, src/c++/library/common.cc:56-106).
  *
- * Shape: `concurrency` worker threads each own one keep-alive HTTP/1.1 connection and
- * keep one request in flight (closed loop).  A request is a pre-formed byte string per
- * concurrency slot (with shared memory it only names regions, golden "A" of SURVEY.md
- * 9.4).  One device thread serves all slots: slots whose responses came back are
- * validated (tb200_check_async) and regenerated (tb200_fill_async) in ONE launch each,
- * then handed back to the workers -- the transport threads never touch tensor bytes.
+ * Shape: `concurrency` keep-alive HTTP/1.1 connections, one per slot, each with one request
+ * in flight (closed loop), served by a few epoll-driven transport threads.  A request is a
+ * pre-formed byte string per concurrency slot (with shared memory it only names regions,
+ * golden "A" of SURVEY.md 9.4).  One device thread serves all slots: slots whose responses
+ * came back are validated (tb200_check_async) and regenerated (tb200_fill_async) as parallel
+ * branches of ONE pass, then handed back to the transport threads in one batch -- the
+ * transport threads never touch tensor bytes and no thread is woken per request.
  */
 #ifndef TB200_LOADGEN_H_
 #define TB200_LOADGEN_H_
@@ -29,7 +30,7 @@ typedef struct tb200_loadgen tb200_loadgen;
 typedef struct tb200_loadgen_config {
   const char* host;              /* numeric IPv4 address, e.g. "127.0.0.1" */
   int port;
-  int concurrency;               /* requests in flight = worker threads = slots */
+  int concurrency;               /* requests in flight = connections = slots */
   const uint8_t* const* requests; /* [concurrency] complete HTTP requests (headers + body) */
   const uint64_t* request_sizes;  /* [concurrency] */
   /* optional binary tails sent right after requests[s] and NOT copied: they point into
