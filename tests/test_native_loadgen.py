@@ -82,3 +82,34 @@ def test_closed_loop_against_mock_server_system_shm():
     finally:
         proc.terminate()
         proc.wait(10)
+
+
+def test_many_connections_per_thread_and_large_borrowed_tails():
+    """40 slots over a handful of event-loop threads, every request followed by a 1 MiB
+    borrowed tail (HTTP binary-tensor body in --shared-memory none mode): the non-blocking
+    send has to continue across EPOLLOUT rounds, and the server must see whole bodies."""
+    srv = StubServer()
+    lib = _native.load()
+    try:
+        n, tail_bytes = 40, 1 << 20
+        head = b'{"inputs":[{"name":"X","shape":[%d],"datatype":"UINT8","parameters":{"binary_data_size":%d}}]}' % (tail_bytes, tail_bytes)
+        req = frame_http_request(srv.host, srv.port, "v2/models/m/infer", head, len(head), head_only_bytes=tail_bytes)
+        tail = ctypes.create_string_buffer(bytes(range(256)) * (tail_bytes // 256), tail_bytes)
+        bufs = [ctypes.create_string_buffer(req, len(req)) for _ in range(n)]
+        cfg = LoadgenConfig()
+        cfg.host, cfg.port, cfg.concurrency = srv.host.encode(), srv.port, n
+        cfg.requests = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
+        cfg.request_sizes = (ctypes.c_uint64 * n)(*[len(req)] * n)
+        cfg.tails = (ctypes.c_void_p * n)(*[ctypes.addressof(tail)] * n)
+        cfg.tail_sizes = (ctypes.c_uint64 * n)(*[tail_bytes] * n)
+        h = ctypes.c_void_p()
+        _native.check(lib.tb200_loadgen_create(ctypes.byref(cfg), ctypes.byref(h)))
+        _native.check(lib.tb200_loadgen_start(h))
+        st = LoadgenStats()
+        _native.check(lib.tb200_loadgen_window(h, 1.0, ctypes.byref(st)))
+        lib.tb200_loadgen_stop(h)
+        lib.tb200_loadgen_destroy(h)
+        assert st.failed_request_count == 0 and st.completed_request_count >= n, (st.completed_request_count, st.failed_request_count)
+        assert st.cumulative_send_time_ns > 0
+    finally:
+        srv.stop()
