@@ -138,6 +138,7 @@ SIGNATURES = {
     "tb200_fill_async": (c_int, [c_vp, ctypes.POINTER(FillJob), c_int, c_u64, c_u64]),
     "tb200_fill_epoch_async": (c_int, [c_vp, ctypes.POINTER(FillJob), c_int, c_u64, c_u64]),
     "tb200_pack_image_async": (c_int, [c_vp, c_vp, c_u32, c_u32, c_vp, c_int, c_int, c_int, c_int, c_u32]),
+    "tb200_resize_pack_image_async": (c_int, [c_vp, c_vp, c_u32, c_u32, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_u32]),
     "tb200_cast_async": (c_int, [c_vp, c_vp, c_u32, c_vp, c_u32, c_u64]),
     "tb200_pack_strided_async": (c_int, [c_vp, c_vp, c_vp, c_u32, c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "tb200_concat_async": (c_int, [c_vp, ctypes.POINTER(CopyJob), c_int]),

@@ -542,6 +542,84 @@ pack_image_generic_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__
   }
 }
 
+// ---- resize + pack: one CTA per 32 x tile_h output tile --------------------------------
+// Phase A resamples the source rows the tile needs horizontally into shared memory
+// (8-bit, exactly Pillow's intermediate image), phase B resamples those vertically and
+// applies astype / scaling / layout on the way out.
+constexpr int kResizeBits = 22;  // Pillow: PRECISION_BITS = 32 - 8 - 2
+__device__ __forceinline__ uint32_t resize_clip8(int32_t acc) {
+  const int32_t v = acc >> kResizeBits;
+  return static_cast<uint32_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+__global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
+  extern __shared__ uint8_t rp_tmp[];  // [rows][32][c]
+  const int x0 = blockIdx.x * 32;
+  const int y0 = blockIdx.y * p.tile_h;
+  const int y1 = min(y0 + p.tile_h, p.dh) - 1;
+  const int img = blockIdx.z;
+  const int r0 = p.vbounds[y0].x;
+  const int rows = p.vbounds[y1].x + p.vbounds[y1].y - r0;
+  const int c = p.c;
+  const uint8_t* src = p.src + static_cast<size_t>(img) * p.sh * p.sw * c;
+  const int items = rows * 32 * c;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int row = i / (32 * c);
+    const int rem = i - row * 32 * c;
+    const int xl = rem / c;
+    const int ch = rem - xl * c;
+    const int x = x0 + xl;
+    uint32_t v = 0;
+    if (x < p.dw) {
+      const int2 b = p.hbounds[x];
+      const int32_t* k = p.hcoeffs + static_cast<size_t>(x) * p.hk;
+      const uint8_t* line = src + (static_cast<size_t>(r0 + row) * p.sw + b.x) * c + ch;
+      int32_t acc = 1 << (kResizeBits - 1);
+      for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(line[t * c]) * k[t];
+      v = resize_clip8(acc);
+    }
+    rp_tmp[i] = static_cast<uint8_t>(v);
+  }
+  __syncthreads();
+  const int xl = threadIdx.x & 31;
+  const int x = x0 + xl;
+  const int y = y0 + (threadIdx.x >> 5);
+  if (x >= p.dw || y > y1) return;
+  const int2 b = p.vbounds[y];
+  const int32_t* k = p.vcoeffs + static_cast<size_t>(y) * p.vk;
+  const size_t hw = static_cast<size_t>(p.dh) * p.dw;
+  for (int ch = 0; ch < c; ++ch) {
+    int32_t acc = 1 << (kResizeBits - 1);
+    const uint8_t* col = rp_tmp + (static_cast<size_t>(b.x - r0) * 32 + xl) * c + ch;
+    for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(col[static_cast<size_t>(t) * 32 * c]) * k[t];
+    const uint32_t px = resize_clip8(acc);
+    const size_t pos = static_cast<size_t>(y) * p.dw + x;
+    const size_t idx = p.layout == TB200_NCHW ? (static_cast<size_t>(img) * c + ch) * hw + pos
+                                              : (static_cast<size_t>(img) * hw + pos) * c + ch;
+    if (p.dst_dtype == kF32) {
+      static_cast<float*>(p.dst)[idx] = scale_pixel_f32(px, p.scaling, c, ch);
+    } else if (p.dst_dtype == kF16) {
+      static_cast<uint16_t*>(p.dst)[idx] = scale_pixel_f16(px, p.scaling, c, ch);
+    } else if (p.dst_dtype == TB200_BF16) {
+      static_cast<uint16_t*>(p.dst)[idx] = f32_to_bf16_trunc(scale_pixel_f32(px, p.scaling, c, ch));
+    } else {
+      static_cast<uint8_t*>(p.dst)[idx] = static_cast<uint8_t>(px);
+    }
+  }
+}
+
+cudaError_t launch_resize_pack(const ResizePack& p, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(resize_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((p.dw + 31) / 32, (p.dh + p.tile_h - 1) / p.tile_h, p.n);
+  resize_pack_kernel<<<grid, 256, p.smem_bytes, s>>>(p);
+  return cudaGetLastError();
+}
+
 template <uint32_t DST, int C>
 static cudaError_t launch_pack_tma(const ImagePack& p, int sm_count, cudaStream_t s) {
   using T = PackTraits<DST>;

@@ -45,6 +45,21 @@ struct ImagePack {
 cudaError_t launch_pack_image(const ImagePack& p, int sm_count, cudaStream_t s,
                               int* launches);
 
+// resize + cast + scaling + layout (Pillow BILINEAR semantics); tables live on the device
+struct ResizePack {
+  void* dst;
+  const uint8_t* src;
+  const int2* hbounds;    // [dst_w] (first source column, taps)
+  const int32_t* hcoeffs; // [dst_w * hk]
+  const int2* vbounds;    // [dst_h] (first source row, taps)
+  const int32_t* vcoeffs; // [dst_h * vk]
+  uint32_t dst_dtype, layout, scaling;
+  int n, sh, sw, c, dh, dw, hk, vk;
+  int tile_h;             // output rows per CTA (1..8)
+  uint32_t smem_bytes;    // rows a tile needs * 32 * c
+};
+cudaError_t launch_resize_pack(const ResizePack& p, cudaStream_t s);
+
 cudaError_t launch_cast(void* dst, uint32_t dst_dtype, const void* src,
                         uint32_t src_dtype, uint64_t nelem, int sm_count,
                         cudaStream_t s);

@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -24,6 +25,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "resample.h"
 
 namespace {
 
@@ -189,6 +191,13 @@ struct tb200_ctx {
   // epoch + flush scratch
   uint64_t* dev_epoch = nullptr;       // [0] epoch, [1] CTA-done counter of the fill kernel
   void* flush_buf = nullptr;
+  // resize coefficient tables, keyed by (src_h, src_w, dst_h, dst_w); device resident
+  struct ResizeTables {
+    int sh, sw, dh, dw, hk, vk, max_rows[4];  // max source rows a tile of 8/4/2/1 output rows needs
+    void* dev;                                // hbounds | vbounds | hcoeffs | vcoeffs
+    size_t off_vb, off_hc, off_vc;
+  };
+  std::vector<ResizeTables> resize_tables;
   // capture state
   tb200_graph* capture = nullptr;
   uint64_t capture_launches0 = 0;
@@ -388,6 +397,7 @@ int tb200_ctx_destroy(tb200_ctx* ctx) {
   if (ctx->accum) cudaFree(ctx->accum);
   if (ctx->dev_epoch) cudaFree(ctx->dev_epoch);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  for (auto& t : ctx->resize_tables) cudaFree(t.dev);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -823,6 +833,104 @@ int tb200_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype, uint32
   }
   TB200_CUDA(e);
   ctx->launches += launches;
+  return TB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// resize + pack.  Coefficients as Pillow computes them (libImaging/Resample.c,
+// precompute_coeffs + normalize_coeffs_8bpc; third-party to the reference, which calls it
+// through Image.resize at src/python/examples/image_client.py:166): for output index xx,
+// center = (xx + 0.5) * scale, triangle filter of half-width support = max(scale, 1),
+// taps [xmin, xmax) rounded to the nearest source index, weights normalised to sum 1 in
+// double precision and quantised to 22-bit fixed point with round-half-up.
+// ---------------------------------------------------------------------------
+
+int tb200_resize_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype, uint32_t dst_layout, const void* src_u8_nhwc,
+                                  int n, int src_h, int src_w, int c, int dst_h, int dst_w, uint32_t scaling) {
+  if (ctx == nullptr || dst == nullptr || src_u8_nhwc == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
+  if (dst_layout != TB200_NCHW && dst_layout != TB200_NHWC) return fail(TB200_ERR_INVALID, "unknown layout %u", dst_layout);
+  if (n <= 0 || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || (c != 1 && c != 3) || n > 65535) {
+    return fail(TB200_ERR_INVALID, "resize_pack: bad shape (n=%d, %dx%dx%d -> %dx%d)", n, src_h, src_w, c, dst_h, dst_w);
+  }
+  if (dst_dtype != TB200_FP32 && dst_dtype != TB200_FP16 && dst_dtype != TB200_BF16 && dst_dtype != TB200_UINT8) {
+    return fail(TB200_ERR_INVALID, "resize_pack: destination dtype %s is not supported", tb200_dtype_name(dst_dtype));
+  }
+  if (dst_dtype == TB200_UINT8 && scaling != TB200_SCALE_NONE) return fail(TB200_ERR_INVALID, "resize_pack: UINT8 output takes no scaling");
+  if (scaling > TB200_SCALE_VGG) return fail(TB200_ERR_INVALID, "unknown scaling %u", scaling);
+  if (static_cast<int64_t>(src_h) > 100ll * src_w) {
+    return fail(TB200_ERR_INVALID, "resize_pack: source taller than 100:1 (%dx%d); Pillow resamples those vertically first", src_h, src_w);
+  }
+  DeviceGuard g(ctx->device);
+  tb200_ctx::ResizeTables* tab = nullptr;
+  for (auto& t : ctx->resize_tables) {
+    if (t.sh == src_h && t.sw == src_w && t.dh == dst_h && t.dw == dst_w) tab = &t;
+  }
+  if (tab == nullptr) {
+    std::vector<tb200::ResampleBound> hb, vb;  // layout-compatible with int2
+    std::vector<int32_t> hc, vc;
+    tb200_ctx::ResizeTables t{};
+    t.sh = src_h; t.sw = src_w; t.dh = dst_h; t.dw = dst_w;
+    tb200::resample_coefficients(src_w, dst_w, &hb, &hc, &t.hk);
+    tb200::resample_coefficients(src_h, dst_h, &vb, &vc, &t.vk);
+    const int tiles[4] = {8, 4, 2, 1};
+    for (int i = 0; i < 4; ++i) {
+      int mr = 0;
+      for (int y0 = 0; y0 < dst_h; y0 += tiles[i]) {
+        const int y1 = std::min(y0 + tiles[i], dst_h) - 1;
+        mr = std::max(mr, vb[static_cast<size_t>(y1)].first + vb[static_cast<size_t>(y1)].count - vb[static_cast<size_t>(y0)].first);
+      }
+      t.max_rows[i] = mr;
+    }
+    static_assert(sizeof(tb200::ResampleBound) == sizeof(int2), "bounds are read as int2 on the device");
+    t.off_vb = hb.size() * sizeof(int2);
+    t.off_hc = t.off_vb + vb.size() * sizeof(int2);
+    t.off_vc = t.off_hc + hc.size() * sizeof(int32_t);
+    const size_t total = t.off_vc + vc.size() * sizeof(int32_t);
+    std::vector<char> host(total);
+    memcpy(host.data(), hb.data(), hb.size() * sizeof(int2));
+    memcpy(host.data() + t.off_vb, vb.data(), vb.size() * sizeof(int2));
+    memcpy(host.data() + t.off_hc, hc.data(), hc.size() * sizeof(int32_t));
+    memcpy(host.data() + t.off_vc, vc.data(), vc.size() * sizeof(int32_t));
+    TB200_CUDA(cudaMalloc(&t.dev, total));
+    // synchronous and outside any capture: the table outlives graphs that use it
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    const cudaError_t e = cudaMemcpy(t.dev, host.data(), total, cudaMemcpyHostToDevice);
+    cudaThreadExchangeStreamCaptureMode(&mode);
+    if (e != cudaSuccess) {
+      cudaFree(t.dev);
+      return fail(TB200_ERR_CUDA, "resize table upload failed: %s", cudaGetErrorString(e));
+    }
+    if (ctx->resize_tables.size() >= 64) {  // bounded cache: drop the oldest
+      TB200_CUDA(cudaStreamSynchronize(ctx->cur));
+      cudaFree(ctx->resize_tables.front().dev);
+      ctx->resize_tables.erase(ctx->resize_tables.begin());
+    }
+    ctx->resize_tables.push_back(t);
+    tab = &ctx->resize_tables.back();
+  }
+  ResizePack p;
+  p.dst = dst;
+  p.src = static_cast<const uint8_t*>(src_u8_nhwc);
+  const char* base = static_cast<const char*>(tab->dev);
+  p.hbounds = reinterpret_cast<const int2*>(base);
+  p.vbounds = reinterpret_cast<const int2*>(base + tab->off_vb);
+  p.hcoeffs = reinterpret_cast<const int32_t*>(base + tab->off_hc);
+  p.vcoeffs = reinterpret_cast<const int32_t*>(base + tab->off_vc);
+  p.dst_dtype = dst_dtype; p.layout = dst_layout; p.scaling = scaling;
+  p.n = n; p.sh = src_h; p.sw = src_w; p.c = c; p.dh = dst_h; p.dw = dst_w; p.hk = tab->hk; p.vk = tab->vk;
+  const int tiles[4] = {8, 4, 2, 1};
+  p.tile_h = 0;
+  for (int i = 0; i < 4 && p.tile_h == 0; ++i) {
+    const size_t bytes = static_cast<size_t>(tab->max_rows[i]) * 32 * c;
+    if (bytes <= 200u * 1024u) {
+      p.tile_h = tiles[i];
+      p.smem_bytes = static_cast<uint32_t>(bytes);
+    }
+  }
+  if (p.tile_h == 0) return fail(TB200_ERR_INVALID, "resize_pack: vertical down-scale %d -> %d needs more source rows than shared memory holds", src_h, dst_h);
+  TB200_CUDA(launch_resize_pack(p, ctx->cur));
+  ctx->launches += 1;
   return TB200_OK;
 }
 

@@ -239,6 +239,24 @@ class DeviceOps:
         self.pack_image(dst_ptr, datatype, layout, staging.ptr, n, h, w, c, scaling)
         self.sync()  # arr must stay alive until the H2D completed
 
+    def resize_pack_image(self, dst_ptr, datatype, layout, src_ptr, n, src_h, src_w, c, dst_h, dst_w, scaling="NONE"):
+        """Image.resize((dst_w, dst_h), BILINEAR) + astype + scaling + layout in one launch."""
+        _native.check(
+            self._lib.tb200_resize_pack_image_async(
+                self._ctx.handle, dst_ptr, _native.DTYPE_CODES[datatype],
+                _native.NCHW if layout == "NCHW" else _native.NHWC,
+                src_ptr, int(n), int(src_h), int(src_w), int(c), int(dst_h), int(dst_w), _native.SCALING_CODES[scaling],
+            )
+        )
+
+    def resize_pack_image_from_host(self, dst_ptr, datatype, layout, images_u8_nhwc, dst_h, dst_w, scaling="NONE"):
+        arr = np.ascontiguousarray(images_u8_nhwc, dtype=np.uint8)
+        n, h, w, c = arr.shape
+        staging = self._scratch(arr.nbytes)
+        self.h2d(staging.ptr, arr.ctypes.data, arr.nbytes)
+        self.resize_pack_image(dst_ptr, datatype, layout, staging.ptr, n, h, w, c, dst_h, dst_w, scaling)
+        self.sync()  # arr must stay alive until the H2D completed
+
     def _scratch(self, nbytes):
         cur = getattr(self, "_scratch_buf", None)
         if cur is None or cur.nbytes < nbytes:

@@ -299,12 +299,15 @@ def fill_shared_memory_region(
 
 
 def set_shared_memory_region_from_image(
-    cuda_shm_handle, images_u8_nhwc, datatype="FP32", scaling="NONE", layout="NCHW", offset=0
+    cuda_shm_handle, images_u8_nhwc, datatype="FP32", scaling="NONE", layout="NCHW", offset=0, resize=None
 ):
     """uint8 NHWC host images -> scaled ``datatype`` tensor in ``layout`` inside
-    the region.  Only the uint8 bytes cross PCIe; cast, scaling and the HWC->CHW
-    transpose run in the pack kernel (numpy equivalent:
-    src/python/examples/image_client.py:154-193)."""
+    the region.  Only the uint8 bytes cross PCIe; resize, cast, scaling and the HWC->CHW
+    transpose run in one kernel — the whole of ``image_client.preprocess``
+    (src/python/examples/image_client.py:154-193) after the decode.
+
+    ``resize=(h, w)``: ``Image.resize((w, h), Image.BILINEAR)`` first, bit-identical to
+    Pillow (antialiased triangle filter, horizontal pass first, 8-bit intermediate)."""
     from ...device import DeviceOps
 
     arr = np.ascontiguousarray(images_u8_nhwc)
@@ -313,13 +316,20 @@ def set_shared_memory_region_from_image(
     if arr.ndim == 3:
         arr = arr[None]
     n, h, w, c = arr.shape
+    out_h, out_w = (int(resize[0]), int(resize[1])) if resize is not None else (h, w)
     es = _native.DTYPE_SIZES[datatype]
-    if offset + n * h * w * c * es > cuda_shm_handle._byte_size:
+    if offset + n * out_h * out_w * c * es > cuda_shm_handle._byte_size:
         raise CudaSharedMemoryException(
             "The size of the shared memory region is insufficient for the packed images"
         )
     ops = DeviceOps(_ctx(cuda_shm_handle._device_id))
-    ops.pack_image_from_host(cuda_shm_handle._base_addr + offset, datatype, layout, arr, scaling)
+    try:
+        if resize is not None:
+            ops.resize_pack_image_from_host(cuda_shm_handle._base_addr + offset, datatype, layout, arr, out_h, out_w, scaling)
+        else:
+            ops.pack_image_from_host(cuda_shm_handle._base_addr + offset, datatype, layout, arr, scaling)
+    except _native.NativeError as ex:
+        raise CudaSharedMemoryException(str(ex)) from ex
     ops.sync()
 
 

@@ -233,6 +233,20 @@ int tb200_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
                            uint32_t dst_layout, const void* src_u8_nhwc,
                            int n, int h, int w, int c, uint32_t scaling);
 
+/* The whole image_client.preprocess (src/python/examples/image_client.py:154-193) in one
+ * launch: Image.resize((dst_w, dst_h), Image.BILINEAR) -> astype -> scaling -> layout.
+ * The resize restates Pillow's separable antialiased triangle filter bit for bit
+ * (horizontal pass first, 8-bit intermediate, 22-bit fixed-point coefficients normalised
+ * in double precision on the host; oracle/image.py pins it against Pillow itself).
+ * src: n uint8 images [src_h, src_w, c] (c = 1 or 3; decoded RGB / L pixels);
+ * dst_dtype FP32 | FP16 | BF16, or UINT8 with TB200_SCALE_NONE for the bare resize.
+ * Limits: src_h <= 100 * src_w (Pillow switches the pass order beyond), and the source
+ * rows one 32-pixel-wide output tile needs must fit into shared memory. */
+int tb200_resize_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
+                                  uint32_t dst_layout, const void* src_u8_nhwc, int n,
+                                  int src_h, int src_w, int c, int dst_h, int dst_w,
+                                  uint32_t scaling);
+
 int tb200_cast_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
                      const void* src, uint32_t src_dtype, uint64_t nelem);
 

@@ -339,6 +339,23 @@ def gen_image():
         out["src_%dx%dx%d" % (h, w, c)] = px
     np.savez_compressed(os.path.join(OUT_DIR, "image_golden.npz"), **out)
     print("wrote image_golden.npz with", len(out), "arrays")
+    # preprocess WITH a real resize (Image.resize((w, h), Image.BILINEAR) inside the reference):
+    # smooth synthetic photos so that the fixture compresses, plus noise in the low bits
+    res = {}
+    for (sh, sw, c, h, w) in [(375, 500, 3, 224, 224), (60, 80, 3, 32, 32), (48, 36, 1, 64, 48), (100, 75, 3, 40, 120)]:
+        yy, xx = np.mgrid[0:sh, 0:sw]
+        base = np.stack([(127 + 120 * np.sin(xx / (7.0 + 3 * k) + yy / 11.0 + k)) for k in range(c)], axis=2)
+        px = np.clip(base + rng.integers(-6, 7, base.shape), 0, 255).astype(np.uint8)
+        img = Image.fromarray(px if c == 3 else px[:, :, 0])
+        tag = "%dx%dx%d_to_%dx%d" % (sh, sw, c, h, w)
+        res["src_" + tag] = px
+        for dtype, scaling, fmt, fname in (("FP32", "INCEPTION", mc.ModelInput.FORMAT_NCHW, "NCHW"),
+                                           ("FP16", "VGG", mc.ModelInput.FORMAT_NHWC, "NHWC"),
+                                           ("FP16", "INCEPTION", mc.ModelInput.FORMAT_NCHW, "NCHW")):
+            ref = image_client.preprocess(img, fmt, dtype, c, h, w, scaling, "http")
+            res["%s_%s_%s_%s" % (tag, dtype, scaling, fname)] = np.ascontiguousarray(ref)
+    np.savez_compressed(os.path.join(OUT_DIR, "image_resize_golden.npz"), **res)
+    print("wrote image_resize_golden.npz with", len(res), "arrays")
 
 
 if __name__ == "__main__":

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "../../client_b200/csrc/philox.cuh"
+#include "../../client_b200/csrc/resample.h"
 
 using namespace tb200;
 
@@ -51,4 +52,19 @@ uint32_t emul_scale_f16_bits(uint32_t px, uint32_t scaling, int c, int ch) {
 }
 uint32_t emul_f32_to_f16(uint32_t bits) { return f32_to_f16_bits(bits_f32(bits)); }
 uint32_t emul_f16_to_f32(uint32_t h) { return f32_bits(f16_bits_to_f32(static_cast<uint16_t>(h))); }
+
+// the resize kernel's host tables; returns ksize, fills bounds[2*out] and coeffs[out*cap]
+int emul_resample_tables(int in_size, int out_size, int* bounds, int* coeffs, int cap) {
+  std::vector<ResampleBound> b;
+  std::vector<int32_t> c;
+  int ks = 0;
+  resample_coefficients(in_size, out_size, &b, &c, &ks);
+  if (ks > cap) return -ks;
+  for (int i = 0; i < out_size; ++i) {
+    bounds[2 * i] = b[i].first;
+    bounds[2 * i + 1] = b[i].count;
+    for (int t = 0; t < ks; ++t) coeffs[i * cap + t] = c[static_cast<size_t>(i) * ks + t];
+  }
+  return ks;
+}
 }

@@ -86,3 +86,20 @@ def test_software_half_conversions(emul):
     got = np.array([emul.emul_f32_to_f16(int(b)) for b in bits], dtype=np.uint16)
     ok = ~np.isnan(bits.view(np.float32))
     assert np.array_equal(want[ok], got[ok])
+
+
+def test_resize_tables_match_the_pillow_pinned_oracle(emul):
+    """client_b200/csrc/resample.h (what the runtime uploads for the resize kernel) ==
+    oracle.image.resample_coefficients, which tests/test_oracle.py pins against Pillow."""
+    from oracle import image
+
+    emul.emul_resample_tables.restype = ctypes.c_int
+    emul.emul_resample_tables.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    for in_size, out_size in [(500, 224), (375, 224), (224, 224), (37, 224), (1920, 224), (4000, 224), (7, 23), (23, 7), (1, 4), (449, 224), (299, 600)]:
+        want_b, want_c = image.resample_coefficients(in_size, out_size)
+        cap = want_c.shape[1]
+        bounds = np.zeros((out_size, 2), dtype=np.int32)
+        coeffs = np.zeros((out_size, cap), dtype=np.int32)
+        ks = emul.emul_resample_tables(in_size, out_size, bounds.ctypes.data, coeffs.ctypes.data, cap)
+        assert ks == cap
+        assert np.array_equal(bounds, want_b) and np.array_equal(coeffs, want_c), (in_size, out_size)

@@ -452,3 +452,93 @@ def test_step_sync_call(gpu_ops):
     assert np.array_equal(got[n:], cref.fill(n, "FP32", seed=3, stream=1 + 9))
     gpu_ops.step(jobs, [], res.device_ptr, seed=4)  # no validation this time
     assert np.array_equal(gpu_ops.download(buf.ptr, n), cref.fill(n, "FP32", seed=4, stream=0))
+
+
+# ---- resize + pack (image_client.preprocess with its Image.resize) ---------------------------
+def _resize_on_device(ops, src, dtype, layout, scaling, oh, ow):
+    from client_b200.device import DeviceBuffer
+
+    n, sh, sw, c = src.shape
+    es = {"FP32": 4, "FP16": 2, "BF16": 2, "UINT8": 1}[dtype]
+    dsrc = ops.upload(src)
+    dst = DeviceBuffer(0, n * oh * ow * c * es)
+    ops.resize_pack_image(dst.ptr, dtype, layout, dsrc.ptr, n, sh, sw, c, oh, ow, scaling)
+    ops.sync()
+    return ops.download(dst.ptr, n * oh * ow * c * es)
+
+
+def test_resize_pack_against_reference_goldens():
+    """Device resize + cast + scaling + layout == the reference's preprocess output
+    (tests/golden/image_resize_golden.npz, generated from image_client.preprocess)."""
+    from client_b200 import _native
+    from client_b200.device import DeviceOps
+    from test_oracle import _resize_golden_cases
+
+    ops = DeviceOps(_native.default_context(0))
+    n = 0
+    for key, src, ref, dtype, scaling, layout, oh, ow in _resize_golden_cases():
+        got = _resize_on_device(ops, src[None], dtype, layout, scaling, oh, ow)
+        assert np.array_equal(got, np.frombuffer(np.ascontiguousarray(ref).tobytes(), np.uint8)), key
+        n += 1
+    assert n == 12
+
+
+@pytest.mark.parametrize("shape", [(375, 500, 224, 224), (224, 224, 224, 224), (100, 37, 224, 224), (1080, 1920, 224, 224),
+                                   (224, 500, 224, 224), (300, 224, 224, 224), (17, 23, 5, 7), (5, 7, 17, 23), (600, 600, 299, 299),
+                                   (1, 1, 4, 4), (449, 449, 224, 224), (2900, 30, 61, 48), (30, 3500, 48, 64), (4000, 3000, 224, 224)])
+def test_resize_bare_u8_matches_pillow_pinned_oracle(shape):
+    """UINT8 output = the bare Image.resize((w, h), BILINEAR): random pixels, batches of 2,
+    c = 1 and 3, up/down/one-axis/identity/extreme scales."""
+    from client_b200 import _native
+    from client_b200.device import DeviceOps
+    from oracle import image
+
+    sh, sw, oh, ow = shape
+    ops = DeviceOps(_native.default_context(0))
+    rng = np.random.default_rng(sh * 7 + sw)
+    for c in (3, 1):
+        src = rng.integers(0, 256, (2, sh, sw, c), dtype=np.uint8)
+        got = _resize_on_device(ops, src, "UINT8", "NHWC", "NONE", oh, ow).reshape(2, oh, ow, c)
+        for i in range(2):
+            assert np.array_equal(got[i], image.pil_bilinear_resize(src[i], oh, ow)), (shape, c, i)
+
+
+def test_resize_pack_dtypes_layouts_and_errors():
+    from client_b200 import _native
+    from client_b200.device import DeviceBuffer, DeviceOps
+    from oracle import cref, image
+
+    ops = DeviceOps(_native.default_context(0))
+    rng = np.random.default_rng(9)
+    src = rng.integers(0, 256, (3, 90, 130, 3), dtype=np.uint8)
+    resized = np.stack([image.pil_bilinear_resize(s, 64, 48) for s in src])
+    for dtype in ("FP32", "FP16", "BF16"):
+        for layout in ("NCHW", "NHWC"):
+            for scaling in ("NONE", "INCEPTION", "VGG"):
+                got = _resize_on_device(ops, src, dtype, layout, scaling, 64, 48)
+                assert np.array_equal(got, cref.pack_image(resized, dtype, layout, scaling)), (dtype, layout, scaling)
+    d = DeviceBuffer(0, 1 << 20)
+    with pytest.raises(_native.NativeError, match="100:1"):
+        ops.resize_pack_image(d.ptr, "FP32", "NCHW", d.ptr, 1, 3100, 30, 3, 8, 8, "NONE")
+    with pytest.raises(_native.NativeError, match="no scaling"):
+        ops.resize_pack_image(d.ptr, "UINT8", "NCHW", d.ptr, 1, 30, 30, 3, 8, 8, "VGG")
+    with pytest.raises(_native.NativeError, match="bad shape"):
+        ops.resize_pack_image(d.ptr, "FP32", "NCHW", d.ptr, 1, 30, 30, 2, 8, 8, "NONE")
+    with pytest.raises(_native.NativeError, match="shared memory"):
+        ops.resize_pack_image(d.ptr, "FP32", "NCHW", d.ptr, 1, 100000, 1001, 3, 8, 8, "NONE")
+
+
+def test_set_shared_memory_region_from_image_with_resize():
+    import client_b200.utils.cuda_shared_memory as cudashm
+    from oracle import cref, image
+
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (375, 500, 3), dtype=np.uint8)
+    h = cudashm.create_shared_memory_region("resize_in", 3 * 224 * 224 * 4, 0)
+    cudashm.set_shared_memory_region_from_image(h, img, "FP32", "INCEPTION", resize=(224, 224))
+    got = cudashm.get_contents_as_numpy(h, np.float32, [3, 224, 224])
+    want = cref.pack_image(image.pil_bilinear_resize(img, 224, 224)[None], "FP32", "NCHW", "INCEPTION")
+    assert np.array_equal(got.view(np.uint8).reshape(-1), want)
+    with pytest.raises(cudashm.CudaSharedMemoryException):
+        cudashm.set_shared_memory_region_from_image(h, img, "FP32", "INCEPTION", resize=(448, 448))
+    cudashm.destroy_shared_memory_region(h)

@@ -236,3 +236,43 @@ def test_topk_oracle_is_numpy_stable_argsort():
         assert np.array_equal(idx[:m], order.astype(np.uint32)[:m])
         assert np.array_equal(vals[:m], x[order[:m]], equal_nan=True)
         assert (idx[m:] == 0xFFFFFFFF).all()
+
+
+def test_resize_oracle_is_pillow_bilinear():
+    """oracle.image.pil_bilinear_resize == Image.resize((w, h), Image.BILINEAR), the call of
+    image_client.preprocess (src/python/examples/image_client.py:166): up- and down-scaling,
+    one axis only, identity, extreme aspect ratios (pass order switch at 100:1)."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(3)
+    cases = [(375, 500, 224, 224), (224, 224, 224, 224), (100, 37, 224, 224), (1080, 1920, 224, 224), (224, 500, 224, 224),
+             (300, 224, 224, 224), (17, 23, 5, 7), (5, 7, 17, 23), (600, 600, 299, 299), (1, 1, 4, 4), (449, 449, 224, 224),
+             (2, 3, 64, 64), (3000, 30, 64, 48), (3030, 30, 64, 48), (30, 3500, 48, 64)]
+    for h, w, oh, ow in cases:
+        for c in (3, 1):
+            a = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+            pil = np.array(Image.fromarray(a if c == 3 else a[:, :, 0]).resize((ow, oh), Image.BILINEAR))
+            if pil.ndim == 2:
+                pil = pil[:, :, None]
+            assert np.array_equal(image.pil_bilinear_resize(a, oh, ow), pil), (h, w, oh, ow, c)
+
+
+def _resize_golden_cases():
+    z = np.load(os.path.join(GOLD, "image_resize_golden.npz"))
+    for key in z.files:
+        if key.startswith("src_"):
+            continue
+        tag, dtype, scaling, layout = key.rsplit("_", 3)
+        oh, ow = (int(v) for v in tag.split("_to_")[1].split("x"))
+        yield key, z["src_" + tag], z[key], dtype, scaling, layout, oh, ow
+
+
+def test_resize_and_pack_oracle_against_reference_preprocess():
+    """The reference's image_client.preprocess WITH its Image.resize (fixtures generated by
+    oracle/gen_golden.py from the reference itself): resize oracle + scaling oracle."""
+    n = 0
+    for key, src, ref, dtype, scaling, layout, oh, ow in _resize_golden_cases():
+        resized = image.pil_bilinear_resize(src, oh, ow)
+        want = np.frombuffer(np.ascontiguousarray(ref).tobytes(), np.uint8)
+        assert np.array_equal(image.pack_batch(resized[None], dtype, layout, scaling), want), key
+        n += 1
+    assert n == 12
