@@ -552,58 +552,123 @@ __device__ __forceinline__ uint32_t resize_clip8(int32_t acc) {
   return static_cast<uint32_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
+// shared memory: raw source block [rows][raw_stride] | horizontally resampled [rows][32*C] |
+// the tile's coefficients (32*hk + tile_h*vk int32) | per-row alignment shifts
+template <int C>
 __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
-  extern __shared__ uint8_t rp_tmp[];  // [rows][32][c]
+  extern __shared__ __align__(16) uint8_t rp_smem[];
+  constexpr int P = 32 * C;  // (column, channel) pairs of a tile
   const int x0 = blockIdx.x * 32;
+  const int xe = min(x0 + 32, p.dw) - 1;
   const int y0 = blockIdx.y * p.tile_h;
   const int y1 = min(y0 + p.tile_h, p.dh) - 1;
   const int img = blockIdx.z;
   const int r0 = p.vbounds[y0].x;
   const int rows = p.vbounds[y1].x + p.vbounds[y1].y - r0;
-  const int c = p.c;
-  const uint8_t* src = p.src + static_cast<size_t>(img) * p.sh * p.sw * c;
-  const int items = rows * 32 * c;
-  for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int row = i / (32 * c);
-    const int rem = i - row * 32 * c;
-    const int xl = rem / c;
-    const int ch = rem - xl * c;
-    const int x = x0 + xl;
-    uint32_t v = 0;
-    if (x < p.dw) {
-      const int2 b = p.hbounds[x];
-      const int32_t* k = p.hcoeffs + static_cast<size_t>(x) * p.hk;
-      const uint8_t* line = src + (static_cast<size_t>(r0 + row) * p.sw + b.x) * c + ch;
-      int32_t acc = 1 << (kResizeBits - 1);
-      for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(line[t * c]) * k[t];
-      v = resize_clip8(acc);
+  const int c0 = p.hbounds[x0].x;
+  const int span = p.hbounds[xe].x + p.hbounds[xe].y - c0;  // source columns the tile reads
+  uint8_t* raw = rp_smem;
+  uint8_t* tmp = rp_smem + static_cast<size_t>(p.max_rows) * p.raw_stride;
+  int32_t* hk_s = reinterpret_cast<int32_t*>(tmp + ((static_cast<size_t>(p.max_rows) * P + 15) & ~static_cast<size_t>(15)));
+  int32_t* vk_s = hk_s + 32 * p.hk;
+  uint8_t* shift_s = reinterpret_cast<uint8_t*>(vk_s + p.tile_h * p.vk);
+  const uint8_t* src = p.src + static_cast<size_t>(img) * p.sh * p.sw * C;
+  const uint8_t* src_end = p.src + static_cast<size_t>(p.n) * p.sh * p.sw * C;
+
+  // phase 0: the source block as aligned 4-byte words (row starts are arbitrary byte addresses)
+  for (int row = threadIdx.x >> 5; row < rows; row += 8) {
+    const uint8_t* g = src + (static_cast<size_t>(r0 + row) * p.sw + c0) * C;
+    const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 3u);
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(g - shift);
+    const int nwords = (static_cast<int>(shift) + span * C + 3) >> 2;
+    uint32_t* sw_ = reinterpret_cast<uint32_t*>(raw + static_cast<size_t>(row) * p.raw_stride);
+    if ((threadIdx.x & 31) == 0) shift_s[row] = static_cast<uint8_t>(shift);
+    for (int w = threadIdx.x & 31; w < nwords; w += 32) {
+      const uint8_t* wp = reinterpret_cast<const uint8_t*>(gw + w);
+      uint32_t val = 0;
+      if (wp >= p.src && wp + 4 <= src_end) {
+        val = __ldg(gw + w);
+      } else {  // first / last word of the whole source: stay inside the buffer
+        for (int bb = 0; bb < 4; ++bb) {
+          if (wp + bb >= p.src && wp + bb < src_end) val |= static_cast<uint32_t>(wp[bb]) << (8 * bb);
+        }
+      }
+      sw_[w] = val;
     }
-    rp_tmp[i] = static_cast<uint8_t>(v);
+  }
+  for (int i = threadIdx.x; i < 32 * p.hk; i += 256) {
+    const int xl = i / p.hk;
+    hk_s[i] = (x0 + xl < p.dw) ? p.hcoeffs[static_cast<size_t>(x0) * p.hk + i] : 0;
+  }
+  for (int i = threadIdx.x; i < p.tile_h * p.vk; i += 256) {
+    const int yl = i / p.vk;
+    vk_s[i] = (y0 + yl < p.dh) ? p.vcoeffs[static_cast<size_t>(y0) * p.vk + i] : 0;
   }
   __syncthreads();
+
+  // phase A: horizontal pass into 8-bit rows (Pillow's intermediate image).  A thread keeps one
+  // (column, channel) pair and its taps in registers and walks down the rows.
+  {
+    constexpr int RG = 256 / P;  // row groups (2 for RGB: 192 threads busy, 8 for grey)
+    const int pair = threadIdx.x % P;
+    const int rg = threadIdx.x / P;
+    if (rg < RG) {
+      const int xl = pair / C;
+      const int ch = pair - xl * C;
+      const bool live = x0 + xl < p.dw;
+      const int2 b = live ? p.hbounds[x0 + xl] : make_int2(c0, 0);
+      const int32_t* k = hk_s + xl * p.hk;
+      const int off = (b.x - c0) * C + ch;
+      if (b.y <= 8) {
+        int32_t kr[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) kr[t] = t < b.y ? k[t] : 0;
+        const int last = b.y > 0 ? b.y - 1 : 0;
+        for (int row = rg; row < rows; row += RG) {
+          const uint8_t* line = raw + static_cast<size_t>(row) * p.raw_stride + shift_s[row] + off;
+          int32_t acc = 1 << (kResizeBits - 1);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc += static_cast<int32_t>(line[min(t, last) * C]) * kr[t];  // kr[t] == 0 past the taps
+          tmp[row * P + pair] = static_cast<uint8_t>(live ? resize_clip8(acc) : 0u);
+        }
+      } else {
+        for (int row = rg; row < rows; row += RG) {
+          const uint8_t* line = raw + static_cast<size_t>(row) * p.raw_stride + shift_s[row] + off;
+          int32_t acc = 1 << (kResizeBits - 1);
+          for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(line[t * C]) * k[t];
+          tmp[row * P + pair] = static_cast<uint8_t>(resize_clip8(acc));
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase B: vertical pass + astype / scaling / layout
   const int xl = threadIdx.x & 31;
   const int x = x0 + xl;
-  const int y = y0 + (threadIdx.x >> 5);
-  if (x >= p.dw || y > y1) return;
-  const int2 b = p.vbounds[y];
-  const int32_t* k = p.vcoeffs + static_cast<size_t>(y) * p.vk;
+  if (x >= p.dw) return;
   const size_t hw = static_cast<size_t>(p.dh) * p.dw;
-  for (int ch = 0; ch < c; ++ch) {
-    int32_t acc = 1 << (kResizeBits - 1);
-    const uint8_t* col = rp_tmp + (static_cast<size_t>(b.x - r0) * 32 + xl) * c + ch;
-    for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(col[static_cast<size_t>(t) * 32 * c]) * k[t];
-    const uint32_t px = resize_clip8(acc);
+  for (int y = y0 + (threadIdx.x >> 5); y <= y1; y += 8) {
+    const int2 b = p.vbounds[y];
+    const int32_t* k = vk_s + (y - y0) * p.vk;
     const size_t pos = static_cast<size_t>(y) * p.dw + x;
-    const size_t idx = p.layout == TB200_NCHW ? (static_cast<size_t>(img) * c + ch) * hw + pos
-                                              : (static_cast<size_t>(img) * hw + pos) * c + ch;
-    if (p.dst_dtype == kF32) {
-      static_cast<float*>(p.dst)[idx] = scale_pixel_f32(px, p.scaling, c, ch);
-    } else if (p.dst_dtype == kF16) {
-      static_cast<uint16_t*>(p.dst)[idx] = scale_pixel_f16(px, p.scaling, c, ch);
-    } else if (p.dst_dtype == TB200_BF16) {
-      static_cast<uint16_t*>(p.dst)[idx] = f32_to_bf16_trunc(scale_pixel_f32(px, p.scaling, c, ch));
-    } else {
-      static_cast<uint8_t*>(p.dst)[idx] = static_cast<uint8_t>(px);
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+      int32_t acc = 1 << (kResizeBits - 1);
+      const uint8_t* col = tmp + (b.x - r0) * P + xl * C + ch;
+      for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(col[t * P]) * k[t];
+      const uint32_t px = resize_clip8(acc);
+      const size_t idx = p.layout == TB200_NCHW ? (static_cast<size_t>(img) * C + ch) * hw + pos
+                                                : (static_cast<size_t>(img) * hw + pos) * C + ch;
+      if (p.dst_dtype == kF32) {
+        static_cast<float*>(p.dst)[idx] = scale_pixel_f32(px, p.scaling, C, ch);
+      } else if (p.dst_dtype == kF16) {
+        static_cast<uint16_t*>(p.dst)[idx] = scale_pixel_f16(px, p.scaling, C, ch);
+      } else if (p.dst_dtype == TB200_BF16) {
+        static_cast<uint16_t*>(p.dst)[idx] = f32_to_bf16_trunc(scale_pixel_f32(px, p.scaling, C, ch));
+      } else {
+        static_cast<uint8_t*>(p.dst)[idx] = static_cast<uint8_t>(px);
+      }
     }
   }
 }
@@ -611,12 +676,14 @@ __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
 cudaError_t launch_resize_pack(const ResizePack& p, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(resize_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(resize_pack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resize_pack_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid((p.dw + 31) / 32, (p.dh + p.tile_h - 1) / p.tile_h, p.n);
-  resize_pack_kernel<<<grid, 256, p.smem_bytes, s>>>(p);
+  if (p.c == 1) resize_pack_kernel<1><<<grid, 256, p.smem_bytes, s>>>(p);
+  else resize_pack_kernel<3><<<grid, 256, p.smem_bytes, s>>>(p);
   return cudaGetLastError();
 }
 

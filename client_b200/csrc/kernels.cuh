@@ -56,7 +56,9 @@ struct ResizePack {
   uint32_t dst_dtype, layout, scaling;
   int n, sh, sw, c, dh, dw, hk, vk;
   int tile_h;             // output rows per CTA (1..8)
-  uint32_t smem_bytes;    // rows a tile needs * 32 * c
+  int max_rows;           // source rows the tallest tile needs
+  uint32_t raw_stride;    // bytes per staged source row (widest tile's span * c + slack, 16-aligned)
+  uint32_t smem_bytes;    // max_rows * (raw_stride + 32 * c) + coefficient tables
 };
 cudaError_t launch_resize_pack(const ResizePack& p, cudaStream_t s);
 

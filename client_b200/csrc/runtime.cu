@@ -193,7 +193,8 @@ struct tb200_ctx {
   void* flush_buf = nullptr;
   // resize coefficient tables, keyed by (src_h, src_w, dst_h, dst_w); device resident
   struct ResizeTables {
-    int sh, sw, dh, dw, hk, vk, max_rows[4];  // max source rows a tile of 8/4/2/1 output rows needs
+    int sh, sw, dh, dw, hk, vk, max_rows[6];  // max source rows a tile of 32/16/8/4/2/1 output rows needs
+    int max_span;                             // max source columns a 32-column output tile needs
     void* dev;                                // hbounds | vbounds | hcoeffs | vcoeffs
     size_t off_vb, off_hc, off_vc;
   };
@@ -872,8 +873,8 @@ int tb200_resize_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
     t.sh = src_h; t.sw = src_w; t.dh = dst_h; t.dw = dst_w;
     tb200::resample_coefficients(src_w, dst_w, &hb, &hc, &t.hk);
     tb200::resample_coefficients(src_h, dst_h, &vb, &vc, &t.vk);
-    const int tiles[4] = {8, 4, 2, 1};
-    for (int i = 0; i < 4; ++i) {
+    const int tiles[6] = {32, 16, 8, 4, 2, 1};
+    for (int i = 0; i < 6; ++i) {
       int mr = 0;
       for (int y0 = 0; y0 < dst_h; y0 += tiles[i]) {
         const int y1 = std::min(y0 + tiles[i], dst_h) - 1;
@@ -882,6 +883,10 @@ int tb200_resize_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
       t.max_rows[i] = mr;
     }
     static_assert(sizeof(tb200::ResampleBound) == sizeof(int2), "bounds are read as int2 on the device");
+    for (int x0 = 0; x0 < dst_w; x0 += 32) {
+      const int xe = std::min(x0 + 32, dst_w) - 1;
+      t.max_span = std::max(t.max_span, hb[static_cast<size_t>(xe)].first + hb[static_cast<size_t>(xe)].count - hb[static_cast<size_t>(x0)].first);
+    }
     t.off_vb = hb.size() * sizeof(int2);
     t.off_hc = t.off_vb + vb.size() * sizeof(int2);
     t.off_vc = t.off_hc + hc.size() * sizeof(int32_t);
@@ -919,16 +924,26 @@ int tb200_resize_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
   p.vcoeffs = reinterpret_cast<const int32_t*>(base + tab->off_vc);
   p.dst_dtype = dst_dtype; p.layout = dst_layout; p.scaling = scaling;
   p.n = n; p.sh = src_h; p.sw = src_w; p.c = c; p.dh = dst_h; p.dw = dst_w; p.hk = tab->hk; p.vk = tab->vk;
-  const int tiles[4] = {8, 4, 2, 1};
+  // the tallest tile whose block fits: taller tiles repeat less of the horizontal pass, but
+  // stay within 40 KB while possible so that several CTAs share an SM
+  const int tiles[6] = {32, 16, 8, 4, 2, 1};
   p.tile_h = 0;
-  for (int i = 0; i < 4 && p.tile_h == 0; ++i) {
-    const size_t bytes = static_cast<size_t>(tab->max_rows[i]) * 32 * c;
-    if (bytes <= 200u * 1024u) {
-      p.tile_h = tiles[i];
-      p.smem_bytes = static_cast<uint32_t>(bytes);
+  p.raw_stride = static_cast<uint32_t>((tab->max_span * c + 3 + 4 + 15) & ~15);  // + alignment shift + word tail
+  for (int pass = 0; pass < 2 && p.tile_h == 0; ++pass) {
+    const size_t limit = pass == 0 ? 40u * 1024u : 200u * 1024u;
+    for (int i = 0; i < 6 && p.tile_h == 0; ++i) {
+      const size_t tmp_bytes = (static_cast<size_t>(tab->max_rows[i]) * 32 * c + 15) & ~static_cast<size_t>(15);
+      const size_t bytes = static_cast<size_t>(tab->max_rows[i]) * p.raw_stride + tmp_bytes +
+                           (32 * static_cast<size_t>(tab->hk) + static_cast<size_t>(tiles[i]) * tab->vk) * sizeof(int32_t) +
+                           ((static_cast<size_t>(tab->max_rows[i]) + 15) & ~static_cast<size_t>(15));
+      if (bytes <= limit) {
+        p.tile_h = tiles[i];
+        p.max_rows = tab->max_rows[i];
+        p.smem_bytes = static_cast<uint32_t>(bytes);
+      }
     }
   }
-  if (p.tile_h == 0) return fail(TB200_ERR_INVALID, "resize_pack: vertical down-scale %d -> %d needs more source rows than shared memory holds", src_h, dst_h);
+  if (p.tile_h == 0) return fail(TB200_ERR_INVALID, "resize_pack: down-scale %dx%d -> %dx%d needs a larger source block per tile than shared memory holds", src_h, src_w, dst_h, dst_w);
   TB200_CUDA(launch_resize_pack(p, ctx->cur));
   ctx->launches += 1;
   return TB200_OK;
