@@ -552,6 +552,47 @@ __device__ __forceinline__ uint32_t resize_clip8(int32_t acc) {
   return static_cast<uint32_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
+// N-tap dot product of bytes at stride `step` with int32 coefficients, N a compile-time bound
+template <int N>
+__device__ __forceinline__ int32_t resize_dot(const uint8_t* px, int step, const int32_t* k) {
+  int32_t acc = 1 << (kResizeBits - 1);
+#pragma unroll
+  for (int t = 0; t < N; ++t) acc += static_cast<int32_t>(px[t * step]) * k[t];
+  return acc;
+}
+// the same with a run-time tap count: warp-uniform `n` picks the unrolled body
+__device__ __forceinline__ int32_t resize_dot_n(const uint8_t* px, int step, const int32_t* k, int n) {
+  switch (n) {
+    case 1: return resize_dot<1>(px, step, k);
+    case 2: return resize_dot<2>(px, step, k);
+    case 3: return resize_dot<3>(px, step, k);
+    case 4: return resize_dot<4>(px, step, k);
+    case 5: return resize_dot<5>(px, step, k);
+    case 6: return resize_dot<6>(px, step, k);
+    case 7: return resize_dot<7>(px, step, k);
+    case 8: return resize_dot<8>(px, step, k);
+    default: {
+      int32_t acc = 1 << (kResizeBits - 1);
+      for (int t = 0; t < n; ++t) acc += static_cast<int32_t>(px[t * step]) * k[t];
+      return acc;
+    }
+  }
+}
+
+// phase A inner loop for one (column, channel) pair with N unrolled taps (taps past the
+// pair's own count carry a zero coefficient and re-read the last valid pixel)
+template <int N, int C>
+__device__ __forceinline__ void resize_rows(const uint8_t* rowp, uint8_t* outp, const uint8_t* shift_s, const int32_t (&kr)[8],
+                                            int last, int row0, int rows, int row_step, uint32_t raw_step, int out_step, bool live) {
+  for (int row = row0; row < rows; row += row_step, rowp += raw_step, outp += out_step) {
+    const uint8_t* line = rowp + shift_s[row];
+    int32_t acc = 1 << (kResizeBits - 1);
+#pragma unroll
+    for (int t = 0; t < N; ++t) acc += static_cast<int32_t>(line[min(t, last) * C]) * kr[t];
+    *outp = static_cast<uint8_t>(live ? resize_clip8(acc) : 0u);
+  }
+}
+
 // shared memory: raw source block [rows][raw_stride] | horizontally resampled [rows][32*C] |
 // the tile's coefficients (32*hk + tile_h*vk int32) | per-row alignment shifts
 template <int C>
@@ -619,17 +660,23 @@ __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
       const int2 b = live ? p.hbounds[x0 + xl] : make_int2(c0, 0);
       const int32_t* k = hk_s + xl * p.hk;
       const int off = (b.x - c0) * C + ch;
-      if (b.y <= 8) {
+      const int nmax = __reduce_max_sync(0xFFFFFFFFu, b.y);  // P is a multiple of 32: whole warps are here
+      if (nmax <= 8) {
         int32_t kr[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) kr[t] = t < b.y ? k[t] : 0;
         const int last = b.y > 0 ? b.y - 1 : 0;
-        for (int row = rg; row < rows; row += RG) {
-          const uint8_t* line = raw + static_cast<size_t>(row) * p.raw_stride + shift_s[row] + off;
-          int32_t acc = 1 << (kResizeBits - 1);
-#pragma unroll
-          for (int t = 0; t < 8; ++t) acc += static_cast<int32_t>(line[min(t, last) * C]) * kr[t];  // kr[t] == 0 past the taps
-          tmp[row * P + pair] = static_cast<uint8_t>(live ? resize_clip8(acc) : 0u);
+        const uint8_t* rowp = raw + static_cast<size_t>(rg) * p.raw_stride + off;
+        uint8_t* outp = tmp + rg * P + pair;
+        const uint32_t raw_step = RG * p.raw_stride;
+        switch (nmax) {
+          case 0: case 1: case 2: case 3:
+            resize_rows<3, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
+          case 4: resize_rows<4, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
+          case 5: resize_rows<5, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
+          case 6: resize_rows<6, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
+          case 7: resize_rows<7, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
+          default: resize_rows<8, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
         }
       } else {
         for (int row = rg; row < rows; row += RG) {
@@ -654,10 +701,8 @@ __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
     const size_t pos = static_cast<size_t>(y) * p.dw + x;
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) {
-      int32_t acc = 1 << (kResizeBits - 1);
       const uint8_t* col = tmp + (b.x - r0) * P + xl * C + ch;
-      for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(col[t * P]) * k[t];
-      const uint32_t px = resize_clip8(acc);
+      const uint32_t px = resize_clip8(resize_dot_n(col, P, k, b.y));  // b.y is warp-uniform (one y per warp)
       const size_t idx = p.layout == TB200_NCHW ? (static_cast<size_t>(img) * C + ch) * hw + pos
                                                 : (static_cast<size_t>(img) * hw + pos) * C + ch;
       if (p.dst_dtype == kF32) {

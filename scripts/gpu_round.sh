@@ -27,5 +27,7 @@ timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k re
 echo "ncu pack rc=$?"
 timeout -s KILL 600 ncu --set full --clock-control none -k regex:check_kernel -s 1 -c 1 -f -o gpurun_out/prof_check \
     python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-loopback > gpurun_out/ncu_check.log 2>&1
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:resize_pack -s 2 -c 1 -f -o gpurun_out/prof_resize \
+    python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-loopback > gpurun_out/ncu_resize.log 2>&1
 fi
 ls -la gpurun_out
