@@ -343,7 +343,8 @@ def test_check_kinds(gpu_ops):
     assert int(r[5]["sum"]) == 0 and int(r[5]["mismatches"]) == 0
     # finite logits: argmax equals numpy's
     logits2 = rng.standard_normal(1000).astype(np.float32)
-    out = gpu_ops.check_one("top1", gpu_ops.upload(logits2).ptr, 4000)
+    dlog = gpu_ops.upload(logits2)  # keep the buffer alive for the launch
+    out = gpu_ops.check_one("top1", dlog.ptr, 4000)
     assert out["argmax"] == int(np.argmax(logits2)) and out["max_value"] == float(logits2.max())
 
 
