@@ -107,6 +107,9 @@ def _specs(args, client, protocol):
 def run_instance(args, device_id, prefix, out_queue=None, staging_factory=None):
     protocol = args.protocol.lower()
     url = args.url or ("localhost:8001" if protocol == "grpc" else "localhost:8000")
+    if "," in url:  # one server per GPU instance: -u host:p0,host:p1,...
+        urls = [u.strip() for u in url.split(",") if u.strip()]
+        url = urls[device_id % len(urls)]
     make_client = _client_factory(protocol, url, args.verbose)
     control = make_client()
     inputs, outputs = _specs(args, control, protocol)
