@@ -25,6 +25,29 @@ timeout 300 python scripts/cpu_client_baseline.py -u 127.0.0.1:18100 --concurren
 kill $SRV
 wait $SRV 2>/dev/null
 cat gpurun_out/native_server.log >> gpurun_out/perf_native.txt
+{
+echo "## generator capacity against the canned-response server (no model, no second CUDA context)"
+timeout 200 python - <<'PY'
+import json
+from client_b200.perf.loadgen import SlotSet, TensorSpec
+from client_b200.perf.native import NativeLoadGenerator, StubServer
+stub = StubServer()
+c2 = ([TensorSpec("data_0", "FP32", [3, 224, 224])], [TensorSpec("fc6_1", "FP32", [1000])])
+c4 = ([TensorSpec("input_ids", "INT64", [1, 384]), TensorSpec("attention_mask", "INT64", [1, 384])], [TensorSpec("logits", "FP32", [1, 2])])
+c5 = ([TensorSpec("input_ids", "INT32", [1, 4096])], [TensorSpec("logits", "FP32", [1, 16])])
+for label, (ins, outs), shm, conc in (("C2 cuda-shm", c2, "cuda", 64), ("C2 cuda-shm", c2, "cuda", 256),
+                                      ("C4 bert wire (HTTP binary body from pinned staging)", c4, "none", 256),
+                                      ("C5 llama prompt wire", c5, "none", 256),
+                                      ("C2 wire (602 KB bodies)", c2, "none", 64)):
+    ss = SlotSet(ins, outs, conc, shm, 0, "random", 1, {"input_ids": (0, 30522), "attention_mask": (0, 2)}, name_prefix="cap%s%d" % (shm, conc))
+    gen = NativeLoadGenerator(stub.url, "m", "", ss, conc, regenerate=True, validate=(shm == "cuda"))
+    gen.start(); gen.window(0.5); w = gen.window(2.0); gen.stop(); ss.close()
+    print(json.dumps({"case": label, "concurrency": conc, "infer_per_s": round(w["throughput"]), "p50_us": w["p50_us"], "failed": w["failed"],
+                      "slots_per_pass": round(w["device_slots"] / max(1, w["device_batches"]), 1),
+                      "input_gbps": round(w["throughput"] * ss.in_bytes / 1e9, 2)}))
+stub.stop()
+PY
+} >> gpurun_out/perf_native.txt 2>&1
 # ---- the same comparison with client and server sharing the GPU through CUDA MPS
 if which nvidia-cuda-mps-control > /dev/null 2>&1; then
   export CUDA_MPS_PIPE_DIRECTORY=/tmp/mps_pipe CUDA_MPS_LOG_DIRECTORY=/tmp/mps_log
