@@ -82,7 +82,8 @@ __device__ __forceinline__ void fill_segment_random(uint8_t* __restrict__ dst, u
     for (int k = 0; k < UNROLL; ++k) {
       const uint64_t g = g0 + i + k * THREADS;
       const U32x4 r = philox4x32_10_rk<ROUNDS>(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), s_lo, s_hi, rk);
-      o[k] = fill_group(DT, r, p);
+      if constexpr (DT == kBytes) o[k] = fill_group_bytes(r, g, static_cast<uint32_t>(p.irange));
+      else o[k] = fill_group(DT, r, p);
     }
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k) st_cs_v4(dst + (g0 + i + k * THREADS) * 16, o[k]);
@@ -90,7 +91,9 @@ __device__ __forceinline__ void fill_segment_random(uint8_t* __restrict__ dst, u
   for (; i < count; i += THREADS) {
     const uint64_t g = g0 + i;
     const U32x4 r = philox4x32_10_rk<ROUNDS>(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), s_lo, s_hi, rk);
-    const U32x4 o = fill_group(DT, r, p);
+    U32x4 o;
+    if constexpr (DT == kBytes) o = fill_group_bytes(r, g, static_cast<uint32_t>(p.irange));
+    else o = fill_group(DT, r, p);
     if (i < full) {
       st_cs_v4(dst + g * 16, o);
     } else {
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fill_kernel(const FillLaunch L)
         case kI32: case kU32: TB200_FILL_CASE(kI32);
         case kI16: case kU16: TB200_FILL_CASE(kI16);
         case kI8: case kU8: TB200_FILL_CASE(kI8);
+        case kBytes: TB200_FILL_CASE(kBytes);
         default: TB200_FILL_CASE(kBool);
       }
 #undef TB200_FILL_CASE

@@ -387,6 +387,30 @@ TB200_HD U32x4 fill_group(uint32_t dtype, U32x4 r, const FillParams& p) {
   return o;
 }
 
+// BYTES tensors of fixed-length strings (perf_analyzer's --string-length inputs): the
+// serialised form of PY/utils/__init__.py:208-261 generated in place -- element e occupies
+// bytes [e*(4+L), (e+1)*(4+L)): a little-endian u32 length L, then L characters.  Byte i
+// of group g takes Philox byte i of that group; a character is "0-9A-Za-z"[(b * 62) >> 8].
+TB200_HD uint32_t alnum_char(uint32_t b) {
+  const uint32_t k = (b * 62u) >> 8;
+  return k < 10u ? 48u + k : (k < 36u ? 55u + k : 61u + k);
+}
+TB200_HD U32x4 fill_group_bytes(U32x4 r, uint64_t g, uint32_t len) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t out[4] = {0u, 0u, 0u, 0u};
+  const uint32_t per = len + 4u;
+  uint32_t o = static_cast<uint32_t>((g * 16u) % per);
+  for (uint32_t i = 0; i < 16u; ++i) {
+    const uint32_t rb = (w[i >> 2] >> (8u * (i & 3u))) & 0xFFu;
+    const uint32_t byte = o < 4u ? ((len >> (8u * o)) & 0xFFu) : alnum_char(rb);
+    out[i >> 2] |= byte << (8u * (i & 3u));
+    o = (o + 1u == per) ? 0u : o + 1u;
+  }
+  U32x4 v;
+  v.x = out[0]; v.y = out[1]; v.z = out[2]; v.w = out[3];
+  return v;
+}
+
 // ---- image scaling arithmetic (image_client.py:171-181) ---------------------
 // The source is a uint8 pixel, so every formula below has only 256 inputs per
 // channel; tests enumerate all of them against numpy.

@@ -727,14 +727,24 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
     uint64_t total = 0;
     for (int i = 0; i < n; ++i) {
       const tb200_fill_job& jb = jobs[base + i];
-      const uint32_t es = tb200_dtype_size(jb.dtype);
+      const bool strings = jb.dtype == TB200_BYTES;
+      const uint32_t es = strings ? 1u : tb200_dtype_size(jb.dtype);
       if (es == 0) return fail(TB200_ERR_INVALID, "job %d: dtype %u cannot be filled", base + i, jb.dtype);
+      if (strings && jb.mode == TB200_FILL_RANDOM) {
+        // fixed-length strings: irange = string length, nbytes = count * (4 + length)
+        if (jb.irange >= (1ull << 31) || jb.nbytes % (jb.irange + 4) != 0) {
+          return fail(TB200_ERR_INVALID, "job %d: BYTES fill needs nbytes = count * (4 + string length %llu)", base + i,
+                      static_cast<unsigned long long>(jb.irange));
+        }
+      } else if (strings) {
+        return fail(TB200_ERR_INVALID, "job %d: BYTES tensors take TB200_FILL_RANDOM only", base + i);
+      }
       if (jb.mode > TB200_FILL_BYTE) return fail(TB200_ERR_INVALID, "job %d: unknown fill mode %u", base + i, jb.mode);
       if (jb.nbytes != 0 && jb.dst == 0) return fail(TB200_ERR_INVALID, "job %d: dst is NULL", base + i);
       if (jb.mode == TB200_FILL_RANDOM) {
         const uint64_t lim = es == 1 ? 256ull : (es == 2 ? 65536ull : (es == 4 ? (1ull << 32) : 0ull));
         const bool is_int = jb.dtype != TB200_FP16 && jb.dtype != TB200_FP32 && jb.dtype != TB200_FP64 &&
-                            jb.dtype != TB200_BF16 && jb.dtype != TB200_BOOL;
+                            jb.dtype != TB200_BF16 && jb.dtype != TB200_BOOL && !strings;
         if (is_int && lim != 0 && jb.irange > lim) {
           return fail(TB200_ERR_INVALID, "job %d: irange %llu exceeds the %u-byte element range", base + i,
                       static_cast<unsigned long long>(jb.irange), es);
@@ -742,7 +752,7 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
       }
       const uint64_t groups = (jb.nbytes + 15) / 16;
       const tb200_fill_job& f = jobs[base];
-      if (jb.mode != TB200_FILL_RANDOM || jb.dtype != f.dtype || jb.lo != f.lo || jb.span != f.span ||
+      if (strings || jb.mode != TB200_FILL_RANDOM || jb.dtype != f.dtype || jb.lo != f.lo || jb.span != f.span ||
           jb.ilo != f.ilo || jb.irange != f.irange || (jb.nbytes & 15) != 0 || (jb.dst & 15) != 0) {
         homogeneous = false;
       }

@@ -17,21 +17,29 @@ _KINDS = {"sum": _native.CHECK_SUM, "equal": _native.CHECK_EQUAL,
           "addsub": _native.CHECK_ADDSUB, "top1": _native.CHECK_TOP1}
 
 
-def make_fill_job(dst, nbytes, datatype, stream_id=0, mode="random", low=0.0, high=None):
+def make_fill_job(dst, nbytes, datatype, stream_id=0, mode="random", low=0.0, high=None, string_length=None):
     """Build a tb200_fill_job.
 
     Floats: uniform in [low, high); ``high=None`` -> the unit interval (``low``
     must be 0).  Integers: uniform in [low, high); ``high=None`` -> raw bits.
     ``mode`` "zero" writes zeros, "byte" writes ``low`` as a repeated byte.
+    BYTES: ``string_length`` random alphanumeric characters per element in the
+    serialised ``<u32 length><chars>`` form; nbytes = count * (4 + string_length).
     """
     code = _native.DTYPE_CODES.get(datatype)
-    if code is None or datatype == "BYTES":
+    if code is None or (datatype == "BYTES" and (string_length is None or mode != "random")):
         raise ValueError("datatype '%s' cannot be generated" % datatype)
     job = FillJob()
     job.dst = int(dst)
     job.nbytes = int(nbytes)
     job.stream = int(stream_id) & 0xFFFFFFFFFFFFFFFF
     job.dtype = code
+    if datatype == "BYTES":
+        if int(nbytes) % (4 + int(string_length)) != 0:
+            raise ValueError("nbytes must be count * (4 + string_length)")
+        job.mode = _native.FILL_RANDOM
+        job.irange = int(string_length)
+        return job
     if mode == "zero":
         job.mode = _native.FILL_ZERO
         return job

@@ -26,9 +26,13 @@ from ..utils import InferenceServerException, triton_to_np_dtype
 
 
 class TensorSpec:
-    def __init__(self, name, datatype, shape):
+    """One model input / output.  BYTES tensors carry fixed-length strings
+    (perf_analyzer's --string-length): 4 + string_length serialised bytes per element."""
+
+    def __init__(self, name, datatype, shape, string_length=128):
         self.name, self.datatype, self.shape = name, datatype, [int(d) for d in shape]
-        es = _native.DTYPE_SIZES.get(datatype)
+        self.string_length = int(string_length) if datatype == "BYTES" else None
+        es = 4 + self.string_length if datatype == "BYTES" else _native.DTYPE_SIZES.get(datatype)
         if es is None:
             raise ValueError("tensor '%s': datatype %s is not supported by the load generator" % (name, datatype))
         self.nbytes = int(np.prod(self.shape)) * es if self.shape else es
@@ -133,6 +137,12 @@ class SlotSet:
                 if t.datatype.startswith(("INT", "UINT")) and mode == "random":
                     rng = self.token_range.get(t.name)
                     lo, hi = (rng if rng else (0, None))
+                if t.datatype == "BYTES":
+                    # zero data for strings = empty-content strings is not expressible at a
+                    # fixed byte size; perf_analyzer sends random strings in both modes
+                    jobs.append(make_fill_job(self.in_base + self.input_offset(s, i), t.nbytes, "BYTES",
+                                              stream_id=(s << 8) | i, string_length=t.string_length))
+                    continue
                 jobs.append(make_fill_job(self.in_base + self.input_offset(s, i), t.nbytes, t.datatype,
                                           stream_id=(s << 8) | i, mode=mode, low=lo, high=hi))
         return jobs

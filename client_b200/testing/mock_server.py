@@ -11,6 +11,7 @@ Models (inputs -> outputs):
                          (src/python/examples/simple_http_infer_client.py:242-263)
   custom_identity_int32  INPUT0 INT32[-1] -> OUTPUT0 (memory_growth_test.py)
   identity_*             any single input -> OUTPUT0 with the same bytes
+  string_identity        INPUT0 BYTES[1,8] -> OUTPUT0 (generated string inputs)
   densenet_onnx          data_0 FP32[3,224,224] -> fc6_1 FP32[1000]: mean of the input
                          elements i with i % 1000 == j (deterministic stand-in)
   bert_large             input_ids, attention_mask INT64[1,384] -> logits FP32[1,384]
@@ -190,6 +191,7 @@ MODELS = {
     "densenet_onnx": ("onnxruntime_onnx", [("data_0", "FP32", [3, 224, 224])], [("fc6_1", "FP32", [1000])], False),
     "bert_large": ("mock", [("input_ids", "INT64", [1, 384]), ("attention_mask", "INT64", [1, 384])],
                    [("logits", "FP32", [1, 384])], False),
+    "string_identity": ("mock", [("INPUT0", "BYTES", [1, 8])], [("OUTPUT0", "BYTES", [1, 8])], False),
     "repeat_int32": ("mock", [("IN", "INT32", [-1])], [("OUT", "INT32", [1])], True),
     "llama3_8b": ("mock", [("input_ids", "INT32", [1, -1])], [("token", "INT32", [1, 1])], True),
 }
@@ -216,7 +218,7 @@ def run_model(model, inputs, params):
         n = int(params.get("max_tokens", 4))
         base = int(ids.astype(np.int64).sum() % 128256)
         return [{"token": ("INT32", np.array([[(base + k) % 128256]], np.int32))} for k in range(n)]
-    if model.startswith("identity") or model == "custom_identity_int32":
+    if model.startswith("identity") or model in ("custom_identity_int32", "string_identity"):
         (name, arr), = list(inputs.items())[:1]
         dt = utils.np_to_triton_dtype(arr.dtype)
         return [{"OUTPUT0": (dt, arr)}]

@@ -182,7 +182,11 @@ int tb200_memcpy_d2h_async(tb200_ctx* ctx, void* dst, const void* src,
  * ---------------------------------------------------------------------- */
 typedef enum tb200_fill_mode {
   TB200_FILL_RANDOM = 0, /* uniform: floats in [lo, lo+span), ints in
-                            [ilo, ilo+irange) or raw bits when irange == 0 */
+                            [ilo, ilo+irange) or raw bits when irange == 0;
+                            dtype TB200_BYTES: fixed-length random strings in the
+                            serialised <u32 length><chars> form of
+                            PY/utils/__init__.py:208-261, irange = string length,
+                            nbytes = count * (4 + length), chars from 0-9A-Za-z */
   TB200_FILL_ZERO = 1,
   TB200_FILL_BYTE = 2    /* every byte = (uint8_t)ilo */
 } tb200_fill_mode;

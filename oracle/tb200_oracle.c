@@ -145,6 +145,15 @@ void oracle_fill(uint8_t* dst, uint64_t nbytes, uint32_t dtype, uint32_t mode, u
     uint32_t w[4];
     uint8_t grp[16];
     oracle_philox4x32_10(ctr, key, w);
+    if (dtype == 13) { /* BYTES: <u32 length><alnum chars> per element, irange = length */
+      const uint64_t per = irange + 4;
+      for (int i = 0; i < 16; ++i) {
+        const uint64_t o = (g * 16 + (uint64_t)i) % per;
+        const uint32_t rb = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+        const uint32_t k = (rb * 62u) >> 8;
+        grp[i] = o < 4 ? (uint8_t)((irange >> (8 * o)) & 0xFF) : (uint8_t)(k < 10 ? 48 + k : (k < 36 ? 55 + k : 61 + k));
+      }
+    } else
     group_bytes(dtype, w, lo, span, ilo, irange, grp);
     uint64_t left = nbytes - g * 16;
     memcpy(dst + g * 16, grp, left < 16 ? left : 16);

@@ -53,6 +53,19 @@ uint32_t emul_scale_f16_bits(uint32_t px, uint32_t scaling, int c, int ch) {
 uint32_t emul_f32_to_f16(uint32_t bits) { return f32_to_f16_bits(bits_f32(bits)); }
 uint32_t emul_f16_to_f32(uint32_t h) { return f32_bits(f16_bits_to_f32(static_cast<uint16_t>(h))); }
 
+// BYTES fill: group g of a fixed-length string tensor (what fill_segment_random<kBytes> stores)
+void emul_fill_bytes(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t stream, uint32_t len) {
+  for (uint64_t g = 0; g * 16 < nbytes; ++g) {
+    const U32x4 r = philox4x32<10>(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32),
+                                   static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32),
+                                   static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    const U32x4 o = fill_group_bytes(r, g, len);
+    const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+    const uint64_t left = nbytes - g * 16;
+    memcpy(dst + g * 16, w, left < 16 ? left : 16);
+  }
+}
+
 // the resize kernel's host tables; returns ksize, fills bounds[2*out] and coeffs[out*cap]
 int emul_resample_tables(int in_size, int out_size, int* bounds, int* coeffs, int cap) {
   std::vector<ResampleBound> b;

@@ -103,3 +103,21 @@ def test_resize_tables_match_the_pillow_pinned_oracle(emul):
         ks = emul.emul_resample_tables(in_size, out_size, bounds.ctypes.data, coeffs.ctypes.data, cap)
         assert ks == cap
         assert np.array_equal(bounds, want_b) and np.array_equal(coeffs, want_c), (in_size, out_size)
+
+
+def test_bytes_fill_header_vs_oracle(emul):
+    """fill_group_bytes (client_b200/csrc/philox.cuh) == oracle_fill for BYTES, and the result
+    is what deserialize_bytes_tensor expects: count strings of the requested length."""
+    from client_b200.utils import deserialize_bytes_tensor
+    from oracle import cref
+
+    emul.emul_fill_bytes.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]
+    emul.emul_fill_bytes.restype = None
+    for count, length in [(1, 0), (5, 1), (7, 13), (100, 128), (3, 1000), (16, 12)]:
+        n = count * (4 + length)
+        got = np.zeros(max(n, 1), np.uint8)
+        emul.emul_fill_bytes(got.ctypes.data, n, 77, 5, length)
+        want = cref.fill(n, "BYTES", seed=77, stream=5, irange=length)
+        assert np.array_equal(got[:n], want), (count, length)
+        strings = deserialize_bytes_tensor(want.tobytes())
+        assert len(strings) == count and all(len(x) == length and (length == 0 or x.isalnum()) for x in strings)

@@ -543,3 +543,35 @@ def test_set_shared_memory_region_from_image_with_resize():
     with pytest.raises(cudashm.CudaSharedMemoryException):
         cudashm.set_shared_memory_region_from_image(h, img, "FP32", "INCEPTION", resize=(448, 448))
     cudashm.destroy_shared_memory_region(h)
+
+
+# ---- BYTES tensors of fixed-length strings generated in place ------------------------------
+@pytest.mark.parametrize("count,length", [(1, 0), (5, 1), (7, 13), (1000, 128), (3, 1000), (64, 12)])
+def test_fill_bytes_strings(gpu_ops, count, length):
+    from client_b200.device import DeviceBuffer, make_fill_job
+    from client_b200.utils import deserialize_bytes_tensor
+
+    n = count * (4 + length)
+    buf = DeviceBuffer(0, n + 64)
+    jobs = [make_fill_job(buf.ptr, n, "BYTES", stream_id=9, string_length=length),
+            make_fill_job(buf.ptr + ((n + 15) // 16) * 16, 16, "INT32", stream_id=1)]  # mixed launch
+    gpu_ops.fill(jobs, seed=21)
+    gpu_ops.sync()
+    got = gpu_ops.download(buf.ptr, n)
+    assert np.array_equal(got, cref.fill(n, "BYTES", seed=21, stream=9, irange=length))
+    strings = deserialize_bytes_tensor(got.tobytes())
+    assert len(strings) == count and all(len(s) == length for s in strings)
+
+
+def test_fill_bytes_rejects_bad_sizes(gpu_ops):
+    from client_b200 import _native
+    from client_b200._native import FillJob
+    from client_b200.device import DeviceBuffer
+
+    buf = DeviceBuffer(0, 4096)
+    bad = FillJob(dst=buf.ptr, nbytes=100, stream=0, dtype=_native.DTYPE_CODES["BYTES"], mode=0, irange=13)
+    with pytest.raises(_native.NativeError, match="BYTES fill needs"):
+        gpu_ops.fill([bad], seed=1)
+    zero = FillJob(dst=buf.ptr, nbytes=68, stream=0, dtype=_native.DTYPE_CODES["BYTES"], mode=1, irange=13)
+    with pytest.raises(_native.NativeError, match="TB200_FILL_RANDOM only"):
+        gpu_ops.fill([zero], seed=1)

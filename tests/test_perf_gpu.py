@@ -71,3 +71,14 @@ def test_native_engine_wire_mode_and_stub_capacity(server):
         assert w["failed"] == 0 and w["throughput"] > 2000 and w["device_slots"] > 0, w
     finally:
         stub.stop()
+
+
+def test_generated_string_inputs_over_the_wire(server):
+    """BYTES inputs (perf_analyzer --string-length): the fill kernel writes the serialised
+    <u32 length><chars> elements into the pinned body; the server deserialises them."""
+    rows = cli.main(["-m", "string_identity", "-u", server["http"], "--shared-memory", "none", "--string-length", "24",
+                     "--concurrency-range", "2", "-p", "300", "-r", "3", "--json"])
+    assert rows[0]["count"] > 3 and rows[0]["failed"] == 0 and rows[0]["input_bytes"] == 8 * 28
+    rows = cli.main(["-m", "string_identity", "-u", server["grpc"], "-i", "grpc", "--shared-memory", "none",
+                     "--concurrency-range", "2", "-p", "300", "-r", "3", "--json"])
+    assert rows[0]["count"] > 3 and rows[0]["failed"] == 0 and rows[0]["input_bytes"] == 8 * 132
