@@ -22,7 +22,7 @@ import time
 import numpy as np
 
 from .. import _native
-from ..utils import InferenceServerException, triton_to_np_dtype
+from ..utils import InferenceServerException, deserialize_bytes_tensor, triton_to_np_dtype
 
 
 class TensorSpec:
@@ -265,7 +265,10 @@ class ConcurrencyManager:
     def _attach_wire_data(self, inputs, slot):
         ss = self.slotset
         for i, t in enumerate(ss.inputs):
-            arr = np.frombuffer(ss.input_bytes(slot, i), dtype=triton_to_np_dtype(t.datatype)).reshape(t.shape)
+            if t.datatype == "BYTES":  # the staging holds the serialised elements
+                arr = deserialize_bytes_tensor(bytes(ss.input_bytes(slot, i))).reshape(t.shape)
+            else:
+                arr = np.frombuffer(ss.input_bytes(slot, i), dtype=triton_to_np_dtype(t.datatype)).reshape(t.shape)
             inputs[i].set_data_from_numpy(arr)
 
     # -- threads --------------------------------------------------------------------------------

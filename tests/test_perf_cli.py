@@ -24,6 +24,11 @@ class HostStaging:
     def fill(self, tensors, input_data, seed):
         rng = np.random.default_rng(seed)
         for off, t in tensors:
+            if t.datatype == "BYTES":  # must be well-formed <u32 length><chars> elements
+                from oracle import cref
+
+                self.buf[off:off + t.nbytes] = cref.fill(t.nbytes, "BYTES", seed=seed, stream=off, irange=t.string_length)
+                continue
             self.buf[off:off + t.nbytes] = 0 if input_data == "zero" else rng.integers(0, 256, t.nbytes, dtype=np.uint8)
 
 
@@ -76,3 +81,13 @@ def test_no_gpu_no_fallback(server):
         pytest.skip("a GPU is present")
     with pytest.raises(Exception):
         cli.main(["-m", "simple", "-u", server["http"], "--shared-memory", "none", "--concurrency-range", "1", "-p", "100", "-r", "1"])
+
+
+@pytest.mark.parametrize("protocol", ["http", "grpc"])
+def test_string_inputs_over_the_wire(server, protocol):
+    """BYTES inputs of fixed-length strings (--string-length) through the wire path."""
+    rows = cli.main(["-m", "string_identity", "-u", server[protocol], "-i", protocol, "--shared-memory", "none",
+                     "--string-length", "24", "--concurrency-range", "2", "-p", "200", "-r", "3", "--json"],
+                    staging_factory=HostStaging)
+    assert rows[0]["count"] > 3 and rows[0]["failed"] == 0 and rows[0]["input_bytes"] == 8 * 28
+
