@@ -16,7 +16,6 @@ import json
 import queue
 import socket
 import ssl as _ssl
-import threading
 import zlib
 from concurrent.futures import ThreadPoolExecutor
 from concurrent.futures import TimeoutError as _FutureTimeout

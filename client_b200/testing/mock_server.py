@@ -27,7 +27,6 @@ import argparse
 import base64
 import ctypes
 import json
-import struct
 import sys
 import threading
 import time

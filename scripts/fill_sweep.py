@@ -6,7 +6,6 @@ wire shape (512 x 3,072 B INT64) and a 256-slot launch (154 MB), all timed with 
 events around back-to-back launches inside one CUDA graph, rotating over > L2 of memory.
 """
 
-import ctypes
 import os
 import sys
 

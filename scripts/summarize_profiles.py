@@ -9,7 +9,6 @@ bench JSON lines.  Needs the ncu CLI (reads .ncu-rep files, no GPU).
 import collections
 import csv
 import io
-import json
 import os
 import shutil
 import subprocess

@@ -5,7 +5,6 @@ is bit-exact against the C oracle (which uses fmaf like the kernel); against the
 numpy oracle the stated tolerance is 1 ulp for scaled ranges (oracle/fill.py).
 """
 
-import ctypes
 
 import numpy as np
 import pytest

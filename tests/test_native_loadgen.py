@@ -4,7 +4,6 @@ canned-response server and against the Python mock server (system shm, no device
 import ctypes
 
 import numpy as np
-import pytest
 
 from client_b200 import _native
 from client_b200._native_loadgen import LoadgenConfig, LoadgenStats
