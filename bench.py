@@ -192,6 +192,8 @@ def run_b200(args):
     achieved = fill_bytes / (fill_ms / 1e3) / 1e9
     peak, peak_src = measured_peak()
 
+    if os.environ.get("TB200_STEP_PARALLEL_MIN_MB"):  # experiment knob (see include/tb200.h)
+        _native.check(_native.load().tb200_tune(b"step_parallel_min_mb", int(os.environ["TB200_STEP_PARALLEL_MIN_MB"])))
     # --- e2e: the same step through the public API, job tables H2D + results D2H every step
     e2e_steps = max(10, min(steps, 20000))
     for i in range(warmup):

@@ -359,7 +359,9 @@ int tb200_step_sync(tb200_ctx* ctx, const tb200_fill_job* fill_jobs, int nfill, 
                     uint64_t stream_epoch, const tb200_check_job* check_jobs, int ncheck,
                     tb200_check_result* results);
 
-/* experiment knobs (scripts/fill_sweep.py); key "fill_variant", 0 = default */
+/* knobs: "fill_variant" (experiment matrix of scripts/fill_sweep.py, 0 = default policy);
+ * "step_parallel_min_mb": tb200_step_sync runs check and fill as parallel branches only
+ * when the fill writes at least this many MiB (default 0 = always) */
 int tb200_tune(const char* key, int value);
 
 /* write > L2-size bytes so the next timed kernel starts with a cold L2 */
