@@ -143,6 +143,8 @@ SIGNATURES = {
     "tb200_pack_strided_async": (c_int, [c_vp, c_vp, c_vp, c_u32, c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "tb200_concat_async": (c_int, [c_vp, ctypes.POINTER(CopyJob), c_int]),
     "tb200_check_async": (c_int, [c_vp, ctypes.POINTER(CheckJob), c_int, c_vp]),
+    "tb200_deflate_bound": (c_u64, [c_u64]),
+    "tb200_deflate_async": (c_int, [c_vp, c_vp, c_u64, c_vp, c_u64, c_u32, c_vp]),
     "tb200_topk_async": (c_int, [c_vp, ctypes.POINTER(TopkJob), c_int, c_int, c_vp]),
     "tb200_graph_begin": (c_int, [c_vp]),
     "tb200_graph_end": (c_int, [c_vp, ctypes.POINTER(c_vp)]),

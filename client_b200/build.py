@@ -18,7 +18,7 @@ BUILD = os.path.join(ROOT, "build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + ARCH
-SOURCES = ["kernels.cu", "runtime.cu", "loadgen.cc", "mock_server.cu"]
+SOURCES = ["kernels.cu", "deflate.cu", "runtime.cu", "loadgen.cc", "mock_server.cu"]
 
 
 def _nvcc():

@@ -105,6 +105,17 @@ struct CheckLaunch {
 };
 cudaError_t launch_check(const CheckLaunch& l, cudaStream_t s);
 
+// ---- deflate (deflate.cu) ---------------------------------------------------------
+struct DeflateChunkMeta {
+  unsigned long long offset;  // of the chunk's bytes in the stream body (set by the finalize kernel)
+  uint32_t out_bytes, in_bytes;
+  uint32_t adler_a, adler_b;  // Adler-32 piece sums (a from 0)
+  uint32_t crc_raw0;          // CRC-32 register over the chunk from init 0, no final xor
+  uint32_t pad;
+};
+cudaError_t launch_deflate(const uint8_t* src, uint64_t nbytes, uint32_t format, uint8_t* scratch, DeflateChunkMeta* meta, uint8_t* dst,
+                           uint64_t* out_size, cudaStream_t s);
+
 cudaError_t launch_topk(const tb200_topk_job* jobs, uint32_t njobs, uint32_t k, tb200_topk_entry* out, cudaStream_t s);
 
 cudaError_t launch_epoch_bump(uint64_t* dev_epoch, uint64_t delta, cudaStream_t s);

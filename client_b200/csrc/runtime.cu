@@ -202,6 +202,10 @@ struct tb200_ctx {
     size_t off_vb, off_hc, off_vc;
   };
   std::vector<ResizeTables> resize_tables;
+  // deflate scratch: per-chunk output slots + metadata
+  void* deflate_scratch = nullptr;
+  void* deflate_meta = nullptr;
+  uint64_t deflate_chunks_cap = 0;
   // capture state
   tb200_graph* capture = nullptr;
   uint64_t capture_launches0 = 0;
@@ -404,6 +408,8 @@ int tb200_ctx_destroy(tb200_ctx* ctx) {
   if (ctx->dev_epoch) cudaFree(ctx->dev_epoch);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   for (auto& t : ctx->resize_tables) cudaFree(t.dev);
+  if (ctx->deflate_scratch) cudaFree(ctx->deflate_scratch);
+  if (ctx->deflate_meta) cudaFree(ctx->deflate_meta);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -1121,6 +1127,45 @@ int tb200_topk_async(tb200_ctx* ctx, const tb200_topk_job* jobs, int njobs, int 
                            out + static_cast<size_t>(base) * k, ctx->cur));
     ctx->launches += 1;
   }
+  return TB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// deflate
+// ---------------------------------------------------------------------------
+static constexpr uint64_t kDeflateChunkBytes = 8192, kDeflateChunkOutBytes = 8192 + 16;
+
+uint64_t tb200_deflate_bound(uint64_t nbytes) {
+  const uint64_t chunks = (nbytes + kDeflateChunkBytes - 1) / kDeflateChunkBytes;
+  return 10 + chunks * kDeflateChunkOutBytes + 5 + 8;
+}
+
+int tb200_deflate_async(tb200_ctx* ctx, void* dst, uint64_t dst_capacity, const void* src, uint64_t nbytes, uint32_t format,
+                        uint64_t* out_size) {
+  if (ctx == nullptr || dst == nullptr || out_size == nullptr || (src == nullptr && nbytes != 0)) return fail(TB200_ERR_INVALID, "NULL argument");
+  if (format != TB200_DEFLATE_ZLIB && format != TB200_DEFLATE_GZIP) return fail(TB200_ERR_INVALID, "unknown deflate format %u", format);
+  if (dst_capacity < tb200_deflate_bound(nbytes)) {
+    return fail(TB200_ERR_RANGE, "deflate: dst holds %llu bytes, tb200_deflate_bound(%llu) = %llu", static_cast<unsigned long long>(dst_capacity),
+                static_cast<unsigned long long>(nbytes), static_cast<unsigned long long>(tb200_deflate_bound(nbytes)));
+  }
+  if (ctx->capture != nullptr) return fail(TB200_ERR_STATE, "deflate is not capturable (scratch may be reallocated)");
+  const uint64_t chunks = (nbytes + kDeflateChunkBytes - 1) / kDeflateChunkBytes;
+  if (chunks >= (1ull << 31)) return fail(TB200_ERR_INVALID, "deflate: input too large");
+  DeviceGuard g(ctx->device);
+  if (chunks > ctx->deflate_chunks_cap || ctx->deflate_meta == nullptr) {
+    TB200_CUDA(cudaStreamSynchronize(ctx->cur));
+    if (ctx->deflate_scratch) cudaFree(ctx->deflate_scratch);
+    if (ctx->deflate_meta) cudaFree(ctx->deflate_meta);
+    ctx->deflate_scratch = ctx->deflate_meta = nullptr;
+    ctx->deflate_chunks_cap = 0;
+    const uint64_t cap = std::max<uint64_t>(chunks, 64);
+    TB200_CUDA(cudaMalloc(&ctx->deflate_scratch, cap * kDeflateChunkOutBytes));
+    TB200_CUDA(cudaMalloc(&ctx->deflate_meta, cap * sizeof(DeflateChunkMeta)));
+    ctx->deflate_chunks_cap = cap;
+  }
+  TB200_CUDA(launch_deflate(static_cast<const uint8_t*>(src), nbytes, format, static_cast<uint8_t*>(ctx->deflate_scratch),
+                            static_cast<DeflateChunkMeta*>(ctx->deflate_meta), static_cast<uint8_t*>(dst), out_size, ctx->cur));
+  ctx->launches += chunks > 0 ? 3 : 1;
   return TB200_OK;
 }
 

@@ -326,6 +326,31 @@ class DeviceOps:
         ent = buf.array(np.dtype([("value", "<f4"), ("index", "<u4")]), n * k).reshape(n, k)
         return ent["value"].copy(), ent["index"].copy()
 
+    def deflate_async(self, dst_ptr, dst_capacity, src_ptr, nbytes, out_size_ptr, algorithm="gzip"):
+        """Compress device bytes into a zlib ("deflate") or gzip stream on the device
+        (tb200_deflate_async); the stream length lands in ``*out_size_ptr`` (uint64)."""
+        fmt = {"deflate": 0, "zlib": 0, "gzip": 1}[algorithm]
+        _native.check(self._lib.tb200_deflate_async(self._ctx.handle, dst_ptr, int(dst_capacity), src_ptr, int(nbytes), fmt, out_size_ptr))
+
+    def deflate(self, src_ptr, nbytes, algorithm="gzip"):
+        """Blocking convenience: the compressed stream as ``bytes`` — what
+        ``gzip.compress`` / ``zlib.compress`` produce for a request body
+        (reference http/_client.py:1440-1460), decodable by the same decoders."""
+        cap = int(self._lib.tb200_deflate_bound(int(nbytes)))
+        dst = self._scratch2(cap)
+        size = self._result_buf()
+        self.deflate_async(dst.ptr, cap, src_ptr, nbytes, size.device_ptr + 2048, algorithm)
+        self.sync()
+        n = int(size.array(np.uint64, 1, offset=2048)[0])
+        return self.download(dst.ptr, n).tobytes()
+
+    def _scratch2(self, nbytes):
+        cur = getattr(self, "_scratch2_buf", None)
+        if cur is None or cur.nbytes < nbytes:
+            self.sync()
+            self._scratch2_buf = DeviceBuffer(self.device_id, max(int(nbytes), 1 << 20))
+        return self._scratch2_buf
+
     def _result_buf(self):
         cur = getattr(self, "_res_buf", None)
         if cur is None:

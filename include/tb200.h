@@ -333,6 +333,25 @@ int tb200_topk_async(tb200_ctx* ctx, const tb200_topk_job* jobs, int njobs, int 
                      tb200_topk_entry* out);
 
 /* ------------------------------------------------------------------------
+ * Kernel 4: request-body compression.  The reference compresses a body with zlib / gzip on
+ * the host (PY/http/_client.py:1440-1460, CC/http_client.cc:146-221, `Content-Encoding:
+ * deflate | gzip`); a body generated on the device is compressed there: 8 KiB chunks, one
+ * fixed-Huffman deflate block each (LZ77 matches inside the chunk), sync-flush between
+ * chunks, stored fallback, Adler-32 / CRC-32 combined on the device.  Any zlib / gzip
+ * decoder accepts the stream; it is not byte-identical to zlib's own output.
+ * `dst` must hold tb200_deflate_bound(nbytes) bytes; *out_size (device or mapped-host
+ * memory) receives the stream length when the stream reaches the launch.
+ * ---------------------------------------------------------------------- */
+typedef enum tb200_deflate_format {
+  TB200_DEFLATE_ZLIB = 0, /* "deflate" content encoding: 2-byte header, Adler-32 trailer */
+  TB200_DEFLATE_GZIP = 1  /* 10-byte header, CRC-32 + ISIZE trailer                      */
+} tb200_deflate_format;
+
+uint64_t tb200_deflate_bound(uint64_t nbytes);
+int tb200_deflate_async(tb200_ctx* ctx, void* dst, uint64_t dst_capacity, const void* src,
+                        uint64_t nbytes, uint32_t format, uint64_t* out_size);
+
+/* ------------------------------------------------------------------------
  * Issue loop building blocks: capture any sequence of the *_async calls above
  * into a CUDA graph and replay it per measurement step / concurrency slot.
  * The concurrency loop itself (the absent perf_analyzer ConcurrencyManager /

@@ -121,3 +121,39 @@ def test_bytes_fill_header_vs_oracle(emul):
         assert np.array_equal(got[:n], want), (count, length)
         strings = deserialize_bytes_tensor(want.tobytes())
         assert len(strings) == count and all(len(x) == length and (length == 0 or x.isalnum()) for x in strings)
+
+
+def _deflate_inputs():
+    rng = np.random.default_rng(12)
+    yield "empty", b""
+    yield "one byte", b"\x07"
+    yield "zeros 100k", bytes(100000)
+    yield "random 20k (stored fallback)", rng.integers(0, 256, 20000, dtype=np.uint8).tobytes()
+    yield "text", (b"the quick brown fox jumps over the lazy dog. " * 700)
+    yield "int64 token ids", rng.integers(0, 30522, 384 * 5, dtype=np.int64).tobytes()
+    yield "fp32 unit interval", rng.random(6000, dtype=np.float32).tobytes()
+    yield "exactly one chunk", bytes(range(256)) * 32
+    yield "chunk + 1", bytes(range(256)) * 32 + b"x"
+    yield "high bytes", bytes([200 + (i % 50) for i in range(30000)])
+    yield "runs of 258+", b"".join(bytes([i]) * (300 + i) for i in range(60))
+
+
+@pytest.mark.parametrize("gzip_format", [0, 1])
+def test_device_deflate_logic_round_trips_through_zlib(emul, gzip_format):
+    """client_b200/csrc/deflate.cuh run on the CPU: the stream the encoder produces is decoded
+    by the reference's own decompressor (zlib / gzip, PY/http/_infer_result.py:71-76 and the
+    server side of PY/http/_client.py:1440-1460) back to the input, checksums included."""
+    import gzip
+    import zlib
+
+    emul.emul_deflate.restype = ctypes.c_uint64
+    emul.emul_deflate.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p]
+    for label, data in _deflate_inputs():
+        src = np.frombuffer(data, dtype=np.uint8).copy() if data else np.zeros(1, np.uint8)
+        dst = np.zeros(len(data) + (len(data) // 8192 + 2) * 32 + 64, dtype=np.uint8)
+        n = emul.emul_deflate(src.ctypes.data, len(data), gzip_format, dst.ctypes.data)
+        stream = dst[:n].tobytes()
+        back = gzip.decompress(stream) if gzip_format else zlib.decompress(stream)
+        assert back == data, label
+        if label in ("zeros 100k", "text", "int64 token ids", "runs of 258+"):
+            assert n < len(data) * 0.6, (label, n, len(data))

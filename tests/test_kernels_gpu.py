@@ -574,3 +574,50 @@ def test_fill_bytes_rejects_bad_sizes(gpu_ops):
     zero = FillJob(dst=buf.ptr, nbytes=68, stream=0, dtype=_native.DTYPE_CODES["BYTES"], mode=1, irange=13)
     with pytest.raises(_native.NativeError, match="TB200_FILL_RANDOM only"):
         gpu_ops.fill([zero], seed=1)
+
+
+# ---- device deflate: decoded by the reference's decompressors ------------------------------
+@pytest.mark.parametrize("algorithm", ["gzip", "deflate"])
+def test_device_deflate_round_trip(gpu_ops, algorithm):
+    import gzip
+    import zlib
+
+    from test_host_emul import _deflate_inputs
+
+    for label, data in _deflate_inputs():
+        src = gpu_ops.upload(np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8))
+        stream = gpu_ops.deflate(src.ptr, len(data), algorithm)
+        back = gzip.decompress(stream) if algorithm == "gzip" else zlib.decompress(stream)
+        assert back == data, label
+
+
+def test_device_deflate_of_generated_tensors(gpu_ops):
+    """What the wire path would send: generated tensors compressed where they were generated.
+    Large input (4704 chunks), zero data, token ids, random floats (stored fallback)."""
+    import zlib
+
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    n = 38535168
+    buf = DeviceBuffer(0, n)
+    cases = [("zero", make_fill_job(buf.ptr, n, "FP32", mode="zero"), 0.02),
+             ("ids", make_fill_job(buf.ptr, n, "INT64", stream_id=3, low=0, high=30522), 0.55),
+             ("fp32", make_fill_job(buf.ptr, n, "FP32", stream_id=4), 1.01)]
+    for label, job, max_ratio in cases:
+        gpu_ops.fill([job], seed=8)
+        gpu_ops.sync()
+        stream = gpu_ops.deflate(buf.ptr, n, "deflate")
+        raw = gpu_ops.download(buf.ptr, n).tobytes()
+        assert zlib.decompress(stream) == raw, label
+        assert len(stream) <= n * max_ratio, (label, len(stream))
+
+
+def test_device_deflate_rejects_small_destination(gpu_ops):
+    from client_b200 import _native
+    from client_b200.device import DeviceBuffer, HostBuffer
+
+    src = DeviceBuffer(0, 1 << 20)
+    dst = DeviceBuffer(0, 1 << 20)
+    size = HostBuffer(64)
+    with pytest.raises(_native.NativeError, match="tb200_deflate_bound"):
+        gpu_ops.deflate_async(dst.ptr, 1 << 20, src.ptr, 1 << 20, size.device_ptr, "gzip")
