@@ -305,6 +305,36 @@ def run_b200(args):
     ops.sync()
     rs_ms = timer.elapsed_ms() / (20 * SETS)
     rs_bytes = SLOTS * (RS_H * RS_W * 3 + IN_BYTES)
+    # --- request-body compression on the device (HTTP Content-Encoding gzip of a generated body)
+    import zlib
+
+    dfl = []
+    dfl_src = in_regions[0]._base_addr
+    dfl_n = SLOTS * IN_BYTES
+    dfl_cap = int(_native.load().tb200_deflate_bound(dfl_n))
+    dfl_dst = DeviceBuffer(local, dfl_cap)
+    for label, job in (("token ids INT64 [0,30522)", make_fill_job(dfl_src, dfl_n, "INT64", stream_id=stream0 + 7300, low=0, high=30522)),
+                       ("zero data", make_fill_job(dfl_src, dfl_n, "FP32", mode="zero")),
+                       ("FP32 unit interval (incompressible: stored)", make_fill_job(dfl_src, dfl_n, "FP32", stream_id=stream0 + 7301))):
+        ops.fill([job], seed=SEED)
+        ops.sync()
+        for _ in range(2):
+            ops.deflate_async(dfl_dst.ptr, dfl_cap, dfl_src, dfl_n, results.device_ptr + 3072, "gzip")
+        ops.sync()
+        timer.start()
+        for _ in range(5):
+            ops.deflate_async(dfl_dst.ptr, dfl_cap, dfl_src, dfl_n, results.device_ptr + 3072, "gzip")
+        timer.stop()
+        ops.sync()
+        d_ms = timer.elapsed_ms() / 5
+        out_bytes = int(results.array(np.uint64, 1, offset=3072)[0])
+        sample = ops.download(dfl_src, 4 << 20).tobytes()  # host zlib on a 4 MB sample of the same data
+        t0 = time.perf_counter()
+        zl = zlib.compress(sample, 6)
+        z_s = time.perf_counter() - t0
+        dfl.append({"data": label, "in_bytes": dfl_n, "out_bytes": out_bytes, "ratio": round(out_bytes / dfl_n, 4), "ms": round(d_ms, 4),
+                    "in_gbps": round(dfl_n / (d_ms / 1e3) / 1e9, 1), "host_zlib6_mbps": round(len(sample) / z_s / 1e6, 1),
+                    "host_zlib6_ratio": round(len(zl) / len(sample), 4)})
     clocks = sampler.stop()
 
     line = {
@@ -335,6 +365,7 @@ def run_b200(args):
                         "ms_per_launch": round(rs_ms, 6), "images_per_s": round(SLOTS / (rs_ms / 1e3), 1),
                         "achieved_gbps": round(rs_bytes / (rs_ms / 1e3) / 1e9, 1), "algorithmic_bytes_per_launch": rs_bytes,
                         "frac": round(rs_bytes / (rs_ms / 1e3) / 1e9 / peak, 4)},
+        "deflate": {"kernel": "deflate_chunk_kernel + finalize + gather (gzip container, 8 KiB chunks)", "cases": dfl},
         "c3_resnet50_b128_fp16": {
             "fill": {"achieved_gbps": round(SLOTS * IN_BYTES / (c3_fill_ms / 1e3) / 1e9, 1), "ms_per_request": round(c3_fill_ms, 6),
                      "frac": round(SLOTS * IN_BYTES / (c3_fill_ms / 1e3) / 1e9 / peak, 4), "algorithmic_bytes": SLOTS * IN_BYTES},

@@ -1,6 +1,6 @@
 // deflate.cu -- device deflate encoder (zlib / gzip containers) built on deflate.cuh.
-//   deflate_chunk_kernel     one CTA of 64 threads per 8 KiB chunk: hash candidates, two-pass
-//                            greedy parse per 128-byte sub-block, fixed-Huffman bit packing in
+//   deflate_chunk_kernel     one CTA of 128 threads per 8 KiB chunk: hash candidates, greedy
+//                            parse per 64-byte sub-block, emit pass, fixed-Huffman bit packing in
 //                            shared memory, stored fallback, per-chunk Adler-32 / CRC-32 pieces
 //   deflate_finalize_kernel  sizes -> offsets, checksum combination across chunks, header/trailer
 //   deflate_gather_kernel    chunk bytes -> their final places
@@ -11,10 +11,12 @@ namespace tb200 {
 
 __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const uint8_t* __restrict__ src, uint64_t nbytes,
                                                                          uint8_t* __restrict__ scratch, DeflateChunkMeta* __restrict__ meta) {
-  __shared__ __align__(16) uint8_t in[kDeflateChunk + 16];
+  __shared__ __align__(16) uint8_t in[kDeflateInBytes];  // skewed layout, deflate_at()
+  __shared__ uint32_t crc_tbl[256];
   __shared__ uint16_t cand[kDeflateChunk];
-  __shared__ uint16_t table[1 << kDeflateHashBits];
   __shared__ uint32_t words[kDeflateOutWords];
+  uint16_t* table = reinterpret_cast<uint16_t*>(words);  // hash heads; dead before the bit buffer is used
+  static_assert(sizeof(uint16_t) * (1 << kDeflateHashBits) <= sizeof(uint32_t) * kDeflateOutWords, "table aliases words");
   __shared__ uint32_t sub_bits[kDeflateThreads];
   __shared__ uint32_t sub_off[kDeflateThreads];
   __shared__ uint32_t crc_s[kDeflateThreads];
@@ -28,10 +30,12 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
   const uint32_t n = static_cast<uint32_t>(nbytes - base < static_cast<uint64_t>(kDeflateChunk) ? nbytes - base : kDeflateChunk);
   const uint8_t* g = src + base;
 
-  for (uint32_t i = tid; i < n; i += kDeflateThreads) in[i] = g[i];
-  for (uint32_t i = n + tid; i < n + 16 && i < kDeflateChunk + 16; i += kDeflateThreads) in[i] = 0;
+  for (uint32_t i = tid; i < n; i += kDeflateThreads) in[deflate_at(i)] = g[i];
+  for (uint32_t i = tid; i < 256u; i += kDeflateThreads) {
+    const uint8_t b = static_cast<uint8_t>(i);
+    crc_tbl[i] = crc32_raw(0u, &b, 1);
+  }
   for (uint32_t i = tid; i < (1u << kDeflateHashBits); i += kDeflateThreads) table[i] = static_cast<uint16_t>(kDeflateNoCand);
-  for (uint32_t i = tid; i < static_cast<uint32_t>(kDeflateOutWords); i += kDeflateThreads) words[i] = 0;
   if (tid < 8) pw[tid] = crc32_xpow8n(static_cast<uint64_t>(kDeflateSub) << tid);
   __syncthreads();
 
@@ -41,7 +45,7 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
     uint32_t h = 0;
     const bool ok = p + 3 < n;
     if (ok) {
-      h = deflate_hash(in + p);
+      h = deflate_hash(in, p);
       cand[p] = table[h];
     } else if (p < n) {
       cand[p] = static_cast<uint16_t>(kDeflateNoCand);
@@ -51,20 +55,21 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
     __syncthreads();
   }
 
+  for (uint32_t i = tid; i < static_cast<uint32_t>(kDeflateOutWords); i += kDeflateThreads) words[i] = 0;  // table -> bit buffer
   // checksum pieces of the raw bytes
   const uint32_t begin = tid * kDeflateSub;
   const uint32_t end = begin < n ? (begin + kDeflateSub < n ? begin + kDeflateSub : n) : begin;
   {
     uint32_t a = 0, b = 0;
-    adler_piece(in + begin, end - begin, &a, &b);
+    adler_piece(in + deflate_at(begin), end - begin, &a, &b);  // a sub-block is contiguous
     adl_a[tid] = a;
     adl_b[tid] = b;
-    crc_s[tid] = crc32_raw(0u, in + begin, end - begin);
+    crc_s[tid] = crc32_raw_tbl(crc_tbl, 0u, in + deflate_at(begin), end - begin);
     len_s[tid] = end - begin;
   }
 
   // pass 1: bits per sub-block
-  sub_bits[tid] = end > begin ? deflate_parse(in, begin, end, cand, words, 0, false) : 0u;
+  sub_bits[tid] = end > begin ? deflate_parse(in, begin, end, cand) : 0u;
   __syncthreads();
   if (tid == 0) {
     uint32_t off = 3;  // block header: BFINAL=0, BTYPE=01
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
   const bool stored = comp_bytes >= n + 5;
   uint8_t* out = scratch + static_cast<size_t>(blockIdx.x) * kDeflateMaxChunkOut;
   if (!stored) {
-    if (end > begin) deflate_parse(in, begin, end, cand, words, sub_off[tid], true);
+    if (end > begin) deflate_emit(in, begin, end, cand, words, sub_off[tid]);
     __syncthreads();
     if (tid == 0) {
       deflate_put(words, (flush_at + 2) * 8, 0xFFFFu, 16);  // LEN = 0 is already there
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
       out[3] = static_cast<uint8_t>(~n & 0xFF);
       out[4] = static_cast<uint8_t>((~n >> 8) & 0xFF);
     }
-    for (uint32_t i = tid; i < n; i += kDeflateThreads) out[5 + i] = in[i];
+    for (uint32_t i = tid; i < n; i += kDeflateThreads) out[5 + i] = in[deflate_at(i)];
   }
   if (tid == 0) {
     uint32_t A = 0, B = 0;
@@ -130,13 +135,14 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
 }
 
 // One CTA: offsets of the chunks in the final stream, checksums of the whole input, container
-// header and trailer.  Threads own contiguous ranges of chunks, partials meet in a tree.
+// header and trailer.  Threads own contiguous ranges of chunks.  Both checksums are linear in
+// the pieces, so each partial is moved to the end of the stream on its own
+// (crc * x^(8*bytes_after), b + bytes_after * a) and the results are summed -- no serial chain.
 __global__ void __launch_bounds__(1024) deflate_finalize_kernel(DeflateChunkMeta* __restrict__ meta, uint32_t nchunks, uint64_t nbytes,
                                                                 uint32_t format, uint8_t* __restrict__ dst, uint64_t* __restrict__ out_size) {
-  __shared__ unsigned long long sz[1024];
-  __shared__ unsigned long long ln[1024];
-  __shared__ uint32_t crc[1024];
-  __shared__ uint32_t aa[1024], ab[1024];
+  __shared__ unsigned long long sz[1024];   // inclusive scan of output sizes
+  __shared__ unsigned long long ln[1024];   // inclusive scan of input lengths
+  __shared__ uint32_t red[32 * 3];
   const uint32_t tid = threadIdx.x;
   const uint32_t per = (nchunks + 1023u) / 1024u;
   const uint32_t c0 = min(tid * per, nchunks), c1 = min(c0 + per, nchunks);
@@ -152,44 +158,48 @@ __global__ void __launch_bounds__(1024) deflate_finalize_kernel(DeflateChunkMeta
   }
   sz[tid] = bytes;
   ln[tid] = len;
-  crc[tid] = c;
-  aa[tid] = A;
-  ab[tid] = B;
   __syncthreads();
-  // exclusive prefix of the sizes (serial over 1024 partials by one warp-less loop is fine)
-  __shared__ unsigned long long start[1024];
-  if (tid == 0) {
-    unsigned long long run = 0;
-    for (int i = 0; i < 1024; ++i) {
-      start[i] = run;
-      run += sz[i];
-    }
+  for (uint32_t d = 1; d < 1024u; d <<= 1) {  // Hillis-Steele inclusive scans
+    const unsigned long long s0 = tid >= d ? sz[tid - d] : 0ull;
+    const unsigned long long l0 = tid >= d ? ln[tid - d] : 0ull;
+    __syncthreads();
+    sz[tid] += s0;
+    ln[tid] += l0;
+    __syncthreads();
   }
-  __syncthreads();
   {
-    unsigned long long off = start[tid];
+    unsigned long long off = sz[tid] - bytes;  // exclusive
     for (uint32_t i = c0; i < c1; ++i) {
       const uint32_t ob = meta[i].out_bytes;
       meta[i].offset = off;
       off += ob;
     }
   }
-  // checksum tree over the 1024 partials
-  for (uint32_t stride = 1; stride < 1024u; stride <<= 1) {
-    __syncthreads();
-    if ((tid & (2 * stride - 1)) == 0) {
-      const unsigned long long ly = ln[tid + stride];
-      crc[tid] = crc32_mulmod(crc[tid], crc32_xpow8n(ly)) ^ crc[tid + stride];
-      uint32_t A2 = aa[tid], B2 = ab[tid];
-      adler_append(&A2, &B2, aa[tid + stride], ab[tid + stride], ly);
-      aa[tid] = A2;
-      ab[tid] = B2;
-      ln[tid] += ly;
-    }
+  // move this thread's partial to the end of the stream
+  const unsigned long long after = nbytes - ln[tid];
+  uint32_t crc_part = len != 0 ? crc32_mulmod(c, crc32_xpow8n(after)) : 0u;
+  uint32_t a_part = A;
+  uint32_t b_part = static_cast<uint32_t>((B + (after % kAdlerMod) * A) % kAdlerMod);
+  // block reduction: xor for the CRC, modular sums for Adler
+  for (int off = 16; off > 0; off >>= 1) {
+    crc_part ^= __shfl_xor_sync(0xFFFFFFFFu, crc_part, off);
+    a_part += __shfl_xor_sync(0xFFFFFFFFu, a_part, off);
+    b_part += __shfl_xor_sync(0xFFFFFFFFu, b_part, off);  // 32 * 65520 < 2^32
+  }
+  if ((tid & 31u) == 0) {
+    red[(tid >> 5) * 3 + 0] = crc_part;
+    red[(tid >> 5) * 3 + 1] = a_part % kAdlerMod;
+    red[(tid >> 5) * 3 + 2] = b_part % kAdlerMod;
   }
   __syncthreads();
   if (tid == 0) {
-    const unsigned long long body = start[1023] + sz[1023];
+    uint32_t crc_all = 0, a_all = 0, b_all = 0;
+    for (int w = 0; w < 32; ++w) {
+      crc_all ^= red[w * 3];
+      a_all = (a_all + red[w * 3 + 1]) % kAdlerMod;
+      b_all = (b_all + red[w * 3 + 2]) % kAdlerMod;
+    }
+    const unsigned long long body = sz[1023];
     const uint32_t hdr = format == TB200_DEFLATE_GZIP ? 10u : 2u;
     if (format == TB200_DEFLATE_GZIP) {
       const uint8_t h[10] = {0x1F, 0x8B, 0x08, 0x00, 0, 0, 0, 0, 0x00, 0xFF};
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(1024) deflate_finalize_kernel(DeflateChunkMeta
     unsigned long long total = hdr + body + 5;
     if (format == TB200_DEFLATE_GZIP) {
       // register from init 0xFFFFFFFF over the whole stream, final xor
-      const uint32_t raw = crc32_mulmod(0xFFFFFFFFu, crc32_xpow8n(nbytes)) ^ crc[0];
+      const uint32_t raw = crc32_mulmod(0xFFFFFFFFu, crc32_xpow8n(nbytes)) ^ crc_all;
       const uint32_t v = raw ^ 0xFFFFFFFFu;
       const uint32_t isize = static_cast<uint32_t>(nbytes);
       for (int i = 0; i < 4; ++i) t[i] = static_cast<uint8_t>(v >> (8 * i));
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(1024) deflate_finalize_kernel(DeflateChunkMeta
     } else {
       // Adler-32 starts from a = 1: A = 1 + sum, B = n*1 + b
       uint32_t A1 = 1, B1 = 0;
-      adler_append(&A1, &B1, aa[0], ab[0], nbytes);
+      adler_append(&A1, &B1, a_all, b_all, nbytes);
       const uint32_t v = (B1 << 16) | A1;
       for (int i = 0; i < 4; ++i) t[i] = static_cast<uint8_t>(v >> (8 * (3 - i)));  // big endian
       total += 4;

@@ -26,8 +26,9 @@
 namespace tb200 {
 
 constexpr int kDeflateChunk = 8192;   // bytes per CTA
-constexpr int kDeflateSub = 128;      // bytes per thread
-constexpr int kDeflateThreads = kDeflateChunk / kDeflateSub;  // 64
+constexpr int kDeflateSub = 64;       // bytes per thread
+constexpr int kDeflateSubShift = 6;
+constexpr int kDeflateThreads = kDeflateChunk / kDeflateSub;  // 128
 constexpr int kDeflateHashBits = 12;
 constexpr uint32_t kDeflateNoCand = 0xFFFFu;
 // worst case of a fixed-Huffman chunk: 9 bits per byte + header/EOB/flush
@@ -119,14 +120,20 @@ TB200_HD uint32_t deflate_emit_match(uint32_t* words, uint32_t pos, uint32_t len
 }
 
 // ---- match finding --------------------------------------------------------------------------
-TB200_HD uint32_t deflate_hash(const uint8_t* p) {
-  const uint32_t v = static_cast<uint32_t>(p[0]) | (static_cast<uint32_t>(p[1]) << 8) |
-                     (static_cast<uint32_t>(p[2]) << 16) | (static_cast<uint32_t>(p[3]) << 24);
+// The chunk sits in shared memory with every sub-block shifted by one more word: thread t
+// walks sub-block t, and without the skew the threads of a warp would hit the same banks on
+// every byte they compare.  A sub-block itself stays contiguous.
+TB200_HD uint32_t deflate_at(uint32_t p) { return p + ((p >> kDeflateSubShift) << 2); }
+constexpr int kDeflateInBytes = kDeflateChunk + (kDeflateChunk / kDeflateSub) * 4 + 16;
+
+TB200_HD uint32_t deflate_hash(const uint8_t* in, uint32_t p) {
+  const uint32_t v = static_cast<uint32_t>(in[deflate_at(p)]) | (static_cast<uint32_t>(in[deflate_at(p + 1)]) << 8) |
+                     (static_cast<uint32_t>(in[deflate_at(p + 2)]) << 16) | (static_cast<uint32_t>(in[deflate_at(p + 3)]) << 24);
   return (v * 2654435761u) >> (32 - kDeflateHashBits);
 }
 TB200_HD uint32_t deflate_match_len(const uint8_t* in, uint32_t a, uint32_t b, uint32_t maxlen) {
   uint32_t n = 0;
-  while (n < maxlen && in[a + n] == in[b + n]) ++n;
+  while (n < maxlen && in[deflate_at(a + n)] == in[deflate_at(b + n)]) ++n;
   return n;
 }
 // best (len, dist) at position p, match not longer than `room`; candidates: the hash chain
@@ -152,23 +159,44 @@ TB200_HD void deflate_best(const uint8_t* in, uint32_t p, uint32_t room, uint32_
 }
 
 // Greedy parse of sub-block [begin, end) of the chunk `in`; cand[p] = an earlier position with
-// the same 4-byte hash (or kDeflateNoCand).  emit == false: only count.  Returns the bits used.
-TB200_HD uint32_t deflate_parse(const uint8_t* in, uint32_t begin, uint32_t end, const uint16_t* cand, uint32_t* words,
-                                uint32_t bitpos, bool emit) {
-  uint32_t pos = bitpos;
+// the same 4-byte hash (or kDeflateNoCand).  Counts the bits and leaves the decisions in the
+// cand array itself for the emitting pass: cand[p] = distance (0 = literal) and, for a match,
+// cand[p + 1] = length (a match covers >= 3 positions of its own sub-block, and the positions
+// it covers are never parsed, so their candidates are dead).
+TB200_HD uint32_t deflate_parse(const uint8_t* in, uint32_t begin, uint32_t end, uint16_t* cand) {
+  uint32_t bits = 0;
   uint32_t p = begin;
   while (p < end) {
     uint32_t len, dist;
     deflate_best(in, p, end - p, cand[p], &len, &dist);
     if (len >= 3u) {
-      pos += emit ? deflate_emit_match(words, pos, len, dist) : deflate_match_bits(len, dist);
+      bits += deflate_match_bits(len, dist);
+      cand[p] = static_cast<uint16_t>(dist);
+      cand[p + 1] = static_cast<uint16_t>(len);
       p += len;
     } else {
-      pos += emit ? deflate_emit_literal(words, pos, in[p]) : deflate_literal_bits(in[p]);
+      bits += deflate_literal_bits(in[deflate_at(p)]);
+      cand[p] = 0;
       p += 1;
     }
   }
-  return pos - bitpos;
+  return bits;
+}
+// Emit the tokens deflate_parse left behind, starting at bit `bitpos`.
+TB200_HD void deflate_emit(const uint8_t* in, uint32_t begin, uint32_t end, const uint16_t* tokens, uint32_t* words, uint32_t bitpos) {
+  uint32_t pos = bitpos;
+  uint32_t p = begin;
+  while (p < end) {
+    const uint32_t dist = tokens[p];
+    if (dist != 0u) {
+      const uint32_t len = tokens[p + 1];
+      pos += deflate_emit_match(words, pos, len, dist);
+      p += len;
+    } else {
+      pos += deflate_emit_literal(words, pos, in[deflate_at(p)]);
+      p += 1;
+    }
+  }
 }
 
 // ---- checksums ---------------------------------------------------------------------------------
@@ -176,7 +204,7 @@ TB200_HD uint32_t deflate_parse(const uint8_t* in, uint32_t begin, uint32_t end,
 constexpr uint32_t kAdlerMod = 65521u;
 TB200_HD void adler_piece(const uint8_t* d, uint32_t n, uint32_t* a_out, uint32_t* b_out) {
   uint32_t a = 0, b = 0;
-  for (uint32_t i = 0; i < n; ++i) {  // n <= 128: no overflow (a < 32640, b < 2.1e6)
+  for (uint32_t i = 0; i < n; ++i) {  // n <= kDeflateSub: no overflow
     a += d[i];
     b += a;
   }
@@ -199,6 +227,12 @@ TB200_HD uint32_t crc32_raw(uint32_t init, const uint8_t* d, uint32_t n) {
     c ^= d[i];
     for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
   }
+  return c;
+}
+// the same through a 256-entry table (tbl[i] = crc32_raw(0, {i}, 1))
+TB200_HD uint32_t crc32_raw_tbl(const uint32_t* tbl, uint32_t init, const uint8_t* d, uint32_t n) {
+  uint32_t c = init;
+  for (uint32_t i = 0; i < n; ++i) c = tbl[(c ^ d[i]) & 0xFFu] ^ (c >> 8);
   return c;
 }
 // multiply two polynomials mod P in the reflected representation (zlib's multmodp)

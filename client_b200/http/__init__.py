@@ -4,7 +4,7 @@ src/python/library/tritonclient/http/__init__.py:29-53)."""
 from ..utils import *  # noqa: F401,F403
 from .._plugin import InferenceServerClientPlugin
 from .._request import Request
-from ._client import InferAsyncRequest, InferenceServerClient
+from ._client import InferAsyncRequest, InferenceServerClient, set_device_compression
 from ._infer_input import InferInput
 from ._infer_result import InferResult
 from ._requested_output import InferRequestedOutput
@@ -19,4 +19,5 @@ __all__ = [
     "InferResult",
     "InferAsyncRequest",
     "InferenceServerException",
+    "set_device_compression",
 ]

@@ -222,6 +222,32 @@ class _ConnectionPool:
                 conn.close()
 
 
+_device_compression = {"enabled": False}
+
+
+def set_device_compression(enabled):
+    """Compress request bodies with the device deflate encoder (``tb200_deflate_async``)
+    instead of host zlib / gzip (reference :1440-1460).  Off by default: the reference's
+    behaviour.  When switched on there is no host fallback: without libtb200 and a GPU the
+    next compressed request raises.  The stream is a valid zlib / gzip stream but not
+    byte-identical to zlib's own output."""
+    _device_compression["enabled"] = bool(enabled)
+
+
+def _compress_on_device(body, algorithm):
+    import numpy as np
+
+    from .. import _native
+    from ..device import DeviceOps
+
+    ops = DeviceOps(_native.default_context(0))
+    host = np.frombuffer(body, dtype=np.uint8)
+    src = ops._scratch(max(len(body), 16))
+    if len(body):
+        ops.h2d(src.ptr, host.ctypes.data, len(body))
+    return ops.deflate(src.ptr, len(body), algorithm)  # synchronises: `host` stays alive until then
+
+
 class InferAsyncRequest:
     """Handle of an in-flight asynchronous inference request.
 
@@ -577,12 +603,14 @@ class InferenceServerClient(InferenceServerClientBase):
             timeout=timeout, custom_parameters=parameters,
         )
         extra = {}
-        if request_compression_algorithm == "gzip":
-            extra["Content-Encoding"] = "gzip"
-            body = gzip.compress(body)
-        elif request_compression_algorithm == "deflate":
-            extra["Content-Encoding"] = "deflate"
-            body = zlib.compress(body)
+        if request_compression_algorithm in ("gzip", "deflate"):
+            extra["Content-Encoding"] = request_compression_algorithm
+            if _device_compression["enabled"]:
+                body = _compress_on_device(body, request_compression_algorithm)
+            elif request_compression_algorithm == "gzip":
+                body = gzip.compress(body)
+            else:
+                body = zlib.compress(body)
         if response_compression_algorithm in ("gzip", "deflate"):
             extra["Accept-Encoding"] = response_compression_algorithm
         if json_size is not None:

@@ -71,21 +71,20 @@ uint64_t emul_deflate(const uint8_t* src, uint64_t nbytes, uint32_t gzip, uint8_
     out = 2;
   }
   uint32_t A = 0, B = 0, crc = 0;
-  std::vector<uint8_t> in(kDeflateChunk + 16);
+  std::vector<uint8_t> in(kDeflateInBytes);
   std::vector<uint16_t> cand(kDeflateChunk), table(1 << kDeflateHashBits);
   std::vector<uint32_t> words(kDeflateOutWords);
   for (uint64_t base = 0; base < nbytes; base += kDeflateChunk) {
     const uint32_t n = static_cast<uint32_t>(nbytes - base < static_cast<uint64_t>(kDeflateChunk) ? nbytes - base : kDeflateChunk);
-    memcpy(in.data(), src + base, n);
-    memset(in.data() + n, 0, 16);
+    for (uint32_t i = 0; i < n; ++i) in[deflate_at(i)] = src[base + i];
     std::fill(table.begin(), table.end(), static_cast<uint16_t>(kDeflateNoCand));
     std::fill(words.begin(), words.end(), 0u);
     for (uint32_t r0 = 0; r0 < n; r0 += kDeflateThreads) {
       for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads) && r0 + t < n; ++t) {
         const uint32_t p = r0 + t;
-        cand[p] = p + 3 < n ? table[deflate_hash(in.data() + p)] : static_cast<uint16_t>(kDeflateNoCand);
+        cand[p] = p + 3 < n ? table[deflate_hash(in.data(), p)] : static_cast<uint16_t>(kDeflateNoCand);
       }
-      for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads) && r0 + t + 3 < n; ++t) table[deflate_hash(in.data() + r0 + t)] = static_cast<uint16_t>(r0 + t);
+      for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads) && r0 + t + 3 < n; ++t) table[deflate_hash(in.data(), r0 + t)] = static_cast<uint16_t>(r0 + t);
     }
     uint32_t off[kDeflateThreads], total = 3;
     uint32_t chunk_crc = 0;
@@ -93,11 +92,11 @@ uint64_t emul_deflate(const uint8_t* src, uint64_t nbytes, uint32_t gzip, uint8_
       const uint32_t b0 = t * kDeflateSub;
       const uint32_t e0 = b0 < n ? (b0 + kDeflateSub < n ? b0 + kDeflateSub : n) : b0;
       off[t] = total;
-      if (e0 > b0) total += deflate_parse(in.data(), b0, e0, cand.data(), words.data(), 0, false);
+      if (e0 > b0) total += deflate_parse(in.data(), b0, e0, cand.data());
       uint32_t a, b;
-      adler_piece(in.data() + b0, e0 - b0, &a, &b);
+      adler_piece(in.data() + deflate_at(b0), e0 - b0, &a, &b);
       adler_append(&A, &B, a, b, e0 - b0);
-      chunk_crc = crc32_concat_raw(chunk_crc, crc32_raw(0u, in.data() + b0, e0 - b0), e0 - b0);
+      chunk_crc = crc32_concat_raw(chunk_crc, crc32_raw(0u, in.data() + deflate_at(b0), e0 - b0), e0 - b0);
     }
     crc = crc32_concat_raw(crc, chunk_crc, n);
     const uint32_t flush_at = (total + 7 + 3 + 7) >> 3;
@@ -108,14 +107,14 @@ uint64_t emul_deflate(const uint8_t* src, uint64_t nbytes, uint32_t gzip, uint8_
       dst[out + 2] = static_cast<uint8_t>(n >> 8);
       dst[out + 3] = static_cast<uint8_t>(~n & 0xFF);
       dst[out + 4] = static_cast<uint8_t>((~n >> 8) & 0xFF);
-      memcpy(dst + out + 5, in.data(), n);
+      for (uint32_t i = 0; i < n; ++i) dst[out + 5 + i] = in[deflate_at(i)];
       out += n + 5;
     } else {
       deflate_put(words.data(), 0, 2u, 3);
       for (int t = 0; t < kDeflateThreads; ++t) {
         const uint32_t b0 = t * kDeflateSub;
         const uint32_t e0 = b0 < n ? (b0 + kDeflateSub < n ? b0 + kDeflateSub : n) : b0;
-        if (e0 > b0) deflate_parse(in.data(), b0, e0, cand.data(), words.data(), off[t], true);
+        if (e0 > b0) deflate_emit(in.data(), b0, e0, cand.data(), words.data(), off[t]);
       }
       deflate_put(words.data(), (flush_at + 2) * 8, 0xFFFFu, 16);
       memcpy(dst + out, words.data(), comp);

@@ -91,3 +91,28 @@ def test_grpc_cudashm_device_generated_inputs(server):
         client.unregister_cuda_shared_memory()
     cudashm.destroy_shared_memory_region(ip)
     cudashm.destroy_shared_memory_region(op)
+
+
+@pytest.mark.parametrize("algorithm", ["gzip", "deflate"])
+def test_request_body_compressed_on_the_device(server, algorithm):
+    """request_compression_algorithm with the device encoder switched on: the mock server
+    inflates the body with zlib / gzip (like the reference's peer) and computes add/sub."""
+    import client_b200.http as httpclient
+
+    a = np.arange(16, dtype=np.int32)[None, :]
+    b = np.full((1, 16), 7, dtype=np.int32)
+    big = np.zeros((1, 1 << 18), dtype=np.int32)  # 1 MB of mostly-zero data through identity
+    big[0, ::977] = np.arange(big[0, ::977].size)
+    httpclient.set_device_compression(True)
+    try:
+        with httpclient.InferenceServerClient(server["http"]) as client:
+            inputs = [httpclient.InferInput("INPUT0", [1, 16], "INT32").set_data_from_numpy(a),
+                      httpclient.InferInput("INPUT1", [1, 16], "INT32").set_data_from_numpy(b)]
+            res = client.infer("simple", inputs, request_compression_algorithm=algorithm)
+            assert np.array_equal(res.as_numpy("OUTPUT0"), a + b) and np.array_equal(res.as_numpy("OUTPUT1"), a - b)
+            inp = httpclient.InferInput("INPUT0", list(big.shape), "INT32").set_data_from_numpy(big)
+            res = client.infer("custom_identity_int32", [inp], request_compression_algorithm=algorithm,
+                               response_compression_algorithm=algorithm)
+            assert np.array_equal(res.as_numpy("OUTPUT0"), big)
+    finally:
+        httpclient.set_device_compression(False)

@@ -74,3 +74,27 @@ def test_sass_has_tma_bulk_copy_and_wide_stores():
         pytest.skip("cuobjdump not available")
     assert "UBLKCP" in sass and "STG.E.EF.128" in sass and "IMAD.WIDE.U32" in sass
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_device_compression_has_no_host_fallback():
+    """http.set_device_compression(True) on a machine without a GPU: the compressed request
+    raises instead of silently using zlib."""
+    import numpy as np
+    import pytest
+
+    import client_b200.http as httpclient
+    from client_b200 import _native
+
+    try:
+        _native.default_context(0)
+        pytest.skip("a CUDA device is present")
+    except _native.NativeError:
+        pass
+    httpclient.set_device_compression(True)
+    try:
+        client = httpclient.InferenceServerClient("127.0.0.1:1")
+        inp = httpclient.InferInput("X", [4], "INT32").set_data_from_numpy(np.arange(4, dtype=np.int32))
+        with pytest.raises(_native.NativeError):
+            client.infer("m", [inp], request_compression_algorithm="gzip")
+    finally:
+        httpclient.set_device_compression(False)
