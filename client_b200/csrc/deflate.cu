@@ -15,8 +15,8 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
   __shared__ uint32_t crc_tbl[256];
   __shared__ uint16_t cand[kDeflateChunk];
   __shared__ uint32_t words[kDeflateOutWords];
-  uint16_t* table = reinterpret_cast<uint16_t*>(words);  // hash heads; dead before the bit buffer is used
-  static_assert(sizeof(uint16_t) * (1 << kDeflateHashBits) <= sizeof(uint32_t) * kDeflateOutWords, "table aliases words");
+  uint32_t* table = words;  // hash heads (position + 1, 0 = none); dead before the bit buffer is used
+  static_assert((1 << kDeflateHashBits) <= kDeflateOutWords, "table aliases words");
   __shared__ uint32_t sub_bits[kDeflateThreads];
   __shared__ uint32_t sub_off[kDeflateThreads];
   __shared__ uint32_t crc_s[kDeflateThreads];
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
     const uint8_t b = static_cast<uint8_t>(i);
     crc_tbl[i] = crc32_raw(0u, &b, 1);
   }
-  for (uint32_t i = tid; i < (1u << kDeflateHashBits); i += kDeflateThreads) table[i] = static_cast<uint16_t>(kDeflateNoCand);
+  for (uint32_t i = tid; i < (1u << kDeflateHashBits); i += kDeflateThreads) table[i] = 0u;
   if (tid < 8) pw[tid] = crc32_xpow8n(static_cast<uint64_t>(kDeflateSub) << tid);
   __syncthreads();
 
@@ -46,12 +46,13 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
     const bool ok = p + 3 < n;
     if (ok) {
       h = deflate_hash(in, p);
-      cand[p] = table[h];
+      const uint32_t head = table[h];
+      cand[p] = head != 0u ? static_cast<uint16_t>(head - 1u) : static_cast<uint16_t>(kDeflateNoCand);
     } else if (p < n) {
       cand[p] = static_cast<uint16_t>(kDeflateNoCand);
     }
     __syncthreads();
-    if (ok) table[h] = static_cast<uint16_t>(p);
+    if (ok) atomicMax(table + h, p + 1u);  // several positions of a round may share a hash: the latest stays
     __syncthreads();
   }
 

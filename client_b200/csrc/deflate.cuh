@@ -29,7 +29,7 @@ constexpr int kDeflateChunk = 8192;   // bytes per CTA
 constexpr int kDeflateSub = 64;       // bytes per thread
 constexpr int kDeflateSubShift = 6;
 constexpr int kDeflateThreads = kDeflateChunk / kDeflateSub;  // 128
-constexpr int kDeflateHashBits = 12;
+constexpr int kDeflateHashBits = 11;   // 2048 heads of 32 bits: atomicMax keeps the latest position
 constexpr uint32_t kDeflateNoCand = 0xFFFFu;
 // worst case of a fixed-Huffman chunk: 9 bits per byte + header/EOB/flush
 constexpr int kDeflateOutWords = (kDeflateChunk * 9 / 8 + 64) / 4;
