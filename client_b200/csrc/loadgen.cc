@@ -255,6 +255,7 @@ void request_start(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, boo
     conn_close(t, c);  // keep-alive connection the server dropped: reconnect once
     if (++c.attempts >= 2) break;
   }
+  std::this_thread::sleep_for(std::chrono::milliseconds(1));  // unreachable server: fail slowly, do not spin
   request_done(lg, t, c, index, false, now_ns());
 }
 
@@ -277,8 +278,7 @@ void request_done(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool
     if (ok) {
       request_start(lg, t, c, index, false);
     } else {
-      // do not spin (or recurse) on a dead server: retry from the event loop a little later
-      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+      // do not recurse on a dead server: retry from the event loop
       {
         std::lock_guard<std::mutex> lk(t->mu);
         t->ready.push_back(c.slot);
