@@ -42,4 +42,11 @@ def install_as_tritonclient(include_cuda=True):
         mod = importlib.import_module(__name__ + "." + sub)
         sys.modules["tritonclient." + sub] = mod
         registered.append("tritonclient." + sub)
+    # the protobuf modules the gRPC package builds at import time (reference: generated
+    # service_pb2 / service_pb2_grpc / model_config_pb2, tritonclient/grpc/__init__.py:29-73)
+    for name in ("service_pb2", "service_pb2_grpc", "model_config_pb2"):
+        mod = sys.modules.get(__name__ + ".grpc." + name)
+        if mod is not None:
+            sys.modules["tritonclient.grpc." + name] = mod
+            registered.append("tritonclient.grpc." + name)
     return registered

@@ -191,6 +191,13 @@ MODELS = {
     "bert_large": ("mock", [("input_ids", "INT64", [1, 384]), ("attention_mask", "INT64", [1, 384])],
                    [("logits", "FP32", [1, 384])], False),
     "string_identity": ("mock", [("INPUT0", "BYTES", [1, 8])], [("OUTPUT0", "BYTES", [1, 8])], False),
+    # models of the reference's example scripts (src/python/examples/simple_*_string_*, *_int8_*, *_sequence_*)
+    "simple_string": ("mock", [("INPUT0", "BYTES", [1, 16]), ("INPUT1", "BYTES", [1, 16])],
+                      [("OUTPUT0", "BYTES", [1, 16]), ("OUTPUT1", "BYTES", [1, 16])], False),
+    "simple_int8": ("mock", [("INPUT0", "INT8", [1, 16]), ("INPUT1", "INT8", [1, 16])],
+                    [("OUTPUT0", "INT8", [1, 16]), ("OUTPUT1", "INT8", [1, 16])], False),
+    "simple_sequence": ("mock", [("INPUT", "INT32", [1, 1])], [("OUTPUT", "INT32", [1, 1])], False),
+    "simple_identity": ("mock", [("INPUT0", "BYTES", [-1, -1])], [("OUTPUT0", "BYTES", [-1, -1])], False),
     "repeat_int32": ("mock", [("IN", "INT32", [-1])], [("OUT", "INT32", [1])], True),
     "llama3_8b": ("mock", [("input_ids", "INT32", [1, -1])], [("token", "INT32", [1, 1])], True),
 }
@@ -201,6 +208,20 @@ def run_model(model, inputs, params):
     if model == "simple":
         a, b = inputs["INPUT0"], inputs["INPUT1"]
         return [{"OUTPUT0": ("INT32", a + b), "OUTPUT1": ("INT32", a - b)}]
+    if model == "simple_int8":
+        a, b = inputs["INPUT0"].astype(np.int8), inputs["INPUT1"].astype(np.int8)
+        return [{"OUTPUT0": ("INT8", (a + b).astype(np.int8)), "OUTPUT1": ("INT8", (a - b).astype(np.int8))}]
+    if model == "simple_string":  # decimal strings in, decimal strings out
+        a = np.array([int(x) for x in inputs["INPUT0"].reshape(-1)], dtype=np.int64)
+        b = np.array([int(x) for x in inputs["INPUT1"].reshape(-1)], dtype=np.int64)
+        shape = inputs["INPUT0"].shape
+        enc = lambda v: np.array([str(int(x)).encode() for x in v], dtype=object).reshape(shape)  # noqa: E731
+        return [{"OUTPUT0": ("BYTES", enc(a + b)), "OUTPUT1": ("BYTES", enc(a - b))}]
+    if model == "simple_sequence":
+        # the value checked by simple_*_sequence_*_client.py: the input, plus one on the
+        # request that starts a sequence
+        x = inputs["INPUT"].astype(np.int32)
+        return [{"OUTPUT": ("INT32", x + (1 if params.get("sequence_start") else 0))}]
     if model == "densenet_onnx":
         x = inputs["data_0"].astype(np.float32).reshape(-1)
         pad = (-x.size) % 1000
@@ -217,7 +238,7 @@ def run_model(model, inputs, params):
         n = int(params.get("max_tokens", 4))
         base = int(ids.astype(np.int64).sum() % 128256)
         return [{"token": ("INT32", np.array([[(base + k) % 128256]], np.int32))} for k in range(n)]
-    if model.startswith("identity") or model in ("custom_identity_int32", "string_identity"):
+    if model.startswith("identity") or model in ("custom_identity_int32", "string_identity", "simple_identity"):
         (name, arr), = list(inputs.items())[:1]
         dt = utils.np_to_triton_dtype(arr.dtype)
         return [{"OUTPUT0": (dt, arr)}]
@@ -297,7 +318,7 @@ class MockCore:
                     k = int(spec["classification"])
                     flat = np.asarray(arr, dtype=np.float64).reshape(-1)
                     top = np.argsort(-flat, kind="stable")[:k]
-                    labels = np.array([("%f:%d" % (flat[i], i)).encode() for i in top], dtype=object)
+                    labels = np.array([("%f:%d:class_%d" % (flat[i], i, i)).encode() for i in top], dtype=object)  # value:index:label
                     entry.update(datatype="BYTES", shape=[len(top)], raw=_encode("BYTES", labels), array=labels)
                 elif spec and spec.get("shm") is not None:
                     region, size, offset = spec["shm"]
@@ -366,7 +387,7 @@ def _http_handler(core, verbose=False):
                 if path == ["v2", "health", "live"] or path == ["v2", "health", "ready"]:
                     return self._send(200)
                 if path == ["v2"]:
-                    return self._json({"name": "tb200-mock", "version": "0.1", "extensions": ["binary_tensor_data", "system_shared_memory", "cuda_shared_memory"]})
+                    return self._json({"name": "triton", "version": "0.1-tb200-mock", "extensions": ["binary_tensor_data", "system_shared_memory", "cuda_shared_memory"]})
                 if path[:2] == ["v2", "models"] and len(path) >= 3:
                     model = path[2]
                     rest = path[3:]
@@ -582,7 +603,7 @@ def _grpc_servicer(core):
             return pb.ModelReadyResponse(ready=core.known(request.name))
 
         def ServerMetadata(self, request, context):
-            return pb.ServerMetadataResponse(name="tb200-mock", version="0.1", extensions=["system_shared_memory", "cuda_shared_memory"])
+            return pb.ServerMetadataResponse(name="triton", version="0.1-tb200-mock", extensions=["system_shared_memory", "cuda_shared_memory"])
 
         def ModelMetadata(self, request, context):
             try:
@@ -610,6 +631,8 @@ def _grpc_servicer(core):
                 e.name = t["name"]
                 e.data_type = utils_dtype_enum(t["datatype"])
                 e.dims.extend(t["shape"])
+                if len(t["shape"]) == 3 and t["shape"][0] in (1, 3):  # image-shaped input: CHW
+                    e.format = 2  # FORMAT_NCHW
             for t in md["outputs"]:
                 e = resp.config.output.add()
                 e.name = t["name"]

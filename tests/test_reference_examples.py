@@ -1,0 +1,80 @@
+"""The reference's own example scripts, UNMODIFIED, run against the drop-in package
+(`client_b200.install_as_tritonclient()`) and the mock server: every script ends with its own
+value checks and exits non-zero on a mismatch ("examples as tests").
+Needs /root/reference (present in the build container, absent on the GPU box -> skipped there).
+Not run: the CUDA shared memory examples (GPU tests restate them), the model-control examples
+(server repository semantics), simple_http_infer_client.py (imports gevent itself, absent here),
+ensemble_image_client.py / image_client.py over HTTP (import attrdict, absent here)."""
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from test_loopback import start_server
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXAMPLES = "/root/reference/src/python/examples"
+RUNNER = ("import sys; sys.path.insert(0, %r); import client_b200; client_b200.install_as_tritonclient(); "
+          "import runpy; sys.argv = sys.argv[1:]; runpy.run_path(sys.argv[0], run_name='__main__')" % ROOT)
+
+SCRIPTS = [
+    "grpc_client.py", "grpc_explicit_byte_content_client.py", "grpc_explicit_int8_content_client.py",
+    "grpc_explicit_int_content_client.py", "reuse_infer_objects_client.py", "simple_grpc_aio_infer_client.py",
+    "simple_grpc_aio_sequence_stream_infer_client.py", "simple_grpc_async_infer_client.py",
+    "simple_grpc_custom_args_client.py", "simple_grpc_custom_repeat.py", "simple_grpc_health_metadata.py",
+    "simple_grpc_infer_client.py", "simple_grpc_keepalive_client.py", "simple_grpc_sequence_stream_infer_client.py",
+    "simple_grpc_sequence_sync_infer_client.py", "simple_grpc_shm_client.py", "simple_grpc_shm_string_client.py",
+    "simple_grpc_string_infer_client.py", "simple_http_aio_infer_client.py", "simple_http_async_infer_client.py",
+    "simple_http_health_metadata.py", "simple_http_sequence_sync_infer_client.py", "simple_http_shm_client.py",
+    "simple_http_shm_string_client.py", "simple_http_string_infer_client.py",
+]
+IMAGE_RUNS = [
+    ("image_client.py", ["-m", "densenet_onnx", "-s", "INCEPTION", "-c", "3", "-i", "grpc"]),
+    ("image_client.py", ["-m", "densenet_onnx", "-s", "VGG", "-c", "2", "-i", "grpc", "--streaming"]),
+    ("image_client.py", ["-m", "densenet_onnx", "-s", "NONE", "-c", "1", "-i", "grpc", "-a"]),
+    ("grpc_image_client.py", ["-m", "densenet_onnx", "-s", "INCEPTION", "-c", "3"]),
+]
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(EXAMPLES), reason="the reference tree is not mounted")
+
+
+@pytest.fixture(scope="module")
+def outcomes(tmp_path_factory):
+    from PIL import Image
+
+    img = str(tmp_path_factory.mktemp("img") / "photo.png")
+    Image.fromarray(np.random.default_rng(0).integers(0, 256, (300, 400, 3), dtype=np.uint8)).save(img)
+    proc, http_port, grpc_port = start_server()
+    jobs = []
+    for name in SCRIPTS:
+        port = grpc_port if name.startswith(("grpc_", "simple_grpc")) else http_port
+        jobs.append((name, [os.path.join(EXAMPLES, name), "-u", "127.0.0.1:%d" % port]))
+    for name, args in IMAGE_RUNS:
+        jobs.append(("%s %s" % (name, " ".join(args)), [os.path.join(EXAMPLES, name)] + args + ["-u", "127.0.0.1:%d" % grpc_port, img]))
+
+    def run(job):
+        label, argv = job
+        try:
+            r = subprocess.run([sys.executable, "-c", RUNNER] + argv, capture_output=True, text=True, timeout=120, cwd=str(tmp_path_factory.getbasetemp()))
+            return label, r.returncode, (r.stdout + r.stderr)[-1500:]
+        except subprocess.TimeoutExpired:
+            return label, -1, "timeout"
+
+    try:
+        with ThreadPoolExecutor(max_workers=6) as pool:
+            results = {label: (rc, tail) for label, rc, tail in pool.map(run, jobs)}
+    finally:
+        proc.terminate()
+        proc.wait(10)
+    return results
+
+
+@pytest.mark.parametrize("label", SCRIPTS + ["%s %s" % (n, " ".join(a)) for n, a in IMAGE_RUNS])
+def test_unmodified_reference_example(outcomes, label):
+    rc, tail = outcomes[label]
+    assert rc == 0, tail
+    assert "FAILED" not in tail, tail
