@@ -133,7 +133,7 @@ def test_grpc_infer_async_and_shm(server):
         assert client.is_server_live() and client.is_model_ready("simple") and not client.is_model_ready("nope")
         assert client.get_model_metadata("simple").inputs[0].name == "INPUT0"
         assert client.get_model_config("repeat_int32").config.model_transaction_policy.decoupled
-        assert client.get_server_metadata(as_json=True)["name"] == "tb200-mock"
+        assert client.get_server_metadata(as_json=True)["name"] == "triton"
         a = np.arange(16, dtype=np.int32)[None, :]
         b = np.ones((1, 16), dtype=np.int32)
         inputs = [grpcclient.InferInput("INPUT0", [1, 16], "INT32").set_data_from_numpy(a),
