@@ -1,0 +1,56 @@
+"""Compile the reference's own C++ example programs, UNMODIFIED and from where they lie under
+/root/reference/src/c++/examples, against this repo's C++ front end (client_b200/cpp/compat
+headers + libtb200client.so).  Outputs go to oracle/_ref/cc_examples/ (git-ignored; they travel
+to the GPU box with the snapshot).  Test infrastructure: the binaries end with the examples' own
+value checks ("PASS : ..."), so running them against the stand-in servers shows that code
+written for the reference C++ HTTP client builds and behaves the same on the front end.
+
+Not built: examples that need grpc_client.h (gRPC front end: out of scope), json_utils.h
+(RapidJSON, absent) or OpenCV (image clients).
+"""
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference/src/c++/examples"
+OUT = os.path.join(HERE, "_ref", "cc_examples")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+EXAMPLES = ["simple_http_infer_client", "simple_http_async_infer_client", "simple_http_string_infer_client",
+            "simple_http_shm_client", "simple_http_sequence_sync_infer_client"]
+CUDA_EXAMPLES = ["simple_http_cudashm_client"]  # cudaMalloc + cudaIpcGetMemHandle by hand, needs cudart
+
+
+def build_ref_examples(force=False):
+    """Returns {name: path}; {} when the reference tree or g++ is absent."""
+    if not os.path.isdir(REF) or shutil.which("g++") is None:
+        return {}
+    from client_b200.build import build_cpp_client, build_native
+
+    build_native()
+    build_cpp_client()
+    os.makedirs(OUT, exist_ok=True)
+    cpp = os.path.join(ROOT, "client_b200", "cpp")
+    libdir = os.path.join(ROOT, "client_b200", "lib")
+    built = {}
+    for name in EXAMPLES + CUDA_EXAMPLES:
+        src = os.path.join(REF, name + ".cc")
+        exe = os.path.join(OUT, name)
+        deps = [src, os.path.join(libdir, "libtb200client.so"), os.path.join(cpp, "tb200_client.h")]
+        if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+            cmd = ["g++", "-O1", "-std=c++17", "-I" + os.path.join(cpp, "compat"), "-I" + cpp, src, "-o", exe,
+                   "-L" + libdir, "-ltb200client", "-ltb200", "-Wl,-rpath,$ORIGIN/../../../client_b200/lib", "-lpthread", "-lrt"]
+            if name in CUDA_EXAMPLES:
+                cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart"]
+            subprocess.run(cmd, check=True)
+        built[name] = exe
+    return built
+
+
+if __name__ == "__main__":
+    for k, v in build_ref_examples(force=True).items():
+        print(k, "->", v)

@@ -90,3 +90,15 @@ def test_native_engine_against_native_server(server):
     rows = cli.main(["-m", "densenet_onnx", "-u", server, "--shared-memory", "cuda", "--concurrency-range", "2",
                      "-p", "300", "-r", "3", "--json"])
     assert rows[0]["count"] > 10 and rows[0]["failed"] == 0 and rows[0]["nonfinite"] == 0
+
+
+def test_reference_cc_cudashm_example_if_prebuilt(server):
+    """The reference's simple_http_cudashm_client.cc (cudaMalloc + cudaIpcGetMemHandle +
+    RegisterCudaSharedMemory by hand), compiled unmodified against the C++ front end in the
+    build container (oracle/build_ref_examples.py -> oracle/_ref/), run here against the
+    native server."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "cc_examples", "simple_http_cudashm_client")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/cc_examples was not prebuilt")
+    r = subprocess.run([exe, "-u", server], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "PASS : Cuda Shared Memory" in r.stdout, r.stdout[-800:] + r.stderr[-400:]

@@ -78,3 +78,35 @@ def test_unmodified_reference_example(outcomes, label):
     rc, tail = outcomes[label]
     assert rc == 0, tail
     assert "FAILED" not in tail, tail
+
+
+# ---- the reference's C++ examples, compiled unmodified against client_b200/cpp ----------------
+CC_OUT = os.path.join(ROOT, "oracle", "_ref", "cc_examples")
+CC_EXAMPLES = {
+    "simple_http_infer_client": "PASS : Infer",
+    "simple_http_async_infer_client": "PASS : Async Infer",
+    "simple_http_string_infer_client": "PASS : String Infer",
+    "simple_http_shm_client": "PASS : System Shared Memory",
+    "simple_http_sequence_sync_infer_client": "[7] 1 : -1 : -1",
+}
+
+
+@pytest.fixture(scope="module")
+def cc_binaries():
+    from oracle.build_ref_examples import build_ref_examples
+
+    return build_ref_examples()
+
+
+@pytest.mark.parametrize("name", sorted(CC_EXAMPLES))
+def test_unmodified_reference_cc_example(cc_binaries, name):
+    """src/c++/examples/<name>.cc compiled as is against compat/http_client.h + libtb200client.so
+    (oracle/build_ref_examples.py) and run against the mock server's `simple*` models."""
+    assert name in cc_binaries
+    proc, http_port, _ = start_server()
+    try:
+        r = subprocess.run([cc_binaries[name], "-u", "127.0.0.1:%d" % http_port], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0 and CC_EXAMPLES[name] in r.stdout, r.stdout[-800:] + r.stderr[-400:]
+    finally:
+        proc.terminate()
+        proc.wait(10)
