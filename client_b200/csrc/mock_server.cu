@@ -249,6 +249,7 @@ bool handle(tb200_mock_server* s, uint64_t conn_id, const tb200::HttpRequest& re
     else if (path == "/v2/models/densenet_onnx") *resp = EpollHttpServer::Response(200, kDensenetMeta);
     else if (path == "/v2/models/simple") *resp = EpollHttpServer::Response(200, kSimpleMeta);
     else if (path == "/v2/models/densenet_onnx/ready" || path == "/v2/models/simple/ready") *resp = EpollHttpServer::Response(200, "");
+    else if (path.rfind("/v2/systemsharedmemory", 0) == 0) *resp = EpollHttpServer::Response(200, "[]");
     else if (path.rfind("/v2/cudasharedmemory", 0) == 0) {
       std::string js = "[";
       std::lock_guard<std::mutex> lk(s->mu);
@@ -312,6 +313,10 @@ bool handle(tb200_mock_server* s, uint64_t conn_id, const tb200::HttpRequest& re
       *resp = EpollHttpServer::Response(200, "");
       return true;
     }
+  }
+  if (path.rfind("/v2/systemsharedmemory", 0) == 0 && path.size() > 11 && path.compare(path.size() - 11, 11, "/unregister") == 0) {
+    *resp = EpollHttpServer::Response(200, "");  // no system regions are ever registered here
+    return true;
   }
   if (path == "/v2/cudasharedmemory/unregister") {
     std::lock_guard<std::mutex> lk(s->mu);
