@@ -462,7 +462,56 @@ def loopback_extra(device, seconds=1.5):
             srv.wait(10)
         except Exception:
             srv.kill()
+    try:
+        out["under_mps"] = loopback_under_mps(device)
+    except Exception as ex:
+        out["under_mps"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     return out
+
+
+def loopback_under_mps(device):
+    """The same loop with server and generator as two processes that share the GPU through
+    CUDA MPS (their kernels run concurrently instead of time-sliced).  The daemon listens on a
+    private pipe directory, so nothing else on the box is affected; it is shut down afterwards."""
+    import shutil
+    import socket
+
+    if shutil.which("nvidia-cuda-mps-control") is None:
+        return {"available": False}
+    env = dict(os.environ, CUDA_MPS_PIPE_DIRECTORY="/tmp/tb200_mps_pipe", CUDA_MPS_LOG_DIRECTORY="/tmp/tb200_mps_log")
+    os.makedirs(env["CUDA_MPS_PIPE_DIRECTORY"], exist_ok=True)
+    os.makedirs(env["CUDA_MPS_LOG_DIRECTORY"], exist_ok=True)
+    subprocess.run(["nvidia-cuda-mps-control", "-d"], env=env, timeout=30, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    srv = None
+    try:
+        time.sleep(1.0)
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        srv = subprocess.Popen([sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(device)],
+                               cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if "listening" not in srv.stdout.readline():
+            raise RuntimeError("native server did not start under MPS")
+        r = subprocess.run([sys.executable, "-m", "client_b200.perf", "-m", "densenet_onnx", "-u", "127.0.0.1:%d" % port,
+                            "--shared-memory", "cuda", "--engine", "native", "--concurrency-range", "1:256:4x",
+                            "-p", "700", "-r", "4", "--json"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+        levels = []
+        for line in r.stdout.splitlines():
+            if line.startswith("{"):
+                w = json.loads(line)
+                levels.append({"concurrency": w["concurrency"], "infer_per_s": round(w["throughput"], 1), "p50_us": round(w["p50_us"], 1),
+                               "p99_us": round(w["p99_us"], 1), "failed": int(w["failed"]), "nonfinite": int(w["nonfinite"])})
+        if not levels:
+            raise RuntimeError("no result rows: " + (r.stdout + r.stderr)[-300:])
+        return {"available": True, "levels": levels}
+    finally:
+        if srv is not None:
+            srv.terminate()
+            try:
+                srv.wait(10)
+            except Exception:
+                srv.kill()
+        subprocess.run(["nvidia-cuda-mps-control"], input="quit\n", env=env, text=True, timeout=30, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def cpu_baseline_port(seconds=12.0):
