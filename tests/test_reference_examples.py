@@ -110,3 +110,15 @@ def test_unmodified_reference_cc_example(cc_binaries, name):
     finally:
         proc.terminate()
         proc.wait(10)
+
+
+def test_reference_unit_tests_for_system_shared_memory_unmodified():
+    """src/python/library/tests/test_shared_memory.py (the reference's own unittest module)
+    loaded as is with the drop-in aliased as `tritonclient`."""
+    runner = ("import sys, unittest, importlib.util; sys.path.insert(0, %r); import client_b200; client_b200.install_as_tritonclient(); "
+              "spec = importlib.util.spec_from_file_location('ref_shm_tests', '/root/reference/src/python/library/tests/test_shared_memory.py'); "
+              "mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod); "
+              "res = unittest.TextTestRunner(verbosity=0).run(unittest.TestLoader().loadTestsFromModule(mod)); "
+              "print('RAN', res.testsRun, len(res.failures), len(res.errors)); sys.exit(0 if res.wasSuccessful() else 1)" % ROOT)
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", runner], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "RAN 7 0 0" in r.stdout, r.stdout + r.stderr
