@@ -1246,21 +1246,30 @@ int tb200_step_sync(tb200_ctx* ctx, const tb200_fill_job* fill_jobs, int nfill, 
     if (rc != TB200_OK) return rc;
     return tb200_ctx_sync(ctx);
   }
-  if (ncheck > 0) {
-    rc = tb200_ctx_fork(ctx);
-    if (rc == TB200_OK) rc = tb200_check_async(ctx, check_jobs, ncheck, results);
-    if (rc == TB200_OK) rc = tb200_ctx_select(ctx, 0);
-    if (rc != TB200_OK) {
-      if (ctx->forked) tb200_ctx_join(ctx);
-      return rc;
-    }
+  if (ncheck == 0) {
+    rc = tb200_fill_async(ctx, fill_jobs, nfill, seed, stream_epoch);
+    return rc != TB200_OK ? rc : tb200_ctx_sync(ctx);
+  }
+  // Neither launch depends on anything issued before (the server wrote the outputs, the
+  // inputs are write-only), so the side stream needs no fork event: the fill -- the long
+  // pole -- goes out first on the main stream, the check on the side stream, and the call
+  // returns when both streams are idle.
+  DeviceGuard g(ctx->device);
+  if (ctx->side == nullptr) {
+    TB200_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    TB200_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    TB200_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   }
   rc = tb200_fill_async(ctx, fill_jobs, nfill, seed, stream_epoch);
-  if (ctx->forked) {
-    const int rj = tb200_ctx_join(ctx);
-    if (rc == TB200_OK) rc = rj;
-  }
   if (rc != TB200_OK) return rc;
+  ctx->forked = true;  // uploads and launches below go to the side stream
+  ctx->cur = ctx->side;
+  rc = tb200_check_async(ctx, check_jobs, ncheck, results);
+  ctx->cur = ctx->stream;
+  const cudaError_t e_side = cudaStreamSynchronize(ctx->side);
+  ctx->forked = false;
+  if (rc != TB200_OK) return rc;
+  if (e_side != cudaSuccess) return fail(TB200_ERR_CUDA, "cudaStreamSynchronize(side) failed: %s", cudaGetErrorString(e_side));
   return tb200_ctx_sync(ctx);
 }
 
