@@ -564,42 +564,43 @@ __device__ __forceinline__ int32_t resize_dot(const uint8_t* px, int step, const
   for (int t = 0; t < N; ++t) acc += static_cast<int32_t>(px[t * step]) * k[t];
   return acc;
 }
-// the same with a run-time tap count: warp-uniform `n` picks the unrolled body
-__device__ __forceinline__ int32_t resize_dot_n(const uint8_t* px, int step, const int32_t* k, int n) {
-  switch (n) {
-    case 1: return resize_dot<1>(px, step, k);
-    case 2: return resize_dot<2>(px, step, k);
-    case 3: return resize_dot<3>(px, step, k);
-    case 4: return resize_dot<4>(px, step, k);
-    case 5: return resize_dot<5>(px, step, k);
-    case 6: return resize_dot<6>(px, step, k);
-    case 7: return resize_dot<7>(px, step, k);
-    case 8: return resize_dot<8>(px, step, k);
-    default: {
-      int32_t acc = 1 << (kResizeBits - 1);
-      for (int t = 0; t < n; ++t) acc += static_cast<int32_t>(px[t * step]) * k[t];
-      return acc;
-    }
-  }
-}
-
 // phase A inner loop for one (column, channel) pair with N unrolled taps (taps past the
-// pair's own count carry a zero coefficient and re-read the last valid pixel)
+// pair's own count carry a zero coefficient; the bytes they read lie inside the shared
+// memory block -- the staged rows are followed by the 8-bit image -- and do not matter)
 template <int N, int C>
 __device__ __forceinline__ void resize_rows(const uint8_t* rowp, uint8_t* outp, const uint8_t* shift_s, const int32_t (&kr)[8],
-                                            int last, int row0, int rows, int row_step, uint32_t raw_step, int out_step, bool live) {
+                                            int row0, int rows, int row_step, uint32_t raw_step, int out_step, bool live) {
   for (int row = row0; row < rows; row += row_step, rowp += raw_step, outp += out_step) {
     const uint8_t* line = rowp + shift_s[row];
     int32_t acc = 1 << (kResizeBits - 1);
 #pragma unroll
-    for (int t = 0; t < N; ++t) acc += static_cast<int32_t>(line[min(t, last) * C]) * kr[t];
+    for (int t = 0; t < N; ++t) acc += static_cast<int32_t>(line[t * C]) * kr[t];  // kr[t] == 0 past the pair's own taps
     *outp = static_cast<uint8_t>(live ? resize_clip8(acc) : 0u);
   }
 }
 
 // shared memory: raw source block [rows][raw_stride] | horizontally resampled [rows][32*C] |
 // the tile's coefficients (32*hk + tile_h*vk int32) | per-row alignment shifts
-template <int C>
+// one output element: astype + scaling of an 8-bit pixel, by destination type
+template <uint32_t DST, uint32_t SCALING, int C>
+__device__ __forceinline__ void resize_store(void* dst, size_t idx, uint32_t px, int ch) {
+  if constexpr (DST == kF32) static_cast<float*>(dst)[idx] = scale_pixel_f32(px, SCALING, C, ch);
+  else if constexpr (DST == kF16) static_cast<uint16_t*>(dst)[idx] = scale_pixel_f16(px, SCALING, C, ch);
+  else if constexpr (DST == kBF16) static_cast<uint16_t*>(dst)[idx] = f32_to_bf16_trunc(scale_pixel_f32(px, SCALING, C, ch));
+  else static_cast<uint8_t*>(dst)[idx] = static_cast<uint8_t>(px);
+}
+
+// phase B for one output pixel: N-tap vertical dot product per channel, then store
+template <int N, uint32_t DST, uint32_t SCALING, int C>
+__device__ __forceinline__ void resize_column(const uint8_t* col, const int32_t* k, void* dst, size_t base, size_t ch_stride) {
+#pragma unroll
+  for (int ch = 0; ch < C; ++ch) {
+    const uint32_t px = resize_clip8(resize_dot<N>(col + ch, 32 * C, k));
+    resize_store<DST, SCALING, C>(dst, base + ch * ch_stride, px, ch);
+  }
+}
+
+template <int C, uint32_t DST, uint32_t SCALING>
 __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
   extern __shared__ __align__(16) uint8_t rp_smem[];
   constexpr int P = 32 * C;  // (column, channel) pairs of a tile
@@ -628,17 +629,18 @@ __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
     const int nwords = (static_cast<int>(shift) + span * C + 3) >> 2;
     uint32_t* sw_ = reinterpret_cast<uint32_t*>(raw + static_cast<size_t>(row) * p.raw_stride);
     if ((threadIdx.x & 31) == 0) shift_s[row] = static_cast<uint8_t>(shift);
-    for (int w = threadIdx.x & 31; w < nwords; w += 32) {
-      const uint8_t* wp = reinterpret_cast<const uint8_t*>(gw + w);
-      uint32_t val = 0;
-      if (wp >= p.src && wp + 4 <= src_end) {
-        val = __ldg(gw + w);
-      } else {  // first / last word of the whole source: stay inside the buffer
+    const bool inside = reinterpret_cast<const uint8_t*>(gw) >= p.src && reinterpret_cast<const uint8_t*>(gw + nwords) <= src_end;
+    if (inside) {
+      for (int w = threadIdx.x & 31; w < nwords; w += 32) sw_[w] = __ldg(gw + w);
+    } else {  // the row holding the first / last word of the whole source: stay inside the buffer
+      for (int w = threadIdx.x & 31; w < nwords; w += 32) {
+        const uint8_t* wp = reinterpret_cast<const uint8_t*>(gw + w);
+        uint32_t val = 0;
         for (int bb = 0; bb < 4; ++bb) {
           if (wp + bb >= p.src && wp + bb < src_end) val |= static_cast<uint32_t>(wp[bb]) << (8 * bb);
         }
+        sw_[w] = val;
       }
-      sw_[w] = val;
     }
   }
   for (int i = threadIdx.x; i < 32 * p.hk; i += 256) {
@@ -669,18 +671,17 @@ __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
         int32_t kr[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) kr[t] = t < b.y ? k[t] : 0;
-        const int last = b.y > 0 ? b.y - 1 : 0;
         const uint8_t* rowp = raw + static_cast<size_t>(rg) * p.raw_stride + off;
         uint8_t* outp = tmp + rg * P + pair;
         const uint32_t raw_step = RG * p.raw_stride;
         switch (nmax) {
           case 0: case 1: case 2: case 3:
-            resize_rows<3, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
-          case 4: resize_rows<4, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
-          case 5: resize_rows<5, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
-          case 6: resize_rows<6, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
-          case 7: resize_rows<7, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
-          default: resize_rows<8, C>(rowp, outp, shift_s, kr, last, rg, rows, RG, raw_step, RG * P, live); break;
+            resize_rows<3, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
+          case 4: resize_rows<4, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
+          case 5: resize_rows<5, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
+          case 6: resize_rows<6, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
+          case 7: resize_rows<7, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
+          default: resize_rows<8, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
         }
       } else {
         for (int row = rg; row < rows; row += RG) {
@@ -700,40 +701,64 @@ __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
   if (x >= p.dw) return;
   const size_t hw = static_cast<size_t>(p.dh) * p.dw;
   for (int y = y0 + (threadIdx.x >> 5); y <= y1; y += 8) {
-    const int2 b = p.vbounds[y];
+    const int2 b = p.vbounds[y];  // one y per warp: the tap count is warp-uniform
     const int32_t* k = vk_s + (y - y0) * p.vk;
     const size_t pos = static_cast<size_t>(y) * p.dw + x;
-#pragma unroll
-    for (int ch = 0; ch < C; ++ch) {
-      const uint8_t* col = tmp + (b.x - r0) * P + xl * C + ch;
-      const uint32_t px = resize_clip8(resize_dot_n(col, P, k, b.y));  // b.y is warp-uniform (one y per warp)
-      const size_t idx = p.layout == TB200_NCHW ? (static_cast<size_t>(img) * C + ch) * hw + pos
-                                                : (static_cast<size_t>(img) * hw + pos) * C + ch;
-      if (p.dst_dtype == kF32) {
-        static_cast<float*>(p.dst)[idx] = scale_pixel_f32(px, p.scaling, C, ch);
-      } else if (p.dst_dtype == kF16) {
-        static_cast<uint16_t*>(p.dst)[idx] = scale_pixel_f16(px, p.scaling, C, ch);
-      } else if (p.dst_dtype == TB200_BF16) {
-        static_cast<uint16_t*>(p.dst)[idx] = f32_to_bf16_trunc(scale_pixel_f32(px, p.scaling, C, ch));
-      } else {
-        static_cast<uint8_t*>(p.dst)[idx] = static_cast<uint8_t>(px);
-      }
+    const size_t base = p.layout == TB200_NCHW ? static_cast<size_t>(img) * C * hw + pos : (static_cast<size_t>(img) * hw + pos) * C;
+    const size_t ch_stride = p.layout == TB200_NCHW ? hw : 1;
+    const uint8_t* col = tmp + (b.x - r0) * P + xl * C;
+    switch (b.y) {
+      case 1: resize_column<1, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
+      case 2: resize_column<2, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
+      case 3: resize_column<3, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
+      case 4: resize_column<4, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
+      case 5: resize_column<5, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
+      case 6: resize_column<6, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
+      case 7: resize_column<7, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
+      case 8: resize_column<8, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
+      default:
+        for (int ch = 0; ch < C; ++ch) {
+          int32_t acc = 1 << (kResizeBits - 1);
+          for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(col[ch + t * P]) * k[t];
+          resize_store<DST, SCALING, C>(p.dst, base + ch * ch_stride, resize_clip8(acc), ch);
+        }
     }
   }
 }
 
-cudaError_t launch_resize_pack(const ResizePack& p, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(resize_pack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(resize_pack_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+template <int C, uint32_t DST>
+static cudaError_t launch_resize_scaling(const ResizePack& p, dim3 grid, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
+  switch (p.scaling) {
+    case TB200_SCALE_NONE:
+      e = cudaFuncSetAttribute(resize_pack_kernel<C, DST, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) resize_pack_kernel<C, DST, 0><<<grid, 256, p.smem_bytes, s>>>(p);
+      break;
+    case TB200_SCALE_INCEPTION:
+      e = cudaFuncSetAttribute(resize_pack_kernel<C, DST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) resize_pack_kernel<C, DST, 1><<<grid, 256, p.smem_bytes, s>>>(p);
+      break;
+    default:
+      e = cudaFuncSetAttribute(resize_pack_kernel<C, DST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) resize_pack_kernel<C, DST, 2><<<grid, 256, p.smem_bytes, s>>>(p);
+      break;
   }
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+template <int C>
+static cudaError_t launch_resize_dtype(const ResizePack& p, dim3 grid, cudaStream_t s) {
+  switch (p.dst_dtype) {
+    case kF32: return launch_resize_scaling<C, kF32>(p, grid, s);
+    case kF16: return launch_resize_scaling<C, kF16>(p, grid, s);
+    case kBF16: return launch_resize_scaling<C, kBF16>(p, grid, s);
+    default: return launch_resize_scaling<C, kU8>(p, grid, s);
+  }
+}
+
+cudaError_t launch_resize_pack(const ResizePack& p, cudaStream_t s) {
   dim3 grid((p.dw + 31) / 32, (p.dh + p.tile_h - 1) / p.tile_h, p.n);
-  if (p.c == 1) resize_pack_kernel<1><<<grid, 256, p.smem_bytes, s>>>(p);
-  else resize_pack_kernel<3><<<grid, 256, p.smem_bytes, s>>>(p);
-  return cudaGetLastError();
+  return p.c == 1 ? launch_resize_dtype<1>(p, grid, s) : launch_resize_dtype<3>(p, grid, s);
 }
 
 template <uint32_t DST, int C>
