@@ -51,6 +51,23 @@ SEED = 20260921
 WORKLOAD = "C2 densenet_onnx FP32[3,224,224] --shared-memory=cuda concurrency=64"
 
 
+def profiled_traffic(label):
+    """dram read + write bytes per launch of a kernel from the committed ncu --set full summary
+    (profiles/r01_<label>_full.txt, written by scripts/summarize_profiles.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_%s_full.txt" % label)
+    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        total, seen = 0.0, 0
+        for line in open(path):
+            parts = line.split()
+            if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and seen < 2:
+                total += float(parts[1]) * unit.get(parts[2], 1)
+                seen += 1
+        return int(total) if seen == 2 else None
+    except OSError:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -355,11 +372,14 @@ def run_b200(args):
         "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "kernel": "fill_kernel (Philox4x32-10 -> FP32, 64 slots per launch)",
                      "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "algorithmic_bytes_per_launch": fill_bytes, "ms_per_launch": round(fill_ms, 6),
+                     "traffic": profiled_traffic("fill_kernel"),
+                     "traffic_note": "dram read+write per launch from profiles/r01_fill_kernel_full.txt (ncu --set full); a write-only 38.5 MB launch stays in the 126 MB L2",
+                     "algorithmic_bytes_per_launch": fill_bytes, "ms_per_launch": round(fill_ms, 6),
                      "peak_source": peak_src, "timing": "CUDA events on the launching stream around %d back-to-back launches in a graph" % (n_graph * reps * SETS)},
         "roofline_pack": {"bound": "hbm", "kernel": "pack_image_chw_tma_kernel (uint8 HWC -> FP32 CHW, INCEPTION)",
                           "achieved": round(pack_bytes / (pack_ms / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                           "frac": round(pack_bytes / (pack_ms / 1e3) / 1e9 / peak, 4),
+                          "traffic": profiled_traffic("pack_image_kernel"),
                           "algorithmic_bytes_per_launch": pack_bytes, "ms_per_launch": round(pack_ms, 6)},
         "resize_pack": {"kernel": "resize_pack_kernel (64 x uint8 375x500x3 -> Pillow BILINEAR 224x224 -> FP32 CHW INCEPTION)",
                         "ms_per_launch": round(rs_ms, 6), "images_per_s": round(SLOTS / (rs_ms / 1e3), 1),
