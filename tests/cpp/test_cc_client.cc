@@ -457,7 +457,65 @@ static void TestLoopback(const std::string& url) {
   delete o1;
 }
 
+static void TestJsonParser() {
+  using tb200::json::Value;
+  Value v;
+  std::string err;
+  const std::string doc = R"({"a":[1,-2,3.5,1e3,18446744073709551615],"s":"x\"y\u00e9\ud83d\ude00\n","o":{"t":true,"f":false,"n":null},"e":[],"eo":{}})";
+  CHECK(Value::Parse(doc.data(), doc.size(), &v, &err));
+  const Value* a = v.Find("a");
+  CHECK(a != nullptr && a->size() == 5);
+  int64_t i = 0;
+  uint64_t u = 0;
+  double d = 0;
+  CHECK((*a)[0].AsInt(&i) && i == 1);
+  CHECK((*a)[1].AsInt(&i) && i == -2);
+  CHECK((*a)[2].AsDouble(&d) && d == 3.5);
+  CHECK((*a)[3].AsDouble(&d) && d == 1000.0);
+  CHECK((*a)[4].AsUInt(&u) && u == 18446744073709551615ULL);
+  CHECK(v.Find("s")->str() == std::string("x\"y\xc3\xa9\xf0\x9f\x98\x80\n"));
+  bool b = false;
+  CHECK(v.Find("o")->Find("t")->AsBool(&b) && b);
+  CHECK(v.Find("o")->Find("n")->is_null());
+  CHECK(v.Find("e")->is_array() && v.Find("e")->size() == 0 && v.Find("eo")->is_object());
+  // writer round trip keeps member order and escapes
+  Value again;
+  const std::string dumped = v.Dump();
+  CHECK(Value::Parse(dumped.data(), dumped.size(), &again, &err) && again.Dump() == dumped);
+  CHECK(dumped.find("\\\"") != std::string::npos && dumped.rfind("{\"a\":[1,-2,3.5,1000.0,18446744073709551615]", 0) == 0);
+  for (const char* bad : {"{", "[1,]", "{\"a\" 1}", "tru", "\"abc", "[1] x", "{\"a\":}", ""}) {
+    Value w;
+    CHECK(!Value::Parse(bad, strlen(bad), &w, &err));
+  }
+  // an error body and a malformed body through the result class
+  tc::InferResult* r = nullptr;
+  const std::string junk = "not json";
+  tc::InferenceServerHttpClient::ParseResponseBody(&r, std::vector<char>(junk.begin(), junk.end()));
+  CHECK(!r->RequestStatus().IsOk());
+  std::string name;
+  CHECK(!r->ModelName(&name).IsOk());
+  delete r;
+}
+
+static void TestBytesInputFromStrings() {
+  tc::InferInput* s = nullptr;
+  tc::InferInput::Create(&s, "S", {1, 2}, "BYTES");
+  s->AppendFromString({"ab", "c"});
+  std::vector<char> body;
+  size_t header_length = 0;
+  tc::InferOptions options("m");
+  CHECK_OK(tc::InferenceServerHttpClient::GenerateRequestBody(&body, &header_length, options, {s}));
+  CHECK(std::string(body.data(), header_length).find("\"binary_data_size\":11") != std::string::npos);
+  CHECK(body.size() == header_length + 11 && memcmp(body.data() + header_length, "\x02\0\0\0ab\x01\0\0\0c", 11) == 0);
+  s->SetBinaryData(false);
+  CHECK_OK(tc::InferenceServerHttpClient::GenerateRequestBody(&body, &header_length, options, {s}));
+  CHECK(std::string(body.data(), body.size()).find("\"data\":[\"ab\",\"c\"]") != std::string::npos && body.size() == header_length);
+  delete s;
+}
+
 int main(int argc, char** argv) {
+  TestJsonParser();
+  TestBytesInputFromStrings();
   TestBinaryInputsToJson();
   TestBinaryInputToJson();
   TestDoubleFormatting();
