@@ -17,7 +17,7 @@ class LoadgenConfig(ctypes.Structure):
         ("ctx", c_vp), ("fill_jobs", ctypes.POINTER(FillJob)), ("fill_jobs_per_slot", c_int),
         ("seed", c_u64), ("regenerate", c_int),
         ("check_jobs", ctypes.POINTER(CheckJob)), ("check_jobs_per_slot", c_int), ("results", c_vp),
-        ("device_window_us", ctypes.c_uint32),
+        ("device_window_us", ctypes.c_uint32), ("protocol", ctypes.c_uint32), ("grpc_path", ctypes.c_char_p),
     ]
 
 
@@ -42,6 +42,8 @@ LOADGEN_SIGNATURES = {
     "tb200_loadgen_destroy": (c_int, [c_vp]),
     "tb200_stub_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "tb200_stub_server_stop": (c_int, [c_vp]),
+    "tb200_grpc_stub_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), c_vp, c_u64, ctypes.POINTER(c_vp)]),
+    "tb200_grpc_stub_server_stop": (c_int, [c_vp]),
     "tb200_mock_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_vp)]),
     "tb200_mock_server_requests": (ctypes.c_uint64, [c_vp]),
     "tb200_mock_server_batches": (ctypes.c_uint64, [c_vp]),

@@ -15,6 +15,7 @@
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
+#include <poll.h>
 #include <fcntl.h>
 #include <sys/epoll.h>
 #include <sys/eventfd.h>
@@ -37,6 +38,8 @@
 #include <vector>
 
 #include "../../include/tb200_loadgen.h"
+#include "h2.h"
+#include "h2_stub_server.h"
 #include "http_server.h"
 
 namespace {
@@ -120,7 +123,9 @@ struct WorkerStats {
 struct Conn {
   int fd = -1;
   int slot = 0;
-  size_t send_off = 0;     // bytes of request + tail already sent
+  std::vector<iovec> tx;   // what is left of the request being sent
+  size_t tx_idx = 0;
+  std::vector<uint8_t> txbuf;  // gRPC: frame headers + message prefix + protobuf head of this request
   bool want_out = false;   // EPOLLOUT armed
   bool in_flight = false;
   int attempts = 0;
@@ -128,6 +133,14 @@ struct Conn {
   size_t header_end = 0;
   long body = 0;
   uint64_t t_start = 0, t_send_end = 0, t_recv_start = 0;
+  // gRPC over cleartext HTTP/2 (h2.h)
+  uint32_t next_stream = 1, cur_stream = 0;
+  int64_t conn_window = tb200::h2::kDefaultWindow;      // what the peer lets us send on the connection
+  uint32_t peer_stream_window = tb200::h2::kDefaultWindow;
+  uint32_t peer_max_frame = tb200::h2::kDefaultMaxFrame;
+  uint64_t recv_consumed = 0;
+  bool got_data = false, waiting_window = false, goaway = false;
+  std::string ctrl;        // control frames (acks, window updates) waiting for a frame boundary
 };
 
 struct Transport {
@@ -148,6 +161,8 @@ struct tb200_loadgen {
   std::vector<const uint8_t*> tails;  // borrowed (pinned staging), may be empty
   std::vector<uint64_t> tail_sizes;
   bool passthrough = false;           // no device work per request: workers keep their slot
+  bool grpc = false;                  // requests[] are ModelInferRequest bytes sent as unary gRPC calls
+  std::string grpc_headers;           // HEADERS payload shared by all requests
   tb200_ctx* ctx = nullptr;
   std::vector<tb200_fill_job> fill_jobs;
   int fill_per_slot = 0;
@@ -174,7 +189,10 @@ namespace {
 
 constexpr uint32_t kEvTag = 0xFFFFFFFFu;
 
+void h2_flush_ctrl(Conn& c);
+
 void conn_close(Transport* t, Conn& c) {
+  c.ctrl.clear();
   if (c.fd >= 0) {
     epoll_ctl(t->epfd, EPOLL_CTL_DEL, c.fd, nullptr);
     close(c.fd);
@@ -191,6 +209,18 @@ bool conn_open(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
   ev.events = EPOLLIN;
   ev.data.u32 = index;
   epoll_ctl(t->epfd, EPOLL_CTL_ADD, c.fd, &ev);
+  if (lg->grpc) {  // fresh HTTP/2 connection state; requests may follow the preface at once
+    c.next_stream = 1;
+    c.cur_stream = 0;
+    c.conn_window = tb200::h2::kDefaultWindow;
+    c.peer_stream_window = tb200::h2::kDefaultWindow;
+    c.peer_max_frame = tb200::h2::kDefaultMaxFrame;
+    c.recv_consumed = 0;
+    c.waiting_window = c.goaway = false;
+    c.buf.clear();
+    c.ctrl = tb200::h2::client_preface();
+    h2_flush_ctrl(c);
+  }
   return true;
 }
 
@@ -205,25 +235,33 @@ void conn_arm(Transport* t, Conn& c, uint32_t index, bool want_out) {
 
 void request_done(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool ok, uint64_t t_end);
 
-// push the rest of request + tail; false on a dead connection
-bool conn_send(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
-  const std::vector<uint8_t>& req = lg->requests[c.slot];
-  const uint8_t* tail = lg->tails.empty() ? nullptr : lg->tails[c.slot];
-  const size_t tail_size = lg->tails.empty() ? 0 : static_cast<size_t>(lg->tail_sizes[c.slot]);
-  const size_t total = req.size() + tail_size;
-  while (c.send_off < total) {
-    iovec iov[2];
-    int n = 0;
-    if (c.send_off < req.size()) {
-      iov[n++] = iovec{const_cast<uint8_t*>(req.data()) + c.send_off, req.size() - c.send_off};
-      if (tail_size) iov[n++] = iovec{const_cast<uint8_t*>(tail), tail_size};
+// queued HTTP/2 control frames go out only between requests' frames
+void h2_flush_ctrl(Conn& c) {
+  if (c.ctrl.empty() || c.want_out || c.fd < 0) return;
+  size_t off = 0;
+  while (off < c.ctrl.size()) {
+    const ssize_t k = send(c.fd, c.ctrl.data() + off, c.ctrl.size() - off, MSG_NOSIGNAL | MSG_DONTWAIT);
+    if (k > 0) {
+      off += static_cast<size_t>(k);
+    } else if (k < 0 && errno == EINTR) {
+      continue;
+    } else if (k < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) {
+      pollfd pfd{c.fd, POLLOUT, 0};
+      if (poll(&pfd, 1, 100) <= 0) break;
     } else {
-      const size_t off = c.send_off - req.size();
-      iov[n++] = iovec{const_cast<uint8_t*>(tail) + off, tail_size - off};
+      break;
     }
+  }
+  c.ctrl.erase(0, off);
+}
+
+// push the rest of c.tx; false on a dead connection
+bool conn_send(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
+  (void)lg;
+  while (c.tx_idx < c.tx.size()) {
     msghdr msg{};
-    msg.msg_iov = iov;
-    msg.msg_iovlen = static_cast<size_t>(n);
+    msg.msg_iov = &c.tx[c.tx_idx];
+    msg.msg_iovlen = std::min<size_t>(c.tx.size() - c.tx_idx, 64);
     const ssize_t k = sendmsg(c.fd, &msg, MSG_NOSIGNAL | MSG_DONTWAIT);
     if (k < 0) {
       if (errno == EINTR) continue;
@@ -233,11 +271,70 @@ bool conn_send(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
       }
       return false;
     }
-    c.send_off += static_cast<size_t>(k);
+    size_t left = static_cast<size_t>(k);
+    while (c.tx_idx < c.tx.size() && left >= c.tx[c.tx_idx].iov_len) {
+      left -= c.tx[c.tx_idx].iov_len;
+      ++c.tx_idx;
+    }
+    if (c.tx_idx < c.tx.size() && left > 0) {
+      c.tx[c.tx_idx].iov_base = static_cast<char*>(c.tx[c.tx_idx].iov_base) + left;
+      c.tx[c.tx_idx].iov_len -= left;
+    }
   }
   c.t_send_end = now_ns();
   conn_arm(t, c, index, false);
+  h2_flush_ctrl(c);
   return true;
+}
+
+// Lay out one unary gRPC call on a fresh stream: HEADERS, then DATA frames over
+// prefix(5) | protobuf head | borrowed tail, cut at the peer's maximum frame size.
+// Returns 0 ok, 1 must wait for connection window, -1 cannot be sent at all.
+int grpc_build(tb200_loadgen* lg, Conn& c) {
+  namespace h2 = tb200::h2;
+  const std::vector<uint8_t>& head = lg->requests[c.slot];
+  const uint8_t* tail = lg->tails.empty() ? nullptr : lg->tails[c.slot];
+  const size_t tail_size = lg->tails.empty() ? 0 : static_cast<size_t>(lg->tail_sizes[c.slot]);
+  const size_t message = head.size() + tail_size;
+  const size_t payload = 5 + message;
+  if (payload > c.peer_stream_window || payload > 0x7FFFFFFFu) return -1;
+  if (static_cast<int64_t>(payload) > c.conn_window) return 1;
+  c.cur_stream = c.next_stream;
+  c.next_stream += 2;
+  c.got_data = false;
+  const size_t maxf = c.peer_max_frame;
+  const size_t nframes = (payload + maxf - 1) / maxf;
+  // txbuf: [HEADERS frame][prefix + head][DATA frame headers ...]
+  c.txbuf.resize(9 + lg->grpc_headers.size() + 5 + head.size() + 9 * nframes);
+  uint8_t* w = c.txbuf.data();
+  h2::put_frame_header(w, static_cast<uint32_t>(lg->grpc_headers.size()), h2::HEADERS, h2::kEndHeaders, c.cur_stream);
+  memcpy(w + 9, lg->grpc_headers.data(), lg->grpc_headers.size());
+  uint8_t* body = w + 9 + lg->grpc_headers.size();
+  h2::put_grpc_prefix(body, static_cast<uint32_t>(message));
+  memcpy(body + 5, head.data(), head.size());
+  const size_t in_buf = 5 + head.size();
+  uint8_t* fh = body + in_buf;
+  c.tx.clear();
+  c.tx_idx = 0;
+  c.tx.push_back(iovec{w, 9 + lg->grpc_headers.size()});
+  size_t off = 0;
+  for (size_t f = 0; f < nframes; ++f) {
+    const size_t chunk = std::min(maxf, payload - off);
+    const bool last = off + chunk == payload;
+    h2::put_frame_header(fh + 9 * f, static_cast<uint32_t>(chunk), h2::DATA, last ? h2::kEndStream : 0, c.cur_stream);
+    c.tx.push_back(iovec{fh + 9 * f, 9});
+    size_t o = off, left = chunk;
+    if (o < in_buf) {
+      const size_t n = std::min(left, in_buf - o);
+      c.tx.push_back(iovec{body + o, n});
+      o += n;
+      left -= n;
+    }
+    if (left > 0) c.tx.push_back(iovec{const_cast<uint8_t*>(tail) + (o - in_buf), left});
+    off += chunk;
+  }
+  c.conn_window -= static_cast<int64_t>(payload);
+  return 0;
 }
 
 void request_start(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool retry) {
@@ -245,12 +342,27 @@ void request_start(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, boo
   for (;;) {
     if (c.fd < 0 && !conn_open(lg, t, c, index)) break;
     c.in_flight = true;
-    c.send_off = 0;
-    c.buf.clear();
     c.header_end = 0;
     c.t_recv_start = 0;
     c.t_start = now_ns();  // REQUEST_START == SEND_START (the request is pre-formed)
     c.t_send_end = c.t_start;
+    if (lg->grpc) {
+      const int rc = grpc_build(lg, c);
+      if (rc > 0) {  // resumes when the peer's WINDOW_UPDATE arrives
+        c.waiting_window = true;
+        return;
+      }
+      if (rc < 0) break;
+    } else {
+      c.buf.clear();
+      c.tx.clear();
+      c.tx_idx = 0;
+      const std::vector<uint8_t>& req = lg->requests[c.slot];
+      c.tx.push_back(iovec{const_cast<uint8_t*>(req.data()), req.size()});
+      if (!lg->tails.empty() && lg->tail_sizes[c.slot] != 0) {
+        c.tx.push_back(iovec{const_cast<uint8_t*>(lg->tails[c.slot]), static_cast<size_t>(lg->tail_sizes[c.slot])});
+      }
+    }
     if (conn_send(lg, t, c, index)) return;
     conn_close(t, c);  // keep-alive connection the server dropped: reconnect once
     if (++c.attempts >= 2) break;
@@ -334,6 +446,111 @@ void conn_readable(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
   }
 }
 
+// HTTP/2 frames of a gRPC connection: acknowledgements, flow control, end of the call
+void grpc_readable(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
+  namespace h2 = tb200::h2;
+  char tmp[16384];
+  bool closed = false;
+  for (;;) {
+    const ssize_t k = recv(c.fd, tmp, sizeof(tmp), MSG_DONTWAIT);
+    if (k > 0) {
+      if (c.in_flight && c.t_recv_start == 0 && c.tx_idx >= c.tx.size()) c.t_recv_start = now_ns();
+      c.buf.insert(c.buf.end(), tmp, tmp + k);
+      if (static_cast<size_t>(k) < sizeof(tmp)) break;
+      continue;
+    }
+    if (k < 0 && errno == EINTR) continue;
+    if (k < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) break;
+    closed = true;
+    break;
+  }
+  size_t pos = 0;
+  bool finished = false, ok = false;
+  while (!finished) {
+    h2::FrameView f;
+    const size_t n = h2::parse_frame(reinterpret_cast<const uint8_t*>(c.buf.data()) + pos, c.buf.size() - pos, &f);
+    if (n == 0) break;
+    pos += n;
+    switch (f.type) {
+      case h2::SETTINGS:
+        if (!(f.flags & h2::kAck)) {
+          for (uint32_t o = 0; o + 6 <= f.length; o += 6) {
+            const uint16_t id = static_cast<uint16_t>((f.payload[o] << 8) | f.payload[o + 1]);
+            const uint32_t v = h2::get_u32(f.payload + o + 2);
+            if (id == h2::kSettingsInitialWindow) c.peer_stream_window = v;
+            else if (id == h2::kSettingsMaxFrame && v >= h2::kDefaultMaxFrame) c.peer_max_frame = std::min<uint32_t>(v, 1u << 20);
+          }
+          c.ctrl += h2::frame(h2::SETTINGS, h2::kAck, 0, "");
+        }
+        break;
+      case h2::PING:
+        if (!(f.flags & h2::kAck) && f.length == 8) c.ctrl += h2::frame(h2::PING, h2::kAck, 0, std::string(reinterpret_cast<const char*>(f.payload), 8));
+        break;
+      case h2::WINDOW_UPDATE:
+        if (f.length == 4 && f.stream == 0) c.conn_window += h2::get_u32(f.payload) & 0x7FFFFFFFu;
+        break;
+      case h2::DATA:
+        c.recv_consumed += f.length;
+        if (f.stream == c.cur_stream && c.in_flight) {
+          if (f.length >= 5) c.got_data = true;
+          if (f.flags & h2::kEndStream) {
+            finished = true;
+            ok = c.got_data;
+          }
+        }
+        break;
+      case h2::HEADERS:
+        if (f.stream == c.cur_stream && c.in_flight && (f.flags & h2::kEndStream)) {
+          finished = true;  // trailers; an error arrives as a trailers-only response without DATA
+          ok = c.got_data;
+        }
+        break;
+      case h2::RST_STREAM:
+        if (f.stream == c.cur_stream && c.in_flight) finished = true;
+        break;
+      case h2::GOAWAY:
+        c.goaway = true;
+        break;
+      default:
+        break;
+    }
+  }
+  if (pos) c.buf.erase(c.buf.begin(), c.buf.begin() + static_cast<long>(pos));
+  if (c.recv_consumed >= (1u << 28)) {  // give the connection window back long before it runs out
+    c.ctrl += h2::window_update(0, static_cast<uint32_t>(c.recv_consumed));
+    c.recv_consumed = 0;
+  }
+  h2_flush_ctrl(c);
+  if (finished) {
+    const uint64_t t_end = now_ns();
+    if (c.t_recv_start == 0) c.t_recv_start = t_end;
+    if (c.goaway) conn_close(t, c);
+    request_done(lg, t, c, index, ok, t_end);
+    return;
+  }
+  if (closed) {
+    conn_close(t, c);
+    if (!c.in_flight) return;
+    c.waiting_window = false;
+    if (++c.attempts < 2 && !lg->stop.load(std::memory_order_relaxed)) request_start(lg, t, c, index, true);
+    else request_done(lg, t, c, index, false, now_ns());
+    return;
+  }
+  if (c.waiting_window && c.in_flight) {  // a WINDOW_UPDATE may have made room
+    const int rc = grpc_build(lg, c);
+    if (rc == 0) {
+      c.waiting_window = false;
+      if (!conn_send(lg, t, c, index)) {
+        conn_close(t, c);
+        request_done(lg, t, c, index, false, now_ns());
+      }
+    } else if (rc < 0) {
+      c.waiting_window = false;
+      request_done(lg, t, c, index, false, now_ns());
+    }
+  }
+}
+
 void transport_main(tb200_loadgen* lg, Transport* t) {
   if (lg->passthrough) {
     for (uint32_t i = 0; i < t->conns.size(); ++i) request_start(lg, t, t->conns[i], i, false);
@@ -376,7 +593,10 @@ void transport_main(tb200_loadgen* lg, Transport* t) {
         else request_done(lg, t, c, tag, false, now_ns());
         continue;
       }
-      if (events[e].events & (EPOLLIN | EPOLLERR | EPOLLHUP)) conn_readable(lg, t, c, tag);
+      if (events[e].events & (EPOLLIN | EPOLLERR | EPOLLHUP)) {
+        if (lg->grpc) grpc_readable(lg, t, c, tag);
+        else conn_readable(lg, t, c, tag);
+      }
     }
   }
   for (Conn& c : t->conns) conn_close(t, c);
@@ -510,6 +730,15 @@ int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out) {
   lg->seed = cfg->seed;
   lg->regenerate = cfg->regenerate != 0;
   lg->device_window_ns = 1000ull * cfg->device_window_us;
+  lg->grpc = cfg->protocol == 1;
+  if (cfg->protocol > 1) {
+    delete lg;
+    return lg_fail(TB200_ERR_INVALID, "unknown load generator protocol");
+  }
+  if (lg->grpc) {
+    lg->grpc_headers = tb200::h2::grpc_request_headers(lg->host + ":" + std::to_string(lg->port),
+                                                       cfg->grpc_path ? cfg->grpc_path : "/inference.GRPCInferenceService/ModelInfer");
+  }
   if (cfg->ctx != nullptr && cfg->fill_jobs != nullptr && cfg->fill_jobs_per_slot > 0) {
     lg->fill_per_slot = cfg->fill_jobs_per_slot;
     lg->fill_jobs.assign(cfg->fill_jobs, cfg->fill_jobs + static_cast<size_t>(cfg->concurrency) * cfg->fill_jobs_per_slot);
@@ -668,6 +897,40 @@ int tb200_stub_server_start(const char* host, int* port, const char* response_bo
 int tb200_stub_server_stop(tb200_stub_server* s) {
   if (s == nullptr) return TB200_OK;
   s->http.Stop();
+  delete s;
+  return TB200_OK;
+}
+
+int tb200_grpc_stub_server_start(const char* host, int* port, const uint8_t* response, uint64_t response_bytes,
+                                 tb200_grpc_stub_server** out);
+int tb200_grpc_stub_server_stop(tb200_grpc_stub_server* s);
+
+}  // extern "C"
+
+struct tb200_grpc_stub_server {
+  tb200::H2StubServer h2;
+};
+
+extern "C" {
+
+int tb200_grpc_stub_server_start(const char* host, int* port, const uint8_t* response, uint64_t response_bytes,
+                                 tb200_grpc_stub_server** out) {
+  if (host == nullptr || port == nullptr || out == nullptr || (response == nullptr && response_bytes != 0)) {
+    return lg_fail(TB200_ERR_INVALID, "NULL argument");
+  }
+  tb200_grpc_stub_server* s = new tb200_grpc_stub_server();
+  const int hw = static_cast<int>(std::max(2u, std::thread::hardware_concurrency()));
+  if (!s->h2.Start(host, port, std::min(16, hw / 2), std::string(reinterpret_cast<const char*>(response), response_bytes))) {
+    delete s;
+    return lg_fail(TB200_ERR_IO, "cannot bind the gRPC stub server");
+  }
+  *out = s;
+  return TB200_OK;
+}
+
+int tb200_grpc_stub_server_stop(tb200_grpc_stub_server* s) {
+  if (s == nullptr) return TB200_OK;
+  s->h2.Stop();
   delete s;
   return TB200_OK;
 }

@@ -68,11 +68,18 @@ class SlotSet:
     """Per-slot input/output buffers and their device job tables."""
 
     def __init__(self, inputs, outputs, slots, shared_memory, device_id, input_data, seed, token_range=None,
-                 name_prefix="tb200", staging=None):
+                 name_prefix="tb200", staging=None, wire_prefixes=None):
         self.inputs, self.outputs, self.slots = inputs, outputs, slots
         self.shared_memory, self.device_id = shared_memory, device_id
         self.input_data, self.seed = input_data, seed
         self.in_bytes = sum(t.nbytes for t in inputs)
+        # wire mode only: constant bytes in front of every tensor inside the staging image of a
+        # slot (gRPC: the raw_input_contents tag + length), written once; the kernels fill
+        # the tensor bytes between them
+        self._prefixes = [bytes(b) for b in wire_prefixes] if wire_prefixes else [b""] * len(inputs)
+        if any(self._prefixes) and shared_memory != "none":
+            raise ValueError("wire prefixes only apply to --shared-memory none")
+        self.wire_stride = self.in_bytes + sum(len(b) for b in self._prefixes)
         self.out_bytes = sum(t.nbytes for t in outputs)
         self.prefix = name_prefix
         self.epoch = 0
@@ -101,18 +108,27 @@ class SlotSet:
             # CPU-only machines inject their own ``staging`` object.)
             if staging is not None:
                 self._staging = staging
-                staging.allocate(max(slots * self.in_bytes, 16))
+                staging.allocate(max(slots * self.wire_stride, 16))
             else:
                 from ..device import DeviceOps, HostBuffer
 
                 self._ops = DeviceOps(_native.Context(device_id))
-                self._wire = HostBuffer(max(slots * self.in_bytes, 16))
+                self._wire = HostBuffer(max(slots * self.wire_stride, 16))
                 self.in_base = self._wire.device_ptr
+            if any(self._prefixes):
+                for s in range(slots):
+                    for i, b in enumerate(self._prefixes):
+                        off = self.input_offset(s, i) - len(b)
+                        view = self._staging.view(off, len(b)) if self._staging is not None else self._wire.view(off, len(b))
+                        view[:] = b
         self._results = None
         self._result_view = None
 
     # -- layout ------------------------------------------------------------------------
     def input_offset(self, slot, index):
+        if self.shared_memory == "none":
+            before = sum(len(self._prefixes[k]) + self.inputs[k].nbytes for k in range(index))
+            return slot * self.wire_stride + before + len(self._prefixes[index])
         return slot * self.in_bytes + sum(t.nbytes for t in self.inputs[:index])
 
     def output_offset(self, slot, index):

@@ -1,6 +1,7 @@
 """Driver of the native load generator (include/tb200_loadgen.h): builds the per-slot
-HTTP requests with the drop-in request model, hands them plus the device job tables to
-libtb200 and reads back windowed statistics.  HTTP, synchronous closed loop."""
+requests with the drop-in request model (HTTP/1.1 text, or ModelInferRequest bytes for the
+gRPC-over-HTTP/2 transport), hands them plus the device job tables to libtb200 and reads back
+windowed statistics.  Synchronous closed loop."""
 
 import ctypes
 
@@ -22,12 +23,29 @@ def frame_http_request(host, port, uri, body, json_size, head_only_bytes=None):
     return ("\r\n".join(lines) + "\r\n\r\n").encode("ascii") + body
 
 
+def _varint(n):
+    out = bytearray()
+    while n >= 0x80:
+        out.append((n & 0x7F) | 0x80)
+        n >>= 7
+    out.append(n)
+    return bytes(out)
+
+
+def grpc_wire_prefixes(inputs):
+    """What precedes each tensor inside a serialised ModelInferRequest: the tag of
+    ``raw_input_contents`` (field 7, length-delimited: 0x3A) and the byte length.  Passed to
+    SlotSet(wire_prefixes=...) so that a slot's staging image is the tail of the message."""
+    return [b"\x3a" + _varint(t.nbytes) for t in inputs]
+
+
 class NativeLoadGenerator:
     """One tb200_loadgen instance over a SlotSet (cuda shm or wire mode)."""
 
     def __init__(self, url, model_name, model_version, slotset, concurrency, regenerate=True, validate=True,
-                 device_window_us=0):
+                 device_window_us=0, protocol="http"):
         self._lib = _native.load()
+        self.protocol = protocol
         host, _, port = url.partition(":")
         self.host, self.port = host, int(port or 80)
         ss = slotset
@@ -35,7 +53,9 @@ class NativeLoadGenerator:
         uri = InferenceServerClient._model_uri(model_name, model_version, "/infer")
         self._keep = []
         reqs, tails = [], []
-        for slot in range(concurrency):
+        if protocol == "grpc":
+            reqs, tails = self._grpc_requests(model_name, model_version, ss, concurrency)
+        for slot in range(concurrency if protocol != "grpc" else 0):
             inputs, outputs = [], []
             for i, t in enumerate(ss.inputs):
                 inp = InferInput(t.name, t.shape, t.datatype)
@@ -54,7 +74,7 @@ class NativeLoadGenerator:
             if ss.shared_memory == "none":
                 json_size = len(body)
                 reqs.append(frame_http_request(self.host, self.port, uri, body, json_size, head_only_bytes=ss.in_bytes))
-                tails.append((ss._wire.host_ptr + slot * ss.in_bytes, ss.in_bytes))
+                tails.append((ss._wire.host_ptr + slot * ss.wire_stride, ss.wire_stride))
             else:
                 reqs.append(frame_http_request(self.host, self.port, uri, body, json_size))
         n = concurrency
@@ -90,10 +110,42 @@ class NativeLoadGenerator:
                 cfg.check_jobs_per_slot = len(ss.outputs)
                 cfg.results = self._results.device_ptr
         cfg.device_window_us = int(device_window_us)
+        cfg.protocol = 1 if protocol == "grpc" else 0
         self._keep.append(cfg)
         h = ctypes.c_void_p()
         _native.check(self._lib.tb200_loadgen_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
+
+    @staticmethod
+    def _grpc_requests(model_name, model_version, ss, concurrency):
+        """Per slot: ModelInferRequest bytes up to (not including) raw_input_contents; in wire
+        mode the rest of the message is the slot's staging image (tag + length + tensor per
+        input), which must have been laid out with grpc_wire_prefixes()."""
+        from .. import grpc as grpcclient
+        from ..grpc._utils import _get_inference_request
+
+        reqs, tails = [], []
+        for slot in range(concurrency):
+            inputs, outputs = [], []
+            for i, t in enumerate(ss.inputs):
+                inp = grpcclient.InferInput(t.name, t.shape, t.datatype)
+                if ss.shared_memory in ("cuda", "system"):
+                    inp.set_shared_memory(ss.prefix + "_in", t.nbytes, offset=ss.input_offset(slot, i))
+                inputs.append(inp)
+            for i, t in enumerate(ss.outputs):
+                out = grpcclient.InferRequestedOutput(t.name)
+                if ss.shared_memory in ("cuda", "system"):
+                    out.set_shared_memory(ss.prefix + "_out", t.nbytes, offset=ss.output_offset(slot, i))
+                outputs.append(out)
+            request = _get_inference_request(model_name=model_name, inputs=inputs, model_version=model_version, request_id="",
+                                             outputs=outputs, sequence_id=0, sequence_start=False, sequence_end=False,
+                                             priority=0, timeout=None, parameters=None)
+            reqs.append(request.SerializeToString())
+            if ss.shared_memory == "none":
+                if ss.wire_stride == ss.in_bytes and ss.in_bytes:
+                    raise ValueError("the SlotSet of a gRPC wire-mode run needs wire_prefixes=grpc_wire_prefixes(inputs)")
+                tails.append((ss._wire.host_ptr + slot * ss.wire_stride, ss.wire_stride))
+        return reqs, tails
 
     def start(self):
         _native.check(self._lib.tb200_loadgen_start(self._h))
@@ -125,6 +177,27 @@ class NativeLoadGenerator:
             self.stop()
         except Exception:
             pass
+
+
+class GrpcStubServer:
+    """tb200_grpc_stub_server: every unary call answered with one canned message."""
+
+    def __init__(self, response=b"", host="127.0.0.1", port=0):
+        self._lib = _native.load()
+        p = ctypes.c_int(port)
+        h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(response, max(len(response), 1))
+        _native.check(self._lib.tb200_grpc_stub_server_start(host.encode(), ctypes.byref(p), buf, len(response), ctypes.byref(h)))
+        self._h, self.host, self.port = h, host, p.value
+
+    @property
+    def url(self):
+        return "%s:%d" % (self.host, self.port)
+
+    def stop(self):
+        if getattr(self, "_h", None):
+            self._lib.tb200_grpc_stub_server_stop(self._h)
+            self._h = None
 
 
 class StubServer:

@@ -52,6 +52,13 @@ typedef struct tb200_loadgen_config {
    * when client and server are time-sliced CUDA contexts (no MPS): each GPU hand-over
    * between the processes costs ~100 us, so passes should be few and full */
   uint32_t device_window_us;
+  /* 0: requests[] are complete HTTP/1.1 requests.  1: unary gRPC calls over cleartext HTTP/2
+   * (what grpcio does under PY/grpc/_client.py:1445-1572): requests[s] holds the serialised
+   * ModelInferRequest WITHOUT its raw_input_contents, tails[s] the remaining message bytes
+   * (field-7 tag + length + tensor, per input) in pinned staging; one stream per request,
+   * messages up to the peer's stream window (64 KiB by default) */
+  uint32_t protocol;
+  const char* grpc_path; /* NULL -> "/inference.GRPCInferenceService/ModelInfer" */
 } tb200_loadgen_config;
 
 typedef struct tb200_loadgen_stats {
@@ -86,6 +93,12 @@ typedef struct tb200_stub_server tb200_stub_server;
 int tb200_stub_server_start(const char* host, int* port, const char* response_body,
                             tb200_stub_server** out);
 int tb200_stub_server_stop(tb200_stub_server* s);
+/* the same for gRPC: every unary call is answered with `response` (a serialised protobuf
+ * message, e.g. ModelInferResponse) and grpc-status 0 */
+typedef struct tb200_grpc_stub_server tb200_grpc_stub_server;
+int tb200_grpc_stub_server_start(const char* host, int* port, const uint8_t* response,
+                                 uint64_t response_bytes, tb200_grpc_stub_server** out);
+int tb200_grpc_stub_server_stop(tb200_grpc_stub_server* s);
 
 /* A native KServe-v2 stand-in server for loopback load runs over CUDA shared memory
  * (csrc/mock_server.cu; tooling -- the reference has no server).  It opens

@@ -46,6 +46,20 @@ for label, (ins, outs), shm, conc in (("C2 cuda-shm", c2, "cuda", 64), ("C2 cuda
                       "slots_per_pass": round(w["device_slots"] / max(1, w["device_batches"]), 1),
                       "input_gbps": round(w["throughput"] * ss.in_bytes / 1e9, 2)}))
 stub.stop()
+# the same generator over its gRPC transport (cleartext HTTP/2): C4 / C5 are quoted on gRPC
+from client_b200.perf.native import GrpcStubServer, grpc_wire_prefixes
+gstub = GrpcStubServer(b"\x0a\x01m")
+for label, (ins, outs), shm, conc in (("C4 bert gRPC raw_input_contents from pinned staging", c4, "none", 256),
+                                      ("C5 llama prompt gRPC", c5, "none", 256),
+                                      ("C2 cuda-shm over gRPC", c2, "cuda", 256)):
+    ss = SlotSet(ins, outs, conc, shm, 0, "random", 1, {"input_ids": (0, 30522), "attention_mask": (0, 2)}, name_prefix="gcap%s%d" % (shm, conc),
+                 wire_prefixes=grpc_wire_prefixes(ins) if shm == "none" else None)
+    gen = NativeLoadGenerator(gstub.url, "m", "", ss, conc, regenerate=True, validate=(shm == "cuda"), protocol="grpc")
+    gen.start(); gen.window(0.5); w = gen.window(2.0); gen.stop(); ss.close()
+    print(json.dumps({"case": label, "concurrency": conc, "infer_per_s": round(w["throughput"]), "p50_us": w["p50_us"], "failed": w["failed"],
+                      "slots_per_pass": round(w["device_slots"] / max(1, w["device_batches"]), 1),
+                      "input_gbps": round(w["throughput"] * ss.in_bytes / 1e9, 2)}))
+gstub.stop()
 PY
 } >> gpurun_out/perf_native.txt 2>&1
 # ---- the same comparison with client and server sharing the GPU through CUDA MPS

@@ -112,3 +112,91 @@ def test_many_connections_per_thread_and_large_borrowed_tails():
         assert st.cumulative_send_time_ns > 0
     finally:
         srv.stop()
+
+
+# ---- gRPC over cleartext HTTP/2 (csrc/h2.h) -----------------------------------------------
+def _grpc_request(model, arrays, with_data=True):
+    import client_b200.grpc as grpcclient
+    from client_b200.grpc._utils import _get_inference_request
+
+    ins = []
+    for name, arr in arrays:
+        inp = grpcclient.InferInput(name, list(arr.shape), "INT32")
+        if with_data:
+            inp.set_data_from_numpy(arr)
+        ins.append(inp)
+    return _get_inference_request(model_name=model, inputs=ins, model_version="", request_id="", outputs=None, sequence_id=0,
+                                  sequence_start=False, sequence_end=False, priority=0, timeout=None, parameters=None).SerializeToString()
+
+
+def _run_grpc(host, port, reqs, tails=None, seconds=0.4):
+    lib = _native.load()
+    n = len(reqs)
+    bufs = [ctypes.create_string_buffer(r, len(r)) for r in reqs]
+    cfg = LoadgenConfig()
+    cfg.host, cfg.port, cfg.concurrency, cfg.protocol = host.encode(), port, n, 1
+    cfg.requests = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
+    cfg.request_sizes = (ctypes.c_uint64 * n)(*[len(r) for r in reqs])
+    keep = []
+    if tails:
+        keep = [ctypes.create_string_buffer(t, len(t)) for t in tails]
+        cfg.tails = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in keep])
+        cfg.tail_sizes = (ctypes.c_uint64 * n)(*[len(t) for t in tails])
+    h = ctypes.c_void_p()
+    _native.check(lib.tb200_loadgen_create(ctypes.byref(cfg), ctypes.byref(h)))
+    _native.check(lib.tb200_loadgen_start(h))
+    st = LoadgenStats()
+    _native.check(lib.tb200_loadgen_window(h, seconds, ctypes.byref(st)))
+    lib.tb200_loadgen_stop(h)
+    lib.tb200_loadgen_destroy(h)
+    return st
+
+
+def test_grpc_transport_against_grpcio_server():
+    """The native HTTP/2 client speaks to a real grpcio server (the mock server's gRPC port):
+    message = protobuf head + borrowed tail (raw_input_contents tag/length/tensor), errors
+    arrive as trailers-only responses, a 48 KB message spans several DATA frames."""
+    a = np.arange(16, dtype=np.int32)[None, :]
+    b = np.ones((1, 16), dtype=np.int32)
+    full = _grpc_request("simple", [("INPUT0", a), ("INPUT1", b)])
+    head = _grpc_request("simple", [("INPUT0", a), ("INPUT1", b)], with_data=False)
+    tail = b"\x3a\x40" + a.tobytes() + b"\x3a\x40" + b.tobytes()
+    assert head + tail == full  # raw_input_contents is the last field of ModelInferRequest
+    proc, _, grpc_port = start_server()
+    try:
+        st = _run_grpc("127.0.0.1", grpc_port, [head] * 3, [tail] * 3)
+        assert st.failed_request_count == 0 and st.completed_request_count > 20
+        assert 0 < st.min_ns <= st.p50_ns <= st.max_ns
+        st = _run_grpc("127.0.0.1", grpc_port, [_grpc_request("nope", [("INPUT0", a), ("INPUT1", b)])], seconds=0.2)
+        assert st.completed_request_count == 0 and st.failed_request_count > 0
+        big = np.arange(12000, dtype=np.int32)
+        st = _run_grpc("127.0.0.1", grpc_port, [_grpc_request("custom_identity_int32", [("INPUT0", big)])] * 2, seconds=0.3)
+        assert st.failed_request_count == 0 and st.completed_request_count > 5
+    finally:
+        proc.terminate()
+        proc.wait(10)
+
+
+def test_grpc_stub_server_with_grpcio_client_and_native_client():
+    """The canned-response gRPC stub (HTTP/2 server side) is accepted by a real grpcio client,
+    and the native client sustains a closed loop against it."""
+    import client_b200.grpc as grpcclient
+    from client_b200.grpc import service_pb2
+    from client_b200.perf.native import GrpcStubServer
+
+    resp = service_pb2.ModelInferResponse(model_name="stub", model_version="1")
+    out = resp.outputs.add()
+    out.name, out.datatype = "OUTPUT0", "INT32"
+    out.shape.extend([1, 4])
+    resp.raw_output_contents.append(np.arange(4, dtype=np.int32).tobytes())
+    stub = GrpcStubServer(resp.SerializeToString())
+    try:
+        with grpcclient.InferenceServerClient(stub.url) as client:
+            inp = grpcclient.InferInput("INPUT0", [1, 4], "INT32").set_data_from_numpy(np.ones((1, 4), np.int32))
+            for _ in range(20):
+                assert np.array_equal(client.infer("anything", [inp]).as_numpy("OUTPUT0"), np.arange(4, dtype=np.int32)[None, :])
+        a = np.arange(16, dtype=np.int32)[None, :]
+        st = _run_grpc(stub.host, stub.port, [_grpc_request("simple", [("INPUT0", a), ("INPUT1", a)])] * 8)
+        assert st.failed_request_count == 0 and st.completed_request_count > 1000
+    finally:
+        stub.stop()

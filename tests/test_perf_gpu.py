@@ -82,3 +82,66 @@ def test_generated_string_inputs_over_the_wire(server):
     rows = cli.main(["-m", "string_identity", "-u", server["grpc"], "-i", "grpc", "--shared-memory", "none",
                      "--concurrency-range", "2", "-p", "300", "-r", "3", "--json"])
     assert rows[0]["count"] > 3 and rows[0]["failed"] == 0 and rows[0]["input_bytes"] == 8 * 132
+
+
+def test_native_engine_grpc(server):
+    """--engine native -i grpc: unary ModelInfer over the load generator's own HTTP/2 transport.
+    Wire mode: the message is protobuf head + the slot's pinned staging image (raw_input_contents
+    tag, length, tensor bytes written by the fill kernel); the grpcio mock server parses and
+    executes it.  cuda shm: requests only name regions."""
+    rows = cli.main(["-m", "bert_large", "-u", server["grpc"], "-i", "grpc", "--shared-memory", "none", "--engine", "native",
+                     "--concurrency-range", "4", "-p", "300", "-r", "3", "--json"])
+    assert rows[0]["count"] > 3 and rows[0]["failed"] == 0 and rows[0]["input_bytes"] == 6144, rows
+    rows = cli.main(["-m", "densenet_onnx", "-u", server["grpc"], "-i", "grpc", "--shared-memory", "cuda", "--engine", "native",
+                     "--concurrency-range", "4", "-p", "300", "-r", "3", "--json"])
+    assert rows[0]["count"] > 3 and rows[0]["failed"] == 0 and rows[0]["nonfinite"] == 0, rows
+    rows = cli.main(["-m", "string_identity", "-u", server["grpc"], "-i", "grpc", "--shared-memory", "none", "--engine", "native",
+                     "--string-length", "24", "--concurrency-range", "2", "-p", "300", "-r", "3", "--json"])
+    assert rows[0]["count"] > 3 and rows[0]["failed"] == 0, rows
+
+
+def test_native_grpc_wire_bytes_reach_the_server():
+    """What a real grpcio server receives in raw_input_contents is bit-for-bit what the fill
+    kernel generates for that slot: the oracle recomputes it from the job's seed and stream."""
+    from concurrent import futures
+
+    import grpc
+
+    from client_b200.grpc import service_pb2, service_pb2_grpc
+    from client_b200.perf.loadgen import SlotSet, TensorSpec
+    from client_b200.perf.native import NativeLoadGenerator, grpc_wire_prefixes
+    from oracle import cref
+
+    seen = {}
+
+    class Capture(service_pb2_grpc.GRPCInferenceServiceServicer):
+        def ModelInfer(self, request, context):
+            seen[bytes(request.raw_input_contents[0][:16])] = request
+            return service_pb2.ModelInferResponse(model_name=request.model_name)
+
+    srv = grpc.server(futures.ThreadPoolExecutor(max_workers=4))
+    service_pb2_grpc.add_GRPCInferenceServiceServicer_to_server(Capture(), srv)
+    port = srv.add_insecure_port("127.0.0.1:0")
+    srv.start()
+    ins = [TensorSpec("input_ids", "INT64", [1, 384]), TensorSpec("attention_mask", "INT64", [1, 384])]
+    ranges = {"input_ids": (0, 30522), "attention_mask": (0, 2)}
+    try:
+        ss = SlotSet(ins, [TensorSpec("logits", "FP32", [1, 2])], 8, "none", 0, "random", 5, ranges,
+                     name_prefix="grpcwire", wire_prefixes=grpc_wire_prefixes(ins))
+        gen = NativeLoadGenerator("127.0.0.1:%d" % port, "bert_large", "", ss, 8, regenerate=False, validate=False, protocol="grpc")
+        gen.start()
+        w = gen.window(0.5)
+        gen.stop()
+        assert w["failed"] == 0 and w["count"] >= 8, w
+        expect = {}
+        for slot in range(8):
+            tensors = [cref.fill(t.nbytes, t.datatype, seed=ss.seed, stream=(slot << 8) | i, ilo=ranges[t.name][0],
+                                 irange=ranges[t.name][1] - ranges[t.name][0]).tobytes() for i, t in enumerate(ins)]
+            expect[tensors[0][:16]] = tensors
+        ss.close()
+        assert set(seen) == set(expect)
+        for key, request in seen.items():
+            assert request.model_name == "bert_large" and [i.name for i in request.inputs] == ["input_ids", "attention_mask"]
+            assert [bytes(b) for b in request.raw_input_contents] == expect[key]
+    finally:
+        srv.stop(0)
