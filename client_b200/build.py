@@ -69,11 +69,12 @@ CLIENT_LIB = os.path.join(LIBDIR, "libtb200client.so")
 def build_cpp_client(force=False, verbose=False):
     """The C++ front end (client_b200/cpp): plain g++, linked against libtb200.so."""
     cpp = os.path.join(HERE, "cpp")
-    src = os.path.join(cpp, "tb200_client.cc")
-    deps = [src, os.path.join(cpp, "tb200_client.h"), os.path.join(cpp, "json.h"), os.path.join(ROOT, "include", "tb200.h"), LIB]
+    srcs = [os.path.join(cpp, "tb200_client.cc"), os.path.join(cpp, "tb200_grpc_client.cc")]
+    deps = srcs + [os.path.join(cpp, h) for h in ("tb200_client.h", "tb200_grpc_client.h", "json.h", "pb.h", "grpc_service.pb.h")]
+    deps += [os.path.join(HERE, "csrc", "h2.h"), os.path.join(ROOT, "include", "tb200.h"), LIB]
     if force or _newer(CLIENT_LIB, deps):
         gxx = shutil.which("g++") or "g++"
-        cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", CLIENT_LIB, src,
+        cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", CLIENT_LIB] + srcs + [
                "-L" + LIBDIR, "-ltb200", "-Wl,-rpath,$ORIGIN", "-lpthread"]
         if verbose:
             print(" ".join(cmd))

@@ -15,7 +15,10 @@
 
 #include <cstdint>
 #include <cstring>
+#include <deque>
 #include <string>
+#include <utility>
+#include <vector>
 
 namespace tb200 { namespace h2 {
 
@@ -145,6 +148,116 @@ inline size_t parse_frame(const uint8_t* buf, size_t n, FrameView* f) {
 inline uint32_t get_u32(const uint8_t* p) {
   return (static_cast<uint32_t>(p[0]) << 24) | (static_cast<uint32_t>(p[1]) << 16) | (static_cast<uint32_t>(p[2]) << 8) | p[3];
 }
+
+// ---- HPACK decoding (the C++ gRPC front end reads grpc-status / grpc-message) -----------------
+// Static table + dynamic table + integer / string literals (RFC 7541 2.3, 5, 6).  Huffman-coded
+// strings (5.2, H bit) are not decoded: the field keeps its name when that is indexed, the value
+// becomes empty and `huffman_skipped` counts it -- gRPC servers send status fields raw.
+class HpackDecoder {
+ public:
+  using Field = std::pair<std::string, std::string>;
+  size_t huffman_skipped = 0;
+
+  bool Decode(const uint8_t* p, size_t n, std::vector<Field>* out) {
+    const uint8_t* end = p + n;
+    while (p < end) {
+      const uint8_t b = *p;
+      if (b & 0x80) {  // indexed field
+        uint64_t index;
+        if (!Int(&p, end, 7, &index) || index == 0) return false;
+        Field f;
+        if (!Lookup(index, &f)) return false;
+        out->push_back(std::move(f));
+      } else if ((b & 0xE0) == 0x20) {  // dynamic table size update
+        uint64_t size;
+        if (!Int(&p, end, 5, &size)) return false;
+        max_size_ = size;
+        Evict();
+      } else {
+        const bool add = (b & 0xC0) == 0x40;  // literal with incremental indexing
+        uint64_t index;
+        if (!Int(&p, end, add ? 6 : 4, &index)) return false;
+        Field f;
+        if (index != 0) {
+          Field named;
+          if (!Lookup(index, &named)) return false;
+          f.first = named.first;
+        } else if (!Str(&p, end, &f.first)) {
+          return false;
+        }
+        if (!Str(&p, end, &f.second)) return false;
+        if (add) {
+          size_ += f.first.size() + f.second.size() + 32;
+          table_.push_front(f);
+          Evict();
+        }
+        out->push_back(std::move(f));
+      }
+    }
+    return true;
+  }
+
+ private:
+  static bool Int(const uint8_t** p, const uint8_t* end, int prefix_bits, uint64_t* v) {
+    if (*p >= end) return false;
+    const uint64_t limit = (1u << prefix_bits) - 1;
+    *v = *(*p)++ & limit;
+    if (*v < limit) return true;
+    for (int shift = 0; shift < 56; shift += 7) {
+      if (*p >= end) return false;
+      const uint8_t b = *(*p)++;
+      *v += static_cast<uint64_t>(b & 0x7F) << shift;
+      if (!(b & 0x80)) return true;
+    }
+    return false;
+  }
+  bool Str(const uint8_t** p, const uint8_t* end, std::string* s) {
+    if (*p >= end) return false;
+    const bool huffman = (**p & 0x80) != 0;
+    uint64_t len;
+    if (!Int(p, end, 7, &len) || len > static_cast<uint64_t>(end - *p)) return false;
+    if (huffman) {
+      ++huffman_skipped;
+      s->clear();
+    } else {
+      s->assign(reinterpret_cast<const char*>(*p), len);
+    }
+    *p += len;
+    return true;
+  }
+  bool Lookup(uint64_t index, Field* f) const {
+    static const char* const kStatic[61][2] = {
+        {":authority", ""}, {":method", "GET"}, {":method", "POST"}, {":path", "/"}, {":path", "/index.html"},
+        {":scheme", "http"}, {":scheme", "https"}, {":status", "200"}, {":status", "204"}, {":status", "206"},
+        {":status", "304"}, {":status", "400"}, {":status", "404"}, {":status", "500"}, {"accept-charset", ""},
+        {"accept-encoding", "gzip, deflate"}, {"accept-language", ""}, {"accept-ranges", ""}, {"accept", ""},
+        {"access-control-allow-origin", ""}, {"age", ""}, {"allow", ""}, {"authorization", ""}, {"cache-control", ""},
+        {"content-disposition", ""}, {"content-encoding", ""}, {"content-language", ""}, {"content-length", ""},
+        {"content-location", ""}, {"content-range", ""}, {"content-type", ""}, {"cookie", ""}, {"date", ""}, {"etag", ""},
+        {"expect", ""}, {"expires", ""}, {"from", ""}, {"host", ""}, {"if-match", ""}, {"if-modified-since", ""},
+        {"if-none-match", ""}, {"if-range", ""}, {"if-unmodified-since", ""}, {"last-modified", ""}, {"link", ""},
+        {"location", ""}, {"max-forwards", ""}, {"proxy-authenticate", ""}, {"proxy-authorization", ""}, {"range", ""},
+        {"referer", ""}, {"refresh", ""}, {"retry-after", ""}, {"server", ""}, {"set-cookie", ""},
+        {"strict-transport-security", ""}, {"transfer-encoding", ""}, {"user-agent", ""}, {"vary", ""}, {"via", ""},
+        {"www-authenticate", ""}};
+    if (index <= 61) {
+      f->first = kStatic[index - 1][0];
+      f->second = kStatic[index - 1][1];
+      return true;
+    }
+    if (index - 62 >= table_.size()) return false;
+    *f = table_[index - 62];
+    return true;
+  }
+  void Evict() {
+    while (size_ > max_size_ && !table_.empty()) {
+      size_ -= table_.back().first.size() + table_.back().second.size() + 32;
+      table_.pop_back();
+    }
+  }
+  std::deque<Field> table_;
+  size_t size_ = 0, max_size_ = 4096;
+};
 
 }}  // namespace tb200::h2
 

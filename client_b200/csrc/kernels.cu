@@ -42,6 +42,29 @@ __device__ __forceinline__ void store_bytes(uint8_t* p, const U32x4& v, uint32_t
   }
 }
 
+// bytes [from, to) of v
+__device__ __forceinline__ void store_byte_range(uint8_t* p, const U32x4& v, uint32_t from, uint32_t to) {
+  for (uint32_t i = from; i < to; ++i) {
+    p[i] = static_cast<uint8_t>(word_of(v, i >> 2) >> (8 * (i & 3)));
+  }
+}
+// the 16 bytes at byte offset `off` (1..15) of the 32-byte concatenation a | b
+__device__ __forceinline__ U32x4 funnel16(const U32x4& a, const U32x4& b, uint32_t off) {
+  const uint32_t q = off >> 2, r = (off & 3) * 8;
+  uint32_t w[5];
+#pragma unroll
+  for (uint32_t k = 0; k < 5; ++k) {
+    const uint32_t i = q + k;  // <= 7
+    w[k] = i < 4 ? word_of(a, i) : word_of(b, i - 4);
+  }
+  U32x4 o;
+  o.x = __funnelshift_r(w[0], w[1], r);
+  o.y = __funnelshift_r(w[1], w[2], r);
+  o.z = __funnelshift_r(w[2], w[3], r);
+  o.w = __funnelshift_r(w[3], w[4], r);
+  return o;
+}
+
 // largest j in [0, n) with prefix[j] <= tile (prefix has n+1 entries, prefix[n] > tile)
 __device__ __forceinline__ uint32_t find_job(const uint32_t* __restrict__ prefix, uint32_t n,
                                              uint32_t tile) {
@@ -103,6 +126,60 @@ __device__ __forceinline__ void fill_segment_random(uint8_t* __restrict__ dst, u
   }
 }
 
+// Destinations that are not 16-byte aligned (tensors behind a protobuf tag + length inside a
+// gRPC message image, odd offsets in a region): the thread of group g writes the ALIGNED
+// 16-byte cell that holds the end of group g-1 and the start of group g with one store,
+// generating both groups (Philox is counter based; twice the arithmetic, but full-width
+// stores instead of 16 single bytes -- these tensors are small and often sit in pinned host
+// memory, where a byte store is a PCIe transaction).  Cells that reach outside the tensor
+// (first, last, spill-over of the last group) are written byte-wise.  Lives in its own
+// kernel (fill_unaligned_kernel, launched only when a launch has such jobs), dtype
+// dispatched at run time: the aligned kernel's register budget is not touched.
+template <int THREADS, int ROUNDS>
+__device__ __forceinline__ void fill_segment_unaligned(const tb200_fill_job& jb, uint64_t g0, uint32_t count, uint64_t stream,
+                                                    const RoundKeys& rk) {
+  uint8_t* dst = reinterpret_cast<uint8_t*>(jb.dst);
+  const uint64_t nbytes = jb.nbytes;
+  const uint32_t k = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15);  // 1..15
+  const uint64_t last_group = (nbytes + 15) / 16 - 1;
+  FillParams p;
+  p.lo_f = static_cast<float>(jb.lo);
+  p.span_f = static_cast<float>(jb.span);
+  p.lo_d = jb.lo;
+  p.span_d = jb.span;
+  p.ilo = jb.ilo;
+  p.irange = jb.irange;
+  p.unit = (jb.span == 0.0) ? 1u : 0u;
+  const uint32_t s_lo = static_cast<uint32_t>(stream), s_hi = static_cast<uint32_t>(stream >> 32);
+  const uint32_t const_word = jb.mode == TB200_FILL_BYTE ? (static_cast<uint32_t>(jb.ilo) & 0xFFu) * 0x01010101u : 0u;
+  auto group = [&](uint64_t g) -> U32x4 {
+    if (jb.mode != TB200_FILL_RANDOM) return U32x4{const_word, const_word, const_word, const_word};
+    const U32x4 r = philox4x32_10_rk<ROUNDS>(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), s_lo, s_hi, rk);
+    if (jb.dtype == kBytes) return fill_group_bytes(r, g, static_cast<uint32_t>(jb.irange));
+    return fill_group(jb.dtype, r, p);
+  };
+  for (uint32_t i = threadIdx.x; i < count; i += THREADS) {
+    const uint64_t g = g0 + i;
+    uint8_t* at = dst + g * 16;  // group g starts here; its cell starts k bytes earlier
+    const U32x4 cur = group(g);
+    const uint64_t left = nbytes - g * 16;  // bytes of this group and everything after it
+    if (g != 0) {
+      const U32x4 prev = group(g - 1);
+      if (left >= 16 - k) {
+        st_cs_v4(at - k, funnel16(prev, cur, 16 - k));
+      } else {
+        store_byte_range(at - 16, prev, 16 - k, 16);
+        store_byte_range(at, cur, 0, static_cast<uint32_t>(left));
+      }
+    } else {
+      store_byte_range(at, cur, 0, left < 16 - k ? static_cast<uint32_t>(left) : 16 - k);
+    }
+    if (g == last_group && left > 16 - k) {  // what of the last group lies in the next cell
+      store_byte_range(at, cur, 16 - k, left < 16 ? static_cast<uint32_t>(left) : 16u);
+    }
+  }
+}
+
 template <int THREADS>
 __device__ __forceinline__ void fill_segment_const(uint8_t* __restrict__ dst, uint64_t nbytes,
                                                    uint64_t g0, uint32_t count, uint32_t full,
@@ -149,6 +226,10 @@ __global__ void __launch_bounds__(THREADS, MINB) fill_kernel(const FillLaunch L)
     if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
       const uint64_t whole = jb.nbytes / 16;
       if (whole > g0) full = (whole - g0) < count ? static_cast<uint32_t>(whole - g0) : count;
+    } else {  // fill_unaligned_kernel's job
+      lo = seg_hi;
+      ++j;
+      continue;
     }
     if (jb.mode != TB200_FILL_RANDOM) {
       uint32_t word = 0;
@@ -192,6 +273,36 @@ __global__ void __launch_bounds__(THREADS, MINB) fill_kernel(const FillLaunch L)
     __threadfence();
     const unsigned int prev = atomicInc(L.done_counter, gridDim.x - 1);
     if (prev == gridDim.x - 1) *L.dev_epoch += L.bump;
+  }
+}
+
+// The jobs fill_kernel leaves out: destinations that are not 16-byte aligned.  Same split of
+// the launch's groups over the CTAs.  Runs BEFORE fill_kernel on the stream (it reads the
+// device epoch that fill_kernel's last CTA advances).
+template <int THREADS, int ROUNDS>
+__global__ void __launch_bounds__(THREADS) fill_unaligned_kernel(const FillLaunch L) {
+  uint64_t epoch = L.epoch;
+  if (L.dev_epoch != nullptr) epoch += *L.dev_epoch;
+  uint64_t lo = (L.total_groups * blockIdx.x) / gridDim.x;
+  const uint64_t hi = (L.total_groups * (blockIdx.x + 1ull)) / gridDim.x;
+  uint32_t j = 0;
+  if (lo < hi) {
+    j = L.uniform_groups != 0 ? static_cast<uint32_t>(lo / L.uniform_groups) : find_job64(L.group_prefix, L.njobs, lo);
+  }
+  while (lo < hi) {
+    const uint64_t job_begin = L.uniform_groups != 0 ? L.uniform_groups * j : __ldg(L.group_prefix + j);
+    const uint64_t job_end = L.uniform_groups != 0 ? job_begin + L.uniform_groups : __ldg(L.group_prefix + j + 1);
+    if (job_end <= lo) {
+      ++j;
+      continue;
+    }
+    const uint64_t seg_hi = hi < job_end ? hi : job_end;
+    const tb200_fill_job jb = L.jobs[j];
+    if ((jb.dst & 15) != 0) {
+      fill_segment_unaligned<THREADS, ROUNDS>(jb, lo - job_begin, static_cast<uint32_t>(seg_hi - lo), jb.stream + epoch, L.rk);
+    }
+    lo = seg_hi;
+    ++j;
   }
 }
 
@@ -298,6 +409,15 @@ static cudaError_t launch_fill_t(const FillLaunch& l, int sm_count, cudaStream_t
 
 cudaError_t launch_fill(const FillLaunch& l, int sm_count, cudaStream_t s) {
   if (l.total_groups == 0 && l.bump == 0) return cudaSuccess;
+  if (l.unaligned_jobs != 0) {
+    uint64_t grid = static_cast<uint64_t>(sm_count) * 4;
+    const uint64_t max_useful = (l.total_groups + 255) / 256;
+    if (grid > max_useful) grid = max_useful;
+    fill_unaligned_kernel<256, 10><<<static_cast<uint32_t>(grid), 256, 0, s>>>(l);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (l.unaligned_jobs == l.njobs && l.bump == 0) return cudaSuccess;  // nothing left for the aligned kernel
+  }
   const int v = g_fill_variant;
   // Default policy (scripts/fill_sweep.py, profiles/): the kernel is issue-bound at 10
   // Philox rounds, so the cheapest indexing wins: many small equal tensors (wire-mode

@@ -26,6 +26,7 @@ struct FillLaunch {
   uint32_t dtype0;               // dtype of job 0 (the dtype of a homogeneous launch)
   uint32_t homogeneous;          // 1: uniform sizes, one dtype/range, random mode, every tensor a
                                  //    16-byte-aligned multiple of 16 bytes -> grid-stride kernel
+  uint32_t unaligned_jobs;       // jobs whose dst is not 16-byte aligned (fill_unaligned_kernel's share)
   RoundKeys rk;                  // Philox key schedule of `seed`
 };
 cudaError_t launch_fill(const FillLaunch& l, int sm_count, cudaStream_t s);

@@ -738,8 +738,10 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
     bool uniform = true;
     bool homogeneous = true;
     uint64_t total = 0;
+    uint32_t unaligned = 0;
     for (int i = 0; i < n; ++i) {
       const tb200_fill_job& jb = jobs[base + i];
+      if ((jb.dst & 15) != 0 && jb.nbytes != 0) ++unaligned;
       const bool strings = jb.dtype == TB200_BYTES;
       const uint32_t es = strings ? 1u : tb200_dtype_size(jb.dtype);
       if (es == 0) return fail(TB200_ERR_INVALID, "job %d: dtype %u cannot be filled", base + i, jb.dtype);
@@ -796,6 +798,7 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
     L.total_groups = total;
     L.uniform_groups = (uniform && total != 0) ? prefix[1] : 0;
     L.homogeneous = (homogeneous && L.uniform_groups != 0) ? 1u : 0u;
+    L.unaligned_jobs = unaligned;
     L.div_magic = 0;
     L.dtype0 = jobs[base].dtype;
     // exact g / d by multiply-high needs g * d < 2^64

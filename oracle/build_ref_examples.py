@@ -3,10 +3,9 @@
 headers + libtb200client.so).  Outputs go to oracle/_ref/cc_examples/ (git-ignored; they travel
 to the GPU box with the snapshot).  Test infrastructure: the binaries end with the examples' own
 value checks ("PASS : ..."), so running them against the stand-in servers shows that code
-written for the reference C++ HTTP client builds and behaves the same on the front end.
+written for the reference C++ HTTP / gRPC clients builds and behaves the same on the front end.
 
-Not built: examples that need grpc_client.h (gRPC front end: out of scope), json_utils.h
-(RapidJSON, absent) or OpenCV (image clients).
+Not built: examples that need json_utils.h (RapidJSON, absent) or OpenCV (image clients).
 """
 
 import os
@@ -22,7 +21,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 EXAMPLES = ["simple_http_infer_client", "simple_http_async_infer_client", "simple_http_string_infer_client",
             "simple_http_shm_client", "simple_http_sequence_sync_infer_client"]
-CUDA_EXAMPLES = ["simple_http_cudashm_client"]  # cudaMalloc + cudaIpcGetMemHandle by hand, needs cudart
+GRPC_EXAMPLES = ["simple_grpc_infer_client", "simple_grpc_async_infer_client", "simple_grpc_string_infer_client",
+                 "simple_grpc_shm_client", "simple_grpc_health_metadata", "simple_grpc_sequence_sync_infer_client",
+                 "simple_grpc_sequence_stream_infer_client", "simple_grpc_keepalive_client", "simple_grpc_custom_args_client",
+                 "simple_grpc_custom_repeat", "simple_grpc_model_control"]
+CUDA_EXAMPLES = ["simple_http_cudashm_client", "simple_grpc_cudashm_client"]  # cudaMalloc + cudaIpcGetMemHandle by hand, needs cudart
 
 
 def build_ref_examples(force=False):
@@ -37,10 +40,10 @@ def build_ref_examples(force=False):
     cpp = os.path.join(ROOT, "client_b200", "cpp")
     libdir = os.path.join(ROOT, "client_b200", "lib")
     built = {}
-    for name in EXAMPLES + CUDA_EXAMPLES:
+    for name in EXAMPLES + GRPC_EXAMPLES + CUDA_EXAMPLES:
         src = os.path.join(REF, name + ".cc")
         exe = os.path.join(OUT, name)
-        deps = [src, os.path.join(libdir, "libtb200client.so"), os.path.join(cpp, "tb200_client.h")]
+        deps = [src, os.path.join(libdir, "libtb200client.so"), os.path.join(cpp, "tb200_client.h"), os.path.join(cpp, "tb200_grpc_client.h")]
         if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
             cmd = ["g++", "-O1", "-std=c++17", "-I" + os.path.join(cpp, "compat"), "-I" + cpp, src, "-o", exe,
                    "-L" + libdir, "-ltb200client", "-ltb200", "-Wl,-rpath,$ORIGIN/../../../client_b200/lib", "-lpthread", "-lrt"]

@@ -87,6 +87,41 @@ def test_fill_unaligned_destination(gpu_ops):
         assert np.array_equal(got, cref.fill(5000, "UINT8", seed=9, stream=1))
 
 
+def test_fill_unaligned_cells_every_offset_and_tail(gpu_ops):
+    """fill_unaligned_kernel: every misalignment 1..15 x tensor sizes around the cell
+    boundaries (shorter than the first cell, ending inside / exactly at / just after a cell),
+    guard bytes on both sides; plus mixed aligned + unaligned jobs in one launch."""
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    for off in range(1, 16):
+        for nbytes in (1, 2, 15 - off + 1, 16 - off, 17 - off, 16, 17, 31, 32, 33, 48 - off, 1000, 4096 + off):
+            if nbytes <= 0:
+                continue
+            got = _fill_device(gpu_ops, nbytes, "UINT8", seed=3, stream=off * 131 + nbytes, offset=off)
+            assert np.array_equal(got, cref.fill(nbytes, "UINT8", seed=3, stream=off * 131 + nbytes)), (off, nbytes)
+    for dt, kw, okw in (("INT64", dict(low=0, high=30522), dict(ilo=0, irange=30522)), ("FP32", {}, {}), ("FP16", dict(low=-1.0, high=1.0), dict(lo=-1.0, span=2.0)),
+                        ("INT32", dict(low=0, high=128256), dict(ilo=0, irange=128256)), ("BOOL", {}, {})):
+        for off in (3, 5, 10, 13):
+            got = _fill_device(gpu_ops, 3072, dt, seed=11, stream=7, offset=off, **kw)
+            assert np.array_equal(got, cref.fill(3072, dt, seed=11, stream=7, **okw)), (dt, off)
+    got = _fill_device(gpu_ops, 8 * 28, "BYTES", seed=5, stream=2, offset=7, string_length=24)
+    assert np.array_equal(got, cref.fill(8 * 28, "BYTES", seed=5, stream=2, irange=24))
+    # one launch: aligned job, unaligned jobs (random / zero / byte), sizes that split across CTAs
+    size = 300000
+    buf = DeviceBuffer(0, 4 * size + 256)
+    gpu_ops.h2d(buf.ptr, np.full(4 * size + 256, 0xA5, np.uint8).ctypes.data, 4 * size + 256)
+    jobs = [make_fill_job(buf.ptr, size - 16, "FP32", 1), make_fill_job(buf.ptr + size + 3, size - 16, "INT64", 2, low=-5, high=1 << 40),
+            make_fill_job(buf.ptr + 2 * size + 9, size - 16, "FP32", 3, mode="zero"), make_fill_job(buf.ptr + 3 * size + 14, size - 16, "FP32", 4, mode="byte", low=0x3C)]
+    gpu_ops.fill(jobs, seed=21)
+    out = gpu_ops.download(buf.ptr, 4 * size + 256)
+    n = size - 16
+    assert np.array_equal(out[:n], cref.fill(n, "FP32", seed=21, stream=1))
+    assert np.array_equal(out[size + 3:size + 3 + n], cref.fill(n, "INT64", seed=21, stream=2, ilo=-5, irange=(1 << 40) + 5))
+    assert (out[2 * size + 9:2 * size + 9 + n] == 0).all() and (out[3 * size + 14:3 * size + 14 + n] == 0x3C).all()
+    for a, b in ((n, size + 3), (size + 3 + n, 2 * size + 9), (2 * size + 9 + n, 3 * size + 14), (3 * size + 14 + n, 4 * size + 256)):
+        assert (out[a:b] == 0xA5).all(), "fill wrote between its tensors"
+
+
 def test_fill_zero_and_byte(gpu_ops):
     from client_b200.device import DeviceBuffer, make_fill_job
 

@@ -94,6 +94,17 @@ CC_EXAMPLES = {
     "simple_http_string_infer_client": "PASS : String Infer",
     "simple_http_shm_client": "PASS : System Shared Memory",
     "simple_http_sequence_sync_infer_client": "[7] 1 : -1 : -1",
+    # gRPC front end (client_b200/cpp/tb200_grpc_client.h: own HTTP/2 framing + message classes)
+    "simple_grpc_infer_client": "PASS : Infer",
+    "simple_grpc_async_infer_client": "PASS : Async Infer",
+    "simple_grpc_string_infer_client": "PASS : String Infer",
+    "simple_grpc_shm_client": "PASS : System Shared Memory",
+    "simple_grpc_health_metadata": "Request for unknown model: 'wrong_model_name' is not found",
+    "simple_grpc_sequence_sync_infer_client": "[7] 1 : -1 : -1",
+    "simple_grpc_sequence_stream_infer_client": "[7] 1 : -1 : -1",
+    "simple_grpc_keepalive_client": "PASS : KeepAlive",
+    "simple_grpc_custom_args_client": "PASS : CustomArgs",
+    "simple_grpc_custom_repeat": "",
 }
 
 
@@ -104,18 +115,23 @@ def cc_binaries():
     return build_ref_examples()
 
 
+@pytest.fixture(scope="module")
+def cc_server():
+    proc, http_port, grpc_port = start_server()
+    yield {"http": "127.0.0.1:%d" % http_port, "grpc": "127.0.0.1:%d" % grpc_port}
+    proc.terminate()
+    proc.wait(10)
+
+
 @pytest.mark.parametrize("name", sorted(CC_EXAMPLES))
-def test_unmodified_reference_cc_example(cc_binaries, name):
-    """src/c++/examples/<name>.cc compiled as is against compat/http_client.h + libtb200client.so
-    (oracle/build_ref_examples.py) and run against the mock server's `simple*` models."""
+def test_unmodified_reference_cc_example(cc_binaries, cc_server, name):
+    """src/c++/examples/<name>.cc compiled as is against compat/{http,grpc}_client.h +
+    libtb200client.so (oracle/build_ref_examples.py) and run against the mock server's models;
+    the programs end with their own value checks."""
     assert name in cc_binaries
-    proc, http_port, _ = start_server()
-    try:
-        r = subprocess.run([cc_binaries[name], "-u", "127.0.0.1:%d" % http_port], capture_output=True, text=True, timeout=60)
-        assert r.returncode == 0 and CC_EXAMPLES[name] in r.stdout, r.stdout[-800:] + r.stderr[-400:]
-    finally:
-        proc.terminate()
-        proc.wait(10)
+    url = cc_server["grpc" if "_grpc_" in name else "http"]
+    r = subprocess.run([cc_binaries[name], "-u", url], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and CC_EXAMPLES[name] in r.stdout + r.stderr, r.stdout[-800:] + r.stderr[-400:]
 
 
 def test_reference_unit_tests_for_system_shared_memory_unmodified():
