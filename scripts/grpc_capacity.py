@@ -1,8 +1,10 @@
 """Generator capacity over the gRPC transport against the canned-response gRPC stub (no model,
 no second CUDA context): the C4 / C5 wire shapes and C2 over CUDA shared memory."""
 import json
+import os
 import sys
 
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from client_b200.perf.loadgen import SlotSet, TensorSpec
 from client_b200.perf.native import GrpcStubServer, NativeLoadGenerator, grpc_wire_prefixes
 
