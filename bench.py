@@ -218,19 +218,44 @@ def run_b200(args):
         ops.check(check_jobs[i % SETS], results.device_ptr + (i % SETS) * SLOTS * 32)
     ops.sync()
     rep.barrier()
+    # (a) one step per call, waited for before the next one is formed
     t0 = time.perf_counter()
     timer.start()
     bad = 0
-    for i in range(e2e_steps):
+    sync_steps = max(10, e2e_steps // 4)
+    for i in range(sync_steps):
         s = i % SETS
         ops.step(fill_jobs[s], check_jobs[s], results.device_ptr + s * SLOTS * 32, seed=SEED, epoch=i * SLOTS)
         bad += int(res["mismatches"][s * SLOTS:(s + 1) * SLOTS].sum())
+    timer.stop()
+    ops.sync()
+    sync_ms = rep.max(max(timer.elapsed_ms(), (time.perf_counter() - t0) * 1e3))
+    e2e_sync_value = world * SLOTS * sync_steps / (sync_ms / 1e3)
+    # (b) the same steps pipelined (step_submit / step_wait, E2E_DEPTH in flight): the host copies
+    #     the job tables of step i+1 while the device runs step i; every step's results are still
+    #     read by the host inside the timed region, after its own wait
+    E2E_DEPTH = 2
+    rep.barrier()
+    t0 = time.perf_counter()
+    timer.start()
+    inflight = []
+    for i in range(e2e_steps):
+        s = i % SETS
+        inflight.append((ops.step_submit(fill_jobs[s], check_jobs[s], results.device_ptr + s * SLOTS * 32, seed=SEED, epoch=i * SLOTS), s))
+        if len(inflight) > E2E_DEPTH:
+            ticket, s0 = inflight.pop(0)
+            ops.step_wait(ticket)
+            bad += int(res["mismatches"][s0 * SLOTS:(s0 + 1) * SLOTS].sum())
+    for ticket, s0 in inflight:
+        ops.step_wait(ticket)
+        bad += int(res["mismatches"][s0 * SLOTS:(s0 + 1) * SLOTS].sum())
     timer.stop()
     ops.sync()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     rep.barrier()
     e2e_ms = rep.max(max(timer.elapsed_ms(), e2e_wall_ms))
     assert bad == 0
+    assert SETS > E2E_DEPTH  # steps in flight use different slot sets and result entries
     e2e_value = world * SLOTS * e2e_steps / (e2e_ms / 1e3)
     h2d_step = SLOTS * 64 + (SLOTS + 1) * 4 + SLOTS * 48
     d2h_step = SLOTS * 32
@@ -365,7 +390,8 @@ def run_b200(args):
         "input_pack_gbps": round(world * SLOTS * IN_BYTES * steps / (ms_value / 1e3) / 1e9, 1),
         "e2e": {"value": round(e2e_value, 1), "unit": "infer/s", "h2d_bytes_per_step": h2d_step,
                 "d2h_bytes_per_step": d2h_step, "steps": e2e_steps,
-                "what": "client_b200.device.DeviceOps.step() per step: job tables H2D from pinned memory, fill || validate, results D2H into mapped host memory, sync, host reads the 64 results"},
+                "what": "client_b200.device.DeviceOps.step_submit()/step_wait() per step, 2 steps in flight: job tables H2D from pinned memory, fill || validate, results D2H into mapped host memory, host waits for the step and reads its 64 results",
+                "sync_per_step": {"value": round(e2e_sync_value, 1), "steps": sync_steps, "what": "DeviceOps.step(): the same, each step waited for before the next is formed"}},
         "e2e_host_images": {"value": round(img_value, 1), "unit": "infer/s", "h2d_bytes_per_step": SLOTS * 224 * 224 * 3,
                             "d2h_bytes_per_step": d2h_step, "steps": img_steps,
                             "what": "64 uint8 HWC host images (pinned) -> H2D -> INCEPTION cast + CHW pack into the IPC slots -> validate"},
@@ -396,6 +422,11 @@ def run_b200(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_port()
+    if rank == 0 and world == 1:
+        try:
+            line["wire_c4_c5"] = wire_extra(ops, ctx, local)
+        except Exception as ex:
+            line["wire_c4_c5"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     if rank == 0 and world == 1 and not args.no_loopback:
         try:
             line["loopback"] = loopback_extra(local)
@@ -404,6 +435,59 @@ def run_b200(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     rep.close()
+
+
+def wire_extra(ops, ctx, device, seconds=1.0):
+    """BASELINE configs[3] / [4] (C4 BERT-large seq384, C5 Llama prompt; quoted on gRPC, no shared
+    memory): the tensors go over the wire, so the fill kernel writes them into pinned, device-mapped
+    staging laid out as the tail of the ModelInferRequest (raw_input_contents tag + length + tensor
+    per input).  (1) the fill launch for 256 slots, timed with CUDA events (its stores cross PCIe /
+    C2C to host memory, so the HBM roofline does not apply: GB/s reported as is); (2) the native load
+    generator over its gRPC transport against the canned-response gRPC stub, inputs regenerated for
+    every request."""
+    from client_b200 import _native
+    from client_b200.perf.loadgen import SlotSet, TensorSpec
+    from client_b200.perf.native import GrpcStubServer, NativeLoadGenerator, grpc_wire_prefixes
+
+    cases = {
+        "c4_bert_large_seq384": ([TensorSpec("input_ids", "INT64", [1, 384]), TensorSpec("attention_mask", "INT64", [1, 384])],
+                                 [TensorSpec("logits", "FP32", [1, 2])], {"input_ids": (0, 30522), "attention_mask": (0, 2)}),
+        "c5_llama3_prompt4096": ([TensorSpec("input_ids", "INT32", [1, 4096])], [TensorSpec("logits", "FP32", [1, 16])],
+                                 {"input_ids": (0, 128256)}),
+    }
+    out = {"transport": "unary gRPC over the generator's own HTTP/2 framing (csrc/h2.h), canned-response gRPC stub (no model)", "concurrency": 256}
+    stub = GrpcStubServer(b"\x0a\x01m")
+    timer = _native.Timer(ctx)
+    try:
+        for key, (ins, outs, ranges) in cases.items():
+            ss = SlotSet(ins, outs, 256, "none", device, "random", SEED, ranges, name_prefix="bench_" + key, wire_prefixes=grpc_wire_prefixes(ins))
+            jobs = ss._fill_jobs(list(range(256)))
+            arr = (_native.FillJob * len(jobs))(*jobs)
+            for _ in range(3):
+                ops.fill(arr, seed=SEED)
+            ops.sync()
+            timer.start()
+            for i in range(50):
+                ops.fill(arr, seed=SEED, epoch=i)
+            timer.stop()
+            ops.sync()
+            fill_us = timer.elapsed_ms() / 50 * 1e3
+            gen = NativeLoadGenerator(stub.url, "m", "", ss, 256, regenerate=True, validate=False, protocol="grpc")
+            gen.start()
+            try:
+                gen.window(0.3)
+                w = gen.window(seconds)
+            finally:
+                gen.stop()
+            out[key] = {"request_input_bytes": ss.in_bytes, "fill_256_slots_us": round(fill_us, 2),
+                        "fill_pinned_gbps": round(256 * ss.in_bytes / (fill_us / 1e6) / 1e9, 2),
+                        "fill_requests_per_s": round(256 / (fill_us / 1e6)),
+                        "generator_infer_per_s": round(w["throughput"]), "p50_us": round(w["p50_us"], 1), "failed": w["failed"],
+                        "slots_per_pass": round(w["device_slots"] / max(1, w["device_batches"]), 1)}
+            ss.close()
+    finally:
+        stub.stop()
+    return out
 
 
 def loopback_extra(device, seconds=1.5):

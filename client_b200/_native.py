@@ -155,6 +155,8 @@ SIGNATURES = {
     "tb200_l2_flush_async": (c_int, [c_vp]),
     "tb200_tune": (c_int, [ctypes.c_char_p, c_int]),
     "tb200_step_sync": (c_int, [c_vp, ctypes.POINTER(FillJob), c_int, c_u64, c_u64, ctypes.POINTER(CheckJob), c_int, c_vp]),
+    "tb200_step_submit": (c_int, [c_vp, ctypes.POINTER(FillJob), c_int, c_u64, c_u64, ctypes.POINTER(CheckJob), c_int, c_vp, ctypes.POINTER(c_u64)]),
+    "tb200_step_wait": (c_int, [c_vp, c_u64]),
 }
 
 _lib = None

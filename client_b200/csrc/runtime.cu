@@ -172,6 +172,12 @@ struct tb200_ctx {
   cudaStream_t cur = nullptr;      // stream launches go to (main, or side between fork/join)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // pipelined steps (tb200_step_submit / tb200_step_wait): per ring entry the event after the
+  // fill (main stream) and after the validation (side stream)
+  cudaEvent_t step_ev[TB200_STEP_DEPTH][2] = {};
+  uint64_t step_ticket[TB200_STEP_DEPTH] = {};  // ticket occupying the entry, 0 = free
+  bool step_has_side[TB200_STEP_DEPTH] = {};
+  uint64_t step_next = 1;
   bool own_stream = true;
   bool forked = false;
   uint64_t launches = 0;
@@ -186,6 +192,10 @@ struct tb200_ctx {
   // job_epoch[slot] < sync_epoch; otherwise the stream it went to is synchronised first
   uint64_t sync_epoch = 1;
   uint64_t job_epoch[kJobSlots];
+  // ... or when a pipelined step submitted after it has been waited for (tb200_step_wait)
+  uint64_t upload_seq = 0, uploads_done = 0;
+  uint64_t job_seq[kJobSlots] = {};
+  uint64_t step_upload_mark[TB200_STEP_DEPTH] = {};
   cudaStream_t job_stream[kJobSlots];
   int job_next = 0;
   // check scratch
@@ -269,7 +279,7 @@ int upload(tb200_ctx* ctx, const void* host, size_t bytes, const void** dev_out)
   if (rc != TB200_OK) return rc;
   const int slot = ctx->job_next;
   ctx->job_next = (slot + 1) % kJobSlots;
-  if (ctx->job_epoch[slot] == ctx->sync_epoch) {
+  if (ctx->job_epoch[slot] == ctx->sync_epoch && ctx->job_seq[slot] > ctx->uploads_done) {
     // 32 uploads without a synchronisation in between: wait for the slot's previous copy
     TB200_CUDA(cudaStreamSynchronize(ctx->job_stream[slot]));
   }
@@ -278,6 +288,7 @@ int upload(tb200_ctx* ctx, const void* host, size_t bytes, const void** dev_out)
   memcpy(h, host, bytes);
   TB200_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->cur));
   ctx->job_epoch[slot] = ctx->sync_epoch;
+  ctx->job_seq[slot] = ++ctx->upload_seq;
   ctx->job_stream[slot] = ctx->cur;
   *dev_out = d;
   return TB200_OK;
@@ -411,6 +422,11 @@ int tb200_ctx_destroy(tb200_ctx* ctx) {
   if (ctx->deflate_scratch) cudaFree(ctx->deflate_scratch);
   if (ctx->deflate_meta) cudaFree(ctx->deflate_meta);
   if (ctx->side) cudaStreamDestroy(ctx->side);
+  for (auto& pair : ctx->step_ev) {
+    for (cudaEvent_t e : pair) {
+      if (e) cudaEventDestroy(e);
+    }
+  }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1274,6 +1290,63 @@ int tb200_step_sync(tb200_ctx* ctx, const tb200_fill_job* fill_jobs, int nfill, 
   if (rc != TB200_OK) return rc;
   if (e_side != cudaSuccess) return fail(TB200_ERR_CUDA, "cudaStreamSynchronize(side) failed: %s", cudaGetErrorString(e_side));
   return tb200_ctx_sync(ctx);
+}
+
+int tb200_step_wait(tb200_ctx* ctx, uint64_t ticket) {
+  if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
+  if (ticket == 0 || ticket >= ctx->step_next) return fail(TB200_ERR_INVALID, "unknown step ticket");
+  const int k = static_cast<int>(ticket % TB200_STEP_DEPTH);
+  if (ctx->step_ticket[k] != ticket) return TB200_OK;  // already waited for (or displaced, which waited)
+  DeviceGuard g(ctx->device);
+  TB200_CUDA(cudaEventSynchronize(ctx->step_ev[k][0]));
+  if (ctx->step_has_side[k]) TB200_CUDA(cudaEventSynchronize(ctx->step_ev[k][1]));
+  ctx->step_ticket[k] = 0;
+  // both streams are past this step's events: every job table uploaded up to its submit is consumed
+  if (ctx->step_upload_mark[k] > ctx->uploads_done) ctx->uploads_done = ctx->step_upload_mark[k];
+  return TB200_OK;
+}
+
+int tb200_step_submit(tb200_ctx* ctx, const tb200_fill_job* fill_jobs, int nfill, uint64_t seed,
+                      uint64_t stream_epoch, const tb200_check_job* check_jobs, int ncheck,
+                      tb200_check_result* results, uint64_t* ticket) {
+  if (ctx == nullptr || ticket == nullptr) return fail(TB200_ERR_INVALID, "ctx / ticket is NULL");
+  if (ctx->forked || ctx->capture != nullptr) return fail(TB200_ERR_STATE, "step inside a fork / capture");
+  DeviceGuard g(ctx->device);
+  const uint64_t t = ctx->step_next;
+  const int k = static_cast<int>(t % TB200_STEP_DEPTH);
+  if (ctx->step_ticket[k] != 0) {
+    const int rc = tb200_step_wait(ctx, ctx->step_ticket[k]);
+    if (rc != TB200_OK) return rc;
+  }
+  if (ctx->step_ev[k][0] == nullptr) {
+    TB200_CUDA(cudaEventCreateWithFlags(&ctx->step_ev[k][0], cudaEventDisableTiming));
+    TB200_CUDA(cudaEventCreateWithFlags(&ctx->step_ev[k][1], cudaEventDisableTiming));
+  }
+  if (ctx->side == nullptr) {
+    TB200_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    TB200_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    TB200_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  int rc = tb200_fill_async(ctx, fill_jobs, nfill, seed, stream_epoch);
+  if (rc != TB200_OK) return rc;
+  TB200_CUDA(cudaEventRecord(ctx->step_ev[k][0], ctx->stream));
+  ctx->step_has_side[k] = ncheck > 0;
+  if (ncheck > 0) {
+    ctx->forked = true;  // uploads and launches below go to the side stream
+    ctx->cur = ctx->side;
+    rc = tb200_check_async(ctx, check_jobs, ncheck, results);
+    cudaError_t e = cudaSuccess;
+    if (rc == TB200_OK) e = cudaEventRecord(ctx->step_ev[k][1], ctx->side);
+    ctx->cur = ctx->stream;
+    ctx->forked = false;
+    if (rc != TB200_OK) return rc;
+    if (e != cudaSuccess) return fail(TB200_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+  }
+  ctx->step_ticket[k] = t;
+  ctx->step_upload_mark[k] = ctx->upload_seq;
+  ctx->step_next = t + 1;
+  *ticket = t;
+  return TB200_OK;
 }
 
 int tb200_tune(const char* key, int value) {

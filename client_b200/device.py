@@ -363,6 +363,19 @@ class DeviceOps:
         ca, nc = self.job_array(check_jobs, CheckJob)
         _native.check(self._lib.tb200_step_sync(self._ctx.handle, fa, nf, int(seed), int(epoch), ca, nc, results_ptr))
 
+    def step_submit(self, fill_jobs, check_jobs, results_ptr, seed=0, epoch=0):
+        """The same step without the wait (tb200_step_submit): returns a ticket for step_wait().
+        Up to 8 steps may be in flight; they must not share slots or result entries."""
+        fa, nf = self.job_array(fill_jobs, FillJob)
+        ca, nc = self.job_array(check_jobs, CheckJob)
+        ticket = ctypes.c_uint64(0)
+        _native.check(self._lib.tb200_step_submit(self._ctx.handle, fa, nf, int(seed), int(epoch), ca, nc, results_ptr, ctypes.byref(ticket)))
+        return ticket.value
+
+    def step_wait(self, ticket):
+        """Returns when the step's inputs are generated and its results are visible."""
+        _native.check(self._lib.tb200_step_wait(self._ctx.handle, int(ticket)))
+
     def l2_flush(self):
         _native.check(self._lib.tb200_l2_flush_async(self._ctx.handle))
 

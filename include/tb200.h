@@ -378,6 +378,19 @@ int tb200_step_sync(tb200_ctx* ctx, const tb200_fill_job* fill_jobs, int nfill, 
                     uint64_t stream_epoch, const tb200_check_job* check_jobs, int ncheck,
                     tb200_check_result* results);
 
+/* The same step without the wait: tb200_step_submit returns once both launches are queued (the
+ * fill on the context's stream, the validation on its side stream) and hands out a ticket;
+ * tb200_step_wait(ticket) returns when that step's inputs are generated and its results are
+ * visible in `results`.  Up to TB200_STEP_DEPTH steps may be in flight, so the host forms the job
+ * tables of step i+1 while the device runs step i (steps in flight must not share slots or
+ * result entries); submitting a step whose ring entry is still unwaited waits for it first.
+ * This is the load generator's pipelined pass and bench.py's e2e loop. */
+#define TB200_STEP_DEPTH 8
+int tb200_step_submit(tb200_ctx* ctx, const tb200_fill_job* fill_jobs, int nfill, uint64_t seed,
+                      uint64_t stream_epoch, const tb200_check_job* check_jobs, int ncheck,
+                      tb200_check_result* results, uint64_t* ticket);
+int tb200_step_wait(tb200_ctx* ctx, uint64_t ticket);
+
 /* knobs: "fill_variant" (experiment matrix of scripts/fill_sweep.py, 0 = default policy);
  * "step_parallel_min_mb": tb200_step_sync runs check and fill as parallel branches only
  * when the fill writes at least this many MiB (default 0 = always) */

@@ -489,6 +489,41 @@ def test_step_sync_call(gpu_ops):
     assert np.array_equal(gpu_ops.download(buf.ptr, n), cref.fill(n, "FP32", seed=4, stream=0))
 
 
+def test_step_submit_wait_pipeline(gpu_ops):
+    """tb200_step_submit / tb200_step_wait: many steps in flight (more than the ring holds, so
+    submits displace and wait for old tickets; more uploads than the job-table ring holds, so slots
+    are reclaimed through waited steps), every step's tensors and results exact."""
+    from client_b200._native import CheckJob
+    from client_b200.device import DeviceBuffer, HostBuffer, make_fill_job, results_array
+
+    n, sets = 48000, 12
+    buf = DeviceBuffer(0, sets * n)
+    logits = np.random.default_rng(9).standard_normal((sets, 1000)).astype(np.float32)
+    outs = gpu_ops.upload(logits)
+    res = HostBuffer(sets * 32)
+    tickets = []
+    for i in range(100):
+        s = i % sets
+        if len(tickets) >= 10:  # > TB200_STEP_DEPTH: the oldest were displaced (and waited for) by submits
+            t, s0, i0 = tickets.pop(0)
+            gpu_ops.step_wait(t)
+            assert int(results_array(res, sets)["argmax"][s0]) == int(np.argmax(logits[s0]))
+            if i0 % 17 == 0:
+                assert np.array_equal(gpu_ops.download(buf.ptr + s0 * n, n), cref.fill(n, "FP32", seed=5, stream=s0 + i0))
+        t = gpu_ops.step_submit([make_fill_job(buf.ptr + s * n, n, "FP32", stream_id=s)],
+                                [CheckJob(a=outs.ptr + s * 4000, nbytes=4000, kind=3)], res.device_ptr + s * 32, seed=5, epoch=i)
+        tickets.append((t, s, i))
+    for t, s0, i0 in tickets:
+        gpu_ops.step_wait(t)
+        gpu_ops.step_wait(t)  # idempotent
+        assert np.array_equal(gpu_ops.download(buf.ptr + s0 * n, n), cref.fill(n, "FP32", seed=5, stream=s0 + i0))
+    with pytest.raises(Exception):
+        gpu_ops.step_wait(10**9)
+    t = gpu_ops.step_submit([make_fill_job(buf.ptr, n, "FP32", stream_id=1)], [], res.device_ptr, seed=6)  # no validation
+    gpu_ops.step_wait(t)
+    assert np.array_equal(gpu_ops.download(buf.ptr, n), cref.fill(n, "FP32", seed=6, stream=1))
+
+
 # ---- resize + pack (image_client.preprocess with its Image.resize) ---------------------------
 def _resize_on_device(ops, src, dtype, layout, scaling, oh, ow):
     from client_b200.device import DeviceBuffer
