@@ -487,6 +487,27 @@ def wire_extra(ops, ctx, device, seconds=1.0):
             ss.close()
     finally:
         stub.stop()
+    # C5 as quoted: prompts on one ModelStreamInfer stream per connection, 16 token responses each
+    from client_b200.perf.native import stream_token_responses
+
+    resp, fin = stream_token_responses()
+    sstub = GrpcStubServer(resp, final_response=fin, responses_per_request=16)
+    try:
+        ins, _, ranges = cases["c5_llama3_prompt4096"]
+        ss = SlotSet(ins, [], 64, "none", device, "random", SEED, ranges, name_prefix="bench_c5_stream", wire_prefixes=grpc_wire_prefixes(ins))
+        gen = NativeLoadGenerator(sstub.url, "llama3_8b", "", ss, 64, regenerate=True, validate=False, protocol="grpc-stream")
+        gen.start()
+        try:
+            gen.window(0.3)
+            w = gen.window(seconds)
+        finally:
+            gen.stop()
+        ss.close()
+        out["c5_llama3_stream"] = {"concurrency": 64, "tokens_per_request": 16, "infer_per_s": round(w["throughput"]),
+                                   "tokens_per_s": round(w["responses_per_s"]), "ttft_p50_us": round(w["ttft_p50_us"], 1),
+                                   "ttft_p99_us": round(w["ttft_p99_us"], 1), "p50_us": round(w["p50_us"], 1), "failed": w["failed"]}
+    finally:
+        sstub.stop()
     return out
 
 

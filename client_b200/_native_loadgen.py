@@ -31,6 +31,7 @@ class LoadgenStats(ctypes.Structure):
         ("p50_ns", c_u64), ("p90_ns", c_u64), ("p95_ns", c_u64), ("p99_ns", c_u64), ("min_ns", c_u64), ("max_ns", c_u64),
         ("window_seconds", ctypes.c_double),
         ("device_batches", c_u64), ("device_slots", c_u64), ("nonfinite_outputs", c_u64), ("check_mismatches", c_u64),
+        ("response_count", c_u64), ("first_response_p50_ns", c_u64), ("first_response_p99_ns", c_u64),
     ]
 
 
@@ -43,6 +44,7 @@ LOADGEN_SIGNATURES = {
     "tb200_stub_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "tb200_stub_server_stop": (c_int, [c_vp]),
     "tb200_grpc_stub_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), c_vp, c_u64, ctypes.POINTER(c_vp)]),
+    "tb200_grpc_stub_server_start_streaming": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), c_vp, c_u64, c_vp, c_u64, c_int, ctypes.POINTER(c_vp)]),
     "tb200_grpc_stub_server_stop": (c_int, [c_vp]),
     "tb200_mock_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_vp)]),
     "tb200_mock_server_requests": (ctypes.c_uint64, [c_vp]),

@@ -17,7 +17,9 @@
 #include <sys/socket.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -31,6 +33,27 @@ namespace tb200 {
 class H2StubServer {
  public:
   ~H2StubServer() { Stop(); }
+
+  // Stream mode (ModelStreamInfer): every request MESSAGE on a stream is answered with
+  // `responses_per_request - 1` copies of `message` and one `final_message`; the response
+  // HEADERS go out once per stream, the trailers when the client half-closes.
+  bool StartStreaming(const char* host, int* port, int nthreads, const std::string& message, const std::string& final_message,
+                      int responses_per_request) {
+    streaming_ = true;
+    auto framed = [](const std::string& m) {
+      std::string d(5, '\0');
+      h2::put_grpc_prefix(reinterpret_cast<uint8_t*>(&d[0]), static_cast<uint32_t>(m.size()));
+      return h2::frame(h2::DATA, 0, 0, d + m);
+    };
+    stream_reply_.clear();
+    for (int i = 0; i + 1 < responses_per_request; ++i) {
+      reply_id_off_.push_back(stream_reply_.size() + 5);
+      stream_reply_ += framed(message);
+    }
+    reply_id_off_.push_back(stream_reply_.size() + 5);
+    stream_reply_ += framed(final_message);
+    return Start(host, port, nthreads, message);
+  }
 
   bool Start(const char* host, int* port, int nthreads, const std::string& message) {
     // response image of one call; the three stream ids are patched per call
@@ -103,11 +126,19 @@ class H2StubServer {
 
  private:
   static constexpr uint32_t kEvTag = 0xFFFFFFFFu;
+  struct StreamState {  // stream mode: where we are inside the client's message sequence
+    bool headers_sent = false;
+    uint8_t prefix[5];
+    uint32_t prefix_have = 0;
+    uint64_t body_left = 0;
+    uint64_t consumed = 0;
+  };
   struct Conn {
     int fd = -1;
     bool preface = false;
     uint64_t consumed = 0;
     std::string buf;
+    std::map<uint32_t, StreamState> streams;
   };
   struct Loop {
     int epfd = -1, evfd = -1;
@@ -162,6 +193,58 @@ class H2StubServer {
     c.preface = false;
     c.consumed = 0;
     c.buf.clear();
+    c.streams.clear();
+  }
+
+  static void PatchIds(std::string* out, size_t base, const std::vector<size_t>& offsets, uint32_t stream) {
+    for (size_t off : offsets) {
+      (*out)[base + off + 0] = static_cast<char>((stream >> 24) & 0x7F);
+      (*out)[base + off + 1] = static_cast<char>(stream >> 16);
+      (*out)[base + off + 2] = static_cast<char>(stream >> 8);
+      (*out)[base + off + 3] = static_cast<char>(stream);
+    }
+  }
+
+  // stream mode: DATA payload of one stream; a reply per completed request message
+  void ServeStreamData(Conn& c, const h2::FrameView& f, std::string* out) {
+    StreamState& st = c.streams[f.stream];
+    if (!st.headers_sent) {
+      *out += h2::frame(h2::HEADERS, h2::kEndHeaders, f.stream, h2::grpc_response_headers());
+      st.headers_sent = true;
+    }
+    const uint8_t* p = f.payload;
+    size_t left = f.length;
+    while (left > 0) {
+      if (st.body_left == 0 && st.prefix_have < 5) {
+        const size_t n = std::min<size_t>(5 - st.prefix_have, left);
+        memcpy(st.prefix + st.prefix_have, p, n);
+        st.prefix_have += static_cast<uint32_t>(n);
+        p += n;
+        left -= n;
+        if (st.prefix_have < 5) break;
+        st.body_left = h2::get_u32(st.prefix + 1);
+      }
+      const size_t n = static_cast<size_t>(std::min<uint64_t>(st.body_left, left));
+      st.body_left -= n;
+      p += n;
+      left -= n;
+      if (st.body_left == 0 && st.prefix_have == 5) {  // one request message complete
+        st.prefix_have = 0;
+        const size_t base = out->size();
+        *out += stream_reply_;
+        PatchIds(out, base, reply_id_off_, f.stream);
+        calls_.fetch_add(1, std::memory_order_relaxed);
+      }
+    }
+    st.consumed += f.length;
+    if (st.consumed >= (1u << 18) && !(f.flags & h2::kEndStream)) {
+      *out += h2::window_update(f.stream, static_cast<uint32_t>(st.consumed));
+      st.consumed = 0;
+    }
+    if (f.flags & h2::kEndStream) {
+      *out += h2::frame(h2::HEADERS, h2::kEndHeaders | h2::kEndStream, f.stream, h2::grpc_trailers_ok());
+      c.streams.erase(f.stream);
+    }
   }
 
   // everything complete in c.buf; false when the connection should be dropped
@@ -191,10 +274,14 @@ class H2StubServer {
           break;
         case h2::DATA:
           c.consumed += f.length;
-          answer = (f.flags & h2::kEndStream) != 0;
+          if (streaming_) ServeStreamData(c, f, &out);
+          else answer = (f.flags & h2::kEndStream) != 0;
           break;
         case h2::HEADERS:
-          answer = (f.flags & h2::kEndStream) != 0;  // a call without a message
+          answer = !streaming_ && (f.flags & h2::kEndStream) != 0;  // a call without a message
+          break;
+        case h2::RST_STREAM:
+          c.streams.erase(f.stream);
           break;
         default:
           break;
@@ -202,12 +289,7 @@ class H2StubServer {
       if (answer && f.stream != 0) {
         const size_t base = out.size();
         out += response_;
-        for (size_t off : id_off_) {
-          out[base + off + 0] = static_cast<char>((f.stream >> 24) & 0x7F);
-          out[base + off + 1] = static_cast<char>(f.stream >> 16);
-          out[base + off + 2] = static_cast<char>(f.stream >> 8);
-          out[base + off + 3] = static_cast<char>(f.stream);
-        }
+        PatchIds(&out, base, std::vector<size_t>(id_off_, id_off_ + 3), f.stream);
         calls_.fetch_add(1, std::memory_order_relaxed);
       }
     }
@@ -269,6 +351,9 @@ class H2StubServer {
 
   std::string response_, hello_;
   size_t id_off_[3] = {0, 0, 0};
+  bool streaming_ = false;
+  std::string stream_reply_;          // DATA frames answering one request message (stream mode)
+  std::vector<size_t> reply_id_off_;  // where their stream ids are
   int listen_fd_ = -1;
   std::atomic<bool> stop_{false};
   std::atomic<uint64_t> calls_{0};

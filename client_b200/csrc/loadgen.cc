@@ -38,6 +38,7 @@
 #include <vector>
 
 #include "../../include/tb200_loadgen.h"
+#include "../cpp/pb.h"
 #include "h2.h"
 #include "h2_stub_server.h"
 #include "http_server.h"
@@ -116,7 +117,8 @@ struct SlotQueue {
 struct WorkerStats {
   std::mutex mu;
   std::vector<uint64_t> latencies;  // REQUEST_START -> REQUEST_END
-  uint64_t completed = 0, failed = 0, total_ns = 0, send_ns = 0, recv_ns = 0;
+  std::vector<uint64_t> first_ns;   // stream mode: REQUEST_START -> first response of the request
+  uint64_t completed = 0, failed = 0, total_ns = 0, send_ns = 0, recv_ns = 0, responses = 0;
 };
 
 // one keep-alive connection = one concurrency slot
@@ -141,6 +143,13 @@ struct Conn {
   uint64_t recv_consumed = 0;
   bool got_data = false, waiting_window = false, goaway = false;
   std::string ctrl;        // control frames (acks, window updates) waiting for a frame boundary
+  // stream mode (ModelStreamInfer): one long-lived stream per connection, a request = one message on it
+  bool stream_open = false;
+  int64_t stream_window = 0;        // what the peer lets us send on the stream
+  uint64_t stream_recv_consumed = 0;
+  std::string rx_msg;               // response messages being reassembled from DATA frames
+  uint64_t t_first = 0;             // first response of the request in flight
+  uint32_t responses = 0;
 };
 
 struct Transport {
@@ -162,6 +171,7 @@ struct tb200_loadgen {
   std::vector<uint64_t> tail_sizes;
   bool passthrough = false;           // no device work per request: workers keep their slot
   bool grpc = false;                  // requests[] are ModelInferRequest bytes sent as unary gRPC calls
+  bool grpc_stream = false;           // ... or as messages of one ModelStreamInfer stream per connection
   std::string grpc_headers;           // HEADERS payload shared by all requests
   tb200_ctx* ctx = nullptr;
   std::vector<tb200_fill_job> fill_jobs;
@@ -217,6 +227,10 @@ bool conn_open(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
     c.peer_max_frame = tb200::h2::kDefaultMaxFrame;
     c.recv_consumed = 0;
     c.waiting_window = c.goaway = false;
+    c.stream_open = false;
+    c.stream_window = 0;
+    c.stream_recv_consumed = 0;
+    c.rx_msg.clear();
     c.buf.clear();
     c.ctrl = tb200::h2::client_preface();
     h2_flush_ctrl(c);
@@ -299,28 +313,39 @@ int grpc_build(tb200_loadgen* lg, Conn& c) {
   const size_t payload = 5 + message;
   if (payload > c.peer_stream_window || payload > 0x7FFFFFFFu) return -1;
   if (static_cast<int64_t>(payload) > c.conn_window) return 1;
-  c.cur_stream = c.next_stream;
-  c.next_stream += 2;
+  const bool open_stream = !lg->grpc_stream || !c.stream_open;
+  if (lg->grpc_stream && c.stream_open && static_cast<int64_t>(payload) > c.stream_window) return 1;
+  if (open_stream) {
+    c.cur_stream = c.next_stream;
+    c.next_stream += 2;
+    c.stream_window = c.peer_stream_window;
+    c.stream_open = lg->grpc_stream;
+  }
   c.got_data = false;
+  c.t_first = 0;
+  c.responses = 0;
   const size_t maxf = c.peer_max_frame;
   const size_t nframes = (payload + maxf - 1) / maxf;
-  // txbuf: [HEADERS frame][prefix + head][DATA frame headers ...]
-  c.txbuf.resize(9 + lg->grpc_headers.size() + 5 + head.size() + 9 * nframes);
+  const size_t hdr_bytes = open_stream ? 9 + lg->grpc_headers.size() : 0;
+  // txbuf: [HEADERS frame (a new stream only)][prefix + head][DATA frame headers ...]
+  c.txbuf.resize(hdr_bytes + 5 + head.size() + 9 * nframes);
   uint8_t* w = c.txbuf.data();
-  h2::put_frame_header(w, static_cast<uint32_t>(lg->grpc_headers.size()), h2::HEADERS, h2::kEndHeaders, c.cur_stream);
-  memcpy(w + 9, lg->grpc_headers.data(), lg->grpc_headers.size());
-  uint8_t* body = w + 9 + lg->grpc_headers.size();
+  if (open_stream) {
+    h2::put_frame_header(w, static_cast<uint32_t>(lg->grpc_headers.size()), h2::HEADERS, h2::kEndHeaders, c.cur_stream);
+    memcpy(w + 9, lg->grpc_headers.data(), lg->grpc_headers.size());
+  }
+  uint8_t* body = w + hdr_bytes;
   h2::put_grpc_prefix(body, static_cast<uint32_t>(message));
   memcpy(body + 5, head.data(), head.size());
   const size_t in_buf = 5 + head.size();
   uint8_t* fh = body + in_buf;
   c.tx.clear();
   c.tx_idx = 0;
-  c.tx.push_back(iovec{w, 9 + lg->grpc_headers.size()});
+  if (open_stream) c.tx.push_back(iovec{w, hdr_bytes});
   size_t off = 0;
   for (size_t f = 0; f < nframes; ++f) {
     const size_t chunk = std::min(maxf, payload - off);
-    const bool last = off + chunk == payload;
+    const bool last = off + chunk == payload && !lg->grpc_stream;  // a stream stays open between requests
     h2::put_frame_header(fh + 9 * f, static_cast<uint32_t>(chunk), h2::DATA, last ? h2::kEndStream : 0, c.cur_stream);
     c.tx.push_back(iovec{fh + 9 * f, 9});
     size_t o = off, left = chunk;
@@ -334,7 +359,68 @@ int grpc_build(tb200_loadgen* lg, Conn& c) {
     off += chunk;
   }
   c.conn_window -= static_cast<int64_t>(payload);
+  c.stream_window -= static_cast<int64_t>(payload);
   return 0;
+}
+
+// One ModelStreamInferResponse (grpc_service.proto: 1 error_message, 2 infer_response; in the latter
+// 4 parameters map<string, InferParameter{1 bool_param}>): *error when error_message is set, *final
+// unless the response carries triton_final_response = false (the rule of the Python engine,
+// perf/loadgen.py, and of perf_analyzer for decoupled models).
+void parse_stream_response(const uint8_t* p, size_t n, bool* error, bool* final) {
+  namespace pb = tb200::pb;
+  *error = false;
+  *final = true;
+  pb::Reader r(p, n);
+  uint32_t field = 0, wt = 0;
+  while (r.tag(&field, &wt)) {
+    const uint8_t* d = nullptr;
+    size_t len = 0;
+    if (wt != pb::kBytes || !r.bytes(&d, &len)) {
+      r.skip(wt);
+      continue;
+    }
+    if (field == 1 && len != 0) *error = true;
+    if (field != 2) continue;
+    pb::Reader resp(d, len);
+    uint32_t f2 = 0, w2 = 0;
+    while (resp.tag(&f2, &w2)) {
+      const uint8_t* e = nullptr;
+      size_t elen = 0;
+      if (w2 != pb::kBytes || !resp.bytes(&e, &elen)) {
+        resp.skip(w2);
+        continue;
+      }
+      if (f2 != 4) continue;
+      pb::Reader entry(e, elen);
+      uint32_t f3 = 0, w3 = 0;
+      bool is_final_key = false, value = false, has_value = false;
+      while (entry.tag(&f3, &w3)) {
+        const uint8_t* v = nullptr;
+        size_t vlen = 0;
+        if (w3 != pb::kBytes || !entry.bytes(&v, &vlen)) {
+          entry.skip(w3);
+          continue;
+        }
+        if (f3 == 1) {
+          is_final_key = vlen == 21 && memcmp(v, "triton_final_response", 21) == 0;
+        } else if (f3 == 2) {
+          pb::Reader param(v, vlen);
+          uint32_t f4 = 0, w4 = 0;
+          while (param.tag(&f4, &w4)) {
+            if (f4 == 1 && w4 == pb::kVarint) {
+              value = param.varint() != 0;
+              has_value = true;
+            } else {
+              param.skip(w4);
+            }
+          }
+        }
+      }
+      if (is_final_key && has_value) *final = value;
+    }
+  }
+  if (!r.ok) *error = true;
 }
 
 void request_start(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool retry) {
@@ -381,6 +467,10 @@ void request_done(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool
       t->stats.send_ns += c.t_send_end - c.t_start;
       t->stats.recv_ns += t_end - c.t_recv_start;
       t->stats.latencies.push_back(t_end - c.t_start);
+      if (lg->grpc_stream) {
+        t->stats.responses += c.responses;
+        t->stats.first_ns.push_back((c.t_first != 0 ? c.t_first : t_end) - c.t_start);
+      }
     } else {
       t->stats.failed += 1;
     }
@@ -477,7 +567,10 @@ void grpc_readable(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
           for (uint32_t o = 0; o + 6 <= f.length; o += 6) {
             const uint16_t id = static_cast<uint16_t>((f.payload[o] << 8) | f.payload[o + 1]);
             const uint32_t v = h2::get_u32(f.payload + o + 2);
-            if (id == h2::kSettingsInitialWindow) c.peer_stream_window = v;
+            if (id == h2::kSettingsInitialWindow) {
+              c.stream_window += static_cast<int64_t>(v) - static_cast<int64_t>(c.peer_stream_window);
+              c.peer_stream_window = v;
+            }
             else if (id == h2::kSettingsMaxFrame && v >= h2::kDefaultMaxFrame) c.peer_max_frame = std::min<uint32_t>(v, 1u << 20);
           }
           c.ctrl += h2::frame(h2::SETTINGS, h2::kAck, 0, "");
@@ -488,9 +581,38 @@ void grpc_readable(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
         break;
       case h2::WINDOW_UPDATE:
         if (f.length == 4 && f.stream == 0) c.conn_window += h2::get_u32(f.payload) & 0x7FFFFFFFu;
+        else if (f.length == 4 && f.stream == c.cur_stream) c.stream_window += h2::get_u32(f.payload) & 0x7FFFFFFFu;
         break;
       case h2::DATA:
         c.recv_consumed += f.length;
+        if (lg->grpc_stream) {
+          if (f.stream != c.cur_stream) break;
+          c.stream_recv_consumed += f.length;
+          c.rx_msg.append(reinterpret_cast<const char*>(f.payload), f.length);
+          size_t off = 0;
+          while (c.rx_msg.size() - off >= 5) {
+            const uint8_t* h = reinterpret_cast<const uint8_t*>(c.rx_msg.data()) + off;
+            const size_t len = h2::get_u32(h + 1);
+            if (c.rx_msg.size() - off - 5 < len) break;
+            if (c.in_flight && !finished) {
+              bool error = false, final = true;
+              parse_stream_response(h + 5, len, &error, &final);
+              c.responses += 1;
+              if (c.t_first == 0) c.t_first = now_ns();
+              if (error || final) {
+                finished = true;
+                ok = !error;
+              }
+            }
+            off += 5 + len;
+          }
+          if (off) c.rx_msg.erase(0, off);
+          if (f.flags & h2::kEndStream) {  // the server ended the stream: start over on a new connection
+            c.goaway = true;
+            if (c.in_flight && !finished) finished = true;
+          }
+          break;
+        }
         if (f.stream == c.cur_stream && c.in_flight) {
           if (f.length >= 5) c.got_data = true;
           if (f.flags & h2::kEndStream) {
@@ -500,12 +622,20 @@ void grpc_readable(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
         }
         break;
       case h2::HEADERS:
+        if (lg->grpc_stream) {
+          if (f.stream == c.cur_stream && (f.flags & h2::kEndStream)) {  // trailers: the stream is over
+            c.goaway = true;
+            if (c.in_flight) finished = true;
+          }
+          break;
+        }
         if (f.stream == c.cur_stream && c.in_flight && (f.flags & h2::kEndStream)) {
           finished = true;  // trailers; an error arrives as a trailers-only response without DATA
           ok = c.got_data;
         }
         break;
       case h2::RST_STREAM:
+        if (f.stream == c.cur_stream && lg->grpc_stream) c.goaway = true;
         if (f.stream == c.cur_stream && c.in_flight) finished = true;
         break;
       case h2::GOAWAY:
@@ -516,6 +646,10 @@ void grpc_readable(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
     }
   }
   if (pos) c.buf.erase(c.buf.begin(), c.buf.begin() + static_cast<long>(pos));
+  if (c.stream_recv_consumed >= (tb200::h2::kOurStreamWindow / 2) && c.fd >= 0 && !c.goaway) {
+    c.ctrl += h2::window_update(c.cur_stream, static_cast<uint32_t>(c.stream_recv_consumed));
+    c.stream_recv_consumed = 0;
+  }
   if (c.recv_consumed >= (1u << 28)) {  // give the connection window back long before it runs out
     c.ctrl += h2::window_update(0, static_cast<uint32_t>(c.recv_consumed));
     c.recv_consumed = 0;
@@ -526,6 +660,10 @@ void grpc_readable(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
     if (c.t_recv_start == 0) c.t_recv_start = t_end;
     if (c.goaway) conn_close(t, c);
     request_done(lg, t, c, index, ok, t_end);
+    return;
+  }
+  if (c.goaway && !c.in_flight && c.fd >= 0) {  // nothing pending on a connection the server is done with
+    conn_close(t, c);
     return;
   }
   if (closed) {
@@ -730,14 +868,17 @@ int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out) {
   lg->seed = cfg->seed;
   lg->regenerate = cfg->regenerate != 0;
   lg->device_window_ns = 1000ull * cfg->device_window_us;
-  lg->grpc = cfg->protocol == 1;
-  if (cfg->protocol > 1) {
+  lg->grpc = cfg->protocol == 1 || cfg->protocol == 2;
+  lg->grpc_stream = cfg->protocol == 2;
+  if (cfg->protocol > 2) {
     delete lg;
     return lg_fail(TB200_ERR_INVALID, "unknown load generator protocol");
   }
   if (lg->grpc) {
     lg->grpc_headers = tb200::h2::grpc_request_headers(lg->host + ":" + std::to_string(lg->port),
-                                                       cfg->grpc_path ? cfg->grpc_path : "/inference.GRPCInferenceService/ModelInfer");
+                                                       cfg->grpc_path ? cfg->grpc_path
+                                                                      : (lg->grpc_stream ? "/inference.GRPCInferenceService/ModelStreamInfer"
+                                                                                         : "/inference.GRPCInferenceService/ModelInfer"));
   }
   if (cfg->ctx != nullptr && cfg->fill_jobs != nullptr && cfg->fill_jobs_per_slot > 0) {
     lg->fill_per_slot = cfg->fill_jobs_per_slot;
@@ -803,7 +944,7 @@ int tb200_loadgen_window(tb200_loadgen* lg, double seconds, tb200_loadgen_stats*
   if (lg == nullptr || out == nullptr || !lg->started) return lg_fail(TB200_ERR_STATE, "load generator not running");
   if (seconds > 0) std::this_thread::sleep_for(std::chrono::duration<double>(seconds));
   memset(out, 0, sizeof(*out));
-  std::vector<uint64_t> lat;
+  std::vector<uint64_t> lat, first;
   for (auto& tr : lg->transports) {
     WorkerStats& st = tr->stats;
     std::lock_guard<std::mutex> lk(st.mu);
@@ -814,7 +955,10 @@ int tb200_loadgen_window(tb200_loadgen* lg, double seconds, tb200_loadgen_stats*
     out->cumulative_receive_time_ns += st.recv_ns;
     lat.insert(lat.end(), st.latencies.begin(), st.latencies.end());
     st.latencies.clear();
-    st.completed = st.failed = st.total_ns = st.send_ns = st.recv_ns = 0;
+    first.insert(first.end(), st.first_ns.begin(), st.first_ns.end());
+    st.first_ns.clear();
+    out->response_count += st.responses;
+    st.completed = st.failed = st.total_ns = st.send_ns = st.recv_ns = st.responses = 0;
   }
   const uint64_t t = now_ns();
   out->window_seconds = static_cast<double>(t - lg->window_start_ns) * 1e-9;
@@ -828,6 +972,12 @@ int tb200_loadgen_window(tb200_loadgen* lg, double seconds, tb200_loadgen_stats*
     out->p99_ns = pct(0.99);
     out->min_ns = lat.front();
     out->max_ns = lat.back();
+  }
+  if (!first.empty()) {
+    std::sort(first.begin(), first.end());
+    auto pct = [&](double p) { return first[std::min(first.size() - 1, static_cast<size_t>(p * (first.size() - 1) + 0.5))]; };
+    out->first_response_p50_ns = pct(0.50);
+    out->first_response_p99_ns = pct(0.99);
   }
   {
     std::lock_guard<std::mutex> lk(lg->dev_mu);
@@ -903,6 +1053,9 @@ int tb200_stub_server_stop(tb200_stub_server* s) {
 
 int tb200_grpc_stub_server_start(const char* host, int* port, const uint8_t* response, uint64_t response_bytes,
                                  tb200_grpc_stub_server** out);
+int tb200_grpc_stub_server_start_streaming(const char* host, int* port, const uint8_t* response, uint64_t response_bytes,
+                                           const uint8_t* final_response, uint64_t final_bytes, int responses_per_request,
+                                           tb200_grpc_stub_server** out);
 int tb200_grpc_stub_server_stop(tb200_grpc_stub_server* s);
 
 }  // extern "C"
@@ -921,6 +1074,24 @@ int tb200_grpc_stub_server_start(const char* host, int* port, const uint8_t* res
   tb200_grpc_stub_server* s = new tb200_grpc_stub_server();
   const int hw = static_cast<int>(std::max(2u, std::thread::hardware_concurrency()));
   if (!s->h2.Start(host, port, std::min(16, hw / 2), std::string(reinterpret_cast<const char*>(response), response_bytes))) {
+    delete s;
+    return lg_fail(TB200_ERR_IO, "cannot bind the gRPC stub server");
+  }
+  *out = s;
+  return TB200_OK;
+}
+
+int tb200_grpc_stub_server_start_streaming(const char* host, int* port, const uint8_t* response, uint64_t response_bytes,
+                                           const uint8_t* final_response, uint64_t final_bytes, int responses_per_request,
+                                           tb200_grpc_stub_server** out) {
+  if (host == nullptr || port == nullptr || out == nullptr || (response == nullptr && response_bytes != 0) ||
+      (final_response == nullptr && final_bytes != 0) || responses_per_request < 1) {
+    return lg_fail(TB200_ERR_INVALID, "NULL argument / responses_per_request < 1");
+  }
+  tb200_grpc_stub_server* s = new tb200_grpc_stub_server();
+  const int hw = static_cast<int>(std::max(2u, std::thread::hardware_concurrency()));
+  if (!s->h2.StartStreaming(host, port, std::min(16, hw / 2), std::string(reinterpret_cast<const char*>(response), response_bytes),
+                            std::string(reinterpret_cast<const char*>(final_response), final_bytes), responses_per_request)) {
     delete s;
     return lg_fail(TB200_ERR_IO, "cannot bind the gRPC stub server");
   }

@@ -43,9 +43,13 @@ class NativeLoadGenerator:
     """One tb200_loadgen instance over a SlotSet (cuda shm or wire mode)."""
 
     def __init__(self, url, model_name, model_version, slotset, concurrency, regenerate=True, validate=True,
-                 device_window_us=0, protocol="http"):
+                 device_window_us=0, protocol="http", request_parameters=None):
+        """``protocol``: "http" (HTTP/1.1), "grpc" (unary ModelInfer) or "grpc-stream" (one
+        ModelStreamInfer stream per connection; windows then report ``ttft_p50_us`` and
+        ``responses``)."""
         self._lib = _native.load()
         self.protocol = protocol
+        self.request_parameters = request_parameters
         host, _, port = url.partition(":")
         self.host, self.port = host, int(port or 80)
         ss = slotset
@@ -53,9 +57,10 @@ class NativeLoadGenerator:
         uri = InferenceServerClient._model_uri(model_name, model_version, "/infer")
         self._keep = []
         reqs, tails = [], []
-        if protocol == "grpc":
-            reqs, tails = self._grpc_requests(model_name, model_version, ss, concurrency)
-        for slot in range(concurrency if protocol != "grpc" else 0):
+        grpc_like = protocol in ("grpc", "grpc-stream")
+        if grpc_like:
+            reqs, tails = self._grpc_requests(model_name, model_version, ss, concurrency, request_parameters)
+        for slot in range(0 if grpc_like else concurrency):
             inputs, outputs = [], []
             for i, t in enumerate(ss.inputs):
                 inp = InferInput(t.name, t.shape, t.datatype)
@@ -70,7 +75,7 @@ class NativeLoadGenerator:
                 if ss.shared_memory in ("cuda", "system"):
                     out.set_shared_memory(ss.prefix + "_out", t.nbytes, offset=ss.output_offset(slot, i))
                 outputs.append(out)
-            body, json_size = InferenceServerClient.generate_request_body(inputs, outputs=outputs)
+            body, json_size = InferenceServerClient.generate_request_body(inputs, outputs=outputs, parameters=request_parameters)
             if ss.shared_memory == "none":
                 json_size = len(body)
                 reqs.append(frame_http_request(self.host, self.port, uri, body, json_size, head_only_bytes=ss.in_bytes))
@@ -110,14 +115,14 @@ class NativeLoadGenerator:
                 cfg.check_jobs_per_slot = len(ss.outputs)
                 cfg.results = self._results.device_ptr
         cfg.device_window_us = int(device_window_us)
-        cfg.protocol = 1 if protocol == "grpc" else 0
+        cfg.protocol = {"http": 0, "grpc": 1, "grpc-stream": 2}[protocol]
         self._keep.append(cfg)
         h = ctypes.c_void_p()
         _native.check(self._lib.tb200_loadgen_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
 
     @staticmethod
-    def _grpc_requests(model_name, model_version, ss, concurrency):
+    def _grpc_requests(model_name, model_version, ss, concurrency, request_parameters=None):
         """Per slot: ModelInferRequest bytes up to (not including) raw_input_contents; in wire
         mode the rest of the message is the slot's staging image (tag + length + tensor per
         input), which must have been laid out with grpc_wire_prefixes()."""
@@ -139,7 +144,7 @@ class NativeLoadGenerator:
                 outputs.append(out)
             request = _get_inference_request(model_name=model_name, inputs=inputs, model_version=model_version, request_id="",
                                              outputs=outputs, sequence_id=0, sequence_start=False, sequence_end=False,
-                                             priority=0, timeout=None, parameters=None)
+                                             priority=0, timeout=None, parameters=request_parameters)
             reqs.append(request.SerializeToString())
             if ss.shared_memory == "none":
                 if ss.wire_stride == ss.in_bytes and ss.in_bytes:
@@ -164,6 +169,9 @@ class NativeLoadGenerator:
             "min_us": st.min_ns / 1e3, "max_us": st.max_ns / 1e3,
             "device_batches": int(st.device_batches), "device_slots": int(st.device_slots),
             "nonfinite": int(st.nonfinite_outputs), "mismatches": int(st.check_mismatches),
+            **({"responses": int(st.response_count), "responses_per_s": st.response_count / st.window_seconds if st.window_seconds > 0 else 0.0,
+                "ttft_p50_us": st.first_response_p50_ns / 1e3, "ttft_p99_us": st.first_response_p99_ns / 1e3}
+               if self.protocol == "grpc-stream" else {}),
         }
 
     def stop(self):
@@ -180,14 +188,21 @@ class NativeLoadGenerator:
 
 
 class GrpcStubServer:
-    """tb200_grpc_stub_server: every unary call answered with one canned message."""
+    """tb200_grpc_stub_server: every unary call answered with one canned message; with
+    ``final_response`` given (stream mode, ModelStreamInfer) every request MESSAGE on a stream is
+    answered with ``responses_per_request - 1`` x ``response`` and one ``final_response``."""
 
-    def __init__(self, response=b"", host="127.0.0.1", port=0):
+    def __init__(self, response=b"", host="127.0.0.1", port=0, final_response=None, responses_per_request=1):
         self._lib = _native.load()
         p = ctypes.c_int(port)
         h = ctypes.c_void_p()
         buf = ctypes.create_string_buffer(response, max(len(response), 1))
-        _native.check(self._lib.tb200_grpc_stub_server_start(host.encode(), ctypes.byref(p), buf, len(response), ctypes.byref(h)))
+        if final_response is not None:
+            fin = ctypes.create_string_buffer(final_response, max(len(final_response), 1))
+            _native.check(self._lib.tb200_grpc_stub_server_start_streaming(host.encode(), ctypes.byref(p), buf, len(response), fin,
+                                                                           len(final_response), int(responses_per_request), ctypes.byref(h)))
+        else:
+            _native.check(self._lib.tb200_grpc_stub_server_start(host.encode(), ctypes.byref(p), buf, len(response), ctypes.byref(h)))
         self._h, self.host, self.port = h, host, p.value
 
     @property
@@ -198,6 +213,27 @@ class GrpcStubServer:
         if getattr(self, "_h", None):
             self._lib.tb200_grpc_stub_server_stop(self._h)
             self._h = None
+
+
+def stream_token_responses(output_name="token", token=7):
+    """(response, final_response) for GrpcStubServer's stream mode: ModelStreamInferResponse
+    messages carrying one INT32[1,1] token, the last one flagged triton_final_response."""
+    import numpy as np
+
+    from ..grpc import service_pb2
+
+    out = []
+    for final in (False, True):
+        m = service_pb2.ModelStreamInferResponse()
+        r = m.infer_response
+        r.model_name = "stub"
+        r.parameters["triton_final_response"].bool_param = final
+        o = r.outputs.add()
+        o.name, o.datatype = output_name, "INT32"
+        o.shape.extend([1, 1])
+        r.raw_output_contents.append(np.array([[token]], np.int32).tobytes())
+        out.append(m.SerializeToString())
+    return tuple(out)
 
 
 class StubServer:

@@ -56,7 +56,11 @@ typedef struct tb200_loadgen_config {
    * (what grpcio does under PY/grpc/_client.py:1445-1572): requests[s] holds the serialised
    * ModelInferRequest WITHOUT its raw_input_contents, tails[s] the remaining message bytes
    * (field-7 tag + length + tensor, per input) in pinned staging; one stream per request,
-   * messages up to the peer's stream window (64 KiB by default) */
+   * messages up to the peer's stream window (64 KiB by default);
+   * 2 = the same messages on ONE long-lived ModelStreamInfer stream per connection (reference
+   * grpc/_client.py start_stream / async_stream_infer): a request completes at the response
+   * that does not carry triton_final_response = false, or at a response with an error message;
+   * the time to the first response is reported */
   uint32_t protocol;
   const char* grpc_path; /* NULL -> "/inference.GRPCInferenceService/ModelInfer" */
 } tb200_loadgen_config;
@@ -77,6 +81,10 @@ typedef struct tb200_loadgen_stats {
                               /* requests covered per launch)                          */
   uint64_t nonfinite_outputs; /* from TOP1 checks                                      */
   uint64_t check_mismatches;  /* from EQUAL / ADDSUB checks                            */
+  /* protocol 2 (one ModelStreamInfer stream per connection): responses received for the    */
+  /* completed requests (tokens of a decoupled model) and REQUEST_START -> first response   */
+  uint64_t response_count;
+  uint64_t first_response_p50_ns, first_response_p99_ns;
 } tb200_loadgen_stats;
 
 int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out);
@@ -98,6 +106,13 @@ int tb200_stub_server_stop(tb200_stub_server* s);
 typedef struct tb200_grpc_stub_server tb200_grpc_stub_server;
 int tb200_grpc_stub_server_start(const char* host, int* port, const uint8_t* response,
                                  uint64_t response_bytes, tb200_grpc_stub_server** out);
+/* Stream mode of the same stub (ModelStreamInfer): every request message on a stream is answered
+ * with `responses_per_request - 1` copies of `response` and one `final_response` (serialised
+ * ModelStreamInferResponse messages; the caller marks the last one triton_final_response = true). */
+int tb200_grpc_stub_server_start_streaming(const char* host, int* port, const uint8_t* response,
+                                           uint64_t response_bytes, const uint8_t* final_response,
+                                           uint64_t final_bytes, int responses_per_request,
+                                           tb200_grpc_stub_server** out);
 int tb200_grpc_stub_server_stop(tb200_grpc_stub_server* s);
 
 /* A native KServe-v2 stand-in server for loopback load runs over CUDA shared memory

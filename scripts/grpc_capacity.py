@@ -28,3 +28,21 @@ for label, (ins, outs), shm in (("C4 bert gRPC raw_input_contents from pinned st
                           "slots_per_pass": round(w["device_slots"] / max(1, w["device_batches"]), 1),
                           "input_gbps": round(w["throughput"] * ss.in_bytes / 1e9, 2)}), flush=True)
 gstub.stop()
+# C5 as BASELINE quotes it: a ModelStreamInfer stream per connection, the decoupled model answers with 16 tokens
+from client_b200.perf.native import stream_token_responses
+resp, fin = stream_token_responses()
+sstub = GrpcStubServer(resp, final_response=fin, responses_per_request=16)
+ins, outs = c5
+for conc in levels:
+    ss = SlotSet(ins, [], conc, "none", 0, "random", 1, {"input_ids": (0, 128256)}, name_prefix="gstream%d" % conc, wire_prefixes=grpc_wire_prefixes(ins))
+    gen = NativeLoadGenerator(sstub.url, "llama3_8b", "", ss, conc, regenerate=True, validate=False, protocol="grpc-stream")
+    gen.start()
+    gen.window(0.5)
+    w = gen.window(2.0)
+    gen.stop()
+    ss.close()
+    print(json.dumps({"case": "C5 llama prompt on a ModelStreamInfer stream, 16 token responses per request", "concurrency": conc,
+                      "infer_per_s": round(w["throughput"]), "tokens_per_s": round(w["responses_per_s"]), "ttft_p50_us": w["ttft_p50_us"],
+                      "ttft_p99_us": w["ttft_p99_us"], "p50_us": w["p50_us"], "failed": w["failed"],
+                      "slots_per_pass": round(w["device_slots"] / max(1, w["device_batches"]), 1)}), flush=True)
+sstub.stop()

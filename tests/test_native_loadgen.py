@@ -200,3 +200,87 @@ def test_grpc_stub_server_with_grpcio_client_and_native_client():
         assert st.failed_request_count == 0 and st.completed_request_count > 1000
     finally:
         stub.stop()
+
+
+def _run_stream(host, port, reqs, seconds=0.4):
+    lib = _native.load()
+    n = len(reqs)
+    bufs = [ctypes.create_string_buffer(r, len(r)) for r in reqs]
+    cfg = LoadgenConfig()
+    cfg.host, cfg.port, cfg.concurrency, cfg.protocol = host.encode(), port, n, 2
+    cfg.requests = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
+    cfg.request_sizes = (ctypes.c_uint64 * n)(*[len(r) for r in reqs])
+    h = ctypes.c_void_p()
+    _native.check(lib.tb200_loadgen_create(ctypes.byref(cfg), ctypes.byref(h)))
+    _native.check(lib.tb200_loadgen_start(h))
+    st = LoadgenStats()
+    _native.check(lib.tb200_loadgen_window(h, seconds, ctypes.byref(st)))
+    lib.tb200_loadgen_stop(h)
+    lib.tb200_loadgen_destroy(h)
+    return st
+
+
+def test_grpc_stream_mode_against_grpcio_server():
+    """protocol 2: one ModelStreamInfer stream per connection (reference start_stream /
+    async_stream_infer).  Against the grpcio mock server: a decoupled model answers
+    max_tokens times per request and the request completes at the response flagged
+    triton_final_response; a plain model answers once; an unknown model fails the request
+    through error_message and the stream stays usable."""
+    import client_b200.grpc as grpcclient
+    from client_b200.grpc._utils import _get_inference_request
+
+    ins = [grpcclient.InferInput("input_ids", [1, 64], "INT32").set_data_from_numpy(np.arange(64, dtype=np.int32)[None, :])]
+    llama = _get_inference_request(model_name="llama3_8b", inputs=ins, model_version="", request_id="", outputs=None, sequence_id=0,
+                                   sequence_start=False, sequence_end=False, priority=0, timeout=None,
+                                   parameters={"max_tokens": 5}).SerializeToString()
+    z = np.zeros((1, 16), np.int32)
+    proc, _, grpc_port = start_server()
+    try:
+        st = _run_stream("127.0.0.1", grpc_port, [llama] * 3)
+        assert st.failed_request_count == 0 and st.completed_request_count > 10
+        assert st.response_count == 5 * st.completed_request_count
+        assert 0 < st.first_response_p50_ns <= st.p50_ns and st.first_response_p50_ns <= st.first_response_p99_ns
+        st = _run_stream("127.0.0.1", grpc_port, [_grpc_request("simple", [("INPUT0", z), ("INPUT1", z)])] * 2, 0.3)
+        assert st.failed_request_count == 0 and st.completed_request_count > 10 and st.response_count == st.completed_request_count
+        st = _run_stream("127.0.0.1", grpc_port, [_grpc_request("nope", [("INPUT0", z)])], 0.2)
+        assert st.completed_request_count == 0 and st.failed_request_count > 3
+    finally:
+        proc.terminate()
+        proc.wait(10)
+
+
+def test_grpc_stream_stub_with_grpcio_and_native_clients():
+    """The streaming mode of the canned-response gRPC stub: N responses per request message,
+    accepted by a real grpcio bidirectional stream; the native generator sustains the loop
+    (requests larger than one HTTP/2 frame, many more bytes than one stream window)."""
+    import threading
+
+    import client_b200.grpc as grpcclient
+    from client_b200.perf.native import GrpcStubServer, stream_token_responses
+
+    resp, fin = stream_token_responses()
+    stub = GrpcStubServer(resp, final_response=fin, responses_per_request=16)
+    a = np.arange(4096, dtype=np.int32)[None, :]
+    try:
+        got, done = [], threading.Event()
+
+        def on_response(result, error):
+            got.append((result, error))
+            if len(got) == 48:
+                done.set()
+
+        with grpcclient.InferenceServerClient(stub.url) as client:
+            client.start_stream(callback=on_response)
+            inp = grpcclient.InferInput("input_ids", [1, 4096], "INT32").set_data_from_numpy(a)
+            for _ in range(3):
+                client.async_stream_infer("anything", [inp])
+            assert done.wait(10)
+            client.stop_stream()
+        assert all(e is None for _, e in got)
+        finals = [r.get_response().parameters["triton_final_response"].bool_param for r, _ in got]
+        assert finals == ([False] * 15 + [True]) * 3
+        st = _run_stream(stub.host, stub.port, [_grpc_request("llama3_8b", [("input_ids", a)])] * 8, 0.5)
+        assert st.failed_request_count == 0 and st.completed_request_count > 2000  # > 32 MB on each stream
+        assert st.response_count == 16 * st.completed_request_count
+    finally:
+        stub.stop()

@@ -145,3 +145,14 @@ def test_native_grpc_wire_bytes_reach_the_server():
             assert [bytes(b) for b in request.raw_input_contents] == expect[key]
     finally:
         srv.stop(0)
+
+
+def test_native_engine_grpc_streaming(server):
+    """--engine native --streaming: BASELINE configs[4] (Llama prompt INT32[1,4096] on a
+    ModelStreamInfer stream, decoupled responses): the prompt is generated by the fill kernel
+    into the pinned message tail, TTFT and tokens/s come from the native transport."""
+    rows = cli.main(["-m", "llama3_8b", "-u", server["grpc"], "-i", "grpc", "--streaming", "--engine", "native", "--shape", "input_ids:1,4096",
+                     "--shared-memory", "none", "--concurrency-range", "4", "-p", "300", "-r", "3", "--request-parameter", "max_tokens:6:int", "--json"])
+    r = rows[0]
+    assert r["count"] > 3 and r["failed"] == 0 and r["input_bytes"] == 16384, r
+    assert r["responses"] == 6 * r["count"] and 0 < r["ttft_p50_us"] <= r["p50_us"], r
