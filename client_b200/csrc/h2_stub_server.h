@@ -289,7 +289,7 @@ class H2StubServer {
       if (answer && f.stream != 0) {
         const size_t base = out.size();
         out += response_;
-        PatchIds(&out, base, std::vector<size_t>(id_off_, id_off_ + 3), f.stream);
+        PatchIds(&out, base, id_off_, f.stream);
         calls_.fetch_add(1, std::memory_order_relaxed);
       }
     }
@@ -350,7 +350,7 @@ class H2StubServer {
   }
 
   std::string response_, hello_;
-  size_t id_off_[3] = {0, 0, 0};
+  std::vector<size_t> id_off_{0, 0, 0};
   bool streaming_ = false;
   std::string stream_reply_;          // DATA frames answering one request message (stream mode)
   std::vector<size_t> reply_id_off_;  // where their stream ids are

@@ -29,6 +29,8 @@ timeout -s KILL 600 ncu --set full --clock-control none -k regex:check_kernel -s
     python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-loopback > gpurun_out/ncu_check.log 2>&1
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:resize_pack -s 2 -c 1 -f -o gpurun_out/prof_resize \
     python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-loopback > gpurun_out/ncu_resize.log 2>&1
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:fill_unaligned -s 3 -c 1 -f -o gpurun_out/prof_fill_unaligned \
+    python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-loopback > gpurun_out/ncu_fill_unaligned.log 2>&1
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:deflate_chunk -s 2 -c 1 -f -o gpurun_out/prof_deflate \
     python scripts/deflate_probe.py > gpurun_out/ncu_deflate.log 2>&1
 fi

@@ -93,6 +93,7 @@ def main():
     full(tag, "prof_check.ncu-rep", "check_kernel")
     full(tag, "prof_resize.ncu-rep", "resize_pack_kernel")
     full(tag, "prof_deflate.ncu-rep", "deflate_chunk_kernel")
+    full(tag, "prof_fill_unaligned.ncu-rep", "fill_unaligned_kernel")
     for src, dst in (("bench.json", "bench_b200.json"), ("bench_ref.json", "bench_reference.json"),
                      ("fill_sweep.txt", "fill_sweep.txt"), ("store_bench.txt", "store_bench.txt"),
                      ("nvidia_smi.txt", "nvidia_smi.txt")):
