@@ -1104,7 +1104,7 @@ Error InferenceServerGrpcClient::StartInfer(std::shared_ptr<detail::GrpcCall>* o
                                             const std::vector<InferInput*>& inputs,
                                             const std::vector<const InferRequestedOutput*>& outputs, const Headers& headers,
                                             grpc_compression_algorithm compression_algorithm,
-                                            std::function<void(detail::GrpcCall*)> on_done) {
+                                            std::function<void(detail::GrpcCall*)> on_done, RequestTimers* timer) {
   std::shared_ptr<detail::GrpcChannel> channel;
   Error err = Channel(&channel);
   if (!err.IsOk()) return err;
@@ -1125,6 +1125,9 @@ Error InferenceServerGrpcClient::StartInfer(std::shared_ptr<detail::GrpcCall>* o
   call->metadata = headers;
   call->timeout_us = options.client_timeout_;
   call->on_done = std::move(on_done);
+  // the send timer covers the marshalling (as in the reference); it must be complete before the
+  // call can finish on the I/O thread
+  if (timer != nullptr) timer->CaptureTimestamp(RequestTimers::Kind::SEND_END);
   channel->Start(call, std::move(framed), true);
   *out = std::move(call);
   return Error::Success;
@@ -1152,8 +1155,7 @@ Error InferenceServerGrpcClient::Infer(InferResult** result, const InferOptions&
   timer.CaptureTimestamp(RequestTimers::Kind::REQUEST_START);
   timer.CaptureTimestamp(RequestTimers::Kind::SEND_START);  // marshalling, as in the reference
   std::shared_ptr<detail::GrpcCall> call;
-  Error err = StartInfer(&call, options, inputs, outputs, headers, compression_algorithm, nullptr);
-  timer.CaptureTimestamp(RequestTimers::Kind::SEND_END);
+  Error err = StartInfer(&call, options, inputs, outputs, headers, compression_algorithm, nullptr, &timer);
   if (!err.IsOk()) return err;
   call->Wait();
   timer.CaptureTimestamp(RequestTimers::Kind::RECV_START);
@@ -1214,8 +1216,8 @@ Error InferenceServerGrpcClient::AsyncInfer(OnCompleteFn callback, const InferOp
                              if (!stat.IsOk()) std::cerr << "Failed to update context stat: " << stat << std::endl;
                              callback(result);
                            });
-                         });
-  timer->CaptureTimestamp(RequestTimers::Kind::SEND_END);
+                         },
+                         timer.get());
   return err;
 }
 

@@ -176,7 +176,7 @@ class InferenceServerGrpcClient : public InferenceServerClient {
   Error StartInfer(std::shared_ptr<detail::GrpcCall>* call, const InferOptions& options,
                    const std::vector<InferInput*>& inputs, const std::vector<const InferRequestedOutput*>& outputs,
                    const Headers& headers, grpc_compression_algorithm compression_algorithm,
-                   std::function<void(detail::GrpcCall*)> on_done);
+                   std::function<void(detail::GrpcCall*)> on_done, RequestTimers* timer);
   void CallbackWorker();
   void Dispatch(std::function<void()> fn);
 

@@ -743,16 +743,20 @@ void transport_main(tb200_loadgen* lg, Transport* t) {
 // hand slots to the transport threads that own them: one eventfd write per thread
 void release_slots(tb200_loadgen* lg, const std::vector<int>& slots) {
   const int T = static_cast<int>(lg->transports.size());
-  std::vector<char> touched(static_cast<size_t>(T), 0);
-  for (int s : slots) {
-    Transport* t = lg->transports[static_cast<size_t>(s % T)].get();
-    std::lock_guard<std::mutex> lk(t->mu);
-    t->ready.push_back(s);
-    touched[static_cast<size_t>(s % T)] = 1;
-  }
+  // one lock and one wake-up per transport thread, not per slot
+  static thread_local std::vector<std::vector<int>> per;
+  per.resize(static_cast<size_t>(T));
+  for (auto& v : per) v.clear();
+  for (int s : slots) per[static_cast<size_t>(s % T)].push_back(s);
   const uint64_t one = 1;
   for (int i = 0; i < T; ++i) {
-    if (touched[static_cast<size_t>(i)] && write(lg->transports[static_cast<size_t>(i)]->evfd, &one, sizeof(one)) < 0) continue;
+    if (per[static_cast<size_t>(i)].empty()) continue;
+    Transport* t = lg->transports[static_cast<size_t>(i)].get();
+    {
+      std::lock_guard<std::mutex> lk(t->mu);
+      t->ready.insert(t->ready.end(), per[static_cast<size_t>(i)].begin(), per[static_cast<size_t>(i)].end());
+    }
+    if (write(t->evfd, &one, sizeof(one)) < 0) continue;
   }
 }
 

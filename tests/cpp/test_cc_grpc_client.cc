@@ -558,6 +558,82 @@ static void TestCompression(const std::string& url, bool expect_device) {
   delete in;
 }
 
+// The canned-response gRPC stub of libtb200 in this process: a server that goes away fails the
+// calls in flight with an Error and the next call opens a new connection (grpc_client.cc keeps
+// its channel; here a broken one is replaced, cached or not).
+extern "C" {
+struct tb200_grpc_stub_server;
+int tb200_grpc_stub_server_start(const char* host, int* port, const uint8_t* response, uint64_t response_bytes,
+                                 tb200_grpc_stub_server** out);
+int tb200_grpc_stub_server_stop(tb200_grpc_stub_server* s);
+}
+static void TestReconnect() {
+  inference::ModelInferResponse canned;
+  canned.set_model_name("stub");
+  auto* o = canned.add_outputs();
+  o->set_name("OUTPUT0");
+  o->set_datatype("INT32");
+  o->add_shape(2);
+  const int32_t vals[2] = {41, 42};
+  canned.add_raw_output_contents(vals, sizeof(vals));
+  const std::string bytes = canned.SerializeAsString();
+  int port = 0;
+  tb200_grpc_stub_server* srv = nullptr;
+  CHECK(tb200_grpc_stub_server_start("127.0.0.1", &port, reinterpret_cast<const uint8_t*>(bytes.data()), bytes.size(), &srv) == 0);
+  const std::string url = "127.0.0.1:" + std::to_string(port);
+  std::unique_ptr<tc::InferenceServerGrpcClient> client, second;
+  CHECK_OK(tc::InferenceServerGrpcClient::Create(&client, url));
+  CHECK_OK(tc::InferenceServerGrpcClient::Create(&second, url));
+  tc::InferInput* in;
+  tc::InferInput::Create(&in, "INPUT0", {2}, "INT32");
+  in->AppendRaw(reinterpret_cast<const uint8_t*>(vals), sizeof(vals));
+  tc::InferOptions opt("anything");
+  auto infer_ok = [&](tc::InferenceServerGrpcClient* c) {
+    tc::InferResult* r = nullptr;
+    tc::Error e = c->Infer(&r, opt, {in});
+    bool ok = e.IsOk();
+    const uint8_t* p = nullptr;
+    size_t n = 0;
+    if (ok) ok = r->RawData("OUTPUT0", &p, &n).IsOk() && n == 8 && memcmp(p, vals, 8) == 0;
+    delete r;
+    return ok;
+  };
+  CHECK(infer_ok(client.get()) && infer_ok(second.get()));
+  CHECK(client->GetNumCachedChannels() >= 1);  // both clients share the URL's channel
+  tb200_grpc_stub_server_stop(srv);
+  CHECK(!infer_ok(client.get()));              // the server is gone: an Error, not a hang
+  int again = port;
+  srv = nullptr;
+  CHECK(tb200_grpc_stub_server_start("127.0.0.1", &again, reinterpret_cast<const uint8_t*>(bytes.data()), bytes.size(), &srv) == 0 && again == port);
+  CHECK(infer_ok(client.get()) && infer_ok(second.get()));  // new connection, same client objects
+  // many requests in flight on one connection (stream ids advance by two each)
+  std::mutex mu;
+  std::condition_variable cv;
+  int done = 0, good = 0;
+  for (int i = 0; i < 200; ++i) {
+    CHECK_OK(client->AsyncInfer(
+        [&](tc::InferResult* r) {
+          std::lock_guard<std::mutex> lk(mu);
+          const uint8_t* p = nullptr;
+          size_t n = 0;
+          if (r->RequestStatus().IsOk() && r->RawData("OUTPUT0", &p, &n).IsOk() && n == 8) ++good;
+          ++done;
+          delete r;
+          cv.notify_all();
+        },
+        opt, {in}));
+  }
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    CHECK(cv.wait_for(lk, std::chrono::seconds(20), [&] { return done == 200; }));
+  }
+  CHECK(good == 200);
+  client.reset();
+  second.reset();
+  tb200_grpc_stub_server_stop(srv);
+  delete in;
+}
+
 int main(int argc, char** argv) {
   if (argc > 2 && std::string(argv[1]) == "--roundtrip") return RoundTrip(argv[2]);
   if (argc > 1 && std::string(argv[1]) == "--requests") {
@@ -573,6 +649,7 @@ int main(int argc, char** argv) {
     bool live = true;
     CHECK(!client->IsServerLive(&live).IsOk() && !live);  // nothing listens there
   }
+  TestReconnect();
   if (argc > 2 && std::string(argv[2]) == "slow") TestSlowServer(argv[1]);
   else if (argc > 2 && std::string(argv[2]) == "compress-gpu") TestCompression(argv[1], true);
   else if (argc > 2 && std::string(argv[2]) == "compress-nogpu") TestCompression(argv[1], false);

@@ -328,3 +328,25 @@ def test_reference_grpc_cudashm_example_if_prebuilt():
     finally:
         proc.terminate()
         proc.wait(10)
+
+
+def test_thread_sanitizer_clean(tmp_path):
+    """The client sources under -fsanitize=thread: offline checks (incl. the reconnect and
+    200-calls-in-flight cases against the in-process stub) and the loopback run report no race."""
+    cpp = os.path.join(ROOT, "client_b200", "cpp")
+    exe = str(tmp_path / "test_cc_grpc_tsan")
+    build = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-I" + os.path.join(cpp, "compat"), "-I" + cpp,
+                            "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_cc_grpc_client.cc"),
+                            os.path.join(cpp, "tb200_client.cc"), os.path.join(cpp, "tb200_grpc_client.cc"), "-o", exe,
+                            "-L" + LIBDIR, "-ltb200", "-Wl,-rpath," + LIBDIR, "-lpthread"], capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime for g++ here: " + build.stderr[-200:])
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0")
+    proc, _, grpc_port = start_server()
+    try:
+        r = subprocess.run([exe, "127.0.0.1:%d" % grpc_port], capture_output=True, text=True, timeout=300, env=env)
+    finally:
+        proc.terminate()
+        proc.wait(10)
+    assert r.returncode == 0 and "PASS (offline + loopback)" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "ThreadSanitizer" not in r.stdout + r.stderr, (r.stdout + r.stderr)[-3000:]
