@@ -46,7 +46,10 @@ LOADGEN_SIGNATURES = {
     "tb200_grpc_stub_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), c_vp, c_u64, ctypes.POINTER(c_vp)]),
     "tb200_grpc_stub_server_start_streaming": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), c_vp, c_u64, c_vp, c_u64, c_int, ctypes.POINTER(c_vp)]),
     "tb200_grpc_stub_server_stop": (c_int, [c_vp]),
+    "tb200_grpc_echo_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), ctypes.POINTER(c_vp)]),
+    "tb200_grpc_echo_server_stop": (c_int, [c_vp]),
     "tb200_mock_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_vp)]),
+    "tb200_mock_server_start2": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_vp)]),
     "tb200_mock_server_requests": (ctypes.c_uint64, [c_vp]),
     "tb200_mock_server_batches": (ctypes.c_uint64, [c_vp]),
     "tb200_mock_server_stop": (c_int, [c_vp]),

@@ -39,6 +39,7 @@
 
 #include "../../include/tb200_loadgen.h"
 #include "../cpp/pb.h"
+#include "grpc_server.h"
 #include "h2.h"
 #include "h2_stub_server.h"
 #include "http_server.h"
@@ -1067,6 +1068,9 @@ int tb200_grpc_stub_server_stop(tb200_grpc_stub_server* s);
 struct tb200_grpc_stub_server {
   tb200::H2StubServer h2;
 };
+struct tb200_grpc_echo_server {
+  tb200::EpollGrpcServer server;
+};
 
 extern "C" {
 
@@ -1100,6 +1104,43 @@ int tb200_grpc_stub_server_start_streaming(const char* host, int* port, const ui
     return lg_fail(TB200_ERR_IO, "cannot bind the gRPC stub server");
   }
   *out = s;
+  return TB200_OK;
+}
+
+int tb200_grpc_echo_server_start(const char* host, int* port, tb200_grpc_echo_server** out) {
+  if (host == nullptr || port == nullptr || out == nullptr) return lg_fail(TB200_ERR_INVALID, "NULL argument");
+  tb200_grpc_echo_server* s = new tb200_grpc_echo_server();
+  auto handler = [](uint64_t, const std::string& path, std::string&& message, bool is_message, bool half_close, tb200::GrpcReply* reply) {
+    const bool stream = path.size() >= 16 && path.compare(path.size() - 16, 16, "ModelStreamInfer") == 0;
+    if (path.find("/inference.GRPCInferenceService/") != 0) {
+      reply->status = 12;  // UNIMPLEMENTED
+      reply->status_message = "unknown service in " + path;
+      return true;
+    }
+    if (is_message) {
+      if (stream) {  // ModelStreamInferResponse{infer_response = the request bytes}
+        std::string wrapped;
+        tb200::pb::put_bytes(&wrapped, 2, message);
+        reply->messages.push_back(std::move(wrapped));
+      } else {
+        reply->messages.push_back(std::move(message));
+      }
+    }
+    reply->finish = stream ? half_close : true;
+    return true;
+  };
+  if (!s->server.Start(host, port, 4, handler)) {
+    delete s;
+    return lg_fail(TB200_ERR_IO, "cannot bind the gRPC echo server");
+  }
+  *out = s;
+  return TB200_OK;
+}
+
+int tb200_grpc_echo_server_stop(tb200_grpc_echo_server* s) {
+  if (s == nullptr) return TB200_OK;
+  s->server.Stop();
+  delete s;
   return TB200_OK;
 }
 

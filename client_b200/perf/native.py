@@ -215,6 +215,26 @@ class GrpcStubServer:
             self._h = None
 
 
+class GrpcEchoServer:
+    """tb200_grpc_echo_server (csrc/grpc_server.h): answers every call with its own request."""
+
+    def __init__(self, host="127.0.0.1", port=0):
+        self._lib = _native.load()
+        p = ctypes.c_int(port)
+        h = ctypes.c_void_p()
+        _native.check(self._lib.tb200_grpc_echo_server_start(host.encode(), ctypes.byref(p), ctypes.byref(h)))
+        self._h, self.host, self.port = h, host, p.value
+
+    @property
+    def url(self):
+        return "%s:%d" % (self.host, self.port)
+
+    def stop(self):
+        if getattr(self, "_h", None):
+            self._lib.tb200_grpc_echo_server_stop(self._h)
+            self._h = None
+
+
 def stream_token_responses(output_name="token", token=7):
     """(response, final_response) for GrpcStubServer's stream mode: ModelStreamInferResponse
     messages carrying one INT32[1,1] token, the last one flagged triton_final_response."""

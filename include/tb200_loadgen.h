@@ -115,6 +115,16 @@ int tb200_grpc_stub_server_start_streaming(const char* host, int* port, const ui
                                            tb200_grpc_stub_server** out);
 int tb200_grpc_stub_server_stop(tb200_grpc_stub_server* s);
 
+/* A gRPC echo server on the event-loop core the native model server uses (csrc/grpc_server.h):
+ * every unary call of inference.GRPCInferenceService is answered with its own request message
+ * (a ModelInferRequest parses as a ModelInferResponse: the fields line up), every message on a
+ * ModelStreamInfer stream with ModelStreamInferResponse{infer_response = that message}.  Test
+ * tooling: exercises HPACK decoding, message reassembly and flow control in both directions
+ * against real gRPC clients without a GPU. */
+typedef struct tb200_grpc_echo_server tb200_grpc_echo_server;
+int tb200_grpc_echo_server_start(const char* host, int* port, tb200_grpc_echo_server** out);
+int tb200_grpc_echo_server_stop(tb200_grpc_echo_server* s);
+
 /* A native KServe-v2 stand-in server for loopback load runs over CUDA shared memory
  * (csrc/mock_server.cu; tooling -- the reference has no server).  It opens
  * the client's cudaIpcMemHandle_t from the register call (protocol of
@@ -123,6 +133,13 @@ int tb200_grpc_stub_server_stop(tb200_grpc_stub_server* s);
  * on the mapped regions. */
 typedef struct tb200_mock_server tb200_mock_server;
 int tb200_mock_server_start(const char* host, int* port, int device_id, tb200_mock_server** out);
+/* ... and with a gRPC port beside the HTTP one (csrc/grpc_server.h + the generated message
+ * classes): health / metadata / config / repository index / CUDA shared memory RPCs, ModelInfer
+ * and ModelStreamInfer for `densenet_onnx`, `simple` (shared memory or tensors in the message),
+ * `bert_large` (2 x INT64[1,384] -> FP32[1,384], BASELINE configs[3]) and the decoupled
+ * `llama3_8b` (INT32[1,n] prompt -> max_tokens token responses, configs[4]); tensors that travel
+ * in messages are staged in pinned, device-mapped slabs (16 KiB of inputs per request). */
+int tb200_mock_server_start2(const char* host, int* port, int* grpc_port, int device_id, tb200_mock_server** out);
 uint64_t tb200_mock_server_requests(tb200_mock_server* s);
 uint64_t tb200_mock_server_batches(tb200_mock_server* s); /* kernel launches that served them */
 int tb200_mock_server_stop(tb200_mock_server* s);

@@ -342,11 +342,19 @@ def test_thread_sanitizer_clean(tmp_path):
     if build.returncode != 0:
         pytest.skip("no ThreadSanitizer runtime for g++ here: " + build.stderr[-200:])
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0")
-    proc, _, grpc_port = start_server()
-    try:
-        r = subprocess.run([exe, "127.0.0.1:%d" % grpc_port], capture_output=True, text=True, timeout=300, env=env)
-    finally:
-        proc.terminate()
-        proc.wait(10)
-    assert r.returncode == 0 and "PASS (offline + loopback)" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
-    assert "ThreadSanitizer" not in r.stdout + r.stderr, (r.stdout + r.stderr)[-3000:]
+    first = ""
+    for attempt in range(2):
+        proc, _, grpc_port = start_server()
+        try:
+            r = subprocess.run([exe, "127.0.0.1:%d" % grpc_port], capture_output=True, text=True, timeout=300, env=env)
+        finally:
+            proc.terminate()
+            proc.wait(10)
+        out = r.stdout + r.stderr
+        # a race report fails at once; a failed CHECK (the instrumented binary is ~10x slower, its
+        # time limits are the loopback test's) gets one more run, and both outputs are shown
+        assert "ThreadSanitizer" not in out, out[-3000:]
+        if r.returncode == 0 and "PASS (offline + loopback)" in r.stdout:
+            return
+        first = first or out[-1500:]
+    raise AssertionError("instrumented run failed twice:\n" + first + "\n---\n" + out[-1500:])
