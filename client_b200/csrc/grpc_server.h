@@ -41,6 +41,10 @@ struct GrpcReply {
   bool finish = true;                 // send the trailers after them (unary: always; stream: at half-close)
   int status = 0;                     // grpc-status of the trailers
   std::string status_message;         // grpc-message
+  // optional: fills in the fields above on the event-loop thread that owns the connection, right
+  // before the reply is queued -- response serialisation then runs on all loop threads instead of
+  // the one thread that called CompleteLater()
+  std::function<void(GrpcReply*)> build;
 };
 
 class EpollGrpcServer {
@@ -529,6 +533,11 @@ class EpollGrpcServer {
           }
           fds.clear();
           for (Done& d : done) {
+            if (d.reply.build) {
+              std::function<void(GrpcReply*)> build = std::move(d.reply.build);
+              d.reply.build = nullptr;
+              build(&d.reply);  // runs even when the connection is gone: it may own resources to release
+            }
             const uint32_t index = static_cast<uint32_t>((d.call_id >> 44) & 0x3FFF);
             if (index >= l->conns.size()) continue;
             Conn& c = l->conns[index];

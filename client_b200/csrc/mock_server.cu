@@ -329,16 +329,15 @@ bool shm_of(const std::map<std::string, inference::InferParameter>& params, ShmR
   return true;
 }
 
-// the responses of one finished ticket (device thread, after the launch)
-void grpc_complete(tb200_mock_server* s, const Ticket& t, bool ok) {
-  tb200::GrpcReply reply;
+// the responses of one finished ticket: formed on the event-loop thread of its connection
+void grpc_build_reply(tb200_mock_server* s, const Ticket& t, bool ok, tb200::GrpcReply* out) {
+  tb200::GrpcReply& reply = *out;
   reply.finish = !t.stream;
   const ModelInfo& m = models()[static_cast<size_t>(t.job.kind)];
   if (!ok) {
     if (t.stream) stream_error(&reply, t.id, "model execution failed");
     else grpc_error(&reply, 13, "model execution failed");
     give_slab(s, t.slab);
-    s->grpc.CompleteLater(t.conn_id, std::move(reply));
     return;
   }
   auto base = [&](inference::ModelInferResponse* r) {
@@ -398,7 +397,15 @@ void grpc_complete(tb200_mock_server* s, const Ticket& t, bool ok) {
     reply.messages.push_back(wrap(r));
   }
   give_slab(s, t.slab);
-  s->grpc.CompleteLater(t.conn_id, std::move(reply));
+}
+
+// device thread, after the launch: hand the ticket over, the loop thread serialises
+void grpc_complete(tb200_mock_server* s, Ticket&& t, bool ok) {
+  tb200::GrpcReply reply;
+  const uint64_t call_id = t.conn_id;
+  auto ticket = std::make_shared<Ticket>(std::move(t));
+  reply.build = [s, ticket, ok](tb200::GrpcReply* out) { grpc_build_reply(s, *ticket, ok, out); };
+  s->grpc.CompleteLater(call_id, std::move(reply));
 }
 
 // ModelInfer / one message of ModelStreamInfer.  true: *reply is the answer; false: parked.
@@ -712,7 +719,7 @@ void device_main(tb200_mock_server* s) {
       const bool ok = cudaStreamSynchronize(s->stream) == cudaSuccess;
       if (!ok) cudaGetLastError();
       for (size_t i = 0; i < n; ++i) {
-        const Ticket& t = batch[base + i];
+        Ticket& t = batch[base + i];
         if (t.grpc) {
           any_grpc = true;
           if (t.job.kind < 0) {  // the client half-closed its stream behind the last message
@@ -720,7 +727,7 @@ void device_main(tb200_mock_server* s) {
             end.finish = true;
             s->grpc.CompleteLater(t.conn_id, std::move(end));
           } else {
-            grpc_complete(s, t, ok);
+            grpc_complete(s, std::move(t), ok);
           }
         } else {
           any_http = true;
