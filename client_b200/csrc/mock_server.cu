@@ -187,6 +187,9 @@ struct Ticket {
   bool wire_out = false;  // the outputs travel in the response (second half of the slab)
   int tokens = 0;         // llama3_8b: responses to send
   std::string id;         // request id, echoed
+  // a stream's reply that needs no model run (an error message, the end of the stream): it still
+  // travels through the device thread's queue so that the replies of a stream keep request order
+  std::shared_ptr<tb200::GrpcReply> canned;
 };
 constexpr size_t kMaxBatch = 1024;
 // wire-mode gRPC requests: inputs are copied into, outputs read from, pinned device-mapped slabs
@@ -522,28 +525,38 @@ bool handle_grpc(tb200_mock_server* s, uint64_t call_id, const std::string& path
   }
   const std::string rpc = path.substr(kPrefix.size());
   if (rpc == "ModelStreamInfer") {
-    if (!is_message) {  // half-close without a message: end of the stream
-      reply->finish = half_close;
-      return true;
+    if (!is_message) {  // half-close without a message: the stream ends behind what is parked
+      Ticket fin;
+      fin.conn_id = call_id;
+      fin.grpc = true;
+      fin.stream = true;
+      fin.job.kind = -1;
+      submit_ticket(s, std::move(fin));
+      return false;
     }
     // the trailers follow when the client half-closes; answers of parked messages come first
     // because replies of one call are queued in order
     const bool now = grpc_infer(s, call_id, message, true, reply);
-    if (now) reply->finish = false;
-    if (half_close) {
-      // a message and the half-close in one frame: the stream ends after this message's replies
-      if (now) {
-        reply->finish = true;
-      } else {
-        Ticket fin;  // ordered behind the parked message
-        fin.conn_id = call_id;
-        fin.grpc = true;
-        fin.stream = true;
-        fin.job.kind = -1;
-        submit_ticket(s, std::move(fin));
-      }
+    if (now) {  // an error message: behind the replies of the messages parked before it
+      reply->finish = false;
+      Ticket err;
+      err.conn_id = call_id;
+      err.grpc = true;
+      err.stream = true;
+      err.job.kind = -1;
+      err.canned = std::make_shared<tb200::GrpcReply>(std::move(*reply));
+      *reply = tb200::GrpcReply();
+      submit_ticket(s, std::move(err));
     }
-    return now;
+    if (half_close) {  // a message and the half-close in one frame: the stream ends after its replies
+      Ticket fin;
+      fin.conn_id = call_id;
+      fin.grpc = true;
+      fin.stream = true;
+      fin.job.kind = -1;
+      submit_ticket(s, std::move(fin));
+    }
+    return false;
   }
   if (!is_message) {
     grpc_error(reply, 13, "unary call without a request message");
@@ -722,10 +735,10 @@ void device_main(tb200_mock_server* s) {
         Ticket& t = batch[base + i];
         if (t.grpc) {
           any_grpc = true;
-          if (t.job.kind < 0) {  // the client half-closed its stream behind the last message
+          if (t.job.kind < 0) {  // no model run: a canned stream reply, or the end of the stream
             tb200::GrpcReply end;
             end.finish = true;
-            s->grpc.CompleteLater(t.conn_id, std::move(end));
+            s->grpc.CompleteLater(t.conn_id, t.canned ? std::move(*t.canned) : std::move(end));
           } else {
             grpc_complete(s, std::move(t), ok);
           }
