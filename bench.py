@@ -528,12 +528,14 @@ def loopback_extra(device, seconds=1.5):
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
-    srv = subprocess.Popen([sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(device)],
+    srv = subprocess.Popen([sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(device), "--grpc-port", "0"],
                            cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     out = {"server": "client_b200.testing.native_server (own process, CUDA IPC, batched model kernel)", "mps": False, "levels": []}
     try:
-        if "listening" not in srv.stdout.readline():
+        hello = srv.stdout.readline()
+        if "listening" not in hello:
             raise RuntimeError("native server did not start")
+        grpc_url = hello.split("grpc=")[1].strip() if "grpc=" in hello else None
         url = "127.0.0.1:%d" % port
         control = httpclient.InferenceServerClient(url)
         for conc, window in ((1, 0), (64, 150), (256, 150)):
@@ -581,6 +583,11 @@ def loopback_extra(device, seconds=1.5):
         cudashm.destroy_shared_memory_region(in_h)
         cudashm.destroy_shared_memory_region(out_h)
         control.close()
+        if grpc_url:
+            try:
+                out["grpc"] = _grpc_loopback_levels(grpc_url)
+            except Exception as ex:
+                out["grpc"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     finally:
         srv.terminate()
         try:
@@ -591,6 +598,29 @@ def loopback_extra(device, seconds=1.5):
         out["under_mps"] = loopback_under_mps(device)
     except Exception as ex:
         out["under_mps"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    return out
+
+
+def _grpc_loopback_levels(grpc_url, env=None):
+    """BASELINE configs[3] / [4] against the native server's gRPC port: the CLI's native engine
+    (tensors generated by the fill kernel into the message tails; C5 on ModelStreamInfer streams
+    with 16 token responses per prompt)."""
+    out = {}
+    for key, argv in (("c4_bert_large_grpc", ["-m", "bert_large"]),
+                      ("c5_llama3_stream", ["-m", "llama3_8b", "--streaming", "--shape", "input_ids:1,4096", "--request-parameter", "max_tokens:16:int"])):
+        r = subprocess.run([sys.executable, "-m", "client_b200.perf", "-u", grpc_url, "-i", "grpc", "--shared-memory", "none", "--engine", "native",
+                            "--concurrency-range", "1:256:16x", "-p", "600", "-r", "4", "--json"] + argv,
+                           cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+        rows = []
+        for line in r.stdout.splitlines():
+            if line.startswith("{"):
+                w = json.loads(line)
+                row = {"concurrency": w["concurrency"], "infer_per_s": round(w["throughput"], 1), "p50_us": round(w["p50_us"], 1),
+                       "p99_us": round(w["p99_us"], 1), "failed": int(w["failed"])}
+                if "ttft_p50_us" in w:
+                    row.update(ttft_p50_us=round(w["ttft_p50_us"], 1), tokens_per_s=round(w["responses_per_s"], 1))
+                rows.append(row)
+        out[key] = rows if rows else {"error": (r.stdout + r.stderr)[-300:]}
     return out
 
 
@@ -613,9 +643,10 @@ def loopback_under_mps(device):
         with socket.socket() as sk:
             sk.bind(("127.0.0.1", 0))
             port = sk.getsockname()[1]
-        srv = subprocess.Popen([sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(device)],
+        srv = subprocess.Popen([sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(device), "--grpc-port", "0"],
                                cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        if "listening" not in srv.stdout.readline():
+        hello = srv.stdout.readline()
+        if "listening" not in hello:
             raise RuntimeError("native server did not start under MPS")
         r = subprocess.run([sys.executable, "-m", "client_b200.perf", "-m", "densenet_onnx", "-u", "127.0.0.1:%d" % port,
                             "--shared-memory", "cuda", "--engine", "native", "--concurrency-range", "1:256:4x",
@@ -628,7 +659,13 @@ def loopback_under_mps(device):
                                "p99_us": round(w["p99_us"], 1), "failed": int(w["failed"]), "nonfinite": int(w["nonfinite"])})
         if not levels:
             raise RuntimeError("no result rows: " + (r.stdout + r.stderr)[-300:])
-        return {"available": True, "levels": levels}
+        res = {"available": True, "levels": levels}
+        if "grpc=" in hello:
+            try:
+                res["grpc"] = _grpc_loopback_levels(hello.split("grpc=")[1].strip(), env)
+            except Exception as ex:
+                res["grpc"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        return res
     finally:
         if srv is not None:
             srv.terminate()
