@@ -151,6 +151,7 @@ struct Conn {
   std::string rx_msg;               // response messages being reassembled from DATA frames
   uint64_t t_first = 0;             // first response of the request in flight
   uint32_t responses = 0;
+  uint32_t image = 0;               // look-ahead: which of the slot's staging images goes out next
 };
 
 struct Transport {
@@ -170,6 +171,8 @@ struct tb200_loadgen {
   std::vector<std::vector<uint8_t>> requests;
   std::vector<const uint8_t*> tails;  // borrowed (pinned staging), may be empty
   std::vector<uint64_t> tail_sizes;
+  uint32_t lookahead = 1;             // staging images per slot (wire mode)
+  uint64_t tail_stride = 0;
   bool passthrough = false;           // no device work per request: workers keep their slot
   bool grpc = false;                  // requests[] are ModelInferRequest bytes sent as unary gRPC calls
   bool grpc_stream = false;           // ... or as messages of one ModelStreamInfer stream per connection
@@ -308,7 +311,7 @@ bool conn_send(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
 int grpc_build(tb200_loadgen* lg, Conn& c) {
   namespace h2 = tb200::h2;
   const std::vector<uint8_t>& head = lg->requests[c.slot];
-  const uint8_t* tail = lg->tails.empty() ? nullptr : lg->tails[c.slot];
+  const uint8_t* tail = lg->tails.empty() ? nullptr : lg->tails[c.slot] + static_cast<uint64_t>(c.image) * lg->tail_stride;
   const size_t tail_size = lg->tails.empty() ? 0 : static_cast<size_t>(lg->tail_sizes[c.slot]);
   const size_t message = head.size() + tail_size;
   const size_t payload = 5 + message;
@@ -447,7 +450,8 @@ void request_start(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, boo
       const std::vector<uint8_t>& req = lg->requests[c.slot];
       c.tx.push_back(iovec{const_cast<uint8_t*>(req.data()), req.size()});
       if (!lg->tails.empty() && lg->tail_sizes[c.slot] != 0) {
-        c.tx.push_back(iovec{const_cast<uint8_t*>(lg->tails[c.slot]), static_cast<size_t>(lg->tail_sizes[c.slot])});
+        c.tx.push_back(iovec{const_cast<uint8_t*>(lg->tails[c.slot]) + static_cast<uint64_t>(c.image) * lg->tail_stride,
+                             static_cast<size_t>(lg->tail_sizes[c.slot])});
       }
     }
     if (conn_send(lg, t, c, index)) return;
@@ -476,7 +480,10 @@ void request_done(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool
       t->stats.failed += 1;
     }
   }
-  if (lg->passthrough) {
+  // look-ahead: the slot's next staging image is ready to go, no device work needed yet
+  const bool more_images = !lg->passthrough && ok && c.image + 1 < lg->lookahead;
+  if (more_images) ++c.image;
+  if (lg->passthrough || more_images) {
     if (lg->stop.load(std::memory_order_relaxed)) return;
     if (ok) {
       request_start(lg, t, c, index, false);
@@ -490,6 +497,7 @@ void request_done(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool
       if (write(t->evfd, &one, sizeof(one)) < 0) return;
     }
   } else {
+    c.image = 0;
     lg->returned.push(c.slot);
   }
 }
@@ -873,6 +881,12 @@ int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out) {
   lg->seed = cfg->seed;
   lg->regenerate = cfg->regenerate != 0;
   lg->device_window_ns = 1000ull * cfg->device_window_us;
+  lg->lookahead = cfg->lookahead > 1 ? cfg->lookahead : 1;
+  lg->tail_stride = cfg->tail_stride;
+  if (lg->lookahead > 1 && (cfg->tails == nullptr || cfg->tail_stride == 0)) {
+    delete lg;
+    return lg_fail(TB200_ERR_INVALID, "lookahead needs tails and a tail_stride");
+  }
   lg->grpc = cfg->protocol == 1 || cfg->protocol == 2;
   lg->grpc_stream = cfg->protocol == 2;
   if (cfg->protocol > 2) {

@@ -68,8 +68,15 @@ class SlotSet:
     """Per-slot input/output buffers and their device job tables."""
 
     def __init__(self, inputs, outputs, slots, shared_memory, device_id, input_data, seed, token_range=None,
-                 name_prefix="tb200", staging=None, wire_prefixes=None):
+                 name_prefix="tb200", staging=None, wire_prefixes=None, lookahead=1):
         self.inputs, self.outputs, self.slots = inputs, outputs, slots
+        # wire mode + native engine: every slot owns `lookahead` staging images that one device
+        # pass generates together; the transport sends them one after the other and returns the
+        # slot to the device thread only when all are used (every request still carries fresh
+        # data, the device is visited once per `lookahead` requests)
+        self.lookahead = max(1, int(lookahead))
+        if self.lookahead > 1 and shared_memory != "none":
+            raise ValueError("lookahead only applies to --shared-memory none")
         self.shared_memory, self.device_id = shared_memory, device_id
         self.input_data, self.seed = input_data, seed
         self.in_bytes = sum(t.nbytes for t in inputs)
@@ -108,27 +115,27 @@ class SlotSet:
             # CPU-only machines inject their own ``staging`` object.)
             if staging is not None:
                 self._staging = staging
-                staging.allocate(max(slots * self.wire_stride, 16))
+                staging.allocate(max(slots * self.lookahead * self.wire_stride, 16))
             else:
                 from ..device import DeviceOps, HostBuffer
 
                 self._ops = DeviceOps(_native.Context(device_id))
-                self._wire = HostBuffer(max(slots * self.wire_stride, 16))
+                self._wire = HostBuffer(max(slots * self.lookahead * self.wire_stride, 16))
                 self.in_base = self._wire.device_ptr
             if any(self._prefixes):
-                for s in range(slots):
+                for s, g in ((s, g) for s in range(slots) for g in range(self.lookahead)):
                     for i, b in enumerate(self._prefixes):
-                        off = self.input_offset(s, i) - len(b)
+                        off = self.input_offset(s, i, g) - len(b)
                         view = self._staging.view(off, len(b)) if self._staging is not None else self._wire.view(off, len(b))
                         view[:] = b
         self._results = None
         self._result_view = None
 
     # -- layout ------------------------------------------------------------------------
-    def input_offset(self, slot, index):
+    def input_offset(self, slot, index, generation=0):
         if self.shared_memory == "none":
             before = sum(len(self._prefixes[k]) + self.inputs[k].nbytes for k in range(index))
-            return slot * self.wire_stride + before + len(self._prefixes[index])
+            return (slot * self.lookahead + generation) * self.wire_stride + before + len(self._prefixes[index])
         return slot * self.in_bytes + sum(t.nbytes for t in self.inputs[:index])
 
     def output_offset(self, slot, index):
@@ -146,7 +153,8 @@ class SlotSet:
         from ..device import make_fill_job
 
         jobs = []
-        for s in slot_ids:
+        for s, g in ((s, g) for s in slot_ids for g in range(self.lookahead)):
+            image = s * self.lookahead + g  # == s without lookahead: stream ids as before
             for i, t in enumerate(self.inputs):
                 mode = "zero" if self.input_data == "zero" else "random"
                 lo, hi = 0.0, None
@@ -156,11 +164,11 @@ class SlotSet:
                 if t.datatype == "BYTES":
                     # zero data for strings = empty-content strings is not expressible at a
                     # fixed byte size; perf_analyzer sends random strings in both modes
-                    jobs.append(make_fill_job(self.in_base + self.input_offset(s, i), t.nbytes, "BYTES",
-                                              stream_id=(s << 8) | i, string_length=t.string_length))
+                    jobs.append(make_fill_job(self.in_base + self.input_offset(s, i, g), t.nbytes, "BYTES",
+                                              stream_id=(image << 8) | i, string_length=t.string_length))
                     continue
-                jobs.append(make_fill_job(self.in_base + self.input_offset(s, i), t.nbytes, t.datatype,
-                                          stream_id=(s << 8) | i, mode=mode, low=lo, high=hi))
+                jobs.append(make_fill_job(self.in_base + self.input_offset(s, i, g), t.nbytes, t.datatype,
+                                          stream_id=(image << 8) | i, mode=mode, low=lo, high=hi))
         return jobs
 
     def generate(self, slot_ids):
@@ -168,7 +176,7 @@ class SlotSet:
         if not slot_ids:
             return
         if self._staging is not None:
-            self._staging.fill([(self.input_offset(s, i), t) for s in slot_ids for i, t in enumerate(self.inputs)],
+            self._staging.fill([(self.input_offset(s, i, g), t) for s in slot_ids for g in range(self.lookahead) for i, t in enumerate(self.inputs)],
                                self.input_data, self.seed + self.epoch)
         else:
             self._ops.fill(self._fill_jobs(slot_ids), seed=self.seed, epoch=self.epoch)

@@ -79,7 +79,7 @@ class NativeLoadGenerator:
             if ss.shared_memory == "none":
                 json_size = len(body)
                 reqs.append(frame_http_request(self.host, self.port, uri, body, json_size, head_only_bytes=ss.in_bytes))
-                tails.append((ss._wire.host_ptr + slot * ss.wire_stride, ss.wire_stride))
+                tails.append((ss._wire.host_ptr + slot * ss.lookahead * ss.wire_stride, ss.wire_stride))
             else:
                 reqs.append(frame_http_request(self.host, self.port, uri, body, json_size))
         n = concurrency
@@ -97,7 +97,7 @@ class NativeLoadGenerator:
         if ss._ops is not None:
             cfg.ctx = ss._ops.ctx.handle
             fills = ss._fill_jobs(list(range(n)))
-            per = len(ss.inputs)
+            per = len(ss.inputs) * ss.lookahead
             cfg.fill_jobs = (_native.FillJob * len(fills))(*fills)
             cfg.fill_jobs_per_slot = per
             cfg.seed = ss.seed
@@ -115,6 +115,8 @@ class NativeLoadGenerator:
                 cfg.check_jobs_per_slot = len(ss.outputs)
                 cfg.results = self._results.device_ptr
         cfg.device_window_us = int(device_window_us)
+        cfg.lookahead = ss.lookahead
+        cfg.tail_stride = ss.wire_stride
         cfg.protocol = {"http": 0, "grpc": 1, "grpc-stream": 2}[protocol]
         self._keep.append(cfg)
         h = ctypes.c_void_p()
@@ -149,7 +151,7 @@ class NativeLoadGenerator:
             if ss.shared_memory == "none":
                 if ss.wire_stride == ss.in_bytes and ss.in_bytes:
                     raise ValueError("the SlotSet of a gRPC wire-mode run needs wire_prefixes=grpc_wire_prefixes(inputs)")
-                tails.append((ss._wire.host_ptr + slot * ss.wire_stride, ss.wire_stride))
+                tails.append((ss._wire.host_ptr + slot * ss.lookahead * ss.wire_stride, ss.wire_stride))
         return reqs, tails
 
     def start(self):

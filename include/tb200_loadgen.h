@@ -63,6 +63,13 @@ typedef struct tb200_loadgen_config {
    * the time to the first response is reported */
   uint32_t protocol;
   const char* grpc_path; /* NULL -> "/inference.GRPCInferenceService/ModelInfer" */
+  /* wire mode look-ahead: tails[s] is the first of `lookahead` staging images, `tail_stride`
+   * bytes apart, each tail_sizes[s] long; fill_jobs_per_slot then covers all of them.  The
+   * transport sends image 0, 1, ... with consecutive requests and hands the slot back to the
+   * device thread only after the last one, so every request carries freshly generated tensors
+   * while the device is visited once per `lookahead` requests.  0 or 1 = off. */
+  uint32_t lookahead;
+  uint64_t tail_stride;
 } tb200_loadgen_config;
 
 typedef struct tb200_loadgen_stats {

@@ -100,7 +100,8 @@ def test_native_engine_grpc(server):
     assert rows[0]["count"] > 3 and rows[0]["failed"] == 0, rows
 
 
-def test_native_grpc_wire_bytes_reach_the_server():
+@pytest.mark.parametrize("lookahead", [1, 4])
+def test_native_grpc_wire_bytes_reach_the_server(lookahead):
     """What a real grpcio server receives in raw_input_contents is bit-for-bit what the fill
     kernel generates for that slot: the oracle recomputes it from the job's seed and stream."""
     from concurrent import futures
@@ -127,15 +128,15 @@ def test_native_grpc_wire_bytes_reach_the_server():
     ranges = {"input_ids": (0, 30522), "attention_mask": (0, 2)}
     try:
         ss = SlotSet(ins, [TensorSpec("logits", "FP32", [1, 2])], 8, "none", 0, "random", 5, ranges,
-                     name_prefix="grpcwire", wire_prefixes=grpc_wire_prefixes(ins))
+                     name_prefix="grpcwire", wire_prefixes=grpc_wire_prefixes(ins), lookahead=lookahead)
         gen = NativeLoadGenerator("127.0.0.1:%d" % port, "bert_large", "", ss, 8, regenerate=False, validate=False, protocol="grpc")
         gen.start()
         w = gen.window(0.5)
         gen.stop()
-        assert w["failed"] == 0 and w["count"] >= 8, w
+        assert w["failed"] == 0 and w["count"] >= 8 * lookahead, w
         expect = {}
-        for slot in range(8):
-            tensors = [cref.fill(t.nbytes, t.datatype, seed=ss.seed, stream=(slot << 8) | i, ilo=ranges[t.name][0],
+        for image in range(8 * lookahead):  # with look-ahead every slot cycles through its staging images
+            tensors = [cref.fill(t.nbytes, t.datatype, seed=ss.seed, stream=(image << 8) | i, ilo=ranges[t.name][0],
                                  irange=ranges[t.name][1] - ranges[t.name][0]).tobytes() for i, t in enumerate(ins)]
             expect[tensors[0][:16]] = tensors
         ss.close()
@@ -156,3 +157,13 @@ def test_native_engine_grpc_streaming(server):
     r = rows[0]
     assert r["count"] > 3 and r["failed"] == 0 and r["input_bytes"] == 16384, r
     assert r["responses"] == 6 * r["count"] and 0 < r["ttft_p50_us"] <= r["p50_us"], r
+
+
+def test_lookahead_regenerates_every_image(server):
+    """--lookahead 4 with per-request data: the device thread is visited once per 4 requests and
+    regenerates all 4 staging images of the returned slots in that pass."""
+    rows = cli.main(["-m", "bert_large", "-u", server["grpc"], "-i", "grpc", "--shared-memory", "none", "--engine", "native", "--lookahead", "4",
+                     "--concurrency-range", "4", "-p", "300", "-r", "3", "--json"])
+    r = rows[0]
+    assert r["count"] > 3 and r["failed"] == 0 and r["input_bytes"] == 6144, r
+    assert 0 < r["device_slots"] <= r["count"] / 4 + 8, r
