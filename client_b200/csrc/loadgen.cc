@@ -480,9 +480,15 @@ void request_done(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool
       t->stats.failed += 1;
     }
   }
-  // look-ahead: the slot's next staging image is ready to go, no device work needed yet
-  const bool more_images = !lg->passthrough && ok && c.image + 1 < lg->lookahead;
-  if (more_images) ++c.image;
+  // look-ahead: the slot's next staging image is ready to go, no device work needed until the
+  // last one is used (without per-request device work the images are simply cycled)
+  bool more_images = false;
+  if (ok && lg->lookahead > 1) {
+    c.image = (c.image + 1) % lg->lookahead;
+    more_images = c.image != 0;
+  } else if (!ok) {
+    c.image = 0;
+  }
   if (lg->passthrough || more_images) {
     if (lg->stop.load(std::memory_order_relaxed)) return;
     if (ok) {
@@ -497,7 +503,6 @@ void request_done(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, bool
       if (write(t->evfd, &one, sizeof(one)) < 0) return;
     }
   } else {
-    c.image = 0;
     lg->returned.push(c.slot);
   }
 }
