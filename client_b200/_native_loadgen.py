@@ -18,7 +18,7 @@ class LoadgenConfig(ctypes.Structure):
         ("seed", c_u64), ("regenerate", c_int),
         ("check_jobs", ctypes.POINTER(CheckJob)), ("check_jobs_per_slot", c_int), ("results", c_vp),
         ("device_window_us", ctypes.c_uint32), ("protocol", ctypes.c_uint32), ("grpc_path", ctypes.c_char_p),
-        ("lookahead", ctypes.c_uint32), ("tail_stride", c_u64),
+        ("lookahead", ctypes.c_uint32), ("tail_stride", c_u64), ("requests_per_slot", ctypes.c_uint32),
     ]
 
 

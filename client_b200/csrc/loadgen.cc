@@ -171,7 +171,8 @@ struct tb200_loadgen {
   std::vector<std::vector<uint8_t>> requests;
   std::vector<const uint8_t*> tails;  // borrowed (pinned staging), may be empty
   std::vector<uint64_t> tail_sizes;
-  uint32_t lookahead = 1;             // staging images per slot (wire mode)
+  uint32_t lookahead = 1;             // staging images per slot
+  uint32_t rps = 1;                   // pre-formed requests per slot (shared-memory look-ahead: one per image)
   uint64_t tail_stride = 0;
   bool passthrough = false;           // no device work per request: workers keep their slot
   bool grpc = false;                  // requests[] are ModelInferRequest bytes sent as unary gRPC calls
@@ -310,7 +311,7 @@ bool conn_send(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
 // Returns 0 ok, 1 must wait for connection window, -1 cannot be sent at all.
 int grpc_build(tb200_loadgen* lg, Conn& c) {
   namespace h2 = tb200::h2;
-  const std::vector<uint8_t>& head = lg->requests[c.slot];
+  const std::vector<uint8_t>& head = lg->requests[static_cast<size_t>(c.slot) * lg->rps + (lg->rps > 1 ? c.image : 0)];
   const uint8_t* tail = lg->tails.empty() ? nullptr : lg->tails[c.slot] + static_cast<uint64_t>(c.image) * lg->tail_stride;
   const size_t tail_size = lg->tails.empty() ? 0 : static_cast<size_t>(lg->tail_sizes[c.slot]);
   const size_t message = head.size() + tail_size;
@@ -447,7 +448,7 @@ void request_start(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index, boo
       c.buf.clear();
       c.tx.clear();
       c.tx_idx = 0;
-      const std::vector<uint8_t>& req = lg->requests[c.slot];
+      const std::vector<uint8_t>& req = lg->requests[static_cast<size_t>(c.slot) * lg->rps + (lg->rps > 1 ? c.image : 0)];
       c.tx.push_back(iovec{const_cast<uint8_t*>(req.data()), req.size()});
       if (!lg->tails.empty() && lg->tail_sizes[c.slot] != 0) {
         c.tx.push_back(iovec{const_cast<uint8_t*>(lg->tails[c.slot]) + static_cast<uint64_t>(c.image) * lg->tail_stride,
@@ -878,8 +879,10 @@ int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out) {
   lg->host = cfg->host;
   lg->port = cfg->port;
   lg->concurrency = cfg->concurrency;
-  lg->requests.resize(cfg->concurrency);
-  for (int s = 0; s < cfg->concurrency; ++s) {
+  lg->rps = cfg->requests_per_slot > 1 ? cfg->requests_per_slot : 1;
+  const size_t nreq = static_cast<size_t>(cfg->concurrency) * lg->rps;
+  lg->requests.resize(nreq);
+  for (size_t s = 0; s < nreq; ++s) {
     lg->requests[s].assign(cfg->requests[s], cfg->requests[s] + cfg->request_sizes[s]);
   }
   lg->ctx = cfg->ctx;
@@ -888,9 +891,13 @@ int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out) {
   lg->device_window_ns = 1000ull * cfg->device_window_us;
   lg->lookahead = cfg->lookahead > 1 ? cfg->lookahead : 1;
   lg->tail_stride = cfg->tail_stride;
-  if (lg->lookahead > 1 && (cfg->tails == nullptr || cfg->tail_stride == 0)) {
+  if (lg->lookahead > 1 && (cfg->tails == nullptr || cfg->tail_stride == 0) && lg->rps != lg->lookahead) {
     delete lg;
-    return lg_fail(TB200_ERR_INVALID, "lookahead needs tails and a tail_stride");
+    return lg_fail(TB200_ERR_INVALID, "lookahead needs tails with a tail_stride, or one request per image (requests_per_slot)");
+  }
+  if (lg->rps > 1 && lg->rps != lg->lookahead) {
+    delete lg;
+    return lg_fail(TB200_ERR_INVALID, "requests_per_slot must equal lookahead");
   }
   lg->grpc = cfg->protocol == 1 || cfg->protocol == 2;
   lg->grpc_stream = cfg->protocol == 2;

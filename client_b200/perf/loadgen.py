@@ -75,8 +75,8 @@ class SlotSet:
         # slot to the device thread only when all are used (every request still carries fresh
         # data, the device is visited once per `lookahead` requests)
         self.lookahead = max(1, int(lookahead))
-        if self.lookahead > 1 and shared_memory != "none":
-            raise ValueError("lookahead only applies to --shared-memory none")
+        if self.lookahead > 1 and shared_memory == "system":
+            raise ValueError("lookahead applies to --shared-memory none / cuda")
         self.shared_memory, self.device_id = shared_memory, device_id
         self.input_data, self.seed = input_data, seed
         self.in_bytes = sum(t.nbytes for t in inputs)
@@ -99,8 +99,8 @@ class SlotSet:
 
             self._cudashm = cudashm
             self._ops = DeviceOps(_native.Context(device_id))
-            self.in_region = cudashm.create_shared_memory_region(self.prefix + "_in", max(slots * self.in_bytes, 16), device_id)
-            self.out_region = cudashm.create_shared_memory_region(self.prefix + "_out", max(slots * self.out_bytes, 16), device_id)
+            self.in_region = cudashm.create_shared_memory_region(self.prefix + "_in", max(slots * self.lookahead * self.in_bytes, 16), device_id)
+            self.out_region = cudashm.create_shared_memory_region(self.prefix + "_out", max(slots * self.lookahead * self.out_bytes, 16), device_id)
             self.in_base, self.out_base = self.in_region._base_addr, self.out_region._base_addr
         elif shared_memory == "system":
             from ..utils import shared_memory as sysshm
@@ -136,10 +136,10 @@ class SlotSet:
         if self.shared_memory == "none":
             before = sum(len(self._prefixes[k]) + self.inputs[k].nbytes for k in range(index))
             return (slot * self.lookahead + generation) * self.wire_stride + before + len(self._prefixes[index])
-        return slot * self.in_bytes + sum(t.nbytes for t in self.inputs[:index])
+        return (slot * self.lookahead + generation) * self.in_bytes + sum(t.nbytes for t in self.inputs[:index])
 
-    def output_offset(self, slot, index):
-        return slot * self.out_bytes + sum(t.nbytes for t in self.outputs[:index])
+    def output_offset(self, slot, index, generation=0):
+        return (slot * self.lookahead + generation) * self.out_bytes + sum(t.nbytes for t in self.outputs[:index])
 
     def input_bytes(self, slot, index):
         """Host view of a generated input (wire / system-shm modes)."""
@@ -221,8 +221,8 @@ class SlotSet:
     # -- server registration --------------------------------------------------------------------
     def register(self, client):
         if self.shared_memory == "cuda":
-            client.register_cuda_shared_memory(self.prefix + "_in", self._cudashm.get_raw_handle(self.in_region), self.device_id, max(self.slots * self.in_bytes, 16))
-            client.register_cuda_shared_memory(self.prefix + "_out", self._cudashm.get_raw_handle(self.out_region), self.device_id, max(self.slots * self.out_bytes, 16))
+            client.register_cuda_shared_memory(self.prefix + "_in", self._cudashm.get_raw_handle(self.in_region), self.device_id, max(self.slots * self.lookahead * self.in_bytes, 16))
+            client.register_cuda_shared_memory(self.prefix + "_out", self._cudashm.get_raw_handle(self.out_region), self.device_id, max(self.slots * self.lookahead * self.out_bytes, 16))
         elif self.shared_memory == "system":
             client.register_system_shared_memory(self.prefix + "_in", "/" + self.prefix + "_in", max(self.slots * self.in_bytes, 16))
             client.register_system_shared_memory(self.prefix + "_out", "/" + self.prefix + "_out", max(self.slots * self.out_bytes, 16))

@@ -60,12 +60,14 @@ class NativeLoadGenerator:
         grpc_like = protocol in ("grpc", "grpc-stream")
         if grpc_like:
             reqs, tails = self._grpc_requests(model_name, model_version, ss, concurrency, request_parameters)
-        for slot in range(0 if grpc_like else concurrency):
+        # requests that name shared-memory offsets exist once per staging image of a slot
+        self._rps = ss.lookahead if ss.shared_memory == "cuda" else 1
+        for slot, gen in ((s, g) for s in range(0 if grpc_like else concurrency) for g in range(self._rps)):
             inputs, outputs = [], []
             for i, t in enumerate(ss.inputs):
                 inp = InferInput(t.name, t.shape, t.datatype)
                 if ss.shared_memory in ("cuda", "system"):
-                    inp.set_shared_memory(ss.prefix + "_in", t.nbytes, offset=ss.input_offset(slot, i))
+                    inp.set_shared_memory(ss.prefix + "_in", t.nbytes, offset=ss.input_offset(slot, i, gen))
                 else:
                     inp._parameters["binary_data_size"] = t.nbytes  # bytes follow from the pinned tail
                     inp._raw_data = b""
@@ -73,7 +75,7 @@ class NativeLoadGenerator:
             for i, t in enumerate(ss.outputs):
                 out = InferRequestedOutput(t.name)
                 if ss.shared_memory in ("cuda", "system"):
-                    out.set_shared_memory(ss.prefix + "_out", t.nbytes, offset=ss.output_offset(slot, i))
+                    out.set_shared_memory(ss.prefix + "_out", t.nbytes, offset=ss.output_offset(slot, i, gen))
                 outputs.append(out)
             body, json_size = InferenceServerClient.generate_request_body(inputs, outputs=outputs, parameters=request_parameters)
             if ss.shared_memory == "none":
@@ -89,8 +91,10 @@ class NativeLoadGenerator:
         cfg.host = self.host.encode("ascii")
         cfg.port = self.port
         cfg.concurrency = n
-        cfg.requests = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
-        cfg.request_sizes = (ctypes.c_uint64 * n)(*[len(r) for r in reqs])
+        cfg.requests_per_slot = self._rps
+        assert len(reqs) == n * self._rps
+        cfg.requests = (ctypes.c_void_p * len(reqs))(*[ctypes.addressof(b) for b in bufs])
+        cfg.request_sizes = (ctypes.c_uint64 * len(reqs))(*[len(r) for r in reqs])
         if tails:
             cfg.tails = (ctypes.c_void_p * n)(*[p for p, _ in tails])
             cfg.tail_sizes = (ctypes.c_uint64 * n)(*[s for _, s in tails])
@@ -106,13 +110,13 @@ class NativeLoadGenerator:
                 from ..device import HostBuffer
 
                 checks = []
-                for s in range(n):
+                for s, g in ((s, g) for s in range(n) for g in range(ss.lookahead)):
                     for i, t in enumerate(ss.outputs):
                         kind = _native.CHECK_TOP1 if t.datatype == "FP32" else _native.CHECK_SUM
-                        checks.append(_native.CheckJob(a=ss.out_base + ss.output_offset(s, i), nbytes=t.nbytes, kind=kind))
+                        checks.append(_native.CheckJob(a=ss.out_base + ss.output_offset(s, i, g), nbytes=t.nbytes, kind=kind))
                 self._results = HostBuffer(len(checks) * 32)
                 cfg.check_jobs = (_native.CheckJob * len(checks))(*checks)
-                cfg.check_jobs_per_slot = len(ss.outputs)
+                cfg.check_jobs_per_slot = len(ss.outputs) * ss.lookahead
                 cfg.results = self._results.device_ptr
         cfg.device_window_us = int(device_window_us)
         cfg.lookahead = ss.lookahead
@@ -132,17 +136,18 @@ class NativeLoadGenerator:
         from ..grpc._utils import _get_inference_request
 
         reqs, tails = [], []
-        for slot in range(concurrency):
+        rps = ss.lookahead if ss.shared_memory == "cuda" else 1
+        for slot, gen in ((s, g) for s in range(concurrency) for g in range(rps)):
             inputs, outputs = [], []
             for i, t in enumerate(ss.inputs):
                 inp = grpcclient.InferInput(t.name, t.shape, t.datatype)
                 if ss.shared_memory in ("cuda", "system"):
-                    inp.set_shared_memory(ss.prefix + "_in", t.nbytes, offset=ss.input_offset(slot, i))
+                    inp.set_shared_memory(ss.prefix + "_in", t.nbytes, offset=ss.input_offset(slot, i, gen))
                 inputs.append(inp)
             for i, t in enumerate(ss.outputs):
                 out = grpcclient.InferRequestedOutput(t.name)
                 if ss.shared_memory in ("cuda", "system"):
-                    out.set_shared_memory(ss.prefix + "_out", t.nbytes, offset=ss.output_offset(slot, i))
+                    out.set_shared_memory(ss.prefix + "_out", t.nbytes, offset=ss.output_offset(slot, i, gen))
                 outputs.append(out)
             request = _get_inference_request(model_name=model_name, inputs=inputs, model_version=model_version, request_id="",
                                              outputs=outputs, sequence_id=0, sequence_start=False, sequence_end=False,

@@ -70,6 +70,10 @@ typedef struct tb200_loadgen_config {
    * while the device is visited once per `lookahead` requests.  0 or 1 = off. */
   uint32_t lookahead;
   uint64_t tail_stride;
+  /* shared-memory look-ahead: requests[] holds `requests_per_slot` (= lookahead) pre-formed requests
+   * per slot, slot-major, one per staging image (they name different region offsets); check and
+   * fill jobs per slot cover all images.  0 or 1 = one request per slot. */
+  uint32_t requests_per_slot;
 } tb200_loadgen_config;
 
 typedef struct tb200_loadgen_stats {

@@ -248,3 +248,14 @@ def test_reference_cc_grpc_examples_against_native_server_if_prebuilt(grpc_serve
             pytest.skip("oracle/_ref/cc_examples was not prebuilt")
         r = subprocess.run([exe, "-u", grpc_server["grpc"]], capture_output=True, text=True, timeout=60)
         assert r.returncode == 0 and mark in r.stdout, r.stdout[-800:] + r.stderr[-400:]
+
+
+def test_lookahead_over_cuda_shm(server):
+    """--lookahead 4 with CUDA shared memory: four input / output images per slot, requests name
+    the image's offsets, one device pass validates four outputs and regenerates four inputs."""
+    rows = cli.main(["-m", "densenet_onnx", "-u", server, "--shared-memory", "cuda", "--engine", "native", "--lookahead", "4",
+                     "--concurrency-range", "1:8:8x", "-p", "300", "-r", "3", "--json"])
+    assert [r["concurrency"] for r in rows] == [1, 8]
+    for r in rows:
+        assert r["count"] > 20 and r["failed"] == 0 and r["nonfinite"] == 0, r
+        assert 0 < r["device_slots"] <= r["count"] / 4 + 8, r
