@@ -538,9 +538,10 @@ def loopback_extra(device, seconds=1.5):
         grpc_url = hello.split("grpc=")[1].strip() if "grpc=" in hello else None
         url = "127.0.0.1:%d" % port
         control = httpclient.InferenceServerClient(url)
-        for conc, window in ((1, 0), (64, 150), (256, 150)):
+        # last two: look-ahead (8 input / output images per slot and device pass, every request fresh)
+        for conc, window, la in ((1, 0, 1), (64, 150, 1), (256, 150, 1), (1, 0, 8), (256, 0, 8)):
             ss = SlotSet([TensorSpec("data_0", "FP32", [3, 224, 224])], [TensorSpec("fc6_1", "FP32", [1000])], conc, "cuda", device,
-                         "random", SEED, name_prefix="bench_lb%d" % conc)
+                         "random", SEED, name_prefix="bench_lb%d_%d" % (conc, la), lookahead=la)
             ss.register(control)
             gen = NativeLoadGenerator(url, "densenet_onnx", "", ss, conc, regenerate=True, validate=True, device_window_us=window)
             gen.start()
@@ -554,7 +555,7 @@ def loopback_extra(device, seconds=1.5):
             out["levels"].append({"concurrency": conc, "infer_per_s": round(w["throughput"], 1), "p50_us": round(w["p50_us"], 1),
                                   "p99_us": round(w["p99_us"], 1), "failed": int(w["failed"]), "nonfinite": int(w["nonfinite"]),
                                   "slots_per_device_pass": round(w["device_slots"] / max(1, w["device_batches"]), 1),
-                                  "device_window_us": window})
+                                  "device_window_us": window, "lookahead": la})
         # reference-style CPU client loop, one thread
         import client_b200.utils.cuda_shared_memory as cudashm
 
@@ -660,6 +661,12 @@ def loopback_under_mps(device):
         if not levels:
             raise RuntimeError("no result rows: " + (r.stdout + r.stderr)[-300:])
         res = {"available": True, "levels": levels}
+        r = subprocess.run([sys.executable, "-m", "client_b200.perf", "-m", "densenet_onnx", "-u", "127.0.0.1:%d" % port,
+                            "--shared-memory", "cuda", "--engine", "native", "--lookahead", "8", "--concurrency-range", "1:256:256x",
+                            "-p", "700", "-r", "4", "--json"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+        res["lookahead_8"] = [{"concurrency": w["concurrency"], "infer_per_s": round(w["throughput"], 1), "p50_us": round(w["p50_us"], 1),
+                               "p99_us": round(w["p99_us"], 1), "failed": int(w["failed"]), "nonfinite": int(w["nonfinite"])}
+                              for w in (json.loads(line) for line in r.stdout.splitlines() if line.startswith("{"))]
         if "grpc=" in hello:
             try:
                 res["grpc"] = _grpc_loopback_levels(hello.split("grpc=")[1].strip(), env)
