@@ -424,11 +424,16 @@ bool grpc_infer(tb200_mock_server* s, uint64_t call_id, const std::string& messa
     return true;
   };
   s->requests.fetch_add(1, std::memory_order_relaxed);
+  Ticket t;
+  auto fail_free = [&](int status, const std::string& msg) {  // ... after a slab was taken
+    give_slab(s, t.slab);
+    t.slab = -1;
+    return fail(status, msg);
+  };
   const ModelInfo* m = find_model(req.model_name());
   if (m == nullptr) return fail(5, "Request for unknown model: '" + req.model_name() + "' is not found");
   if (m->decoupled && !stream) return fail(3, "ModelInfer RPC doesn't support models with decoupled transaction policy");
   if (req.inputs_size() != static_cast<int>(m->inputs.size())) return fail(3, std::string(m->name) + ": expected " + std::to_string(m->inputs.size()) + " inputs");
-  Ticket t;
   t.conn_id = call_id;
   t.grpc = true;
   t.stream = stream;
@@ -450,27 +455,27 @@ bool grpc_infer(tb200_mock_server* s, uint64_t call_id, const std::string& messa
     for (size_t k = 0; k < m->inputs.size(); ++k) {
       if (tensor.name() == m->inputs[k].name) slot = static_cast<int>(k);
     }
-    if (slot < 0) return give_slab(s, t.slab), fail(3, "unexpected input '" + tensor.name() + "' for model '" + m->name + "'");
+    if (slot < 0) return fail_free(3, "unexpected input '" + tensor.name() + "' for model '" + m->name + "'");
     size_t expect = strcmp(m->inputs[static_cast<size_t>(slot)].datatype, "INT64") == 0 ? 8 : 4;
     for (int64_t d : tensor.shape()) expect *= static_cast<size_t>(d < 0 ? 0 : d);
     ShmRef ref;
     if (shm_of(tensor.parameters(), &ref)) {
       char* p = nullptr;
-      if (ref.size < expect || !resolve(s, ref, &p)) return give_slab(s, t.slab), fail(3, "input '" + tensor.name() + "': shared memory region not registered or too small");
+      if (ref.size < expect || !resolve(s, ref, &p)) return fail_free(3, "input '" + tensor.name() + "': shared memory region not registered or too small");
       in_ptr[slot] = p;
       continue;
     }
-    if (raw_index >= req.raw_input_contents_size()) return give_slab(s, t.slab), fail(3, "input '" + tensor.name() + "' has no data (raw_input_contents expected)");
+    if (raw_index >= req.raw_input_contents_size()) return fail_free(3, "input '" + tensor.name() + "' has no data (raw_input_contents expected)");
     const std::string& raw = req.raw_input_contents(raw_index++);
     if (raw.size() != expect || expect == 0) {
-      return give_slab(s, t.slab), fail(3, "input '" + tensor.name() + "': got " + std::to_string(raw.size()) + " bytes, shape needs " + std::to_string(expect));
+      return fail_free(3, "input '" + tensor.name() + "': got " + std::to_string(raw.size()) + " bytes, shape needs " + std::to_string(expect));
     }
     if (slab == nullptr) {
       t.slab = take_slab(s);
       if (t.slab < 0) return fail(8, "the server is out of staging slabs");
       slab = s->slabs + static_cast<size_t>(t.slab) * kSlabBytes;
     }
-    if (slab_off + raw.size() > kSlabOut) return give_slab(s, t.slab), fail(3, "wire-mode inputs of this server are limited to 16 KiB per request; use shared memory");
+    if (slab_off + raw.size() > kSlabOut) return fail_free(3, "wire-mode inputs of this server are limited to 16 KiB per request; use shared memory");
     memcpy(slab + slab_off, raw.data(), raw.size());
     in_ptr[slot] = slab + slab_off;
     if (t.job.kind == 3) t.job.pad = static_cast<int>(raw.size() / 4);
@@ -489,16 +494,16 @@ bool grpc_infer(tb200_mock_server* s, uint64_t call_id, const std::string& messa
     }
     if (in_shm) {
       char* p = nullptr;
-      if (!resolve(s, ref, &p)) return give_slab(s, t.slab), fail(3, std::string("output '") + m->outputs[k].name + "': shared memory region not registered");
+      if (!resolve(s, ref, &p)) return fail_free(3, std::string("output '") + m->outputs[k].name + "': shared memory region not registered");
       out_ptr[k] = p;
     } else {
       any_wire_out = true;
     }
   }
   if (any_wire_out) {
-    if (t.job.kind == 0) return give_slab(s, t.slab), fail(3, "densenet_onnx outputs of this server go to shared memory");
+    if (t.job.kind == 0) return fail_free(3, "densenet_onnx outputs of this server go to shared memory");
     for (size_t k = 0; k < m->outputs.size(); ++k) {
-      if (out_ptr[k] != nullptr) return give_slab(s, t.slab), fail(3, "outputs must be all in shared memory or all in the response");
+      if (out_ptr[k] != nullptr) return fail_free(3, "outputs must be all in shared memory or all in the response");
     }
     if (t.slab < 0) {
       t.slab = take_slab(s);
@@ -508,7 +513,7 @@ bool grpc_infer(tb200_mock_server* s, uint64_t call_id, const std::string& messa
     out_ptr[0] = slab + kSlabOut;
     if (m->outputs.size() > 1) out_ptr[1] = slab + kSlabOut + 64;  // simple: OUTPUT0 | OUTPUT1, 64 B each
   }
-  if (t.job.kind == 0 && (in_ptr[0] == nullptr || slab != nullptr)) return give_slab(s, t.slab), fail(3, "densenet_onnx inputs of this server come from shared memory");
+  if (t.job.kind == 0 && (in_ptr[0] == nullptr || slab != nullptr)) return fail_free(3, "densenet_onnx inputs of this server come from shared memory");
   t.job.c = out_ptr[0];
   t.job.d = out_ptr[1];
   t.wire_out = any_wire_out;  // inputs on the wire with outputs in shared memory (or the reverse) are fine
