@@ -20,7 +20,7 @@ OUT = os.path.join(HERE, "_ref", "cc_examples")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 EXAMPLES = ["simple_http_infer_client", "simple_http_async_infer_client", "simple_http_string_infer_client",
-            "simple_http_shm_client", "simple_http_sequence_sync_infer_client"]
+            "simple_http_shm_client", "simple_http_sequence_sync_infer_client", "reuse_infer_objects_client"]
 GRPC_EXAMPLES = ["simple_grpc_infer_client", "simple_grpc_async_infer_client", "simple_grpc_string_infer_client",
                  "simple_grpc_shm_client", "simple_grpc_health_metadata", "simple_grpc_sequence_sync_infer_client",
                  "simple_grpc_sequence_stream_infer_client", "simple_grpc_keepalive_client", "simple_grpc_custom_args_client",

@@ -105,6 +105,9 @@ CC_EXAMPLES = {
     "simple_grpc_keepalive_client": "PASS : KeepAlive",
     "simple_grpc_custom_args_client": "PASS : CustomArgs",
     "simple_grpc_custom_repeat": "",
+    # both front ends in one program (-i http | grpc), system shared memory, objects reused across calls
+    "reuse_infer_objects_client": "15 - 1 = 14",
+    "reuse_infer_objects_client:grpc": "15 - 1 = 14",
 }
 
 
@@ -128,9 +131,11 @@ def test_unmodified_reference_cc_example(cc_binaries, cc_server, name):
     """src/c++/examples/<name>.cc compiled as is against compat/{http,grpc}_client.h +
     libtb200client.so (oracle/build_ref_examples.py) and run against the mock server's models;
     the programs end with their own value checks."""
-    assert name in cc_binaries
-    url = cc_server["grpc" if "_grpc_" in name else "http"]
-    r = subprocess.run([cc_binaries[name], "-u", url], capture_output=True, text=True, timeout=60)
+    exe, _, variant = name.partition(":")
+    assert exe in cc_binaries
+    grpc = "_grpc_" in exe or variant == "grpc"
+    url = cc_server["grpc" if grpc else "http"]
+    r = subprocess.run([cc_binaries[exe], "-u", url] + (["-i", "grpc"] if variant == "grpc" else []), capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and CC_EXAMPLES[name] in r.stdout + r.stderr, r.stdout[-800:] + r.stderr[-400:]
 
 
