@@ -2,5 +2,12 @@
 // `namespace tc = triton::client;` builds against tb200_grpc_client.h (message classes in
 // namespace `inference`, grpc_compression_algorithm and grpc::ChannelArguments stand-ins).
 #pragma once
+// the reference headers pull in the CUDA runtime API when built with GPU support; code written
+// against them uses cudaIpcMemHandle_t without including it
+#if defined(__has_include)
+#if __has_include(<cuda_runtime_api.h>)
+#include <cuda_runtime_api.h>
+#endif
+#endif
 #include "../tb200_grpc_client.h"
 namespace triton { namespace client = ::tb200::client; }

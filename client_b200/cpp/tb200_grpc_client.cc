@@ -937,29 +937,29 @@ Error InferenceServerGrpcClient::Unary(const char* method, const pb::Message& re
   return Error::Success;
 }
 
-Error InferenceServerGrpcClient::IsServerLive(bool* live, const Headers& headers) {
+Error InferenceServerGrpcClient::IsServerLive(bool* live, const Headers& headers, const uint64_t timeout_ms) {
   inference::ServerLiveRequest request;
   inference::ServerLiveResponse response;
-  Error err = Unary("ServerLive", request, &response, headers);
+  Error err = Unary("ServerLive", request, &response, headers, 1000 * timeout_ms);
   *live = err.IsOk() && response.live();
   if (verbose_ && err.IsOk()) std::cout << "Server Live : " << *live << std::endl;
   return err;
 }
-Error InferenceServerGrpcClient::IsServerReady(bool* ready, const Headers& headers) {
+Error InferenceServerGrpcClient::IsServerReady(bool* ready, const Headers& headers, const uint64_t timeout_ms) {
   inference::ServerReadyRequest request;
   inference::ServerReadyResponse response;
-  Error err = Unary("ServerReady", request, &response, headers);
+  Error err = Unary("ServerReady", request, &response, headers, 1000 * timeout_ms);
   *ready = err.IsOk() && response.ready();
   if (verbose_ && err.IsOk()) std::cout << "Server Ready : " << *ready << std::endl;
   return err;
 }
 Error InferenceServerGrpcClient::IsModelReady(bool* ready, const std::string& model_name, const std::string& model_version,
-                                              const Headers& headers) {
+                                              const Headers& headers, const uint64_t timeout_ms) {
   inference::ModelReadyRequest request;
   request.set_name(model_name);
   request.set_version(model_version);
   inference::ModelReadyResponse response;
-  Error err = Unary("ModelReady", request, &response, headers);
+  Error err = Unary("ModelReady", request, &response, headers, 1000 * timeout_ms);
   *ready = err.IsOk() && response.ready();
   if (verbose_ && err.IsOk()) {
     std::cout << "Model Ready : name: " << model_name;
@@ -968,94 +968,94 @@ Error InferenceServerGrpcClient::IsModelReady(bool* ready, const std::string& mo
   }
   return err;
 }
-Error InferenceServerGrpcClient::ServerMetadata(inference::ServerMetadataResponse* server_metadata, const Headers& headers) {
+Error InferenceServerGrpcClient::ServerMetadata(inference::ServerMetadataResponse* server_metadata, const Headers& headers, const uint64_t timeout_ms) {
   inference::ServerMetadataRequest request;
-  return Unary("ServerMetadata", request, server_metadata, headers);
+  return Unary("ServerMetadata", request, server_metadata, headers, 1000 * timeout_ms);
 }
 Error InferenceServerGrpcClient::ModelMetadata(inference::ModelMetadataResponse* model_metadata, const std::string& model_name,
-                                               const std::string& model_version, const Headers& headers) {
+                                               const std::string& model_version, const Headers& headers, const uint64_t timeout_ms) {
   inference::ModelMetadataRequest request;
   request.set_name(model_name);
   request.set_version(model_version);
-  return Unary("ModelMetadata", request, model_metadata, headers);
+  return Unary("ModelMetadata", request, model_metadata, headers, 1000 * timeout_ms);
 }
 Error InferenceServerGrpcClient::ModelConfig(inference::ModelConfigResponse* model_config, const std::string& model_name,
-                                             const std::string& model_version, const Headers& headers) {
+                                             const std::string& model_version, const Headers& headers, const uint64_t timeout_ms) {
   inference::ModelConfigRequest request;
   request.set_name(model_name);
   request.set_version(model_version);
-  return Unary("ModelConfig", request, model_config, headers);
+  return Unary("ModelConfig", request, model_config, headers, 1000 * timeout_ms);
 }
-Error InferenceServerGrpcClient::ModelRepositoryIndex(inference::RepositoryIndexResponse* repository_index, const Headers& headers) {
+Error InferenceServerGrpcClient::ModelRepositoryIndex(inference::RepositoryIndexResponse* repository_index, const Headers& headers, const uint64_t timeout_ms) {
   inference::RepositoryIndexRequest request;
-  return Unary("RepositoryIndex", request, repository_index, headers);
+  return Unary("RepositoryIndex", request, repository_index, headers, 1000 * timeout_ms);
 }
 Error InferenceServerGrpcClient::LoadModel(const std::string& model_name, const Headers& headers, const std::string& config,
-                                           const std::map<std::string, std::vector<char>>& files) {
+                                           const std::map<std::string, std::vector<char>>& files, const uint64_t timeout_ms) {
   inference::RepositoryModelLoadRequest request;
   request.set_model_name(model_name);
   if (!config.empty()) (*request.mutable_parameters())["config"].set_string_param(config);
   for (const auto& kv : files) (*request.mutable_parameters())[kv.first].set_bytes_param(kv.second.data(), kv.second.size());
   inference::RepositoryModelLoadResponse response;
-  Error err = Unary("RepositoryModelLoad", request, &response, headers);
+  Error err = Unary("RepositoryModelLoad", request, &response, headers, 1000 * timeout_ms);
   if (verbose_ && err.IsOk()) std::cout << "Loaded model '" << model_name << "'" << std::endl;
   return err;
 }
-Error InferenceServerGrpcClient::UnloadModel(const std::string& model_name, const Headers& headers) {
+Error InferenceServerGrpcClient::UnloadModel(const std::string& model_name, const Headers& headers, const uint64_t timeout_ms) {
   inference::RepositoryModelUnloadRequest request;
   request.set_model_name(model_name);
   inference::RepositoryModelUnloadResponse response;
-  Error err = Unary("RepositoryModelUnload", request, &response, headers);
+  Error err = Unary("RepositoryModelUnload", request, &response, headers, 1000 * timeout_ms);
   if (verbose_ && err.IsOk()) std::cout << "Unloaded model '" << model_name << "'" << std::endl;
   return err;
 }
 Error InferenceServerGrpcClient::ModelInferenceStatistics(inference::ModelStatisticsResponse* infer_stat, const std::string& model_name,
-                                                          const std::string& model_version, const Headers& headers) {
+                                                          const std::string& model_version, const Headers& headers, const uint64_t timeout_ms) {
   inference::ModelStatisticsRequest request;
   request.set_name(model_name);
   request.set_version(model_version);
-  return Unary("ModelStatistics", request, infer_stat, headers);
+  return Unary("ModelStatistics", request, infer_stat, headers, 1000 * timeout_ms);
 }
 Error InferenceServerGrpcClient::UpdateTraceSettings(inference::TraceSettingResponse* response, const std::string& model_name,
                                                      const std::map<std::string, std::vector<std::string>>& settings,
-                                                     const Headers& headers) {
+                                                     const Headers& headers, const uint64_t timeout_ms) {
   inference::TraceSettingRequest request;
   if (!model_name.empty()) request.set_model_name(model_name);
   for (const auto& kv : settings) {
     auto& value = (*request.mutable_settings())[kv.first];  // an empty list clears the setting
     for (const std::string& v : kv.second) value.add_value(v);
   }
-  return Unary("TraceSetting", request, response, headers);
+  return Unary("TraceSetting", request, response, headers, 1000 * timeout_ms);
 }
 Error InferenceServerGrpcClient::GetTraceSettings(inference::TraceSettingResponse* settings, const std::string& model_name,
-                                                  const Headers& headers) {
+                                                  const Headers& headers, const uint64_t timeout_ms) {
   inference::TraceSettingRequest request;
   if (!model_name.empty()) request.set_model_name(model_name);
-  return Unary("TraceSetting", request, settings, headers);
+  return Unary("TraceSetting", request, settings, headers, 1000 * timeout_ms);
 }
 Error InferenceServerGrpcClient::SystemSharedMemoryStatus(inference::SystemSharedMemoryStatusResponse* status,
-                                                          const std::string& region_name, const Headers& headers) {
+                                                          const std::string& region_name, const Headers& headers, const uint64_t timeout_ms) {
   inference::SystemSharedMemoryStatusRequest request;
   request.set_name(region_name);
-  return Unary("SystemSharedMemoryStatus", request, status, headers);
+  return Unary("SystemSharedMemoryStatus", request, status, headers, 1000 * timeout_ms);
 }
 Error InferenceServerGrpcClient::RegisterSystemSharedMemory(const std::string& name, const std::string& key, const size_t byte_size,
-                                                            const size_t offset, const Headers& headers) {
+                                                            const size_t offset, const Headers& headers, const uint64_t timeout_ms) {
   inference::SystemSharedMemoryRegisterRequest request;
   request.set_name(name);
   request.set_key(key);
   request.set_offset(offset);
   request.set_byte_size(byte_size);
   inference::SystemSharedMemoryRegisterResponse response;
-  Error err = Unary("SystemSharedMemoryRegister", request, &response, headers);
+  Error err = Unary("SystemSharedMemoryRegister", request, &response, headers, 1000 * timeout_ms);
   if (verbose_ && err.IsOk()) std::cout << "Registered system shared memory with name '" << name << "'" << std::endl;
   return err;
 }
-Error InferenceServerGrpcClient::UnregisterSystemSharedMemory(const std::string& name, const Headers& headers) {
+Error InferenceServerGrpcClient::UnregisterSystemSharedMemory(const std::string& name, const Headers& headers, const uint64_t timeout_ms) {
   inference::SystemSharedMemoryUnregisterRequest request;
   request.set_name(name);
   inference::SystemSharedMemoryUnregisterResponse response;
-  Error err = Unary("SystemSharedMemoryUnregister", request, &response, headers);
+  Error err = Unary("SystemSharedMemoryUnregister", request, &response, headers, 1000 * timeout_ms);
   if (verbose_ && err.IsOk()) {
     if (!name.empty()) std::cout << "Unregistered system shared memory with name '" << name << "'" << std::endl;
     else std::cout << "Unregistered all system shared memory regions" << std::endl;
@@ -1063,28 +1063,28 @@ Error InferenceServerGrpcClient::UnregisterSystemSharedMemory(const std::string&
   return err;
 }
 Error InferenceServerGrpcClient::CudaSharedMemoryStatus(inference::CudaSharedMemoryStatusResponse* status,
-                                                        const std::string& region_name, const Headers& headers) {
+                                                        const std::string& region_name, const Headers& headers, const uint64_t timeout_ms) {
   inference::CudaSharedMemoryStatusRequest request;
   request.set_name(region_name);
-  return Unary("CudaSharedMemoryStatus", request, status, headers);
+  return Unary("CudaSharedMemoryStatus", request, status, headers, 1000 * timeout_ms);
 }
 Error InferenceServerGrpcClient::RegisterCudaSharedMemoryRaw(const std::string& name, const uint8_t* handle64, const size_t device_id,
-                                                             const size_t byte_size, const Headers& headers) {
+                                                             const size_t byte_size, const Headers& headers, const uint64_t timeout_ms) {
   inference::CudaSharedMemoryRegisterRequest request;
   request.set_name(name);
   request.set_raw_handle(handle64, 64);
   request.set_device_id(static_cast<int64_t>(device_id));
   request.set_byte_size(byte_size);
   inference::CudaSharedMemoryRegisterResponse response;
-  Error err = Unary("CudaSharedMemoryRegister", request, &response, headers);
+  Error err = Unary("CudaSharedMemoryRegister", request, &response, headers, 1000 * timeout_ms);
   if (verbose_ && err.IsOk()) std::cout << "Registered cuda shared memory with name '" << name << "'" << std::endl;
   return err;
 }
-Error InferenceServerGrpcClient::UnregisterCudaSharedMemory(const std::string& name, const Headers& headers) {
+Error InferenceServerGrpcClient::UnregisterCudaSharedMemory(const std::string& name, const Headers& headers, const uint64_t timeout_ms) {
   inference::CudaSharedMemoryUnregisterRequest request;
   request.set_name(name);
   inference::CudaSharedMemoryUnregisterResponse response;
-  Error err = Unary("CudaSharedMemoryUnregister", request, &response, headers);
+  Error err = Unary("CudaSharedMemoryUnregister", request, &response, headers, 1000 * timeout_ms);
   if (verbose_ && err.IsOk()) {
     if (!name.empty()) std::cout << "Unregistered cuda shared memory with name '" << name << "'" << std::endl;
     else std::cout << "Unregistered all cuda shared memory regions" << std::endl;

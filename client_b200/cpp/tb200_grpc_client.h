@@ -93,43 +93,43 @@ class InferenceServerGrpcClient : public InferenceServerClient {
                       const grpc::ChannelArguments& channel_args, bool verbose = false, bool use_ssl = false,
                       const SslOptions& ssl_options = SslOptions(), const bool use_cached_channel = true);
 
-  Error IsServerLive(bool* live, const Headers& headers = Headers());
-  Error IsServerReady(bool* ready, const Headers& headers = Headers());
+  Error IsServerLive(bool* live, const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
+  Error IsServerReady(bool* ready, const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   Error IsModelReady(bool* ready, const std::string& model_name, const std::string& model_version = "",
-                     const Headers& headers = Headers());
-  Error ServerMetadata(inference::ServerMetadataResponse* server_metadata, const Headers& headers = Headers());
+                     const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
+  Error ServerMetadata(inference::ServerMetadataResponse* server_metadata, const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   Error ModelMetadata(inference::ModelMetadataResponse* model_metadata, const std::string& model_name,
-                      const std::string& model_version = "", const Headers& headers = Headers());
+                      const std::string& model_version = "", const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   Error ModelConfig(inference::ModelConfigResponse* model_config, const std::string& model_name,
-                    const std::string& model_version = "", const Headers& headers = Headers());
-  Error ModelRepositoryIndex(inference::RepositoryIndexResponse* repository_index, const Headers& headers = Headers());
+                    const std::string& model_version = "", const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
+  Error ModelRepositoryIndex(inference::RepositoryIndexResponse* repository_index, const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   Error LoadModel(const std::string& model_name, const Headers& headers = Headers(),
-                  const std::string& config = std::string(), const std::map<std::string, std::vector<char>>& files = {});
-  Error UnloadModel(const std::string& model_name, const Headers& headers = Headers());
+                  const std::string& config = std::string(), const std::map<std::string, std::vector<char>>& files = {}, const uint64_t timeout_ms = 0);
+  Error UnloadModel(const std::string& model_name, const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   Error ModelInferenceStatistics(inference::ModelStatisticsResponse* infer_stat, const std::string& model_name = "",
-                                 const std::string& model_version = "", const Headers& headers = Headers());
+                                 const std::string& model_version = "", const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   Error UpdateTraceSettings(inference::TraceSettingResponse* response, const std::string& model_name = "",
                             const std::map<std::string, std::vector<std::string>>& settings = {},
-                            const Headers& headers = Headers());
+                            const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   Error GetTraceSettings(inference::TraceSettingResponse* settings, const std::string& model_name = "",
-                         const Headers& headers = Headers());
+                         const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   Error SystemSharedMemoryStatus(inference::SystemSharedMemoryStatusResponse* status, const std::string& region_name = "",
-                                 const Headers& headers = Headers());
+                                 const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   Error RegisterSystemSharedMemory(const std::string& name, const std::string& key, const size_t byte_size,
-                                   const size_t offset = 0, const Headers& headers = Headers());
-  Error UnregisterSystemSharedMemory(const std::string& name = "", const Headers& headers = Headers());
+                                   const size_t offset = 0, const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
+  Error UnregisterSystemSharedMemory(const std::string& name = "", const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   Error CudaSharedMemoryStatus(inference::CudaSharedMemoryStatusResponse* status, const std::string& region_name = "",
-                               const Headers& headers = Headers());
+                               const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
   // `cuda_shm_handle`: any 64-byte cudaIpcMemHandle_t-compatible object (see tb200_client.h)
   template <typename IpcHandle>
   Error RegisterCudaSharedMemory(const std::string& name, const IpcHandle& cuda_shm_handle, const size_t device_id,
-                                 const size_t byte_size, const Headers& headers = Headers()) {
+                                 const size_t byte_size, const Headers& headers = Headers(), const uint64_t timeout_ms = 0) {
     static_assert(sizeof(IpcHandle) == 64, "a CUDA IPC memory handle is 64 bytes");
-    return RegisterCudaSharedMemoryRaw(name, reinterpret_cast<const uint8_t*>(&cuda_shm_handle), device_id, byte_size, headers);
+    return RegisterCudaSharedMemoryRaw(name, reinterpret_cast<const uint8_t*>(&cuda_shm_handle), device_id, byte_size, headers, timeout_ms);
   }
   Error RegisterCudaSharedMemoryRaw(const std::string& name, const uint8_t* handle64, const size_t device_id,
-                                    const size_t byte_size, const Headers& headers = Headers());
-  Error UnregisterCudaSharedMemory(const std::string& name = "", const Headers& headers = Headers());
+                                    const size_t byte_size, const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
+  Error UnregisterCudaSharedMemory(const std::string& name = "", const Headers& headers = Headers(), const uint64_t timeout_ms = 0);
 
   Error Infer(InferResult** result, const InferOptions& options, const std::vector<InferInput*>& inputs,
               const std::vector<const InferRequestedOutput*>& outputs = std::vector<const InferRequestedOutput*>(),

@@ -25,7 +25,10 @@ GRPC_EXAMPLES = ["simple_grpc_infer_client", "simple_grpc_async_infer_client", "
                  "simple_grpc_shm_client", "simple_grpc_health_metadata", "simple_grpc_sequence_sync_infer_client",
                  "simple_grpc_sequence_stream_infer_client", "simple_grpc_keepalive_client", "simple_grpc_custom_args_client",
                  "simple_grpc_custom_repeat", "simple_grpc_model_control"]
-CUDA_EXAMPLES = ["simple_http_cudashm_client", "simple_grpc_cudashm_client"]  # cudaMalloc + cudaIpcGetMemHandle by hand, needs cudart
+CUDA_EXAMPLES = ["simple_http_cudashm_client", "simple_grpc_cudashm_client"]
+# the reference's own client test programs that need no gtest (src/c++/tests); they use
+# cudaIpcMemHandle_t through the client headers, hence the CUDA include path and cudart
+TESTS = ["client_timeout_test", "memory_leak_test"]  # cudaMalloc + cudaIpcGetMemHandle by hand, needs cudart
 
 
 def build_ref_examples(force=False):
@@ -40,14 +43,14 @@ def build_ref_examples(force=False):
     cpp = os.path.join(ROOT, "client_b200", "cpp")
     libdir = os.path.join(ROOT, "client_b200", "lib")
     built = {}
-    for name in EXAMPLES + GRPC_EXAMPLES + CUDA_EXAMPLES:
-        src = os.path.join(REF, name + ".cc")
+    for name in EXAMPLES + GRPC_EXAMPLES + CUDA_EXAMPLES + TESTS:
+        src = os.path.join(REF if name not in TESTS else os.path.join(os.path.dirname(REF), "tests"), name + ".cc")
         exe = os.path.join(OUT, name)
         deps = [src, os.path.join(libdir, "libtb200client.so"), os.path.join(cpp, "tb200_client.h"), os.path.join(cpp, "tb200_grpc_client.h")]
         if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
             cmd = ["g++", "-O1", "-std=c++17", "-I" + os.path.join(cpp, "compat"), "-I" + cpp, src, "-o", exe,
                    "-L" + libdir, "-ltb200client", "-ltb200", "-Wl,-rpath,$ORIGIN/../../../client_b200/lib", "-lpthread", "-lrt"]
-            if name in CUDA_EXAMPLES:
+            if name in CUDA_EXAMPLES or name in TESTS:
                 cmd += ["-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart"]
             subprocess.run(cmd, check=True)
         built[name] = exe

@@ -139,6 +139,49 @@ def test_unmodified_reference_cc_example(cc_binaries, cc_server, name):
     assert r.returncode == 0 and CC_EXAMPLES[name] in r.stdout + r.stderr, r.stdout[-800:] + r.stderr[-400:]
 
 
+def test_reference_client_timeout_test_unmodified(cc_binaries):
+    """src/c++/tests/client_timeout_test.cc (the reference's own timeout test program, compiled as
+    is): sync / async / streaming over gRPC and sync / async over HTTP succeed with a generous
+    client time-out and fail with the reference's "Deadline Exceeded" when the model takes 300 ms
+    and the client allows 50 ms."""
+    exe = cc_binaries.get("client_timeout_test")
+    assert exe
+    modes = (["-i", "grpc"], ["-i", "grpc", "-a"], ["-i", "grpc", "-s"], ["-i", "http"], ["-i", "http", "-a"])
+    for extra, timeout_us, rc in (((), "5000000", 0), (("--delay-us", "300000"), "50000", 1)):
+        proc, http_port, grpc_port = start_server(extra)
+        try:
+            for mode in modes:
+                url = "127.0.0.1:%d" % (grpc_port if "grpc" in mode else http_port)
+                r = subprocess.run([exe, "-u", url, "-t", timeout_us] + mode, capture_output=True, text=True, timeout=60)
+                assert r.returncode == rc, (mode, r.stdout[-300:], r.stderr[-300:])
+                if rc and "-s" not in mode:
+                    assert "Deadline Exceeded" in r.stderr, (mode, r.stderr[-300:])
+        finally:
+            proc.terminate()
+            proc.wait(10)
+
+
+def test_reference_memory_leak_test_unmodified(cc_binaries, cc_server):
+    """src/c++/tests/memory_leak_test.cc (compiled as is; the reference runs it under valgrind):
+    200 vs 2000 repetitions, new client per repetition and one reused client, over HTTP and gRPC --
+    the peak resident set must not grow with the repetition count."""
+    exe = cc_binaries.get("memory_leak_test")
+    assert exe
+
+    def peak_kb(args):
+        code = ("import resource, subprocess, sys; r = subprocess.run(%r, capture_output=True); "
+                "print(r.returncode, resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss)" % (args,))
+        rc, kb = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300).stdout.split()
+        assert rc == "0", args
+        return int(kb)
+
+    for proto in ("http", "grpc"):
+        for flag in ([], ["-R"]):
+            base = [exe, "-u", cc_server[proto], "-i", proto]
+            few, many = peak_kb(base + ["-r", "200"] + flag), peak_kb(base + ["-r", "2000"] + flag)
+            assert many - few < 2048, (proto, flag, few, many)
+
+
 def test_reference_unit_tests_for_system_shared_memory_unmodified():
     """src/python/library/tests/test_shared_memory.py (the reference's own unittest module)
     loaded as is with the drop-in aliased as `tritonclient`."""
