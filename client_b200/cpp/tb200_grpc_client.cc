@@ -860,6 +860,19 @@ InferenceServerGrpcClient::InferenceServerGrpcClient(const std::string& url, boo
 InferenceServerGrpcClient::~InferenceServerGrpcClient() {
   StopStream();
   {
+    // nothing of this object may be touched by the I/O thread after this block
+    std::shared_ptr<detail::GrpcChannel> channel;
+    {
+      std::lock_guard<std::mutex> lk(channel_mu_);
+      channel = channel_;
+    }
+    std::unique_lock<std::mutex> lk(calls_mu_);
+    if (channel) {
+      for (auto& kv : active_calls_) channel->Cancel(kv.second);
+    }
+    calls_cv_.wait(lk, [this] { return active_calls_.empty(); });
+  }
+  {
     std::lock_guard<std::mutex> lk(worker_mu_);
     exiting_ = true;
   }
@@ -1128,6 +1141,10 @@ Error InferenceServerGrpcClient::StartInfer(std::shared_ptr<detail::GrpcCall>* o
   // the send timer covers the marshalling (as in the reference); it must be complete before the
   // call can finish on the I/O thread
   if (timer != nullptr) timer->CaptureTimestamp(RequestTimers::Kind::SEND_END);
+  if (call->on_done) {  // asynchronous: the destructor cancels and waits for it
+    std::lock_guard<std::mutex> lk(calls_mu_);
+    active_calls_[call.get()] = call;
+  }
   channel->Start(call, std::move(framed), true);
   *out = std::move(call);
   return Error::Success;
@@ -1168,10 +1185,10 @@ Error InferenceServerGrpcClient::Infer(InferResult** result, const InferOptions&
 }
 
 void InferenceServerGrpcClient::Dispatch(std::function<void()> fn) {
-  {
-    std::lock_guard<std::mutex> lk(worker_mu_);
-    worker_jobs_.push_back(std::move(fn));
-  }
+  // notified under the lock: the destructor joins the worker, which cannot run (and finish) the
+  // job before this thread is done with the members
+  std::lock_guard<std::mutex> lk(worker_mu_);
+  worker_jobs_.push_back(std::move(fn));
   worker_cv_.notify_one();
 }
 
@@ -1199,7 +1216,17 @@ Error InferenceServerGrpcClient::AsyncInfer(OnCompleteFn callback, const InferOp
   std::shared_ptr<detail::GrpcCall> call;
   Error err = StartInfer(&call, options, inputs, outputs, headers, compression_algorithm,
                          [this, callback, timer](detail::GrpcCall* done) {
-                           // I/O thread: hand the finished call to the callback thread
+                           // I/O thread: hand the finished call to the callback thread, then
+                           // drop it from the calls the destructor waits for (last access to `this`)
+                           struct Deregister {
+                             InferenceServerGrpcClient* self;
+                             detail::GrpcCall* call;
+                             ~Deregister() {
+                               std::lock_guard<std::mutex> lk(self->calls_mu_);
+                               self->active_calls_.erase(call);
+                               self->calls_cv_.notify_all();
+                             }
+                           } deregister{this, done};
                            auto status = done->status;
                            auto message = std::make_shared<std::string>(std::move(done->response));
                            auto status_message = done->status_message;

@@ -191,6 +191,12 @@ class InferenceServerGrpcClient : public InferenceServerClient {
   std::condition_variable worker_cv_;
   std::deque<std::function<void()>> worker_jobs_;
   bool exiting_ = false;
+  // asynchronous calls in flight: cancelled and waited for by the destructor (their completion
+  // handlers run on the channel's I/O thread and touch this object; the channel may be shared
+  // with other clients and outlive this one)
+  std::mutex calls_mu_;
+  std::condition_variable calls_cv_;
+  std::map<detail::GrpcCall*, std::shared_ptr<detail::GrpcCall>> active_calls_;
 
   // bidirectional stream (one at a time)
   OnCompleteFn stream_callback_;

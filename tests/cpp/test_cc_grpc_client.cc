@@ -523,6 +523,32 @@ static void TestSlowServer(const std::string& url) {
   CHECK_OK(client->Infer(&result, options, {in0, in1}));
   CHECK(AddSubOk(result, a, b));
   delete result;
+  // a client destroyed with asynchronous calls in flight: they are cancelled, their callbacks
+  // run (with an error) before the destructor returns, nothing touches the object afterwards
+  {
+    std::unique_ptr<tc::InferenceServerGrpcClient> doomed, survivor;
+    CHECK_OK(tc::InferenceServerGrpcClient::Create(&doomed, url));      // cached channel, shared ...
+    CHECK_OK(tc::InferenceServerGrpcClient::Create(&survivor, url));    // ... with this one
+    std::atomic<int> called{0}, failed{0};
+    tc::InferOptions slow("simple");
+    for (int i = 0; i < 3; ++i) {
+      CHECK_OK(doomed->AsyncInfer(
+          [&](tc::InferResult* r) {
+            if (!r->RequestStatus().IsOk()) ++failed;
+            ++called;
+            delete r;
+          },
+          slow, {in0, in1}));
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    doomed.reset();
+    const double gone_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    CHECK(called == 3 && failed == 3 && gone_ms < 250.0);
+    result = nullptr;
+    CHECK_OK(survivor->Infer(&result, slow, {in0, in1}));  // the shared connection is still good
+    CHECK(AddSubOk(result, a, b));
+    delete result;
+  }
   delete in0;
   delete in1;
 }
