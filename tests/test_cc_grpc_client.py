@@ -271,7 +271,7 @@ def test_loopback_against_grpcio_server(binary):
 
 
 def test_client_timeout_is_deadline_exceeded(binary):
-    proc, _, grpc_port = start_server(["--delay-us", "300000"])
+    proc, _, grpc_port = start_server(["--delay-us", "600000"])
     try:
         r = subprocess.run([binary, "127.0.0.1:%d" % grpc_port, "slow"], capture_output=True, text=True, timeout=120)
         assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]
