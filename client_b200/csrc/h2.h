@@ -9,7 +9,8 @@
 // literal-without-indexing fields and two static-table indices, so no encoder state exists;
 // header blocks we RECEIVE are skipped (a response counts as successful when a DATA frame
 // arrived before the stream ended -- gRPC reports errors as trailers-only responses), so no
-// decoder state is needed either.
+// decoder state is needed either.  (The C++ gRPC front end and the servers do decode: HpackDecoder
+// below, dynamic table and Huffman strings included.)
 #ifndef TB200_CSRC_H2_H_
 #define TB200_CSRC_H2_H_
 
@@ -19,6 +20,8 @@
 #include <string>
 #include <utility>
 #include <vector>
+
+#include "hpack_huffman.h"
 
 namespace tb200 { namespace h2 {
 
@@ -149,14 +152,67 @@ inline uint32_t get_u32(const uint8_t* p) {
   return (static_cast<uint32_t>(p[0]) << 24) | (static_cast<uint32_t>(p[1]) << 16) | (static_cast<uint32_t>(p[2]) << 8) | p[3];
 }
 
-// ---- HPACK decoding (the C++ gRPC front end reads grpc-status / grpc-message) -----------------
-// Static table + dynamic table + integer / string literals (RFC 7541 2.3, 5, 6).  Huffman-coded
-// strings (5.2, H bit) are not decoded: the field keeps its name when that is indexed, the value
-// becomes empty and `huffman_skipped` counts it -- gRPC servers send status fields raw.
+// ---- HPACK Huffman decoding (RFC 7541 5.2, code table in hpack_huffman.h) --------------------
+// A binary trie over the 257 codes, built once; decoding walks it bit by bit.  The string must
+// end on a symbol boundary followed by fewer than 8 padding bits that are all ones, and must not
+// contain EOS.
+class HuffmanDecoder {
+ public:
+  static bool Decode(const uint8_t* p, size_t n, std::string* out) {
+    static const HuffmanDecoder kTrie;
+    out->clear();
+    int node = 0;
+    int since_symbol = 0;   // bits consumed since the last complete symbol
+    bool all_ones = true;   // ... and whether they were all ones
+    for (size_t i = 0; i < n; ++i) {
+      for (int bit = 7; bit >= 0; --bit) {
+        const int b = (p[i] >> bit) & 1;
+        node = kTrie.nodes_[static_cast<size_t>(node)].child[b];
+        if (node < 0) return false;
+        ++since_symbol;
+        all_ones = all_ones && b == 1;
+        const int sym = kTrie.nodes_[static_cast<size_t>(node)].symbol;
+        if (sym >= 0) {
+          if (sym == 256) return false;  // EOS inside a string is a decoding error
+          out->push_back(static_cast<char>(sym));
+          node = 0;
+          since_symbol = 0;
+          all_ones = true;
+        }
+      }
+    }
+    return since_symbol < 8 && all_ones;
+  }
+
+ private:
+  struct Node {
+    int child[2] = {-1, -1};
+    int symbol = -1;
+  };
+  HuffmanDecoder() {
+    nodes_.emplace_back();
+    for (int s = 0; s < 257; ++s) {
+      int node = 0;
+      for (int bit = kHpackHuffman[s].bits - 1; bit >= 0; --bit) {
+        const int b = (kHpackHuffman[s].code >> bit) & 1;
+        if (nodes_[static_cast<size_t>(node)].child[b] < 0) {
+          nodes_[static_cast<size_t>(node)].child[b] = static_cast<int>(nodes_.size());
+          nodes_.emplace_back();
+        }
+        node = nodes_[static_cast<size_t>(node)].child[b];
+      }
+      nodes_[static_cast<size_t>(node)].symbol = s;
+    }
+  }
+  std::vector<Node> nodes_;
+};
+
+// ---- HPACK decoding (the C++ gRPC front end reads grpc-status / grpc-message, the servers :path)
+// Static table + dynamic table + integer / string literals, raw or Huffman coded
+// (RFC 7541 2.3, 5, 6).
 class HpackDecoder {
  public:
   using Field = std::pair<std::string, std::string>;
-  size_t huffman_skipped = 0;
 
   bool Decode(const uint8_t* p, size_t n, std::vector<Field>* out) {
     const uint8_t* end = p + n;
@@ -217,8 +273,7 @@ class HpackDecoder {
     uint64_t len;
     if (!Int(p, end, 7, &len) || len > static_cast<uint64_t>(end - *p)) return false;
     if (huffman) {
-      ++huffman_skipped;
-      s->clear();
+      if (!HuffmanDecoder::Decode(*p, static_cast<size_t>(len), s)) return false;
     } else {
       s->assign(reinterpret_cast<const char*>(*p), len);
     }
