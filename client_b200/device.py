@@ -158,6 +158,8 @@ class DeviceOps:
     def __init__(self, ctx=None, device_id=0):
         self._lib = _native.load()
         self._ctx = ctx if ctx is not None else _native.default_context(device_id)
+        self._ticket = ctypes.c_uint64(0)
+        self._ticket_ref = ctypes.byref(self._ticket)
 
     @property
     def ctx(self):
@@ -368,13 +370,13 @@ class DeviceOps:
         Up to 8 steps may be in flight; they must not share slots or result entries."""
         fa, nf = self.job_array(fill_jobs, FillJob)
         ca, nc = self.job_array(check_jobs, CheckJob)
-        ticket = ctypes.c_uint64(0)
-        _native.check(self._lib.tb200_step_submit(self._ctx.handle, fa, nf, int(seed), int(epoch), ca, nc, results_ptr, ctypes.byref(ticket)))
+        ticket = self._ticket  # one reusable out-parameter: this object is used by one thread (like the context)
+        _native.check(self._lib.tb200_step_submit(self._ctx.handle, fa, nf, seed, epoch, ca, nc, results_ptr, self._ticket_ref))
         return ticket.value
 
     def step_wait(self, ticket):
         """Returns when the step's inputs are generated and its results are visible."""
-        _native.check(self._lib.tb200_step_wait(self._ctx.handle, int(ticket)))
+        _native.check(self._lib.tb200_step_wait(self._ctx.handle, ticket))
 
     def l2_flush(self):
         _native.check(self._lib.tb200_l2_flush_async(self._ctx.handle))
