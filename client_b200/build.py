@@ -75,7 +75,7 @@ def build_cpp_client(force=False, verbose=False):
     if force or _newer(CLIENT_LIB, deps):
         gxx = shutil.which("g++") or "g++"
         cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", CLIENT_LIB] + srcs + [
-               "-L" + LIBDIR, "-ltb200", "-Wl,-rpath,$ORIGIN", "-lpthread"]
+               "-L" + LIBDIR, "-ltb200", "-Wl,-rpath,$ORIGIN", "-lpthread", "-lz"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

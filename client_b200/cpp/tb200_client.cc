@@ -6,6 +6,8 @@
 // statistics (common.cc:56-106).  The transport is our own socket code.
 #include "tb200_client.h"
 
+#include <zlib.h>
+
 #include <arpa/inet.h>
 #include <netdb.h>
 #include <netinet/in.h>
@@ -1002,7 +1004,72 @@ class HttpResult : public InferResult {
 
 // ---- client -------------------------------------------------------------------------------------
 
+namespace detail {
+
+// zlib ("deflate") / gzip stream of `body`, produced on the device (tb200_deflate_async): the
+// request side of http_client.cc:146-221.  There is no host encoder in this library.
+Error DeflateOnDevice(std::string* body, bool gzip) {
+  int count = 0;
+  if (tb200_device_count(&count) != TB200_OK || count < 1) {
+    return Error("request compression runs on the device (tb200_deflate_async) and no CUDA device is available");
+  }
+  tb200_ctx* ctx = nullptr;
+  if (tb200_ctx_create(0, &ctx) != TB200_OK) return Error(std::string("request compression: ") + tb200_last_error());
+  const uint64_t n = body->size();
+  const uint64_t cap = tb200_deflate_bound(n);
+  void *src = nullptr, *dst = nullptr, *host = nullptr, *host_dev = nullptr;
+  Error err;
+  auto check = [&err](int rc) {
+    if (rc != TB200_OK && err.IsOk()) err = Error(std::string("request compression: ") + tb200_last_error());
+    return rc == TB200_OK;
+  };
+  const uint64_t size_off = (cap + 15) & ~static_cast<uint64_t>(15);  // pinned staging: [stream | pad | uint64 size]
+  if (check(tb200_device_alloc(0, n + 16, &src)) && check(tb200_device_alloc(0, cap + 16, &dst)) &&
+      check(tb200_host_alloc(size_off + 16, &host, &host_dev)) && check(tb200_memcpy_h2d_async(ctx, src, body->data(), n)) &&
+      check(tb200_deflate_async(ctx, dst, cap, src, n, gzip ? TB200_DEFLATE_GZIP : TB200_DEFLATE_ZLIB,
+                                reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(host_dev) + size_off))) &&
+      check(tb200_ctx_sync(ctx))) {
+    uint64_t out_size = 0;
+    memcpy(&out_size, static_cast<uint8_t*>(host) + size_off, 8);
+    if (out_size == 0 || out_size > cap) {
+      err = Error("request compression: the device encoder reported an invalid stream size");
+    } else if (check(tb200_memcpy_d2h_async(ctx, host, dst, out_size)) && check(tb200_ctx_sync(ctx))) {
+      body->assign(static_cast<const char*>(host), out_size);
+    }
+  }
+  if (src) tb200_device_free(0, src);
+  if (dst) tb200_device_free(0, dst);
+  if (host) tb200_host_free(host);
+  tb200_ctx_destroy(ctx);
+  return err;
+}
+
+// zlib or gzip stream -> bytes (response side, http_client.cc:2211-2254: zlib on the host)
+Error Inflate(const std::string& in, std::string* out) {
+  z_stream zs;
+  memset(&zs, 0, sizeof(zs));
+  if (inflateInit2(&zs, 15 + 32) != Z_OK) return Error("failed to initialise zlib");  // +32: zlib or gzip header
+  zs.next_in = reinterpret_cast<Bytef*>(const_cast<char*>(in.data()));
+  zs.avail_in = static_cast<uInt>(in.size());
+  out->clear();
+  char buf[65536];
+  int rc = Z_OK;
+  while (rc == Z_OK) {
+    zs.next_out = reinterpret_cast<Bytef*>(buf);
+    zs.avail_out = sizeof(buf);
+    rc = inflate(&zs, Z_NO_FLUSH);
+    if (rc == Z_OK || rc == Z_STREAM_END) out->append(buf, sizeof(buf) - zs.avail_out);
+    if (rc == Z_OK && zs.avail_in == 0 && zs.avail_out != 0) break;  // truncated stream
+  }
+  inflateEnd(&zs);
+  if (rc != Z_STREAM_END) return Error("failed to decompress the response body");
+  return Error::Success;
+}
+
+}  // namespace detail
+
 struct InferenceServerHttpClient::AsyncJob {
+  CompressionType request_compression = CompressionType::NONE, response_compression = CompressionType::NONE;
   OnCompleteFn callback;
   OnMultiCompleteFn multi_callback;
   std::vector<InferOptions> options;
@@ -1297,7 +1364,8 @@ Error InferenceServerHttpClient::ParseResponseBody(InferResult** result, const s
 Error InferenceServerHttpClient::InferOn(detail::HttpConnection* conn, InferResult** result, const InferOptions& options,
                                          const std::vector<InferInput*>& inputs,
                                          const std::vector<const InferRequestedOutput*>& outputs, const Headers& headers,
-                                         const Parameters& query_params) {
+                                         const Parameters& query_params, CompressionType request_compression,
+                                         CompressionType response_compression) {
   RequestTimers timer;
   timer.CaptureTimestamp(RequestTimers::Kind::REQUEST_START);
   std::string js;
@@ -1310,17 +1378,39 @@ Error InferenceServerHttpClient::InferOn(detail::HttpConnection* conn, InferResu
   for (const InferInput* io : inputs) {
     if (io->BinaryData()) all_json = false;
   }
+  std::vector<std::pair<std::string, std::string>> extra = {{kInferHeaderContentLengthHTTPHeader, std::to_string(js.size())},
+                                                            {"Content-Type", all_json ? "application/json" : "application/octet-stream"}};
+  if (response_compression != CompressionType::NONE) {
+    extra.emplace_back("Accept-Encoding", response_compression == CompressionType::GZIP ? "gzip" : "deflate");
+  }
+  if (verbose_) std::cout << "inference request: " << js << std::endl;
+  std::string payload = js;
+  size_t content_length = js.size() + tail_bytes;
+  if (request_compression != CompressionType::NONE) {
+    // the whole body (JSON + tensors) becomes one zlib / gzip stream made on the device; the
+    // Inference-Header-Content-Length keeps the uncompressed JSON size (http_client.cc:1498-1527)
+    payload.reserve(content_length);
+    for (const iovec& v : tails) payload.append(static_cast<const char*>(v.iov_base), v.iov_len);
+    tails.clear();
+    err = detail::DeflateOnDevice(&payload, request_compression == CompressionType::GZIP);
+    if (!err.IsOk()) return err;
+    content_length = payload.size();
+    extra.emplace_back("Content-Encoding", request_compression == CompressionType::GZIP ? "gzip" : "deflate");
+  }
   std::string head = RequestHead(
       "POST", host_, port_, base_path_ + ModelPath(options.model_name_, options.model_version_) + "/infer" + detail::QueryString(query_params),
-      headers,
-      {{kInferHeaderContentLengthHTTPHeader, std::to_string(js.size())},
-       {"Content-Type", all_json ? "application/json" : "application/octet-stream"}},
-      js.size() + tail_bytes);
-  if (verbose_) std::cout << "inference request: " << js << std::endl;
-  head += js;
+      headers, extra, content_length);
+  head += payload;
   detail::HttpResponse resp;
   err = conn->Exchange(head, tails, options.client_timeout_, &resp, &timer);
   if (!err.IsOk()) return err;
+  const auto encoding = resp.headers.find("content-encoding");
+  if (encoding != resp.headers.end() && (encoding->second == "gzip" || encoding->second == "deflate")) {
+    std::string plain;
+    err = detail::Inflate(resp.body, &plain);
+    if (!err.IsOk()) return err;
+    resp.body = std::move(plain);
+  }
   size_t header_length = 0;
   auto it = resp.headers.find("inference-header-content-length");
   if (it != resp.headers.end()) header_length = strtoull(it->second.c_str(), nullptr, 10);
@@ -1331,23 +1421,13 @@ Error InferenceServerHttpClient::InferOn(detail::HttpConnection* conn, InferResu
   return (*result)->RequestStatus();
 }
 
-namespace {
-Error NoCompression(InferenceServerHttpClient::CompressionType a, InferenceServerHttpClient::CompressionType b) {
-  if (a != InferenceServerHttpClient::CompressionType::NONE || b != InferenceServerHttpClient::CompressionType::NONE) {
-    return Error("Compression type needs to be CompressionType::NONE since ZLIB is not included in client build");
-  }
-  return Error::Success;
-}
-}  // namespace
-
 Error InferenceServerHttpClient::Infer(InferResult** result, const InferOptions& options, const std::vector<InferInput*>& inputs,
                                        const std::vector<const InferRequestedOutput*>& outputs, const Headers& headers,
                                        const Parameters& query_params, const CompressionType request_compression_algorithm,
                                        const CompressionType response_compression_algorithm) {
-  Error err = NoCompression(request_compression_algorithm, response_compression_algorithm);
-  if (!err.IsOk()) return err;
   std::lock_guard<std::mutex> lk(sync_mu_);
-  return InferOn(sync_conn_.get(), result, options, inputs, outputs, headers, query_params);
+  return InferOn(sync_conn_.get(), result, options, inputs, outputs, headers, query_params, request_compression_algorithm,
+                 response_compression_algorithm);
 }
 
 void InferenceServerHttpClient::AsyncWorker() {
@@ -1366,7 +1446,8 @@ void InferenceServerHttpClient::AsyncWorker() {
       InferResult* r = nullptr;
       static const std::vector<const InferRequestedOutput*> none;
       const auto& outs = job->outputs.empty() ? none : job->outputs[job->outputs.size() == 1 ? 0 : i];
-      Error err = InferOn(&conn, &r, job->options[i], job->inputs[i], outs, job->headers, job->query_params);
+      Error err = InferOn(&conn, &r, job->options[i], job->inputs[i], outs, job->headers, job->query_params, job->request_compression,
+                          job->response_compression);
       if (r == nullptr) r = new HttpResult(err);
       results.push_back(r);
     }
@@ -1380,9 +1461,9 @@ Error InferenceServerHttpClient::AsyncInfer(OnCompleteFn callback, const InferOp
                                             const Parameters& query_params, const CompressionType request_compression_algorithm,
                                             const CompressionType response_compression_algorithm) {
   if (callback == nullptr) return Error("Callback function must be provided along with AsyncInfer() call.");
-  Error err = NoCompression(request_compression_algorithm, response_compression_algorithm);
-  if (!err.IsOk()) return err;
   auto job = std::make_shared<AsyncJob>();
+  job->request_compression = request_compression_algorithm;
+  job->response_compression = response_compression_algorithm;
   job->callback = std::move(callback);
   job->options.push_back(options);
   job->inputs.push_back(inputs);
@@ -1441,9 +1522,9 @@ Error InferenceServerHttpClient::AsyncInferMulti(OnMultiCompleteFn callback, con
   if (callback == nullptr) return Error("Callback function must be provided along with AsyncInferMulti() call.");
   Error err = CheckMulti(options, inputs, outputs);
   if (!err.IsOk()) return err;
-  err = NoCompression(request_compression_algorithm, response_compression_algorithm);
-  if (!err.IsOk()) return err;
   auto job = std::make_shared<AsyncJob>();
+  job->request_compression = request_compression_algorithm;
+  job->response_compression = response_compression_algorithm;
   job->multi_callback = std::move(callback);
   for (size_t i = 0; i < inputs.size(); ++i) job->options.push_back(options.size() == 1 ? options[0] : options[i]);
   job->inputs = inputs;

@@ -5,8 +5,10 @@
 // Same class and method names, argument meaning and error texts as the reference so that
 // code written against `namespace tc = triton::client;` compiles against this header
 // (compat/http_client.h, compat/common.h alias the namespace).  Differences by design:
-//  * transport is a plain keep-alive HTTP/1.1 socket (no libcurl, no TLS, no body
-//    compression: both report an Error instead of silently doing something else);
+//  * transport is a plain keep-alive HTTP/1.1 socket (no libcurl; TLS reports an Error instead of
+//    silently doing something else); compressed request bodies are made by libtb200's device
+//    encoder (a CUDA device is needed for CompressionType::GZIP|DEFLATE requests), compressed
+//    responses are inflated with zlib;
 //  * CudaRegion (bottom of this file) puts tensors into server-mapped CUDA-IPC memory
 //    through the C ABI of include/tb200.h -- generated, gathered or packed on the device.
 #ifndef TB200_CPP_CLIENT_H_
@@ -221,6 +223,10 @@ class HttpConnection;
 Error BinaryInputToJsonText(const uint8_t* buf, size_t element_count, const std::string& datatype,
                             std::vector<std::string>* items);
 Error BinaryInputsToJsonText(InferInput& input, std::vector<std::string>* items);
+// body compression (http_client.cc:146-254): requests are deflated on the device
+// (tb200_deflate_async, zlib / gzip container), responses inflated with zlib on the host
+Error DeflateOnDevice(std::string* body, bool gzip);
+Error Inflate(const std::string& in, std::string* out);
 }  // namespace detail
 
 // http_client.h:105-651
@@ -324,7 +330,8 @@ class InferenceServerHttpClient : public InferenceServerClient {
              const Parameters& query_params, std::string* response, long* http_code = nullptr);
   Error InferOn(detail::HttpConnection* conn, InferResult** result, const InferOptions& options,
                 const std::vector<InferInput*>& inputs, const std::vector<const InferRequestedOutput*>& outputs,
-                const Headers& headers, const Parameters& query_params);
+                const Headers& headers, const Parameters& query_params, CompressionType request_compression,
+                CompressionType response_compression);
   void AsyncWorker();
 
   std::string host_;

@@ -203,7 +203,7 @@ class GrpcChannel {
 
   void SendHeaders(const std::shared_ptr<GrpcCall>& call) {
     std::string block = h2::grpc_request_headers(authority_, call->path);
-    h2::hpack_literal(&block, "grpc-accept-encoding", "identity");
+    h2::hpack_literal(&block, "grpc-accept-encoding", "identity,deflate,gzip");
     if (!call->encoding.empty()) h2::hpack_literal(&block, "grpc-encoding", call->encoding);
     if (call->timeout_us != 0) h2::hpack_literal(&block, "grpc-timeout", std::to_string(call->timeout_us) + "u");
     for (const auto& kv : call->metadata) h2::hpack_literal(&block, Lower(kv.first), kv.second);
@@ -357,14 +357,18 @@ class GrpcChannel {
       const uint8_t* h = reinterpret_cast<const uint8_t*>(call->rx.data()) + off;
       const uint32_t len = h2::get_u32(h + 1);
       if (call->rx.size() - off - 5 < len) break;
-      if (h[0] != 0) {  // we advertise grpc-accept-encoding: identity
-        std::string code;
-        h2::put_u32(&code, 8);
-        out_ += h2::frame(h2::RST_STREAM, 0, stream, code);
-        Finish(call, kUnimplemented, "compressed response messages are not supported");
-        return;
-      }
       std::string message = call->rx.substr(off + 5, len);
+      if (h[0] != 0) {  // compressed with the response's grpc-encoding (deflate = zlib stream, or gzip)
+        std::string plain;
+        if (!detail::Inflate(message, &plain).IsOk()) {
+          std::string code;
+          h2::put_u32(&code, 8);
+          out_ += h2::frame(h2::RST_STREAM, 0, stream, code);
+          Finish(call, kInternal, "failed to decompress a response message");
+          return;
+        }
+        message = std::move(plain);
+      }
       off += 5 + static_cast<size_t>(len);
       if (call->on_message) call->on_message(std::move(message));
       else call->response = std::move(message);
@@ -810,43 +814,9 @@ Error AppendInferMessage(std::string* message, const InferOptions& options, cons
   return Error::Success;
 }
 
-// message body -> zlib ("deflate") / gzip container, produced on the device (tb200_deflate_async)
+// message body -> zlib ("deflate") / gzip container, produced on the device (tb200_client.cc)
 Error CompressOnDevice(std::string* body, grpc_compression_algorithm algorithm) {
-  int count = 0;
-  if (tb200_device_count(&count) != TB200_OK || count < 1) {
-    return Error("request compression runs on the device (tb200_deflate_async) and no CUDA device is available");
-  }
-  tb200_ctx* ctx = nullptr;
-  if (tb200_ctx_create(0, &ctx) != TB200_OK) return Error(std::string("request compression: ") + tb200_last_error());
-  const uint64_t n = body->size();
-  const uint64_t cap = tb200_deflate_bound(n);
-  void *src = nullptr, *dst = nullptr, *host = nullptr, *host_dev = nullptr;
-  Error err;
-  auto check = [&err](int rc) {
-    if (rc != TB200_OK && err.IsOk()) err = Error(std::string("request compression: ") + tb200_last_error());
-    return rc == TB200_OK;
-  };
-  // pinned staging: [compressed stream (cap) | pad | uint64 size]
-  const uint64_t size_off = (cap + 15) & ~static_cast<uint64_t>(15);
-  if (check(tb200_device_alloc(0, n + 16, &src)) && check(tb200_device_alloc(0, cap + 16, &dst)) &&
-      check(tb200_host_alloc(size_off + 16, &host, &host_dev)) &&
-      check(tb200_memcpy_h2d_async(ctx, src, body->data(), n)) &&
-      check(tb200_deflate_async(ctx, dst, cap, src, n, algorithm == GRPC_COMPRESS_GZIP ? TB200_DEFLATE_GZIP : TB200_DEFLATE_ZLIB,
-                                reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(host_dev) + size_off))) &&
-      check(tb200_ctx_sync(ctx))) {
-    uint64_t out_size = 0;
-    memcpy(&out_size, static_cast<uint8_t*>(host) + size_off, 8);
-    if (out_size == 0 || out_size > cap) {
-      err = Error("request compression: the device encoder reported an invalid stream size");
-    } else if (check(tb200_memcpy_d2h_async(ctx, host, dst, out_size)) && check(tb200_ctx_sync(ctx))) {
-      body->assign(static_cast<const char*>(host), out_size);
-    }
-  }
-  if (src) tb200_device_free(0, src);
-  if (dst) tb200_device_free(0, dst);
-  if (host) tb200_host_free(host);
-  tb200_ctx_destroy(ctx);
-  return err;
+  return detail::DeflateOnDevice(body, algorithm == GRPC_COMPRESS_GZIP);
 }
 
 }  // namespace

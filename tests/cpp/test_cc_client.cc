@@ -449,10 +449,6 @@ static void TestLoopback(const std::string& url) {
   tc::InferStat stat;
   CHECK_OK(client->ClientInferStat(&stat));
   CHECK(stat.completed_request_count >= 12 && stat.cumulative_total_request_time_ns > stat.cumulative_send_time_ns);
-  CHECK(client->Infer(nullptr, options, {}, {}, tc::Headers(), tc::Parameters(),
-                      tc::InferenceServerHttpClient::CompressionType::GZIP)
-            .Message()
-            .find("ZLIB") != std::string::npos);
   delete o0;
   delete o1;
 }
@@ -513,6 +509,62 @@ static void TestBytesInputFromStrings() {
   delete s;
 }
 
+// body compression (http_client.cc:146-254): responses inflated with zlib on the host; requests
+// deflated by the device encoder (argv[2] says whether a CUDA device is expected)
+static void TestCompression(const std::string& url, bool expect_device) {
+  using CT = tc::InferenceServerHttpClient::CompressionType;
+  std::unique_ptr<tc::InferenceServerHttpClient> client;
+  CHECK_OK(tc::InferenceServerHttpClient::Create(&client, url));
+  std::vector<int32_t> big(50000);
+  for (size_t i = 0; i < big.size(); ++i) big[i] = static_cast<int32_t>(i % 251);
+  tc::InferInput* in;
+  tc::InferInput::Create(&in, "INPUT0", {static_cast<int64_t>(big.size())}, "INT32");
+  in->AppendRaw(reinterpret_cast<uint8_t*>(big.data()), big.size() * 4);
+  tc::InferOptions opt("custom_identity_int32");
+  auto same = [&](tc::InferResult* r) {
+    const uint8_t* p = nullptr;
+    size_t n = 0;
+    return r != nullptr && r->RequestStatus().IsOk() && r->RawData("OUTPUT0", &p, &n).IsOk() && n == big.size() * 4 &&
+           memcmp(p, big.data(), n) == 0;
+  };
+  for (CT response : {CT::GZIP, CT::DEFLATE}) {  // the server compresses, zlib inflates
+    tc::InferResult* result = nullptr;
+    CHECK_OK(client->Infer(&result, opt, {in}, {}, tc::Headers(), tc::Parameters(), CT::NONE, response));
+    CHECK(same(result));
+    delete result;
+  }
+  {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool done = false, ok = false;
+    CHECK_OK(client->AsyncInfer(
+        [&](tc::InferResult* r) {
+          std::lock_guard<std::mutex> lk(mu);
+          ok = same(r);
+          done = true;
+          delete r;
+          cv.notify_all();
+        },
+        opt, {in}, {}, tc::Headers(), tc::Parameters(), CT::NONE, CT::GZIP));
+    std::unique_lock<std::mutex> lk(mu);
+    CHECK(cv.wait_for(lk, std::chrono::seconds(20), [&] { return done; }) && ok);
+  }
+  for (CT request : {CT::GZIP, CT::DEFLATE}) {  // made by tb200_deflate_async, inflated by the server
+    tc::InferResult* result = nullptr;
+    tc::Error err = client->Infer(&result, opt, {in}, {}, tc::Headers(), tc::Parameters(), request, CT::GZIP);
+    if (expect_device) {
+      CHECK_OK(err);
+      CHECK(same(result));
+    } else {
+      CHECK(!err.IsOk() && err.Message().find("no CUDA device") != std::string::npos);
+    }
+    delete result;
+  }
+  std::string plain;
+  CHECK(!tc::detail::Inflate("not a zlib stream", &plain).IsOk());
+  delete in;
+}
+
 int main(int argc, char** argv) {
   TestJsonParser();
   TestBytesInputFromStrings();
@@ -523,7 +575,8 @@ int main(int argc, char** argv) {
   TestScatterList();
   TestRequestBody();
   TestTimers();
-  if (argc > 1) TestLoopback(argv[1]);
+  if (argc > 2 && std::string(argv[2]).rfind("compress", 0) == 0) TestCompression(argv[1], std::string(argv[2]) == "compress-gpu");
+  else if (argc > 1) TestLoopback(argv[1]);
   if (g_failures == 0) {
     std::cout << "PASS" << (argc > 1 ? " (offline + loopback)" : " (offline)") << std::endl;
     return 0;

@@ -556,7 +556,7 @@ static void TestSlowServer(const std::string& url) {
 // request compression: the message body becomes a zlib / gzip stream made by the device encoder
 // (tb200_deflate_async), flagged in the 5-byte prefix and announced as grpc-encoding; the grpcio
 // server inflates it.  Without a device the call reports an Error (there is no host encoder).
-static void TestCompression(const std::string& url, bool expect_device) {
+static void TestCompression(const std::string& url, bool expect_device, bool responses_only = false) {
   std::unique_ptr<tc::InferenceServerGrpcClient> client;
   CHECK_OK(tc::InferenceServerGrpcClient::Create(&client, url));
   std::vector<int32_t> big(100000);
@@ -565,6 +565,21 @@ static void TestCompression(const std::string& url, bool expect_device) {
   tc::InferInput::Create(&in, "INPUT0", {static_cast<int64_t>(big.size())}, "INT32");
   in->AppendRaw(reinterpret_cast<uint8_t*>(big.data()), big.size() * 4);
   tc::InferOptions opt("custom_identity_int32");
+  if (responses_only) {  // a server that compresses its responses (flag 1 + grpc-encoding): zlib inflates them
+    for (int i = 0; i < 3; ++i) {
+      tc::InferResult* result = nullptr;
+      CHECK_OK(client->Infer(&result, opt, {in}));
+      const uint8_t* p = nullptr;
+      size_t n = 0;
+      if (result != nullptr) {
+        CHECK_OK(result->RawData("OUTPUT0", &p, &n));
+        CHECK(n == big.size() * 4 && memcmp(p, big.data(), n) == 0);
+      }
+      delete result;
+    }
+    delete in;
+    return;
+  }
   for (grpc_compression_algorithm algo : {GRPC_COMPRESS_GZIP, GRPC_COMPRESS_DEFLATE}) {
     tc::InferResult* result = nullptr;
     tc::Error err = client->Infer(&result, opt, {in}, {}, tc::Headers(), algo);
@@ -685,6 +700,7 @@ int main(int argc, char** argv) {
   if (argc > 2 && std::string(argv[2]) == "slow") TestSlowServer(argv[1]);
   else if (argc > 2 && std::string(argv[2]) == "compress-gpu") TestCompression(argv[1], true);
   else if (argc > 2 && std::string(argv[2]) == "compress-nogpu") TestCompression(argv[1], false);
+  else if (argc > 2 && std::string(argv[2]) == "compressed-responses") TestCompression(argv[1], false, true);
   else if (argc > 1) TestLoopback(argv[1]);
   if (g_failures == 0) {
     std::cout << "PASS" << (argc > 1 ? " (offline + loopback)" : " (offline)") << std::endl;

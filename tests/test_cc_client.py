@@ -83,3 +83,38 @@ def test_loopback_simple_model(binary):
     finally:
         proc.terminate()
         proc.wait(10)
+
+
+def _has_gpu():
+    import ctypes
+
+    from client_b200 import _native
+
+    n = ctypes.c_int(0)
+    return _native.load().tb200_device_count(ctypes.byref(n)) == 0 and n.value > 0
+
+
+def test_body_compression_without_a_device(binary):
+    """Responses: the mock server compresses on Accept-Encoding, zlib inflates.  Requests: made by the
+    device encoder only -- without a CUDA device the call reports that."""
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    proc, http_port, _ = start_server()
+    try:
+        r = subprocess.run([binary, "127.0.0.1:%d" % http_port, "compress-nogpu"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+    finally:
+        proc.terminate()
+        proc.wait(10)
+
+
+@pytest.mark.gpu
+def test_body_compression_on_the_device(binary):
+    """gzip / deflate request bodies produced by tb200_deflate_async, inflated by the server; gzip responses."""
+    proc, http_port, _ = start_server()
+    try:
+        r = subprocess.run([binary, "127.0.0.1:%d" % http_port, "compress-gpu"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+    finally:
+        proc.terminate()
+        proc.wait(10)

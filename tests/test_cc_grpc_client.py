@@ -301,6 +301,40 @@ def test_request_compression_needs_the_device(binary):
         proc.wait(10)
 
 
+@pytest.mark.parametrize("algorithm", ["Gzip", "Deflate"])
+def test_compressed_responses_are_inflated(binary, algorithm):
+    """A grpcio server configured to compress its responses (message flag 1 + grpc-encoding): the
+    client announces identity,deflate,gzip and inflates with zlib."""
+    from concurrent import futures
+
+    import grpc
+
+    from client_b200.grpc import service_pb2, service_pb2_grpc
+
+    seen = []
+
+    class Identity(service_pb2_grpc.GRPCInferenceServiceServicer):
+        def ModelInfer(self, request, context):
+            seen.append(dict(context.invocation_metadata()).get("grpc-accept-encoding"))
+            resp = service_pb2.ModelInferResponse(model_name=request.model_name, model_version="1")
+            out = resp.outputs.add()
+            out.name, out.datatype = "OUTPUT0", request.inputs[0].datatype
+            out.shape.extend(request.inputs[0].shape)
+            resp.raw_output_contents.append(request.raw_input_contents[0])
+            return resp
+
+    srv = grpc.server(futures.ThreadPoolExecutor(max_workers=2), compression=getattr(grpc.Compression, algorithm))
+    service_pb2_grpc.add_GRPCInferenceServiceServicer_to_server(Identity(), srv)
+    port = srv.add_insecure_port("127.0.0.1:0")
+    srv.start()
+    try:
+        r = subprocess.run([binary, "127.0.0.1:%d" % port, "compressed-responses"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]
+        assert len(seen) == 3
+    finally:
+        srv.stop(0)
+
+
 @pytest.mark.gpu
 def test_request_compression_on_the_device(binary):
     """gzip / deflate message encoding produced by tb200_deflate_async, inflated by the grpcio server."""
@@ -338,7 +372,7 @@ def test_thread_sanitizer_clean(tmp_path):
     build = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-I" + os.path.join(cpp, "compat"), "-I" + cpp,
                             "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_cc_grpc_client.cc"),
                             os.path.join(cpp, "tb200_client.cc"), os.path.join(cpp, "tb200_grpc_client.cc"), "-o", exe,
-                            "-L" + LIBDIR, "-ltb200", "-Wl,-rpath," + LIBDIR, "-lpthread"], capture_output=True, text=True)
+                            "-L" + LIBDIR, "-ltb200", "-Wl,-rpath," + LIBDIR, "-lpthread", "-lz"], capture_output=True, text=True)
     if build.returncode != 0:
         pytest.skip("no ThreadSanitizer runtime for g++ here: " + build.stderr[-200:])
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0")
