@@ -84,9 +84,16 @@ struct GrpcCall {
   }
 };
 
+struct ChannelKeepAlive {
+  int time_ms = INT_MAX;       // silence from the peer after which a PING goes out
+  int timeout_ms = 20000;      // how long its acknowledgement may take
+  bool without_calls = false;  // ping even when no call is in flight
+};
+
 class GrpcChannel {
  public:
-  static Error Connect(const std::string& url, std::shared_ptr<GrpcChannel>* out) {
+  using KeepAlive = ChannelKeepAlive;
+  static Error Connect(const std::string& url, std::shared_ptr<GrpcChannel>* out, const KeepAlive& keepalive = KeepAlive()) {
     std::string host = url;
     std::string port = "80";
     const size_t scheme = host.find("://");
@@ -117,6 +124,7 @@ class GrpcChannel {
     setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
     fcntl(fd, F_SETFL, fcntl(fd, F_GETFL, 0) | O_NONBLOCK);
     std::shared_ptr<GrpcChannel> ch(new GrpcChannel(fd, host + ":" + port));
+    ch->keepalive_ = keepalive;
     ch->io_ = std::thread(&GrpcChannel::IoMain, ch.get());
     *out = std::move(ch);
     return Error::Success;
@@ -405,6 +413,7 @@ class GrpcChannel {
           break;
         case h2::PING:
           if (!(f.flags & h2::kAck) && len == 8) out_ += h2::frame(h2::PING, h2::kAck, 0, std::string(reinterpret_cast<const char*>(p), 8));
+          else if (f.flags & h2::kAck) ping_outstanding_ = false;
           break;
         case h2::WINDOW_UPDATE:
           if (len == 4) {
@@ -502,8 +511,24 @@ class GrpcChannel {
     }
   }
 
+  // GRPC keepalive (doc/keepalive.md): PING after keepalive_time of silence from the peer, the
+  // connection is declared dead when the acknowledgement does not arrive within keepalive_timeout
+  void KeepAliveTick() {
+    if (keepalive_.time_ms == INT_MAX || broken_.load()) return;
+    const Clock::time_point now = Clock::now();
+    if (ping_outstanding_) {
+      if (now - ping_sent_ > std::chrono::milliseconds(keepalive_.timeout_ms)) FailAll("keepalive watchdog timeout");
+      return;
+    }
+    if ((streams_.empty() && !keepalive_.without_calls) || now - last_read_ < std::chrono::milliseconds(keepalive_.time_ms)) return;
+    out_ += h2::frame(h2::PING, 0, 0, std::string("tb200png", 8));
+    ping_outstanding_ = true;
+    ping_sent_ = now;
+  }
+
   int PollTimeoutMs() const {
     int ms = 200;
+    if (keepalive_.time_ms != INT_MAX) ms = std::max(1, std::min(ms, std::min(keepalive_.time_ms, keepalive_.timeout_ms) / 2));
     const Clock::time_point now = Clock::now();
     for (const auto& kv : streams_) {
       if (!kv.second->has_deadline) continue;
@@ -555,6 +580,7 @@ class GrpcChannel {
           const ssize_t k = recv(fd_, tmp, sizeof(tmp), 0);
           if (k > 0) {
             in_.append(tmp, static_cast<size_t>(k));
+            last_read_ = Clock::now();
             if (static_cast<size_t>(k) < sizeof(tmp)) break;
             continue;
           }
@@ -566,6 +592,7 @@ class GrpcChannel {
         if (!broken_.load() && !HandleFrames()) FailAll("malformed HTTP/2 frame from the server");
       }
       CheckDeadlines();
+      KeepAliveTick();
     }
     FailAll("the client was closed");
     // anything queued but never started
@@ -595,6 +622,9 @@ class GrpcChannel {
   int64_t peer_initial_window_ = h2::kDefaultWindow;
   uint32_t peer_max_frame_ = h2::kDefaultMaxFrame;
   uint32_t conn_recv_consumed_ = 0;
+  KeepAlive keepalive_;
+  bool ping_outstanding_ = false;
+  Clock::time_point ping_sent_{}, last_read_ = Clock::now();
   h2::HpackDecoder hpack_;
   std::string header_block_;
   uint32_t header_stream_ = 0;
@@ -822,8 +852,9 @@ Error CompressOnDevice(std::string* body, grpc_compression_algorithm algorithm) 
 }  // namespace
 
 // =================================================================================================
-InferenceServerGrpcClient::InferenceServerGrpcClient(const std::string& url, bool verbose, bool use_cached_channel)
-    : InferenceServerClient(verbose), url_(url), use_cached_channel_(use_cached_channel) {
+InferenceServerGrpcClient::InferenceServerGrpcClient(const std::string& url, bool verbose, bool use_cached_channel,
+                                                     const KeepAliveOptions& keepalive)
+    : InferenceServerClient(verbose), keepalive_(keepalive), url_(url), use_cached_channel_(use_cached_channel) {
   worker_ = std::thread(&InferenceServerGrpcClient::CallbackWorker, this);
 }
 
@@ -853,17 +884,29 @@ InferenceServerGrpcClient::~InferenceServerGrpcClient() {
 }
 
 Error InferenceServerGrpcClient::Create(std::unique_ptr<InferenceServerGrpcClient>* client, const std::string& server_url,
-                                        bool verbose, bool use_ssl, const SslOptions&, const KeepAliveOptions&,
+                                        bool verbose, bool use_ssl, const SslOptions&, const KeepAliveOptions& keepalive_options,
                                         const bool use_cached_channel) {
   if (use_ssl) return Error("TLS is not built into this client: use_ssl must be false");
-  client->reset(new InferenceServerGrpcClient(server_url, verbose, use_cached_channel));
+  client->reset(new InferenceServerGrpcClient(server_url, verbose, use_cached_channel, keepalive_options));
   return Error::Success;
 }
 Error InferenceServerGrpcClient::Create(std::unique_ptr<InferenceServerGrpcClient>* client, const std::string& server_url,
-                                        const grpc::ChannelArguments&, bool verbose, bool use_ssl, const SslOptions&,
+                                        const grpc::ChannelArguments& channel_args, bool verbose, bool use_ssl, const SslOptions&,
                                         const bool use_cached_channel) {
   if (use_ssl) return Error("TLS is not built into this client: use_ssl must be false");
-  client->reset(new InferenceServerGrpcClient(server_url, verbose, use_cached_channel));
+  KeepAliveOptions keepalive;  // the keep-alive arguments among the generic ones
+  const auto& ints = channel_args.ints();
+  auto get = [&ints](const char* key, int* out) {
+    const auto it = ints.find(key);
+    if (it != ints.end()) *out = it->second;
+  };
+  int permit = keepalive.keepalive_permit_without_calls ? 1 : 0;
+  get(GRPC_ARG_KEEPALIVE_TIME_MS, &keepalive.keepalive_time_ms);
+  get(GRPC_ARG_KEEPALIVE_TIMEOUT_MS, &keepalive.keepalive_timeout_ms);
+  get(GRPC_ARG_KEEPALIVE_PERMIT_WITHOUT_CALLS, &permit);
+  get(GRPC_ARG_HTTP2_MAX_PINGS_WITHOUT_DATA, &keepalive.http2_max_pings_without_data);
+  keepalive.keepalive_permit_without_calls = permit != 0;
+  client->reset(new InferenceServerGrpcClient(server_url, verbose, use_cached_channel, keepalive));
   return Error::Success;
 }
 
@@ -892,7 +935,11 @@ Error InferenceServerGrpcClient::Channel(std::shared_ptr<detail::GrpcChannel>* c
     }
   }
   if (!channel_) {
-    Error err = detail::GrpcChannel::Connect(url_, &channel_);
+    detail::GrpcChannel::KeepAlive ka;
+    ka.time_ms = keepalive_.keepalive_time_ms;
+    ka.timeout_ms = keepalive_.keepalive_timeout_ms;
+    ka.without_calls = keepalive_.keepalive_permit_without_calls;
+    Error err = detail::GrpcChannel::Connect(url_, &channel_, ka);
     if (!err.IsOk()) return err;
     if (use_cached_channel_) {
       std::lock_guard<std::mutex> cache_lk(g_cache_mu);

@@ -10,7 +10,10 @@
 //    (one copy; the reference copies into the protobuf and again at serialisation);
 //  * request compression (deflate / gzip message encoding) is done by libtb200's device
 //    encoder (tb200_deflate_async) and needs a GPU; responses are requested uncompressed;
-//  * KeepAliveOptions / ChannelArguments are accepted and not acted upon.
+//  * KeepAliveOptions: keepalive_time_ms / keepalive_timeout_ms / keepalive_permit_without_calls are
+//    honoured with HTTP/2 PING frames (a ping that is not acknowledged in time fails the calls in
+//    flight with "keepalive watchdog timeout" and the next call reconnects); generic
+//    grpc::ChannelArguments are recorded, the GRPC_ARG_KEEPALIVE_* ones among them are honoured too.
 #ifndef TB200_CPP_GRPC_CLIENT_H_
 #define TB200_CPP_GRPC_CLIENT_H_
 
@@ -169,7 +172,8 @@ class InferenceServerGrpcClient : public InferenceServerClient {
                                          std::vector<const InferRequestedOutput*>());
 
  private:
-  InferenceServerGrpcClient(const std::string& url, bool verbose, bool use_cached_channel);
+  InferenceServerGrpcClient(const std::string& url, bool verbose, bool use_cached_channel, const KeepAliveOptions& keepalive);
+  KeepAliveOptions keepalive_;
   Error Channel(std::shared_ptr<detail::GrpcChannel>* channel);
   Error Unary(const char* method, const tb200::pb::Message& request, tb200::pb::Message* response, const Headers& headers,
               uint64_t timeout_us = 0);

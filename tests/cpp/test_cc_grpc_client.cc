@@ -17,6 +17,7 @@
 #include <iostream>
 #include <mutex>
 #include <sstream>
+#include <thread>
 
 #include "grpc_client.h"
 
@@ -681,6 +682,65 @@ static void TestReconnect() {
   delete in;
 }
 
+// KeepAliveOptions (grpc_client.h:63-85): PINGs keep an idle connection checked; a peer that stops
+// answering fails the calls in flight with the watchdog's message instead of hanging them.
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <sys/socket.h>
+#include <unistd.h>
+static void TestKeepAlive() {
+  inference::ModelInferResponse canned;
+  canned.set_model_name("stub");
+  const std::string bytes = canned.SerializeAsString();
+  int port = 0;
+  tb200_grpc_stub_server* srv = nullptr;
+  CHECK(tb200_grpc_stub_server_start("127.0.0.1", &port, reinterpret_cast<const uint8_t*>(bytes.data()), bytes.size(), &srv) == 0);
+  tc::KeepAliveOptions ka;
+  ka.keepalive_time_ms = 20;
+  ka.keepalive_timeout_ms = 500;
+  ka.keepalive_permit_without_calls = true;
+  {
+    std::unique_ptr<tc::InferenceServerGrpcClient> client;
+    CHECK_OK(tc::InferenceServerGrpcClient::Create(&client, "127.0.0.1:" + std::to_string(port), false, false, tc::SslOptions(), ka, false));
+    tc::InferInput* in;
+    tc::InferInput::Create(&in, "INPUT0", {1}, "INT32");
+    const int32_t one = 1;
+    in->AppendRaw(reinterpret_cast<const uint8_t*>(&one), 4);
+    for (int i = 0; i < 6; ++i) {  // 60 ms of silence between calls: pings go out and are acknowledged
+      tc::InferResult* r = nullptr;
+      CHECK_OK(client->Infer(&r, tc::InferOptions("m"), {in}));
+      delete r;
+      std::this_thread::sleep_for(std::chrono::milliseconds(60));
+    }
+    delete in;
+  }
+  tb200_grpc_stub_server_stop(srv);
+  // a peer that accepts the connection and never says anything
+  const int lfd = socket(AF_INET, SOCK_STREAM, 0);
+  sockaddr_in addr{};
+  addr.sin_family = AF_INET;
+  inet_pton(AF_INET, "127.0.0.1", &addr.sin_addr);
+  CHECK(bind(lfd, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) == 0 && listen(lfd, 4) == 0);
+  socklen_t len = sizeof(addr);
+  getsockname(lfd, reinterpret_cast<sockaddr*>(&addr), &len);
+  std::atomic<int> accepted{-1};
+  std::thread mute([&] { accepted = accept(lfd, nullptr, nullptr); });
+  ka.keepalive_time_ms = 50;
+  ka.keepalive_timeout_ms = 150;
+  {
+    std::unique_ptr<tc::InferenceServerGrpcClient> client;
+    CHECK_OK(tc::InferenceServerGrpcClient::Create(&client, "127.0.0.1:" + std::to_string(ntohs(addr.sin_port)), false, false, tc::SslOptions(), ka, false));
+    bool live = true;
+    const auto t0 = std::chrono::steady_clock::now();
+    tc::Error err = client->IsServerLive(&live);  // no deadline: only the watchdog can end it
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    CHECK(!err.IsOk() && err.Message() == "keepalive watchdog timeout" && ms > 150.0 && ms < 2000.0);
+  }
+  mute.join();
+  if (accepted >= 0) close(accepted);
+  close(lfd);
+}
+
 int main(int argc, char** argv) {
   if (argc > 2 && std::string(argv[1]) == "--roundtrip") return RoundTrip(argv[2]);
   if (argc > 1 && std::string(argv[1]) == "--requests") {
@@ -697,6 +757,7 @@ int main(int argc, char** argv) {
     CHECK(!client->IsServerLive(&live).IsOk() && !live);  // nothing listens there
   }
   TestReconnect();
+  TestKeepAlive();
   if (argc > 2 && std::string(argv[2]) == "slow") TestSlowServer(argv[1]);
   else if (argc > 2 && std::string(argv[2]) == "compress-gpu") TestCompression(argv[1], true);
   else if (argc > 2 && std::string(argv[2]) == "compress-nogpu") TestCompression(argv[1], false);
