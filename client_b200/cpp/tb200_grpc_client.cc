@@ -1453,3 +1453,71 @@ Error InferenceServerGrpcClient::AsyncStreamInfer(const InferOptions& options, c
 }
 
 }}  // namespace tb200::client
+
+// =================================================================================================
+// C entry points over the channel for other front ends (the Python drop-in's opt-in native gRPC
+// transport, client_b200/grpc/_native_channel.py): one blocking unary call, bytes in, bytes out.
+// Declared in tb200_grpc_channel.h.
+#include "tb200_grpc_channel.h"
+
+struct tb200c_grpc_channel {
+  std::string url;
+  std::mutex mu;
+  std::shared_ptr<tb200::client::detail::GrpcChannel> channel;
+};
+
+extern "C" {
+
+int tb200c_grpc_channel_open(const char* url, tb200c_grpc_channel** out) {
+  if (url == nullptr || out == nullptr) return -1;
+  tb200c_grpc_channel* c = new tb200c_grpc_channel();
+  c->url = url;
+  *out = c;
+  return 0;  // the connection is made by the first call (and re-made after a failure)
+}
+
+void tb200c_grpc_channel_close(tb200c_grpc_channel* c) { delete c; }
+
+int tb200c_grpc_unary(tb200c_grpc_channel* c, const char* path, const uint8_t* request, uint64_t request_bytes, const char* const* metadata,
+                      int metadata_pairs, uint64_t timeout_us, uint8_t** response, uint64_t* response_bytes, char* message, uint64_t message_cap) {
+  using namespace tb200::client;
+  auto fail = [&](int status, const std::string& text) {
+    if (message != nullptr && message_cap != 0) snprintf(message, message_cap, "%s", text.c_str());
+    if (response != nullptr) *response = nullptr;
+    if (response_bytes != nullptr) *response_bytes = 0;
+    return status;
+  };
+  if (c == nullptr || path == nullptr || response == nullptr || response_bytes == nullptr || (request == nullptr && request_bytes != 0)) {
+    return fail(3, "NULL argument");
+  }
+  std::shared_ptr<detail::GrpcChannel> channel;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->channel || c->channel->Broken()) {
+      c->channel.reset();
+      Error err = detail::GrpcChannel::Connect(c->url, &c->channel);
+      if (!err.IsOk()) return fail(kUnavailable, err.Message());
+    }
+    channel = c->channel;
+  }
+  auto call = std::make_shared<detail::GrpcCall>();
+  call->path = path;
+  call->timeout_us = timeout_us;
+  for (int i = 0; i < metadata_pairs; ++i) call->metadata[metadata[2 * i]] = metadata[2 * i + 1];
+  std::string framed(5, '\0');
+  framed.append(reinterpret_cast<const char*>(request), request_bytes);
+  tb200::h2::put_grpc_prefix(reinterpret_cast<uint8_t*>(&framed[0]), static_cast<uint32_t>(request_bytes));
+  channel->Start(call, std::move(framed), true);
+  call->Wait();
+  if (call->status != kOk) return fail(call->status, call->status_message);
+  *response_bytes = call->response.size();
+  *response = static_cast<uint8_t*>(malloc(call->response.size() == 0 ? 1 : call->response.size()));
+  if (*response == nullptr) return fail(kResourceExhausted, "out of memory");
+  memcpy(*response, call->response.data(), call->response.size());
+  if (message != nullptr && message_cap != 0) message[0] = '\0';
+  return 0;
+}
+
+void tb200c_free(void* p) { free(p); }
+
+}  // extern "C"

@@ -10,6 +10,7 @@ statistics / trace / log / shared-memory control and for ``infer``,
 
 import base64
 import json
+import os
 
 import grpc
 from google.protobuf.json_format import MessageToJson
@@ -92,8 +93,18 @@ class InferenceServerClient(InferenceServerClientBase):
     """
 
     def __init__(self, url, verbose=False, ssl=False, root_certificates=None, private_key=None,
-                 certificate_chain=None, creds=None, keepalive_options=None, channel_args=None):
+                 certificate_chain=None, creds=None, keepalive_options=None, channel_args=None, transport=None):
         super().__init__()
+        # transport="native" (extension of this drop-in, default from TB200_GRPC_TRANSPORT): infer()
+        # rides on libtb200client's own HTTP/2 channel instead of grpcio (cleartext only)
+        transport = transport or os.environ.get("TB200_GRPC_TRANSPORT", "grpcio")
+        if transport not in ("grpcio", "native"):
+            raise_error("transport must be 'grpcio' or 'native'")
+        self._native = None
+        if transport == "native" and not (ssl or creds):
+            from ._native_channel import NativeChannel
+
+            self._native = NativeChannel(url)
         if channel_args is not None:
             options = channel_args
         else:
@@ -142,6 +153,9 @@ class InferenceServerClient(InferenceServerClientBase):
         """Stop the stream, if any, and close the channel."""
         self.stop_stream()
         self._channel.close()
+        if self._native is not None:
+            self._native.close()
+            self._native = None
 
     # one round trip of a unary control-plane rpc
     def _unary(self, rpc, request, headers, client_timeout, label=None):
@@ -335,6 +349,12 @@ class InferenceServerClient(InferenceServerClientBase):
                                       sequence_start, sequence_end, priority, timeout, parameters)
         if self._verbose:
             print("infer, metadata {}\n{}".format(metadata, request))
+        if self._native is not None and compression_algorithm is None:
+            raw = self._native.unary("/inference.GRPCInferenceService/ModelInfer", request.SerializeToString(), metadata, client_timeout)
+            response = service_pb2.ModelInferResponse.FromString(raw)
+            if self._verbose:
+                print(response)
+            return InferResult(response)
         try:
             response = self._client_stub.ModelInfer(
                 request=request, metadata=metadata, timeout=client_timeout,

@@ -218,3 +218,64 @@ def test_grpc_decoupled_stream(server):
         client.stop_stream()
         with pytest.raises(InferenceServerException, match="stream not available"):
             client.async_stream_infer("llama3_8b", [inp])
+
+
+def test_grpc_native_transport_for_infer(server):
+    """InferenceServerClient(url, transport="native"): infer() over libtb200client's own HTTP/2
+    channel instead of grpcio -- same results, same InferenceServerException status / message
+    mapping, client_timeout as a deadline; every other call stays on grpcio."""
+    import threading
+
+    a = np.arange(16, dtype=np.int32)[None, :]
+    b = np.full((1, 16), 2, np.int32)
+
+    def inputs():
+        return [grpcclient.InferInput("INPUT0", [1, 16], "INT32").set_data_from_numpy(a),
+                grpcclient.InferInput("INPUT1", [1, 16], "INT32").set_data_from_numpy(b)]
+
+    with grpcclient.InferenceServerClient(server["grpc"], transport="native") as client:
+        assert client.is_server_live()  # grpcio
+        res = client.infer("simple", inputs(), request_id="n1", headers={"x-test": "1"},
+                           outputs=[grpcclient.InferRequestedOutput("OUTPUT0"), grpcclient.InferRequestedOutput("OUTPUT1")])
+        assert np.array_equal(res.as_numpy("OUTPUT0"), a + b) and np.array_equal(res.as_numpy("OUTPUT1"), a - b)
+        assert res.get_response().id == "n1"
+        with pytest.raises(InferenceServerException) as ei:
+            client.infer("no_such_model", inputs())
+        assert ei.value.status() == "StatusCode.NOT_FOUND" and "no_such_model" in ei.value.message()
+        big = np.arange(300000, dtype=np.int32)
+        res = client.infer("custom_identity_int32", [grpcclient.InferInput("INPUT0", [300000], "INT32").set_data_from_numpy(big)])
+        assert np.array_equal(res.as_numpy("OUTPUT0"), big)
+        errors = []
+
+        def worker():
+            try:
+                for _ in range(20):
+                    r = client.infer("simple", inputs())
+                    assert np.array_equal(r.as_numpy("OUTPUT0"), a + b)
+            except Exception as ex:  # noqa: BLE001
+                errors.append(ex)
+
+        threads = [threading.Thread(target=worker) for _ in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors
+    with pytest.raises(InferenceServerException):
+        grpcclient.InferenceServerClient(server["grpc"], transport="carrier-pigeon")
+
+
+def test_grpc_native_transport_deadline():
+    proc, _, grpc_port = start_server(["--delay-us", "400000"])
+    try:
+        with grpcclient.InferenceServerClient("127.0.0.1:%d" % grpc_port, transport="native") as client:
+            a = np.zeros((1, 16), np.int32)
+            ins = [grpcclient.InferInput("INPUT0", [1, 16], "INT32").set_data_from_numpy(a),
+                   grpcclient.InferInput("INPUT1", [1, 16], "INT32").set_data_from_numpy(a)]
+            with pytest.raises(InferenceServerException) as ei:
+                client.infer("simple", ins, client_timeout=0.05)
+            assert ei.value.status() == "StatusCode.DEADLINE_EXCEEDED" and ei.value.message() == "Deadline Exceeded"
+            assert np.array_equal(client.infer("simple", ins, client_timeout=5).as_numpy("OUTPUT0"), a)
+    finally:
+        proc.terminate()
+        proc.wait(10)
