@@ -86,6 +86,44 @@ def test_unmodified_reference_example(outcomes, label):
     assert "FAILED" not in tail, tail
 
 
+# ---- the same gRPC examples with infer() on the native transport (TB200_GRPC_TRANSPORT=native) --
+NATIVE_TRANSPORT_SCRIPTS = [
+    "grpc_client.py", "grpc_explicit_byte_content_client.py", "grpc_explicit_int8_content_client.py", "grpc_explicit_int_content_client.py",
+    "simple_grpc_infer_client.py", "simple_grpc_string_infer_client.py", "simple_grpc_sequence_sync_infer_client.py",
+    "simple_grpc_health_metadata.py", "simple_grpc_keepalive_client.py", "simple_grpc_custom_args_client.py",
+]
+
+
+@pytest.fixture(scope="module")
+def native_transport_outcomes(tmp_path_factory):
+    proc, _, grpc_port = start_server()
+    env = dict(os.environ, TB200_GRPC_TRANSPORT="native")
+
+    def run(name):
+        try:
+            r = subprocess.run([sys.executable, "-c", RUNNER, os.path.join(EXAMPLES, name), "-u", "127.0.0.1:%d" % grpc_port],
+                               capture_output=True, text=True, timeout=120, cwd=str(tmp_path_factory.getbasetemp()), env=env)
+            return name, (r.returncode, (r.stdout + r.stderr)[-1500:])
+        except subprocess.TimeoutExpired:
+            return name, (-1, "timeout")
+
+    try:
+        with ThreadPoolExecutor(max_workers=5) as pool:
+            return dict(pool.map(run, NATIVE_TRANSPORT_SCRIPTS))
+    finally:
+        proc.terminate()
+        proc.wait(10)
+
+
+@pytest.mark.parametrize("name", NATIVE_TRANSPORT_SCRIPTS)
+def test_unmodified_reference_example_on_the_native_grpc_transport(native_transport_outcomes, name):
+    """The examples whose inferences are synchronous infer() calls, run with the drop-in's native
+    HTTP/2 transport selected through the environment: same PASS / exit 0."""
+    rc, tail = native_transport_outcomes[name]
+    assert rc == 0, tail
+    assert "FAILED" not in tail, tail
+
+
 # ---- the reference's C++ examples, compiled unmodified against client_b200/cpp ----------------
 CC_OUT = os.path.join(ROOT, "oracle", "_ref", "cc_examples")
 CC_EXAMPLES = {
