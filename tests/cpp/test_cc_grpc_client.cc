@@ -741,6 +741,69 @@ static void TestKeepAlive() {
   close(lfd);
 }
 
+// Both HTTP/2 implementations against each other with messages far beyond the flow-control windows:
+// the client (GrpcChannel) sends 40 MB through the echo server's 4 MiB stream window (csrc/grpc_server.h
+// replenishes it at the half-way mark) and receives 40 MB back through its own; then four 8 MB calls
+// share the connection.  The echoed request parses as a response (same field numbers up to 6).
+extern "C" {
+struct tb200_grpc_echo_server;
+int tb200_grpc_echo_server_start(const char* host, int* port, tb200_grpc_echo_server** out);
+int tb200_grpc_echo_server_stop(tb200_grpc_echo_server* s);
+}
+static void TestLargeMessages() {
+  int port = 0;
+  tb200_grpc_echo_server* srv = nullptr;
+  CHECK(tb200_grpc_echo_server_start("127.0.0.1", &port, &srv) == 0);
+  {
+    std::unique_ptr<tc::InferenceServerGrpcClient> client;
+    CHECK_OK(tc::InferenceServerGrpcClient::Create(&client, "127.0.0.1:" + std::to_string(port), false, false, tc::SslOptions(),
+                                                   tc::KeepAliveOptions(), false));
+    std::vector<int32_t> big(10 * 1000 * 1000);
+    for (size_t i = 0; i < big.size(); ++i) big[i] = static_cast<int32_t>(i);
+    tc::InferInput* in;
+    tc::InferInput::Create(&in, "INPUT0", {static_cast<int64_t>(big.size())}, "INT32");
+    in->AppendRaw(reinterpret_cast<uint8_t*>(big.data()), big.size() * 4);
+    tc::InferOptions opt("echo");
+    opt.request_id_ = "forty-megabytes";
+    tc::InferResult* r = nullptr;
+    CHECK_OK(client->Infer(&r, opt, {in}));
+    std::string id;
+    std::vector<int64_t> shape;
+    if (r != nullptr) {
+      CHECK_OK(r->Id(&id));
+      CHECK_OK(r->Shape("INPUT0", &shape));  // the request's input metadata came back as output metadata
+      CHECK(id == "forty-megabytes" && shape == std::vector<int64_t>({static_cast<int64_t>(big.size())}));
+    }
+    delete r;
+    std::mutex mu;
+    std::condition_variable cv;
+    int done = 0, good = 0;
+    tc::InferInput* mid;
+    tc::InferInput::Create(&mid, "INPUT0", {2000000}, "INT32");
+    mid->AppendRaw(reinterpret_cast<uint8_t*>(big.data()), 8000000);
+    for (int i = 0; i < 4; ++i) {
+      CHECK_OK(client->AsyncInfer(
+          [&](tc::InferResult* res) {
+            std::lock_guard<std::mutex> lk(mu);
+            std::vector<int64_t> s;
+            if (res->RequestStatus().IsOk() && res->Shape("INPUT0", &s).IsOk() && s == std::vector<int64_t>({2000000})) ++good;
+            ++done;
+            delete res;
+            cv.notify_all();
+          },
+          opt, {mid}));
+    }
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      CHECK(cv.wait_for(lk, std::chrono::seconds(60), [&] { return done == 4; }));
+    }
+    CHECK(good == 4);
+    delete in;
+    delete mid;
+  }
+  tb200_grpc_echo_server_stop(srv);
+}
+
 int main(int argc, char** argv) {
   if (argc > 2 && std::string(argv[1]) == "--roundtrip") return RoundTrip(argv[2]);
   if (argc > 1 && std::string(argv[1]) == "--requests") {
@@ -758,6 +821,7 @@ int main(int argc, char** argv) {
   }
   TestReconnect();
   TestKeepAlive();
+  TestLargeMessages();
   if (argc > 2 && std::string(argv[2]) == "slow") TestSlowServer(argv[1]);
   else if (argc > 2 && std::string(argv[2]) == "compress-gpu") TestCompression(argv[1], true);
   else if (argc > 2 && std::string(argv[2]) == "compress-nogpu") TestCompression(argv[1], false);
