@@ -386,6 +386,147 @@ static cudaError_t launch_fill_stride(const FillLaunch& l, uint32_t dtype, int s
   return cudaGetLastError();
 }
 
+// ---- the homogeneous launch (BASELINE C2: 64 x FP32[3,224,224]; C3: 1 x FP16[128,3,224,224]) ----
+// What the general kernel above pays for and this one does not:
+//   * the (dst, stream) table and every parameter sit in the constant bank: a CTA's first
+//     Philox call is ~100 cycles after it starts, nothing is loaded from global memory
+//     (only the device epoch of graph replays, one L2 hit);
+//   * dtype and range are compile-time / constant-bank values, ~30 registers per thread;
+//   * the stream-dependent multiplies of rounds 0 and 1 are folded once per CTA and job
+//     (philox_stream_const): 18 IMAD.WIDE per 16 bytes instead of 20, and the store address
+//     advances by 64-bit adds on the alu pipe instead of a 21st IMAD.WIDE;
+//   * consecutive launches overlap: the kernel releases its dependents at once
+//     (griddepcontrol.launch_dependents) and a successor launched with the programmatic-
+//     serialization attribute starts on the SM slots this grid leaves free, so ramp and tail
+//     of back-to-back fills hide behind each other (6.4 us per 38.5 MB launch in a graph chain
+//     against 7.9 us without; scripts/fill2_bench.cu, profiles/r02_fill2_bench.txt).  Before it
+//     exits every CTA waits for the grid it overlapped with (griddepcontrol.wait), so "this
+//     launch completed" still implies "every earlier launch of the stream completed".
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// groups g = first, first + stride, ... < end of one tensor; U independent Philox chains per thread
+template <uint32_t DT, int U>
+__device__ __forceinline__ void fill_run(uint8_t* __restrict__ dst, uint32_t first, uint32_t stride, uint32_t end,
+                                         const PhiloxStreamConst& sc, const FillUniform& L) {
+  uint32_t g = first;
+  uint8_t* p = dst + static_cast<uint64_t>(g) * 16u;
+  uint64_t pstep = static_cast<uint64_t>(stride) * 16u;
+  asm volatile("" : "+l"(pstep));  // opaque: the pointer advances by IADD3 pairs, not IMAD.WIDE
+  for (; g + (U - 1) * stride < end; g += U * stride) {
+    U32x4 o[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const U32x4 r = philox4x32_10_hoisted<10>(static_cast<uint64_t>(kPhiloxM0) * (g + k * stride), sc, L.rk);
+      o[k] = fill_group(DT, r, L.p);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      st_cs_v4(p, o[k]);
+      p += pstep;
+    }
+  }
+  for (; g < end; g += stride) {
+    const U32x4 r = philox4x32_10_hoisted<10>(static_cast<uint64_t>(kPhiloxM0) * g, sc, L.rk);
+    st_cs_v4(p, fill_group(DT, r, L.p));
+    p += pstep;
+  }
+}
+
+template <uint32_t DT, int CAP, int THREADS, int U>
+__global__ void __launch_bounds__(THREADS, 4) fill_uniform_kernel(const __grid_constant__ FillTab<CAP> tab, const __grid_constant__ FillUniform L) {
+  // the epoch is read BEFORE the dependents are released: when a successor starts, every CTA
+  // of this grid has its epoch (graphs advance the device epoch in their last node)
+  uint64_t epoch = L.epoch;
+  if (L.dev_epoch != nullptr) epoch += *L.dev_epoch;
+  pdl_launch_dependents();
+  if (L.ctas_per_job != 0) {
+    const uint32_t j = blockIdx.x / L.ctas_per_job;
+    const uint32_t part = blockIdx.x - j * L.ctas_per_job;
+    const uint64_t stream = tab.stream[j] + epoch;
+    const PhiloxStreamConst sc = philox_stream_const(static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32), L.rk);
+    fill_run<DT, U>(reinterpret_cast<uint8_t*>(tab.dst[j]), part * THREADS + threadIdx.x, L.ctas_per_job * THREADS,
+                    L.groups_per_job, sc, L);
+  } else {
+    uint64_t lo = (L.total_groups * blockIdx.x) / gridDim.x;
+    const uint64_t hi = (L.total_groups * (blockIdx.x + 1ull)) / gridDim.x;
+    uint32_t j = static_cast<uint32_t>(lo / L.groups_per_job);
+    uint32_t g0 = static_cast<uint32_t>(lo - static_cast<uint64_t>(j) * L.groups_per_job);
+    while (lo < hi) {
+      const uint64_t left = hi - lo;
+      const uint32_t room = L.groups_per_job - g0;
+      const uint32_t n = left < room ? static_cast<uint32_t>(left) : room;
+      const uint64_t stream = tab.stream[j] + epoch;
+      const PhiloxStreamConst sc = philox_stream_const(static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32), L.rk);
+      fill_run<DT, U>(reinterpret_cast<uint8_t*>(tab.dst[j]), g0 + threadIdx.x, THREADS, g0 + n, sc, L);
+      lo += n;
+      ++j;
+      g0 = 0;
+    }
+  }
+  pdl_wait_primary();
+}
+
+void plan_fill_uniform(FillUniform* u, int sm_count) {
+  constexpr uint32_t kThreads = 256, kU = 2;
+  const uint32_t target = static_cast<uint32_t>(sm_count) * 4u;  // CTAs of one grid; 8 fit per SM, the rest is the successor's
+  u->ctas_per_job = 0;
+  const uint32_t cpj = u->njobs <= target ? target / u->njobs : 0;
+  // interleaved rows when the split fills the chip evenly and every part has whole iterations
+  if (cpj != 0 && static_cast<uint64_t>(u->njobs) * cpj * 100 >= static_cast<uint64_t>(target) * 93 &&
+      u->groups_per_job / cpj >= kThreads * kU * 2) {
+    u->ctas_per_job = cpj;
+    u->grid = u->njobs * cpj;
+    return;
+  }
+  uint64_t grid = u->total_groups / (kThreads * kU);
+  if (grid > target) grid = target;
+  if (grid == 0) grid = 1;
+  u->grid = static_cast<uint32_t>(grid);
+}
+
+template <uint32_t DT, int CAP>
+static cudaError_t launch_fill_uniform_t(const FillUniform& u, const tb200_fill_job* host_jobs, cudaStream_t s, bool pdl) {
+  FillTab<CAP> tab;
+  for (uint32_t i = 0; i < u.njobs; ++i) {
+    tab.dst[i] = host_jobs[i].dst;
+    tab.stream[i] = host_jobs[i].stream;
+  }
+  for (uint32_t i = u.njobs; i < static_cast<uint32_t>(CAP); ++i) tab.dst[i] = tab.stream[i] = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(u.grid);
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  if (pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, fill_uniform_kernel<DT, CAP, 256, 2>, tab, u);
+}
+
+cudaError_t launch_fill_uniform(const FillUniform& u, const tb200_fill_job* host_jobs, uint32_t dtype, cudaStream_t s, bool pdl) {
+  if (u.njobs == 0 || u.njobs > static_cast<uint32_t>(kFillTabLarge)) return cudaErrorInvalidValue;
+#define TB200_UNI_CASE(DT)                                                                              \
+  return u.njobs <= static_cast<uint32_t>(kFillTabSmall) ? launch_fill_uniform_t<DT, kFillTabSmall>(u, host_jobs, s, pdl) \
+                                                         : launch_fill_uniform_t<DT, kFillTabLarge>(u, host_jobs, s, pdl)
+  switch (dtype) {
+    case kF32: TB200_UNI_CASE(kF32);
+    case kF16: TB200_UNI_CASE(kF16);
+    case kBF16: TB200_UNI_CASE(kBF16);
+    case kF64: TB200_UNI_CASE(kF64);
+    case kI64: case kU64: TB200_UNI_CASE(kI64);
+    case kI32: case kU32: TB200_UNI_CASE(kI32);
+    case kI16: case kU16: TB200_UNI_CASE(kI16);
+    case kI8: case kU8: TB200_UNI_CASE(kI8);
+    case kBool: TB200_UNI_CASE(kBool);
+    default: return cudaErrorInvalidValue;
+  }
+#undef TB200_UNI_CASE
+}
+
 static int g_fill_variant = 0;
 void set_fill_variant(int v) { g_fill_variant = v; }
 

@@ -30,6 +30,34 @@ struct FillLaunch {
   RoundKeys rk;                  // Philox key schedule of `seed`
 };
 cudaError_t launch_fill(const FillLaunch& l, int sm_count, cudaStream_t s);
+
+// Homogeneous launches (N tensors of one size, dtype and range, 16-byte aligned -- the N slots
+// of one model input, BASELINE configs C2 / C3): the (dst, stream) pairs travel in the kernel
+// parameters (constant bank: no table upload, no global load before the first store), the
+// dtype is a template parameter and the stream-dependent part of Philox is hoisted per CTA.
+constexpr int kFillTabSmall = 64, kFillTabLarge = 256;
+template <int CAP>
+struct FillTab {
+  uint64_t dst[CAP];
+  uint64_t stream[CAP];
+};
+struct FillUniform {
+  RoundKeys rk;               // Philox key schedule of the seed
+  FillParams p;               // range of the dtype
+  const uint64_t* dev_epoch;  // device or nullptr: added to every stream id
+  uint64_t epoch;
+  uint64_t total_groups;      // njobs * groups_per_job
+  uint32_t njobs;
+  uint32_t groups_per_job;    // < 2^31
+  uint32_t ctas_per_job;      // > 0: CTA b owns rows (b % cpj) + k * cpj of job b / cpj (interleaved rows of
+                              //      256 groups); 0: CTA b owns groups [T*b/G, T*(b+1)/G) of the launch
+  uint32_t grid;
+};
+// pdl: launch with the programmatic-stream-serialization attribute (the kernel may start while
+// the previous kernel of the stream drains; only set when the two write disjoint memory)
+cudaError_t launch_fill_uniform(const FillUniform& u, const tb200_fill_job* host_jobs, uint32_t dtype, cudaStream_t s, bool pdl);
+// fills u.ctas_per_job / u.grid for a launch of u.njobs x u.groups_per_job groups
+void plan_fill_uniform(FillUniform* u, int sm_count);
 // tuning knob for experiments (scripts/fill_sweep.py); 0 = default configuration
 void set_fill_variant(int v);
 

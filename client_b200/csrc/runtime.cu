@@ -219,6 +219,16 @@ struct tb200_ctx {
   // capture state
   tb200_graph* capture = nullptr;
   uint64_t capture_launches0 = 0;
+  uint64_t capture_epoch = 0;  // device-epoch advance accumulated by the capture's fill_epoch calls (applied by its last node)
+  // programmatic dependent launch of back-to-back homogeneous fills: the previous launch on
+  // stream s (0 main, 1 side) was a fill_uniform_kernel writing [pdl_lo[s], pdl_hi[s]) iff pdl_mark[s] == stream_seq[s]
+  uint64_t stream_seq[2] = {0, 0};
+  uint64_t pdl_mark[2] = {~0ull, ~0ull};
+  struct PdlEntry {
+    uint64_t lo, hi;
+    uint32_t grid;
+  };
+  std::vector<PdlEntry> pdl_chain[2];  // most recent last; the launches of the current overlap chain
 };
 
 struct tb200_timer {
@@ -236,6 +246,14 @@ struct tb200_region {
 };
 
 namespace {
+
+// every kernel launch is counted per context and per stream (main / side); the per-stream
+// count tells a fill whether the previous kernel of ITS stream was a fill as well
+inline void count_launch(tb200_ctx* ctx, uint64_t n = 1) {
+  ctx->launches += n;
+  ctx->stream_seq[ctx->cur == ctx->side && ctx->side != nullptr ? 1 : 0] += n;
+}
+inline uint64_t stream_seq(const tb200_ctx* ctx) { return ctx->stream_seq[ctx->cur == ctx->side && ctx->side != nullptr ? 1 : 0]; }
 
 int ensure_stage(tb200_ctx* ctx) {
   if (ctx->stage[0] != nullptr) return TB200_OK;
@@ -739,6 +757,9 @@ int tb200_memcpy_d2h_async(tb200_ctx* ctx, void* dst, const void* src, uint64_t 
 // ---------------------------------------------------------------------------
 // fill
 // ---------------------------------------------------------------------------
+static bool g_fill_uniform = true;  // homogeneous launches take fill_uniform_kernel ("fill_uniform" knob)
+static bool g_fill_pdl = true;      // ... and overlap with the previous one when they write disjoint memory ("fill_pdl" knob)
+
 static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint64_t seed,
                      uint64_t epoch, bool use_dev_epoch, uint64_t bump) {
   if (ctx == nullptr || njobs < 0 || (njobs > 0 && jobs == nullptr)) return fail(TB200_ERR_INVALID, "bad argument");
@@ -793,6 +814,71 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
       if (groups != (jobs[base].nbytes + 15) / 16) uniform = false;
     }
     if (total == 0 && !(last && bump != 0 && use_dev_epoch)) continue;
+    // graphs: every captured fill reads the device epoch plus the advance the capture has
+    // accumulated so far; the capture's last node applies the sum (tb200_graph_end), so the
+    // fills of one graph never wait for each other's epoch update
+    uint64_t launch_epoch = epoch, launch_bump = (last && use_dev_epoch) ? bump : 0;
+    if (ctx->capture != nullptr && use_dev_epoch) {
+      launch_epoch += ctx->capture_epoch;
+      if (last) ctx->capture_epoch += bump;
+      launch_bump = 0;
+    }
+    if (g_fill_uniform && homogeneous && uniform && total != 0 && unaligned == 0 && n <= kFillTabLarge && prefix[1] < (1ull << 31)) {
+      const tb200_fill_job& f = jobs[base];
+      FillUniform U;
+      U.rk = rk;
+      U.p.lo_f = static_cast<float>(f.lo);
+      U.p.span_f = static_cast<float>(f.span);
+      U.p.lo_d = f.lo;
+      U.p.span_d = f.span;
+      U.p.ilo = f.ilo;
+      U.p.irange = f.irange;
+      U.p.unit = (f.span == 0.0) ? 1u : 0u;
+      U.dev_epoch = use_dev_epoch ? ctx->dev_epoch : nullptr;
+      U.epoch = launch_epoch;
+      U.total_groups = total;
+      U.njobs = static_cast<uint32_t>(n);
+      U.groups_per_job = static_cast<uint32_t>(prefix[1]);
+      plan_fill_uniform(&U, ctx->sm_count);
+      uint64_t lo = ~0ull, hi = 0;
+      for (int i = 0; i < n; ++i) {
+        lo = std::min(lo, jobs[base + i].dst);
+        hi = std::max(hi, jobs[base + i].dst + jobs[base + i].nbytes);
+      }
+      // overlap with the previous launch only if that was a homogeneous fill on this stream
+      // writing other memory (same memory: the later launch must win)
+      // Which earlier launches of the chain can still be running when this one starts?  A
+      // launch starts only after every CTA of its predecessor started, and no CTA of a launch
+      // exits before the launch it overlapped with completed (griddepcontrol.wait at the end of
+      // the kernel).  So launch -k is still running only if the grids of launches -1 .. -(k-1)
+      // plus one of its own CTAs are resident together: at most 8 CTAs of 256 threads per SM.
+      const int si = (ctx->cur == ctx->side && ctx->side != nullptr) ? 1 : 0;
+      std::vector<tb200_ctx::PdlEntry>& chain = ctx->pdl_chain[si];
+      bool pdl = g_fill_pdl && ctx->pdl_mark[si] == stream_seq(ctx) && !chain.empty();
+      if (pdl) {
+        const uint64_t capacity = static_cast<uint64_t>(ctx->sm_count) * 8;
+        uint64_t newer = 0;
+        size_t live = 0;
+        for (size_t k = chain.size(); k-- > 0;) {
+          if (newer + 1 > capacity) break;  // this one and everything older completed
+          ++live;
+          if (!(hi <= chain[k].lo || lo >= chain[k].hi)) pdl = false;  // same memory: the later launch must win
+          newer += chain[k].grid;
+        }
+        if (live == chain.size() && chain.size() >= 16) pdl = false;  // bounded history
+        if (pdl && live < chain.size()) chain.erase(chain.begin(), chain.end() - live);
+      }
+      if (!pdl) chain.clear();  // a plain launch waits for the whole chain
+      TB200_CUDA(launch_fill_uniform(U, jobs + base, f.dtype, ctx->cur, pdl));
+      count_launch(ctx);
+      ctx->pdl_mark[si] = stream_seq(ctx);
+      chain.push_back({lo, hi, U.grid});
+      if (launch_bump != 0) {  // eager fill_epoch: advance the device epoch behind the fill
+        TB200_CUDA(launch_epoch_bump(ctx->dev_epoch, launch_bump, ctx->cur));
+        count_launch(ctx);
+      }
+      continue;
+    }
     // one upload: [jobs | prefix]
     const size_t jbytes = sizeof(tb200_fill_job) * n;
     const size_t pbytes = sizeof(uint64_t) * (n + 1);
@@ -808,8 +894,8 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
     L.dev_epoch = use_dev_epoch ? ctx->dev_epoch : nullptr;
     L.done_counter = reinterpret_cast<unsigned int*>(ctx->dev_epoch + 1);
     L.seed = seed;
-    L.epoch = epoch;
-    L.bump = (last && use_dev_epoch) ? bump : 0;
+    L.epoch = launch_epoch;
+    L.bump = launch_bump;
     L.njobs = static_cast<uint32_t>(n);
     L.total_groups = total;
     L.uniform_groups = (uniform && total != 0) ? prefix[1] : 0;
@@ -826,7 +912,7 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
     }
     L.rk = rk;
     TB200_CUDA(launch_fill(L, ctx->sm_count, ctx->cur));
-    ctx->launches += 1;
+    count_launch(ctx);
   }
   return TB200_OK;
 }
@@ -849,7 +935,7 @@ int tb200_ctx_epoch_bump_async(tb200_ctx* ctx, uint64_t delta) {
   if (ctx == nullptr) return fail(TB200_ERR_INVALID, "ctx is NULL");
   DeviceGuard g(ctx->device);
   TB200_CUDA(launch_epoch_bump(ctx->dev_epoch, delta, ctx->cur));
-  ctx->launches += 1;
+  count_launch(ctx);
   return TB200_OK;
 }
 
@@ -875,7 +961,7 @@ int tb200_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype, uint32
                 dst_dtype, n, h, w, c, scaling);
   }
   TB200_CUDA(e);
-  ctx->launches += launches;
+  count_launch(ctx, launches);
   return TB200_OK;
 }
 
@@ -987,7 +1073,7 @@ int tb200_resize_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
   }
   if (p.tile_h == 0) return fail(TB200_ERR_INVALID, "resize_pack: down-scale %dx%d -> %dx%d needs a larger source block per tile than shared memory holds", src_h, src_w, dst_h, dst_w);
   TB200_CUDA(launch_resize_pack(p, ctx->cur));
-  ctx->launches += 1;
+  count_launch(ctx);
   return TB200_OK;
 }
 
@@ -1000,7 +1086,7 @@ int tb200_cast_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype, const void* 
   }
   DeviceGuard g(ctx->device);
   TB200_CUDA(launch_cast(dst, dst_dtype, src, src_dtype, nelem, ctx->sm_count, ctx->cur));
-  ctx->launches += 1;
+  count_launch(ctx);
   return TB200_OK;
 }
 
@@ -1027,7 +1113,7 @@ int tb200_pack_strided_async(tb200_ctx* ctx, void* dst, const void* src, uint32_
   if (dst == nullptr || src == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
   DeviceGuard g(ctx->device);
   TB200_CUDA(launch_pack_strided(p, ctx->sm_count, ctx->cur));
-  ctx->launches += 1;
+  count_launch(ctx);
   return TB200_OK;
 }
 
@@ -1062,7 +1148,7 @@ int tb200_concat_async(tb200_ctx* ctx, const tb200_copy_job* jobs, int njobs) {
     L.njobs = static_cast<uint32_t>(n);
     L.total_tiles = static_cast<uint32_t>(total);
     TB200_CUDA(launch_concat(L, ctx->sm_count, ctx->cur));
-    ctx->launches += 1;
+    count_launch(ctx);
   }
   return TB200_OK;
 }
@@ -1118,7 +1204,7 @@ int tb200_check_async(tb200_ctx* ctx, const tb200_check_job* jobs, int njobs, tb
     L.max_chunks = static_cast<uint32_t>((max_bytes + kCheckChunkBytes - 1) / kCheckChunkBytes);
     if (L.max_chunks > 65535u * 32u) return fail(TB200_ERR_INVALID, "check job too large");
     TB200_CUDA(launch_check(L, ctx->cur));
-    ctx->launches += 1;
+    count_launch(ctx);
   }
   return TB200_OK;
 }
@@ -1144,7 +1230,7 @@ int tb200_topk_async(tb200_ctx* ctx, const tb200_topk_job* jobs, int njobs, int 
     if (rc != TB200_OK) return rc;
     TB200_CUDA(launch_topk(static_cast<const tb200_topk_job*>(dev), static_cast<uint32_t>(n), static_cast<uint32_t>(k),
                            out + static_cast<size_t>(base) * k, ctx->cur));
-    ctx->launches += 1;
+    count_launch(ctx);
   }
   return TB200_OK;
 }
@@ -1184,7 +1270,7 @@ int tb200_deflate_async(tb200_ctx* ctx, void* dst, uint64_t dst_capacity, const 
   }
   TB200_CUDA(launch_deflate(static_cast<const uint8_t*>(src), nbytes, format, static_cast<uint8_t*>(ctx->deflate_scratch),
                             static_cast<DeflateChunkMeta*>(ctx->deflate_meta), static_cast<uint8_t*>(dst), out_size, ctx->cur));
-  ctx->launches += chunks > 0 ? 3 : 1;
+  count_launch(ctx, chunks > 0 ? 3 : 1);
   return TB200_OK;
 }
 
@@ -1206,6 +1292,8 @@ int tb200_graph_begin(tb200_ctx* ctx) {
   }
   ctx->capture = gr;
   ctx->capture_launches0 = ctx->launches;
+  ctx->capture_epoch = 0;
+  ctx->pdl_mark[0] = ctx->pdl_mark[1] = ~0ull;
   return TB200_OK;
 }
 
@@ -1215,7 +1303,17 @@ int tb200_graph_end(tb200_ctx* ctx, tb200_graph** out) {
   if (ctx->forked) return fail(TB200_ERR_STATE, "join the side stream before ending the capture");
   DeviceGuard g(ctx->device);
   tb200_graph* gr = ctx->capture;
+  if (ctx->capture_epoch != 0) {
+    // last node: the device epoch moves on by what the capture's fill_epoch calls asked for.
+    // Every fill read the epoch before it released its successor, so all reads of this replay
+    // precede this node and all reads of the next replay follow it.
+    const cudaError_t eb = launch_epoch_bump(ctx->dev_epoch, ctx->capture_epoch, ctx->stream);
+    if (eb != cudaSuccess) return fail(TB200_ERR_CUDA, "epoch node failed: %s", cudaGetErrorString(eb));
+    count_launch(ctx);
+    ctx->capture_epoch = 0;
+  }
   ctx->capture = nullptr;
+  ctx->pdl_mark[0] = ctx->pdl_mark[1] = ~0ull;
   gr->kernels_per_launch = ctx->launches - ctx->capture_launches0;
   ctx->launches = ctx->capture_launches0;  // captured kernels did not run yet
   cudaError_t e = cudaStreamEndCapture(ctx->stream, &gr->graph);
@@ -1232,7 +1330,7 @@ int tb200_graph_launch(tb200_ctx* ctx, tb200_graph* gr) {
   if (ctx == nullptr || gr == nullptr) return fail(TB200_ERR_INVALID, "NULL argument");
   DeviceGuard g(ctx->device);
   TB200_CUDA(cudaGraphLaunch(gr->exec, ctx->stream));
-  ctx->launches += gr->kernels_per_launch;
+  count_launch(ctx, gr->kernels_per_launch);
   return TB200_OK;
 }
 
@@ -1352,6 +1450,15 @@ int tb200_step_submit(tb200_ctx* ctx, const tb200_fill_job* fill_jobs, int nfill
 int tb200_tune(const char* key, int value) {
   if (key != nullptr && strcmp(key, "fill_variant") == 0) {
     set_fill_variant(value);
+    g_fill_uniform = value == 0;  // the experiment matrix addresses the general kernels
+    return TB200_OK;
+  }
+  if (key != nullptr && strcmp(key, "fill_uniform") == 0) {
+    g_fill_uniform = value != 0;
+    return TB200_OK;
+  }
+  if (key != nullptr && strcmp(key, "fill_pdl") == 0) {
+    g_fill_pdl = value != 0;
     return TB200_OK;
   }
   if (key != nullptr && strcmp(key, "step_parallel_min_mb") == 0) {

@@ -5,7 +5,7 @@ table and turned into real protobuf message classes with
 ``descriptor_pb2.FileDescriptorProto`` + ``message_factory``.  Field names,
 numbers and types follow the only copy of the schema in the reference,
 src/rust/triton-client/proto/grpc_service.proto:40-218 (service), :226-1800
-(messages), and model_config.proto:1971+ for the ModelConfig subset.  The
+(messages), and model_config.proto for the whole of ModelConfig (generated table).  The
 reference Python client gets the same classes from generated ``service_pb2`` /
 ``service_pb2_grpc`` / ``model_config_pb2`` modules
 (src/python/library/build_wheel.py:110-139); the module objects built by
@@ -134,33 +134,13 @@ SCHEMA = {
     "LogSettingsResponse.SettingValue": [("bool_param", 1, "bool", _PARAM_ONEOF), ("uint32_param", 2, "uint32", _PARAM_ONEOF), ("string_param", 3, "string", _PARAM_ONEOF)],
 }
 
-# model_config.proto subset (enough for get_model_config round trips and the
-# input/output metadata image-style clients read; field numbers from
-# model_config.proto: ModelConfig :1971+, ModelInput, ModelOutput, DataType).
-MODEL_CONFIG_SCHEMA = {
-    "ModelInput": [
-        ("name", 1, "string", ""), ("data_type", 2, "enum:DataType", ""), ("format", 3, "enum:.Format", ""),
-        ("dims", 4, "int64", "rep"), ("is_shape_tensor", 6, "bool", ""), ("allow_ragged_batch", 7, "bool", ""),
-        ("optional", 8, "bool", ""),
-    ],
-    "ModelOutput": [
-        ("name", 1, "string", ""), ("data_type", 2, "enum:DataType", ""), ("dims", 3, "int64", "rep"),
-        ("label_filename", 4, "string", ""), ("is_shape_tensor", 6, "bool", ""),
-    ],
-    "ModelTransactionPolicy": [("decoupled", 1, "bool", "")],
-    "ModelConfig": [
-        ("name", 1, "string", ""), ("platform", 2, "string", ""), ("max_batch_size", 4, "int32", ""),
-        ("input", 5, "ModelInput", "rep"), ("output", 6, "ModelOutput", "rep"),
-        ("default_model_filename", 8, "string", ""), ("backend", 17, "string", ""),
-        ("model_transaction_policy", 19, "ModelTransactionPolicy", ""), ("runtime", 25, "string", ""),
-    ],
-}
-DATA_TYPE_ENUM = [
-    ("TYPE_INVALID", 0), ("TYPE_BOOL", 1), ("TYPE_UINT8", 2), ("TYPE_UINT16", 3), ("TYPE_UINT32", 4),
-    ("TYPE_UINT64", 5), ("TYPE_INT8", 6), ("TYPE_INT16", 7), ("TYPE_INT32", 8), ("TYPE_INT64", 9),
-    ("TYPE_FP16", 10), ("TYPE_FP32", 11), ("TYPE_FP64", 12), ("TYPE_STRING", 13), ("TYPE_BF16", 14),
-]
-FORMAT_ENUM = [("FORMAT_NONE", 0), ("FORMAT_NHWC", 1), ("FORMAT_NCHW", 2)]
+# model_config.proto: the full ModelConfig schema (55 messages, 9 enums) lives in the generated
+# table _model_config_schema.py (oracle/gen_proto_fixture.py --emit-model-config); qualified type
+# names, 'map:<key type>' labels.
+from ._model_config_schema import MODEL_CONFIG_ENUMS, MODEL_CONFIG_SCHEMA  # noqa: E402
+
+DATA_TYPE_ENUM = MODEL_CONFIG_ENUMS["DataType"]
+FORMAT_ENUM = MODEL_CONFIG_ENUMS["ModelInput.Format"]
 
 # rpc name -> (request, response, client_streaming, server_streaming)
 SERVICE = {
@@ -194,30 +174,35 @@ def _camel(name):
 
 
 def _resolve(type_name, owner):
-    """'.Nested' is relative to the owning top-level message."""
+    """'.Nested' is relative to the owning top-level message; anything else is a qualified name."""
     if type_name.startswith("."):
         return ".%s.%s%s" % (PACKAGE, owner.split(".")[0], type_name)
     return ".%s.%s" % (PACKAGE, type_name)
 
 
-def _fill_message(msg_proto, full_name, fields, schema):
+def _json_name(fname):
+    parts = fname.split("_")
+    return parts[0] + "".join(p.capitalize() for p in parts[1:])
+
+
+def _fill_message(msg_proto, full_name, fields, schema, enums):
     oneofs = {}
     for fname, number, ftype, label in fields:
         f = msg_proto.field.add()
         f.name, f.number = fname, number
-        f.json_name = fname[0] + _camel(fname)[1:] if "_" in fname else fname
+        f.json_name = _json_name(fname)
         f.label = _F.LABEL_OPTIONAL
-        value_type = ftype
-        if label == "map":
-            # map<string, V> = repeated nested <Name>Entry {string key=1; V value=2}
+        if label == "map" or label.startswith("map:"):
+            # map<K, V> = repeated nested <Name>Entry {K key=1; V value=2}
             entry = msg_proto.nested_type.add()
             entry.name = _camel(fname) + "Entry"
             entry.options.map_entry = True
             k = entry.field.add()
-            k.name, k.number, k.label, k.type, k.json_name = "key", 1, _F.LABEL_OPTIONAL, _F.TYPE_STRING, "key"
+            k.name, k.number, k.label, k.json_name = "key", 1, _F.LABEL_OPTIONAL, "key"
+            k.type = _SCALARS[label.split(":", 1)[1] if ":" in label else "string"]
             v = entry.field.add()
             v.name, v.number, v.label, v.json_name = "value", 2, _F.LABEL_OPTIONAL, "value"
-            _set_type(v, value_type, full_name)
+            _set_type(v, ftype, full_name)
             f.label = _F.LABEL_REPEATED
             f.type = _F.TYPE_MESSAGE
             f.type_name = ".%s.%s.%s" % (PACKAGE, full_name, entry.name)
@@ -230,13 +215,23 @@ def _fill_message(msg_proto, full_name, fields, schema):
                 oneofs[group] = len(msg_proto.oneof_decl)
                 msg_proto.oneof_decl.add().name = group
             f.oneof_index = oneofs[group]
-        _set_type(f, value_type, full_name)
+        _set_type(f, ftype, full_name)
     prefix = full_name + "."
     for child, child_fields in schema.items():
         if child.startswith(prefix) and "." not in child[len(prefix):]:
             nested = msg_proto.nested_type.add()
             nested.name = child[len(prefix):]
-            _fill_message(nested, child, child_fields, schema)
+            _fill_message(nested, child, child_fields, schema, enums)
+    for ename, values in enums.items():
+        if ename.startswith(prefix) and "." not in ename[len(prefix):]:
+            _fill_enum(msg_proto.enum_type.add(), ename[len(prefix):], values)
+
+
+def _fill_enum(enum_proto, name, values):
+    enum_proto.name = name
+    for n, v in values:
+        ev = enum_proto.value.add()
+        ev.name, ev.number = n, v
 
 
 def _set_type(field, type_name, owner):
@@ -255,27 +250,16 @@ def _file_descriptor():
     fd.name = "client_b200/grpc_service.proto"
     fd.package = PACKAGE
     fd.syntax = "proto3"
-    enum = fd.enum_type.add()
-    enum.name = "DataType"
-    for n, v in DATA_TYPE_ENUM:
-        ev = enum.value.add()
-        ev.name, ev.number = n, v
-    for name, fields in MODEL_CONFIG_SCHEMA.items():
-        m = fd.message_type.add()
-        m.name = name
-        _fill_message(m, name, fields, MODEL_CONFIG_SCHEMA)
-        if name == "ModelInput":
-            fmt = m.enum_type.add()
-            fmt.name = "Format"
-            for n, v in FORMAT_ENUM:
-                ev = fmt.value.add()
-                ev.name, ev.number = n, v
-    for name, fields in SCHEMA.items():
-        if "." in name:
-            continue
-        m = fd.message_type.add()
-        m.name = name
-        _fill_message(m, name, fields, SCHEMA)
+    for ename, values in MODEL_CONFIG_ENUMS.items():
+        if "." not in ename:
+            _fill_enum(fd.enum_type.add(), ename, values)
+    for schema, enums in ((MODEL_CONFIG_SCHEMA, MODEL_CONFIG_ENUMS), (SCHEMA, {})):
+        for name, fields in schema.items():
+            if "." in name:
+                continue
+            m = fd.message_type.add()
+            m.name = name
+            _fill_message(m, name, fields, schema, enums)
     svc = fd.service.add()
     svc.name = "GRPCInferenceService"
     for rpc, (req, resp, cs, ss) in SERVICE.items():
@@ -288,6 +272,15 @@ def _file_descriptor():
 
 
 _modules = None
+
+
+def _enum_wrapper(desc):
+    try:
+        from google.protobuf.internal import enum_type_wrapper
+
+        return enum_type_wrapper.EnumTypeWrapper(desc)
+    except Exception:  # pragma: no cover
+        return desc
 
 
 def build_modules():
@@ -313,9 +306,13 @@ def build_modules():
     model_config_pb2 = types.ModuleType("client_b200.grpc.model_config_pb2")
     model_config_pb2.DESCRIPTOR = file_desc
     for name in MODEL_CONFIG_SCHEMA:
-        setattr(model_config_pb2, name, cls(name))
-    for n, v in DATA_TYPE_ENUM:
-        setattr(model_config_pb2, n, v)
+        if "." not in name:
+            setattr(model_config_pb2, name, cls(name))
+    for ename, values in MODEL_CONFIG_ENUMS.items():
+        if "." not in ename:  # top-level enum: its values are module attributes, as in generated code
+            setattr(model_config_pb2, ename, _enum_wrapper(pool.FindEnumTypeByName("%s.%s" % (PACKAGE, ename))))
+            for n, v in values:
+                setattr(model_config_pb2, n, v)
     service_pb2.ModelConfig = model_config_pb2.ModelConfig
 
     service_pb2_grpc = types.ModuleType("client_b200.grpc.service_pb2_grpc")

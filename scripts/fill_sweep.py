@@ -17,7 +17,9 @@ from client_b200 import _native  # noqa: E402
 from client_b200.device import DeviceBuffer, DeviceOps, make_fill_job  # noqa: E402
 from oracle import cref  # noqa: E402
 
-VARIANTS = {0: "default policy (range u3 / stride for small tensors)", 20: "stride 256t u1 cap8", 21: "stride 256t u2 cap6",
+# negative keys: knobs of the default policy rather than a general-kernel variant
+VARIANTS = {0: "default: fill_uniform_kernel + overlapped launches (PDL)", -1: "fill_uniform_kernel, launches serialised (fill_pdl=0)",
+            -2: "general kernels only (fill_uniform=0): range u3 / stride", 20: "stride 256t u1 cap8", 21: "stride 256t u2 cap6",
             22: "stride 256t u2 cap16", 24: "stride 256t u4 cap4",
             101: "range 256t u2", 102: "range 256t u4", 106: "range 512t u2", 111: "range 256t u3",
             28: "stride 1 round (NOT the contract)", 110: "range 1 round (NOT the contract)", 109: "range 7 rounds (NOT the contract)"}
@@ -56,7 +58,10 @@ def main():
     all256 = [make_fill_job(big.ptr + k * slot, slot, "FP32", stream_id=k) for k in range(256)]
     print("%-52s %12s %12s %12s %12s" % ("variant", "C2 64xFP32", "C3 1xFP16", "C4 512xI64", "256xFP32"))
     for v, name in VARIANTS.items():
-        _native.check(lib.tb200_tune(b"fill_variant", v))
+        _native.check(lib.tb200_tune(b"fill_variant", max(v, 0)))
+        _native.check(lib.tb200_tune(b"fill_pdl", 0 if v == -1 else 1))
+        if v == -2:
+            _native.check(lib.tb200_tune(b"fill_uniform", 0))
         if v not in NOT_CONTRACT:  # correctness spot check
             ops.fill(c2[0][:2], seed=5)
             got = ops.download(big.ptr + slot, slot)

@@ -47,6 +47,35 @@ void emul_fill(uint8_t* dst, uint64_t nbytes, uint32_t dtype, uint64_t seed, uin
   }
 }
 
+// mirrors fill_uniform_kernel: round keys + philox_stream_const once per tensor, then the
+// hoisted block function on M0 * g per 16-byte group
+void emul_fill_hoisted(uint8_t* dst, uint64_t nbytes, uint32_t dtype, uint64_t seed, uint64_t stream,
+                       double lo, double span, int64_t ilo, uint64_t irange) {
+  FillParams p;
+  p.lo_f = static_cast<float>(lo);
+  p.span_f = static_cast<float>(span);
+  p.lo_d = lo;
+  p.span_d = span;
+  p.ilo = ilo;
+  p.irange = irange;
+  p.unit = (span == 0.0) ? 1u : 0u;
+  uint32_t dt = dtype;
+  if (dt == kU64) dt = kI64;
+  if (dt == kU32) dt = kI32;
+  if (dt == kU16) dt = kI16;
+  if (dt == kU8) dt = kI8;
+  RoundKeys rk;
+  make_round_keys(seed, &rk);
+  const PhiloxStreamConst sc = philox_stream_const(static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32), rk);
+  for (uint64_t g = 0; g * 16 < nbytes; ++g) {
+    const U32x4 r = philox4x32_10_hoisted<10>(static_cast<uint64_t>(kPhiloxM0) * static_cast<uint32_t>(g), sc, rk);
+    const U32x4 o = fill_group(dt, r, p);
+    const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+    const uint64_t left = nbytes - g * 16;
+    memcpy(dst + g * 16, w, left < 16 ? left : 16);
+  }
+}
+
 uint32_t emul_scale_f32_bits(uint32_t px, uint32_t scaling, int c, int ch) {
   return f32_bits(scale_pixel_f32(px, scaling, c, ch));
 }

@@ -26,8 +26,10 @@ def emul():
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", LIB, SRC], check=True)
     L = ctypes.CDLL(LIB)
-    L.emul_fill.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
-                            ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64]
+    for f in (L.emul_fill, L.emul_fill_hoisted):
+        f.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
+                      ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_uint64]
+        f.restype = None
     for f in (L.emul_scale_f32_bits, L.emul_scale_f16_bits):
         f.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
         f.restype = ctypes.c_uint32
@@ -56,6 +58,22 @@ def test_fill_contract_header_vs_oracle(emul, dt):
                        kw.get("lo", 0.0), kw.get("span", 0.0), kw.get("ilo", 0), kw.get("irange", 0))
         ref = cref.fill(n, dt, seed=0xABCDEF0123456789, stream=(9 << 32) | 77, **kw)
         assert np.array_equal(out, ref), (dt, kw)
+
+
+@pytest.mark.parametrize("dt", ["FP32", "FP16", "INT64", "UINT8"])
+def test_stream_hoisted_philox_is_the_same_function(emul, dt):
+    """philox_stream_const + philox4x32_10_hoisted (what fill_uniform_kernel runs: 18 multiplies
+    per call) against the C oracle's plain ten rounds, over seeds and streams that exercise
+    every carry of the folded rounds."""
+    rng = np.random.default_rng(5)
+    kw = dict(lo=-2.0, span=5.0) if dt in ("FP32", "FP16") else (dict(ilo=0, irange=30522) if dt == "INT64" else dict())
+    for seed, stream in [(0, 0), (1, 0xFFFFFFFF), (0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF), (0xABCDEF0123456789, (9 << 32) | 77)] + [
+            (int(rng.integers(0, 2**63)), int(rng.integers(0, 2**63))) for _ in range(8)]:
+        n = 16 * 3001
+        out = np.zeros(n, np.uint8)
+        emul.emul_fill_hoisted(out.ctypes.data, n, cref.DT[dt], seed, stream, kw.get("lo", 0.0), kw.get("span", 0.0),
+                               kw.get("ilo", 0), kw.get("irange", 0))
+        assert np.array_equal(out, cref.fill(n, dt, seed=seed, stream=stream, **kw)), (dt, hex(seed), hex(stream))
 
 
 def test_scaling_all_256_values(emul):

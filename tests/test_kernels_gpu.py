@@ -162,6 +162,115 @@ def test_fill_many_jobs_one_launch(gpu_ops):
         assert np.array_equal(out[i * 602112:(i + 1) * 602112], cref.fill(602112, "FP32", seed=1, stream=i))
 
 
+def _tune(key, value):
+    from client_b200 import _native
+
+    _native.check(_native.load().tb200_tune(key, value))
+
+
+@pytest.mark.parametrize("njobs,nbytes,dt,low,high", [
+    (64, 602112, "FP32", None, None),     # C2: interleaved rows, 9 CTAs per tensor, table of 64
+    (64, 602112, "FP32", -1.0, 1.0),
+    (3, 48, "FP16", None, None),          # one CTA
+    (100, 65536, "INT64", 0, 30522),      # balanced ranges across tensors, table of 256
+    (256, 3072, "INT32", 0, 128256),      # small tensors, several per CTA
+    (37, 16 * 1000, "BF16", -4.0, 4.0),
+    (5, 16 * 70001, "UINT8", 0, 200),
+    (2, 16 * 300000, "FP64", -1.0, 3.0),
+    (7, 16 * 4099, "BOOL", None, None),
+    (257, 3072, "INT16", -300, 300),      # more tensors than the parameter table holds: general kernel
+])
+def test_fill_homogeneous_launch_bit_exact(gpu_ops, njobs, nbytes, dt, low, high):
+    """fill_uniform_kernel (dtype-specialised, stream-hoisted Philox, job table in the kernel
+    parameters) for every dtype class and both work splits, against the C oracle; and the
+    general kernel produces the same bytes for the same launch."""
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    buf = DeviceBuffer(0, njobs * nbytes + 32)
+    kw = _oracle_kwargs(dt, low, high)
+    rng_kw = {} if high is None else dict(low=low, high=high)
+    jobs = [make_fill_job(buf.ptr + 16 + i * nbytes, nbytes, dt, stream_id=(i << 33) | (7 * i + 1), **rng_kw) for i in range(njobs)]
+    outs = []
+    for uniform in (1, 0):
+        _tune(b"fill_uniform", uniform)
+        try:
+            guard = np.full(njobs * nbytes + 32, 0xA5, np.uint8)
+            gpu_ops.h2d(buf.ptr, guard.ctypes.data, guard.size)
+            gpu_ops.sync()
+            launches0 = gpu_ops.ctx.launch_count
+            gpu_ops.fill(jobs, seed=0xC0FFEE1234, epoch=3)
+            gpu_ops.sync()
+            assert gpu_ops.ctx.launch_count - launches0 == 1
+            outs.append(gpu_ops.download(buf.ptr, njobs * nbytes + 32))
+        finally:
+            _tune(b"fill_uniform", 1)
+    out = outs[0]
+    assert (out[:16] == 0xA5).all() and (out[-16:] == 0xA5).all(), "fill wrote outside its tensors"
+    for i in sorted(set([0, 1, njobs // 2, njobs - 1]) if njobs > 8 else range(njobs)):
+        ref = cref.fill(nbytes, dt, seed=0xC0FFEE1234, stream=((i << 33) | (7 * i + 1)) + 3, **kw)
+        assert np.array_equal(out[16 + i * nbytes:16 + (i + 1) * nbytes], ref), (i, dt)
+    assert np.array_equal(outs[0], outs[1]), "specialised and general kernel disagree"
+
+
+def test_fill_overlapped_launches_keep_stream_order(gpu_ops):
+    """Back-to-back homogeneous fills overlap (programmatic dependent launch) only when they write
+    disjoint memory: a rewrite of the same tensors must still win, a rotation over four slot sets
+    must leave each set with the data of its last launch, and everything is complete at sync."""
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    slots, n, sets = 16, 602112, 4
+    buf = DeviceBuffer(0, sets * slots * n)
+    jobs = [[make_fill_job(buf.ptr + (s * slots + k) * n, n, "FP32", stream_id=100 * s + k) for k in range(slots)] for s in range(sets)]
+    for trial in range(6):
+        gpu_ops.fill(jobs[0], seed=1, epoch=trial)
+        gpu_ops.fill(jobs[0], seed=2, epoch=trial)        # same memory: serialised, must win
+        gpu_ops.fill(jobs[1], seed=3, epoch=trial)        # disjoint: may overlap
+        gpu_ops.fill(jobs[0], seed=4, epoch=trial)        # overlaps the chain's first range again
+        gpu_ops.sync()
+        a = gpu_ops.download(buf.ptr + (slots - 1) * n, n)
+        b = gpu_ops.download(buf.ptr + slots * n, n)
+        assert np.array_equal(a, cref.fill(n, "FP32", seed=4, stream=slots - 1 + trial)), trial
+        assert np.array_equal(b, cref.fill(n, "FP32", seed=3, stream=100 + trial)), trial
+    last = {}
+    for i in range(41):
+        s = i % sets
+        gpu_ops.fill(jobs[s], seed=9, epoch=1000 + i)
+        last[s] = 1000 + i
+    res = gpu_ops.check_one("sum", buf.ptr + 3 * n, n)  # a plain kernel behind the chain sees finished data
+    ref = cref.fill(n, "FP32", seed=9, stream=3 + last[0])
+    assert (res["sum"], res["xor32"]) == cref.checksum(ref)
+    gpu_ops.sync()
+    for s in range(sets):
+        for k in (0, slots - 1):
+            got = gpu_ops.download(buf.ptr + (s * slots + k) * n, n)
+            assert np.array_equal(got, cref.fill(n, "FP32", seed=9, stream=100 * s + k + last[s])), (s, k)
+
+
+def test_graph_chain_of_fills_advances_epoch_per_fill(gpu_ops):
+    """Several fill_epoch calls in one capture (overlapping nodes): call i of replay r uses
+    epoch0 + (r * calls + i) * bump, exactly the sequence of the same calls issued one by one."""
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    slots, n, sets, calls = 8, 602112, 4, 8
+    buf = DeviceBuffer(0, sets * slots * n)
+    jobs = [[make_fill_job(buf.ptr + (s * slots + k) * n, n, "FP32", stream_id=k) for k in range(slots)] for s in range(sets)]
+    gpu_ops.epoch_set(50)
+    gpu_ops.graph_begin()
+    for i in range(calls):
+        gpu_ops.fill_epoch(jobs[i % sets], seed=11, bump=slots)
+    g = gpu_ops.graph_end()
+    for r in range(3):
+        g.launch()
+        gpu_ops.sync()
+        for s in range(sets):
+            i_last = max(i for i in range(calls) if i % sets == s)
+            e = 50 + (r * calls + i_last) * slots
+            for k in (0, slots - 1):
+                got = gpu_ops.download(buf.ptr + (s * slots + k) * n, n)
+                assert np.array_equal(got, cref.fill(n, "FP32", seed=11, stream=k + e)), (r, s, k)
+    g.close()
+
+
 def test_fill_full_size_checksum(gpu_ops):
     """C3 size (38,535,168 B FP16): checksum of the device tensor, computed on the
     device, equals the oracle's checksum of the oracle's tensor."""
@@ -436,7 +545,7 @@ def test_graph_with_folded_bump_and_parallel_validate(gpu_ops):
             assert np.array_equal(got[k * n:(k + 1) * n], cref.fill(n, "FP32", seed=99, stream=k + e)), (it, k)
         r = results_array(res, slots)
         assert [int(x) for x in r["argmax"]] == [int(np.argmax(row)) for row in logits]
-    assert gpu_ops.ctx.launch_count - launches0 == 4 * 2
+    assert gpu_ops.ctx.launch_count - launches0 == 4 * 3  # fill, check and the node that advances the device epoch
     g.close()
     # eager fork/join as well
     gpu_ops.fork()
