@@ -1,31 +1,37 @@
 #!/usr/bin/env python
-"""bench.py -- inferences/sec and input-pack GB/s of the client-side hot path.
+"""bench.py -- sustained inferences/sec against a local CUDA-shared-memory server, and the
+input-pack GB/s of the kernels behind it.
 
-Workload (BASELINE.json configs[1], "C2"): perf_analyzer --shared-memory=cuda,
-densenet_onnx, one FP32[3,224,224] input (602,112 B) per request, 1000 x FP32
-output (4,000 B), concurrency 64, one load-generator instance per GPU.
+Workload (BASELINE.json configs[1], "C2"): perf_analyzer --shared-memory=cuda, densenet_onnx, one
+FP32[3,224,224] input (602,112 B) per request, 1000 x FP32 output (4,000 B), concurrency 64, one
+load-generation instance per GPU.  A *step* = one closed-loop round of the 64 slots = 64 completed
+requests against the stand-in server (client_b200.testing.native_server: its own process per GPU,
+opens the client's CUDA-IPC handles, runs the model as one batched kernel).  Client and server
+share the GPU through a private CUDA MPS daemon when the box has one (stated in `config.mps`).
 
-One *step* = one closed-loop round of the 64 concurrency slots on the client side:
-generate the 64 synthetic inputs (Philox4x32-10 -> FP32) directly inside the
-server-visible CUDA-IPC input regions (one launch), then unpack/validate the 64
-output regions on the device (top-1, non-finite count, checksum).  Input regions
-rotate over 4 sets (4 x 38.5 MB = 154 MB > 126 MB L2) so every step's stores go
-to HBM.
+  value     the native generator (include/tb200_loadgen.h, `python -m client_b200.perf.loopback`):
+            every request's input regenerated on the device inside its IPC region (Philox4x32-10 ->
+            FP32), every response validated on the device; K timed steps (count window), repeated
+            to >= 0.1 s, median repetition; all ranks start together, value = sum of requests /
+            max time.
+  e2e       the same metric through the tritonclient-compatible API with HOST tensors:
+            P processes each looping numpy tensor -> cuda_shared_memory.set_shared_memory_region
+            (H2D) -> InferenceServerClient.infer -> get_contents_as_numpy (D2H)
+            (client_b200/perf/host_loop.py), free-running for a fixed wall time.
+  --impl reference   that loop on the restated reference code (oracle/ref_client.py: cuda-python
+            cudaMemcpyAsync + sync per request, stdlib HTTP), same server, same process count.
+  fill_once both arms again with regions filled once and requests only naming them (what
+            perf_analyzer itself does).
+  roofline  the fill kernel (the dominant kernel of a step): 38,535,168 algorithmic bytes per launch /
+            CUDA-event time of back-to-back launches over rotating region sets (> L2), against
+            MEASURED_PEAKS.json hbm_gbs.
+  generator_capacity   the device side of a step alone (fill || validate as graph replays, no server).
+  cpu_baseline  the C oracle (oracle/tb200_oracle.c) doing the per-request generation + body marshal
+            on one host core.
 
-  value     steps captured as CUDA graphs, job tables resident on the device.
-  e2e       the same step through the public Python API (client_b200.device):
-            every step the job tables are copied host->device from pinned memory
-            and the 64 validation results are read back device->host.
-  roofline  the fill kernel (the dominant kernel): 38,535,168 algorithmic bytes
-            per launch / CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  the C oracle (oracle/tb200_oracle.c) doing the same per-request
-            work on one host core (Philox fill + tobytes + body join).
-  --impl reference   the reference client's CPU path (numpy Generator -> FP32 tensor,
-            InferInput.set_data_from_numpy = tobytes, generate_request_body = JSON +
-            b"".join; restated in oracle/wire.py) on all host cores.
-
-Multi-GPU: replicas only -- one process per GPU, no data-path
-collective; torch.distributed is used for the barrier and the max over ranks.
+Multi-GPU: replicas only -- one server + one generator per GPU, each pinned to its
+GPU's share of the local NUMA node's cores (client_b200/perf/topology.py); torch.distributed carries
+the barrier, the max over ranks and the sums.
 """
 
 import argparse
@@ -52,20 +58,24 @@ WORKLOAD = "C2 densenet_onnx FP32[3,224,224] --shared-memory=cuda concurrency=64
 
 
 def profiled_traffic(label):
-    """dram read + write bytes per launch of a kernel from the committed ncu --set full summary
-    (profiles/r01_<label>_full.txt, written by scripts/summarize_profiles.py); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01_%s_full.txt" % label)
+    """dram read + write bytes per launch of a kernel from the committed ncu summary
+    (profiles/r0N_<label>_full.txt, written by scripts/summarize_profiles.py; newest round first);
+    the first kernel block of the file.  None if absent."""
     unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    try:
-        total, seen = 0.0, 0
-        for line in open(path):
-            parts = line.split()
-            if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and seen < 2:
-                total += float(parts[1]) * unit.get(parts[2], 1)
-                seen += 1
-        return int(total) if seen == 2 else None
-    except OSError:
-        return None
+    for tag in ("r02", "r01"):
+        path = os.path.join(ROOT, "profiles", "%s_%s_full.txt" % (tag, label))
+        try:
+            total, seen = 0.0, 0
+            for line in open(path):
+                parts = line.split()
+                if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and seen < 2:
+                    total += float(parts[1].replace(",", "")) * unit.get(parts[2], 1)
+                    seen += 1
+            if seen == 2:
+                return int(total)
+        except OSError:
+            continue
+    return None
 
 
 def measured_peak():
@@ -176,38 +186,51 @@ def run_b200(args):
     run_steps(max(warmup, GRAPH_STEPS))
     ops.sync()
     rep.barrier()
-    launches0 = ctx.launch_count
+    # generator capacity (no server): whole graphs only, at least ~100 ms of device time
+    cap_steps = max(GRAPH_STEPS, (max(steps, 8000) // GRAPH_STEPS) * GRAPH_STEPS)
     timer.start()
-    run_steps(steps)
+    run_steps(cap_steps)
     timer.stop()
     ops.sync()
     rep.barrier()
-    ms_value = rep.max(timer.elapsed_ms())
-    gpu_launches = ctx.launch_count - launches0
+    ms_cap = rep.max(timer.elapsed_ms())
     res = results_array(results, SETS * SLOTS)
     assert int(res["mismatches"].sum()) == 0, "non-finite logits reported by the validate kernel"
-    value = world * SLOTS * steps / (ms_value / 1e3)
+    cap_value = world * SLOTS * cap_steps / (ms_cap / 1e3)
 
     # --- roofline of the dominant kernel: fill launches only, back to back inside one graph
     reps = 4
-    ops.graph_begin()
-    for r in range(reps):
-        for s in range(SETS):
-            ops.fill_epoch(fill_jobs[s], seed=SEED)
-    gfill = ops.graph_end()
-    for _ in range(3):
-        gfill.launch()
-    ops.sync()
-    n_graph = max(8, min(200, steps // (reps * SETS) + 1))
-    timer.start()
-    for _ in range(n_graph):
-        gfill.launch()
-    timer.stop()
-    ops.sync()
-    fill_ms = timer.elapsed_ms() / (n_graph * reps * SETS)
     fill_bytes = SLOTS * IN_BYTES
-    achieved = fill_bytes / (fill_ms / 1e3) / 1e9
     peak, peak_src = measured_peak()
+
+    def fill_chain(launch):
+        """ms per launch of `reps * SETS` back-to-back fills replayed as one graph, >= 100 ms timed"""
+        ops.graph_begin()
+        for r in range(reps):
+            for s in range(SETS):
+                launch(r, s)
+        g = ops.graph_end()
+        for _ in range(3):
+            g.launch()
+        ops.sync()
+        n = 1000  # 16,000 launches of ~7 us
+        timer.start()
+        for _ in range(n):
+            g.launch()
+        timer.stop()
+        ops.sync()
+        ms = timer.elapsed_ms() / (n * reps * SETS)
+        g.close()
+        return ms, n * reps * SETS
+
+    # the launch a device pass of the generator issues: stream epoch in the kernel parameters
+    fill_ms, fill_launches = fill_chain(lambda r, s: ops.fill(fill_jobs[s], seed=SEED, epoch=(r * SETS + s) * SLOTS))
+    achieved = fill_bytes / (fill_ms / 1e3) / 1e9
+    # the same kernel reading the device-resident epoch (graph replays that never repeat data)
+    fill_dev_ms, _ = fill_chain(lambda r, s: ops.fill_epoch(fill_jobs[s], seed=SEED, bump=SLOTS))
+    _native.check(_native.load().tb200_tune(b"fill_pdl", 0))
+    fill_serial_ms, _ = fill_chain(lambda r, s: ops.fill(fill_jobs[s], seed=SEED, epoch=(r * SETS + s) * SLOTS))
+    _native.check(_native.load().tb200_tune(b"fill_pdl", 1))
 
     if os.environ.get("TB200_STEP_PARALLEL_MIN_MB"):  # experiment knob (see include/tb200.h)
         _native.check(_native.load().tb200_tune(b"step_parallel_min_mb", int(os.environ["TB200_STEP_PARALLEL_MIN_MB"])))
@@ -258,7 +281,7 @@ def run_b200(args):
     e2e_ms = rep.max(max(timer.elapsed_ms(), e2e_wall_ms))
     assert bad == 0
     assert SETS > E2E_DEPTH  # steps in flight use different slot sets and result entries
-    e2e_value = world * SLOTS * e2e_steps / (e2e_ms / 1e3)
+    api_value = world * SLOTS * e2e_steps / (e2e_ms / 1e3)
     h2d_step = SLOTS * 64 + (SLOTS + 1) * 4 + SLOTS * 48
     d2h_step = SLOTS * 32
 
@@ -379,31 +402,141 @@ def run_b200(args):
         dfl.append({"data": label, "in_bytes": dfl_n, "out_bytes": out_bytes, "ratio": round(out_bytes / dfl_n, 4), "ms": round(d_ms, 4),
                     "in_gbps": round(dfl_n / (d_ms / 1e3) / 1e9, 1), "host_zlib6_mbps": round(len(sample) / z_s / 1e6, 1),
                     "host_zlib6_ratio": round(len(zl) / len(sample), 4)})
+
+    # ------------------------------------------------------------------------------------------
+    # the north-star metric: sustained inferences/sec against the stand-in server (one per GPU)
+    # ------------------------------------------------------------------------------------------
+    ops.sync()
+    nproc, host_cores = host_process_count(world)
+    nproc_rank = max(1, nproc // world)
+    lb, lb_error = {}, None
+    import shutil
+
+    have_mps = shutil.which("nvidia-cuda-mps-control") is not None and not args.no_mps
+    if rank == 0 and have_mps:
+        try:
+            LoopbackBox.start_mps()
+        except Exception:
+            have_mps = False
+    if world > 1:  # rank 0 decides
+        have_mps = rep.sum(1.0 if (rank == 0 and have_mps) else 0.0) > 0
+    rep.barrier()
+    box = None
+    try:
+        box = LoopbackBox([local], use_mps=have_mps, manage_mps=False, grpc=(world == 1)).__enter__()
+    except Exception as ex:
+        lb_error = "%s: %s" % (type(ex).__name__, ex)
+    # every rank walks the same list and meets the others at a barrier after each entry, whatever happened
+    plan = [("warm", lambda: box.generator(local, 50, 5, min_seconds=0.05)),
+            ("value", lambda: box.generator(local, steps, warmup)),
+            ("once", lambda: box.generator(local, steps, warmup, mode="once")),
+            ("warm_host", lambda: host_loops(box, "b200", min(nproc_rank, 4), 0.5, "per-request")),
+            ("e2e", lambda: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "per-request")),
+            ("e2e_once", lambda: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "once"))]
+    for name, fn in plan:
+        if box is not None and lb_error is None:
+            try:
+                lb[name] = fn()
+            except Exception as ex:
+                lb_error = "%s: %s: %s" % (name, type(ex).__name__, ex)
+        rep.barrier()
+    if box is not None and lb_error is None and world == 1 and not args.no_loopback:
+        extras = {}
+        for key, conc, extra in (("c1", 1, ()), ("c256", 256, ()), ("c64_one_pass_at_a_time", 64, ("--device-pipeline", "1")),
+                                 ("c1_lookahead8", 1, ("--lookahead", "8")), ("c256_lookahead8", 256, ("--lookahead", "8"))):
+            try:
+                g = box.generator(local, 400 if conc >= 64 else 4000, 10, concurrency=conc, extra=extra, min_seconds=0.5)
+                extras[key] = {k: (round(v, 1) if isinstance(v, float) else v) for k, v in g.items()
+                               if k in ("concurrency", "infer_per_s", "p50_us", "p99_us", "failed", "nonfinite", "slots_per_device_pass", "pipeline_depth")}
+            except Exception as ex:
+                extras[key] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        if box.grpc_urls.get(local):
+            try:
+                extras["grpc"] = _grpc_loopback_levels(box.grpc_urls[local], box.env)
+            except Exception as ex:
+                extras["grpc"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        lb["levels"] = extras
+    if box is not None:
+        box.__exit__(None, None, None)
+    rep.barrier()
+    if rank == 0 and have_mps:
+        try:
+            LoopbackBox.stop_mps()
+        except Exception:
+            pass
+    time_sliced = None
+    if world == 1 and have_mps and not args.no_loopback and lb_error is None:
+        try:  # the same run without MPS: client and server are time-sliced CUDA contexts
+            with LoopbackBox([local], use_mps=False, manage_mps=False) as box:
+                box.generator(local, 50, 5, min_seconds=0.05)
+                g = box.generator(local, min(steps, 2000), warmup, extra=("--device-window-us", "150"), min_seconds=0.5)
+                time_sliced = {"infer_per_s": round(g["infer_per_s"], 1), "p50_us": round(g["p50_us"], 1), "device_window_us": 150,
+                               "slots_per_device_pass": round(g["slots_per_device_pass"], 1)}
+        except Exception as ex:
+            time_sliced = {"error": "%s: %s" % (type(ex).__name__, ex)}
     clocks = sampler.stop()
+
+    any_error = rep.sum(0.0 if lb_error is None else 1.0) > 0
+    if any_error and lb_error is None:
+        lb_error = "another rank's loopback run failed"
+
+    def total(key, field):
+        return rep.sum(lb[key][field])
+
+    if lb_error is None:
+        v = lb["value"]
+        seconds = rep.max(v["seconds"])
+        value = rep.sum(v["count"]) / seconds
+        gpu_launches = int(rep.sum(v["gpu_launches"]))
+        once_value = rep.sum(lb["once"]["count"]) / rep.max(lb["once"]["seconds"])
+        e2e_value = total("e2e", "count") / HOST_LOOP_SECONDS
+        e2e_once_value = total("e2e_once", "count") / HOST_LOOP_SECONDS
+        ms_step = seconds * 1e3 / (v["count"] / SLOTS)
+    else:  # no server could be had: the device side alone, flagged
+        value, gpu_launches, once_value, e2e_value, e2e_once_value = 0.0, 0, 0.0, 0.0, 0.0
+        ms_step = None
+        v = {}
 
     line = {
         "metric": "inferences/sec", "value": round(value, 1), "unit": "infer/s",
         "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": round(ms_value / steps, 6), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": round(ms_step, 6) if ms_step else None, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "concurrency": SLOTS, "request_input_bytes": IN_BYTES,
-                   "request_output_bytes": OUT_BYTES, "l2": "inputs rotate over %d region sets = %d MB > 126 MB L2" % (SETS, SETS * SLOTS * IN_BYTES // 1000000),
-                   "parallelism": "replicas x%d (one load-gen per GPU, no collective)" % world, "seed": SEED},
-        "input_pack_gbps": round(world * SLOTS * IN_BYTES * steps / (ms_value / 1e3) / 1e9, 1),
-        "e2e": {"value": round(e2e_value, 1), "unit": "infer/s", "h2d_bytes_per_step": h2d_step,
-                "d2h_bytes_per_step": d2h_step, "steps": e2e_steps,
-                "what": "client_b200.device.DeviceOps.step_submit()/step_wait() per step, 2 steps in flight: job tables H2D from pinned memory, fill || validate, results D2H into mapped host memory, host waits for the step and reads its 64 results",
-                "sync_per_step": {"value": round(e2e_sync_value, 1), "steps": sync_steps, "what": "DeviceOps.step(): the same, each step waited for before the next is formed"}},
+        "config": common_config(have_mps, world),
+        "what": "sustained inferences/sec of the native generator against the stand-in server: every request's FP32[3,224,224] input regenerated "
+                "on the device inside its CUDA-IPC region, every response validated on the device; %d timed steps of %d requests per repetition, "
+                "median of %s repetitions" % (steps, SLOTS, v.get("repetitions")),
+        "p50_us": round(v.get("p50_us", 0.0), 1), "p99_us": round(v.get("p99_us", 0.0), 1),
+        "failed": int(total("value", "failed")) if lb_error is None else None, "nonfinite": int(total("value", "nonfinite")) if lb_error is None else None,
+        "slots_per_device_pass": round(v.get("slots_per_device_pass", 0.0), 1), "pipeline_depth": v.get("pipeline_depth"),
+        "pinned_cpus_per_generator": v.get("cpus"), "host_cores": host_cores,
+        "input_pack_gbps": round(value * IN_BYTES / 1e9, 1),
+        "l2": "inputs of the kernel timings rotate over %d region sets = %d MB > 126 MB L2" % (SETS, SETS * SLOTS * IN_BYTES // 1000000),
+        "e2e": {"value": round(e2e_value, 1), "unit": "infer/s", "h2d_bytes_per_step": SLOTS * IN_BYTES, "d2h_bytes_per_step": SLOTS * OUT_BYTES,
+                "processes": nproc_rank * world, "seconds": HOST_LOOP_SECONDS, "p50_us": lb.get("e2e", {}).get("p50_us"),
+                "what": "tritonclient-compatible API with host tensors (client_b200/perf/host_loop.py): numpy FP32[3,224,224] -> "
+                        "cuda_shared_memory.set_shared_memory_region (H2D) -> http.InferenceServerClient.infer naming the regions -> "
+                        "get_contents_as_numpy (D2H), free-running processes, same server"},
+        "fill_once": {"value": round(once_value, 1), "e2e": round(e2e_once_value, 1), "p50_us": lb.get("once", {}).get("p50_us"),
+                      "what": "regions filled once, every request only names them (perf_analyzer's own behaviour): native generator / drop-in API loop"},
+        "gpu_launches": gpu_launches,
+        "roofline": {"bound": "issue (FMA-heavy pipe: 18 IMAD.WIDE per 16 B), then HBM write", "kernel": "fill_uniform_kernel (Philox4x32-10 -> FP32, 64 slots per launch)",
+                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": profiled_traffic("fill_uniform_kernel"),
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of a steady-state launch (rotating sets, no cache control), profiles/r02_fill_uniform_kernel_full.txt",
+                     "algorithmic_bytes_per_launch": fill_bytes, "ms_per_launch": round(fill_ms, 6),
+                     "peak_source": peak_src, "timing": "CUDA events on the launching stream around %d back-to-back launches (graph replays of 16, stream epoch in the kernel parameters -- the launch a device pass issues)" % fill_launches,
+                     "device_epoch_graph": {"ms_per_launch": round(fill_dev_ms, 6), "frac": round(fill_bytes / (fill_dev_ms / 1e3) / 1e9 / peak, 4)},
+                     "launches_serialised": {"ms_per_launch": round(fill_serial_ms, 6), "frac": round(fill_bytes / (fill_serial_ms / 1e3) / 1e9 / peak, 4),
+                                             "what": "the same chain without programmatic dependent launch (tb200_tune fill_pdl=0)"}},
+        "generator_capacity": {"value": round(cap_value, 1), "unit": "infer/s", "steps": cap_steps, "ms_per_step": round(ms_cap / cap_steps, 6),
+                               "what": "the device side of a step alone, no server: fill(64 slots) || validate(64 outputs) as CUDA-graph replays of 16 steps",
+                               "api_pipelined": {"value": round(api_value, 1), "steps": e2e_steps, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                                                 "what": "DeviceOps.step_submit()/step_wait(), 2 steps in flight: job tables H2D, results D2H, host reads every step's 64 results"},
+                               "api_sync_per_step": {"value": round(e2e_sync_value, 1), "steps": sync_steps}},
         "e2e_host_images": {"value": round(img_value, 1), "unit": "infer/s", "h2d_bytes_per_step": SLOTS * 224 * 224 * 3,
                             "d2h_bytes_per_step": d2h_step, "steps": img_steps,
-                            "what": "64 uint8 HWC host images (pinned) -> H2D -> INCEPTION cast + CHW pack into the IPC slots -> validate"},
-        "gpu_launches": int(gpu_launches),
-        "roofline": {"bound": "hbm", "kernel": "fill_kernel (Philox4x32-10 -> FP32, 64 slots per launch)",
-                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": profiled_traffic("fill_kernel"),
-                     "traffic_note": "dram read+write per launch from profiles/r01_fill_kernel_full.txt (ncu --set full); a write-only 38.5 MB launch stays in the 126 MB L2",
-                     "algorithmic_bytes_per_launch": fill_bytes, "ms_per_launch": round(fill_ms, 6),
-                     "peak_source": peak_src, "timing": "CUDA events on the launching stream around %d back-to-back launches in a graph" % (n_graph * reps * SETS)},
+                            "what": "no server: 64 uint8 HWC host images (pinned) -> H2D -> INCEPTION cast + CHW pack into the IPC slots -> validate"},
         "roofline_pack": {"bound": "hbm", "kernel": "pack_image_chw_tma_kernel (uint8 HWC -> FP32 CHW, INCEPTION)",
                           "achieved": round(pack_bytes / (pack_ms / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                           "frac": round(pack_bytes / (pack_ms / 1e3) / 1e9 / peak, 4),
@@ -422,6 +555,12 @@ def run_b200(args):
         },
         "clocks": clocks,
     }
+    if lb_error is not None:
+        line["loopback_error"] = lb_error
+    if "levels" in lb:
+        line["loopback_levels"] = lb["levels"]
+    if time_sliced is not None:
+        line["time_sliced_no_mps"] = time_sliced
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_port()
     if rank == 0 and world == 1:
@@ -429,11 +568,6 @@ def run_b200(args):
             line["wire_c4_c5"] = wire_extra(ops, ctx, local)
         except Exception as ex:
             line["wire_c4_c5"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
-    if rank == 0 and world == 1 and not args.no_loopback:
-        try:
-            line["loopback"] = loopback_extra(local)
-        except Exception as ex:  # the extra must never cost the bench line
-            line["loopback"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     rep.close()
@@ -513,96 +647,163 @@ def wire_extra(ops, ctx, device, seconds=1.0):
     return out
 
 
-def loopback_extra(device, seconds=1.5):
-    """The north star's first metric as the user sees it: sustained inferences/sec against a
-    local CUDA-shared-memory server.  The native stand-in server runs as its own process (it
-    opens our IPC handles); requests only name regions; every request's FP32[3,224,224] input is
-    regenerated and its output validated on the device by the native load generator.  Beside it,
-    the reference-style CPU client loop (numpy tensor -> set_shared_memory_region -> infer ->
-    get_contents_as_numpy), one thread, same server.  Client and server are time-sliced CUDA
-    contexts here (no MPS): see profiles/ for the MPS numbers."""
-    import socket
+SERVER_DESC = "client_b200.testing.native_server (own process per GPU, opens the CUDA-IPC handles, batched model kernel)"
 
-    import client_b200.http as httpclient
-    from client_b200.perf.loadgen import SlotSet, TensorSpec
-    from client_b200.perf.native import NativeLoadGenerator
 
-    with socket.socket() as sk:
-        sk.bind(("127.0.0.1", 0))
-        port = sk.getsockname()[1]
-    srv = subprocess.Popen([sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(device), "--grpc-port", "0"],
-                           cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    out = {"server": "client_b200.testing.native_server (own process, CUDA IPC, batched model kernel)", "mps": False, "levels": []}
+def common_config(mps, world):
+    """The config block both arms print (identical keys and values for the same box)."""
+    return {"workload": WORKLOAD, "concurrency": SLOTS, "request_input_bytes": IN_BYTES, "request_output_bytes": OUT_BYTES,
+            "server": SERVER_DESC, "mps": bool(mps), "instances": world}
+
+
+class LoopbackBox:
+    """The serving side of a loopback run: a private CUDA MPS daemon (when the box has the binary and
+    `manage_mps`) and one native server process per device, each pinned to its GPU's server cores."""
+
+    MPS_ENV = {"CUDA_MPS_PIPE_DIRECTORY": "/tmp/tb200_mps_pipe", "CUDA_MPS_LOG_DIRECTORY": "/tmp/tb200_mps_log"}
+
+    def __init__(self, devices, use_mps=True, manage_mps=True, grpc=False, pin=True):
+        import shutil
+
+        self.devices, self.grpc, self.pin = list(devices), grpc, pin
+        self.manage_mps = manage_mps and use_mps and shutil.which("nvidia-cuda-mps-control") is not None
+        self.mps = use_mps and shutil.which("nvidia-cuda-mps-control") is not None
+        self.env = dict(os.environ, **self.MPS_ENV) if self.mps else dict(os.environ)
+        self.servers, self.urls, self.grpc_urls = {}, {}, {}
+
+    @classmethod
+    def start_mps(cls):
+        env = dict(os.environ, **cls.MPS_ENV)
+        for d in cls.MPS_ENV.values():
+            os.makedirs(d, exist_ok=True)
+        subprocess.run(["nvidia-cuda-mps-control", "-d"], env=env, timeout=30, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        time.sleep(1.0)
+
+    @classmethod
+    def stop_mps(cls):
+        env = dict(os.environ, **cls.MPS_ENV)
+        subprocess.run(["nvidia-cuda-mps-control"], input="quit\n", env=env, text=True, timeout=30, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+    def __enter__(self):
+        import socket
+
+        if self.manage_mps:
+            try:
+                self.start_mps()
+            except Exception:
+                self.mps = self.manage_mps = False
+                self.env = dict(os.environ)
+        for dev in self.devices:
+            with socket.socket() as sk:
+                sk.bind(("127.0.0.1", 0))
+                port = sk.getsockname()[1]
+            cmd = [sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(dev)]
+            if self.grpc:
+                cmd += ["--grpc-port", "0"]
+            if self.pin:
+                cmd += ["--pin-cpus"]
+            self.servers[dev] = subprocess.Popen(cmd, cwd=ROOT, env=self.env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            self.urls[dev] = "127.0.0.1:%d" % port
+        for dev, srv in self.servers.items():
+            hello = srv.stdout.readline()
+            if "listening" not in hello:
+                self.__exit__(None, None, None)
+                raise RuntimeError("native server for device %d did not start: %s" % (dev, hello.strip()[:200]))
+            if "grpc=" in hello:
+                self.grpc_urls[dev] = hello.split("grpc=")[1].strip()
+        return self
+
+    def __exit__(self, *exc):
+        for srv in self.servers.values():
+            srv.terminate()
+        for srv in self.servers.values():
+            try:
+                srv.wait(10)
+            except Exception:
+                srv.kill()
+        self.servers = {}
+        if self.manage_mps:
+            try:
+                self.stop_mps()
+            except Exception:
+                pass
+        return False
+
+    def generator(self, dev, steps, warmup, mode="per-request", concurrency=SLOTS, extra=(), min_seconds=0.1, timeout=180):
+        """One `python -m client_b200.perf.loopback` child against this box's server for `dev`."""
+        cmd = [sys.executable, "-m", "client_b200.perf.loopback", "-u", self.urls[dev], "--device", str(dev), "--concurrency", str(concurrency),
+               "--steps", str(steps), "--warmup", str(warmup), "--input-data-mode", mode, "--min-seconds", str(min_seconds),
+               "--seed", str(SEED), "--json"] + (["--pin-cpus"] if self.pin else []) + list(extra)
+        r = subprocess.run(cmd, cwd=ROOT, env=self.env, capture_output=True, text=True, timeout=timeout)
+        for line in r.stdout.splitlines():
+            if line.startswith("{"):
+                return json.loads(line)
+        raise RuntimeError("generator child failed: " + (r.stdout + r.stderr)[-400:])
+
+
+def _host_loop_worker(impl, url, device, tag, seconds, data_mode, ready, go, q):
     try:
-        hello = srv.stdout.readline()
-        if "listening" not in hello:
-            raise RuntimeError("native server did not start")
-        grpc_url = hello.split("grpc=")[1].strip() if "grpc=" in hello else None
-        url = "127.0.0.1:%d" % port
-        control = httpclient.InferenceServerClient(url)
-        # last two: look-ahead (8 input / output images per slot and device pass, every request fresh)
-        for conc, window, la in ((1, 0, 1), (64, 150, 1), (256, 150, 1), (1, 0, 8), (256, 0, 8)):
-            ss = SlotSet([TensorSpec("data_0", "FP32", [3, 224, 224])], [TensorSpec("fc6_1", "FP32", [1000])], conc, "cuda", device,
-                         "random", SEED, name_prefix="bench_lb%d_%d" % (conc, la), lookahead=la)
-            ss.register(control)
-            gen = NativeLoadGenerator(url, "densenet_onnx", "", ss, conc, regenerate=True, validate=True, device_window_us=window)
-            gen.start()
-            try:
-                gen.window(0.5)
-                w = gen.window(seconds)
-            finally:
-                gen.stop()
-                ss.unregister(control)
-                ss.close()
-            out["levels"].append({"concurrency": conc, "infer_per_s": round(w["throughput"], 1), "p50_us": round(w["p50_us"], 1),
-                                  "p99_us": round(w["p99_us"], 1), "failed": int(w["failed"]), "nonfinite": int(w["nonfinite"]),
-                                  "slots_per_device_pass": round(w["device_slots"] / max(1, w["device_batches"]), 1),
-                                  "device_window_us": window, "lookahead": la})
-        # reference-style CPU client loop, one thread
-        import client_b200.utils.cuda_shared_memory as cudashm
-
-        rng = np.random.default_rng(0)
-        in_h = cudashm.create_shared_memory_region("bench_cpu_in", IN_BYTES, device)
-        out_h = cudashm.create_shared_memory_region("bench_cpu_out", OUT_BYTES, device)
-        control.register_cuda_shared_memory("bench_cpu_in", cudashm.get_raw_handle(in_h), device, IN_BYTES)
-        control.register_cuda_shared_memory("bench_cpu_out", cudashm.get_raw_handle(out_h), device, OUT_BYTES)
-        inp = httpclient.InferInput("data_0", [3, 224, 224], "FP32").set_shared_memory("bench_cpu_in", IN_BYTES)
-        o = httpclient.InferRequestedOutput("fc6_1")
-        o.set_shared_memory("bench_cpu_out", OUT_BYTES)
-        lat, t_end = [], time.perf_counter() + seconds
-        t0 = time.perf_counter()
-        while time.perf_counter() < t_end:
-            t1 = time.perf_counter_ns()
-            x = rng.random((3, 224, 224), dtype=np.float32)
-            cudashm.set_shared_memory_region(in_h, [x])
-            control.infer("densenet_onnx", [inp], outputs=[o])
-            y = cudashm.get_contents_as_numpy(out_h, np.float32, [1000])
-            assert np.isfinite(y).all()
-            lat.append(time.perf_counter_ns() - t1)
-        dt = time.perf_counter() - t0
-        out["cpu_client_loop"] = {"concurrency": 1, "infer_per_s": round(len(lat) / dt, 1), "p50_us": round(float(np.percentile(lat, 50)) / 1e3, 1),
-                                  "what": "numpy Generator.random -> set_shared_memory_region (H2D + sync) -> infer -> get_contents_as_numpy (D2H), one thread"}
-        control.unregister_cuda_shared_memory()
-        cudashm.destroy_shared_memory_region(in_h)
-        cudashm.destroy_shared_memory_region(out_h)
-        control.close()
-        if grpc_url:
-            try:
-                out["grpc"] = _grpc_loopback_levels(grpc_url)
-            except Exception as ex:
-                out["grpc"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
-    finally:
-        srv.terminate()
+        if impl == "reference":
+            from oracle import ref_client as mod
+        else:
+            from client_b200.perf import host_loop as mod
+        n, lat = mod.run_loop(url, device, tag, seconds, data_mode, ready=ready, go=go)
+        q.put((n, lat[:: max(1, len(lat) // 2000)], None))
+    except Exception as ex:  # the parent must not hang on the barrier
         try:
-            srv.wait(10)
+            ready.abort()
         except Exception:
-            srv.kill()
-    try:
-        out["under_mps"] = loopback_under_mps(device)
-    except Exception as ex:
-        out["under_mps"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
-    return out
+            pass
+        q.put((0, [], "%s: %s" % (type(ex).__name__, ex)))
 
+
+def host_loops(box, impl, nproc, seconds, data_mode):
+    """`nproc` free-running client processes (round-robin over the box's servers) for `seconds`
+    of wall time; impl "b200" = the drop-in modules, "reference" = the restated reference code."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    saved = {k: os.environ.get(k) for k in LoopbackBox.MPS_ENV}
+    if box.mps:
+        os.environ.update(LoopbackBox.MPS_ENV)  # the children must come up under the MPS daemon
+    try:
+        ready, go, q = ctx.Barrier(nproc + 1), ctx.Event(), ctx.Queue()
+        devs = box.devices
+        procs = [ctx.Process(target=_host_loop_worker,
+                             args=(impl, box.urls[devs[i % len(devs)]], devs[i % len(devs)], "%s%d_%d" % (impl[0], os.getpid(), i), seconds, data_mode, ready, go, q))
+                 for i in range(nproc)]
+        for p in procs:
+            p.start()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    try:
+        ready.wait(timeout=240)  # every client has its CUDA context, regions and connection
+    except Exception:
+        pass
+    t0 = time.perf_counter()
+    go.set()
+    parts = [q.get(timeout=seconds + 240) for _ in procs]
+    dt = time.perf_counter() - t0
+    for p in procs:
+        p.join(30)
+    errors = [e for _, _, e in parts if e]
+    total = sum(n for n, _, _ in parts)
+    lat = np.concatenate([np.asarray(l, dtype=np.float64) for _, l, _ in parts if len(l)]) / 1e3 if total else np.zeros(1)
+    return {"infer_per_s": round(total / seconds, 1), "count": int(total), "seconds": seconds, "wall_seconds": round(dt, 3), "processes": nproc,
+            "p50_us": round(float(np.percentile(lat, 50)), 1), "p99_us": round(float(np.percentile(lat, 99)), 1),
+            **({"errors": errors[:2]} if errors else {})}
+
+
+def host_process_count(world):
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, min(32 * world, cores // 2)), cores
+
+
+HOST_LOOP_SECONDS = 2.5
 
 def _grpc_loopback_levels(grpc_url, env=None):
     """BASELINE configs[3] / [4] against the native server's gRPC port: the CLI's native engine
@@ -627,65 +828,7 @@ def _grpc_loopback_levels(grpc_url, env=None):
     return out
 
 
-def loopback_under_mps(device):
-    """The same loop with server and generator as two processes that share the GPU through
-    CUDA MPS (their kernels run concurrently instead of time-sliced).  The daemon listens on a
-    private pipe directory, so nothing else on the box is affected; it is shut down afterwards."""
-    import shutil
-    import socket
-
-    if shutil.which("nvidia-cuda-mps-control") is None:
-        return {"available": False}
-    env = dict(os.environ, CUDA_MPS_PIPE_DIRECTORY="/tmp/tb200_mps_pipe", CUDA_MPS_LOG_DIRECTORY="/tmp/tb200_mps_log")
-    os.makedirs(env["CUDA_MPS_PIPE_DIRECTORY"], exist_ok=True)
-    os.makedirs(env["CUDA_MPS_LOG_DIRECTORY"], exist_ok=True)
-    subprocess.run(["nvidia-cuda-mps-control", "-d"], env=env, timeout=30, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    srv = None
-    try:
-        time.sleep(1.0)
-        with socket.socket() as sk:
-            sk.bind(("127.0.0.1", 0))
-            port = sk.getsockname()[1]
-        srv = subprocess.Popen([sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(device), "--grpc-port", "0"],
-                               cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        hello = srv.stdout.readline()
-        if "listening" not in hello:
-            raise RuntimeError("native server did not start under MPS")
-        r = subprocess.run([sys.executable, "-m", "client_b200.perf", "-m", "densenet_onnx", "-u", "127.0.0.1:%d" % port,
-                            "--shared-memory", "cuda", "--engine", "native", "--concurrency-range", "1:256:4x",
-                            "-p", "700", "-r", "4", "--json"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
-        levels = []
-        for line in r.stdout.splitlines():
-            if line.startswith("{"):
-                w = json.loads(line)
-                levels.append({"concurrency": w["concurrency"], "infer_per_s": round(w["throughput"], 1), "p50_us": round(w["p50_us"], 1),
-                               "p99_us": round(w["p99_us"], 1), "failed": int(w["failed"]), "nonfinite": int(w["nonfinite"])})
-        if not levels:
-            raise RuntimeError("no result rows: " + (r.stdout + r.stderr)[-300:])
-        res = {"available": True, "levels": levels}
-        r = subprocess.run([sys.executable, "-m", "client_b200.perf", "-m", "densenet_onnx", "-u", "127.0.0.1:%d" % port,
-                            "--shared-memory", "cuda", "--engine", "native", "--lookahead", "8", "--concurrency-range", "1:256:256x",
-                            "-p", "700", "-r", "4", "--json"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
-        res["lookahead_8"] = [{"concurrency": w["concurrency"], "infer_per_s": round(w["throughput"], 1), "p50_us": round(w["p50_us"], 1),
-                               "p99_us": round(w["p99_us"], 1), "failed": int(w["failed"]), "nonfinite": int(w["nonfinite"])}
-                              for w in (json.loads(line) for line in r.stdout.splitlines() if line.startswith("{"))]
-        if "grpc=" in hello:
-            try:
-                res["grpc"] = _grpc_loopback_levels(hello.split("grpc=")[1].strip(), env)
-            except Exception as ex:
-                res["grpc"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
-        return res
-    finally:
-        if srv is not None:
-            srv.terminate()
-            try:
-                srv.wait(10)
-            except Exception:
-                srv.kill()
-        subprocess.run(["nvidia-cuda-mps-control"], input="quit\n", env=env, text=True, timeout=30, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-
-
-def cpu_baseline_port(seconds=12.0):
+def cpu_baseline_port(seconds=8.0):
     """The C oracle on one host core doing the per-request work of the step: Philox fill
     of one FP32[3,224,224] tensor + tobytes + body join (two memcpys)."""
     from oracle import cref
@@ -710,69 +853,40 @@ def cpu_baseline_port(seconds=12.0):
             "sample": "%d requests in %.1f s: oracle_fill FP32[3,224,224] + tobytes + JSON/body join, 1 thread" % (done, dt)}
 
 
-def _ref_worker(args):
-    """One request of the reference client's CPU path (restated in oracle/wire.py)."""
-    count, seed = args
-    from oracle import wire
-
-    rng = np.random.default_rng(seed)
-    total = 0
-    for _ in range(count):
-        x = rng.random(IN_SHAPE, dtype=np.float32)                       # synthetic input tensor
-        inp = wire.HttpInput("data_0", list(IN_SHAPE), "FP32").set_data(x)  # set_data_from_numpy: tobytes()
-        body, _ = wire.http_request_body([inp], [wire.HttpOutput("fc6_1")])  # JSON header + b"".join
-        total += len(body)
-    return total
-
-
 def run_reference(args):
-    """--impl reference: the reference client's own CPU implementation of the step on all
-    host cores (rank 0 only)."""
-    import multiprocessing as mp
-
+    """--impl reference: the reference client's own CPU path for C2 (numpy tensor ->
+    set_shared_memory_region with a real H2D -> infer -> get_contents_as_numpy), restated in
+    oracle/ref_client.py, as free-running worker processes against the same stand-in server(s);
+    rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    world = max(1, args.gpus)
     steps, warmup = args.steps, max(args.warmup, 3)
-    steps = min(steps, 400)  # bounded: a step is 64 requests of ~0.5 ms CPU each
-
-    def split(nproc):
-        per = [SLOTS // nproc + (1 if i < SLOTS % nproc else 0) for i in range(nproc)]
-        return [p for p in per if p]
-
-    def run_steps(pool, per, n, base):
-        t0 = time.perf_counter()
-        for s in range(n):
-            pool.map(_ref_worker, [(p, (base + s) * 1000 + i) for i, p in enumerate(per)])
-        return time.perf_counter() - t0
-
-    # the path is memory-bound: more processes are not always faster, so give the
-    # reference its best process count (probed on untimed steps)
-    best = None
-    candidates = sorted({n for n in (1, 2, 4, 8, 16, 32, 64, cores // 4, cores // 2, cores) if 1 <= n <= min(cores, SLOTS)})
-    for nproc in candidates:
-        per = split(nproc)
-        with mp.get_context("fork").Pool(len(per)) as pool:
-            run_steps(pool, per, 2, 0)
-            dt_probe = min(run_steps(pool, per, 3, 10), run_steps(pool, per, 3, 20))
-        if best is None or dt_probe < best[0]:
-            best = (dt_probe, per)
-    per = best[1]
-    with mp.get_context("fork").Pool(len(per)) as pool:
-        run_steps(pool, per, warmup, 100)
-        dt = run_steps(pool, per, steps, 1000)
-    value = SLOTS * steps / dt
+    nproc, cores = host_process_count(world)
+    with LoopbackBox(range(world), grpc=False) as box:
+        host_loops(box, "reference", min(nproc, 4), 0.5, "per-request")  # warm-up: contexts, page cache, server
+        per_request = host_loops(box, "reference", nproc, HOST_LOOP_SECONDS, "per-request")
+        once = host_loops(box, "reference", nproc, HOST_LOOP_SECONDS, "once")
+        mps = box.mps
+    value = per_request["infer_per_s"]
+    sample = ("%d free-running processes x %.1f s: numpy Generator.random FP32[3,224,224] -> cudaMemcpyAsync H2D + sync (set_shared_memory_region) -> "
+              "HTTP infer naming the regions -> whole-region D2H + sync (get_contents_as_numpy); oracle/ref_client.py + oracle/wire.py" % (nproc, HOST_LOOP_SECONDS))
     line = {
-        "impl": "reference", "metric": "inferences/sec", "value": round(value, 1), "unit": "infer/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(dt / steps * 1e3, 4),
+        "impl": "reference", "metric": "inferences/sec", "value": value, "unit": "infer/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(SLOTS / value * 1e3, 4) if value else None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "concurrency": SLOTS, "request_input_bytes": IN_BYTES},
-        "cpu_baseline": {"value": round(value, 1), "unit": "infer/s", "cores": len(per), "kind": "port",
-                         "sample": "%d steps x 64 requests: numpy Generator.random FP32[3,224,224] + tobytes + JSON/b''.join (oracle/wire.py restatement of the reference client), %d processes" % (steps, len(per))},
-        "e2e": {"value": round(value, 1), "unit": "infer/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": common_config(mps, world),
+        "cpu_baseline": {"value": value, "unit": "infer/s", "cores": nproc, "kind": "port", "sample": sample, "host_cores": cores},
+        "e2e": {"value": value, "unit": "infer/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "p50_us": per_request["p50_us"], "p99_us": per_request["p99_us"],
+        "fill_once": {"value": once["infer_per_s"], "p50_us": once["p50_us"], "processes": nproc,
+                      "what": "regions filled once, every request only names them (no per-request host tensor work)"},
         "input_pack_gbps": round(value * IN_BYTES / 1e9, 3),
+        "timing": "wall clock: completed requests of all processes / the fixed run time (free-running, no per-step barrier)",
     }
+    if per_request.get("errors"):
+        line["errors"] = per_request["errors"]
     print(json.dumps(line), flush=True)
 
 
@@ -783,7 +897,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-loopback", action="store_true", help="skip the loopback extra (native server in its own process)")
+    ap.add_argument("--no-loopback", action="store_true", help="skip the extra loopback levels (other concurrencies, gRPC configs, the run without MPS)")
+    ap.add_argument("--no-mps", action="store_true", help="do not start a CUDA MPS daemon: client and server time-slice the GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

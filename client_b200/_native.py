@@ -146,6 +146,7 @@ SIGNATURES = {
     "tb200_deflate_bound": (c_u64, [c_u64]),
     "tb200_deflate_async": (c_int, [c_vp, c_vp, c_u64, c_vp, c_u64, c_u32, c_vp]),
     "tb200_topk_async": (c_int, [c_vp, ctypes.POINTER(TopkJob), c_int, c_int, c_vp]),
+    "tb200_bytes_decode_async": (c_int, [c_vp, c_vp, c_u64, c_u64, c_vp, c_vp, c_u64, c_vp]),
     "tb200_graph_begin": (c_int, [c_vp]),
     "tb200_graph_end": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "tb200_graph_launch": (c_int, [c_vp, c_vp]),

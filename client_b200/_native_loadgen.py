@@ -19,6 +19,7 @@ class LoadgenConfig(ctypes.Structure):
         ("check_jobs", ctypes.POINTER(CheckJob)), ("check_jobs_per_slot", c_int), ("results", c_vp),
         ("device_window_us", ctypes.c_uint32), ("protocol", ctypes.c_uint32), ("grpc_path", ctypes.c_char_p),
         ("lookahead", ctypes.c_uint32), ("tail_stride", c_u64), ("requests_per_slot", ctypes.c_uint32),
+        ("pipeline_depth", ctypes.c_uint32),
     ]
 
 
@@ -40,6 +41,7 @@ LOADGEN_SIGNATURES = {
     "tb200_loadgen_create": (c_int, [ctypes.POINTER(LoadgenConfig), ctypes.POINTER(c_vp)]),
     "tb200_loadgen_start": (c_int, [c_vp]),
     "tb200_loadgen_window": (c_int, [c_vp, ctypes.c_double, ctypes.POINTER(LoadgenStats)]),
+    "tb200_loadgen_wait_count": (c_int, [c_vp, c_u64, ctypes.c_double, ctypes.POINTER(c_u64)]),
     "tb200_loadgen_stop": (c_int, [c_vp]),
     "tb200_loadgen_destroy": (c_int, [c_vp]),
     "tb200_stub_server_start": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int), ctypes.c_char_p, ctypes.POINTER(c_vp)]),

@@ -406,9 +406,19 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // groups g = first, first + stride, ... < end of one tensor; U independent Philox chains per thread
-template <uint32_t DT, int U>
+// PLAIN: unit-interval floats / raw-bit integers (the default data of the generator): the range
+// test of fill_group folds away at compile time instead of costing a predicated FFMA per word
+template <uint32_t DT, int U, bool PLAIN>
 __device__ __forceinline__ void fill_run(uint8_t* __restrict__ dst, uint32_t first, uint32_t stride, uint32_t end,
                                          const PhiloxStreamConst& sc, const FillUniform& L) {
+  FillParams prm = L.p;
+  if (PLAIN) {
+    prm.unit = 1u;
+    prm.irange = 0;
+  } else {
+    prm.unit = 0u;
+    if (prm.irange == 0) prm.irange = 1;  // never taken: integer launches with irange == 0 are PLAIN
+  }
   uint32_t g = first;
   uint8_t* p = dst + static_cast<uint64_t>(g) * 16u;
   uint64_t pstep = static_cast<uint64_t>(stride) * 16u;
@@ -418,7 +428,7 @@ __device__ __forceinline__ void fill_run(uint8_t* __restrict__ dst, uint32_t fir
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       const U32x4 r = philox4x32_10_hoisted<10>(static_cast<uint64_t>(kPhiloxM0) * (g + k * stride), sc, L.rk);
-      o[k] = fill_group(DT, r, L.p);
+      o[k] = fill_group(DT, r, prm);
     }
 #pragma unroll
     for (int k = 0; k < U; ++k) {
@@ -428,24 +438,29 @@ __device__ __forceinline__ void fill_run(uint8_t* __restrict__ dst, uint32_t fir
   }
   for (; g < end; g += stride) {
     const U32x4 r = philox4x32_10_hoisted<10>(static_cast<uint64_t>(kPhiloxM0) * g, sc, L.rk);
-    st_cs_v4(p, fill_group(DT, r, L.p));
+    st_cs_v4(p, fill_group(DT, r, prm));
     p += pstep;
   }
 }
 
-template <uint32_t DT, int CAP, int THREADS, int U>
+constexpr int kFillUniThreads = 256;
+template <uint32_t DT, int CAP, int THREADS, int U, bool PLAIN>
 __global__ void __launch_bounds__(THREADS, 4) fill_uniform_kernel(const __grid_constant__ FillTab<CAP> tab, const __grid_constant__ FillUniform L) {
-  // the epoch is read BEFORE the dependents are released: when a successor starts, every CTA
-  // of this grid has its epoch (graphs advance the device epoch in their last node)
+  // Release the dependents first: the instruction waits for the thread's outstanding loads, and
+  // the epoch load behind it would delay every successor by its latency (7.2 us instead of 6.5 us
+  // per 38.5 MB launch, scripts/fill2_bench.cu modes 3 / 17).  Reading the epoch afterwards is
+  // safe: the device epoch is only written by a plain kernel behind the chain (the last node of
+  // a graph, tb200_graph_end), which starts after the chain's last fill completed, and that
+  // implies -- by the griddepcontrol.wait below -- that every fill of the chain completed.
+  pdl_launch_dependents();
   uint64_t epoch = L.epoch;
   if (L.dev_epoch != nullptr) epoch += *L.dev_epoch;
-  pdl_launch_dependents();
   if (L.ctas_per_job != 0) {
     const uint32_t j = blockIdx.x / L.ctas_per_job;
     const uint32_t part = blockIdx.x - j * L.ctas_per_job;
     const uint64_t stream = tab.stream[j] + epoch;
     const PhiloxStreamConst sc = philox_stream_const(static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32), L.rk);
-    fill_run<DT, U>(reinterpret_cast<uint8_t*>(tab.dst[j]), part * THREADS + threadIdx.x, L.ctas_per_job * THREADS,
+    fill_run<DT, U, PLAIN>(reinterpret_cast<uint8_t*>(tab.dst[j]), part * THREADS + threadIdx.x, L.ctas_per_job * THREADS,
                     L.groups_per_job, sc, L);
   } else {
     uint64_t lo = (L.total_groups * blockIdx.x) / gridDim.x;
@@ -458,7 +473,7 @@ __global__ void __launch_bounds__(THREADS, 4) fill_uniform_kernel(const __grid_c
       const uint32_t n = left < room ? static_cast<uint32_t>(left) : room;
       const uint64_t stream = tab.stream[j] + epoch;
       const PhiloxStreamConst sc = philox_stream_const(static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32), L.rk);
-      fill_run<DT, U>(reinterpret_cast<uint8_t*>(tab.dst[j]), g0 + threadIdx.x, THREADS, g0 + n, sc, L);
+      fill_run<DT, U, PLAIN>(reinterpret_cast<uint8_t*>(tab.dst[j]), g0 + threadIdx.x, THREADS, g0 + n, sc, L);
       lo += n;
       ++j;
       g0 = 0;
@@ -468,8 +483,10 @@ __global__ void __launch_bounds__(THREADS, 4) fill_uniform_kernel(const __grid_c
 }
 
 void plan_fill_uniform(FillUniform* u, int sm_count) {
-  constexpr uint32_t kThreads = 256, kU = 2;
-  const uint32_t target = static_cast<uint32_t>(sm_count) * 4u;  // CTAs of one grid; 8 fit per SM, the rest is the successor's
+  constexpr uint32_t kThreads = kFillUniThreads, kU = 2;
+  // CTAs of one grid: 4 per SM, half of what fits -- the other slots take the CTAs of the next
+  // launch, whose start-up then hides behind this grid's arithmetic
+  const uint32_t target = static_cast<uint32_t>(sm_count) * 4u;
   u->ctas_per_job = 0;
   const uint32_t cpj = u->njobs <= target ? target / u->njobs : 0;
   // interleaved rows when the split fills the chip evenly and every part has whole iterations
@@ -495,7 +512,7 @@ static cudaError_t launch_fill_uniform_t(const FillUniform& u, const tb200_fill_
   for (uint32_t i = u.njobs; i < static_cast<uint32_t>(CAP); ++i) tab.dst[i] = tab.stream[i] = 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(u.grid);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(kFillUniThreads);
   cfg.stream = s;
   cudaLaunchAttribute at[1];
   if (pdl) {
@@ -504,7 +521,10 @@ static cudaError_t launch_fill_uniform_t(const FillUniform& u, const tb200_fill_
     cfg.attrs = at;
     cfg.numAttrs = 1;
   }
-  return cudaLaunchKernelEx(&cfg, fill_uniform_kernel<DT, CAP, 256, 2>, tab, u);
+  const bool is_float = DT == kF32 || DT == kF16 || DT == kBF16 || DT == kF64;
+  const bool plain = DT == kBool || (is_float ? u.p.unit != 0 : u.p.irange == 0);
+  if (plain) return cudaLaunchKernelEx(&cfg, fill_uniform_kernel<DT, CAP, kFillUniThreads, 2, true>, tab, u);
+  return cudaLaunchKernelEx(&cfg, fill_uniform_kernel<DT, CAP, kFillUniThreads, 2, false>, tab, u);
 }
 
 cudaError_t launch_fill_uniform(const FillUniform& u, const tb200_fill_job* host_jobs, uint32_t dtype, cudaStream_t s, bool pdl) {
@@ -1582,6 +1602,123 @@ __global__ void __launch_bounds__(256) topk_kernel(const tb200_topk_job* __restr
 cudaError_t launch_topk(const tb200_topk_job* jobs, uint32_t njobs, uint32_t k, tb200_topk_entry* out, cudaStream_t s) {
   if (njobs == 0) return cudaSuccess;
   topk_kernel<<<njobs, 256, 0, s>>>(jobs, k, out);
+  return cudaGetLastError();
+}
+
+// =============================================================================
+// BYTES decode: the <u32 length><payload> chain of serialize_byte_tensor, on the device
+// =============================================================================
+// Reference: deserialize_bytes_tensor (PY/utils/__init__.py:264-291) and the BYTES branch of
+// cuda_shared_memory.get_contents_as_numpy (:306-323) walk the chain on the host after copying
+// the whole region.  The walk is a chain of dependent loads -- the offset of element i+1 is
+// known only after the length of element i -- so one CTA stages the stream through shared
+// memory in 32 KiB windows (coalesced 16-byte loads by all threads) and one thread follows the
+// chain inside the window (a shared-memory load per element instead of an L2 round trip);
+// strings longer than the window are skipped over without being staged.  The walk records
+// where every payload starts in the source and the prefix sums of the payload lengths; a
+// second, fully parallel kernel packs the payloads back to back.  Only offsets[count + 1] and
+// the packed payload bytes have to cross PCIe, not the region.
+constexpr uint32_t kBytesWindow = 32768;
+
+__global__ void __launch_bounds__(256) bytes_scan_kernel(const uint8_t* __restrict__ src, uint64_t src_bytes, uint64_t count,
+                                                          uint64_t* __restrict__ src_off, uint32_t* __restrict__ offsets,
+                                                          uint64_t* __restrict__ status) {
+  __shared__ __align__(16) uint8_t win[kBytesWindow + 16];
+  __shared__ uint64_t s_pos, s_done, s_total;
+  __shared__ uint32_t s_err;
+  if (threadIdx.x == 0) {
+    s_pos = 0;
+    s_done = 0;
+    s_total = 0;
+    s_err = 0;
+    offsets[0] = 0;
+  }
+  __syncthreads();
+  const uintptr_t base_addr = reinterpret_cast<uintptr_t>(src);
+  while (true) {
+    const uint64_t pos = s_pos, done = s_done;
+    if (done >= count || s_err != 0 || pos >= src_bytes) break;
+    // window: starts at the 16-byte aligned address at or below src + pos (for pos = 0 and an
+    // unaligned src that is up to 15 bytes before the tensor, inside the same 16-byte cell of
+    // the allocation)
+    const uint64_t lead = (base_addr + pos) & 15;
+    const int64_t w0 = static_cast<int64_t>(pos) - static_cast<int64_t>(lead);  // stream offset of the window's first byte
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>((base_addr + pos) & ~static_cast<uintptr_t>(15));
+    const uint64_t avail = src_bytes - pos + lead;
+    const uint32_t wbytes = static_cast<uint32_t>(avail < kBytesWindow ? avail : kBytesWindow);
+    for (uint32_t i = threadIdx.x * 16; i < wbytes; i += blockDim.x * 16) {
+      if (i + 16 <= wbytes) {
+        *reinterpret_cast<uint4*>(win + i) = ld_nc_v4(wsrc + i);
+      } else {
+        for (uint32_t b = i; b < wbytes; ++b) win[b] = wsrc[b];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t p = pos, n = done, total = s_total;
+      const int64_t wend = w0 + wbytes;  // stream offset one past the window
+      while (n < count) {
+        if (p + 4 > src_bytes) {
+          s_err = 1;  // truncated: no room for a length word
+          break;
+        }
+        if (static_cast<int64_t>(p + 4) > wend) break;  // header not (fully) staged: next window
+        const uint32_t o = static_cast<uint32_t>(static_cast<int64_t>(p) - w0);
+        const uint32_t len = static_cast<uint32_t>(win[o]) | (static_cast<uint32_t>(win[o + 1]) << 8) |
+                             (static_cast<uint32_t>(win[o + 2]) << 16) | (static_cast<uint32_t>(win[o + 3]) << 24);
+        if (len > src_bytes - (p + 4)) {
+          s_err = 2;  // payload runs past the end of the source
+          break;
+        }
+        if (total + len > 0xFFFFFFFFull) {
+          s_err = 3;  // offsets are 32-bit, as in numpy's per-element view of the packed buffer
+          break;
+        }
+        src_off[n] = p + 4;
+        total += len;
+        ++n;
+        offsets[n] = static_cast<uint32_t>(total);
+        p += 4ull + len;
+      }
+      s_pos = p;
+      s_done = n;
+      s_total = total;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    status[0] = s_done;
+    status[1] = s_pos;
+    status[2] = s_total;
+    status[3] = s_err != 0 ? s_err : (s_done < count ? 1u : 0u);
+    __threadfence_system();
+  }
+}
+
+// one warp per element (grid-stride): payload bytes to packed + offsets[i]
+__global__ void __launch_bounds__(256) bytes_gather_kernel(const uint8_t* __restrict__ src, const uint64_t* __restrict__ src_off,
+                                                            const uint32_t* __restrict__ offsets, const uint64_t* __restrict__ status,
+                                                            uint8_t* __restrict__ packed, uint64_t packed_capacity) {
+  const uint64_t n = status[0];
+  if (status[3] != 0 || status[2] > packed_capacity) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+    const uint8_t* from = src + src_off[i];
+    uint8_t* to = packed + offsets[i];
+    const uint32_t len = offsets[i + 1] - offsets[i];
+    for (uint32_t b = lane; b < len; b += 32) to[b] = from[b];
+  }
+}
+
+cudaError_t launch_bytes_decode(const uint8_t* src, uint64_t src_bytes, uint64_t count, uint64_t* src_off, uint32_t* offsets,
+                                uint8_t* packed, uint64_t packed_capacity, uint64_t* status, int sm_count, cudaStream_t s) {
+  bytes_scan_kernel<<<1, 256, 0, s>>>(src, src_bytes, count, src_off, offsets, status);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || count == 0) return e;
+  uint64_t grid = (count + 7) / 8;
+  if (grid > static_cast<uint64_t>(sm_count) * 8) grid = static_cast<uint64_t>(sm_count) * 8;
+  bytes_gather_kernel<<<static_cast<uint32_t>(grid), 256, 0, s>>>(src, src_off, offsets, status, packed, packed_capacity);
   return cudaGetLastError();
 }
 

@@ -147,6 +147,10 @@ cudaError_t launch_deflate(const uint8_t* src, uint64_t nbytes, uint32_t format,
 
 cudaError_t launch_topk(const tb200_topk_job* jobs, uint32_t njobs, uint32_t k, tb200_topk_entry* out, cudaStream_t s);
 
+// serialised BYTES tensor -> offsets[count + 1] + packed payloads; src_off: device scratch, count entries
+cudaError_t launch_bytes_decode(const uint8_t* src, uint64_t src_bytes, uint64_t count, uint64_t* src_off, uint32_t* offsets,
+                                uint8_t* packed, uint64_t packed_capacity, uint64_t* status, int sm_count, cudaStream_t s);
+
 cudaError_t launch_epoch_bump(uint64_t* dev_epoch, uint64_t delta, cudaStream_t s);
 
 }  // namespace tb200

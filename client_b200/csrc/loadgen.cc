@@ -184,6 +184,9 @@ struct tb200_loadgen {
   uint64_t seed = 0;
   bool regenerate = false;
   uint64_t device_window_ns = 0;
+  uint32_t pipeline_depth = 1;        // device passes in flight (tb200_step_submit / tb200_step_wait)
+  tb200_check_result* own_results = nullptr;  // depth > 1: one result block per pass in flight (mapped host)
+  void* own_results_host = nullptr;
   std::vector<tb200_check_job> check_jobs;
   int check_per_slot = 0;
   tb200_check_result* results = nullptr;
@@ -325,6 +328,7 @@ int grpc_build(tb200_loadgen* lg, Conn& c) {
     c.next_stream += 2;
     c.stream_window = c.peer_stream_window;
     c.stream_open = lg->grpc_stream;
+    c.stream_recv_consumed = 0;  // receive credit is per stream
   }
   c.got_data = false;
   c.t_first = 0;
@@ -629,6 +633,9 @@ void grpc_readable(tb200_loadgen* lg, Transport* t, Conn& c, uint32_t index) {
           break;
         }
         if (f.stream == c.cur_stream && c.in_flight) {
+          // unary calls return stream-level credit too: a response larger than the stream window
+          // we advertise (h2::kOurStreamWindow) would otherwise stall the server for good
+          if (!(f.flags & h2::kEndStream)) c.stream_recv_consumed += f.length;
           if (f.length >= 5) c.got_data = true;
           if (f.flags & h2::kEndStream) {
             finished = true;
@@ -775,8 +782,118 @@ void release_slots(tb200_loadgen* lg, const std::vector<int>& slots) {
   }
 }
 
+// The issue loop with several passes in flight (cfg.pipeline_depth > 1).  A pass = the slots whose
+// responses came back: their outputs are validated and their next inputs generated
+// (tb200_step_submit: fill on the context's stream, validation on its side stream, events behind
+// both).  The thread forms pass i+1 -- collects returned slots, builds the job lists, copies the
+// tables, launches -- while the device runs pass i, and retires passes in order (tb200_step_wait,
+// read the results, hand the slots back to their transport threads).  Passes in flight own
+// disjoint slots, so consecutive fills overlap on the device as well (fill_uniform_kernel's
+// programmatic dependent launch).  This is where the reference's clients hand every request
+// through a Python future / queue (grpc/_client.py:1574-1741, grpc/_infer_stream.py:108-168).
+void device_main_pipelined(tb200_loadgen* lg) {
+  struct Pass {
+    std::vector<int> batch;
+    std::vector<tb200_check_job> checks;
+    tb200_check_result* results = nullptr;       // device address of the pass's result block
+    const tb200_check_result* results_host = nullptr;  // the same block as the host reads it
+    uint64_t ticket = 0;
+    int rc = TB200_OK;
+  };
+  const uint32_t depth = lg->pipeline_depth;
+  const size_t max_checks = static_cast<size_t>(lg->concurrency) * static_cast<size_t>(std::max(lg->check_per_slot, 0));
+  std::deque<Pass> inflight;
+  std::vector<Pass> pool(depth);  // reused vectors, one per ring position
+  uint64_t seq = 0;
+  std::vector<tb200_fill_job> fills;
+  const bool do_check = lg->check_per_slot > 0;
+  const bool do_fill = lg->regenerate && lg->fill_per_slot > 0;
+
+  auto retire = [&](Pass& p) {
+    uint64_t bad = 0, mism = 0;
+    int rc = p.rc;
+    if (rc == TB200_OK) rc = tb200_step_wait(lg->ctx, p.ticket);
+    if (rc != TB200_OK) {
+      std::lock_guard<std::mutex> lk(lg->dev_mu);
+      if (lg->error.empty()) lg->error = tb200_last_error();
+    } else {
+      for (size_t k = 0; k < p.checks.size(); ++k) {
+        if (p.checks[k].kind == TB200_CHECK_TOP1) bad += p.results_host[k].mismatches;
+        else if (p.checks[k].kind != TB200_CHECK_SUM) mism += p.results_host[k].mismatches;
+      }
+    }
+    {
+      std::lock_guard<std::mutex> lk(lg->dev_mu);
+      lg->device_batches += 1;
+      lg->device_slots += p.batch.size();
+      lg->nonfinite += bad;
+      lg->mismatches += mism;
+    }
+    release_slots(lg, p.batch);
+  };
+
+  std::vector<int> batch;
+  while (!lg->stop.load(std::memory_order_relaxed)) {
+    batch.clear();
+    if (inflight.empty()) {
+      const int first = lg->returned.pop(50);
+      if (first < 0) continue;
+      batch.push_back(first);
+    }
+    lg->returned.drain(batch);
+    if (inflight.empty() && lg->device_window_ns != 0) {  // accumulation window, see device_main
+      const uint64_t t0 = now_ns();
+      while (batch.size() < static_cast<size_t>(lg->concurrency)) {
+        const uint64_t el = now_ns() - t0;
+        if (el >= lg->device_window_ns) break;
+        const int s = lg->returned.pop_ns(lg->device_window_ns - el);
+        if (s < 0) break;
+        batch.push_back(s);
+        lg->returned.drain(batch);
+      }
+    }
+    if (!batch.empty()) {
+      Pass p = std::move(pool[seq % depth]);
+      p.batch.swap(batch);
+      p.checks.clear();
+      fills.clear();
+      if (do_check) {
+        for (int s : p.batch) {
+          for (int k = 0; k < lg->check_per_slot; ++k) p.checks.push_back(lg->check_jobs[s * lg->check_per_slot + k]);
+        }
+      }
+      if (do_fill) {
+        for (int s : p.batch) {
+          for (int k = 0; k < lg->fill_per_slot; ++k) fills.push_back(lg->fill_jobs[s * lg->fill_per_slot + k]);
+        }
+        lg->epoch += 1ull << 20;  // fresh Philox streams for every generation
+      }
+      p.results = lg->own_results + (seq % depth) * max_checks;
+      p.results_host = static_cast<const tb200_check_result*>(lg->own_results_host) + (seq % depth) * max_checks;
+      p.rc = tb200_step_submit(lg->ctx, fills.data(), static_cast<int>(fills.size()), lg->seed, lg->epoch, p.checks.data(),
+                               static_cast<int>(p.checks.size()), p.results, &p.ticket);
+      ++seq;
+      inflight.push_back(std::move(p));
+      if (inflight.size() < depth) continue;  // room for another pass: look for returned slots first
+    }
+    if (!inflight.empty()) {  // nothing new came back, or the pipeline is full: retire the oldest pass
+      retire(inflight.front());
+      pool[(seq - inflight.size()) % depth] = std::move(inflight.front());
+      inflight.pop_front();
+    }
+  }
+  while (!inflight.empty()) {
+    retire(inflight.front());
+    inflight.pop_front();
+  }
+}
+
 // validate + regenerate the slots that came back, one launch each, then release them
 void device_main(tb200_loadgen* lg) {
+  if (lg->pipeline_depth > 1 && lg->ctx != nullptr) {
+    device_main_pipelined(lg);
+    return;
+  }
   std::vector<int> batch;
   std::vector<tb200_fill_job> fills;
   std::vector<tb200_check_job> checks;
@@ -925,6 +1042,20 @@ int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out) {
     lg->tail_sizes.assign(cfg->tail_sizes, cfg->tail_sizes + cfg->concurrency);
   }
   lg->passthrough = lg->ctx == nullptr || (lg->check_per_slot == 0 && !(lg->regenerate && lg->fill_per_slot > 0));
+  lg->pipeline_depth = cfg->pipeline_depth == 0 ? 1u : std::min<uint32_t>(cfg->pipeline_depth, TB200_STEP_DEPTH / 2);
+  if (getenv("TB200_LOADGEN_DEVICE_MODE") != nullptr) lg->pipeline_depth = 1;  // the experiment modes are synchronous
+  if (lg->pipeline_depth > 1 && !lg->passthrough) {
+    // every pass in flight writes its own block of results
+    const uint64_t per_pass = static_cast<uint64_t>(cfg->concurrency) * static_cast<uint64_t>(std::max(lg->check_per_slot, 1));
+    void* h = nullptr;
+    void* d = nullptr;
+    if (tb200_host_alloc(per_pass * lg->pipeline_depth * sizeof(tb200_check_result), &h, &d) != TB200_OK) {
+      delete lg;
+      return lg_fail(TB200_ERR_CUDA, tb200_last_error());
+    }
+    lg->own_results_host = h;
+    lg->own_results = static_cast<tb200_check_result*>(d);
+  }
   *out = lg;
   return TB200_OK;
 }
@@ -1022,6 +1153,27 @@ int tb200_loadgen_window(tb200_loadgen* lg, double seconds, tb200_loadgen_stats*
   return TB200_OK;
 }
 
+int tb200_loadgen_wait_count(tb200_loadgen* lg, uint64_t count, double timeout_seconds, uint64_t* reached) {
+  if (lg == nullptr || !lg->started) return lg_fail(TB200_ERR_STATE, "load generator not running");
+  const uint64_t deadline = now_ns() + static_cast<uint64_t>(std::max(0.0, timeout_seconds) * 1e9);
+  uint64_t total = 0;
+  for (;;) {
+    total = 0;
+    for (auto& tr : lg->transports) {
+      std::lock_guard<std::mutex> lk(tr->stats.mu);
+      total += tr->stats.completed + tr->stats.failed;
+    }
+    if (total >= count || now_ns() >= deadline) break;
+    {
+      std::lock_guard<std::mutex> lk(lg->dev_mu);
+      if (!lg->error.empty()) break;
+    }
+    std::this_thread::sleep_for(std::chrono::microseconds(100));
+  }
+  if (reached != nullptr) *reached = total;
+  return TB200_OK;
+}
+
 int tb200_loadgen_stop(tb200_loadgen* lg) {
   if (lg == nullptr) return TB200_OK;
   lg->stop.store(true);
@@ -1042,6 +1194,7 @@ int tb200_loadgen_stop(tb200_loadgen* lg) {
 int tb200_loadgen_destroy(tb200_loadgen* lg) {
   if (lg == nullptr) return TB200_OK;
   tb200_loadgen_stop(lg);
+  if (lg->own_results_host != nullptr) tb200_host_free(lg->own_results_host);
   delete lg;
   return TB200_OK;
 }

@@ -149,7 +149,7 @@ class CopyPool {
 };
 
 constexpr size_t kStageBytes = 8u << 20;  // one pinned staging buffer
-constexpr size_t kDirectBytes = 64u << 10; // below this the driver's own staging is faster
+static size_t kDirectBytes = 64u << 10;   // below this the driver's own staging is faster ("h2d_direct_kb" knob)
 constexpr int kStageCount = 4;            // in flight per context
 constexpr size_t kJobSlotBytes = 64u << 10;
 constexpr int kJobSlots = 32;
@@ -216,6 +216,9 @@ struct tb200_ctx {
   void* deflate_scratch = nullptr;
   void* deflate_meta = nullptr;
   uint64_t deflate_chunks_cap = 0;
+  // BYTES decode scratch: where each payload starts in the source
+  uint64_t* bytes_src_off = nullptr;
+  uint64_t bytes_src_off_cap = 0;
   // capture state
   tb200_graph* capture = nullptr;
   uint64_t capture_launches0 = 0;
@@ -225,7 +228,7 @@ struct tb200_ctx {
   uint64_t stream_seq[2] = {0, 0};
   uint64_t pdl_mark[2] = {~0ull, ~0ull};
   struct PdlEntry {
-    uint64_t lo, hi;
+    std::vector<std::pair<uint64_t, uint64_t>> spans;  // [lo, hi) written, sorted and merged
     uint32_t grid;
   };
   std::vector<PdlEntry> pdl_chain[2];  // most recent last; the launches of the current overlap chain
@@ -757,6 +760,37 @@ int tb200_memcpy_d2h_async(tb200_ctx* ctx, void* dst, const void* src, uint64_t 
 // ---------------------------------------------------------------------------
 // fill
 // ---------------------------------------------------------------------------
+// the byte ranges a launch writes, sorted and merged (the 64 slots of one region set: one span)
+static void written_spans(const tb200_fill_job* jobs, int n, std::vector<std::pair<uint64_t, uint64_t>>* out) {
+  out->clear();
+  out->reserve(static_cast<size_t>(n));
+  bool sorted = true;
+  for (int i = 0; i < n; ++i) {
+    if (jobs[i].nbytes == 0) continue;
+    if (!out->empty() && jobs[i].dst < out->back().first) sorted = false;
+    out->emplace_back(jobs[i].dst, jobs[i].dst + jobs[i].nbytes);
+  }
+  if (!sorted) std::sort(out->begin(), out->end());
+  size_t w = 0;
+  for (size_t i = 0; i < out->size(); ++i) {
+    if (w != 0 && (*out)[i].first <= (*out)[w - 1].second) {
+      (*out)[w - 1].second = std::max((*out)[w - 1].second, (*out)[i].second);
+    } else {
+      (*out)[w++] = (*out)[i];
+    }
+  }
+  out->resize(w);
+}
+static bool spans_overlap(const std::vector<std::pair<uint64_t, uint64_t>>& a, const std::vector<std::pair<uint64_t, uint64_t>>& b) {
+  size_t i = 0, j = 0;
+  while (i < a.size() && j < b.size()) {
+    if (a[i].second <= b[j].first) ++i;
+    else if (b[j].second <= a[i].first) ++j;
+    else return true;
+  }
+  return false;
+}
+
 static bool g_fill_uniform = true;  // homogeneous launches take fill_uniform_kernel ("fill_uniform" knob)
 static bool g_fill_pdl = true;      // ... and overlap with the previous one when they write disjoint memory ("fill_pdl" knob)
 
@@ -840,11 +874,8 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
       U.njobs = static_cast<uint32_t>(n);
       U.groups_per_job = static_cast<uint32_t>(prefix[1]);
       plan_fill_uniform(&U, ctx->sm_count);
-      uint64_t lo = ~0ull, hi = 0;
-      for (int i = 0; i < n; ++i) {
-        lo = std::min(lo, jobs[base + i].dst);
-        hi = std::max(hi, jobs[base + i].dst + jobs[base + i].nbytes);
-      }
+      tb200_ctx::PdlEntry mine;
+      written_spans(jobs + base, n, &mine.spans);
       // overlap with the previous launch only if that was a homogeneous fill on this stream
       // writing other memory (same memory: the later launch must win)
       // Which earlier launches of the chain can still be running when this one starts?  A
@@ -862,7 +893,7 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
         for (size_t k = chain.size(); k-- > 0;) {
           if (newer + 1 > capacity) break;  // this one and everything older completed
           ++live;
-          if (!(hi <= chain[k].lo || lo >= chain[k].hi)) pdl = false;  // same memory: the later launch must win
+          if (spans_overlap(mine.spans, chain[k].spans)) pdl = false;  // same memory: the later launch must win
           newer += chain[k].grid;
         }
         if (live == chain.size() && chain.size() >= 16) pdl = false;  // bounded history
@@ -872,7 +903,8 @@ static int fill_impl(tb200_ctx* ctx, const tb200_fill_job* jobs, int njobs, uint
       TB200_CUDA(launch_fill_uniform(U, jobs + base, f.dtype, ctx->cur, pdl));
       count_launch(ctx);
       ctx->pdl_mark[si] = stream_seq(ctx);
-      chain.push_back({lo, hi, U.grid});
+      mine.grid = U.grid;
+      chain.push_back(std::move(mine));
       if (launch_bump != 0) {  // eager fill_epoch: advance the device epoch behind the fill
         TB200_CUDA(launch_epoch_bump(ctx->dev_epoch, launch_bump, ctx->cur));
         count_launch(ctx);
@@ -1235,6 +1267,30 @@ int tb200_topk_async(tb200_ctx* ctx, const tb200_topk_job* jobs, int njobs, int 
   return TB200_OK;
 }
 
+int tb200_bytes_decode_async(tb200_ctx* ctx, const void* src, uint64_t src_bytes, uint64_t count, uint32_t* offsets, void* packed,
+                             uint64_t packed_capacity, uint64_t* status) {
+  if (ctx == nullptr || offsets == nullptr || status == nullptr || (src_bytes != 0 && src == nullptr)) return fail(TB200_ERR_INVALID, "bad argument");
+  if (count != 0 && packed == nullptr && packed_capacity != 0) return fail(TB200_ERR_INVALID, "packed is NULL");
+  if (ctx->capture != nullptr) return fail(TB200_ERR_STATE, "BYTES decode cannot be captured (it sizes its scratch per call)");
+  DeviceGuard g(ctx->device);
+  if (count > ctx->bytes_src_off_cap) {
+    TB200_CUDA(cudaStreamSynchronize(ctx->cur));
+    if (ctx->bytes_src_off != nullptr) cudaFree(ctx->bytes_src_off);
+    ctx->bytes_src_off = nullptr;
+    const uint64_t cap = std::max<uint64_t>(count, 4096);
+    TB200_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->bytes_src_off), cap * sizeof(uint64_t)));
+    ctx->bytes_src_off_cap = cap;
+  }
+  if (ctx->bytes_src_off == nullptr) {
+    TB200_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->bytes_src_off), 4096 * sizeof(uint64_t)));
+    ctx->bytes_src_off_cap = 4096;
+  }
+  TB200_CUDA(launch_bytes_decode(static_cast<const uint8_t*>(src), src_bytes, count, ctx->bytes_src_off, offsets, static_cast<uint8_t*>(packed),
+                                 packed_capacity, status, ctx->sm_count, ctx->cur));
+  count_launch(ctx, count != 0 ? 2 : 1);
+  return TB200_OK;
+}
+
 // ---------------------------------------------------------------------------
 // deflate
 // ---------------------------------------------------------------------------
@@ -1451,6 +1507,10 @@ int tb200_tune(const char* key, int value) {
   if (key != nullptr && strcmp(key, "fill_variant") == 0) {
     set_fill_variant(value);
     g_fill_uniform = value == 0;  // the experiment matrix addresses the general kernels
+    return TB200_OK;
+  }
+  if (key != nullptr && strcmp(key, "h2d_direct_kb") == 0) {
+    kDirectBytes = static_cast<size_t>(value) << 10;
     return TB200_OK;
   }
   if (key != nullptr && strcmp(key, "fill_uniform") == 0) {

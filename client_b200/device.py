@@ -308,6 +308,31 @@ class DeviceOps:
         self.sync()
         return result_dict(res.array(np.uint8, ctypes.sizeof(CheckResult)).tobytes())
 
+    def bytes_decode(self, src_ptr, src_bytes, count):
+        """Blocking on-device decode of a serialised BYTES tensor (tb200_bytes_decode_async):
+        ``count`` elements of ``<u32 length><payload>`` starting at device address ``src_ptr``.
+        Returns (offsets uint32[count + 1], packed payload bytes, consumed source bytes); only the
+        offsets and the payloads cross PCIe.  Raises on a truncated or inconsistent stream."""
+        count, src_bytes = int(count), int(src_bytes)
+        need = 64 + (count + 1) * 4 + src_bytes  # status | offsets | packed (payloads <= source bytes)
+        buf = getattr(self, "_bytes_buf", None)
+        if buf is None or buf.nbytes < need:
+            buf = self._bytes_buf = HostBuffer(max(need, 1 << 16))
+        off_at = 64
+        packed_at = (off_at + (count + 1) * 4 + 15) & ~15
+        if buf.nbytes < packed_at + src_bytes:
+            buf = self._bytes_buf = HostBuffer(packed_at + src_bytes)
+        _native.check(self._lib.tb200_bytes_decode_async(self._ctx.handle, int(src_ptr), src_bytes, count, buf.device_ptr + off_at,
+                                                        buf.device_ptr + packed_at, src_bytes, buf.device_ptr))
+        self.sync()
+        status = buf.array(np.uint64, 4)
+        if int(status[3]) != 0:
+            raise ValueError("serialised BYTES tensor is %s after %d of %d elements" % (
+                {1: "truncated", 2: "inconsistent (a length runs past the buffer)", 3: "larger than 4 GiB"}.get(int(status[3]), "invalid"), int(status[0]), count))
+        offsets = buf.array(np.uint32, count + 1, offset=off_at).copy()
+        packed = buf.array(np.uint8, int(status[2]), offset=packed_at).tobytes()
+        return offsets, packed, int(status[1])
+
     def topk(self, vectors, k):
         """Blocking top-k of device vectors (tb200_topk_async).
 

@@ -43,10 +43,10 @@ class NativeLoadGenerator:
     """One tb200_loadgen instance over a SlotSet (cuda shm or wire mode)."""
 
     def __init__(self, url, model_name, model_version, slotset, concurrency, regenerate=True, validate=True,
-                 device_window_us=0, protocol="http", request_parameters=None):
+                 device_window_us=0, protocol="http", request_parameters=None, pipeline_depth=3):
         """``protocol``: "http" (HTTP/1.1), "grpc" (unary ModelInfer) or "grpc-stream" (one
         ModelStreamInfer stream per connection; windows then report ``ttft_p50_us`` and
-        ``responses``)."""
+        ``responses``).  ``pipeline_depth``: device passes in flight (1 = one at a time)."""
         self._lib = _native.load()
         self.protocol = protocol
         self.request_parameters = request_parameters
@@ -122,6 +122,7 @@ class NativeLoadGenerator:
         cfg.lookahead = ss.lookahead
         cfg.tail_stride = ss.wire_stride
         cfg.protocol = {"http": 0, "grpc": 1, "grpc-stream": 2}[protocol]
+        cfg.pipeline_depth = int(pipeline_depth)
         self._keep.append(cfg)
         h = ctypes.c_void_p()
         _native.check(self._lib.tb200_loadgen_create(ctypes.byref(cfg), ctypes.byref(h)))
@@ -167,7 +168,7 @@ class NativeLoadGenerator:
         _native.check(self._lib.tb200_loadgen_window(self._h, float(seconds), ctypes.byref(st)))
         n = st.completed_request_count
         return {
-            "count": int(n), "failed": int(st.failed_request_count),
+            "count": int(n), "failed": int(st.failed_request_count), "seconds": st.window_seconds,
             "throughput": n / st.window_seconds if st.window_seconds > 0 else 0.0,
             "avg_us": st.cumulative_total_request_time_ns / n / 1e3 if n else 0.0,
             "send_us": st.cumulative_send_time_ns / n / 1e3 if n else 0.0,
@@ -180,6 +181,12 @@ class NativeLoadGenerator:
                 "ttft_p50_us": st.first_response_p50_ns / 1e3, "ttft_p99_us": st.first_response_p99_ns / 1e3}
                if self.protocol == "grpc-stream" else {}),
         }
+
+    def wait_count(self, count, timeout=60.0):
+        """Block until ``count`` requests finished since the last window() (count windows)."""
+        got = ctypes.c_uint64(0)
+        _native.check(self._lib.tb200_loadgen_wait_count(self._h, int(count), float(timeout), ctypes.byref(got)))
+        return int(got.value)
 
     def stop(self):
         if getattr(self, "_h", None):

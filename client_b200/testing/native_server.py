@@ -58,7 +58,12 @@ def main(argv=None):
     ap.add_argument("--port", type=int, default=8000)
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--grpc-port", type=int, default=None, help="also serve gRPC on this port (0 = pick one)")
+    ap.add_argument("--pin-cpus", action="store_true", help="pin the server's threads to its GPU's share of the local NUMA node (perf/topology.py)")
     args = ap.parse_args(argv)
+    if args.pin_cpus:
+        from ..perf.topology import pin_for
+
+        pin_for(args.device, "server")  # before the server's threads exist
     srv = NativeServer(args.host, args.port, args.device, args.grpc_port)
     print("native mock server listening on %s%s" % (srv.url, "" if srv.grpc_port is None else " grpc=%s:%d" % (srv.host, srv.grpc_port)), flush=True)
     stop = []

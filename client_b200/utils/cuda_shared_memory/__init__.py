@@ -41,6 +41,19 @@ def _ctx(device_id):
     return _native.default_context(device_id)
 
 
+_device_ops = {}
+
+
+def _ops(device_id):
+    """One DeviceOps per device (it caches its pinned scratch buffers)."""
+    ops = _device_ops.get(device_id)
+    if ops is None:
+        from ...device import DeviceOps
+
+        ops = _device_ops[device_id] = DeviceOps(_ctx(device_id))
+    return ops
+
+
 def _is_device_supported(device):
     return int(device[0]) in (
         _dlpack.DLDeviceType.kDLCPU,
@@ -181,7 +194,17 @@ def get_contents_as_numpy(cuda_shm_handle, datatype, shape):
             )
         nbytes = requested
     else:
-        nbytes = cuda_shm_handle._byte_size  # element lengths are in the data
+        # BYTES: the <u32 length><payload> chain is walked on the device (tb200_bytes_decode_async);
+        # offsets + packed payloads come back instead of the whole region (reference :306-323
+        # copies the region and walks it with struct.unpack_from)
+        count = max(int(np.prod(shape)), 1)
+        try:
+            offsets, packed, _ = _ops(cuda_shm_handle._device_id).bytes_decode(
+                cuda_shm_handle._base_addr, cuda_shm_handle._byte_size, count)
+        except Exception as ex:
+            raise CudaSharedMemoryException("failed to read cuda shared memory results") from ex
+        strs = [packed[offsets[i]:offsets[i + 1]] for i in range(count)]
+        return np.reshape(np.array(strs, dtype=object), shape)
     try:
         host = _read_region(cuda_shm_handle, 0, nbytes)
     except Exception as ex:
@@ -189,19 +212,9 @@ def get_contents_as_numpy(cuda_shm_handle, datatype, shape):
             raise
         raise CudaSharedMemoryException("failed to read cuda shared memory results") from ex
 
-    if fixed:
-        if nbytes == 0:
-            return np.empty(shape, dtype=datatype)
-        return host.view(np.dtype(datatype)).reshape(shape)
-    buf = memoryview(host)
-    strs = []
-    pos = 0
-    for _ in range(max(int(np.prod(shape)), 1)):
-        n = int.from_bytes(buf[pos : pos + 4], "little")
-        pos += 4
-        strs.append(bytes(buf[pos : pos + n]))
-        pos += n
-    return np.reshape(np.array(strs, dtype=object), shape)
+    if nbytes == 0:
+        return np.empty(shape, dtype=datatype)
+    return host.view(np.dtype(datatype)).reshape(shape)
 
 
 def set_shared_memory_region_from_dlpack(cuda_shm_handle, input_values):

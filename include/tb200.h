@@ -332,6 +332,18 @@ typedef struct tb200_topk_entry {
 int tb200_topk_async(tb200_ctx* ctx, const tb200_topk_job* jobs, int njobs, int k,
                      tb200_topk_entry* out);
 
+/* Response side, BYTES tensors on the device: walk the <u32 LE length><payload> chain of a
+ * serialised BYTES tensor of `count` elements -- what deserialize_bytes_tensor
+ * (PY/utils/__init__.py:264-291) and the BYTES branch of cuda_shared_memory.get_contents_as_numpy
+ * (PY/utils/cuda_shared_memory/__init__.py:306-323) do on the host after copying the whole region --
+ * and write  offsets[count + 1]  (prefix sums of the payload lengths, offsets[0] = 0) and the
+ * payloads packed back to back into `packed`.  offsets / packed / status may be device or mapped
+ * host memory.  status[0] = elements decoded, [1] = bytes of `src` consumed, [2] = packed bytes,
+ * [3] = 0 ok | 1 truncated (fewer than `count` elements fit) | 2 a payload runs past src_bytes |
+ * 3 more than 4 GiB of payload; nothing is packed when status[3] != 0 or status[2] > packed_capacity. */
+int tb200_bytes_decode_async(tb200_ctx* ctx, const void* src, uint64_t src_bytes, uint64_t count,
+                             uint32_t* offsets, void* packed, uint64_t packed_capacity, uint64_t* status);
+
 /* ------------------------------------------------------------------------
  * Kernel 4: request-body compression.  The reference compresses a body with zlib / gzip on
  * the host (PY/http/_client.py:1440-1460, CC/http_client.cc:146-221, `Content-Encoding:

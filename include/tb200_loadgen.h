@@ -14,7 +14,9 @@
  * golden "A" of SURVEY.md 9.4).  One device thread serves all slots: slots whose responses
  * came back are validated (tb200_check_async) and regenerated (tb200_fill_async) as parallel
  * branches of ONE pass, then handed back to the transport threads in one batch -- the
- * transport threads never touch tensor bytes and no thread is woken per request.
+ * transport threads never touch tensor bytes and no thread is woken per request.  Several
+ * passes can be in flight (pipeline_depth): the issue loop the reference leaves to Python
+ * futures and queues (grpc/_client.py:1574-1741, grpc/_infer_stream.py:108-168).
  */
 #ifndef TB200_LOADGEN_H_
 #define TB200_LOADGEN_H_
@@ -74,6 +76,12 @@ typedef struct tb200_loadgen_config {
    * per slot, slot-major, one per staging image (they name different region offsets); check and
    * fill jobs per slot cover all images.  0 or 1 = one request per slot. */
   uint32_t requests_per_slot;
+  /* device passes in flight.  0 / 1: the device thread runs one pass at a time (validate the
+   * returned slots || generate their next inputs, wait, hand the slots back).  N > 1: up to N
+   * passes are in flight (tb200_step_submit / tb200_step_wait): the thread forms the next pass
+   * while the device runs the previous ones, consecutive generations overlap on the device, and
+   * slots go back to their connections in pass order.  At most TB200_STEP_DEPTH / 2. */
+  uint32_t pipeline_depth;
 } tb200_loadgen_config;
 
 typedef struct tb200_loadgen_stats {
@@ -102,6 +110,10 @@ int tb200_loadgen_create(const tb200_loadgen_config* cfg, tb200_loadgen** out);
 int tb200_loadgen_start(tb200_loadgen* lg);
 /* sleep `seconds`, then report and reset the statistics gathered meanwhile */
 int tb200_loadgen_window(tb200_loadgen* lg, double seconds, tb200_loadgen_stats* out);
+/* count-window helper (perf_analyzer's --measurement-mode count_windows): block until `count`
+ * requests finished (completed + failed) since the last tb200_loadgen_window call, or the
+ * timeout; *reached = how many had.  Follow it with tb200_loadgen_window(lg, 0, &stats). */
+int tb200_loadgen_wait_count(tb200_loadgen* lg, uint64_t count, double timeout_seconds, uint64_t* reached);
 int tb200_loadgen_stop(tb200_loadgen* lg);
 int tb200_loadgen_destroy(tb200_loadgen* lg);
 

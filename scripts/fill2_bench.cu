@@ -134,11 +134,19 @@ __device__ __forceinline__ uint32_t conv(uint32_t w) {
 // ---- KB: job-split rows.  CTA b: job b / cpj, part b % cpj; its rows part, part + cpj, ...
 // Constants hoisted once per CTA.  ADD: p0 by running 64-bit sum instead of a multiply.
 __device__ uint64_t g_dev_epoch = 7;
+__constant__ uint64_t c_epoch[4] = {7, 7, 7, 7};
 template <int DT, int THREADS, int U, int MINB, bool ADD, bool PDL, int MODE = 0>
 __global__ void __launch_bounds__(THREADS, MINB) k_jobsplit(const __grid_constant__ JobTab tab, const __grid_constant__ Launch L) {
   uint64_t epoch = L.epoch;
   if (MODE & 2) epoch = epoch - 7 + *reinterpret_cast<volatile uint64_t*>(&g_dev_epoch);
+  if (MODE & 4) epoch = epoch - 7 + c_epoch[1];
+  if (MODE & 8) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::evict_last.u64 %0, [%1];" : "=l"(v) : "l"(&g_dev_epoch));
+    epoch = epoch - 7 + v;
+  }
   if (PDL) pdl_launch_dependents();
+  if (MODE & 16) epoch = epoch - 7 + *reinterpret_cast<volatile uint64_t*>(&g_dev_epoch);  // load AFTER the signal
   const uint32_t j = blockIdx.x / L.ctas_per_job;
   const uint32_t part = blockIdx.x - j * L.ctas_per_job;
   const uint64_t stream = tab.stream[j] + epoch;
@@ -415,7 +423,7 @@ static double time_variant(const Variant& v, bool c3, int mech, int launches) {
 #define V_JS(DT, T, U, MB, ADD, PSM) \
   Variant{std::string("jobsplit " #T "t u" #U " minb" #MB) + (ADD ? " add" : " mul") + " cap" #PSM, k_jobsplit<DT, T, U, MB, ADD, false>, k_jobsplit<DT, T, U, MB, ADD, true>, T, DT, 0, PSM}
 #define V_JSM(DT, T, U, MB, PSM, MODE) \
-  Variant{std::string("jobsplit " #T "t u" #U " minb" #MB " cap" #PSM " mode" #MODE " (1=wait at end, 2=epoch load)"), k_jobsplit<DT, T, U, MB, false, false, MODE>, k_jobsplit<DT, T, U, MB, false, true, MODE>, T, DT, 0, PSM}
+  Variant{std::string("jobsplit " #T "t u" #U " minb" #MB " cap" #PSM " mode" #MODE " (1=wait at end, 2=epoch ld.volatile, 4=epoch __constant__, 8=epoch ld.nc evict_last, 16=epoch ld.volatile after the signal)"), k_jobsplit<DT, T, U, MB, false, false, MODE>, k_jobsplit<DT, T, U, MB, false, true, MODE>, T, DT, 0, PSM}
 #define V_ROWS(DT, T, U, MB, H, PSM) \
   Variant{std::string("rows     " #T "t u" #U " minb" #MB) + (H ? " hoist" : " full ") + " cap" #PSM, k_rows<DT, T, U, MB, H, false>, k_rows<DT, T, U, MB, H, true>, T, DT, 1, PSM}
 #define V_JR(DT, T, U, MB, PSM) \
@@ -428,6 +436,16 @@ static std::vector<Variant> variants() {
   v.push_back(V_JSM(DT, 256, 2, 4, 4, 1));
   v.push_back(V_JSM(DT, 256, 2, 4, 4, 2));
   v.push_back(V_JSM(DT, 256, 2, 4, 4, 3));
+  v.push_back(V_JSM(DT, 256, 2, 4, 4, 17));
+  v.push_back(V_JSM(DT, 256, 4, 4, 4, 17));
+  v.push_back(V_JSM(DT, 128, 2, 4, 4, 17));
+  v.push_back(V_JSM(DT, 128, 2, 8, 8, 17));
+  v.push_back(V_JSM(DT, 256, 2, 4, 4, 5));
+  v.push_back(V_JSM(DT, 256, 2, 4, 4, 9));
+  v.push_back(V_JSM(DT, 256, 2, 3, 3, 3));
+  v.push_back(V_JSM(DT, 256, 2, 2, 2, 3));
+  v.push_back(V_JSM(DT, 128, 2, 4, 4, 3));
+  v.push_back(V_JSM(DT, 128, 2, 6, 6, 3));
   if (getenv("FILL2_SHORT")) return v;
   v.push_back(V_JS(DT, 256, 2, 6, false, 4));
   v.push_back(V_JS(DT, 256, 2, 6, false, 6));

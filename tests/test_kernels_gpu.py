@@ -246,6 +246,33 @@ def test_fill_overlapped_launches_keep_stream_order(gpu_ops):
             assert np.array_equal(got, cref.fill(n, "FP32", seed=9, stream=100 * s + k + last[s])), (s, k)
 
 
+def test_fill_overlap_hazards_are_per_tensor_not_per_hull(gpu_ops):
+    """Interleaved slot subsets of ONE region (what consecutive device passes of the load generator
+    write) are disjoint byte ranges and may overlap; a subset that shares a slot with a launch
+    still in flight may not.  The final bytes are always those of the last writer."""
+    from client_b200.device import DeviceBuffer, make_fill_job
+
+    slots, n = 64, 602112
+    buf = DeviceBuffer(0, slots * n)
+    job = lambda k, sid: make_fill_job(buf.ptr + k * n, n, "FP32", stream_id=sid)  # noqa: E731
+    for trial in range(4):
+        even = [job(k, 1000 + k) for k in range(0, slots, 2)]
+        odd = [job(k, 2000 + k) for k in range(1, slots, 2)]
+        third = [job(k, 3000 + k) for k in (0, 5, 63)]          # shares slots with both
+        shuffled = [job(k, 4000 + k) for k in (40, 3, 22, 9)]    # unsorted job order, shares slots with `odd`
+        gpu_ops.fill(even, seed=6, epoch=trial)
+        gpu_ops.fill(odd, seed=6, epoch=trial)
+        gpu_ops.fill(third, seed=6, epoch=trial)
+        gpu_ops.fill(shuffled, seed=6, epoch=trial)
+        gpu_ops.sync()
+        owner = {k: (1000 if k % 2 == 0 else 2000) + k for k in range(slots)}
+        owner.update({k: 3000 + k for k in (0, 5, 63)})
+        owner.update({k: 4000 + k for k in (40, 3, 22, 9)})
+        for k in (0, 1, 2, 3, 5, 9, 22, 40, 62, 63):
+            got = gpu_ops.download(buf.ptr + k * n, n)
+            assert np.array_equal(got, cref.fill(n, "FP32", seed=6, stream=owner[k] + trial)), (trial, k)
+
+
 def test_graph_chain_of_fills_advances_epoch_per_fill(gpu_ops):
     """Several fill_epoch calls in one capture (overlapping nodes): call i of replay r uses
     epoch0 + (r * calls + i) * bump, exactly the sequence of the same calls issued one by one."""
@@ -800,3 +827,79 @@ def test_device_deflate_rejects_small_destination(gpu_ops):
     size = HostBuffer(64)
     with pytest.raises(_native.NativeError, match="tb200_deflate_bound"):
         gpu_ops.deflate_async(dst.ptr, 1 << 20, src.ptr, 1 << 20, size.device_ptr, "gzip")
+
+
+def _serialized(strings):
+    from client_b200.utils import serialize_byte_tensor
+
+    arr = np.array(strings, dtype=object)
+    ser = serialize_byte_tensor(arr)
+    return np.frombuffer(ser.item() if ser.size else b"", dtype=np.uint8)
+
+
+@pytest.mark.parametrize("case", ["digits", "empty_and_long", "many", "window_edges", "single"])
+def test_bytes_decode_on_device_matches_deserialize_bytes_tensor(gpu_ops, case):
+    """tb200_bytes_decode_async against utils.deserialize_bytes_tensor (reference
+    PY/utils/__init__.py:264-291) on the same serialised bytes: element boundaries (offsets) and
+    payloads, for strings shorter / longer than the 32 KiB staging window, empty strings, a header
+    straddling a window edge, an unaligned source, and trailing garbage after the last element."""
+    from client_b200.device import DeviceBuffer
+    from client_b200.utils import deserialize_bytes_tensor
+
+    rng = np.random.default_rng(11)
+    if case == "digits":
+        strings = [str(i).encode() for i in range(16)]  # the reference's own cudashm BYTES test values
+    elif case == "empty_and_long":
+        strings = [b"", b"a", b"", rng.bytes(100000), b"tail", rng.bytes(32768), b""]
+    elif case == "many":
+        strings = [rng.bytes(int(n)) for n in rng.integers(0, 40, 50000)]
+    elif case == "window_edges":
+        strings = [rng.bytes(32768 - 4 - 2), b"xy", rng.bytes(32768 - 7), b"", rng.bytes(5)]  # headers land across window ends
+    else:
+        strings = [b"only"]
+    ser = _serialized(strings)
+    for lead in (0, 3):  # source 16-byte aligned / unaligned
+        buf = DeviceBuffer(0, ser.size + 64)
+        host = np.concatenate([np.full(lead, 0xEE, np.uint8), ser, np.full(61 - lead, 0xEE, np.uint8)])
+        gpu_ops.h2d(buf.ptr, host.ctypes.data, host.size)
+        gpu_ops.sync()
+        offsets, packed, consumed = gpu_ops.bytes_decode(buf.ptr + lead, ser.size + 20, len(strings))
+        want = deserialize_bytes_tensor(ser.tobytes())
+        got = [packed[offsets[i]:offsets[i + 1]] for i in range(len(strings))]
+        assert consumed == ser.size and len(packed) == sum(len(x) for x in strings)
+        assert got == list(want) == strings
+
+
+def test_bytes_decode_reports_truncated_and_inconsistent_streams(gpu_ops):
+    from client_b200.device import DeviceBuffer
+
+    ser = _serialized([b"abc", b"defgh"])
+    buf = DeviceBuffer(0, 64)
+    gpu_ops.h2d(buf.ptr, ser.ctypes.data, ser.size)
+    gpu_ops.sync()
+    with pytest.raises(ValueError, match="truncated"):
+        gpu_ops.bytes_decode(buf.ptr, ser.size, 3)           # a third element is asked for
+    with pytest.raises(ValueError, match="inconsistent"):
+        gpu_ops.bytes_decode(buf.ptr, ser.size - 2, 2)       # the second payload runs past the buffer
+    offsets, packed, consumed = gpu_ops.bytes_decode(buf.ptr, ser.size, 0)
+    assert list(offsets) == [0] and packed == b"" and consumed == 0
+
+
+def test_get_contents_as_numpy_bytes_goes_through_the_device_decode(gpu_ops):
+    """The drop-in's BYTES read-back (reference cuda_shared_memory/__init__.py:306-323): same
+    object array as the reference flow, for the values of the reference's own unit test and for a
+    2-D shape."""
+    import client_b200.utils.cuda_shared_memory as cudashm
+    from client_b200.utils import serialize_byte_tensor
+
+    arr = np.array([str(i).encode() for i in range(16)], dtype=object).reshape(4, 4)
+    ser = serialize_byte_tensor(arr)
+    h = cudashm.create_shared_memory_region("bytes_decode_region", ser.item().__len__() + 32, 0)
+    try:
+        launches0 = gpu_ops.ctx.launch_count
+        cudashm.set_shared_memory_region(h, [ser])
+        got = cudashm.get_contents_as_numpy(h, np.object_, [4, 4])
+        assert got.dtype == np.object_ and got.shape == (4, 4) and (got == arr).all()
+        assert gpu_ops.ctx.launch_count - launches0 >= 2  # scan + gather ran on the device
+    finally:
+        cudashm.destroy_shared_memory_region(h)

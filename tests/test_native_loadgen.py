@@ -202,6 +202,27 @@ def test_grpc_stub_server_with_grpcio_client_and_native_client():
         stub.stop()
 
 
+def test_unary_grpc_response_larger_than_the_stream_window():
+    """a unary ModelInfer response of 3 MB against the 1 MiB stream window the client
+    advertises -- the client has to hand stream-level credit back (WINDOW_UPDATE on the call's
+    stream), or the server stalls on the second MiB and the slot never completes."""
+    from client_b200.grpc import service_pb2
+    from client_b200.perf.native import GrpcStubServer
+
+    resp = service_pb2.ModelInferResponse(model_name="stub", model_version="1")
+    out = resp.outputs.add()
+    out.name, out.datatype = "OUTPUT0", "UINT8"
+    out.shape.extend([3 << 20])
+    resp.raw_output_contents.append(bytes(3 << 20))
+    stub = GrpcStubServer(resp.SerializeToString())
+    try:
+        a = np.arange(16, dtype=np.int32)[None, :]
+        st = _run_grpc(stub.host, stub.port, [_grpc_request("simple", [("INPUT0", a), ("INPUT1", a)])] * 2, seconds=0.6)
+        assert st.failed_request_count == 0 and st.completed_request_count >= 4, (st.completed_request_count, st.failed_request_count)
+    finally:
+        stub.stop()
+
+
 def _run_stream(host, port, reqs, seconds=0.4):
     lib = _native.load()
     n = len(reqs)

@@ -148,6 +148,63 @@ def test_native_grpc_wire_bytes_reach_the_server(lookahead):
         srv.stop(0)
 
 
+@pytest.mark.parametrize("depth", [1, 3])
+def test_pipelined_passes_send_fresh_oracle_exact_tensors(depth):
+    """The issue loop with several device passes in flight (pipeline_depth): every request a real
+    grpcio server receives carries tensors that (a) equal the oracle's for that slot and some
+    generation epoch, (b) were never sent before -- no request goes out with stale or half-written
+    inputs although fills of consecutive passes overlap on the device."""
+    from concurrent import futures
+
+    import grpc
+
+    from client_b200.grpc import service_pb2, service_pb2_grpc
+    from client_b200.perf.loadgen import SlotSet, TensorSpec
+    from client_b200.perf.native import NativeLoadGenerator, grpc_wire_prefixes
+    from oracle import cref
+
+    received = []
+
+    class Capture(service_pb2_grpc.GRPCInferenceServiceServicer):
+        def ModelInfer(self, request, context):
+            received.append([bytes(b) for b in request.raw_input_contents])
+            return service_pb2.ModelInferResponse(model_name=request.model_name)
+
+    srv = grpc.server(futures.ThreadPoolExecutor(max_workers=8))
+    service_pb2_grpc.add_GRPCInferenceServiceServicer_to_server(Capture(), srv)
+    port = srv.add_insecure_port("127.0.0.1:0")
+    srv.start()
+    slots = 16
+    ins = [TensorSpec("input_ids", "INT32", [1, 4096])]  # one homogeneous tensor per slot: the specialised fill kernel
+    try:
+        ss = SlotSet(ins, [], slots, "none", 0, "random", 9, {"input_ids": (0, 128256)}, name_prefix="pipe%d" % depth,
+                     wire_prefixes=grpc_wire_prefixes(ins))
+        gen = NativeLoadGenerator("127.0.0.1:%d" % port, "llama3_8b", "", ss, slots, regenerate=True, validate=False, protocol="grpc",
+                                  pipeline_depth=depth)
+        gen.start()
+        w = gen.window(0.6)
+        gen.stop()
+        ss.close()
+        assert w["failed"] == 0 and w["count"] > 4 * slots and w["device_batches"] > 4, w
+        passes = w["device_batches"] + 64
+        heads = {}
+        for slot in range(slots):
+            for e in range(passes + 1):
+                heads[cref.fill(16, "INT32", seed=ss.seed, stream=(slot << 8) + (e << 20), ilo=0, irange=128256).tobytes()] = (slot, e)
+        seen = set()
+        for tensors in received:
+            assert len(tensors) == 1 and len(tensors[0]) == 16384
+            key = tensors[0][:16]
+            assert key in heads, "a request carried bytes no (slot, epoch) of the contract produces"
+            assert key not in seen, "the same generation was sent twice"
+            seen.add(key)
+        for tensors in received[:: max(1, len(received) // 40)]:  # full tensors, sampled
+            slot, e = heads[tensors[0][:16]]
+            assert tensors[0] == cref.fill(16384, "INT32", seed=ss.seed, stream=(slot << 8) + (e << 20), ilo=0, irange=128256).tobytes()
+    finally:
+        srv.stop(0)
+
+
 def test_native_engine_grpc_streaming(server):
     """--engine native --streaming: BASELINE configs[4] (Llama prompt INT32[1,4096] on a
     ModelStreamInfer stream, decoupled responses): the prompt is generated by the fill kernel

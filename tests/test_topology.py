@@ -1,0 +1,49 @@
+"""perf/topology.py: the per-GPU core plan (no GPU needed: the sysfs facts are passed in)."""
+
+import os
+
+from client_b200.perf import topology
+
+
+def _gpus():
+    # the 8-GPU box of SCALE_r01: GPU0-3 -> 0-31,64-95; GPU4-7 -> 32-63,96-127
+    a, b = topology.parse_cpulist("0-31,64-95"), topology.parse_cpulist("32-63,96-127")
+    return [{"index": i, "bus_id": "x", "numa_node": 0 if i < 4 else 1, "ranges": a if i < 4 else b} for i in range(8)]
+
+
+def test_parse_cpulist():
+    assert topology.parse_cpulist("0-3,8,10-11\n") == [[0, 1, 2, 3], [8], [10, 11]]
+
+
+def test_plan_slices_are_disjoint_and_numa_local():
+    plan = topology.plan(_gpus(), allowed=set(range(128)))
+    seen = set()
+    for i in range(8):
+        p = plan[i]
+        assert len(p["all"]) == 16 and not (set(p["all"]) & seen)
+        seen |= set(p["all"])
+        node_cpus = set(range(0, 32)) | set(range(64, 96)) if i < 4 else set(range(32, 64)) | set(range(96, 128))
+        assert set(p["all"]) <= node_cpus
+        assert len(p["server"]) == 8 and len(p["generator"]) == 8 and not set(p["server"]) & set(p["generator"])
+        assert set(p["server"]) | set(p["generator"]) == set(p["all"])
+        # a core and its hyperthread sibling (cpu + 64) stay in the same slice
+        assert {c + 64 for c in p["server"] if c < 64} == {c for c in p["server"] if c >= 64}
+    assert plan[0]["all"][:8] == list(range(0, 8)) and plan[3]["all"][:8] == list(range(24, 32))
+    assert seen == set(range(128))
+
+
+def test_plan_respects_the_allowed_mask_and_small_boxes():
+    plan = topology.plan(_gpus()[:1], allowed={0, 1, 2, 3, 64, 65, 66, 67})
+    assert plan[0]["all"] == [0, 1, 2, 3, 64, 65, 66, 67]
+    assert plan[0]["server"] == [0, 1, 64, 65] and plan[0]["generator"] == [2, 3, 66, 67]
+    tiny = topology.plan([{"index": 0, "bus_id": "x", "numa_node": -1, "ranges": [[5]]}], allowed={5})
+    assert tiny[0]["server"] == tiny[0]["generator"] == [5]
+
+
+def test_pin_changes_and_restores_the_affinity_mask():
+    before = sorted(os.sched_getaffinity(0))
+    try:
+        assert topology.pin(before[:1]) == before[:1]
+        assert topology.pin([]) == []
+    finally:
+        os.sched_setaffinity(0, set(before))
