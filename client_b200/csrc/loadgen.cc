@@ -832,10 +832,14 @@ void device_main_pipelined(tb200_loadgen* lg) {
     release_slots(lg, p.batch);
   };
 
+  // A pass costs the host ~15 us of launches and table copies whatever its size, so while passes
+  // are in flight a new one is only worth forming once enough slots are back (an eighth of the
+  // concurrency); fewer than that wait for the oldest pass to retire and accumulate meanwhile.
+  // With nothing in flight whatever is back goes out at once (latency at low concurrency).
+  const size_t min_batch = std::max<size_t>(1, static_cast<size_t>(lg->concurrency) / 8);
   std::vector<int> batch;
   while (!lg->stop.load(std::memory_order_relaxed)) {
-    batch.clear();
-    if (inflight.empty()) {
+    if (inflight.empty() && batch.empty()) {
       const int first = lg->returned.pop(50);
       if (first < 0) continue;
       batch.push_back(first);
@@ -852,8 +856,10 @@ void device_main_pipelined(tb200_loadgen* lg) {
         lg->returned.drain(batch);
       }
     }
-    if (!batch.empty()) {
+    const bool submit = !batch.empty() && (inflight.empty() || (inflight.size() < depth && batch.size() >= min_batch));
+    if (submit) {
       Pass p = std::move(pool[seq % depth]);
+      p.batch.clear();
       p.batch.swap(batch);
       p.checks.clear();
       fills.clear();
@@ -876,7 +882,7 @@ void device_main_pipelined(tb200_loadgen* lg) {
       inflight.push_back(std::move(p));
       if (inflight.size() < depth) continue;  // room for another pass: look for returned slots first
     }
-    if (!inflight.empty()) {  // nothing new came back, or the pipeline is full: retire the oldest pass
+    if (!inflight.empty()) {  // too little came back, or the pipeline is full: retire the oldest pass
       retire(inflight.front());
       pool[(seq - inflight.size()) % depth] = std::move(inflight.front());
       inflight.pop_front();

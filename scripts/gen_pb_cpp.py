@@ -27,13 +27,16 @@ class Field:
         self.owner, self.name, self.number, self.label = owner, name, number, label
         self.oneof = label.split(":", 1)[1] if label.startswith("oneof:") else None
         self.repeated = label == "rep"
-        self.map = label == "map"
+        self.map = label == "map" or label.startswith("map:")
+        self.key = None
+        if self.map:  # map<K, V>: K string or an integer type; the field's type is V
+            self.key = Field(owner, "key", 1, label.split(":", 1)[1] if ":" in label else "string", "")
         self.enum = None
         self.msg = None
         top = owner.split(".")[0]
         if ftype.startswith("enum:"):
             e = ftype[5:]
-            self.enum = (top + "_" + e[1:]) if e.startswith(".") else e
+            self.enum = ((top + e) if e.startswith(".") else e).replace(".", "_")
             self.kind = "varint"
             self.ctype = self.enum
         elif ftype in VARINT:
@@ -87,10 +90,11 @@ def collect():
     return msgs, order
 
 
-def emit_enum(out, cname, values):
+def emit_enum(out, qualified, values):
+    cname = qualified.replace(".", "_")
     out.append("enum %s : int {" % cname)
     for n, v in values:
-        out.append("  %s = %d," % (n if "_" not in cname or cname == "DataType" else cname + "_" + n, v))
+        out.append("  %s = %d," % (n if "." not in qualified else cname + "_" + n, v))
     out.append("};")
     out.append("inline const char* %s_Name(int v) {" % cname)
     out.append("  switch (v) {")
@@ -98,6 +102,37 @@ def emit_enum(out, cname, values):
         out.append('    case %d: return "%s";' % (v, n))
     out.append('    default: return "";')
     out.append("  }\n}")
+
+
+def map_types(f):
+    """(C++ key type, C++ value type) of a map field."""
+    kt = "std::string" if f.key.kind == "string" else f.key.ctype
+    return kt, f.ctype
+
+
+def put_scalar(f, field_no, v, out="out"):
+    """statement(s) appending one scalar / string / message value `v` as field `field_no`"""
+    if f.kind == "message":
+        return "{ std::string sub_; %s.AppendTo(&sub_); put_bytes(%s, %d, sub_); }" % (v, out, field_no)
+    if f.kind == "string":
+        return "put_bytes(%s, %d, %s);" % (out, field_no, v)
+    if f.kind == "varint":
+        return "{ put_tag(%s, %d, kVarint); put_varint(%s, %s); }" % (out, field_no, out, f.to_u64(v))
+    _, wt, rd, tobits, _ = FIXED[f.ftype]
+    return "{ put_tag(%s, %d, %s); put_%s(%s, %s(%s)); }" % (out, field_no, wt, rd, out, tobits, v)
+
+
+def read_scalar(f, reader, target, wt="ewt"):
+    """expression statement reading one value of f from Reader `reader` into lvalue `target`
+    (caller checked the field number); returns code that evaluates to true when consumed"""
+    if f.kind == "message":
+        return "(%s == kBytes && %s.bytes(&ed, &elen) && ((r.ok = %s.MergeFrom(ed, elen) && r.ok), true))" % (wt, reader, target)
+    if f.kind == "string":
+        return "(%s == kBytes && %s.bytes(&ed, &elen) && (%s.assign(reinterpret_cast<const char*>(ed), elen), true))" % (wt, reader, target)
+    if f.kind == "varint":
+        return "(%s == kVarint && ((%s = %s), true))" % (wt, target, f.from_u64("%s.varint()" % reader))
+    _, wtn, rd, _, frombits = FIXED[f.ftype]
+    return "(%s == %s && ((%s = %s(%s.%s())), true))" % (wt, wtn, target, frombits, reader, rd)
 
 
 def generate():
@@ -117,8 +152,8 @@ def generate():
     w("")
     w("namespace inference {")
     w("")
-    emit_enum(out, "DataType", _proto.DATA_TYPE_ENUM)
-    emit_enum(out, "ModelInput_Format", _proto.FORMAT_ENUM)
+    for qualified, values in _proto.MODEL_CONFIG_ENUMS.items():
+        emit_enum(out, qualified, values)
     w("")
     for name in order:
         fields = sorted(msgs[name], key=lambda f: f.number)
@@ -132,10 +167,12 @@ def generate():
         for child in msgs:
             if child.startswith(name + ".") and "." not in child[len(name) + 1:]:
                 w("  using %s = %s;" % (child[len(name) + 1:], child.replace(".", "_")))
-        if name == "ModelInput":
-            w("  using Format = ModelInput_Format;")
-            for n, v in _proto.FORMAT_ENUM:
-                w("  static constexpr Format %s = ModelInput_Format_%s;" % (n, n))
+        for qualified, values in _proto.MODEL_CONFIG_ENUMS.items():  # enums nested in this message
+            if qualified.startswith(name + ".") and "." not in qualified[len(name) + 1:]:
+                short, ecname = qualified[len(name) + 1:], qualified.replace(".", "_")
+                w("  using %s = %s;" % (short, ecname))
+                for n, v in values:
+                    w("  static constexpr %s %s = %s_%s;" % (short, n, ecname, n))
         for group, members in oneofs.items():
             w("  enum %sCase { %s %s_NOT_SET = 0 };" % (camel(group), " ".join("k%s = %d," % (camel(m.name), m.number) for m in members), group.upper()))
             w("  %sCase %s_case() const { return static_cast<%sCase>(%s_case_); }" % (camel(group), group, camel(group), group))
@@ -143,8 +180,9 @@ def generate():
         for f in fields:
             n, m, ct = f.name, f.m, f.ctype
             if f.map:
-                w("  const std::map<std::string, %s>& %s() const { return %s; }" % (ct, n, m))
-                w("  std::map<std::string, %s>* mutable_%s() { return &%s; }" % (ct, n, m))
+                kt, vt = map_types(f)
+                w("  const std::map<%s, %s>& %s() const { return %s; }" % (kt, vt, n, m))
+                w("  std::map<%s, %s>* mutable_%s() { return &%s; }" % (kt, vt, n, m))
                 w("  int %s_size() const { return static_cast<int>(%s.size()); }" % (n, m))
                 w("  void clear_%s() { %s.clear(); }" % (n, m))
             elif f.repeated:
@@ -167,6 +205,11 @@ def generate():
                 else:
                     w("  %s %s(int i) const { return static_cast<%s>(%s[static_cast<size_t>(i)]); }" % (ct, n, ct, m))
                     w("  void add_%s(%s v) { %s.push_back(static_cast<%s>(v)); }" % (n, ct, m, et))
+            elif f.kind == "message" and f.oneof:
+                w("  bool has_%s() const { return %s_case_ == %d; }" % (n, f.oneof, f.number))
+                w("  const %s& %s() const {\n    static const tb200::pb::Box<%s> kNone;\n    return %s_case_ == %d ? %s.get() : kNone.get();\n  }" % (ct, n, ct, f.oneof, f.number, m))
+                w("  %s* mutable_%s() {\n    %s_case_ = %d;\n    return %s.mut();\n  }" % (ct, n, f.oneof, f.number, m))
+                w("  void clear_%s() {\n    if (%s_case_ == %d) %s_case_ = 0;\n    %s.reset();\n  }" % (n, f.oneof, f.number, f.oneof, m))
             elif f.kind == "message":
                 w("  bool has_%s() const { return %s.has(); }" % (n, m))
                 w("  const %s& %s() const { return %s.get(); }" % (ct, n, m))
@@ -219,7 +262,8 @@ def generate():
             N, m = f.number, f.m
             if f.map:
                 w("    for (const auto& kv : %s) {" % m)
-                w("      std::string entry, sub;\n      put_bytes(&entry, 1, kv.first);\n      kv.second.AppendTo(&sub);\n      put_bytes(&entry, 2, sub);\n      put_bytes(out, %d, entry);\n    }" % N)
+                w("      std::string entry;\n      %s\n      %s\n      put_bytes(out, %d, entry);\n    }" % (
+                    put_scalar(f.key, 1, "kv.first", "&entry"), put_scalar(f, 2, "kv.second", "&entry"), N))
             elif f.repeated:
                 if f.kind == "message":
                     w("    for (const auto& v : %s) {\n      std::string sub;\n      v.AppendTo(&sub);\n      put_bytes(out, %d, sub);\n    }" % (m, N))
@@ -231,7 +275,8 @@ def generate():
                     _, _, rd, tobits, _ = FIXED[f.ftype]
                     w("    if (!%s.empty()) {\n      std::string sub;\n      for (auto v : %s) put_%s(&sub, %s(v));\n      put_bytes(out, %d, sub);\n    }" % (m, m, rd, tobits, N))
             elif f.kind == "message":
-                w("    if (%s.has()) {\n      std::string sub;\n      %s.get().AppendTo(&sub);\n      put_bytes(out, %d, sub);\n    }" % (m, m, N))
+                cond = ("%s_case_ == %d" % (f.oneof, N)) if f.oneof else ("%s.has()" % m)
+                w("    if (%s) {\n      std::string sub;\n      %s.get().AppendTo(&sub);\n      put_bytes(out, %d, sub);\n    }" % (cond, m, N))
             else:
                 if f.oneof:
                     cond = "%s_case_ == %d" % (f.oneof, N)
@@ -262,12 +307,15 @@ def generate():
             if f.map or f.repeated or f.kind in ("message", "string"):
                 w("          const uint8_t* d = nullptr;\n          size_t len = 0;")
             if f.map:
+                kt, vt = map_types(f)
+                kinit = "" if f.key.kind == "string" else " = 0"
+                vinit = "" if f.kind in ("message", "string") else (" = false" if f.ftype == "bool" else " = static_cast<%s>(0)" % vt)
                 w("          if (wt == kBytes && r.bytes(&d, &len)) {")
-                w("            Reader e(d, len);\n            std::string key;\n            %s value;\n            uint32_t ef = 0, ewt = 0;" % f.ctype)
-                w("            while (e.tag(&ef, &ewt)) {\n              const uint8_t* ed = nullptr;\n              size_t elen = 0;")
-                w("              if (ef == 1 && ewt == kBytes && e.bytes(&ed, &elen)) key.assign(reinterpret_cast<const char*>(ed), elen);")
-                w("              else if (ef == 2 && ewt == kBytes && e.bytes(&ed, &elen)) r.ok = value.MergeFrom(ed, elen) && r.ok;")
-                w("              else e.skip(ewt);\n            }")
+                w("            Reader e(d, len);\n            %s key%s;\n            %s value%s;\n            uint32_t ef = 0, ewt = 0;" % (kt, kinit, vt, vinit))
+                w("            while (e.tag(&ef, &ewt)) {\n              const uint8_t* ed = nullptr;\n              size_t elen = 0;\n              (void)ed;\n              (void)elen;")
+                w("              if (ef == 1 && %s) {" % read_scalar(f.key, "e", "key"))
+                w("              } else if (ef == 2 && %s) {" % read_scalar(f, "e", "value"))
+                w("              } else {\n                e.skip(ewt);\n              }\n            }")
                 w("            if (!e.ok) r.ok = false;\n            %s[key] = std::move(value);\n          } else {\n            r.skip(wt);\n          }" % m)
             elif f.repeated and f.kind == "message":
                 w("          if (wt == kBytes && r.bytes(&d, &len)) {\n            %s.emplace_back();\n            if (!%s.back().MergeFrom(d, len)) r.ok = false;\n          } else {\n            r.skip(wt);\n          }" % (m, m))
@@ -282,7 +330,8 @@ def generate():
                 w("          if (wt == kBytes && r.bytes(&d, &len)) {\n            Reader p(d, len);\n            while (!p.done()) {\n              const auto v = p.%s();\n              if (p.ok) %s.push_back(%s(v));\n            }\n            if (!p.ok) r.ok = false;" % (rd, m, frombits))
                 w("          } else if (wt == %s) {\n            %s.push_back(%s(r.%s()));\n          } else {\n            r.skip(wt);\n          }" % (wtn, m, frombits, rd))
             elif f.kind == "message":
-                w("          if (wt == kBytes && r.bytes(&d, &len)) {\n            if (!%s.mut()->MergeFrom(d, len)) r.ok = false;\n          } else {\n            r.skip(wt);\n          }" % m)
+                setcase = ("            %s_case_ = %d;\n" % (f.oneof, N)) if f.oneof else ""
+                w("          if (wt == kBytes && r.bytes(&d, &len)) {\n%s            if (!%s.mut()->MergeFrom(d, len)) r.ok = false;\n          } else {\n            r.skip(wt);\n          }" % (setcase, m))
             else:
                 setcase = ("            %s_case_ = %d;\n" % (f.oneof, N)) if f.oneof else ""
                 if f.kind == "string":
@@ -302,8 +351,9 @@ def generate():
         def scalar_text(f, v):
             if f.kind == "string":
                 return "text_escaped(out, %s);" % v
-            if f.enum:
-                return "out->append(%s_Name(static_cast<int>(%s)));" % (f.enum, v)
+            if f.enum:  # an unknown value prints as its number, like libprotobuf's text format
+                return ("{ const char* nm_ = %s_Name(static_cast<int>(%s)); if (*nm_) out->append(nm_); else out->append(std::to_string(static_cast<int>(%s))); }"
+                        % (f.enum, v, v))
             if f.ftype == "bool":
                 return 'out->append(%s ? "true" : "false");' % v
             if f.kind == "fixed":
@@ -317,15 +367,22 @@ def generate():
             if f.map:
                 w("    for (const auto& kv : %s) {" % m)
                 w('      text_indent(out, indent);\n      out->append("%s {\\n");' % n)
-                w('      text_indent(out, indent + 2);\n      out->append("key: ");\n      text_escaped(out, kv.first);\n      out->append("\\n");')
-                w('      text_indent(out, indent + 2);\n      out->append("value {\\n");\n      kv.second.PrintTo(out, indent + 4);\n      text_indent(out, indent + 2);\n      out->append("}\\n");')
+                def nondefault(ff, v):
+                    return ("!%s.empty()" % v) if ff.kind == "string" else ("%s != 0" % v if ff.ftype != "bool" else v)
+
+                # default-valued keys / scalar values of an entry are not printed (proto3 text format)
+                w('      if (%s) {\n        text_indent(out, indent + 2);\n        out->append("key: ");\n        %s\n        out->append("\\n");\n      }' % (nondefault(f.key, "kv.first"), scalar_text(f.key, "kv.first")))
+                if f.kind == "message":
+                    w('      text_indent(out, indent + 2);\n      out->append("value {\\n");\n      kv.second.PrintTo(out, indent + 4);\n      text_indent(out, indent + 2);\n      out->append("}\\n");')
+                else:
+                    w('      if (%s) {\n        text_indent(out, indent + 2);\n        out->append("value: ");\n        %s\n        out->append("\\n");\n      }' % (nondefault(f, "kv.second"), scalar_text(f, "kv.second")))
                 w('      text_indent(out, indent);\n      out->append("}\\n");\n    }')
             elif f.kind == "message":
                 if f.repeated:
                     w("    for (const auto& v : %s) {" % m)
                     w('      text_indent(out, indent);\n      out->append("%s {\\n");\n      v.PrintTo(out, indent + 2);\n      text_indent(out, indent);\n      out->append("}\\n");\n    }' % n)
                 else:
-                    w("    if (%s.has()) {" % m)
+                    w("    if (%s) {" % (("%s_case_ == %d" % (f.oneof, f.number)) if f.oneof else ("%s.has()" % m)))
                     w('      text_indent(out, indent);\n      out->append("%s {\\n");\n      %s.get().PrintTo(out, indent + 2);\n      text_indent(out, indent);\n      out->append("}\\n");\n    }' % (n, m))
             elif f.repeated:
                 w("    for (const auto& v : %s) {" % m)
@@ -347,7 +404,7 @@ def generate():
         w(" private:")
         for f in fields:
             if f.map:
-                w("  std::map<std::string, %s> %s;" % (f.ctype, f.m))
+                w("  std::map<%s, %s> %s;" % (map_types(f) + (f.m,)))
             elif f.repeated:
                 w("  std::vector<%s> %s;" % (f.elem_type(), f.m))
             elif f.kind == "message":

@@ -8,6 +8,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# tests/golden/ holds fixtures -- among them unmodified copies of the reference's own unit-test
+# modules, which tests/test_reference_unit_tests.py runs in a subprocess with the drop-in aliased as
+# `tritonclient`; pytest must not collect them itself
+collect_ignore_glob = ["golden/*"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

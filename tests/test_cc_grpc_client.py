@@ -177,6 +177,84 @@ def _random_messages(rng):
             o.dims.extend([1000])
         if rng.random() < 0.5:
             c.config.model_transaction_policy.decoupled = rng.random() < 0.5
+        # the sections of model_config.proto beyond inputs / outputs: nested enums, oneofs
+        # with message members, map<uint64, message>, map<string, string>, map<string, message>
+        for _ in range(rng.randrange(3)):
+            g = c.config.instance_group.add()
+            g.name, g.kind, g.count = text(), rng.randrange(5), rng.randrange(4)
+            g.gpus.extend(rng.randrange(8) for _ in range(rng.randrange(3)))
+            if rng.random() < 0.4:
+                r = g.rate_limiter.resources.add()
+                r.name, r.count = text(), rng.randrange(9)
+                setattr(r, "global", rng.random() < 0.5)
+            for _ in range(rng.randrange(2)):
+                sd = g.secondary_devices.add()
+                sd.kind, sd.device_id = 0, rng.randrange(4)
+        pick = rng.randrange(4)
+        if pick == 0:
+            c.config.dynamic_batching.preferred_batch_size.extend([4, 8][: rng.randrange(3)])
+            c.config.dynamic_batching.max_queue_delay_microseconds = rng.randrange(10**6)
+            for _ in range(rng.randrange(3)):
+                q = c.config.dynamic_batching.priority_queue_policy[rng.randrange(1, 6)]
+                q.timeout_action, q.max_queue_size, q.allow_timeout_override = rng.randrange(2), rng.randrange(100), rng.random() < 0.5
+            if rng.random() < 0.5:
+                c.config.dynamic_batching.default_queue_policy.default_timeout_microseconds = rng.randrange(10**9)
+        elif pick == 1:
+            sb = c.config.sequence_batching
+            sb.max_sequence_idle_microseconds = rng.randrange(10**9)
+            if rng.random() < 0.5:
+                sb.oldest.max_candidate_sequences = rng.randrange(64)
+                sb.oldest.preferred_batch_size.extend([2, 4])
+            else:
+                sb.direct.max_queue_delay_microseconds = rng.randrange(1000)
+            ci = sb.control_input.add()
+            ci.name = text()
+            k = ci.control.add()
+            k.kind = rng.randrange(4)
+            k.int32_false_true.extend([0, 1])
+            st8 = sb.state.add()
+            st8.input_name, st8.output_name, st8.data_type = text(), text(), rng.randrange(15)
+            st8.dims.extend([-1])
+            if rng.random() < 0.5:
+                st8.initial_state.add(name=text(), data_type=11, dims=[1], zero_data=True)
+            else:
+                st8.initial_state.add(name=text(), data_type=11, dims=[1], data_file=text())
+        elif pick == 2:
+            step = c.config.ensemble_scheduling.step.add()
+            step.model_name, step.model_version = text(), rng.choice([-1, 1, 3])
+            for _ in range(rng.randrange(3)):
+                step.input_map[text() or "in"] = text()
+                step.output_map[text() or "out"] = text()
+        for _ in range(rng.randrange(3)):
+            c.config.parameters[text() or "p"].string_value = text()
+        if rng.random() < 0.5:
+            c.config.version_policy.specific.versions.extend([1, 3, rng.randrange(10)])
+        elif rng.random() < 0.5:
+            c.config.version_policy.latest.num_versions = rng.randrange(4)
+        if rng.random() < 0.4:
+            c.config.optimization.cuda.graphs = True
+            gs = c.config.optimization.cuda.graph_spec.add()
+            gs.batch_size = rng.randrange(8)
+            gs.input[text() or "x"].dim.extend([1, 3])
+            acc = c.config.optimization.execution_accelerators.gpu_execution_accelerator.add()
+            acc.name = "tensorrt"
+            acc.parameters["precision_mode"] = rng.choice(["FP16", "FP32"])
+            c.config.optimization.priority = rng.randrange(3)
+        for _ in range(rng.randrange(2)):
+            wu = c.config.model_warmup.add()
+            wu.name, wu.batch_size = text(), rng.randrange(4)
+            wi = wu.inputs[text() or "in"]
+            wi.data_type = rng.randrange(15)
+            wi.dims.extend([3])
+            k = rng.randrange(3)
+            if k == 0:
+                wi.zero_data = True
+            elif k == 1:
+                wi.random_data = rng.random() < 0.5
+            else:
+                wi.input_data_file = text()
+        if rng.random() < 0.3:
+            c.config.response_cache.enable = True
         out.append(("ModelConfigResponse", c))
         md = service_pb2.ModelMetadataResponse(name=text(), platform=text())
         md.versions.extend(text(3) for _ in range(rng.randrange(3)))
