@@ -39,7 +39,9 @@ KEYS = [
 
 
 def launches(tag):
-    path = os.path.join(OUT, "launches.csv")
+    path = os.path.join(OUT, tag + "_launches.csv")
+    if not os.path.exists(path):
+        path = os.path.join(OUT, "launches.csv")
     if not os.path.exists(path):
         return
     rows = list(csv.reader(open(path)))
@@ -55,7 +57,7 @@ def launches(tag):
                 pass
     total = sum(sum(v) for v in agg.values())
     with open(os.path.join(DST, tag + "_launches.csv"), "w") as fh:
-        fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 24 --warmup 3\n")
+        fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 20 --warmup 5 (device sections)\n")
         fh.write("# per-launch times under ncu are cold-cache and serialised: compare the SHARES\n")
         fh.write("kernel,launches,avg_us,min_us,max_us,share_pct\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
@@ -84,10 +86,49 @@ def full(tag, rep, label):
             fh.write("# traffic = dram read + write per launch, unit as above\n")
 
 
+def steady_dram(tag):
+    """profiles/<tag>_fill_steady_dram.txt from the single-purpose DRAM captures of scripts/ncu_round2.sh
+    (application replay, no cache control, launches 240.. of a rotating chain)."""
+    lines = []
+    for dt in ("FP32", "FP16"):
+        path = os.path.join(OUT, "%s_fill_steady_dram_%s.csv" % (tag, dt))
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+        hdr = rows[start]
+        ki, mn, mv, idi = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+        per = collections.OrderedDict()
+        for r in rows[start + 1:]:
+            if len(r) > mv:
+                per.setdefault(r[idi], {"kernel": r[ki].split("(")[0]})[r[mn]] = r[mv].replace(",", "")
+        lines.append("== %s: launches 240..247 of 256 back-to-back %s fills of 38,535,168 B rotating over 4 region sets (154 MB)" % (
+            next(iter(per.values()))["kernel"], "64 x FP32[3,224,224]" if dt == "FP32" else "1 x FP16[128,3,224,224]"))
+        lines.append("%-8s %16s %16s %14s %14s" % ("launch", "dram_write_B", "dram_read_B", "duration_ns", "warps_active_%"))
+        tw = 0.0
+        for k, v in per.items():
+            w = float(v.get("dram__bytes_write.sum", 0))
+            tw += w
+            lines.append("%-8s %16d %16d %14s %14s" % (k, w, float(v.get("dram__bytes_read.sum", 0)), v.get("gpu__time_duration.sum", "?"),
+                                                    v.get("sm__warps_active.avg.pct_of_peak_sustained_active", "?")))
+        lines.append("mean dram write per launch: %.0f B = %.3f of the 38,535,168 algorithmic bytes (the rest is overwritten in L2 before eviction)" % (tw / len(per), tw / len(per) / 38535168))
+        lines.append("")
+    if lines:
+        with open(os.path.join(DST, tag + "_fill_steady_dram.txt"), "w") as fh:
+            fh.write("# ncu --replay-mode application --cache-control none --clock-control none -k regex:fill_uniform_kernel --launch-skip 240 --launch-count 8\n")
+            fh.write("# (scripts/ncu_round2.sh, scripts/fill_steady.py): steady-state HBM traffic of the fill launch; durations under ncu are serialised launches\n\n")
+            fh.write("\n".join(lines))
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(DST, exist_ok=True)
     launches(tag)
+    steady_dram(tag)
+    full(tag, tag + "_prof_fill_uniform.ncu-rep", "fill_uniform_kernel")
+    if tag != "r01":  # the captures below are round 1's; later rounds name their files <tag>_*
+        print(sorted(os.listdir(DST)))
+        return
     full(tag, "prof_fill.ncu-rep", "fill_kernel")
     full(tag, "prof_pack.ncu-rep", "pack_image_kernel")
     full(tag, "prof_check.ncu-rep", "check_kernel")
