@@ -93,7 +93,8 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
+    def __init__(self, device, period=0.2):
+        self.period = period
         self.samples = []
         self._stop = threading.Event()
         self._thread = None
@@ -109,7 +110,7 @@ class ClockSampler:
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(self.period)
 
     def start(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -180,8 +181,9 @@ def run_b200(args):
         for i in range(n % GRAPH_STEPS):
             graphs_one[i % SETS].launch()
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local, period=0.2 if world == 1 else 0.5)
+    if rank == 0:  # one nvidia-smi loop per box, not one per rank
+        sampler.start()
     timer = _native.Timer(ctx)
     run_steps(max(warmup, GRAPH_STEPS))
     ops.sync()
@@ -660,7 +662,10 @@ class LoopbackBox:
     """The serving side of a loopback run: a private CUDA MPS daemon (when the box has the binary and
     `manage_mps`) and one native server process per device, each pinned to its GPU's server cores."""
 
-    MPS_ENV = {"CUDA_MPS_PIPE_DIRECTORY": "/tmp/tb200_mps_pipe", "CUDA_MPS_LOG_DIRECTORY": "/tmp/tb200_mps_log"}
+    # per launch (torchrun ranks share MASTER_PORT): a daemon of an earlier run that is still shutting
+    # down cannot be mistaken for ours
+    _TAG = os.environ.get("MASTER_PORT", "") + "_" + str(os.getppid() if os.environ.get("RANK") else os.getpid())
+    MPS_ENV = {"CUDA_MPS_PIPE_DIRECTORY": "/tmp/tb200_mps_pipe_" + _TAG, "CUDA_MPS_LOG_DIRECTORY": "/tmp/tb200_mps_log_" + _TAG}
 
     def __init__(self, devices, use_mps=True, manage_mps=True, grpc=False, pin=True):
         import shutil
@@ -704,8 +709,11 @@ class LoopbackBox:
                 cmd += ["--pin-cpus"]
             self.servers[dev] = subprocess.Popen(cmd, cwd=ROOT, env=self.env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
             self.urls[dev] = "127.0.0.1:%d" % port
+        import select
+
         for dev, srv in self.servers.items():
-            hello = srv.stdout.readline()
+            ready, _, _ = select.select([srv.stdout], [], [], 90.0)  # a server that never comes up must not hang the bench
+            hello = srv.stdout.readline() if ready else "timeout waiting for the server"
             if "listening" not in hello:
                 self.__exit__(None, None, None)
                 raise RuntimeError("native server for device %d did not start: %s" % (dev, hello.strip()[:200]))
@@ -729,7 +737,7 @@ class LoopbackBox:
                 pass
         return False
 
-    def generator(self, dev, steps, warmup, mode="per-request", concurrency=SLOTS, extra=(), min_seconds=0.1, timeout=180):
+    def generator(self, dev, steps, warmup, mode="per-request", concurrency=SLOTS, extra=(), min_seconds=0.1, timeout=120):
         """One `python -m client_b200.perf.loopback` child against this box's server for `dev`."""
         cmd = [sys.executable, "-m", "client_b200.perf.loopback", "-u", self.urls[dev], "--device", str(dev), "--concurrency", str(concurrency),
                "--steps", str(steps), "--warmup", str(warmup), "--input-data-mode", mode, "--min-seconds", str(min_seconds),

@@ -1,6 +1,6 @@
-// deflate.cuh -- the per-chunk logic of the device deflate encoder (RFC 1951 fixed-Huffman
-// blocks with LZ77 matches), written as host+device functions so that tests/host_emul can
-// run the exact code on the CPU and hand its output to zlib.
+// deflate.cuh -- the per-chunk logic of the device deflate encoder (RFC 1951: LZ77 matches +
+// a DYNAMIC Huffman code per chunk, fixed-Huffman and stored fallbacks), written as host+device
+// functions so that tests/host_emul can run the exact code on the CPU and hand its output to zlib.
 //
 // Why: the reference compresses a request body with zlib / gzip on one host core
 // (PY/http/_client.py:1440-1460 -> gzip.compress / zlib.compress; CC/http_client.cc:146-221).
@@ -8,14 +8,25 @@
 // valid deflate stream is acceptable to the peer, so parity here means: the reference's own
 // decompressor (zlib) returns the original bytes -- not byte equality with zlib's encoder.
 //
-// Layout of the work: the input is cut into chunks of kDeflateChunk bytes, one CTA each; a
-// chunk becomes ONE fixed-Huffman block followed by an empty stored block (a "sync flush":
-// 00 00 FF FF), which ends on a byte boundary, so chunks concatenate bytewise (pigz does the
-// same between threads).  Inside a chunk every thread parses its own kDeflateSub-byte
-// sub-block: matches may point anywhere earlier in the chunk but do not run past the
-// sub-block's end, so sub-blocks parse independently; a first pass counts bits, a prefix
-// sum gives every sub-block its bit offset, a second pass emits.  A chunk that does not
-// shrink is stored (BTYPE=00).
+// Layout of the work (round 2).  The input is cut into chunks of kDeflateChunk bytes, one CTA of
+// kDeflateThreads threads each; a chunk becomes ONE deflate block followed by an empty stored block
+// (a "sync flush": 00 00 FF FF), which ends on a byte boundary, so chunks concatenate bytewise.
+// Thread t owns sub-block t: kDeflateSub bytes held in registers.
+//   1. match finding.  Typed tensors repeat at distances 1, 2, 4, 8: for each of them a 64-bit
+//      equality mask of the sub-block (byte i == byte i-d, SIMD byte compares on the register
+//      words) turns "how long is the match at p" into a count of trailing ones -- no byte loop.
+//      Longer distances: a hash table of the FIRST position of every 4-byte hash in the chunk
+//      (one atomicMin pass), verified against shared memory only when it hits.
+//   2. greedy parse per sub-block (matches do not cross a sub-block's end, so sub-blocks parse
+//      independently), tokens left in shared memory, symbol histograms by shared atomics.
+//   3. a code per chunk: code lengths = ceil(log2(total / count)) (a Shannon code, Kraft sum <= 1),
+//      made complete on the 15-bin length histogram (promote the longest steps that still fit),
+//      lengths handed out by frequency rank, canonical codes -- every step is parallel over the
+//      symbols except a 15-iteration fix of the histogram; within ~1 % of a true Huffman code on
+//      token ids.  The code-length header (RLE symbols 16 / 17 / 18, code-length code of <= 7 bits)
+//      is formed by one thread and emitted by all.
+//   4. bit counts per sub-block under the dynamic and the fixed code, the cheaper of dynamic /
+//      fixed / stored wins per chunk; prefix sum; every thread emits its sub-block.
 #ifndef TB200_CSRC_DEFLATE_CUH_
 #define TB200_CSRC_DEFLATE_CUH_
 
@@ -29,10 +40,13 @@ constexpr int kDeflateChunk = 8192;   // bytes per CTA
 constexpr int kDeflateSub = 64;       // bytes per thread
 constexpr int kDeflateSubShift = 6;
 constexpr int kDeflateThreads = kDeflateChunk / kDeflateSub;  // 128
-constexpr int kDeflateHashBits = 11;   // 2048 heads of 32 bits: atomicMax keeps the latest position
-constexpr uint32_t kDeflateNoCand = 0xFFFFu;
-// worst case of a fixed-Huffman chunk: 9 bits per byte + header/EOB/flush
-constexpr int kDeflateOutWords = (kDeflateChunk * 9 / 8 + 64) / 4;
+constexpr int kDeflateHashBits = 11;   // 2048 entries: first position of a 4-byte hash in the chunk
+constexpr uint32_t kDeflateNoCand = 0xFFFFFFFFu;
+constexpr int kDeflateLitSyms = 288, kDeflateDistSyms = 32;  // 286 / 30 used
+constexpr int kDeflateHdrMax = 320;                          // code-length entries of a header (<= 286 + 30)
+// worst case of a chunk: 9 bits per byte (fixed code) or 15 bits per byte in a hypothetical dynamic
+// code never chosen (the cheapest of dynamic / fixed / stored is taken), + header + flush
+constexpr int kDeflateOutWords = (kDeflateChunk * 9 / 8 + 512) / 4;
 constexpr int kDeflateMaxChunkOut = kDeflateChunk + 16;  // stored fallback bounds the output
 
 // ---- bit stream (LSB-first within bytes, RFC 1951 section 3.1.1) ---------------------------
@@ -51,9 +65,13 @@ TB200_HD void deflate_put(uint32_t* words, uint32_t pos, uint32_t value, uint32_
   if (sh + nbits > 32u) deflate_or(words + w + 1, value >> (32u - sh));
 }
 TB200_HD uint32_t deflate_reverse(uint32_t code, uint32_t nbits) {
+#ifdef __CUDA_ARCH__
+  return nbits == 0 ? 0u : (__brev(code) >> (32u - nbits));
+#else
   uint32_t r = 0;
   for (uint32_t i = 0; i < nbits; ++i) r |= ((code >> i) & 1u) << (nbits - 1u - i);
   return r;
+#endif
 }
 
 // ---- fixed Huffman tables (RFC 1951 section 3.2.6), codes are sent MSB first ---------------
@@ -63,14 +81,19 @@ TB200_HD void deflate_litlen_code(uint32_t sym, uint32_t* code, uint32_t* nbits)
   else if (sym < 280u) { *code = sym - 256u; *nbits = 7; }
   else { *code = 0xC0u + (sym - 280u); *nbits = 8; }
 }
+TB200_HD uint32_t deflate_fixed_litlen_bits(uint32_t sym) { return sym < 144u ? 8u : (sym < 256u ? 9u : (sym < 280u ? 7u : 8u)); }
 // length 3..258 -> (symbol 257..285, extra bit count, extra value)
 TB200_HD void deflate_len_symbol(uint32_t len, uint32_t* sym, uint32_t* ebits, uint32_t* eval) {
   if (len == 258u) { *sym = 285; *ebits = 0; *eval = 0; return; }
   const uint32_t l = len - 3u;  // 0..254
   if (l < 8u) { *sym = 257u + l; *ebits = 0; *eval = 0; return; }
   // groups of 4 symbols share an extra-bit count e = 1..5: base offset 8, 16, 32, 64, 128
+#ifdef __CUDA_ARCH__
+  const uint32_t e = 29u - static_cast<uint32_t>(__clz(l));  // l in [8<<(e-1), 8<<e)
+#else
   uint32_t e = 1;
-  while ((8u << e) <= l) ++e;  // l in [8<<(e-1), 8<<e)
+  while ((8u << e) <= l) ++e;
+#endif
   const uint32_t base = 8u << (e - 1u);
   *sym = 261u + 4u * e + ((l - base) >> e);
   *ebits = e;
@@ -80,121 +103,339 @@ TB200_HD void deflate_len_symbol(uint32_t len, uint32_t* sym, uint32_t* ebits, u
 TB200_HD void deflate_dist_symbol(uint32_t dist, uint32_t* code, uint32_t* ebits, uint32_t* eval) {
   const uint32_t d = dist - 1u;
   if (d < 4u) { *code = d; *ebits = 0; *eval = 0; return; }
+#ifdef __CUDA_ARCH__
+  const uint32_t e = 30u - static_cast<uint32_t>(__clz(d));  // d in [4<<(e-1), 4<<e)
+#else
   uint32_t e = 1;
-  while ((4u << e) <= d) ++e;  // d in [4<<(e-1), 4<<e)
+  while ((4u << e) <= d) ++e;
+#endif
   const uint32_t base = 4u << (e - 1u);
   *code = 2u + 2u * e + ((d - base) >> e);
   *ebits = e;
   *eval = (d - base) & ((1u << e) - 1u);
 }
 
-TB200_HD uint32_t deflate_literal_bits(uint32_t byte) { return byte < 144u ? 8u : 9u; }
-TB200_HD uint32_t deflate_match_bits(uint32_t len, uint32_t dist) {
-  uint32_t sym, eb, ev, code, nb, dc, deb, dev;
-  deflate_len_symbol(len, &sym, &eb, &ev);
-  deflate_litlen_code(sym, &code, &nb);
-  deflate_dist_symbol(dist, &dc, &deb, &dev);
-  return nb + eb + 5u + deb;
-}
-TB200_HD uint32_t deflate_emit_literal(uint32_t* words, uint32_t pos, uint32_t byte) {
-  uint32_t code, nb;
-  deflate_litlen_code(byte, &code, &nb);
-  deflate_put(words, pos, deflate_reverse(code, nb), nb);
-  return nb;
-}
-TB200_HD uint32_t deflate_emit_match(uint32_t* words, uint32_t pos, uint32_t len, uint32_t dist) {
-  uint32_t sym, eb, ev, code, nb, dc, deb, dev;
-  deflate_len_symbol(len, &sym, &eb, &ev);
-  deflate_litlen_code(sym, &code, &nb);
-  deflate_dist_symbol(dist, &dc, &deb, &dev);
-  uint32_t p = pos;
-  deflate_put(words, p, deflate_reverse(code, nb), nb);
-  p += nb;
-  deflate_put(words, p, ev, eb);
-  p += eb;
-  deflate_put(words, p, deflate_reverse(dc, 5), 5);
-  p += 5;
-  deflate_put(words, p, dev, deb);
-  p += deb;
-  return p - pos;
-}
-
-// ---- match finding --------------------------------------------------------------------------
-// The chunk sits in shared memory with every sub-block shifted by one more word: thread t
-// walks sub-block t, and without the skew the threads of a warp would hit the same banks on
-// every byte they compare.  A sub-block itself stays contiguous.
+// ---- the chunk in shared memory ----------------------------------------------------------------
+// Every sub-block is shifted by one more word: thread t reads sub-block t, and without the skew the
+// threads of a warp would hit the same two banks on every access.  A sub-block itself stays contiguous.
 TB200_HD uint32_t deflate_at(uint32_t p) { return p + ((p >> kDeflateSubShift) << 2); }
 constexpr int kDeflateInBytes = kDeflateChunk + (kDeflateChunk / kDeflateSub) * 4 + 16;
 
-TB200_HD uint32_t deflate_hash(const uint8_t* in, uint32_t p) {
-  const uint32_t v = static_cast<uint32_t>(in[deflate_at(p)]) | (static_cast<uint32_t>(in[deflate_at(p + 1)]) << 8) |
-                     (static_cast<uint32_t>(in[deflate_at(p + 2)]) << 16) | (static_cast<uint32_t>(in[deflate_at(p + 3)]) << 24);
-  return (v * 2654435761u) >> (32 - kDeflateHashBits);
+// what a thread keeps in registers between the phases
+struct DeflateThread {
+  uint32_t w[19];        // w[0..1]: the 8 bytes before the sub-block, w[2..17]: the sub-block, w[18]: the 4 bytes after it
+  uint64_t eq[4];        // bit i: byte i == byte i - d, d = 1, 2, 4, 8
+  uint64_t is_match;     // bit i: the token that starts at byte i is a match
+  uint64_t is_start;     // bit i: a token starts at byte i
+  uint32_t begin, end;   // the sub-block's range in the chunk
+};
+
+// 4-bit mask: byte k of a equals byte k of b
+TB200_HD uint32_t deflate_eq4(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  const uint32_t m = __vcmpeq4(a, b) & 0x01010101u;  // 0x01 per equal byte
+  return (m * 0x01020408u) >> 24;                    // gather bits 0, 8, 16, 24 -> 0..3
+#else
+  uint32_t r = 0;
+  for (int k = 0; k < 4; ++k) r |= (((a >> (8 * k)) & 0xFFu) == ((b >> (8 * k)) & 0xFFu) ? 1u : 0u) << k;
+  return r;
+#endif
 }
+
+// equality masks of the sub-block for distances 1, 2, 4, 8 from the register words
+TB200_HD void deflate_masks(DeflateThread& t) {
+  uint64_t m1 = 0, m2 = 0, m4 = 0, m8 = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t cur = t.w[2 + k], a = t.w[1 + k], b = t.w[k];
+    m1 |= static_cast<uint64_t>(deflate_eq4(cur, (cur << 8) | (a >> 24))) << (4 * k);
+    m2 |= static_cast<uint64_t>(deflate_eq4(cur, (cur << 16) | (a >> 16))) << (4 * k);
+    m4 |= static_cast<uint64_t>(deflate_eq4(cur, a)) << (4 * k);
+    m8 |= static_cast<uint64_t>(deflate_eq4(cur, b)) << (4 * k);
+  }
+  const uint32_t len = t.end - t.begin;
+  const uint64_t valid = len >= 64u ? ~0ull : ((1ull << len) - 1ull);
+  // the first sub-block has nothing before it: positions < d cannot match at distance d
+  const uint64_t first = t.begin == 0u ? 1ull : 0ull;
+  t.eq[0] = m1 & valid & ~(first * 0x01ull);
+  t.eq[1] = m2 & valid & ~(first * 0x03ull);
+  t.eq[2] = m4 & valid & ~(first * 0x0Full);
+  t.eq[3] = m8 & valid & ~(first * 0xFFull);
+}
+
+// the 4 bytes at sub-block offset i (0..63) as a little-endian word, from the register words
+TB200_HD uint32_t deflate_word_at(const DeflateThread& t, uint32_t i) {
+  // dynamic register indexing would go through local memory: select by compare instead
+  uint32_t lo = 0, hi = 0;
+  const uint32_t k = i >> 2;
+#pragma unroll
+  for (uint32_t j = 0; j < 16; ++j) {
+    if (j == k) {
+      lo = t.w[2 + j];
+      hi = t.w[3 + j];
+    }
+  }
+  const uint32_t sh = (i & 3u) * 8u;
+  return sh == 0u ? lo : ((lo >> sh) | (hi << (32u - sh)));
+}
+TB200_HD uint32_t deflate_hash4(uint32_t v) { return (v * 2654435761u) >> (32 - kDeflateHashBits); }
+// the 4 bytes at chunk position p from the skewed image: two aligned words of the sub-block (the gap word
+// behind a sub-block repeats the first word of the next one, so this works up to the sub-block's last byte)
+TB200_HD uint32_t deflate_load4(const uint8_t* in, uint32_t p) {
+  const uint32_t a = deflate_at(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(in + (a & ~3u));
+  const uint32_t sh = (a & 3u) * 8u;
+  return sh == 0u ? w[0] : ((w[0] >> sh) | (w[1] << (32u - sh)));
+}
+
+TB200_HD uint32_t deflate_ctz64(uint64_t x) {  // x != 0
+#ifdef __CUDA_ARCH__
+  return static_cast<uint32_t>(__ffsll(static_cast<long long>(x)) - 1);
+#else
+  return static_cast<uint32_t>(__builtin_ctzll(x));
+#endif
+}
+// number of consecutive one bits of m starting at bit p
+TB200_HD uint32_t deflate_run(uint64_t m, uint32_t p) {
+  const uint64_t inv = ~(m >> p);
+  return inv == 0ull ? 64u - p : deflate_ctz64(inv);
+}
+
+// match length between chunk positions a < b in the skewed byte image, at most maxlen
 TB200_HD uint32_t deflate_match_len(const uint8_t* in, uint32_t a, uint32_t b, uint32_t maxlen) {
   uint32_t n = 0;
   while (n < maxlen && in[deflate_at(a + n)] == in[deflate_at(b + n)]) ++n;
   return n;
 }
-// best (len, dist) at position p, match not longer than `room`; candidates: the hash chain
-// head recorded for p and the short periodic distances typed tensors are full of
-TB200_HD void deflate_best(const uint8_t* in, uint32_t p, uint32_t room, uint32_t cand, uint32_t* len, uint32_t* dist) {
-  uint32_t best = 0, bd = 0;
-  const uint32_t maxlen = room < 258u ? room : 258u;
-  if (maxlen >= 3u) {
-    const uint32_t fixed[4] = {1u, 2u, 4u, 8u};
-    for (int i = 0; i < 5; ++i) {
-      uint32_t d;
-      if (i < 4) d = fixed[i];
-      else if (cand != kDeflateNoCand && cand < p) d = p - cand;
-      else continue;
-      if (d > p) continue;
-      const uint32_t l = deflate_match_len(in, p - d, p, maxlen);
-      if (l > best) { best = l; bd = d; }
-    }
-  }
-  if (best < 3u) { best = 0; bd = 0; }
-  *len = best;
-  *dist = bd;
+
+// bits of a match token under a code given as length tables
+TB200_HD uint32_t deflate_match_cost(const uint8_t* lit_len, const uint8_t* dist_len, uint32_t len, uint32_t dist) {
+  uint32_t sym, eb, ev, dc, deb, dev;
+  deflate_len_symbol(len, &sym, &eb, &ev);
+  deflate_dist_symbol(dist, &dc, &deb, &dev);
+  return lit_len[sym] + eb + dist_len[dc] + deb;
+}
+TB200_HD uint32_t deflate_fixed_match_bits(uint32_t len, uint32_t dist) {
+  uint32_t sym, eb, ev, dc, deb, dev;
+  deflate_len_symbol(len, &sym, &eb, &ev);
+  deflate_dist_symbol(dist, &dc, &deb, &dev);
+  return deflate_fixed_litlen_bits(sym) + eb + 5u + deb;
 }
 
-// Greedy parse of sub-block [begin, end) of the chunk `in`; cand[p] = an earlier position with
-// the same 4-byte hash (or kDeflateNoCand).  Counts the bits and leaves the decisions in the
-// cand array itself for the emitting pass: cand[p] = distance (0 = literal) and, for a match,
-// cand[p + 1] = length (a match covers >= 3 positions of its own sub-block, and the positions
-// it covers are never parsed, so their candidates are dead).
-TB200_HD uint32_t deflate_parse(const uint8_t* in, uint32_t begin, uint32_t end, uint16_t* cand) {
-  uint32_t bits = 0;
-  uint32_t p = begin;
-  while (p < end) {
-    uint32_t len, dist;
-    deflate_best(in, p, end - p, cand[p], &len, &dist);
-    if (len >= 3u) {
-      bits += deflate_match_bits(len, dist);
-      cand[p] = static_cast<uint16_t>(dist);
-      cand[p + 1] = static_cast<uint16_t>(len);
-      p += len;
+// Greedy parse of the thread's sub-block.  table: first chunk position of each 4-byte hash.
+// Leaves the decisions in t.is_start / t.is_match and, for a match that starts at chunk position
+// p, tok[p] = distance, tok[p + 1] = length (a match covers >= 3 positions of its own sub-block);
+// counts the symbols into the histograms (shared atomics on the device).
+template <typename AddFn>
+TB200_HD void deflate_parse(const uint8_t* in, DeflateThread& t, const uint32_t* table, uint16_t* tok, uint32_t chunk_bytes, AddFn add) {
+  uint64_t starts = 0, matches = 0;
+  const uint32_t n = t.end - t.begin;
+  uint32_t i = 0;
+  while (i < n) {
+    const uint32_t room = n - i;
+    uint32_t best = 0, bd = 0;
+    if (room >= 3u) {
+      // the periodic distances: longest run of equal bytes at distance d starting here; the
+      // shortest distance wins ties (cheapest distance code)
+      const uint32_t r1 = deflate_run(t.eq[0], i), r2 = deflate_run(t.eq[1], i), r4 = deflate_run(t.eq[2], i), r8 = deflate_run(t.eq[3], i);
+      best = r1;
+      bd = 1;
+      if (r2 > best) { best = r2; bd = 2; }
+      if (r4 > best) { best = r4; bd = 4; }
+      if (r8 > best) { best = r8; bd = 8; }
+      if (best > room) best = room;
+      const uint32_t p = t.begin + i;
+      if (best < 8u && p + 3u < chunk_bytes) {  // a farther candidate is only worth a look when the near ones are short
+        const uint32_t c = table[deflate_hash4(deflate_load4(in, p))];
+        if (c < p) {
+          const uint32_t l = deflate_match_len(in, c, p, room < 258u ? room : 258u);
+          const uint32_t d = p - c;
+          // A far distance costs up to 11 extra bits more than a near one: it has to beat the near
+          // match here by two bytes, must not be a short match far away, and -- lazy evaluation --
+          // must beat what a literal now and the near match one byte later would cover.
+          uint32_t next = 0;
+          if (i + 1u < n) {
+            const uint32_t q1 = deflate_run(t.eq[0], i + 1u), q2 = deflate_run(t.eq[1], i + 1u), q4 = deflate_run(t.eq[2], i + 1u), q8 = deflate_run(t.eq[3], i + 1u);
+            next = q1 > q2 ? q1 : q2;
+            next = q4 > next ? q4 : next;
+            next = q8 > next ? q8 : next;
+          }
+          const uint32_t need = d > 4096u ? 6u : (d > 256u ? 5u : (d > 32u ? 4u : 3u));
+          if (l > best + 1u && l >= need && l > next + 2u) { best = l; bd = d; }
+        }
+      }
+      if (best > 258u) best = 258u;
+    }
+    starts |= 1ull << i;
+    if (best >= 3u) {
+      matches |= 1ull << i;
+      const uint32_t p = t.begin + i;
+      tok[p] = static_cast<uint16_t>(bd);
+      tok[p + 1] = static_cast<uint16_t>(best);
+      uint32_t sym, eb, ev, dc, deb, dev;
+      deflate_len_symbol(best, &sym, &eb, &ev);
+      deflate_dist_symbol(bd, &dc, &deb, &dev);
+      add(sym, kDeflateLitSyms + dc);
+      i += best;
     } else {
-      bits += deflate_literal_bits(in[deflate_at(p)]);
-      cand[p] = 0;
-      p += 1;
+      add(static_cast<uint32_t>(in[deflate_at(t.begin + i)]), 0xFFFFFFFFu);
+      i += 1;
     }
   }
-  return bits;
+  t.is_start = starts;
+  t.is_match = matches;
 }
-// Emit the tokens deflate_parse left behind, starting at bit `bitpos`.
-TB200_HD void deflate_emit(const uint8_t* in, uint32_t begin, uint32_t end, const uint16_t* tokens, uint32_t* words, uint32_t bitpos) {
-  uint32_t pos = bitpos;
-  uint32_t p = begin;
-  while (p < end) {
-    const uint32_t dist = tokens[p];
-    if (dist != 0u) {
-      const uint32_t len = tokens[p + 1];
-      pos += deflate_emit_match(words, pos, len, dist);
-      p += len;
+
+// ---- code construction ---------------------------------------------------------------------------
+// Shannon length of a symbol: smallest l with count << l >= total, clamped to [1, maxl]
+TB200_HD uint32_t deflate_shannon_len(uint32_t count, uint32_t total, uint32_t maxl) {
+  const uint32_t q = (total + count - 1u) / count;  // ceil(total / count) >= 1
+  uint32_t l = 0;
+#ifdef __CUDA_ARCH__
+  l = q <= 1u ? 0u : 32u - static_cast<uint32_t>(__clz(q - 1u));
+#else
+  while ((1u << l) < q) ++l;
+#endif
+  return l < 1u ? 1u : (l > maxl ? maxl : l);
+}
+// Make the length histogram bl[1..maxl] describe a COMPLETE prefix code (Kraft sum exactly 1):
+// demote from the longest lengths while over-subscribed (only after clamping), then promote
+// the largest steps that still fit.  nsym = symbols in use (>= 2).
+TB200_HD void deflate_complete_code(uint32_t* bl, uint32_t maxl) {
+  uint32_t S = 0;
+  const uint32_t T = 1u << maxl;
+  for (uint32_t k = 1; k <= maxl; ++k) S += bl[k] << (maxl - k);
+  for (uint32_t k = maxl - 1u; k >= 1u && S > T; --k) {
+    while (S > T && bl[k] > 0u) {
+      bl[k] -= 1u;
+      bl[k + 1u] += 1u;
+      S -= 1u << (maxl - k - 1u);
+    }
+  }
+  uint32_t gap = T - S;
+  for (int pass = 0; pass < 16 && gap != 0u; ++pass) {
+    for (uint32_t k = 2; k <= maxl; ++k) {
+      const uint32_t step = 1u << (maxl - k);
+      uint32_t take = gap / step;
+      if (take > bl[k]) take = bl[k];
+      bl[k] -= take;
+      bl[k - 1u] += take;
+      gap -= take * step;
+    }
+  }
+}
+// canonical first codes per length (RFC 1951 3.2.2)
+TB200_HD void deflate_next_codes(const uint32_t* bl, uint32_t maxl, uint32_t* next) {
+  uint32_t code = 0;
+  next[0] = 0;
+  for (uint32_t k = 1; k <= maxl; ++k) {
+    code = (code + (k == 1u ? 0u : bl[k - 1u])) << 1;
+    next[k] = code;
+  }
+}
+
+// order in which the code-length code's own lengths are sent (RFC 1951 3.2.7)
+TB200_HD uint32_t deflate_cl_order(uint32_t i) {
+  const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  return order[i];
+}
+
+// Run-length form of the code-length sequence lens[0..n) (RFC 1951 3.2.7): entries (symbol 0..18,
+// extra value); returns the entry count.  One thread.
+TB200_HD uint32_t deflate_rle_lengths(const uint8_t* lens, uint32_t n, uint8_t* sym, uint8_t* extra) {
+  uint32_t out = 0, i = 0;
+  while (i < n) {
+    const uint32_t v = lens[i];
+    uint32_t run = 1;
+    while (i + run < n && lens[i + run] == v) ++run;
+    if (v == 0u) {
+      uint32_t left = run;
+      while (left >= 11u) {
+        const uint32_t r = left > 138u ? 138u : left;
+        sym[out] = 18; extra[out] = static_cast<uint8_t>(r - 11u); ++out;
+        left -= r;
+      }
+      if (left >= 3u) { sym[out] = 17; extra[out] = static_cast<uint8_t>(left - 3u); ++out; left = 0; }
+      while (left > 0u) { sym[out] = 0; extra[out] = 0; ++out; --left; }
     } else {
-      pos += deflate_emit_literal(words, pos, in[deflate_at(p)]);
-      p += 1;
+      sym[out] = static_cast<uint8_t>(v); extra[out] = 0; ++out;
+      uint32_t left = run - 1u;
+      while (left >= 3u) {
+        const uint32_t r = left > 6u ? 6u : left;
+        sym[out] = 16; extra[out] = static_cast<uint8_t>(r - 3u); ++out;
+        left -= r;
+      }
+      while (left > 0u) { sym[out] = static_cast<uint8_t>(v); extra[out] = 0; ++out; --left; }
+    }
+    i += run;
+  }
+  return out;
+}
+TB200_HD uint32_t deflate_cl_extra_bits(uint32_t sym) { return sym == 16u ? 2u : (sym == 17u ? 3u : (sym == 18u ? 7u : 0u)); }
+
+// ---- token walks ---------------------------------------------------------------------------------
+// bits of the thread's sub-block under the dynamic code (length tables) and under the fixed code
+TB200_HD void deflate_count(const uint8_t* in, const DeflateThread& t, const uint16_t* tok, const uint8_t* lit_len, const uint8_t* dist_len,
+                            uint32_t* dyn_bits, uint32_t* fix_bits) {
+  uint32_t dyn = 0, fix = 0;
+  uint64_t s = t.is_start;
+  while (s != 0ull) {
+    const uint32_t i = deflate_ctz64(s);
+    s &= s - 1ull;
+    const uint32_t p = t.begin + i;
+    if ((t.is_match >> i) & 1ull) {
+      const uint32_t dist = tok[p], len = tok[p + 1];
+      dyn += deflate_match_cost(lit_len, dist_len, len, dist);
+      fix += deflate_fixed_match_bits(len, dist);
+    } else {
+      const uint32_t b = in[deflate_at(p)];
+      dyn += lit_len[b];
+      fix += deflate_fixed_litlen_bits(b);
+    }
+  }
+  *dyn_bits = dyn;
+  *fix_bits = fix;
+}
+// emit the sub-block's tokens from bit `bitpos`; dynamic: reversed codes + lengths from the tables,
+// fixed (lit_code == nullptr): RFC 1951 3.2.6
+TB200_HD void deflate_emit(const uint8_t* in, const DeflateThread& t, const uint16_t* tok, const uint16_t* lit_code, const uint8_t* lit_len,
+                           const uint16_t* dist_code, const uint8_t* dist_len, uint32_t* words, uint32_t bitpos) {
+  uint32_t pos = bitpos;
+  uint64_t s = t.is_start;
+  while (s != 0ull) {
+    const uint32_t i = deflate_ctz64(s);
+    s &= s - 1ull;
+    const uint32_t p = t.begin + i;
+    if ((t.is_match >> i) & 1ull) {
+      const uint32_t dist = tok[p], len = tok[p + 1];
+      uint32_t sym, eb, ev, dc, deb, dev;
+      deflate_len_symbol(len, &sym, &eb, &ev);
+      deflate_dist_symbol(dist, &dc, &deb, &dev);
+      if (lit_code != nullptr) {
+        // code, extra bits, distance code, extra bits: at most 15 + 5 + 15 + 13 = 48 bits, two puts
+        deflate_put(words, pos, static_cast<uint32_t>(lit_code[sym]) | (ev << lit_len[sym]), lit_len[sym] + eb);
+        pos += lit_len[sym] + eb;
+        deflate_put(words, pos, static_cast<uint32_t>(dist_code[dc]) | (dev << dist_len[dc]), dist_len[dc] + deb);
+        pos += dist_len[dc] + deb;
+      } else {
+        uint32_t code, nb;
+        deflate_litlen_code(sym, &code, &nb);
+        deflate_put(words, pos, deflate_reverse(code, nb) | (ev << nb), nb + eb);
+        pos += nb + eb;
+        deflate_put(words, pos, deflate_reverse(dc, 5) | (dev << 5), 5u + deb);
+        pos += 5u + deb;
+      }
+    } else {
+      const uint32_t b = in[deflate_at(p)];
+      if (lit_code != nullptr) {
+        deflate_put(words, pos, lit_code[b], lit_len[b]);
+        pos += lit_len[b];
+      } else {
+        uint32_t code, nb;
+        deflate_litlen_code(b, &code, &nb);
+        deflate_put(words, pos, deflate_reverse(code, nb), nb);
+        pos += nb;
+      }
     }
   }
 }

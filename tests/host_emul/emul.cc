@@ -85,10 +85,11 @@ uint32_t emul_scale_f16_bits(uint32_t px, uint32_t scaling, int c, int ch) {
 uint32_t emul_f32_to_f16(uint32_t bits) { return f32_to_f16_bits(bits_f32(bits)); }
 uint32_t emul_f16_to_f32(uint32_t h) { return f32_bits(f16_bits_to_f32(static_cast<uint16_t>(h))); }
 
-// The device deflate encoder's pipeline, sequentially: chunk -> candidates in rounds of
-// kDeflateThreads -> two-pass parse per sub-block -> stored fallback -> checksums -> container.
-// Orchestration mirrors deflate.cu; every bit-level routine is the shared deflate.cuh code.
-uint64_t emul_deflate(const uint8_t* src, uint64_t nbytes, uint32_t gzip, uint8_t* dst) {
+// The device deflate encoder's pipeline, sequentially: the phases of deflate_chunk_kernel with a
+// loop over the 128 threads where the kernel has a barrier.  Orchestration mirrors deflate.cu; every
+// bit-level routine, the parse, the code construction and the token walks are the shared deflate.cuh
+// code.  modes[0..2] (optional) count the chunks that ended up stored / fixed / dynamic.
+uint64_t emul_deflate_modes(const uint8_t* src, uint64_t nbytes, uint32_t gzip, uint8_t* dst, uint32_t* modes) {
   uint64_t out = 0;
   if (gzip) {
     const uint8_t h[10] = {0x1F, 0x8B, 0x08, 0x00, 0, 0, 0, 0, 0x00, 0xFF};
@@ -100,37 +101,189 @@ uint64_t emul_deflate(const uint8_t* src, uint64_t nbytes, uint32_t gzip, uint8_
     out = 2;
   }
   uint32_t A = 0, B = 0, crc = 0;
+  constexpr int NS = kDeflateLitSyms + kDeflateDistSyms;
   std::vector<uint8_t> in(kDeflateInBytes);
-  std::vector<uint16_t> cand(kDeflateChunk), table(1 << kDeflateHashBits);
-  std::vector<uint32_t> words(kDeflateOutWords);
+  std::vector<uint16_t> tok(kDeflateChunk);
+  std::vector<uint32_t> table(1 << kDeflateHashBits), words(kDeflateOutWords);
+  std::vector<DeflateThread> th(kDeflateThreads);
   for (uint64_t base = 0; base < nbytes; base += kDeflateChunk) {
     const uint32_t n = static_cast<uint32_t>(nbytes - base < static_cast<uint64_t>(kDeflateChunk) ? nbytes - base : kDeflateChunk);
-    for (uint32_t i = 0; i < n; ++i) in[deflate_at(i)] = src[base + i];
-    std::fill(table.begin(), table.end(), static_cast<uint16_t>(kDeflateNoCand));
-    std::fill(words.begin(), words.end(), 0u);
-    for (uint32_t r0 = 0; r0 < n; r0 += kDeflateThreads) {
-      for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads) && r0 + t < n; ++t) {
-        const uint32_t p = r0 + t;
-        cand[p] = p + 3 < n ? table[deflate_hash(in.data(), p)] : static_cast<uint16_t>(kDeflateNoCand);
+    uint32_t* inw = reinterpret_cast<uint32_t*>(in.data());
+    std::fill(in.begin(), in.end(), 0);
+    // load
+    for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads); ++t) {
+      DeflateThread& T = th[t];
+      T.begin = t * kDeflateSub;
+      T.end = T.begin < n ? (T.begin + kDeflateSub < n ? T.begin + kDeflateSub : n) : T.begin;
+      for (int k = 0; k < 16; ++k) {
+        uint32_t v = 0;
+        for (uint32_t b = 0; b < 4u; ++b) {
+          const uint32_t p = T.begin + 4u * k + b;
+          if (p < n) v |= static_cast<uint32_t>(src[base + p]) << (8u * b);
+        }
+        T.w[2 + k] = v;
+        inw[17u * t + k] = v;
       }
-      for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads) && r0 + t + 3 < n; ++t) table[deflate_hash(in.data(), r0 + t)] = static_cast<uint16_t>(r0 + t);
     }
-    uint32_t off[kDeflateThreads], total = 3;
+    for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads); ++t) inw[17u * t + 16u] = t + 1 < static_cast<uint32_t>(kDeflateThreads) ? th[t + 1].w[2] : 0u;
+    for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads); ++t) {
+      th[t].w[0] = t > 0 ? inw[17u * (t - 1u) + 14u] : 0u;
+      th[t].w[1] = t > 0 ? inw[17u * (t - 1u) + 15u] : 0u;
+      th[t].w[18] = inw[17u * t + 16u];
+    }
+    // checksums
     uint32_t chunk_crc = 0;
     for (int t = 0; t < kDeflateThreads; ++t) {
-      const uint32_t b0 = t * kDeflateSub;
-      const uint32_t e0 = b0 < n ? (b0 + kDeflateSub < n ? b0 + kDeflateSub : n) : b0;
-      off[t] = total;
-      if (e0 > b0) total += deflate_parse(in.data(), b0, e0, cand.data());
       uint32_t a, b;
-      adler_piece(in.data() + deflate_at(b0), e0 - b0, &a, &b);
-      adler_append(&A, &B, a, b, e0 - b0);
-      chunk_crc = crc32_concat_raw(chunk_crc, crc32_raw(0u, in.data() + deflate_at(b0), e0 - b0), e0 - b0);
+      adler_piece(in.data() + deflate_at(th[t].begin), th[t].end - th[t].begin, &a, &b);
+      adler_append(&A, &B, a, b, th[t].end - th[t].begin);
+      chunk_crc = crc32_concat_raw(chunk_crc, crc32_raw(0u, in.data() + deflate_at(th[t].begin), th[t].end - th[t].begin), th[t].end - th[t].begin);
     }
     crc = crc32_concat_raw(crc, chunk_crc, n);
-    const uint32_t flush_at = (total + 7 + 3 + 7) >> 3;
-    const uint32_t comp = flush_at + 4;
-    if (comp >= n + 5) {
+    // masks + first-occurrence table
+    std::fill(table.begin(), table.end(), kDeflateNoCand);
+    for (int t = 0; t < kDeflateThreads; ++t) {
+      deflate_masks(th[t]);
+      for (uint32_t i = 0; i < 64u; ++i) {
+        const uint32_t p = th[t].begin + i;
+        if (p + 3u < n) {
+          const uint32_t h = deflate_hash4(deflate_word_at(th[t], i));
+          if (p < table[h]) table[h] = p;
+        }
+      }
+    }
+    // parse + histograms
+    uint32_t hist[NS] = {0}, ntok = 0, nmatch = 0;
+    for (int t = 0; t < kDeflateThreads; ++t) {
+      if (th[t].end > th[t].begin) {
+        deflate_parse(in.data(), th[t], table.data(), tok.data(), n, [&](uint32_t a, uint32_t b) {
+          hist[a] += 1u;
+          if (b != 0xFFFFFFFFu) hist[b] += 1u;
+        });
+        ntok += static_cast<uint32_t>(__builtin_popcountll(th[t].is_start));
+        nmatch += static_cast<uint32_t>(__builtin_popcountll(th[t].is_match));
+      } else {
+        th[t].is_start = th[t].is_match = 0;
+      }
+    }
+    hist[256] = 1;
+    // codes: Shannon classes, completed histogram, lengths by (class, index), canonical codes
+    uint8_t len_tab[NS];
+    uint16_t code_tab[NS];
+    uint32_t cls[NS], bl[2][16] = {{0}}, bl0[2][16], next_code[2][16];
+    for (int s2 = 0; s2 < NS; ++s2) {
+      const int a = s2 < kDeflateLitSyms ? 0 : 1;
+      cls[s2] = hist[s2] != 0u ? deflate_shannon_len(hist[s2], a == 0 ? ntok + 1u : nmatch, 15u) : 0u;
+      if (cls[s2]) bl[a][cls[s2]] += 1u;
+    }
+    memcpy(bl0, bl, sizeof(bl));
+    deflate_complete_code(bl[0], 15u);
+    {
+      uint32_t used = 0;
+      for (int k = 1; k <= 15; ++k) used += bl[1][k];
+      if (used >= 2u) deflate_complete_code(bl[1], 15u);
+    }
+    for (int s2 = 0; s2 < NS; ++s2) {
+      len_tab[s2] = 0;
+      if (cls[s2] == 0u) continue;
+      const int a = s2 < kDeflateLitSyms ? 0 : 1;
+      uint32_t pos = 0;
+      for (int j = a == 0 ? 0 : kDeflateLitSyms; j < s2; ++j) pos += cls[j] == cls[s2] ? 1u : 0u;
+      for (uint32_t k = 1; k < cls[s2]; ++k) pos += bl0[a][k];
+      uint32_t k = 1, cum = bl[a][1];
+      while (pos >= cum && k < 15u) {
+        ++k;
+        cum += bl[a][k];
+      }
+      len_tab[s2] = static_cast<uint8_t>(k);
+    }
+    deflate_next_codes(bl[0], 15u, next_code[0]);
+    deflate_next_codes(bl[1], 15u, next_code[1]);
+    for (int s2 = 0; s2 < NS; ++s2) {
+      code_tab[s2] = 0;
+      if (len_tab[s2] == 0) continue;
+      const int a = s2 < kDeflateLitSyms ? 0 : 1;
+      uint32_t idx = 0;
+      for (int j = a == 0 ? 0 : kDeflateLitSyms; j < s2; ++j) idx += len_tab[j] == len_tab[s2] ? 1u : 0u;
+      code_tab[s2] = static_cast<uint16_t>(deflate_reverse(next_code[a][len_tab[s2]] + idx, len_tab[s2]));
+    }
+    // header (thread 0 of the kernel)
+    uint8_t seq[kDeflateHdrMax], hdr_sym[kDeflateHdrMax + 8], hdr_extra[kDeflateHdrMax + 8];
+    uint32_t cl_len[19], cl_code[19];
+    uint32_t nlit = 286, ndist = 30;
+    while (nlit > 257u && len_tab[nlit - 1u] == 0u) --nlit;
+    while (ndist > 1u && len_tab[kDeflateLitSyms + ndist - 1u] == 0u) --ndist;
+    for (uint32_t i = 0; i < nlit; ++i) seq[i] = len_tab[i];
+    for (uint32_t i = 0; i < ndist; ++i) seq[nlit + i] = len_tab[kDeflateLitSyms + i];
+    const uint32_t ne = deflate_rle_lengths(seq, nlit + ndist, hdr_sym, hdr_extra);
+    uint32_t cnt[19] = {0}, lbl[8] = {0}, lnext[8], ord[19];
+    for (uint32_t e = 0; e < ne; ++e) cnt[hdr_sym[e]] += 1u;
+    uint32_t used = 0;
+    for (int i = 0; i < 19; ++i) {
+      cl_len[i] = cnt[i] != 0u ? deflate_shannon_len(cnt[i], ne, 7u) : 0u;
+      if (cnt[i] != 0u) {
+        lbl[cl_len[i]] += 1u;
+        ++used;
+      }
+    }
+    if (used == 1u) {
+      for (int i = 0; i < 19; ++i) {
+        if (cnt[i] == 0u) {
+          cl_len[i] = 1;
+          lbl[1] += 1u;
+          break;
+        }
+      }
+    }
+    uint32_t no = 0;
+    for (uint32_t k = 1; k <= 7u; ++k) {
+      for (uint32_t i = 0; i < 19u; ++i) {
+        if (cl_len[i] == k) ord[no++] = i;
+      }
+    }
+    deflate_complete_code(lbl, 7u);
+    {
+      uint32_t k = 1, left = lbl[1];
+      for (uint32_t o = 0; o < no; ++o) {
+        while (left == 0u && k < 7u) {
+          ++k;
+          left = lbl[k];
+        }
+        cl_len[ord[o]] = k;
+        --left;
+      }
+    }
+    deflate_next_codes(lbl, 7u, lnext);
+    for (uint32_t i = 0; i < 19u; ++i) cl_code[i] = cl_len[i] != 0u ? deflate_reverse(lnext[cl_len[i]]++, cl_len[i]) : 0u;
+    uint32_t ncl = 19;
+    while (ncl > 4u && cl_len[deflate_cl_order(ncl - 1u)] == 0u) --ncl;
+    uint32_t hdr_bits = 3u + 5u + 5u + 4u + 3u * ncl;
+    for (uint32_t e = 0; e < ne; ++e) hdr_bits += cl_len[hdr_sym[e]] + deflate_cl_extra_bits(hdr_sym[e]);
+    // counts, mode, offsets
+    uint32_t sub_dyn[kDeflateThreads], sub_fix[kDeflateThreads], sub_off[kDeflateThreads];
+    uint32_t dyn = hdr_bits, fix = 3u;
+    for (int t = 0; t < kDeflateThreads; ++t) {
+      sub_dyn[t] = sub_fix[t] = 0;
+      if (th[t].end > th[t].begin) deflate_count(in.data(), th[t], tok.data(), len_tab, len_tab + kDeflateLitSyms, &sub_dyn[t], &sub_fix[t]);
+      dyn += sub_dyn[t];
+      fix += sub_fix[t];
+    }
+    dyn += len_tab[256];
+    fix += 7u;
+    const uint32_t best = dyn < fix ? dyn : fix;
+    const uint32_t comp_bytes = ((best + 3u + 7u) >> 3) + 4u;
+    const uint32_t mode = comp_bytes >= n + 5u ? 0u : (dyn < fix ? 2u : 1u);
+    if (modes != nullptr) {
+      modes[mode] += 1u;
+      if (mode == 2u) {  // diagnostics: header bits, body bits, tokens, matches of the dynamic chunks
+        modes[3] += hdr_bits;
+        modes[4] += dyn - hdr_bits;
+        modes[5] += ntok;
+        modes[6] += nmatch;
+        modes[7] += ne;
+      }
+    }
+    if (mode == 0u) {
       dst[out] = 0;
       dst[out + 1] = static_cast<uint8_t>(n & 0xFF);
       dst[out + 2] = static_cast<uint8_t>(n >> 8);
@@ -138,17 +291,44 @@ uint64_t emul_deflate(const uint8_t* src, uint64_t nbytes, uint32_t gzip, uint8_
       dst[out + 4] = static_cast<uint8_t>((~n >> 8) & 0xFF);
       for (uint32_t i = 0; i < n; ++i) dst[out + 5 + i] = in[deflate_at(i)];
       out += n + 5;
+      continue;
+    }
+    std::fill(words.begin(), words.end(), 0u);
+    uint32_t off = mode == 2u ? hdr_bits : 3u;
+    for (int t = 0; t < kDeflateThreads; ++t) {
+      sub_off[t] = off;
+      off += mode == 2u ? sub_dyn[t] : sub_fix[t];
+    }
+    const uint32_t total_bits = off;
+    if (mode == 2u) {
+      deflate_put(words.data(), 0, 4u, 3);
+      deflate_put(words.data(), 3, nlit - 257u, 5);
+      deflate_put(words.data(), 8, ndist - 1u, 5);
+      deflate_put(words.data(), 13, ncl - 4u, 4);
+      for (uint32_t i = 0; i < ncl; ++i) deflate_put(words.data(), 17u + 3u * i, cl_len[deflate_cl_order(i)], 3);
+      uint32_t pos = 17u + 3u * ncl;
+      for (uint32_t e = 0; e < ne; ++e) {
+        const uint32_t sy = hdr_sym[e], l = cl_len[sy], xb = deflate_cl_extra_bits(sy);
+        deflate_put(words.data(), pos, cl_code[sy] | (static_cast<uint32_t>(hdr_extra[e]) << l), l + xb);
+        pos += l + xb;
+      }
+      for (int t = 0; t < kDeflateThreads; ++t) {
+        if (th[t].end > th[t].begin) {
+          deflate_emit(in.data(), th[t], tok.data(), code_tab, len_tab, code_tab + kDeflateLitSyms, len_tab + kDeflateLitSyms, words.data(), sub_off[t]);
+        }
+      }
+      deflate_put(words.data(), total_bits, code_tab[256], len_tab[256]);
     } else {
       deflate_put(words.data(), 0, 2u, 3);
       for (int t = 0; t < kDeflateThreads; ++t) {
-        const uint32_t b0 = t * kDeflateSub;
-        const uint32_t e0 = b0 < n ? (b0 + kDeflateSub < n ? b0 + kDeflateSub : n) : b0;
-        if (e0 > b0) deflate_emit(in.data(), b0, e0, cand.data(), words.data(), off[t]);
+        if (th[t].end > th[t].begin) deflate_emit(in.data(), th[t], tok.data(), nullptr, nullptr, nullptr, nullptr, words.data(), sub_off[t]);
       }
-      deflate_put(words.data(), (flush_at + 2) * 8, 0xFFFFu, 16);
-      memcpy(dst + out, words.data(), comp);
-      out += comp;
     }
+    const uint32_t eob_bits = mode == 2u ? len_tab[256] : 7u;
+    const uint32_t flush_at = (total_bits + eob_bits + 3u + 7u) >> 3;
+    deflate_put(words.data(), (flush_at + 2u) * 8u, 0xFFFFu, 16);
+    memcpy(dst + out, words.data(), flush_at + 4u);
+    out += flush_at + 4u;
   }
   const uint8_t fin[5] = {0x01, 0x00, 0x00, 0xFF, 0xFF};
   memcpy(dst + out, fin, 5);
@@ -168,6 +348,7 @@ uint64_t emul_deflate(const uint8_t* src, uint64_t nbytes, uint32_t gzip, uint8_
   }
   return out;
 }
+uint64_t emul_deflate(const uint8_t* src, uint64_t nbytes, uint32_t gzip, uint8_t* dst) { return emul_deflate_modes(src, nbytes, gzip, dst, nullptr); }
 
 // BYTES fill: group g of a fixed-length string tensor (what fill_segment_random<kBytes> stores)
 void emul_fill_bytes(uint8_t* dst, uint64_t nbytes, uint64_t seed, uint64_t stream, uint32_t len) {
@@ -196,4 +377,55 @@ int emul_resample_tables(int in_size, int out_size, int* bounds, int* coeffs, in
   }
   return ks;
 }
+}
+
+// diagnostics: the tokens of the first chunk (is_start / is_match / tok), out[3*k] = position, [3*k+1] = len (0 literal), [3*k+2] = dist
+extern "C" uint32_t emul_deflate_tokens(const uint8_t* src, uint32_t n, uint32_t* out, uint32_t cap) {
+  using namespace tb200;
+  std::vector<uint8_t> in(kDeflateInBytes, 0);
+  std::vector<uint16_t> tok(kDeflateChunk);
+  std::vector<uint32_t> table(1 << kDeflateHashBits, kDeflateNoCand);
+  std::vector<DeflateThread> th(kDeflateThreads);
+  uint32_t* inw = reinterpret_cast<uint32_t*>(in.data());
+  for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads); ++t) {
+    th[t].begin = t * kDeflateSub;
+    th[t].end = th[t].begin < n ? (th[t].begin + kDeflateSub < n ? th[t].begin + kDeflateSub : n) : th[t].begin;
+    for (int k = 0; k < 16; ++k) {
+      uint32_t v = 0;
+      for (uint32_t b = 0; b < 4u; ++b) {
+        const uint32_t p = th[t].begin + 4u * k + b;
+        if (p < n) v |= static_cast<uint32_t>(src[p]) << (8u * b);
+      }
+      th[t].w[2 + k] = v;
+      inw[17u * t + k] = v;
+    }
+  }
+  for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads); ++t) inw[17u * t + 16u] = t + 1 < static_cast<uint32_t>(kDeflateThreads) ? th[t + 1].w[2] : 0u;
+  for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads); ++t) {
+    th[t].w[0] = t > 0 ? inw[17u * (t - 1u) + 14u] : 0u;
+    th[t].w[1] = t > 0 ? inw[17u * (t - 1u) + 15u] : 0u;
+    th[t].w[18] = inw[17u * t + 16u];
+    deflate_masks(th[t]);
+    for (uint32_t i = 0; i < 64u; ++i) {
+      const uint32_t p = th[t].begin + i;
+      if (p + 3u < n) {
+        const uint32_t h = deflate_hash4(deflate_word_at(th[t], i));
+        if (p < table[h]) table[h] = p;
+      }
+    }
+  }
+  uint32_t k = 0;
+  for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads); ++t) {
+    if (th[t].end <= th[t].begin) continue;
+    deflate_parse(in.data(), th[t], table.data(), tok.data(), n, [&](uint32_t, uint32_t) {});
+    for (uint32_t i = 0; i < 64u; ++i) {
+      if (!((th[t].is_start >> i) & 1ull) || k >= cap) continue;
+      const uint32_t p = th[t].begin + i;
+      out[3 * k] = p;
+      out[3 * k + 1] = ((th[t].is_match >> i) & 1ull) ? tok[p + 1] : 0u;
+      out[3 * k + 2] = ((th[t].is_match >> i) & 1ull) ? tok[p] : 0u;
+      ++k;
+    }
+  }
+  return k;
 }

@@ -22,8 +22,8 @@ LIB = os.path.join(HERE, "host_emul", "libemul.so")
 def emul():
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
-    hdr = os.path.join(HERE, "..", "client_b200", "csrc", "philox.cuh")
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(HERE, "..", "client_b200", "csrc", h) for h in ("philox.cuh", "deflate.cuh", "resample.h")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max([os.path.getmtime(SRC)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", LIB, SRC], check=True)
     L = ctypes.CDLL(LIB)
     for f in (L.emul_fill, L.emul_fill_hoisted):
@@ -154,6 +154,11 @@ def _deflate_inputs():
     yield "chunk + 1", bytes(range(256)) * 32 + b"x"
     yield "high bytes", bytes([200 + (i % 50) for i in range(30000)])
     yield "runs of 258+", b"".join(bytes([i]) * (300 + i) for i in range(60))
+    yield "int32 token ids", rng.integers(0, 128256, 4096 * 3, dtype=np.int32).tobytes()
+    yield "repeated int64 tokens", np.tile(rng.integers(0, 30522, 64, dtype=np.int64), 40).tobytes()
+    yield "two symbols", bytes([7, 9]) * 9000
+    yield "one symbol, no matches possible", b"ab"
+    yield "json header + tensor", b'{"inputs":[{"name":"input_ids","shape":[1,384],"datatype":"INT64","parameters":{"binary_data_size":3072}}]}' + rng.integers(0, 30522, 384, dtype=np.int64).tobytes()
 
 
 @pytest.mark.parametrize("gzip_format", [0, 1])
@@ -175,3 +180,25 @@ def test_device_deflate_logic_round_trips_through_zlib(emul, gzip_format):
         assert back == data, label
         if label in ("zeros 100k", "text", "int64 token ids", "runs of 258+"):
             assert n < len(data) * 0.6, (label, n, len(data))
+
+
+def test_dynamic_huffman_reaches_zlib_level_6_on_token_ids(emul):
+    """with a code per chunk the encoder is within 10 % of zlib level 6 on token ids
+    (round 1, fixed codes: 0.44 against 0.34) -- measured here on the CPU emulation of the kernel's logic;
+    every chunk of such data ends up as a dynamic block."""
+    import zlib
+
+    emul.emul_deflate_modes.restype = ctypes.c_uint64
+    emul.emul_deflate_modes.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(3)
+    for label, data, slack in (("INT64 [0,30522)", rng.integers(0, 30522, 1 << 16, dtype=np.int64).tobytes(), 1.10),
+                               ("INT32 [0,128256)", rng.integers(0, 128256, 1 << 17, dtype=np.int32).tobytes(), 1.10),
+                               ("attention mask 0/1", rng.integers(0, 2, 1 << 16, dtype=np.int64).tobytes(), 2.0)):
+        src = np.frombuffer(data, dtype=np.uint8).copy()
+        dst = np.zeros(len(data) * 2, dtype=np.uint8)
+        modes = (ctypes.c_uint32 * 8)()
+        n = emul.emul_deflate_modes(src.ctypes.data, len(data), 0, dst.ctypes.data, modes)
+        assert zlib.decompress(dst[:n].tobytes()) == data
+        ratio, ref = n / len(data), len(zlib.compress(data, 6)) / len(data)
+        assert ratio <= ref * slack, (label, ratio, ref)
+        assert modes[2] == len(data) // 8192 and modes[0] == 0, (label, list(modes))
