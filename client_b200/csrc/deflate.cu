@@ -12,6 +12,95 @@ namespace tb200 {
 
 namespace {
 
+// CRC tables, computed by the host once per device (crc32_raw / crc32_xpow8n are host+device code):
+// the byte-at-a-time table and x^(8 * 64 * k) for k = 0..128 -- what a sub-block's CRC has to be
+// multiplied with to stand where it belongs in a full chunk (k sub-blocks follow it).
+struct DeflateTables {
+  uint32_t crc4[4][256];  // slicing-by-4: crc4[k][i] = CRC register after byte i and k zero bytes
+  uint32_t pw_after[kDeflateThreads + 1];
+  uint32_t pw_chunks[32];  // x^(8 * 8192 * 2^k): what moves a chunk's CRC past 2^k full chunks
+};
+__device__ DeflateTables g_deflate_tables;
+
+cudaError_t ensure_deflate_tables() {
+  static bool ready[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && ready[dev]) return cudaSuccess;
+  DeflateTables t;
+  for (uint32_t i = 0; i < 256u; ++i) {
+    const uint8_t b = static_cast<uint8_t>(i);
+    t.crc4[0][i] = crc32_raw(0u, &b, 1);
+  }
+  for (int k = 1; k < 4; ++k) {
+    for (uint32_t i = 0; i < 256u; ++i) t.crc4[k][i] = (t.crc4[k - 1][i] >> 8) ^ t.crc4[0][t.crc4[k - 1][i] & 0xFFu];
+  }
+  for (uint32_t k = 0; k <= static_cast<uint32_t>(kDeflateThreads); ++k) t.pw_after[k] = crc32_xpow8n(static_cast<uint64_t>(kDeflateSub) * k);
+  for (uint32_t k = 0; k < 32u; ++k) t.pw_chunks[k] = crc32_xpow8n(static_cast<uint64_t>(kDeflateChunk) << k);
+  e = cudaMemcpyToSymbol(g_deflate_tables, &t, sizeof(t));
+  if (e == cudaSuccess && dev >= 0 && dev < 64) ready[dev] = true;
+  return e;
+}
+
+// sum over the block (128 threads = 4 warps); every thread gets the result.  red: 4 words of scratch.
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* red) {
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  if ((threadIdx.x & 31u) == 0u) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const uint32_t total = red[0] + red[1] + red[2] + red[3];
+  __syncthreads();
+  return total;
+}
+__device__ __forceinline__ uint32_t block_xor(uint32_t v, uint32_t* red) {
+  for (int d = 16; d > 0; d >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  if ((threadIdx.x & 31u) == 0u) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const uint32_t total = red[0] ^ red[1] ^ red[2] ^ red[3];
+  __syncthreads();
+  return total;
+}
+// exclusive prefix sum over the block; *total = the block's sum
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* red, uint32_t* total) {
+  uint32_t incl = v;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= static_cast<uint32_t>(d)) incl += u;
+  }
+  if (lane == 31u) red[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0;
+  for (uint32_t w = 0; w < warp; ++w) before += red[w];
+  *total = red[0] + red[1] + red[2] + red[3];
+  __syncthreads();
+  return before + incl - v;
+}
+
+__device__ __forceinline__ uint64_t block_sum64(uint64_t v, unsigned long long* red) {
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  if ((threadIdx.x & 31u) == 0u) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const uint64_t total = red[0] + red[1] + red[2] + red[3];
+  __syncthreads();
+  return total;
+}
+__device__ __forceinline__ uint64_t block_exclusive_scan64(uint64_t v, unsigned long long* red, uint64_t* total) {
+  uint64_t incl = v;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= static_cast<uint32_t>(d)) incl += u;
+  }
+  if (lane == 31u) red[warp] = incl;
+  __syncthreads();
+  uint64_t before = 0;
+  for (uint32_t w = 0; w < warp; ++w) before += red[w];
+  *total = red[0] + red[1] + red[2] + red[3];
+  __syncthreads();
+  return before + incl - v;
+}
+
 // rank of this lane's symbol among the symbols of the same key with a smaller index, for symbols laid
 // out as s = tid + 128 * round (so a warp of a round holds 32 consecutive symbols = one "unit").
 // unit_cnt: [12 units][16 keys] scratch.  Phase A (this function) fills the unit counts and returns the
@@ -26,8 +115,10 @@ __device__ __forceinline__ uint32_t rank_in_unit(uint32_t key, uint32_t unit, ui
 
 }  // namespace
 
-__global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const uint8_t* __restrict__ src, uint64_t nbytes,
-                                                                         uint8_t* __restrict__ scratch, DeflateChunkMeta* __restrict__ meta) {
+// xr = x^(8 * bytes of the last chunk): with pw_chunks it moves a chunk's CRC to the end of the stream
+__global__ void __launch_bounds__(kDeflateThreads, 5) deflate_chunk_kernel(const uint8_t* __restrict__ src, uint64_t nbytes,
+                                                                         uint8_t* __restrict__ scratch, DeflateChunkMeta* __restrict__ meta,
+                                                                         uint32_t xr, uint32_t format) {
   __shared__ __align__(16) uint8_t in[kDeflateInBytes];  // skewed layout, deflate_at(); the gap word after a sub-block
                                                          // repeats the first word of the next one
   __shared__ uint32_t words[kDeflateOutWords];           // hash table during the parse, bit buffer afterwards
@@ -36,14 +127,12 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
   __shared__ uint8_t len_tab[kDeflateLitSyms + kDeflateDistSyms];
   __shared__ uint16_t code_tab[kDeflateLitSyms + kDeflateDistSyms];
   __shared__ uint32_t bl[2][16], bl0[2][16], next_code[2][16];
-  __shared__ uint32_t unit_cnt[12][16];
+  __shared__ uint32_t unit_cnt[12][16], unit_cnt2[12][16];  // symbols per (unit, class) and per (unit, final length); zeroed: a unit
+                                                            // only writes the keys it holds
   __shared__ uint8_t hdr_sym[kDeflateHdrMax + 8], hdr_extra[kDeflateHdrMax + 8];
   __shared__ uint32_t cl_len[19], cl_code[19];
-  __shared__ uint32_t sub_dyn[kDeflateThreads], sub_fix[kDeflateThreads], sub_off[kDeflateThreads];
-  __shared__ uint32_t crc_tbl[256];
-  __shared__ uint32_t crc_s[kDeflateThreads], len_s[kDeflateThreads], adl_a[kDeflateThreads], adl_b[kDeflateThreads];
-  __shared__ uint32_t pw[8];  // x^(8 * 64 * 2^k)
-  __shared__ uint32_t ntok_s, nmatch_s, hdr_n_s, hdr_bits_s, ncl_s, nlit_s, ndist_s, mode_s, total_bits_s, scan_s[4];
+  __shared__ unsigned long long red64_s[4];
+  __shared__ uint32_t ntok_s, nmatch_s, hdr_n_s, hdr_fixed_bits_s, ncl_s, nlit_s, ndist_s, red_s[4], cl_cnt[19], mult_s;
   uint32_t* table = words;
   static_assert((1 << kDeflateHashBits) <= kDeflateOutWords, "table aliases words");
 
@@ -83,33 +172,67 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
   for (int k = 0; k < 16; ++k) inw[17u * tid + k] = t.w[2 + k];
   if (tid > 0) inw[17u * (tid - 1u) + 16u] = t.w[2];  // look-ahead word of the previous sub-block
   if (tid == kDeflateThreads - 1) inw[17u * tid + 16u] = 0u;
-  for (uint32_t i = tid; i < 256u; i += kDeflateThreads) {
-    const uint8_t b = static_cast<uint8_t>(i);
-    crc_tbl[i] = crc32_raw(0u, &b, 1);
-  }
   for (uint32_t i = tid; i < (1u << kDeflateHashBits); i += kDeflateThreads) table[i] = kDeflateNoCand;
   for (uint32_t i = tid; i < static_cast<uint32_t>(kDeflateLitSyms + kDeflateDistSyms); i += kDeflateThreads) hist[i] = 0u;
   if (tid < 32) (&bl[0][0])[tid] = 0u;
-  if (tid < 8) pw[tid] = crc32_xpow8n(static_cast<uint64_t>(kDeflateSub) << tid);
+  for (uint32_t i = tid; i < 12u * 16u; i += kDeflateThreads) (&unit_cnt[0][0])[i] = (&unit_cnt2[0][0])[i] = 0u;
   if (tid == 0) {
     ntok_s = 0;
     nmatch_s = 0;
+    nlit_s = 257u;
+    ndist_s = 1u;
   }
+  if (tid < 19) cl_cnt[tid] = 0u;
   __syncthreads();
   t.w[0] = tid > 0 ? inw[17u * (tid - 1u) + 14u] : 0u;
   t.w[1] = tid > 0 ? inw[17u * (tid - 1u) + 15u] : 0u;
   t.w[18] = inw[17u * tid + 16u];
 
-  // ---- checksum pieces of the raw bytes (a sub-block is contiguous in the image)
+  // ---- checksum of the raw bytes: CRC-32 for gzip, Adler-32 for zlib, straight from the register words
+  //      (slicing-by-4 tables through the read-only cache; no byte loop through shared memory).  Both are
+  //      linear in the pieces: every thread moves its piece to the end of the chunk (crc * x^(8 * bytes
+  //      after it); b + bytes_after * a) and the block adds them up.
+  uint32_t chunk_crc = 0, chunk_a = 0, chunk_b = 0;
   {
-    uint32_t a = 0, b = 0;
-    adler_piece(in + deflate_at(t.begin), t.end - t.begin, &a, &b);
-    adl_a[tid] = a;
-    adl_b[tid] = b;
-    crc_s[tid] = crc32_raw_tbl(crc_tbl, 0u, in + deflate_at(t.begin), t.end - t.begin);
-    len_s[tid] = t.end - t.begin;
+    const uint32_t len = t.end - t.begin;
+    const uint32_t after = n - t.end;  // bytes of the chunk behind this sub-block
+    if (format == TB200_DEFLATE_GZIP) {
+      uint32_t c = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (4u * k + 4u <= len) {
+          const uint32_t x = c ^ t.w[2 + k];
+          c = __ldg(&g_deflate_tables.crc4[3][x & 0xFFu]) ^ __ldg(&g_deflate_tables.crc4[2][(x >> 8) & 0xFFu]) ^
+              __ldg(&g_deflate_tables.crc4[1][(x >> 16) & 0xFFu]) ^ __ldg(&g_deflate_tables.crc4[0][x >> 24]);
+        } else {
+          for (uint32_t j = 0; j < 4u; ++j) {
+            if (4u * k + j < len) c = __ldg(&g_deflate_tables.crc4[0][(c ^ (t.w[2 + k] >> (8u * j))) & 0xFFu]) ^ (c >> 8);
+          }
+        }
+      }
+      if (len != 0u && after != 0u) {
+        const uint32_t mult = (after & (kDeflateSub - 1u)) == 0u ? g_deflate_tables.pw_after[after >> kDeflateSubShift] : crc32_xpow8n(after);
+        c = crc32_mulmod(c, mult);
+      }
+      chunk_crc = block_xor(c, red_s);
+    } else {
+      uint32_t a = 0, b = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (4u * k + j < len) {
+            a += (t.w[2 + k] >> (8 * j)) & 0xFFu;  // <= 64 * 255: no overflow before the reduction
+            b += a;
+          }
+        }
+      }
+      b = (b % kAdlerMod + (after % kAdlerMod) * a) % kAdlerMod;  // after < 8192, a < 2^14: fits 32 bits
+      const uint64_t both = block_sum64((static_cast<uint64_t>(b) << 32) | a, red64_s);  // 128 * 65520 < 2^32 in each half
+      chunk_a = static_cast<uint32_t>(both) % kAdlerMod;
+      chunk_b = static_cast<uint32_t>(both >> 32) % kAdlerMod;
+    }
   }
-
   // ---- match finding: equality masks, first-occurrence hash table
   deflate_masks(t);
 #pragma unroll
@@ -119,7 +242,7 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
       const uint32_t p = t.begin + 4u * k + j;
       if (p + 3u < n) {
         const uint32_t v = j == 0 ? t.w[2 + k] : ((t.w[2 + k] >> (8 * j)) | (t.w[3 + k] << (32 - 8 * j)));
-        atomicMin(table + deflate_hash4(v), p);
+        if (deflate_hashable(v)) atomicMin(table + deflate_hash4(v), p);
       }
     }
   }
@@ -127,9 +250,9 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
 
   // ---- greedy parse, histograms
   if (t.end > t.begin) {
-    deflate_parse(in, t, table, tok, n, [&](uint32_t a, uint32_t b) {
-      atomicAdd(hist + a, 1u);
-      if (b != 0xFFFFFFFFu) atomicAdd(hist + b, 1u);
+    deflate_parse(in, t, table, tok, n, [&](uint32_t a, uint32_t b, uint32_t times) {
+      atomicAdd(hist + a, times);
+      if (b != 0xFFFFFFFFu) atomicAdd(hist + b, times);
     });
     atomicAdd(&ntok_s, static_cast<uint32_t>(__popcll(t.is_start)));
     atomicAdd(&nmatch_s, static_cast<uint32_t>(__popcll(t.is_match)));
@@ -187,12 +310,16 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
       flen[r] = k;
     }
     if (s < static_cast<uint32_t>(kDeflateLitSyms + kDeflateDistSyms)) len_tab[s] = static_cast<uint8_t>(flen[r]);
+    if (flen[r] != 0u) {  // HLIT / HDIST: one past the last symbol in use
+      if (s < static_cast<uint32_t>(kDeflateLitSyms)) atomicMax(&nlit_s, s + 1u);
+      else atomicMax(&ndist_s, s - static_cast<uint32_t>(kDeflateLitSyms) + 1u);
+    }
   }
-  __syncthreads();  // unit_cnt is reused below
+  __syncthreads();
   if (tid == 0) deflate_next_codes(bl[0], 15u, next_code[0]);
   if (tid == 32) deflate_next_codes(bl[1], 15u, next_code[1]);
 #pragma unroll
-  for (int r = 0; r < 3; ++r) unit_rank[r] = rank_in_unit(flen[r], 4u * r + (tid >> 5), unit_cnt);
+  for (int r = 0; r < 3; ++r) unit_rank[r] = rank_in_unit(flen[r], 4u * r + (tid >> 5), unit_cnt2);
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -201,7 +328,7 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
       const int a = s < static_cast<uint32_t>(kDeflateLitSyms) ? 0 : 1;
       const uint32_t unit = 4u * r + (tid >> 5), first_unit = a == 0 ? 0u : 9u;
       uint32_t idx = unit_rank[r];
-      for (uint32_t u = first_unit; u < unit; ++u) idx += unit_cnt[u][flen[r]];
+      for (uint32_t u = first_unit; u < unit; ++u) idx += unit_cnt2[u][flen[r]];
       code_tab[s] = static_cast<uint16_t>(deflate_reverse(next_code[a][flen[r]] + idx, flen[r]));
     } else if (s < static_cast<uint32_t>(kDeflateLitSyms + kDeflateDistSyms)) {
       code_tab[s] = 0;
@@ -209,119 +336,100 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
   }
   __syncthreads();
 
-  // ---- the header of a dynamic block: thread 0 forms the run-length entries and the code-length code
-  if (tid == 0) {
-    uint32_t nlit = 286, ndist = 30;
-    while (nlit > 257u && len_tab[nlit - 1u] == 0u) --nlit;
-    while (ndist > 1u && len_tab[kDeflateLitSyms + ndist - 1u] == 0u) --ndist;
-    // the two length sequences back to back (the distance lengths follow the literal ones directly)
-    uint8_t* seq = reinterpret_cast<uint8_t*>(unit_cnt);  // 768 bytes of scratch, dead now
-    for (uint32_t i = 0; i < nlit; ++i) seq[i] = len_tab[i];
-    for (uint32_t i = 0; i < ndist; ++i) seq[nlit + i] = len_tab[kDeflateLitSyms + i];
-    const uint32_t ne = deflate_rle_lengths(seq, nlit + ndist, hdr_sym, hdr_extra);
-    uint32_t cnt[19], lbl[8], lnext[8], ord[19];
-    for (int i = 0; i < 19; ++i) cnt[i] = 0;
-    for (uint32_t e = 0; e < ne; ++e) cnt[hdr_sym[e]] += 1u;
-    for (int k = 0; k < 8; ++k) lbl[k] = 0;
-    uint32_t used = 0;
-    for (int i = 0; i < 19; ++i) {
-      cl_len[i] = cnt[i] != 0u ? deflate_shannon_len(cnt[i], ne, 7u) : 0u;
-      if (cnt[i] != 0u) {
-        lbl[cl_len[i]] += 1u;
-        ++used;
-      }
+  // ---- the header of a dynamic block, by warp 0: block-wise run-length entries (one lane per segment of
+  //      16 code lengths), then the code-length code (one lane per symbol, ballots instead of loops)
+  if (tid < 32) {
+    const uint32_t lane = tid, lt = (1u << lane) - 1u;
+    const uint32_t nlit = nlit_s, ndist = ndist_s, N = nlit + ndist;
+    const uint32_t mine = deflate_segment_entries(len_tab, nlit, N, lane);
+    uint32_t incl = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= static_cast<uint32_t>(d)) incl += v;
     }
-    if (used == 1u) {  // a single symbol: give it one bit and a dummy partner (a complete code)
-      for (int i = 0; i < 19; ++i) {
-        if (cnt[i] == 0u) {
-          cl_len[i] = 1;
-          lbl[1] += 1u;
-          break;
-        }
-      }
+    const uint32_t ne = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    deflate_segment_write(len_tab, nlit, N, lane, mine, incl - mine, hdr_sym, hdr_extra, [&](uint32_t v) { atomicAdd(cl_cnt + v, 1u); });
+    __syncwarp();
+    const uint32_t cnt = lane < 19u ? cl_cnt[lane] : 0u;
+    const uint32_t used = __ballot_sync(0xFFFFFFFFu, cnt != 0u);
+    uint32_t c = cnt != 0u ? deflate_shannon_len(cnt, ne, 7u) : 0u;
+    if (__popc(used) == 1 && lane == static_cast<uint32_t>(__ffs(static_cast<int>(~used & 0x7FFFFu)) - 1)) c = 1u;  // a dummy partner
+    uint32_t lbl[8], lbl0[8], lnext[8];
+    lbl[0] = 0;
+#pragma unroll
+    for (int k = 1; k <= 7; ++k) lbl[k] = static_cast<uint32_t>(__popc(__ballot_sync(0xFFFFFFFFu, c == static_cast<uint32_t>(k))));
+#pragma unroll
+    for (int k = 0; k <= 7; ++k) lbl0[k] = lbl[k];
+    deflate_complete_code_t<7>(lbl);
+    uint32_t pos = static_cast<uint32_t>(__popc(__match_any_sync(0xFFFFFFFFu, c) & lt));
+#pragma unroll
+    for (int k = 1; k <= 7; ++k) pos += static_cast<uint32_t>(k) < c ? lbl0[k] : 0u;
+    uint32_t fl = 0, cum = 0;
+#pragma unroll
+    for (int k = 1; k <= 7; ++k) {
+      if (fl == 0u && pos < cum + lbl[k]) fl = static_cast<uint32_t>(k);
+      cum += lbl[k];
     }
-    // order (class, index), lengths by position in the completed histogram
-    uint32_t no = 0;
-    for (uint32_t k = 1; k <= 7u; ++k) {
-      for (uint32_t i = 0; i < 19u; ++i) {
-        if (cl_len[i] == k) ord[no++] = i;
-      }
-    }
-    deflate_complete_code(lbl, 7u);
-    {
-      uint32_t k = 1, left = lbl[1];
-      for (uint32_t o = 0; o < no; ++o) {
-        while (left == 0u && k < 7u) {
-          ++k;
-          left = lbl[k];
-        }
-        cl_len[ord[o]] = k;
-        --left;
-      }
-    }
+    if (c == 0u) fl = 0u;
     deflate_next_codes(lbl, 7u, lnext);
-    for (uint32_t i = 0; i < 19u; ++i) {
-      if (cl_len[i] != 0u) cl_code[i] = deflate_reverse(lnext[cl_len[i]]++, cl_len[i]);
-      else cl_code[i] = 0;
+    const uint32_t idx = static_cast<uint32_t>(__popc(__match_any_sync(0xFFFFFFFFu, fl) & lt));
+    uint32_t first = 0;
+#pragma unroll
+    for (int k = 1; k <= 7; ++k) first = fl == static_cast<uint32_t>(k) ? lnext[k] : first;
+    if (lane < 19u) {
+      cl_len[lane] = fl;
+      cl_code[lane] = fl != 0u ? deflate_reverse(first + idx, fl) : 0u;
     }
-    uint32_t ncl = 19;
-    while (ncl > 4u && cl_len[deflate_cl_order(ncl - 1u)] == 0u) --ncl;
-    uint32_t bits = 3u + 5u + 5u + 4u + 3u * ncl;
-    for (uint32_t e = 0; e < ne; ++e) bits += cl_len[hdr_sym[e]] + deflate_cl_extra_bits(hdr_sym[e]);
-    hdr_n_s = ne;
-    hdr_bits_s = bits;
-    ncl_s = ncl;
-    nlit_s = nlit;
-    ndist_s = ndist;
+    __syncwarp();
+    const uint32_t sent = __ballot_sync(0xFFFFFFFFu, lane < 19u && cl_len[deflate_cl_order(lane < 19u ? lane : 0u)] != 0u);
+    uint32_t ncl = 32u - static_cast<uint32_t>(__clz(sent | 0xFu));  // at least 4
+    if (lane == 0) {
+      hdr_n_s = ne;
+      hdr_fixed_bits_s = 17u + 3u * ncl;
+      ncl_s = ncl;
+    }
+  } else if (tid < 64) {
+    // warp 1: x^(8 * bytes behind this chunk in the stream) = xr * prod over the bits of (full chunks behind it)
+    const uint32_t lane = tid - 32u;
+    const uint64_t nchunks = (nbytes + kDeflateChunk - 1) / kDeflateChunk;
+    uint32_t f = 1u << 31;  // x^0
+    if (static_cast<uint64_t>(blockIdx.x) + 1u < nchunks) {
+      const uint64_t q = nchunks - 2u - blockIdx.x;
+      if ((q >> lane) & 1ull) f = g_deflate_tables.pw_chunks[lane];
+      if (lane == 0) f = crc32_mulmod(f, xr);
+    }
+    for (int d = 16; d > 0; d >>= 1) f = crc32_mulmod(f, __shfl_down_sync(0xFFFFFFFFu, f, d));
+    if (lane == 0) mult_s = f;
   }
 
-  // ---- bits per sub-block under both codes
-  {
-    uint32_t dyn = 0, fix = 0;
-    if (t.end > t.begin) deflate_count(in, t, tok, len_tab, len_tab + kDeflateLitSyms, &dyn, &fix);
-    sub_dyn[tid] = dyn;
-    sub_fix[tid] = fix;
-  }
-  // CRC tree: raw0(X || Y) = raw0(X) * x^(8|Y|) + raw0(Y)
-  for (uint32_t stride = 1, level = 0; stride < kDeflateThreads; stride <<= 1, ++level) {
-    __syncthreads();
-    if ((tid & (2 * stride - 1)) == 0) {
-      const uint32_t ly = len_s[tid + stride];
-      const uint32_t mult = ly == (static_cast<uint32_t>(kDeflateSub) << level) ? pw[level] : crc32_xpow8n(ly);
-      crc_s[tid] = crc32_mulmod(crc_s[tid], mult) ^ crc_s[tid + stride];
-      len_s[tid] += ly;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t dyn = hdr_bits_s, fix = 3u;
-    for (int i = 0; i < kDeflateThreads; ++i) {
-      dyn += sub_dyn[i];
-      fix += sub_fix[i];
-    }
-    dyn += len_tab[256];
-    fix += 7u;
-    // EOB, then the empty stored block: 3 header bits, pad to a byte, 00 00 FF FF
-    const uint32_t best = dyn < fix ? dyn : fix;
-    const uint32_t comp_bytes = ((best + 3u + 7u) >> 3) + 4u;
-    const uint32_t mode = comp_bytes >= n + 5u ? 0u : (dyn < fix ? 2u : 1u);
-    uint32_t off = mode == 2u ? hdr_bits_s : 3u;
-    for (int i = 0; i < kDeflateThreads; ++i) {
-      sub_off[i] = off;
-      off += mode == 2u ? sub_dyn[i] : sub_fix[i];
-    }
-    total_bits_s = off;  // position of the end-of-block code
-    mode_s = mode;
-  }
-  __syncthreads();
+  // ---- bits per sub-block under both codes, bits of the header entries, mode, offsets
+  uint32_t my_dyn = 0, my_fix = 0;
+  if (t.end > t.begin) deflate_count(in, t, tok, len_tab, len_tab + kDeflateLitSyms, &my_dyn, &my_fix);
+  __syncthreads();  // thread 0's header is complete
+  const uint32_t ne = hdr_n_s, ncl = ncl_s;
+  uint32_t my_hdr = 0;
+  for (uint32_t e = 3u * tid; e < 3u * tid + 3u && e < ne; ++e) my_hdr += cl_len[hdr_sym[e]] + deflate_cl_extra_bits(hdr_sym[e]);
+  // one scan for the three running sums: dynamic bits (< 2^20) | fixed bits << 20 | header bits << 40
+  uint64_t totals;
+  const uint64_t before = block_exclusive_scan64(static_cast<uint64_t>(my_dyn) | (static_cast<uint64_t>(my_fix) << 20) | (static_cast<uint64_t>(my_hdr) << 40),
+                                                 red64_s, &totals);
+  const uint32_t dyn_before = static_cast<uint32_t>(before) & 0xFFFFFu, fix_before = static_cast<uint32_t>(before >> 20) & 0xFFFFFu;
+  const uint32_t hdr_before = static_cast<uint32_t>(before >> 40);
+  const uint32_t dyn_body = static_cast<uint32_t>(totals) & 0xFFFFFu, fix_body = static_cast<uint32_t>(totals >> 20) & 0xFFFFFu;
+  const uint32_t hdr_entries_bits = static_cast<uint32_t>(totals >> 40);
+  const uint32_t hdr_bits = hdr_fixed_bits_s + hdr_entries_bits;
+  const uint32_t dyn_total = hdr_bits + dyn_body + len_tab[256], fix_total = 3u + fix_body + 7u;
+  // EOB, then the empty stored block: 3 header bits, pad to a byte, 00 00 FF FF
+  const uint32_t best_bits = dyn_total < fix_total ? dyn_total : fix_total;
+  const uint32_t mode = (((best_bits + 3u + 7u) >> 3) + 4u) >= n + 5u ? 0u : (dyn_total < fix_total ? 2u : 1u);
+  const uint32_t my_off = mode == 2u ? hdr_bits + dyn_before : 3u + fix_before;
+  const uint32_t eob_at = mode == 2u ? hdr_bits + dyn_body : 3u + fix_body;  // position of the end-of-block code
 
-  const uint32_t mode = mode_s;
   uint8_t* out = scratch + static_cast<size_t>(blockIdx.x) * kDeflateMaxChunkOut;
   uint32_t out_bytes = 0;
   if (mode != 0u) {
     if (mode == 2u) {
       // header: fixed part by thread 0, the entries by everyone (three consecutive entries per thread)
-      const uint32_t ne = hdr_n_s, ncl = ncl_s;
       if (tid == 0) {
         deflate_put(words, 0, 4u, 3);  // BFINAL = 0, BTYPE = 10
         deflate_put(words, 3, nlit_s - 257u, 5);
@@ -329,34 +437,22 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
         deflate_put(words, 13, ncl - 4u, 4);
         for (uint32_t i = 0; i < ncl; ++i) deflate_put(words, 17u + 3u * i, cl_len[deflate_cl_order(i)], 3);
       }
-      uint32_t mine = 0;
-      for (uint32_t e = 3u * tid; e < 3u * tid + 3u && e < ne; ++e) mine += cl_len[hdr_sym[e]] + deflate_cl_extra_bits(hdr_sym[e]);
-      // exclusive scan over the 128 threads
-      uint32_t incl = mine;
-      const uint32_t lane = tid & 31u;
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= static_cast<uint32_t>(d)) incl += v;
-      }
-      if (lane == 31u) scan_s[tid >> 5] = incl;
-      __syncthreads();
-      uint32_t pos = 17u + 3u * ncl + incl - mine;
-      for (uint32_t wq = 0; wq < (tid >> 5); ++wq) pos += scan_s[wq];
+      uint32_t pos = hdr_fixed_bits_s + hdr_before;
       for (uint32_t e = 3u * tid; e < 3u * tid + 3u && e < ne; ++e) {
-        const uint32_t s = hdr_sym[e], l = cl_len[s], xb = deflate_cl_extra_bits(s);
-        deflate_put(words, pos, cl_code[s] | (static_cast<uint32_t>(hdr_extra[e]) << l), l + xb);
+        const uint32_t sy = hdr_sym[e], l = cl_len[sy], xb = deflate_cl_extra_bits(sy);
+        deflate_put(words, pos, cl_code[sy] | (static_cast<uint32_t>(hdr_extra[e]) << l), l + xb);
         pos += l + xb;
       }
       if (t.end > t.begin) {
-        deflate_emit(in, t, tok, code_tab, len_tab, code_tab + kDeflateLitSyms, len_tab + kDeflateLitSyms, words, sub_off[tid]);
+        deflate_emit(in, t, tok, code_tab, len_tab, code_tab + kDeflateLitSyms, len_tab + kDeflateLitSyms, words, my_off);
       }
-      if (tid == 0) deflate_put(words, total_bits_s, code_tab[256], len_tab[256]);
+      if (tid == 0) deflate_put(words, eob_at, code_tab[256], len_tab[256]);
     } else {
       if (tid == 0) deflate_put(words, 0, 2u, 3);  // BFINAL = 0, BTYPE = 01; the fixed EOB is 7 zero bits
-      if (t.end > t.begin) deflate_emit(in, t, tok, nullptr, nullptr, nullptr, nullptr, words, sub_off[tid]);
+      if (t.end > t.begin) deflate_emit(in, t, tok, nullptr, nullptr, nullptr, nullptr, words, my_off);
     }
     const uint32_t eob_bits = mode == 2u ? len_tab[256] : 7u;
-    const uint32_t flush_at = (total_bits_s + eob_bits + 3u + 7u) >> 3;  // byte index of LEN
+    const uint32_t flush_at = (eob_at + eob_bits + 3u + 7u) >> 3;  // byte index of LEN
     out_bytes = flush_at + 4u;
     __syncthreads();
     if (tid == 0) deflate_put(words, (flush_at + 2u) * 8u, 0xFFFFu, 16);  // LEN = 0 is already there
@@ -375,53 +471,45 @@ __global__ void __launch_bounds__(kDeflateThreads) deflate_chunk_kernel(const ui
     out_bytes = n + 5u;
   }
   if (tid == 0) {
-    uint32_t A = 0, B = 0;
-    for (uint32_t i = 0; i < static_cast<uint32_t>(kDeflateThreads); ++i) {
-      const uint32_t b0 = i * kDeflateSub;
-      const uint32_t li = b0 < n ? (n - b0 < static_cast<uint32_t>(kDeflateSub) ? n - b0 : kDeflateSub) : 0u;
-      adler_append(&A, &B, adl_a[i], adl_b[i], li);
-    }
     DeflateChunkMeta m;
     m.out_bytes = out_bytes;
     m.in_bytes = n;
-    m.adler_a = A;
-    m.adler_b = B;
-    m.crc_raw0 = crc_s[0];
+    // both checksums as they count at the END OF THE STREAM: the finalize kernel only adds them up
+    const uint64_t after_s = nbytes - (base + n);
+    m.adler_a = chunk_a;
+    m.adler_b = static_cast<uint32_t>((chunk_b + (after_s % kAdlerMod) * chunk_a) % kAdlerMod);
+    m.crc_raw0 = after_s != 0ull ? crc32_mulmod(chunk_crc, mult_s) : chunk_crc;
     meta[blockIdx.x] = m;
   }
 }
 
-// One CTA: offsets of the chunks in the final stream, checksums of the whole input, container
-// header and trailer.  Threads own contiguous ranges of chunks.  Both checksums are linear in
-// the pieces, so each partial is moved to the end of the stream on its own
-// (crc * x^(8*bytes_after), b + bytes_after * a) and the results are summed -- no serial chain.
+// One CTA: offsets of the chunks in the final stream (a scan of their sizes), the checksums of the whole
+// input -- the chunk kernel already moved every chunk's piece to the end of the stream, so they only
+// have to be added up (xor for the CRC, modular sums for Adler) --, container header and trailer.
+// crc_init_term = 0xFFFFFFFF * x^(8 * nbytes): what the CRC register's initial value contributes (host).
 __global__ void __launch_bounds__(1024) deflate_finalize_kernel(DeflateChunkMeta* __restrict__ meta, uint32_t nchunks, uint64_t nbytes,
-                                                                uint32_t format, uint8_t* __restrict__ dst, uint64_t* __restrict__ out_size) {
+                                                                uint32_t format, uint8_t* __restrict__ dst, uint64_t* __restrict__ out_size,
+                                                                uint32_t crc_init_term) {
   __shared__ unsigned long long sz[1024];   // inclusive scan of output sizes
-  __shared__ unsigned long long ln[1024];   // inclusive scan of input lengths
   __shared__ uint32_t red[32 * 3];
   const uint32_t tid = threadIdx.x;
   const uint32_t per = (nchunks + 1023u) / 1024u;
   const uint32_t c0 = min(tid * per, nchunks), c1 = min(c0 + per, nchunks);
-  unsigned long long bytes = 0, len = 0;
-  uint32_t c = 0, A = 0, B = 0;
-  const uint32_t pw_chunk = crc32_xpow8n(kDeflateChunk);
+  unsigned long long bytes = 0;
+  uint32_t crc_part = 0, a_part = 0, b_part = 0;
   for (uint32_t i = c0; i < c1; ++i) {
     const DeflateChunkMeta m = meta[i];
     bytes += m.out_bytes;
-    c = crc32_mulmod(c, m.in_bytes == static_cast<uint32_t>(kDeflateChunk) ? pw_chunk : crc32_xpow8n(m.in_bytes)) ^ m.crc_raw0;
-    adler_append(&A, &B, m.adler_a, m.adler_b, m.in_bytes);
-    len += m.in_bytes;
+    crc_part ^= m.crc_raw0;
+    a_part = (a_part + m.adler_a) % kAdlerMod;
+    b_part = (b_part + m.adler_b) % kAdlerMod;
   }
   sz[tid] = bytes;
-  ln[tid] = len;
   __syncthreads();
-  for (uint32_t d = 1; d < 1024u; d <<= 1) {  // Hillis-Steele inclusive scans
+  for (uint32_t d = 1; d < 1024u; d <<= 1) {  // Hillis-Steele inclusive scan
     const unsigned long long s0 = tid >= d ? sz[tid - d] : 0ull;
-    const unsigned long long l0 = tid >= d ? ln[tid - d] : 0ull;
     __syncthreads();
     sz[tid] += s0;
-    ln[tid] += l0;
     __syncthreads();
   }
   {
@@ -432,12 +520,6 @@ __global__ void __launch_bounds__(1024) deflate_finalize_kernel(DeflateChunkMeta
       off += ob;
     }
   }
-  // move this thread's partial to the end of the stream
-  const unsigned long long after = nbytes - ln[tid];
-  uint32_t crc_part = len != 0 ? crc32_mulmod(c, crc32_xpow8n(after)) : 0u;
-  uint32_t a_part = A;
-  uint32_t b_part = static_cast<uint32_t>((B + (after % kAdlerMod) * A) % kAdlerMod);
-  // block reduction: xor for the CRC, modular sums for Adler
   for (int off = 16; off > 0; off >>= 1) {
     crc_part ^= __shfl_xor_sync(0xFFFFFFFFu, crc_part, off);
     a_part += __shfl_xor_sync(0xFFFFFFFFu, a_part, off);
@@ -475,8 +557,7 @@ __global__ void __launch_bounds__(1024) deflate_finalize_kernel(DeflateChunkMeta
     unsigned long long total = hdr + body + 5;
     if (format == TB200_DEFLATE_GZIP) {
       // register from init 0xFFFFFFFF over the whole stream, final xor
-      const uint32_t raw = crc32_mulmod(0xFFFFFFFFu, crc32_xpow8n(nbytes)) ^ crc_all;
-      const uint32_t v = raw ^ 0xFFFFFFFFu;
+      const uint32_t v = (crc_init_term ^ crc_all) ^ 0xFFFFFFFFu;
       const uint32_t isize = static_cast<uint32_t>(nbytes);
       for (int i = 0; i < 4; ++i) t[i] = static_cast<uint8_t>(v >> (8 * i));
       for (int i = 0; i < 4; ++i) t[4 + i] = static_cast<uint8_t>(isize >> (8 * i));
@@ -506,8 +587,14 @@ cudaError_t launch_deflate(const uint8_t* src, uint64_t nbytes, uint32_t format,
                            uint64_t* out_size, cudaStream_t s) {
   const uint64_t nchunks64 = (nbytes + kDeflateChunk - 1) / kDeflateChunk;
   const uint32_t nchunks = static_cast<uint32_t>(nchunks64);
-  if (nchunks > 0) deflate_chunk_kernel<<<nchunks, kDeflateThreads, 0, s>>>(src, nbytes, scratch, meta);
-  deflate_finalize_kernel<<<1, 1024, 0, s>>>(meta, nchunks, nbytes, format, dst, out_size);
+  const cudaError_t te = ensure_deflate_tables();
+  if (te != cudaSuccess) return te;
+  // host side of the checksum algebra: x^(8 * bytes of the last chunk) and the CRC's initial-value term
+  const uint64_t last = nbytes == 0 ? 0 : nbytes - static_cast<uint64_t>(nchunks - 1u) * kDeflateChunk;
+  const uint32_t xr = crc32_xpow8n(last);
+  const uint32_t crc_init_term = crc32_mulmod(0xFFFFFFFFu, crc32_xpow8n(nbytes));
+  if (nchunks > 0) deflate_chunk_kernel<<<nchunks, kDeflateThreads, 0, s>>>(src, nbytes, scratch, meta, xr, format);
+  deflate_finalize_kernel<<<1, 1024, 0, s>>>(meta, nchunks, nbytes, format, dst, out_size, crc_init_term);
   if (nchunks > 0) deflate_gather_kernel<<<nchunks, 256, 0, s>>>(scratch, meta, dst, format == TB200_DEFLATE_GZIP ? 10u : 2u);
   return cudaGetLastError();
 }

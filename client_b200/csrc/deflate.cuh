@@ -179,6 +179,9 @@ TB200_HD uint32_t deflate_word_at(const DeflateThread& t, uint32_t i) {
   return sh == 0u ? lo : ((lo >> sh) | (hi << (32u - sh)));
 }
 TB200_HD uint32_t deflate_hash4(uint32_t v) { return (v * 2654435761u) >> (32 - kDeflateHashBits); }
+// Windows of four equal bytes (runs of zeros above all) are what the distance-1 mask finds anyway; kept out
+// of the hash table they do not pile thousands of shared-memory atomics onto one bucket.
+TB200_HD bool deflate_hashable(uint32_t v) { return v != ((v << 8) | (v >> 24)); }
 // the 4 bytes at chunk position p from the skewed image: two aligned words of the sub-block (the gap word
 // behind a sub-block repeats the first word of the next one, so this works up to the sub-block's last byte)
 TB200_HD uint32_t deflate_load4(const uint8_t* in, uint32_t p) {
@@ -208,6 +211,9 @@ TB200_HD uint32_t deflate_match_len(const uint8_t* in, uint32_t a, uint32_t b, u
   return n;
 }
 
+// extra bits of a length symbol (257..285) / a distance code (0..29), RFC 1951 3.2.5
+TB200_HD uint32_t deflate_len_extra_bits(uint32_t sym) { return (sym < 265u || sym == 285u) ? 0u : (sym - 261u) >> 2; }
+TB200_HD uint32_t deflate_dist_extra_bits(uint32_t dc) { return dc < 4u ? 0u : (dc - 2u) >> 1; }
 // bits of a match token under a code given as length tables
 TB200_HD uint32_t deflate_match_cost(const uint8_t* lit_len, const uint8_t* dist_len, uint32_t len, uint32_t dist) {
   uint32_t sym, eb, ev, dc, deb, dev;
@@ -231,30 +237,39 @@ TB200_HD void deflate_parse(const uint8_t* in, DeflateThread& t, const uint32_t*
   uint64_t starts = 0, matches = 0;
   const uint32_t n = t.end - t.begin;
   uint32_t i = 0;
+  // typed tensors repeat the same (length, distance) pair element after element: count such repeats
+  // locally and update the shared histograms once per run, not once per token
+  uint32_t run_sym = 0xFFFFFFFFu, run_dsym = 0, run_n = 0;
   while (i < n) {
     const uint32_t room = n - i;
     uint32_t best = 0, bd = 0;
     if (room >= 3u) {
       // the periodic distances: longest run of equal bytes at distance d starting here; the
-      // shortest distance wins ties (cheapest distance code)
-      const uint32_t r1 = deflate_run(t.eq[0], i), r2 = deflate_run(t.eq[1], i), r4 = deflate_run(t.eq[2], i), r8 = deflate_run(t.eq[3], i);
-      best = r1;
-      bd = 1;
-      if (r2 > best) { best = r2; bd = 2; }
-      if (r4 > best) { best = r4; bd = 4; }
-      if (r8 > best) { best = r8; bd = 8; }
-      if (best > room) best = room;
+      // shortest distance wins ties (cheapest distance code).  Most positions of incompressible data
+      // match at none of them: one test of the united masks skips the four run counts.
+      if (((t.eq[0] | t.eq[1] | t.eq[2] | t.eq[3]) >> i) & 1ull) {
+        const uint32_t r1 = deflate_run(t.eq[0], i), r2 = deflate_run(t.eq[1], i), r4 = deflate_run(t.eq[2], i), r8 = deflate_run(t.eq[3], i);
+        best = r1;
+        bd = 1;
+        if (r2 > best) { best = r2; bd = 2; }
+        if (r4 > best) { best = r4; bd = 4; }
+        if (r8 > best) { best = r8; bd = 8; }
+        if (best > room) best = room;
+      }
       const uint32_t p = t.begin + i;
-      if (best < 8u && p + 3u < chunk_bytes) {  // a farther candidate is only worth a look when the near ones are short
-        const uint32_t c = table[deflate_hash4(deflate_load4(in, p))];
-        if (c < p) {
-          const uint32_t l = deflate_match_len(in, c, p, room < 258u ? room : 258u);
+      const uint32_t v4 = best < 8u && p + 3u < chunk_bytes ? deflate_load4(in, p) : 0u;
+      if (best < 8u && p + 3u < chunk_bytes && deflate_hashable(v4)) {  // a farther candidate is only worth a look when the near ones are short
+        const uint32_t c = table[deflate_hash4(v4)];
+        // most hits are hash collisions: one word compare rejects them before the byte loop
+        if (c < p && deflate_load4(in, c) == v4) {
+          const uint32_t cap = room < 258u ? room : 258u;
+          const uint32_t l = cap <= 4u ? cap : 4u + deflate_match_len(in, c + 4u, p + 4u, cap - 4u);
           const uint32_t d = p - c;
           // A far distance costs up to 11 extra bits more than a near one: it has to beat the near
           // match here by two bytes, must not be a short match far away, and -- lazy evaluation --
           // must beat what a literal now and the near match one byte later would cover.
           uint32_t next = 0;
-          if (i + 1u < n) {
+          if (i + 1u < n && (((t.eq[0] | t.eq[1] | t.eq[2] | t.eq[3]) >> (i + 1u)) & 1ull)) {
             const uint32_t q1 = deflate_run(t.eq[0], i + 1u), q2 = deflate_run(t.eq[1], i + 1u), q4 = deflate_run(t.eq[2], i + 1u), q8 = deflate_run(t.eq[3], i + 1u);
             next = q1 > q2 ? q1 : q2;
             next = q4 > next ? q4 : next;
@@ -270,18 +285,29 @@ TB200_HD void deflate_parse(const uint8_t* in, DeflateThread& t, const uint32_t*
     if (best >= 3u) {
       matches |= 1ull << i;
       const uint32_t p = t.begin + i;
-      tok[p] = static_cast<uint16_t>(bd);
-      tok[p + 1] = static_cast<uint16_t>(best);
       uint32_t sym, eb, ev, dc, deb, dev;
       deflate_len_symbol(best, &sym, &eb, &ev);
       deflate_dist_symbol(bd, &dc, &deb, &dev);
-      add(sym, kDeflateLitSyms + dc);
+      // the three positions a match covers at least hold what the later walks need, so that the
+      // symbols are computed once: [p] distance, [p + 1] length, [p + 2] length symbol - 257 | distance code << 5
+      tok[p] = static_cast<uint16_t>(bd);
+      tok[p + 1] = static_cast<uint16_t>(best);
+      tok[p + 2] = static_cast<uint16_t>((sym - 257u) | (dc << 5));
+      if (sym == run_sym && kDeflateLitSyms + dc == run_dsym) {
+        ++run_n;
+      } else {
+        if (run_n != 0u) add(run_sym, run_dsym, run_n);
+        run_sym = sym;
+        run_dsym = kDeflateLitSyms + dc;
+        run_n = 1;
+      }
       i += best;
     } else {
-      add(static_cast<uint32_t>(in[deflate_at(t.begin + i)]), 0xFFFFFFFFu);
+      add(static_cast<uint32_t>(in[deflate_at(t.begin + i)]), 0xFFFFFFFFu, 1u);
       i += 1;
     }
   }
+  if (run_n != 0u) add(run_sym, run_dsym, run_n);
   t.is_start = starts;
   t.is_match = matches;
 }
@@ -298,31 +324,45 @@ TB200_HD uint32_t deflate_shannon_len(uint32_t count, uint32_t total, uint32_t m
 #endif
   return l < 1u ? 1u : (l > maxl ? maxl : l);
 }
-// Make the length histogram bl[1..maxl] describe a COMPLETE prefix code (Kraft sum exactly 1):
+// Make the length histogram bl[1..MAXL] describe a COMPLETE prefix code (Kraft sum exactly 1):
 // demote from the longest lengths while over-subscribed (only after clamping), then promote
-// the largest steps that still fit.  nsym = symbols in use (>= 2).
-TB200_HD void deflate_complete_code(uint32_t* bl, uint32_t maxl) {
+// the largest steps that still fit.  Needs >= 2 symbols in use.  All loops have constant bounds
+// and a local copy of the histogram, so on the device the whole thing runs in registers.
+template <int MAXL>
+TB200_HD void deflate_complete_code_t(uint32_t* bl_io) {
+  uint32_t bl[MAXL + 2];
+#pragma unroll
+  for (int k = 0; k <= MAXL; ++k) bl[k] = bl_io[k];
+  bl[MAXL + 1] = 0;
   uint32_t S = 0;
-  const uint32_t T = 1u << maxl;
-  for (uint32_t k = 1; k <= maxl; ++k) S += bl[k] << (maxl - k);
-  for (uint32_t k = maxl - 1u; k >= 1u && S > T; --k) {
+  const uint32_t T = 1u << MAXL;
+#pragma unroll
+  for (int k = 1; k <= MAXL; ++k) S += bl[k] << (MAXL - k);
+#pragma unroll
+  for (int k = MAXL - 1; k >= 1; --k) {
     while (S > T && bl[k] > 0u) {
       bl[k] -= 1u;
-      bl[k + 1u] += 1u;
-      S -= 1u << (maxl - k - 1u);
+      bl[k + 1] += 1u;
+      S -= 1u << (MAXL - k - 1);
     }
   }
   uint32_t gap = T - S;
   for (int pass = 0; pass < 16 && gap != 0u; ++pass) {
-    for (uint32_t k = 2; k <= maxl; ++k) {
-      const uint32_t step = 1u << (maxl - k);
-      uint32_t take = gap / step;
+#pragma unroll
+    for (int k = 2; k <= MAXL; ++k) {
+      uint32_t take = gap >> (MAXL - k);
       if (take > bl[k]) take = bl[k];
       bl[k] -= take;
-      bl[k - 1u] += take;
-      gap -= take * step;
+      bl[k - 1] += take;
+      gap -= take << (MAXL - k);
     }
   }
+#pragma unroll
+  for (int k = 0; k <= MAXL; ++k) bl_io[k] = bl[k];
+}
+TB200_HD void deflate_complete_code(uint32_t* bl, uint32_t maxl) {
+  if (maxl == 15u) deflate_complete_code_t<15>(bl);
+  else deflate_complete_code_t<7>(bl);
 }
 // canonical first codes per length (RFC 1951 3.2.2)
 TB200_HD void deflate_next_codes(const uint32_t* bl, uint32_t maxl, uint32_t* next) {
@@ -340,36 +380,41 @@ TB200_HD uint32_t deflate_cl_order(uint32_t i) {
   return order[i];
 }
 
-// Run-length form of the code-length sequence lens[0..n) (RFC 1951 3.2.7): entries (symbol 0..18,
-// extra value); returns the entry count.  One thread.
-TB200_HD uint32_t deflate_rle_lengths(const uint8_t* lens, uint32_t n, uint8_t* sym, uint8_t* extra) {
-  uint32_t out = 0, i = 0;
-  while (i < n) {
-    const uint32_t v = lens[i];
-    uint32_t run = 1;
-    while (i + run < n && lens[i + run] == v) ++run;
-    if (v == 0u) {
-      uint32_t left = run;
-      while (left >= 11u) {
-        const uint32_t r = left > 138u ? 138u : left;
-        sym[out] = 18; extra[out] = static_cast<uint8_t>(r - 11u); ++out;
-        left -= r;
-      }
-      if (left >= 3u) { sym[out] = 17; extra[out] = static_cast<uint8_t>(left - 3u); ++out; left = 0; }
-      while (left > 0u) { sym[out] = 0; extra[out] = 0; ++out; --left; }
-    } else {
-      sym[out] = static_cast<uint8_t>(v); extra[out] = 0; ++out;
-      uint32_t left = run - 1u;
-      while (left >= 3u) {
-        const uint32_t r = left > 6u ? 6u : left;
-        sym[out] = 16; extra[out] = static_cast<uint8_t>(r - 3u); ++out;
-        left -= r;
-      }
-      while (left > 0u) { sym[out] = static_cast<uint8_t>(v); extra[out] = 0; ++out; --left; }
-    }
-    i += run;
+// The code-length sequence of a dynamic header: the literal/length lengths [0, nlit) followed directly
+// by the distance lengths [0, ndist).
+TB200_HD uint32_t deflate_hdr_len(const uint8_t* len_tab, uint32_t nlit, uint32_t i) {
+  return i < nlit ? len_tab[i] : len_tab[kDeflateLitSyms + (i - nlit)];
+}
+// Run-length form of that sequence (RFC 1951 3.2.7), block-wise so that it is parallel: the sequence is
+// cut into segments of 16 entries; a segment of >= 11 entries that is all zero becomes ONE entry
+// (symbol 18, "repeat zero 11..138 times"), every other segment sends its lengths as they are.  Segment s
+// -> number of entries it contributes.
+constexpr uint32_t kDeflateHdrSeg = 16;
+TB200_HD uint32_t deflate_segment_entries(const uint8_t* len_tab, uint32_t nlit, uint32_t n, uint32_t s) {
+  const uint32_t b = s * kDeflateHdrSeg, e = b + kDeflateHdrSeg < n ? b + kDeflateHdrSeg : n;
+  if (b >= n) return 0u;
+  bool zero = e - b >= 11u;
+  for (uint32_t i = b; zero && i < e; ++i) zero = deflate_hdr_len(len_tab, nlit, i) == 0u;
+  return zero ? 1u : e - b;
+}
+// write segment s's entries at hdr_sym / hdr_extra[at ...]; count(sym) is called once per entry
+template <typename CountFn>
+TB200_HD void deflate_segment_write(const uint8_t* len_tab, uint32_t nlit, uint32_t n, uint32_t s, uint32_t entries, uint32_t at, uint8_t* hdr_sym,
+                                    uint8_t* hdr_extra, CountFn count) {
+  const uint32_t b = s * kDeflateHdrSeg, e = b + kDeflateHdrSeg < n ? b + kDeflateHdrSeg : n;
+  if (entries == 0u) return;
+  if (entries == 1u && e - b >= 11u) {
+    hdr_sym[at] = 18;
+    hdr_extra[at] = static_cast<uint8_t>(e - b - 11u);
+    count(18u);
+    return;
   }
-  return out;
+  for (uint32_t i = b; i < e; ++i) {
+    const uint32_t v = deflate_hdr_len(len_tab, nlit, i);
+    hdr_sym[at + (i - b)] = static_cast<uint8_t>(v);
+    hdr_extra[at + (i - b)] = 0;
+    count(v);
+  }
 }
 TB200_HD uint32_t deflate_cl_extra_bits(uint32_t sym) { return sym == 16u ? 2u : (sym == 17u ? 3u : (sym == 18u ? 7u : 0u)); }
 
@@ -384,9 +429,10 @@ TB200_HD void deflate_count(const uint8_t* in, const DeflateThread& t, const uin
     s &= s - 1ull;
     const uint32_t p = t.begin + i;
     if ((t.is_match >> i) & 1ull) {
-      const uint32_t dist = tok[p], len = tok[p + 1];
-      dyn += deflate_match_cost(lit_len, dist_len, len, dist);
-      fix += deflate_fixed_match_bits(len, dist);
+      const uint32_t sd = tok[p + 2], sym = 257u + (sd & 31u), dc = sd >> 5;
+      const uint32_t extra = deflate_len_extra_bits(sym) + deflate_dist_extra_bits(dc);
+      dyn += lit_len[sym] + dist_len[dc] + extra;
+      fix += deflate_fixed_litlen_bits(sym) + 5u + extra;
     } else {
       const uint32_t b = in[deflate_at(p)];
       dyn += lit_len[b];
@@ -407,10 +453,12 @@ TB200_HD void deflate_emit(const uint8_t* in, const DeflateThread& t, const uint
     s &= s - 1ull;
     const uint32_t p = t.begin + i;
     if ((t.is_match >> i) & 1ull) {
-      const uint32_t dist = tok[p], len = tok[p + 1];
-      uint32_t sym, eb, ev, dc, deb, dev;
-      deflate_len_symbol(len, &sym, &eb, &ev);
-      deflate_dist_symbol(dist, &dc, &deb, &dev);
+      const uint32_t dist = tok[p], len = tok[p + 1], sd = tok[p + 2];
+      const uint32_t sym = 257u + (sd & 31u), dc = sd >> 5;
+      const uint32_t eb = deflate_len_extra_bits(sym), deb = deflate_dist_extra_bits(dc);
+      // extra values: offset of the length / distance inside its symbol's range
+      const uint32_t ev = eb == 0u ? 0u : ((len - 3u) & ((1u << eb) - 1u));
+      const uint32_t dev = deb == 0u ? 0u : ((dist - 1u) & ((1u << deb) - 1u));
       if (lit_code != nullptr) {
         // code, extra bits, distance code, extra bits: at most 15 + 5 + 15 + 13 = 48 bits, two puts
         deflate_put(words, pos, static_cast<uint32_t>(lit_code[sym]) | (ev << lit_len[sym]), lit_len[sym] + eb);

@@ -147,8 +147,9 @@ uint64_t emul_deflate_modes(const uint8_t* src, uint64_t nbytes, uint32_t gzip, 
       for (uint32_t i = 0; i < 64u; ++i) {
         const uint32_t p = th[t].begin + i;
         if (p + 3u < n) {
-          const uint32_t h = deflate_hash4(deflate_word_at(th[t], i));
-          if (p < table[h]) table[h] = p;
+          const uint32_t v = deflate_word_at(th[t], i);
+          const uint32_t h = deflate_hash4(v);
+          if (deflate_hashable(v) && p < table[h]) table[h] = p;
         }
       }
     }
@@ -156,9 +157,9 @@ uint64_t emul_deflate_modes(const uint8_t* src, uint64_t nbytes, uint32_t gzip, 
     uint32_t hist[NS] = {0}, ntok = 0, nmatch = 0;
     for (int t = 0; t < kDeflateThreads; ++t) {
       if (th[t].end > th[t].begin) {
-        deflate_parse(in.data(), th[t], table.data(), tok.data(), n, [&](uint32_t a, uint32_t b) {
-          hist[a] += 1u;
-          if (b != 0xFFFFFFFFu) hist[b] += 1u;
+        deflate_parse(in.data(), th[t], table.data(), tok.data(), n, [&](uint32_t a, uint32_t b, uint32_t times) {
+          hist[a] += times;
+          if (b != 0xFFFFFFFFu) hist[b] += times;
         });
         ntok += static_cast<uint32_t>(__builtin_popcountll(th[t].is_start));
         nmatch += static_cast<uint32_t>(__builtin_popcountll(th[t].is_match));
@@ -208,16 +209,18 @@ uint64_t emul_deflate_modes(const uint8_t* src, uint64_t nbytes, uint32_t gzip, 
       code_tab[s2] = static_cast<uint16_t>(deflate_reverse(next_code[a][len_tab[s2]] + idx, len_tab[s2]));
     }
     // header (thread 0 of the kernel)
-    uint8_t seq[kDeflateHdrMax], hdr_sym[kDeflateHdrMax + 8], hdr_extra[kDeflateHdrMax + 8];
+    uint8_t hdr_sym[kDeflateHdrMax + 8], hdr_extra[kDeflateHdrMax + 8];
     uint32_t cl_len[19], cl_code[19];
     uint32_t nlit = 286, ndist = 30;
     while (nlit > 257u && len_tab[nlit - 1u] == 0u) --nlit;
     while (ndist > 1u && len_tab[kDeflateLitSyms + ndist - 1u] == 0u) --ndist;
-    for (uint32_t i = 0; i < nlit; ++i) seq[i] = len_tab[i];
-    for (uint32_t i = 0; i < ndist; ++i) seq[nlit + i] = len_tab[kDeflateLitSyms + i];
-    const uint32_t ne = deflate_rle_lengths(seq, nlit + ndist, hdr_sym, hdr_extra);
     uint32_t cnt[19] = {0}, lbl[8] = {0}, lnext[8], ord[19];
-    for (uint32_t e = 0; e < ne; ++e) cnt[hdr_sym[e]] += 1u;
+    uint32_t ne = 0;
+    for (uint32_t seg = 0; seg < 32u; ++seg) {  // one lane per segment on the device
+      const uint32_t entries = deflate_segment_entries(len_tab, nlit, nlit + ndist, seg);
+      deflate_segment_write(len_tab, nlit, nlit + ndist, seg, entries, ne, hdr_sym, hdr_extra, [&](uint32_t v) { cnt[v] += 1u; });
+      ne += entries;
+    }
     uint32_t used = 0;
     for (int i = 0; i < 19; ++i) {
       cl_len[i] = cnt[i] != 0u ? deflate_shannon_len(cnt[i], ne, 7u) : 0u;
@@ -409,15 +412,16 @@ extern "C" uint32_t emul_deflate_tokens(const uint8_t* src, uint32_t n, uint32_t
     for (uint32_t i = 0; i < 64u; ++i) {
       const uint32_t p = th[t].begin + i;
       if (p + 3u < n) {
-        const uint32_t h = deflate_hash4(deflate_word_at(th[t], i));
-        if (p < table[h]) table[h] = p;
+        const uint32_t v = deflate_word_at(th[t], i);
+        const uint32_t h = deflate_hash4(v);
+        if (deflate_hashable(v) && p < table[h]) table[h] = p;
       }
     }
   }
   uint32_t k = 0;
   for (uint32_t t = 0; t < static_cast<uint32_t>(kDeflateThreads); ++t) {
     if (th[t].end <= th[t].begin) continue;
-    deflate_parse(in.data(), th[t], table.data(), tok.data(), n, [&](uint32_t, uint32_t) {});
+    deflate_parse(in.data(), th[t], table.data(), tok.data(), n, [&](uint32_t, uint32_t, uint32_t) {});
     for (uint32_t i = 0; i < 64u; ++i) {
       if (!((th[t].is_start >> i) & 1ull) || k >= cap) continue;
       const uint32_t p = th[t].begin + i;
