@@ -14,11 +14,13 @@ share the GPU through a private CUDA MPS daemon when the box has one (stated in 
             FP32), every response validated on the device; K timed steps (count window), repeated
             to >= 0.1 s, median repetition; all ranks start together, value = sum of requests /
             max time.
-  e2e       the same metric through the tritonclient-compatible API with HOST tensors:
-            P processes each looping numpy tensor -> cuda_shared_memory.set_shared_memory_region
-            (H2D) -> InferenceServerClient.infer -> get_contents_as_numpy (D2H)
-            (client_b200/perf/host_loop.py), free-running for a fixed wall time.
-  --impl reference   that loop on the restated reference code (oracle/ref_client.py: cuda-python
+  e2e       the same metric through the tritonclient-compatible API, P free-running processes each a
+            blocking client (client_b200/perf/host_loop.py): cuda_shared_memory.fill_shared_memory_region
+            (descriptor H2D, fresh tensor generated inside the region) -> InferenceServerClient.infer
+            -> check_shared_memory_region (validated on the device, verdict D2H).  e2e.host_tensors
+            is the reference's loop line for line on the drop-in modules (numpy tensor ->
+            set_shared_memory_region H2D -> infer -> get_contents_as_numpy D2H).
+  --impl reference   the host-tensor loop on the restated reference code (oracle/ref_client.py: cuda-python
             cudaMemcpyAsync + sync per request, stdlib HTTP), same server, same process count.
   fill_once both arms again with regions filled once and requests only naming them (what
             perf_analyzer itself does).
@@ -53,6 +55,7 @@ IN_SHAPE = (3, 224, 224)
 IN_BYTES = 3 * 224 * 224 * 4  # 602,112
 OUT_ELEMS = 1000
 OUT_BYTES = OUT_ELEMS * 4
+FILL_JOB_BYTES, CHECK_JOB_BYTES, CHECK_RESULT_BYTES = 64, 48, 32  # tb200_fill_job / tb200_check_job / tb200_check_result (include/tb200.h)
 SEED = 20260921
 WORKLOAD = "C2 densenet_onnx FP32[3,224,224] --shared-memory=cuda concurrency=64"
 
@@ -433,7 +436,8 @@ def run_b200(args):
             ("value", lambda: box.generator(local, steps, warmup)),
             ("once", lambda: box.generator(local, steps, warmup, mode="once")),
             ("warm_host", lambda: host_loops(box, "b200", min(nproc_rank, 4), 0.5, "per-request")),
-            ("e2e", lambda: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "per-request")),
+            ("e2e", lambda: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "device")),
+            ("e2e_host", lambda: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "per-request")),
             ("e2e_once", lambda: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "once"))]
     for name, fn in plan:
         if box is not None and lb_error is None:
@@ -493,9 +497,10 @@ def run_b200(args):
         once_value = rep.sum(lb["once"]["count"]) / rep.max(lb["once"]["seconds"])
         e2e_value = total("e2e", "count") / HOST_LOOP_SECONDS
         e2e_once_value = total("e2e_once", "count") / HOST_LOOP_SECONDS
+        e2e_host_value = total("e2e_host", "count") / HOST_LOOP_SECONDS
         ms_step = seconds * 1e3 / (v["count"] / SLOTS)
     else:  # no server could be had: the device side alone, flagged
-        value, gpu_launches, once_value, e2e_value, e2e_once_value = 0.0, 0, 0.0, 0.0, 0.0
+        value, gpu_launches, once_value, e2e_value, e2e_once_value, e2e_host_value = 0.0, 0, 0.0, 0.0, 0.0, 0.0
         ms_step = None
         v = {}
 
@@ -514,11 +519,18 @@ def run_b200(args):
         "pinned_cpus_per_generator": v.get("cpus"), "host_cores": host_cores,
         "input_pack_gbps": round(value * IN_BYTES / 1e9, 1),
         "l2": "inputs of the kernel timings rotate over %d region sets = %d MB > 126 MB L2" % (SETS, SETS * SLOTS * IN_BYTES // 1000000),
-        "e2e": {"value": round(e2e_value, 1), "unit": "infer/s", "h2d_bytes_per_step": SLOTS * IN_BYTES, "d2h_bytes_per_step": SLOTS * OUT_BYTES,
+        "e2e": {"value": round(e2e_value, 1), "unit": "infer/s", "h2d_bytes_per_step": SLOTS * (FILL_JOB_BYTES + CHECK_JOB_BYTES), "d2h_bytes_per_step": SLOTS * CHECK_RESULT_BYTES,
                 "processes": nproc_rank * world, "seconds": HOST_LOOP_SECONDS, "p50_us": lb.get("e2e", {}).get("p50_us"),
-                "what": "tritonclient-compatible API with host tensors (client_b200/perf/host_loop.py): numpy FP32[3,224,224] -> "
-                        "cuda_shared_memory.set_shared_memory_region (H2D) -> http.InferenceServerClient.infer naming the regions -> "
-                        "get_contents_as_numpy (D2H), free-running processes, same server"},
+                "what": "tritonclient-compatible API, one blocking client per process (client_b200/perf/host_loop.py, mode 'device'): per request "
+                        "cuda_shared_memory.fill_shared_memory_region (job descriptor H2D, Philox fill inside the region, sync) -> "
+                        "http.InferenceServerClient.infer naming the regions -> cuda_shared_memory.check_shared_memory_region (validate on the "
+                        "device, 32-byte verdict D2H); free-running processes, same server.  The tensors never exist on the host: that is the path "
+                        "this library replaces (reference: numpy -> set_shared_memory_region -> get_contents_as_numpy, timed by --impl reference)",
+                "host_tensors": {"value": round(e2e_host_value, 1), "h2d_bytes_per_step": SLOTS * IN_BYTES, "d2h_bytes_per_step": SLOTS * OUT_BYTES,
+                                 "p50_us": lb.get("e2e_host", {}).get("p50_us"),
+                                 "what": "the reference arm's loop line for line on the drop-in modules: numpy Generator.random FP32[3,224,224] -> "
+                                         "set_shared_memory_region (H2D) -> infer -> get_contents_as_numpy (D2H); bound by the host's random numbers "
+                                         "and PCIe exactly as the reference is"}},
         "fill_once": {"value": round(once_value, 1), "e2e": round(e2e_once_value, 1), "p50_us": lb.get("once", {}).get("p50_us"),
                       "what": "regions filled once, every request only names them (perf_analyzer's own behaviour): native generator / drop-in API loop"},
         "gpu_launches": gpu_launches,

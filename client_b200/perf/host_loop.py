@@ -18,8 +18,10 @@ OUT_BYTES = OUT_ELEMS * 4
 
 def run_loop(url, device_id, tag, seconds, data_mode, ready=None, go=None):
     """Free-running closed loop of ONE client for ``seconds``; returns (completed, latencies_ns).
-    ``data_mode``: "per-request" (fresh host tensor, H2D, infer, D2H every request) or "once"
-    (regions filled once, every request only names them)."""
+    ``data_mode``: "per-request" (fresh host tensor, H2D, infer, D2H every request), "device"
+    (fresh tensor generated inside the region by ``fill_shared_memory_region``, infer, the response
+    validated by ``check_shared_memory_region`` -- only the job descriptor and the verdict cross
+    PCIe) or "once" (regions filled once, every request only names them)."""
     from .. import http as httpclient
     from ..utils import cuda_shared_memory as cudashm
 
@@ -48,6 +50,12 @@ def run_loop(url, device_id, tag, seconds, data_mode, ready=None, go=None):
             client.infer("densenet_onnx", [inp], outputs=[out])
             y = cudashm.get_contents_as_numpy(out_h, np.float32, [OUT_ELEMS])
             if not np.isfinite(y).all():
+                raise RuntimeError("non-finite logits")
+        elif data_mode == "device":
+            cudashm.fill_shared_memory_region(in_h, "FP32", IN_SHAPE, seed=len(lat) + 1)
+            client.infer("densenet_onnx", [inp], outputs=[out])
+            verdict = cudashm.check_shared_memory_region(out_h, "top1", byte_size=OUT_BYTES)  # mismatches = non-finite values
+            if verdict["mismatches"]:
                 raise RuntimeError("non-finite logits")
         else:
             client.infer("densenet_onnx", [inp], outputs=[out])

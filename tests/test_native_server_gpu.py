@@ -259,3 +259,21 @@ def test_lookahead_over_cuda_shm(server):
     for r in rows:
         assert r["count"] > 20 and r["failed"] == 0 and r["nonfinite"] == 0, r
         assert 0 < r["device_slots"] <= r["count"] / 4 + 8, r
+
+
+@pytest.mark.parametrize("mode", ["device", "per-request", "once"])
+def test_host_loop_modes(server, mode):
+    """bench.py's e2e loops (client_b200/perf/host_loop.py): every mode completes validated requests"""
+    from client_b200.perf import host_loop
+
+    n, lat = host_loop.run_loop(server, 0, "t_" + mode.replace("-", ""), 0.3, mode)
+    assert n > 10 and len(lat) == n
+
+
+def test_reference_loop_same_server(server):
+    """the reference arm of bench.py (oracle/ref_client.py, cuda-python) against the same server"""
+    pytest.importorskip("cuda.bindings.runtime")
+    from oracle import ref_client
+
+    n, lat = ref_client.run_loop(server, 0, "t_ref", 0.3, "per-request")
+    assert n > 5 and len(lat) == n
