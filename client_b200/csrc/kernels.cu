@@ -832,10 +832,9 @@ pack_image_generic_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__
 // (8-bit, exactly Pillow's intermediate image), phase B resamples those vertically and
 // applies astype / scaling / layout on the way out.
 constexpr int kResizeBits = 22;  // Pillow: PRECISION_BITS = 32 - 8 - 2
-__device__ __forceinline__ uint32_t resize_clip8(int32_t acc) {
-  const int32_t v = acc >> kResizeBits;
-  return static_cast<uint32_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
-}
+// The triangle filter's coefficients are >= 0 and a pixel's taps sum to 2^22 +- taps/2
+// (resample.h), so 0 < acc and (acc >> 22) <= 255: Pillow's clip8 never clips and is left out.
+__device__ __forceinline__ uint32_t resize_round8(int32_t acc) { return static_cast<uint32_t>(acc) >> kResizeBits; }
 
 // N-tap dot product of bytes at stride `step` with int32 coefficients, N a compile-time bound
 template <int N>
@@ -847,21 +846,21 @@ __device__ __forceinline__ int32_t resize_dot(const uint8_t* px, int step, const
 }
 // phase A inner loop for one (column, channel) pair with N unrolled taps (taps past the
 // pair's own count carry a zero coefficient; the bytes they read lie inside the shared
-// memory block -- the staged rows are followed by the 8-bit image -- and do not matter)
+// memory block -- the staged rows are followed by the 8-bit image -- and do not matter;
+// a pair right of the image has no taps at all and produces 0)
 template <int N, int C>
 __device__ __forceinline__ void resize_rows(const uint8_t* rowp, uint8_t* outp, const uint8_t* shift_s, const int32_t (&kr)[8],
-                                            int row0, int rows, int row_step, uint32_t raw_step, int out_step, bool live) {
+                                            int row0, int rows, int row_step, uint32_t raw_step, int out_step) {
+#pragma unroll 4
   for (int row = row0; row < rows; row += row_step, rowp += raw_step, outp += out_step) {
     const uint8_t* line = rowp + shift_s[row];
     int32_t acc = 1 << (kResizeBits - 1);
 #pragma unroll
     for (int t = 0; t < N; ++t) acc += static_cast<int32_t>(line[t * C]) * kr[t];  // kr[t] == 0 past the pair's own taps
-    *outp = static_cast<uint8_t>(live ? resize_clip8(acc) : 0u);
+    *outp = static_cast<uint8_t>(resize_round8(acc));
   }
 }
 
-// shared memory: raw source block [rows][raw_stride] | horizontally resampled [rows][32*C] |
-// the tile's coefficients (32*hk + tile_h*vk int32) | per-row alignment shifts
 // one output element: astype + scaling of an 8-bit pixel, by destination type
 template <uint32_t DST, uint32_t SCALING, int C>
 __device__ __forceinline__ void resize_store(void* dst, size_t idx, uint32_t px, int ch) {
@@ -874,15 +873,21 @@ __device__ __forceinline__ void resize_store(void* dst, size_t idx, uint32_t px,
 // phase B for one output pixel: N-tap vertical dot product per channel, then store
 template <int N, uint32_t DST, uint32_t SCALING, int C>
 __device__ __forceinline__ void resize_column(const uint8_t* col, const int32_t* k, void* dst, size_t base, size_t ch_stride) {
+  int32_t kr[N];
+#pragma unroll
+  for (int t = 0; t < N; ++t) kr[t] = k[t];
 #pragma unroll
   for (int ch = 0; ch < C; ++ch) {
-    const uint32_t px = resize_clip8(resize_dot<N>(col + ch, 32 * C, k));
+    const uint32_t px = resize_round8(resize_dot<N>(col + ch, 32 * C, kr));
     resize_store<DST, SCALING, C>(dst, base + ch * ch_stride, px, ch);
   }
 }
 
+// shared memory: mbarrier (16 B) | raw source block [max_rows][raw_stride] | horizontally resampled
+// [max_rows][32*C] | the tile's coefficients (32*hk + tile_h*vk int32) | the tile's vertical bounds
+// (int2[tile_h], first row as a byte offset into the resampled block) | per-row alignment shifts
 template <int C, uint32_t DST, uint32_t SCALING>
-__global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
+__global__ void __launch_bounds__(256) resize_pack_kernel(const __grid_constant__ ResizePack p) {
   extern __shared__ __align__(16) uint8_t rp_smem[];
   constexpr int P = 32 * C;  // (column, channel) pairs of a tile
   const int x0 = blockIdx.x * 32;
@@ -890,49 +895,62 @@ __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
   const int y0 = blockIdx.y * p.tile_h;
   const int y1 = min(y0 + p.tile_h, p.dh) - 1;
   const int img = blockIdx.z;
-  const int r0 = p.vbounds[y0].x;
-  const int rows = p.vbounds[y1].x + p.vbounds[y1].y - r0;
-  const int c0 = p.hbounds[x0].x;
-  const int span = p.hbounds[xe].x + p.hbounds[xe].y - c0;  // source columns the tile reads
-  uint8_t* raw = rp_smem;
-  uint8_t* tmp = rp_smem + static_cast<size_t>(p.max_rows) * p.raw_stride;
+  const int2 vb0 = p.vbounds[y0], vb1 = p.vbounds[y1], hb0 = p.hbounds[x0], hb1 = p.hbounds[xe];
+  const int r0 = vb0.x;
+  const int rows = vb1.x + vb1.y - r0;
+  const int c0 = hb0.x;
+  const int span = hb1.x + hb1.y - c0;  // source columns the tile reads
+  uint64_t* bar = reinterpret_cast<uint64_t*>(rp_smem);
+  uint8_t* raw = rp_smem + 16;
+  uint8_t* tmp = raw + static_cast<size_t>(p.max_rows) * p.raw_stride;
   int32_t* hk_s = reinterpret_cast<int32_t*>(tmp + ((static_cast<size_t>(p.max_rows) * P + 15) & ~static_cast<size_t>(15)));
   int32_t* vk_s = hk_s + 32 * p.hk;
-  uint8_t* shift_s = reinterpret_cast<uint8_t*>(vk_s + p.tile_h * p.vk);
-  const uint8_t* src = p.src + static_cast<size_t>(img) * p.sh * p.sw * C;
-  const uint8_t* src_end = p.src + static_cast<size_t>(p.n) * p.sh * p.sw * C;
+  int2* vb_s = reinterpret_cast<int2*>(vk_s + ((p.tile_h * p.vk + 1) & ~1));
+  uint8_t* shift_s = reinterpret_cast<uint8_t*>(vb_s + p.tile_h);
 
-  // phase 0: the source block as aligned 4-byte words (row starts are arbitrary byte addresses)
-  for (int row = threadIdx.x >> 5; row < rows; row += 8) {
-    const uint8_t* g = src + (static_cast<size_t>(r0 + row) * p.sw + c0) * C;
-    const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 3u);
-    const uint32_t* gw = reinterpret_cast<const uint32_t*>(g - shift);
-    const int nwords = (static_cast<int>(shift) + span * C + 3) >> 2;
-    uint32_t* sw_ = reinterpret_cast<uint32_t*>(raw + static_cast<size_t>(row) * p.raw_stride);
-    if ((threadIdx.x & 31) == 0) shift_s[row] = static_cast<uint8_t>(shift);
-    const bool inside = reinterpret_cast<const uint8_t*>(gw) >= p.src && reinterpret_cast<const uint8_t*>(gw + nwords) <= src_end;
-    if (inside) {
-      for (int w = threadIdx.x & 31; w < nwords; w += 32) sw_[w] = __ldg(gw + w);
-    } else {  // the row holding the first / last word of the whole source: stay inside the buffer
-      for (int w = threadIdx.x & 31; w < nwords; w += 32) {
-        const uint8_t* wp = reinterpret_cast<const uint8_t*>(gw + w);
-        uint32_t val = 0;
-        for (int bb = 0; bb < 4; ++bb) {
-          if (wp + bb >= p.src && wp + bb < src_end) val |= static_cast<uint32_t>(wp[bb]) << (8 * bb);
-        }
-        sw_[w] = val;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, static_cast<uint32_t>(rows));  // one arrival per staged row
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // phase 0: one TMA bulk copy per source row, issued by one thread each: the 16-byte granules that
+  // cover the row's bytes (row starts are arbitrary byte addresses; the row's offset inside its
+  // first granule goes to shift_s).  Nothing waits here -- the coefficient tables load meanwhile.
+  {
+    const uint8_t* img_src = p.src + static_cast<size_t>(img) * p.sh * p.sw * C + static_cast<size_t>(c0) * C;
+    const uint8_t* src_end = p.src + static_cast<size_t>(p.n) * p.sh * p.sw * C;
+    const size_t pitch = static_cast<size_t>(p.sw) * C;
+    for (int row = threadIdx.x; row < rows; row += 256) {
+      const uint8_t* g = img_src + static_cast<size_t>(r0 + row) * pitch;
+      const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 15u);
+      const uint8_t* ga = g - shift;
+      const uint32_t bytes = (shift + static_cast<uint32_t>(span) * C + 15u) & ~15u;
+      uint8_t* srow = raw + static_cast<size_t>(row) * p.raw_stride;
+      shift_s[row] = static_cast<uint8_t>(shift);
+      if (ga >= p.src && ga + bytes <= src_end) {
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(srow, ga, bytes, bar);
+      } else {  // the granules of the first / last row of the whole source may leave the buffer: bytes, guarded
+        for (uint32_t i = 0; i < bytes; ++i) srow[i] = (ga + i >= p.src && ga + i < src_end) ? ga[i] : uint8_t{0};
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
       }
     }
   }
-  for (int i = threadIdx.x; i < 32 * p.hk; i += 256) {
-    const int xl = i / p.hk;
-    hk_s[i] = (x0 + xl < p.dw) ? p.hcoeffs[static_cast<size_t>(x0) * p.hk + i] : 0;
+  {
+    const int hlive = (xe - x0 + 1) * p.hk;  // columns right of the image get zero coefficients
+    const int32_t* hc = p.hcoeffs + static_cast<size_t>(x0) * p.hk;
+    for (int i = threadIdx.x; i < 32 * p.hk; i += 256) hk_s[i] = i < hlive ? hc[i] : 0;
+    const int vlive = (y1 - y0 + 1) * p.vk;
+    const int32_t* vc = p.vcoeffs + static_cast<size_t>(y0) * p.vk;
+    for (int i = threadIdx.x; i < vlive; i += 256) vk_s[i] = vc[i];
+    for (int i = threadIdx.x; i <= y1 - y0; i += 256) {
+      const int2 b = p.vbounds[y0 + i];
+      vb_s[i] = make_int2((b.x - r0) * P, b.y);
+    }
   }
-  for (int i = threadIdx.x; i < p.tile_h * p.vk; i += 256) {
-    const int yl = i / p.vk;
-    vk_s[i] = (y0 + yl < p.dh) ? p.vcoeffs[static_cast<size_t>(y0) * p.vk + i] : 0;
-  }
-  __syncthreads();
+  __syncthreads();     // tables + shift_s
+  mbar_wait(bar, 0);   // the staged rows
 
   // phase A: horizontal pass into 8-bit rows (Pillow's intermediate image).  A thread keeps one
   // (column, channel) pair and its taps in registers and walks down the rows.
@@ -943,8 +961,7 @@ __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
     if (rg < RG) {
       const int xl = pair / C;
       const int ch = pair - xl * C;
-      const bool live = x0 + xl < p.dw;
-      const int2 b = live ? p.hbounds[x0 + xl] : make_int2(c0, 0);
+      const int2 b = x0 + xl <= xe ? p.hbounds[x0 + xl] : make_int2(c0, 0);
       const int32_t* k = hk_s + xl * p.hk;
       const int off = (b.x - c0) * C + ch;
       const int nmax = __reduce_max_sync(0xFFFFFFFFu, b.y);  // P is a multiple of 32: whole warps are here
@@ -957,37 +974,39 @@ __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
         const uint32_t raw_step = RG * p.raw_stride;
         switch (nmax) {
           case 0: case 1: case 2: case 3:
-            resize_rows<3, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
-          case 4: resize_rows<4, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
-          case 5: resize_rows<5, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
-          case 6: resize_rows<6, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
-          case 7: resize_rows<7, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
-          default: resize_rows<8, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P, live); break;
+            resize_rows<3, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
+          case 4: resize_rows<4, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
+          case 5: resize_rows<5, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
+          case 6: resize_rows<6, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
+          case 7: resize_rows<7, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
+          default: resize_rows<8, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
         }
       } else {
         for (int row = rg; row < rows; row += RG) {
           const uint8_t* line = raw + static_cast<size_t>(row) * p.raw_stride + shift_s[row] + off;
           int32_t acc = 1 << (kResizeBits - 1);
           for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(line[t * C]) * k[t];
-          tmp[row * P + pair] = static_cast<uint8_t>(resize_clip8(acc));
+          tmp[row * P + pair] = static_cast<uint8_t>(resize_round8(acc));
         }
       }
     }
   }
   __syncthreads();
 
-  // phase B: vertical pass + astype / scaling / layout
+  // phase B: vertical pass + astype / scaling / layout; a warp per output row, a lane per column
   const int xl = threadIdx.x & 31;
-  const int x = x0 + xl;
-  if (x >= p.dw) return;
+  if (x0 + xl > xe) return;
   const size_t hw = static_cast<size_t>(p.dh) * p.dw;
-  for (int y = y0 + (threadIdx.x >> 5); y <= y1; y += 8) {
-    const int2 b = p.vbounds[y];  // one y per warp: the tap count is warp-uniform
-    const int32_t* k = vk_s + (y - y0) * p.vk;
-    const size_t pos = static_cast<size_t>(y) * p.dw + x;
-    const size_t base = p.layout == TB200_NCHW ? static_cast<size_t>(img) * C * hw + pos : (static_cast<size_t>(img) * hw + pos) * C;
-    const size_t ch_stride = p.layout == TB200_NCHW ? hw : 1;
-    const uint8_t* col = tmp + (b.x - r0) * P + xl * C;
+  const bool nchw = p.layout == TB200_NCHW;
+  const size_t ch_stride = nchw ? hw : 1;
+  const size_t row_stride = nchw ? static_cast<size_t>(p.dw) : static_cast<size_t>(p.dw) * C;
+  size_t base = (nchw ? static_cast<size_t>(img) * C * hw + (x0 + xl) : (static_cast<size_t>(img) * hw + (x0 + xl)) * C) +
+                static_cast<size_t>(y0 + (threadIdx.x >> 5)) * row_stride;
+  const uint8_t* colbase = tmp + xl * C;
+  for (int yl = threadIdx.x >> 5; yl <= y1 - y0; yl += 8, base += 8 * row_stride) {
+    const int2 b = vb_s[yl];  // one row per warp: the tap count is warp-uniform
+    const int32_t* k = vk_s + yl * p.vk;
+    const uint8_t* col = colbase + b.x;
     switch (b.y) {
       case 1: resize_column<1, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
       case 2: resize_column<2, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
@@ -1001,7 +1020,7 @@ __global__ void __launch_bounds__(256) resize_pack_kernel(const ResizePack p) {
         for (int ch = 0; ch < C; ++ch) {
           int32_t acc = 1 << (kResizeBits - 1);
           for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(col[ch + t * P]) * k[t];
-          resize_store<DST, SCALING, C>(p.dst, base + ch * ch_stride, resize_clip8(acc), ch);
+          resize_store<DST, SCALING, C>(p.dst, base + ch * ch_stride, resize_round8(acc), ch);
         }
     }
   }

@@ -1089,13 +1089,16 @@ int tb200_resize_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
   // stay within 40 KB while possible so that several CTAs share an SM
   const int tiles[6] = {32, 16, 8, 4, 2, 1};
   p.tile_h = 0;
-  p.raw_stride = static_cast<uint32_t>((tab->max_span * c + 3 + 4 + 15) & ~15);  // + alignment shift + word tail
+  p.raw_stride = static_cast<uint32_t>((tab->max_span * c + 15 + 15) & ~15);  // whole 16-byte granules: + the row's offset in its first one
   for (int pass = 0; pass < 2 && p.tile_h == 0; ++pass) {
     const size_t limit = pass == 0 ? 40u * 1024u : 200u * 1024u;
     for (int i = 0; i < 6 && p.tile_h == 0; ++i) {
       const size_t tmp_bytes = (static_cast<size_t>(tab->max_rows[i]) * 32 * c + 15) & ~static_cast<size_t>(15);
-      const size_t bytes = static_cast<size_t>(tab->max_rows[i]) * p.raw_stride + tmp_bytes +
-                           (32 * static_cast<size_t>(tab->hk) + static_cast<size_t>(tiles[i]) * tab->vk) * sizeof(int32_t) +
+      // mbarrier | staged rows | 8-bit intermediate | coefficients (vertical ones padded to an even count) |
+      // vertical bounds | per-row shifts -- the layout resize_pack_kernel walks
+      const size_t bytes = 16 + static_cast<size_t>(tab->max_rows[i]) * p.raw_stride + tmp_bytes +
+                           (32 * static_cast<size_t>(tab->hk) + ((static_cast<size_t>(tiles[i]) * tab->vk + 1) & ~static_cast<size_t>(1))) * sizeof(int32_t) +
+                           static_cast<size_t>(tiles[i]) * sizeof(int2) +
                            ((static_cast<size_t>(tab->max_rows[i]) + 15) & ~static_cast<size_t>(15));
       if (bytes <= limit) {
         p.tile_h = tiles[i];

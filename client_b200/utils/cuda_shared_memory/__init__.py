@@ -294,7 +294,7 @@ def fill_shared_memory_region(
     ``mode``: "random" (floats uniform in [low, high), default the unit
     interval; integers uniform in [low, high), default raw bits) or "zero".
     """
-    from ...device import DeviceOps, make_fill_job
+    from ...device import make_fill_job
 
     es = _native.DTYPE_SIZES.get(datatype)
     if es is None:
@@ -305,7 +305,7 @@ def fill_shared_memory_region(
             "The size of the shared memory region is insufficient for the generated tensor"
         )
     job = make_fill_job(cuda_shm_handle._base_addr + offset, nbytes, datatype, stream_id, mode, low, high)
-    ops = DeviceOps(_ctx(cuda_shm_handle._device_id))
+    ops = _ops(cuda_shm_handle._device_id)
     ops.fill([job], seed=seed)
     if sync:
         ops.sync()
@@ -321,8 +321,6 @@ def set_shared_memory_region_from_image(
 
     ``resize=(h, w)``: ``Image.resize((w, h), Image.BILINEAR)`` first, bit-identical to
     Pillow (antialiased triangle filter, horizontal pass first, 8-bit intermediate)."""
-    from ...device import DeviceOps
-
     arr = np.ascontiguousarray(images_u8_nhwc)
     if arr.dtype != np.uint8 or arr.ndim not in (3, 4):
         raise CudaSharedMemoryException("images must be a uint8 array of shape [N,]H,W,C")
@@ -335,7 +333,7 @@ def set_shared_memory_region_from_image(
         raise CudaSharedMemoryException(
             "The size of the shared memory region is insufficient for the packed images"
         )
-    ops = DeviceOps(_ctx(cuda_shm_handle._device_id))
+    ops = _ops(cuda_shm_handle._device_id)
     try:
         if resize is not None:
             ops.resize_pack_image_from_host(cuda_shm_handle._base_addr + offset, datatype, layout, arr, out_h, out_w, scaling)
@@ -350,10 +348,8 @@ def check_shared_memory_region(cuda_shm_handle, kind="sum", byte_size=None, offs
     """Validate / checksum region contents on the device; returns a dict with
     ``mismatches``, ``sum``, ``xor32``, ``argmax``, ``max_value``.  ``expected``
     (another region handle) is compared byte-wise for ``kind='equal'``."""
-    from ...device import DeviceOps
-
     nbytes = int(byte_size) if byte_size is not None else cuda_shm_handle._byte_size - offset
-    ops = DeviceOps(_ctx(cuda_shm_handle._device_id))
+    ops = _ops(cuda_shm_handle._device_id)
     b = expected._base_addr if expected is not None else 0
     return ops.check_one(kind, cuda_shm_handle._base_addr + offset, nbytes, b=b)
 
@@ -369,7 +365,6 @@ def classify_shared_memory_region(cuda_shm_handle, datatype, shape, class_count,
     form ``InferResult.as_numpy`` gives for a classification output and
     src/python/examples/image_client.py:196-216 parses.  Only 8 bytes per class leave the GPU.
     """
-    from ...device import DeviceOps
     from ... import _native as nat
 
     if datatype not in ("FP32", "FP16", "BF16"):
@@ -382,7 +377,7 @@ def classify_shared_memory_region(cuda_shm_handle, datatype, shape, class_count,
         raise CudaSharedMemoryException(
             "The size of the shared memory region is insufficient to provide numpy array with requested size"
         )
-    ops = DeviceOps(_ctx(cuda_shm_handle._device_id))
+    ops = _ops(cuda_shm_handle._device_id)
     base = cuda_shm_handle._base_addr + offset
     values, indices = ops.topk([(base + i * classes * es, classes, datatype) for i in range(batch)], class_count)
     out = np.empty((batch, class_count), dtype=np.object_)
