@@ -844,23 +844,6 @@ __device__ __forceinline__ int32_t resize_dot(const uint8_t* px, int step, const
   for (int t = 0; t < N; ++t) acc += static_cast<int32_t>(px[t * step]) * k[t];
   return acc;
 }
-// phase A inner loop for one (column, channel) pair with N unrolled taps (taps past the
-// pair's own count carry a zero coefficient; the bytes they read lie inside the shared
-// memory block -- the staged rows are followed by the 8-bit image -- and do not matter;
-// a pair right of the image has no taps at all and produces 0)
-template <int N, int C>
-__device__ __forceinline__ void resize_rows(const uint8_t* rowp, uint8_t* outp, const uint8_t* shift_s, const int32_t (&kr)[8],
-                                            int row0, int rows, int row_step, uint32_t raw_step, int out_step) {
-#pragma unroll 4
-  for (int row = row0; row < rows; row += row_step, rowp += raw_step, outp += out_step) {
-    const uint8_t* line = rowp + shift_s[row];
-    int32_t acc = 1 << (kResizeBits - 1);
-#pragma unroll
-    for (int t = 0; t < N; ++t) acc += static_cast<int32_t>(line[t * C]) * kr[t];  // kr[t] == 0 past the pair's own taps
-    *outp = static_cast<uint8_t>(resize_round8(acc));
-  }
-}
-
 // one output element: astype + scaling of an 8-bit pixel, by destination type
 template <uint32_t DST, uint32_t SCALING, int C>
 __device__ __forceinline__ void resize_store(void* dst, size_t idx, uint32_t px, int ch) {
@@ -870,158 +853,212 @@ __device__ __forceinline__ void resize_store(void* dst, size_t idx, uint32_t px,
   else static_cast<uint8_t*>(dst)[idx] = static_cast<uint8_t>(px);
 }
 
-// phase B for one output pixel: N-tap vertical dot product per channel, then store
+// what every phase of a tile needs to know
+struct ResizeTile {
+  uint8_t* raw;            // staged source rows [rows][raw_stride], each at its 16-byte granule
+  uint8_t* tmp;            // horizontally resampled 8-bit rows [rows][32*C]
+  const uint8_t* shift_s;  // a row's offset inside its first granule
+  uint64_t* bar;           // completes when every row is staged
+  int2 hb;                 // lane l: (first source column, taps) of output column x0 + l; (c0, 0) right of the image
+  int c0, rows;
+  uint32_t raw_stride;
+};
+
+// phase A with N unrolled taps: a warp per staged row; lane l owns the (column, channel) pairs l, 32 + l, ...
+// (C of them: neighbouring lanes read neighbouring bytes) and keeps their taps in registers.  Taps past a
+// pair's own count carry a zero coefficient -- the bytes they read lie inside the shared memory block (the
+// staged rows are followed by the 8-bit image) and do not matter; a pair right of the image produces 0.
+template <int N, int C>
+__device__ __forceinline__ void resize_phase_a(const ResizeTile& t, const int32_t* __restrict__ hcoeffs, int hk) {
+  constexpr int P = 32 * C;
+  const int lane = threadIdx.x & 31;
+  int32_t kr[C][N];
+  int off[C];
+#pragma unroll
+  for (int g = 0; g < C; ++g) {
+    const int pair = g * 32 + lane;
+    const int xl = pair / C;
+    const int bx = __shfl_sync(0xFFFFFFFFu, t.hb.x, xl), by = __shfl_sync(0xFFFFFFFFu, t.hb.y, xl);
+    off[g] = (bx - t.c0) * C + (pair - xl * C);
+    const int32_t* k = hcoeffs + xl * hk;
+#pragma unroll
+    for (int i = 0; i < N; ++i) kr[g][i] = i < by ? __ldg(k + i) : 0;
+  }
+  mbar_wait(t.bar, 0);  // the coefficient loads above overlap the row copies
+#pragma unroll 2
+  for (int row = threadIdx.x >> 5; row < t.rows; row += 8) {
+    const uint8_t* line = t.raw + static_cast<uint32_t>(row) * t.raw_stride + t.shift_s[row];
+    uint8_t* out = t.tmp + row * P + lane;
+#pragma unroll
+    for (int g = 0; g < C; ++g) {
+      int32_t acc = 1 << (kResizeBits - 1);
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc += static_cast<int32_t>(line[off[g] + i * C]) * kr[g][i];
+      out[g * 32] = static_cast<uint8_t>(resize_round8(acc));
+    }
+  }
+}
+
+// any tap count: the same mapping, coefficients read through the cache
+template <int C>
+__device__ __forceinline__ void resize_phase_a_any(const ResizeTile& t, const int32_t* __restrict__ hcoeffs, int hk) {
+  constexpr int P = 32 * C;
+  const int lane = threadIdx.x & 31;
+  mbar_wait(t.bar, 0);
+  for (int g = 0; g < C; ++g) {
+    const int pair = g * 32 + lane;
+    const int xl = pair / C;
+    const int bx = __shfl_sync(0xFFFFFFFFu, t.hb.x, xl), by = __shfl_sync(0xFFFFFFFFu, t.hb.y, xl);
+    const int off = (bx - t.c0) * C + (pair - xl * C);
+    const int32_t* k = hcoeffs + xl * hk;
+    for (int row = threadIdx.x >> 5; row < t.rows; row += 8) {
+      const uint8_t* line = t.raw + static_cast<uint32_t>(row) * t.raw_stride + t.shift_s[row] + off;
+      int32_t acc = 1 << (kResizeBits - 1);
+      for (int i = 0; i < by; ++i) acc += static_cast<int32_t>(line[i * C]) * __ldg(k + i);
+      t.tmp[row * P + pair] = static_cast<uint8_t>(resize_round8(acc));
+    }
+  }
+}
+
+// phase B with N unrolled taps: a warp per output row, a lane per output column.  Rows with fewer taps
+// use zero coefficients (the table is zero-padded) on rows of the 8-bit image past their own -- the block
+// has `vk` slack rows for that.  voff: lane l holds the byte offset of output row l's first tap row.
 template <int N, uint32_t DST, uint32_t SCALING, int C>
-__device__ __forceinline__ void resize_column(const uint8_t* col, const int32_t* k, void* dst, size_t base, size_t ch_stride) {
-  int32_t kr[N];
+__device__ __forceinline__ void resize_phase_b(const uint8_t* tmp, const int32_t* vk_s, int vk, int voff, int out_rows, bool live,
+                                               void* dst, size_t base, size_t row_stride, size_t ch_stride) {
+  constexpr int P = 32 * C;
+  const uint8_t* colbase = tmp + (threadIdx.x & 31) * C;
+#pragma unroll 2
+  for (int yl = threadIdx.x >> 5; yl < out_rows; yl += 8, base += 8 * row_stride) {
+    const uint8_t* col = colbase + __shfl_sync(0xFFFFFFFFu, voff, yl);
+    const int32_t* k = vk_s + yl * vk;
+    int32_t kr[N];
 #pragma unroll
-  for (int t = 0; t < N; ++t) kr[t] = k[t];
+    for (int i = 0; i < N; ++i) kr[i] = k[i];
+    if (live) {
 #pragma unroll
-  for (int ch = 0; ch < C; ++ch) {
-    const uint32_t px = resize_round8(resize_dot<N>(col + ch, 32 * C, kr));
-    resize_store<DST, SCALING, C>(dst, base + ch * ch_stride, px, ch);
+      for (int ch = 0; ch < C; ++ch) {
+        int32_t acc = 1 << (kResizeBits - 1);
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc += static_cast<int32_t>(col[ch + i * P]) * kr[i];
+        resize_store<DST, SCALING, C>(dst, base + ch * ch_stride, resize_round8(acc), ch);
+      }
+    }
   }
 }
 
 // shared memory: mbarrier (16 B) | raw source block [max_rows][raw_stride] | horizontally resampled
-// [max_rows][32*C] | the tile's coefficients (32*hk + tile_h*vk int32) | the tile's vertical bounds
-// (int2[tile_h], first row as a byte offset into the resampled block) | per-row alignment shifts
+// [max_rows + vk][32*C] | the tile's vertical coefficients (tile_h*vk int32) | per-row alignment shifts
 template <int C, uint32_t DST, uint32_t SCALING>
-__global__ void __launch_bounds__(256) resize_pack_kernel(const __grid_constant__ ResizePack p) {
+__global__ void __launch_bounds__(256, 5) resize_pack_kernel(const __grid_constant__ ResizePack p) {
   extern __shared__ __align__(16) uint8_t rp_smem[];
   constexpr int P = 32 * C;  // (column, channel) pairs of a tile
+  const int lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * 32;
   const int xe = min(x0 + 32, p.dw) - 1;
-  const int y0 = blockIdx.y * p.tile_h;
+  const int y0 = blockIdx.y * p.tile_h;  // tile_h <= 32: a lane per output row as well
   const int y1 = min(y0 + p.tile_h, p.dh) - 1;
   const int img = blockIdx.z;
-  const int2 vb0 = p.vbounds[y0], vb1 = p.vbounds[y1], hb0 = p.hbounds[x0], hb1 = p.hbounds[xe];
-  const int r0 = vb0.x;
-  const int rows = vb1.x + vb1.y - r0;
-  const int c0 = hb0.x;
-  const int span = hb1.x + hb1.y - c0;  // source columns the tile reads
-  uint64_t* bar = reinterpret_cast<uint64_t*>(rp_smem);
-  uint8_t* raw = rp_smem + 16;
-  uint8_t* tmp = raw + static_cast<size_t>(p.max_rows) * p.raw_stride;
-  int32_t* hk_s = reinterpret_cast<int32_t*>(tmp + ((static_cast<size_t>(p.max_rows) * P + 15) & ~static_cast<size_t>(15)));
-  int32_t* vk_s = hk_s + 32 * p.hk;
-  int2* vb_s = reinterpret_cast<int2*>(vk_s + ((p.tile_h * p.vk + 1) & ~1));
-  uint8_t* shift_s = reinterpret_cast<uint8_t*>(vb_s + p.tile_h);
+  // every warp loads the tile's bounds, one column and one row per lane
+  int2 hb = x0 + lane <= xe ? p.hbounds[x0 + lane] : make_int2(0, 0);
+  const int2 vb = y0 + lane <= y1 ? p.vbounds[y0 + lane] : make_int2(0, 0);
+  const int c0 = __shfl_sync(0xFFFFFFFFu, hb.x, 0);
+  const int span = __shfl_sync(0xFFFFFFFFu, hb.x + hb.y, xe - x0) - c0;  // source columns the tile reads
+  const int r0 = __shfl_sync(0xFFFFFFFFu, vb.x, 0);
+  const int rows = __shfl_sync(0xFFFFFFFFu, vb.x + vb.y, y1 - y0) - r0;
+  const int nmaxh = __reduce_max_sync(0xFFFFFFFFu, hb.y);
+  const int nmaxv = __reduce_max_sync(0xFFFFFFFFu, vb.y);
+  if (x0 + lane > xe) hb.x = c0;
+  const int voff = (vb.x - r0) * P;
+
+  ResizeTile t;
+  t.bar = reinterpret_cast<uint64_t*>(rp_smem);
+  t.raw = rp_smem + 16;
+  t.tmp = t.raw + static_cast<size_t>(p.max_rows) * p.raw_stride;
+  int32_t* vk_s = reinterpret_cast<int32_t*>(t.tmp + ((static_cast<size_t>(p.max_rows + p.vk) * P + 15) & ~static_cast<size_t>(15)));
+  uint8_t* shift_s = reinterpret_cast<uint8_t*>(vk_s + p.tile_h * p.vk);
+  t.shift_s = shift_s;
+  t.hb = hb; t.c0 = c0; t.rows = rows; t.raw_stride = p.raw_stride;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar, static_cast<uint32_t>(rows));  // one arrival per staged row
+    mbar_init(t.bar, static_cast<uint32_t>(rows));  // one arrival per staged row
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // phase 0: one TMA bulk copy per source row, issued by one thread each: the 16-byte granules that
-  // cover the row's bytes (row starts are arbitrary byte addresses; the row's offset inside its
-  // first granule goes to shift_s).  Nothing waits here -- the coefficient tables load meanwhile.
+  // phase 0: one TMA bulk copy per source row, issued by one thread each: the 16-byte granules that cover
+  // the row's bytes -- row starts are arbitrary byte addresses; the row's offset inside its first granule
+  // goes to shift_s.  Nothing waits here.
   {
     const uint8_t* img_src = p.src + static_cast<size_t>(img) * p.sh * p.sw * C + static_cast<size_t>(c0) * C;
     const uint8_t* src_end = p.src + static_cast<size_t>(p.n) * p.sh * p.sw * C;
-    const size_t pitch = static_cast<size_t>(p.sw) * C;
-    for (int row = threadIdx.x; row < rows; row += 256) {
-      const uint8_t* g = img_src + static_cast<size_t>(r0 + row) * pitch;
+    const uint32_t pitch = static_cast<uint32_t>(p.sw) * C;
+    // rows dealt round the warps (thread (lane, warp) takes row lane * 8 + warp): the copies of a warp's lanes are
+    // issued one after the other, eight warps get the block under way sooner than two
+    for (int row = lane * 8 + (threadIdx.x >> 5); row < rows; row += 256) {
+      const uint8_t* g = img_src + static_cast<size_t>(static_cast<uint32_t>(r0 + row) * pitch);  // an image is < 4 GiB
       const uint32_t shift = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 15u);
       const uint8_t* ga = g - shift;
       const uint32_t bytes = (shift + static_cast<uint32_t>(span) * C + 15u) & ~15u;
-      uint8_t* srow = raw + static_cast<size_t>(row) * p.raw_stride;
+      uint8_t* srow = t.raw + static_cast<size_t>(row) * p.raw_stride;
       shift_s[row] = static_cast<uint8_t>(shift);
       if (ga >= p.src && ga + bytes <= src_end) {
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(srow, ga, bytes, bar);
+        mbar_expect_tx(t.bar, bytes);
+        bulk_g2s(srow, ga, bytes, t.bar);
       } else {  // the granules of the first / last row of the whole source may leave the buffer: bytes, guarded
         for (uint32_t i = 0; i < bytes; ++i) srow[i] = (ga + i >= p.src && ga + i < src_end) ? ga[i] : uint8_t{0};
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(t.bar)) : "memory");
       }
     }
-  }
-  {
-    const int hlive = (xe - x0 + 1) * p.hk;  // columns right of the image get zero coefficients
-    const int32_t* hc = p.hcoeffs + static_cast<size_t>(x0) * p.hk;
-    for (int i = threadIdx.x; i < 32 * p.hk; i += 256) hk_s[i] = i < hlive ? hc[i] : 0;
-    const int vlive = (y1 - y0 + 1) * p.vk;
     const int32_t* vc = p.vcoeffs + static_cast<size_t>(y0) * p.vk;
-    for (int i = threadIdx.x; i < vlive; i += 256) vk_s[i] = vc[i];
-    for (int i = threadIdx.x; i <= y1 - y0; i += 256) {
-      const int2 b = p.vbounds[y0 + i];
-      vb_s[i] = make_int2((b.x - r0) * P, b.y);
-    }
+    const int vlive = (y1 - y0 + 1) * p.vk;
+#pragma unroll 1
+    for (int i = threadIdx.x; i < vlive; i += 256) vk_s[i] = __ldg(vc + i);  // read after the barrier below
   }
-  __syncthreads();     // tables + shift_s
-  mbar_wait(bar, 0);   // the staged rows
 
-  // phase A: horizontal pass into 8-bit rows (Pillow's intermediate image).  A thread keeps one
-  // (column, channel) pair and its taps in registers and walks down the rows.
+  // phase A: horizontal pass into 8-bit rows (Pillow's intermediate image)
   {
-    constexpr int RG = 256 / P;  // row groups (2 for RGB: 192 threads busy, 8 for grey)
-    const int pair = threadIdx.x % P;
-    const int rg = threadIdx.x / P;
-    if (rg < RG) {
-      const int xl = pair / C;
-      const int ch = pair - xl * C;
-      const int2 b = x0 + xl <= xe ? p.hbounds[x0 + xl] : make_int2(c0, 0);
-      const int32_t* k = hk_s + xl * p.hk;
-      const int off = (b.x - c0) * C + ch;
-      const int nmax = __reduce_max_sync(0xFFFFFFFFu, b.y);  // P is a multiple of 32: whole warps are here
-      if (nmax <= 8) {
-        int32_t kr[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) kr[t] = t < b.y ? k[t] : 0;
-        const uint8_t* rowp = raw + static_cast<size_t>(rg) * p.raw_stride + off;
-        uint8_t* outp = tmp + rg * P + pair;
-        const uint32_t raw_step = RG * p.raw_stride;
-        switch (nmax) {
-          case 0: case 1: case 2: case 3:
-            resize_rows<3, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
-          case 4: resize_rows<4, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
-          case 5: resize_rows<5, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
-          case 6: resize_rows<6, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
-          case 7: resize_rows<7, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
-          default: resize_rows<8, C>(rowp, outp, shift_s, kr, rg, rows, RG, raw_step, RG * P); break;
-        }
-      } else {
-        for (int row = rg; row < rows; row += RG) {
-          const uint8_t* line = raw + static_cast<size_t>(row) * p.raw_stride + shift_s[row] + off;
-          int32_t acc = 1 << (kResizeBits - 1);
-          for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(line[t * C]) * k[t];
-          tmp[row * P + pair] = static_cast<uint8_t>(resize_round8(acc));
-        }
-      }
+    const int32_t* hc = p.hcoeffs + static_cast<size_t>(x0) * p.hk;
+    switch (nmaxh) {
+      case 0: case 1: case 2: case 3: resize_phase_a<3, C>(t, hc, p.hk); break;
+      case 4: resize_phase_a<4, C>(t, hc, p.hk); break;
+      case 5: resize_phase_a<5, C>(t, hc, p.hk); break;
+      case 6: resize_phase_a<6, C>(t, hc, p.hk); break;
+      default: resize_phase_a_any<C>(t, hc, p.hk); break;
     }
   }
   __syncthreads();
 
-  // phase B: vertical pass + astype / scaling / layout; a warp per output row, a lane per column
-  const int xl = threadIdx.x & 31;
-  if (x0 + xl > xe) return;
+  // phase B: vertical pass + astype / scaling / layout
+  const bool live = x0 + lane <= xe;
   const size_t hw = static_cast<size_t>(p.dh) * p.dw;
   const bool nchw = p.layout == TB200_NCHW;
   const size_t ch_stride = nchw ? hw : 1;
   const size_t row_stride = nchw ? static_cast<size_t>(p.dw) : static_cast<size_t>(p.dw) * C;
-  size_t base = (nchw ? static_cast<size_t>(img) * C * hw + (x0 + xl) : (static_cast<size_t>(img) * hw + (x0 + xl)) * C) +
-                static_cast<size_t>(y0 + (threadIdx.x >> 5)) * row_stride;
-  const uint8_t* colbase = tmp + xl * C;
-  for (int yl = threadIdx.x >> 5; yl <= y1 - y0; yl += 8, base += 8 * row_stride) {
-    const int2 b = vb_s[yl];  // one row per warp: the tap count is warp-uniform
-    const int32_t* k = vk_s + yl * p.vk;
-    const uint8_t* col = colbase + b.x;
-    switch (b.y) {
-      case 1: resize_column<1, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
-      case 2: resize_column<2, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
-      case 3: resize_column<3, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
-      case 4: resize_column<4, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
-      case 5: resize_column<5, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
-      case 6: resize_column<6, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
-      case 7: resize_column<7, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
-      case 8: resize_column<8, DST, SCALING, C>(col, k, p.dst, base, ch_stride); break;
-      default:
+  const size_t base = (nchw ? static_cast<size_t>(img) * C * hw + (x0 + lane) : (static_cast<size_t>(img) * hw + (x0 + lane)) * C) +
+                      static_cast<size_t>(y0 + (threadIdx.x >> 5)) * row_stride;
+  const int out_rows = y1 - y0 + 1;
+  switch (nmaxv) {
+    case 1: resize_phase_b<1, DST, SCALING, C>(t.tmp, vk_s, p.vk, voff, out_rows, live, p.dst, base, row_stride, ch_stride); break;
+    case 2: resize_phase_b<2, DST, SCALING, C>(t.tmp, vk_s, p.vk, voff, out_rows, live, p.dst, base, row_stride, ch_stride); break;
+    case 3: resize_phase_b<3, DST, SCALING, C>(t.tmp, vk_s, p.vk, voff, out_rows, live, p.dst, base, row_stride, ch_stride); break;
+    case 4: resize_phase_b<4, DST, SCALING, C>(t.tmp, vk_s, p.vk, voff, out_rows, live, p.dst, base, row_stride, ch_stride); break;
+    case 5: resize_phase_b<5, DST, SCALING, C>(t.tmp, vk_s, p.vk, voff, out_rows, live, p.dst, base, row_stride, ch_stride); break;
+    case 6: resize_phase_b<6, DST, SCALING, C>(t.tmp, vk_s, p.vk, voff, out_rows, live, p.dst, base, row_stride, ch_stride); break;
+    default: {
+      const uint8_t* colbase = t.tmp + lane * C;
+      size_t bs = base;
+      for (int yl = threadIdx.x >> 5; yl < out_rows; yl += 8, bs += 8 * row_stride) {
+        const uint8_t* col = colbase + __shfl_sync(0xFFFFFFFFu, voff, yl);
+        const int taps = __shfl_sync(0xFFFFFFFFu, vb.y, yl);
+        const int32_t* k = vk_s + yl * p.vk;
+        if (!live) continue;
         for (int ch = 0; ch < C; ++ch) {
           int32_t acc = 1 << (kResizeBits - 1);
-          for (int t = 0; t < b.y; ++t) acc += static_cast<int32_t>(col[ch + t * P]) * k[t];
-          resize_store<DST, SCALING, C>(p.dst, base + ch * ch_stride, resize_round8(acc), ch);
+          for (int i = 0; i < taps; ++i) acc += static_cast<int32_t>(col[ch + i * P]) * k[i];
+          resize_store<DST, SCALING, C>(p.dst, bs + ch * ch_stride, resize_round8(acc), ch);
         }
+      }
     }
   }
 }

@@ -84,10 +84,10 @@ struct ResizePack {
   const int32_t* vcoeffs; // [dst_h * vk]
   uint32_t dst_dtype, layout, scaling;
   int n, sh, sw, c, dh, dw, hk, vk;
-  int tile_h;             // output rows per CTA (1..8)
+  int tile_h;             // output rows per CTA (1..32)
   int max_rows;           // source rows the tallest tile needs
-  uint32_t raw_stride;    // bytes per staged source row (widest tile's span * c + slack, 16-aligned)
-  uint32_t smem_bytes;    // max_rows * (raw_stride + 32 * c) + coefficient tables
+  uint32_t raw_stride;    // bytes per staged source row (widest tile's span * c in whole 16-byte granules)
+  uint32_t smem_bytes;    // see resize_pack_kernel
 };
 cudaError_t launch_resize_pack(const ResizePack& p, cudaStream_t s);
 

@@ -1093,12 +1093,11 @@ int tb200_resize_pack_image_async(tb200_ctx* ctx, void* dst, uint32_t dst_dtype,
   for (int pass = 0; pass < 2 && p.tile_h == 0; ++pass) {
     const size_t limit = pass == 0 ? 40u * 1024u : 200u * 1024u;
     for (int i = 0; i < 6 && p.tile_h == 0; ++i) {
-      const size_t tmp_bytes = (static_cast<size_t>(tab->max_rows[i]) * 32 * c + 15) & ~static_cast<size_t>(15);
-      // mbarrier | staged rows | 8-bit intermediate | coefficients (vertical ones padded to an even count) |
-      // vertical bounds | per-row shifts -- the layout resize_pack_kernel walks
+      // mbarrier | staged rows | 8-bit intermediate (+ vk slack rows: short output rows read zero-weighted taps
+      // past their own) | vertical coefficients | per-row shifts -- the layout resize_pack_kernel walks
+      const size_t tmp_bytes = (static_cast<size_t>(tab->max_rows[i] + tab->vk) * 32 * c + 15) & ~static_cast<size_t>(15);
       const size_t bytes = 16 + static_cast<size_t>(tab->max_rows[i]) * p.raw_stride + tmp_bytes +
-                           (32 * static_cast<size_t>(tab->hk) + ((static_cast<size_t>(tiles[i]) * tab->vk + 1) & ~static_cast<size_t>(1))) * sizeof(int32_t) +
-                           static_cast<size_t>(tiles[i]) * sizeof(int2) +
+                           static_cast<size_t>(tiles[i]) * tab->vk * sizeof(int32_t) +
                            ((static_cast<size_t>(tab->max_rows[i]) + 15) & ~static_cast<size_t>(15));
       if (bytes <= limit) {
         p.tile_h = tiles[i];
