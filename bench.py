@@ -15,9 +15,10 @@ share the GPU through a private CUDA MPS daemon when the box has one (stated in 
             to >= 0.1 s, median repetition; all ranks start together, value = sum of requests /
             max time.
   e2e       the same metric through the tritonclient-compatible API, P free-running processes each a
-            blocking client (client_b200/perf/host_loop.py): cuda_shared_memory.fill_shared_memory_region
-            (descriptor H2D, fresh tensor generated inside the region) -> InferenceServerClient.infer
-            -> check_shared_memory_region (validated on the device, verdict D2H).  e2e.host_tensors
+            blocking client (client_b200/perf/host_loop.py): InferenceServerClient.infer ->
+            check_shared_memory_region (validated on the device, verdict D2H) +
+            fill_shared_memory_region (descriptor H2D, the next request's tensor generated inside the
+            region), one stream wait per request.  e2e.host_tensors
             is the reference's loop line for line on the drop-in modules (numpy tensor ->
             set_shared_memory_region H2D -> infer -> get_contents_as_numpy D2H).
   --impl reference   the host-tensor loop on the restated reference code (oracle/ref_client.py: cuda-python
@@ -329,19 +330,8 @@ def run_b200(args):
     pack_bytes = SLOTS * (224 * 224 * 3) * (1 + 4)
     # --- C3 extras (BASELINE configs[2]): one FP16[128,3,224,224] request = 38,535,168 B
     c3_fill = [[make_fill_job(in_regions[s]._base_addr, SLOTS * IN_BYTES, "FP16", stream_id=stream0 + 7000 + s)] for s in range(SETS)]
-    ops.graph_begin()
-    for s in range(SETS):
-        ops.fill_epoch(c3_fill[s], seed=SEED)
-    gc3 = ops.graph_end()
-    for _ in range(3):
-        gc3.launch()
-    ops.sync()
-    timer.start()
-    for _ in range(50):
-        gc3.launch()
-    timer.stop()
-    ops.sync()
-    c3_fill_ms = timer.elapsed_ms() / (50 * SETS)
+    # the same chain as the headline roofline: 16,000 back-to-back launches, stream epoch in the parameters
+    c3_fill_ms, _ = fill_chain(lambda r, s: ops.fill(c3_fill[s], seed=SEED, epoch=r * SETS + s))
     c3_src = [DeviceBuffer(local, 128 * 224 * 224 * 3) for _ in range(SETS)]
     ops.fill([make_fill_job(b.ptr, 128 * 224 * 224 * 3, "UINT8", stream_id=stream0 + 7100 + i) for i, b in enumerate(c3_src)], seed=SEED)
     ops.graph_begin()
@@ -522,9 +512,9 @@ def run_b200(args):
         "e2e": {"value": round(e2e_value, 1), "unit": "infer/s", "h2d_bytes_per_step": SLOTS * (FILL_JOB_BYTES + CHECK_JOB_BYTES), "d2h_bytes_per_step": SLOTS * CHECK_RESULT_BYTES,
                 "processes": nproc_rank * world, "seconds": HOST_LOOP_SECONDS, "p50_us": lb.get("e2e", {}).get("p50_us"),
                 "what": "tritonclient-compatible API, one blocking client per process (client_b200/perf/host_loop.py, mode 'device'): per request "
-                        "cuda_shared_memory.fill_shared_memory_region (job descriptor H2D, Philox fill inside the region, sync) -> "
-                        "http.InferenceServerClient.infer naming the regions -> cuda_shared_memory.check_shared_memory_region (validate on the "
-                        "device, 32-byte verdict D2H); free-running processes, same server.  The tensors never exist on the host: that is the path "
+                        "http.InferenceServerClient.infer naming the regions -> cuda_shared_memory.check_shared_memory_region (validate on the device, "
+                        "32-byte verdict D2H) + cuda_shared_memory.fill_shared_memory_region (job descriptor H2D, Philox fill of the next request's "
+                        "tensor inside the region), one stream wait for both; free-running processes, same server.  The tensors never exist on the host: that is the path "
                         "this library replaces (reference: numpy -> set_shared_memory_region -> get_contents_as_numpy, timed by --impl reference)",
                 "host_tensors": {"value": round(e2e_host_value, 1), "h2d_bytes_per_step": SLOTS * IN_BYTES, "d2h_bytes_per_step": SLOTS * OUT_BYTES,
                                  "p50_us": lb.get("e2e_host", {}).get("p50_us"),

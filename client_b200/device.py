@@ -308,6 +308,20 @@ class DeviceOps:
         self.sync()
         return result_dict(res.array(np.uint8, ctypes.sizeof(CheckResult)).tobytes())
 
+    def check_one_deferred(self, kind, a, nbytes, b=0, c=0, d=0):
+        """Launch one check job and return a callable that waits for the stream and decodes the result --
+        whatever else was queued on the stream in between (the next request's fill) shares that one wait.
+        One deferred check at a time per DeviceOps (they share the pinned result slot)."""
+        job = CheckJob(a=int(a), b=int(b), c=int(c), d=int(d), nbytes=int(nbytes), kind=_KINDS[kind], pad=0)
+        res = self._result_buf()
+        self.check([job], res.device_ptr)
+
+        def result():
+            self.sync()
+            return result_dict(res.array(np.uint8, ctypes.sizeof(CheckResult)).tobytes())
+
+        return result
+
     def bytes_decode(self, src_ptr, src_bytes, count):
         """Blocking on-device decode of a serialised BYTES tensor (tb200_bytes_decode_async):
         ``count`` elements of ``<u32 length><payload>`` starting at device address ``src_ptr``.

@@ -19,9 +19,9 @@ OUT_BYTES = OUT_ELEMS * 4
 def run_loop(url, device_id, tag, seconds, data_mode, ready=None, go=None):
     """Free-running closed loop of ONE client for ``seconds``; returns (completed, latencies_ns).
     ``data_mode``: "per-request" (fresh host tensor, H2D, infer, D2H every request), "device"
-    (fresh tensor generated inside the region by ``fill_shared_memory_region``, infer, the response
-    validated by ``check_shared_memory_region`` -- only the job descriptor and the verdict cross
-    PCIe) or "once" (regions filled once, every request only names them)."""
+    (every request's tensor generated inside the region by ``fill_shared_memory_region``, infer, the
+    response validated by ``check_shared_memory_region`` -- only the job descriptors and the verdict
+    cross PCIe; the check of one response and the fill for the next request share one wait) or "once" (regions filled once, every request only names them)."""
     from .. import http as httpclient
     from ..utils import cuda_shared_memory as cudashm
 
@@ -37,6 +37,8 @@ def run_loop(url, device_id, tag, seconds, data_mode, ready=None, go=None):
     rng = np.random.default_rng(abs(hash(tag)) % (1 << 32))
     cudashm.set_shared_memory_region(in_h, [rng.random(IN_SHAPE, dtype=np.float32)])
     client.infer("densenet_onnx", [inp], outputs=[out])
+    if data_mode == "device":
+        cudashm.fill_shared_memory_region(in_h, "FP32", IN_SHAPE, seed=1)  # the first request's tensor
     if ready is not None:
         ready.wait()
     if go is not None:
@@ -52,10 +54,11 @@ def run_loop(url, device_id, tag, seconds, data_mode, ready=None, go=None):
             if not np.isfinite(y).all():
                 raise RuntimeError("non-finite logits")
         elif data_mode == "device":
-            cudashm.fill_shared_memory_region(in_h, "FP32", IN_SHAPE, seed=len(lat) + 1)
+            # the region already holds this request's tensor (generated while the previous response was checked)
             client.infer("densenet_onnx", [inp], outputs=[out])
-            verdict = cudashm.check_shared_memory_region(out_h, "top1", byte_size=OUT_BYTES)  # mismatches = non-finite values
-            if verdict["mismatches"]:
+            verdict = cudashm.check_shared_memory_region(out_h, "top1", byte_size=OUT_BYTES, defer=True)
+            cudashm.fill_shared_memory_region(in_h, "FP32", IN_SHAPE, seed=len(lat) + 2, sync=False)  # the next request's tensor
+            if verdict()["mismatches"]:  # one wait for both kernels; mismatches = non-finite values
                 raise RuntimeError("non-finite logits")
         else:
             client.infer("densenet_onnx", [inp], outputs=[out])

@@ -344,13 +344,19 @@ def set_shared_memory_region_from_image(
     ops.sync()
 
 
-def check_shared_memory_region(cuda_shm_handle, kind="sum", byte_size=None, offset=0, expected=None):
+def check_shared_memory_region(cuda_shm_handle, kind="sum", byte_size=None, offset=0, expected=None, defer=False):
     """Validate / checksum region contents on the device; returns a dict with
     ``mismatches``, ``sum``, ``xor32``, ``argmax``, ``max_value``.  ``expected``
-    (another region handle) is compared byte-wise for ``kind='equal'``."""
+    (another region handle) is compared byte-wise for ``kind='equal'``.
+
+    ``defer=True`` only launches the check and returns a callable giving that dict: device work queued
+    before it is called (``fill_shared_memory_region(..., sync=False)`` for the next request) is waited
+    for in the same synchronisation.  One deferred check at a time per device."""
     nbytes = int(byte_size) if byte_size is not None else cuda_shm_handle._byte_size - offset
     ops = _ops(cuda_shm_handle._device_id)
     b = expected._base_addr if expected is not None else 0
+    if defer:
+        return ops.check_one_deferred(kind, cuda_shm_handle._base_addr + offset, nbytes, b=b)
     return ops.check_one(kind, cuda_shm_handle._base_addr + offset, nbytes, b=b)
 
 
