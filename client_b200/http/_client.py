@@ -64,7 +64,8 @@ class _RawConnection:
         self._sock = sock
         self._plain = ssl_context is None
         self._buf = b""
-        self._host_line = ("Host: %s:%d\r\nAccept-Encoding: identity\r\n" % (host, port)).encode("ascii")
+        self._host_only = ("Host: %s:%d\r\n" % (host, port)).encode("ascii")
+        self._host_line = self._host_only + b"Accept-Encoding: identity\r\n"
 
     def close(self):
         try:
@@ -79,7 +80,9 @@ class _RawConnection:
         self._buf += chunk
 
     def exchange(self, method, uri, body, headers):
-        head = [("%s %s HTTP/1.1\r\n" % (method, uri)).encode("ascii"), self._host_line]
+        # the default "identity" only when the caller asks for no encoding of its own (one Accept-Encoding per request)
+        own = any(k.lower() == "accept-encoding" for k in headers)
+        head = [("%s %s HTTP/1.1\r\n" % (method, uri)).encode("ascii"), self._host_only if own else self._host_line]
         for k, v in headers.items():
             head.append(("%s: %s\r\n" % (k, v)).encode("latin-1"))
         body = body or b""

@@ -127,6 +127,14 @@ def main():
     steady_dram(tag)
     full(tag, tag + "_prof_fill_uniform.ncu-rep", "fill_uniform_kernel")
     if tag != "r01":  # the captures below are round 1's; later rounds name their files <tag>_*
+        full(tag, tag + "_prof_resize.ncu-rep", "resize_pack_kernel")
+        rep = os.path.join(OUT, tag + "_prof_resize.ncu-rep")
+        dst = os.path.join(DST, tag + "_resize_pack_kernel_full.txt")
+        if os.path.exists(rep) and os.path.exists(dst):  # where the instructions go: the SASS cut at its barriers
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_regions.py"), rep, "3136"], capture_output=True, text=True)
+            with open(dst, "a") as fh:
+                fh.write("\n# scripts/ncu_regions.py (unit = one 32x32 output tile, 3136 per launch): setup | row copies + tables | wait | horizontal pass | vertical pass\n")
+                fh.write(r.stdout)
         print(sorted(os.listdir(DST)))
         return
     full(tag, "prof_fill.ncu-rep", "fill_kernel")

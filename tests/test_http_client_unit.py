@@ -44,3 +44,38 @@ def test_error_plain_text():
 
 def test_success_does_not_raise():
     _raise_if_error(_HttpResponse(200, [("Content-Length", "2")], b"{}"))
+
+
+def test_one_accept_encoding_header_per_request():
+    """The default `Accept-Encoding: identity` gives way to the caller's own (reference: only the requested
+    encoding is sent, http/_client.py:1452-1456 of the reference)."""
+    import socket
+    import threading
+
+    from client_b200.http._client import _RawConnection
+
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(1)
+    seen = []
+
+    def serve():
+        c, _ = srv.accept()
+        for _ in range(2):
+            buf = b""
+            while b"\r\n\r\n" not in buf:
+                buf += c.recv(65536)
+            seen.append(buf)
+            c.sendall(b"HTTP/1.1 200 OK\r\nContent-Length: 0\r\n\r\n")
+        c.close()
+
+    th = threading.Thread(target=serve)
+    th.start()
+    conn = _RawConnection("127.0.0.1", srv.getsockname()[1], 5.0, 5.0, None)
+    conn.exchange("GET", "/v2/health/live", None, {})
+    conn.exchange("GET", "/v2/health/live", None, {"accept-encoding": "gzip"})
+    conn.close()
+    th.join()
+    srv.close()
+    assert seen[0].lower().count(b"accept-encoding") == 1 and b"identity" in seen[0]
+    assert seen[1].lower().count(b"accept-encoding") == 1 and b"gzip" in seen[1] and b"identity" not in seen[1]
