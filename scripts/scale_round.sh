@@ -6,7 +6,12 @@ STEPS=${2:-200}
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/r02_topo_n$N.txt 2>&1
-python bench.py --impl reference --gpus $N --steps $STEPS --warmup 5 > gpurun_out/r02_bench_ref_n$N.json 2> gpurun_out/r02_bench_ref_n$N.err
+if [ "$N" -gt 1 ]; then
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29516 \
+      bench.py --impl reference --gpus $N --steps $STEPS --warmup 5 > gpurun_out/r02_bench_ref_n$N.json 2> gpurun_out/r02_bench_ref_n$N.err
+else
+  python bench.py --impl reference --gpus $N --steps $STEPS --warmup 5 > gpurun_out/r02_bench_ref_n$N.json 2> gpurun_out/r02_bench_ref_n$N.err
+fi
 if [ "$N" -gt 1 ]; then
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
       bench.py --gpus $N --steps $STEPS --warmup 5 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
