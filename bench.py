@@ -421,20 +421,30 @@ def run_b200(args):
         box = LoopbackBox([local], use_mps=have_mps, manage_mps=False, grpc=(world == 1)).__enter__()
     except Exception as ex:
         lb_error = "%s: %s" % (type(ex).__name__, ex)
-    # every rank walks the same list and meets the others at a barrier after each entry, whatever happened
-    plan = [("warm", lambda: box.generator(local, 50, 5, min_seconds=0.05)),
-            ("value", lambda: box.generator(local, steps, warmup)),
-            ("once", lambda: box.generator(local, steps, warmup, mode="once")),
-            ("warm_host", lambda: host_loops(box, "b200", min(nproc_rank, 4), 0.5, "per-request")),
-            ("e2e", lambda: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "device")),
-            ("e2e_host", lambda: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "per-request")),
-            ("e2e_once", lambda: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "once"))]
+    # every entry takes `sync`, the ranks' rendezvous between "my instance is warm" and "time now"
+    plan = [("warm", lambda sync: box.generator(local, 50, 5, min_seconds=0.05, sync=sync)),
+            ("value", lambda sync: box.generator(local, steps, warmup, sync=sync)),
+            ("once", lambda sync: box.generator(local, steps, warmup, mode="once", sync=sync)),
+            ("warm_host", lambda sync: host_loops(box, "b200", min(nproc_rank, 4), 0.5, "per-request", sync=sync)),
+            ("e2e", lambda sync: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "device", sync=sync)),
+            ("e2e_host", lambda sync: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "per-request", sync=sync)),
+            ("e2e_once", lambda sync: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "once", sync=sync))]
+    # every rank walks the same list and meets the others at exactly two barriers per entry, whatever happened:
+    # the one inside the entry (or its stand-in here) and the one after it
     for name, fn in plan:
+        met = [False]
+
+        def sync_once():
+            if not met[0]:
+                met[0] = True
+                rep.barrier()
+
         if box is not None and lb_error is None:
             try:
-                lb[name] = fn()
+                lb[name] = fn(sync_once)
             except Exception as ex:
                 lb_error = "%s: %s: %s" % (name, type(ex).__name__, ex)
+        sync_once()
         rep.barrier()
     if box is not None and lb_error is None and world == 1 and not args.no_loopback:
         extras = {}
@@ -739,16 +749,38 @@ class LoopbackBox:
                 pass
         return False
 
-    def generator(self, dev, steps, warmup, mode="per-request", concurrency=SLOTS, extra=(), min_seconds=0.1, timeout=120):
-        """One `python -m client_b200.perf.loopback` child against this box's server for `dev`."""
+    def generator(self, dev, steps, warmup, mode="per-request", concurrency=SLOTS, extra=(), min_seconds=0.1, timeout=120, sync=None):
+        """One `python -m client_b200.perf.loopback` child against this box's server for `dev`.  `sync`: called
+        once when the child is warm (or has failed); the child starts timing when it returns -- with one
+        rank per GPU that is the barrier that makes every instance time the same interval."""
+        import tempfile
+
         cmd = [sys.executable, "-m", "client_b200.perf.loopback", "-u", self.urls[dev], "--device", str(dev), "--concurrency", str(concurrency),
                "--steps", str(steps), "--warmup", str(warmup), "--input-data-mode", mode, "--min-seconds", str(min_seconds),
                "--seed", str(SEED), "--json"] + (["--pin-cpus"] if self.pin else []) + list(extra)
-        r = subprocess.run(cmd, cwd=ROOT, env=self.env, capture_output=True, text=True, timeout=timeout)
-        for line in r.stdout.splitlines():
+        if sync is None:
+            r = subprocess.run(cmd, cwd=ROOT, env=self.env, capture_output=True, text=True, timeout=timeout)
+            stdout, stderr = r.stdout, r.stderr
+        else:
+            with tempfile.TemporaryDirectory(prefix="tb200_sync_") as sync_dir:
+                child = subprocess.Popen(cmd + ["--sync-dir", sync_dir], cwd=ROOT, env=self.env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                try:
+                    t_end = time.perf_counter() + timeout
+                    while not os.path.exists(os.path.join(sync_dir, "ready")) and child.poll() is None and time.perf_counter() < t_end:
+                        time.sleep(0.002)
+                finally:
+                    sync()
+                with open(os.path.join(sync_dir, "go"), "w"):
+                    pass
+                try:
+                    stdout, stderr = child.communicate(timeout=timeout)
+                except subprocess.TimeoutExpired:
+                    child.kill()
+                    stdout, stderr = child.communicate()
+        for line in stdout.splitlines():
             if line.startswith("{"):
                 return json.loads(line)
-        raise RuntimeError("generator child failed: " + (r.stdout + r.stderr)[-400:])
+        raise RuntimeError("generator child failed: " + (stdout + stderr)[-400:])
 
 
 def _host_loop_worker(impl, url, device, tag, seconds, data_mode, ready, go, q):
@@ -767,9 +799,10 @@ def _host_loop_worker(impl, url, device, tag, seconds, data_mode, ready, go, q):
         q.put((0, [], "%s: %s" % (type(ex).__name__, ex)))
 
 
-def host_loops(box, impl, nproc, seconds, data_mode):
+def host_loops(box, impl, nproc, seconds, data_mode, sync=None):
     """`nproc` free-running client processes (round-robin over the box's servers) for `seconds`
-    of wall time; impl "b200" = the drop-in modules, "reference" = the restated reference code."""
+    of wall time; impl "b200" = the drop-in modules, "reference" = the restated reference code.
+    `sync`: called once when this rank's clients are ready, before they are released (the ranks' barrier)."""
     import multiprocessing as mp
 
     ctx = mp.get_context("spawn")
@@ -794,6 +827,8 @@ def host_loops(box, impl, nproc, seconds, data_mode):
         ready.wait(timeout=240)  # every client has its CUDA context, regions and connection
     except Exception:
         pass
+    if sync is not None:
+        sync()
     t0 = time.perf_counter()
     go.set()
     parts = [q.get(timeout=seconds + 240) for _ in procs]

@@ -24,12 +24,27 @@ import sys
 import time
 
 
-def measure(gen, concurrency, steps, warmup, min_seconds, max_seconds=20.0):
+def rendezvous(sync_dir, timeout=180.0):
+    """Tell the parent this instance is warm (``ready``) and keep the loop running until it says ``go``:
+    with one instance per GPU the timed regions then start together, after every instance's start-up
+    (context creation and region registration of one process stall CUDA calls of the others)."""
+    import os
+
+    with open(os.path.join(sync_dir, "ready"), "w"):
+        pass
+    t_end = time.perf_counter() + timeout
+    while not os.path.exists(os.path.join(sync_dir, "go")) and time.perf_counter() < t_end:
+        time.sleep(0.001)
+
+
+def measure(gen, concurrency, steps, warmup, min_seconds, max_seconds=20.0, sync_dir=None):
     """[per-repetition dicts]; a repetition = `steps` x `concurrency` finished requests."""
     per_rep = steps * concurrency
     gen.window(0.0)
     if warmup > 0:
         gen.wait_count(warmup * concurrency, timeout=30.0)
+    if sync_dir:
+        rendezvous(sync_dir)
     reps, timed, t_start = [], 0.0, time.perf_counter()
     while True:
         gen.window(0.0)  # reset: the count window starts here
@@ -57,6 +72,7 @@ def main(argv=None):
     ap.add_argument("--lookahead", type=int, default=1)
     ap.add_argument("--seed", type=int, default=20260921)
     ap.add_argument("--pin-cpus", action="store_true")
+    ap.add_argument("--sync-dir", default=None, help="after the warm-up create <dir>/ready and start timing when <dir>/go appears")
     ap.add_argument("--no-validate", action="store_true")
     ap.add_argument("--json", action="store_true")
     args = ap.parse_args(argv)
@@ -84,7 +100,7 @@ def main(argv=None):
                               pipeline_depth=args.device_pipeline)
     gen.start()
     try:
-        reps = measure(gen, args.concurrency, args.steps, args.warmup, args.min_seconds)
+        reps = measure(gen, args.concurrency, args.steps, args.warmup, args.min_seconds, sync_dir=args.sync_dir)
     finally:
         gen.stop()
         ss.unregister(control)

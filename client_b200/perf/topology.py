@@ -107,7 +107,16 @@ def pin(cpus):
         return []
 
 
+def physical_index(device_id):
+    """The nvidia-smi index behind CUDA ordinal ``device_id``: CUDA_VISIBLE_DEVICES renumbers the devices a
+    process sees, sysfs and nvidia-smi do not.  (UUID entries cannot be mapped here and leave the ordinal.)"""
+    parts = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+    if parts and all(x.isdigit() for x in parts) and 0 <= int(device_id) < len(parts):
+        return int(parts[int(device_id)])
+    return int(device_id)
+
+
 def pin_for(device_id, role):
     """Pin to the cores planned for (GPU ``device_id``, role 'server' | 'generator' | 'all')."""
-    p = plan().get(int(device_id))
+    p = plan().get(physical_index(device_id))
     return pin(p[role]) if p else []

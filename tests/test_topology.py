@@ -47,3 +47,41 @@ def test_pin_changes_and_restores_the_affinity_mask():
         assert topology.pin([]) == []
     finally:
         os.sched_setaffinity(0, set(before))
+
+
+def test_physical_index_follows_cuda_visible_devices(monkeypatch):
+    from client_b200.perf import topology
+
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES", raising=False)
+    assert topology.physical_index(3) == 3
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "5")
+    assert topology.physical_index(0) == 5
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "2, 6,7")
+    assert [topology.physical_index(i) for i in range(3)] == [2, 6, 7]
+    assert topology.physical_index(4) == 4  # out of range: left alone
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "GPU-8f6c1e2a")
+    assert topology.physical_index(0) == 0
+
+
+def test_loopback_rendezvous_waits_for_go(tmp_path):
+    """client_b200/perf/loopback.py: an instance reports `ready` and starts timing only when `go` appears"""
+    import threading
+    import time
+
+    from client_b200.perf import loopback
+
+    def release():
+        while not (tmp_path / "ready").exists():
+            time.sleep(0.001)
+        time.sleep(0.05)
+        (tmp_path / "go").write_text("")
+
+    th = threading.Thread(target=release)
+    th.start()
+    t0 = time.perf_counter()
+    loopback.rendezvous(str(tmp_path), timeout=5.0)
+    assert time.perf_counter() - t0 >= 0.05 and (tmp_path / "ready").exists()
+    th.join()
+    t0 = time.perf_counter()
+    loopback.rendezvous(str(tmp_path / "missing_parent") if False else str(tmp_path), timeout=0.2)  # go already there: returns at once
+    assert time.perf_counter() - t0 < 0.1
