@@ -407,20 +407,14 @@ def run_b200(args):
     lb, lb_error = {}, None
     import shutil
 
-    have_mps = shutil.which("nvidia-cuda-mps-control") is not None and not args.no_mps
-    if rank == 0 and have_mps:
-        try:
-            LoopbackBox.start_mps()
-        except Exception:
-            have_mps = False
-    if world > 1:  # rank 0 decides
-        have_mps = rep.sum(1.0 if (rank == 0 and have_mps) else 0.0) > 0
-    rep.barrier()
+    want_mps = shutil.which("nvidia-cuda-mps-control") is not None and not args.no_mps
     box = None
-    try:
-        box = LoopbackBox([local], use_mps=have_mps, manage_mps=False, grpc=(world == 1)).__enter__()
+    try:  # this rank's GPU: its own MPS daemon, its server
+        box = LoopbackBox([local], use_mps=want_mps, grpc=(world == 1)).__enter__()
     except Exception as ex:
         lb_error = "%s: %s" % (type(ex).__name__, ex)
+    have_mps = rep.sum(1.0 if (box is not None and box.mps) else 0.0) >= world  # every rank got its daemon
+    rep.barrier()
     # every entry takes `sync`, the ranks' rendezvous between "my instance is warm" and "time now"
     plan = [("warm", lambda sync: box.generator(local, 50, 5, min_seconds=0.05, sync=sync)),
             ("value", lambda sync: box.generator(local, steps, warmup, sync=sync)),
@@ -458,22 +452,17 @@ def run_b200(args):
                 extras[key] = {"error": "%s: %s" % (type(ex).__name__, ex)}
         if box.grpc_urls.get(local):
             try:
-                extras["grpc"] = _grpc_loopback_levels(box.grpc_urls[local], box.env)
+                extras["grpc"] = _grpc_loopback_levels(box.grpc_urls[local], box.envs[local])
             except Exception as ex:
                 extras["grpc"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
         lb["levels"] = extras
     if box is not None:
         box.__exit__(None, None, None)
     rep.barrier()
-    if rank == 0 and have_mps:
-        try:
-            LoopbackBox.stop_mps()
-        except Exception:
-            pass
     time_sliced = None
     if world == 1 and have_mps and not args.no_loopback and lb_error is None:
         try:  # the same run without MPS: client and server are time-sliced CUDA contexts
-            with LoopbackBox([local], use_mps=False, manage_mps=False) as box:
+            with LoopbackBox([local], use_mps=False) as box:
                 box.generator(local, 50, 5, min_seconds=0.05)
                 g = box.generator(local, min(steps, 2000), warmup, extra=("--device-window-us", "150"), min_seconds=0.5)
                 time_sliced = {"infer_per_s": round(g["infer_per_s"], 1), "p50_us": round(g["p50_us"], 1), "device_window_us": 150,
@@ -520,7 +509,8 @@ def run_b200(args):
         "input_pack_gbps": round(value * IN_BYTES / 1e9, 1),
         "l2": "inputs of the kernel timings rotate over %d region sets = %d MB > 126 MB L2" % (SETS, SETS * SLOTS * IN_BYTES // 1000000),
         "e2e": {"value": round(e2e_value, 1), "unit": "infer/s", "h2d_bytes_per_step": SLOTS * (FILL_JOB_BYTES + CHECK_JOB_BYTES), "d2h_bytes_per_step": SLOTS * CHECK_RESULT_BYTES,
-                "processes": nproc_rank * world, "seconds": HOST_LOOP_SECONDS, "p50_us": lb.get("e2e", {}).get("p50_us"),
+                "processes": nproc_rank * world, "failed_clients": int(total("e2e", "failed_workers")) if lb_error is None else None,
+                "seconds": HOST_LOOP_SECONDS, "p50_us": lb.get("e2e", {}).get("p50_us"),
                 "what": "tritonclient-compatible API, one blocking client per process (client_b200/perf/host_loop.py, mode 'device'): per request "
                         "http.InferenceServerClient.infer naming the regions -> cuda_shared_memory.check_shared_memory_region (validate on the device, "
                         "32-byte verdict D2H) + cuda_shared_memory.fill_shared_memory_region (job descriptor H2D, Philox fill of the next request's "
@@ -671,66 +661,106 @@ def common_config(mps, world):
 
 
 class LoopbackBox:
-    """The serving side of a loopback run: a private CUDA MPS daemon (when the box has the binary and
-    `manage_mps`) and one native server process per device, each pinned to its GPU's server cores."""
+    """The serving side of a loopback run: per device one private CUDA MPS daemon (when the box has the binary)
+    and one native server process, pinned to its GPU's server cores.
+
+    One daemon PER GPU, each started with CUDA_VISIBLE_DEVICES = that GPU: an MPS server takes 48 clients in
+    all, not per device -- one shared daemon on an 8-GPU box refuses most of 8 x (server + generator + API
+    clients) with "device(s) busy or unavailable".  The processes of GPU d therefore run with
+    CUDA_VISIBLE_DEVICES=d and address it as ordinal 0 (`ordinal[d]`; pinning maps it back,
+    client_b200/perf/topology.physical_index); without MPS they see every GPU and use ordinal d."""
 
     # per launch (torchrun ranks share MASTER_PORT): a daemon of an earlier run that is still shutting
     # down cannot be mistaken for ours
     _TAG = os.environ.get("MASTER_PORT", "") + "_" + str(os.getppid() if os.environ.get("RANK") else os.getpid())
-    MPS_ENV = {"CUDA_MPS_PIPE_DIRECTORY": "/tmp/tb200_mps_pipe_" + _TAG, "CUDA_MPS_LOG_DIRECTORY": "/tmp/tb200_mps_log_" + _TAG}
 
     def __init__(self, devices, use_mps=True, manage_mps=True, grpc=False, pin=True):
         import shutil
 
         self.devices, self.grpc, self.pin = list(devices), grpc, pin
-        self.manage_mps = manage_mps and use_mps and shutil.which("nvidia-cuda-mps-control") is not None
-        self.mps = use_mps and shutil.which("nvidia-cuda-mps-control") is not None
-        self.env = dict(os.environ, **self.MPS_ENV) if self.mps else dict(os.environ)
-        self.servers, self.urls, self.grpc_urls = {}, {}, {}
+        self.mps = self.manage_mps = use_mps and manage_mps and shutil.which("nvidia-cuda-mps-control") is not None
+        self.servers, self.urls, self.grpc_urls, self.envs, self.ordinal = {}, {}, {}, {}, {}
+        self._daemons = []
+        for d in self.devices:
+            self._plain_env(d)
 
-    @classmethod
-    def start_mps(cls):
-        env = dict(os.environ, **cls.MPS_ENV)
-        for d in cls.MPS_ENV.values():
-            os.makedirs(d, exist_ok=True)
+    def _plain_env(self, d):
+        self.envs[d], self.ordinal[d] = dict(os.environ), d
+
+    def _mps_env(self, d):
+        visible = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+        phys = visible[d] if d < len(visible) else str(d)
+        tag = "%s_g%d" % (self._TAG, d)
+        return dict(os.environ, CUDA_VISIBLE_DEVICES=phys, CUDA_MPS_PIPE_DIRECTORY="/tmp/tb200_mps_pipe_" + tag,
+                    CUDA_MPS_LOG_DIRECTORY="/tmp/tb200_mps_log_" + tag)
+
+    def _start_mps(self, d):
+        env = self._mps_env(d)
+        for key in ("CUDA_MPS_PIPE_DIRECTORY", "CUDA_MPS_LOG_DIRECTORY"):
+            os.makedirs(env[key], exist_ok=True)
         subprocess.run(["nvidia-cuda-mps-control", "-d"], env=env, timeout=30, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        time.sleep(1.0)
+        self._daemons.append(env)
+        self.envs[d], self.ordinal[d] = env, 0
 
-    @classmethod
-    def stop_mps(cls):
-        env = dict(os.environ, **cls.MPS_ENV)
-        subprocess.run(["nvidia-cuda-mps-control"], input="quit\n", env=env, text=True, timeout=30, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    def _stop_mps(self):
+        for env in self._daemons:
+            try:
+                subprocess.run(["nvidia-cuda-mps-control"], input="quit\n", env=env, text=True, timeout=30, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            except Exception:
+                pass
+        self._daemons = []
 
-    def __enter__(self):
+    def _start_server(self, dev):
+        import select
         import socket
 
-        if self.manage_mps:
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(self.ordinal[dev])]
+        if self.grpc:
+            cmd += ["--grpc-port", "0"]
+        if self.pin:
+            cmd += ["--pin-cpus"]
+        srv = subprocess.Popen(cmd, cwd=ROOT, env=self.envs[dev], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        ready, _, _ = select.select([srv.stdout], [], [], 90.0)  # a server that never comes up must not hang the bench
+        hello = srv.stdout.readline() if ready else "timeout waiting for the server"
+        if "listening" not in hello:
+            srv.terminate()
             try:
-                self.start_mps()
+                rest, _ = srv.communicate(timeout=10)  # the rest of what it said (a traceback, usually)
             except Exception:
-                self.mps = self.manage_mps = False
-                self.env = dict(os.environ)
-        for dev in self.devices:
-            with socket.socket() as sk:
-                sk.bind(("127.0.0.1", 0))
-                port = sk.getsockname()[1]
-            cmd = [sys.executable, "-m", "client_b200.testing.native_server", "--port", str(port), "--device", str(dev)]
-            if self.grpc:
-                cmd += ["--grpc-port", "0"]
-            if self.pin:
-                cmd += ["--pin-cpus"]
-            self.servers[dev] = subprocess.Popen(cmd, cwd=ROOT, env=self.env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-            self.urls[dev] = "127.0.0.1:%d" % port
-        import select
+                srv.kill()
+                rest = ""
+            raise RuntimeError("native server for device %d did not start: %s" % (dev, " | ".join((hello + (rest or "")).strip().splitlines()[-4:])[:600]))
+        self.servers[dev] = srv
+        self.urls[dev] = "127.0.0.1:%d" % port
+        if "grpc=" in hello:
+            self.grpc_urls[dev] = hello.split("grpc=")[1].strip()
 
-        for dev, srv in self.servers.items():
-            ready, _, _ = select.select([srv.stdout], [], [], 90.0)  # a server that never comes up must not hang the bench
-            hello = srv.stdout.readline() if ready else "timeout waiting for the server"
-            if "listening" not in hello:
-                self.__exit__(None, None, None)
-                raise RuntimeError("native server for device %d did not start: %s" % (dev, hello.strip()[:200]))
-            if "grpc=" in hello:
-                self.grpc_urls[dev] = hello.split("grpc=")[1].strip()
+    def __enter__(self):
+        try:
+            if self.manage_mps:
+                try:
+                    for d in self.devices:
+                        self._start_mps(d)
+                    time.sleep(1.0)
+                except Exception:  # no daemon to be had: time-sliced contexts
+                    self._stop_mps()
+                    self.mps = self.manage_mps = False
+                    for d in self.devices:
+                        self._plain_env(d)
+            for dev in self.devices:
+                try:
+                    self._start_server(dev)
+                except RuntimeError:
+                    if not self.mps:
+                        raise
+                    time.sleep(5.0)  # a daemon of an earlier run may still hold the GPU while it shuts down: once more
+                    self._start_server(dev)
+        except Exception:
+            self.__exit__(None, None, None)
+            raise
         return self
 
     def __exit__(self, *exc):
@@ -742,11 +772,7 @@ class LoopbackBox:
             except Exception:
                 srv.kill()
         self.servers = {}
-        if self.manage_mps:
-            try:
-                self.stop_mps()
-            except Exception:
-                pass
+        self._stop_mps()
         return False
 
     def generator(self, dev, steps, warmup, mode="per-request", concurrency=SLOTS, extra=(), min_seconds=0.1, timeout=120, sync=None):
@@ -755,15 +781,15 @@ class LoopbackBox:
         rank per GPU that is the barrier that makes every instance time the same interval."""
         import tempfile
 
-        cmd = [sys.executable, "-m", "client_b200.perf.loopback", "-u", self.urls[dev], "--device", str(dev), "--concurrency", str(concurrency),
+        cmd = [sys.executable, "-m", "client_b200.perf.loopback", "-u", self.urls[dev], "--device", str(self.ordinal[dev]), "--concurrency", str(concurrency),
                "--steps", str(steps), "--warmup", str(warmup), "--input-data-mode", mode, "--min-seconds", str(min_seconds),
                "--seed", str(SEED), "--json"] + (["--pin-cpus"] if self.pin else []) + list(extra)
         if sync is None:
-            r = subprocess.run(cmd, cwd=ROOT, env=self.env, capture_output=True, text=True, timeout=timeout)
+            r = subprocess.run(cmd, cwd=ROOT, env=self.envs[dev], capture_output=True, text=True, timeout=timeout)
             stdout, stderr = r.stdout, r.stderr
         else:
             with tempfile.TemporaryDirectory(prefix="tb200_sync_") as sync_dir:
-                child = subprocess.Popen(cmd + ["--sync-dir", sync_dir], cwd=ROOT, env=self.env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                child = subprocess.Popen(cmd + ["--sync-dir", sync_dir], cwd=ROOT, env=self.envs[dev], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
                 try:
                     t_end = time.perf_counter() + timeout
                     while not os.path.exists(os.path.join(sync_dir, "ready")) and child.poll() is None and time.perf_counter() < t_end:
@@ -806,17 +832,23 @@ def host_loops(box, impl, nproc, seconds, data_mode, sync=None):
     import multiprocessing as mp
 
     ctx = mp.get_context("spawn")
-    saved = {k: os.environ.get(k) for k in LoopbackBox.MPS_ENV}
-    if box.mps:
-        os.environ.update(LoopbackBox.MPS_ENV)  # the children must come up under the MPS daemon
+    ready, go, q = ctx.Barrier(nproc + 1), ctx.Event(), ctx.Queue()
+    devs = box.devices
+    procs = []
+    keys = ("CUDA_VISIBLE_DEVICES", "CUDA_MPS_PIPE_DIRECTORY", "CUDA_MPS_LOG_DIRECTORY")
+    saved = {k: os.environ.get(k) for k in keys}
     try:
-        ready, go, q = ctx.Barrier(nproc + 1), ctx.Event(), ctx.Queue()
-        devs = box.devices
-        procs = [ctx.Process(target=_host_loop_worker,
-                             args=(impl, box.urls[devs[i % len(devs)]], devs[i % len(devs)], "%s%d_%d" % (impl[0], os.getpid(), i), seconds, data_mode, ready, go, q))
-                 for i in range(nproc)]
-        for p in procs:
+        for i in range(nproc):
+            dev = devs[i % len(devs)]
+            for k in keys:  # a spawned child inherits this process's environment: its GPU's daemon, its GPU as ordinal 0
+                if k in box.envs[dev]:
+                    os.environ[k] = box.envs[dev][k]
+                else:
+                    os.environ.pop(k, None)
+            p = ctx.Process(target=_host_loop_worker,
+                            args=(impl, box.urls[dev], box.ordinal[dev], "%s%d_%d" % (impl[0], os.getpid(), i), seconds, data_mode, ready, go, q))
             p.start()
+            procs.append(p)
     finally:
         for k, v in saved.items():
             if v is None:
@@ -840,7 +872,7 @@ def host_loops(box, impl, nproc, seconds, data_mode, sync=None):
     lat = np.concatenate([np.asarray(l, dtype=np.float64) for _, l, _ in parts if len(l)]) / 1e3 if total else np.zeros(1)
     return {"infer_per_s": round(total / seconds, 1), "count": int(total), "seconds": seconds, "wall_seconds": round(dt, 3), "processes": nproc,
             "p50_us": round(float(np.percentile(lat, 50)), 1), "p99_us": round(float(np.percentile(lat, 99)), 1),
-            **({"errors": errors[:2]} if errors else {})}
+            "failed_workers": len(errors), **({"errors": errors[:2]} if errors else {})}
 
 
 def host_process_count(world):
@@ -930,6 +962,7 @@ def run_reference(args):
         "input_pack_gbps": round(value * IN_BYTES / 1e9, 3),
         "timing": "wall clock: completed requests of all processes / the fixed run time (free-running, no per-step barrier)",
     }
+    line["failed_clients"] = per_request.get("failed_workers", 0)
     if per_request.get("errors"):
         line["errors"] = per_request["errors"]
     print(json.dumps(line), flush=True)

@@ -1,8 +1,8 @@
 """Why does the loopback rate per GPU drop when two instances run side by side?  On a 2-GPU box:
-  A  both generators at once, one shared MPS daemon (what bench.py does)
-  B  GPU 0 alone under the shared daemon
-  C  both at once, one MPS daemon per GPU (each daemon and its clients see only their GPU)
-  D  both at once, shared daemon, no CPU pinning
+both generators at once vs one alone, and the same for 32 drop-in API clients per GPU (bench.py's e2e loop),
+under bench.LoopbackBox (one MPS daemon per GPU).  Findings of the first version (one shared daemon): the
+native generators do not disturb each other (2 x 452 k), but an MPS server takes 48 clients in all -- 17 of
+2 x 32 API clients were refused ("device(s) busy or unavailable").
 """
 import json
 import os
@@ -31,43 +31,45 @@ def run_pair(boxes, devs, label, seconds=1.0):
     print(label, out, "sum", round(sum(out.values()), 1), flush=True)
 
 
-class PerGpuBox(bench.LoopbackBox):
-    """One daemon per GPU: the daemon, the server and the generator of GPU d run with CUDA_VISIBLE_DEVICES=d."""
-
-    def __init__(self, dev):
-        super().__init__([0], use_mps=True, manage_mps=True)
-        self.phys = dev
-        tag = "_g%d" % dev
-        self.MPS_ENV = {k: v + tag for k, v in bench.LoopbackBox.MPS_ENV.items()}
-        self.env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(dev), **self.MPS_ENV)
-
-    def start_mps(self):
-        for d in self.MPS_ENV.values():
-            os.makedirs(d, exist_ok=True)
-        subprocess.run(["nvidia-cuda-mps-control", "-d"], env=self.env, timeout=30, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        time.sleep(1.0)
-
-    def stop_mps(self):
-        subprocess.run(["nvidia-cuda-mps-control"], input="quit\n", env=self.env, text=True, timeout=30, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-
-
 def main():
-    with bench.LoopbackBox([0, 1], use_mps=True, manage_mps=True) as box:
+    with bench.LoopbackBox([0, 1]) as box:  # one MPS daemon per GPU
         run_pair({0: box, 1: box}, [(0, 0), (1, 1)], "warm", 0.3)
-        run_pair({0: box, 1: box}, [(0, 0), (1, 1)], "A shared daemon, both  ")
-        run_pair({0: box}, [(0, 0)], "B shared daemon, GPU0  ")
-        run_pair({1: box}, [(1, 1)], "B shared daemon, GPU1  ")
-        run_pair({0: box, 1: box}, [(0, 0), (1, 1)], "A again                ")
-    time.sleep(2.0)
-    b0, b1 = PerGpuBox(0), PerGpuBox(1)
-    with b0, b1:
-        run_pair({0: b0, 1: b1}, [(0, 0), (1, 0)], "warm", 0.3)
-        run_pair({0: b0, 1: b1}, [(0, 0), (1, 0)], "C daemon per GPU, both ")
-        run_pair({0: b0}, [(0, 0)], "C daemon per GPU, GPU0 ")
-    time.sleep(2.0)
-    with bench.LoopbackBox([0, 1], use_mps=True, manage_mps=True, pin=False) as box:
-        run_pair({0: box, 1: box}, [(0, 0), (1, 1)], "warm", 0.3)
-        run_pair({0: box, 1: box}, [(0, 0), (1, 1)], "D shared, unpinned     ")
+        run_pair({0: box, 1: box}, [(0, 0), (1, 1)], "generators, both GPUs ")
+        run_pair({0: box}, [(0, 0)], "generator, GPU0 only   ")
+        hosts(box, [0, 1], "drop-in API device loops, both GPUs")
+        hosts(box, [0], "drop-in API device loops, GPU0 only")
+
+
+def hosts(box, devs, label, nproc=32, seconds=2.0):
+    """`nproc` drop-in API clients per GPU in device mode (bench.py's e2e), all GPUs at once"""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    total = nproc * len(devs)
+    ready, go, q = ctx.Barrier(total + 1), ctx.Event(), ctx.Queue()
+    procs = []
+    saved = dict(os.environ)
+    try:
+        for d in devs:
+            os.environ.clear()
+            os.environ.update(box.envs[d])
+            for i in range(nproc):
+                p = ctx.Process(target=bench._host_loop_worker, args=("b200", box.urls[d], box.ordinal[d], "d%d_%d_%d" % (d, os.getpid(), i), seconds, "device", ready, go, q))
+                p.start()
+                procs.append(p)
+    finally:
+        os.environ.clear()
+        os.environ.update(saved)
+    try:
+        ready.wait(timeout=240)
+    except Exception:
+        pass
+    go.set()
+    parts = [q.get(timeout=seconds + 240) for _ in procs]
+    for p in procs:
+        p.join(30)
+    errs = [e for _, _, e in parts if e]
+    print(label, round(sum(n for n, _, _ in parts) / seconds / 1e3, 1), "k infer/s", ("errors: %d, first: %s" % (len(errs), errs[0][:200])) if errs else "", flush=True)
 
 
 if __name__ == "__main__":
