@@ -667,7 +667,7 @@ class LoopbackBox:
     One daemon PER GPU, each started with CUDA_VISIBLE_DEVICES = that GPU: an MPS server takes 48 clients in
     all, not per device -- one shared daemon on an 8-GPU box refuses most of 8 x (server + generator + API
     clients) with "device(s) busy or unavailable".  The processes of GPU d therefore run with
-    CUDA_VISIBLE_DEVICES=d and address it as ordinal 0 (`ordinal[d]`; pinning maps it back,
+    the daemon's only device, ordinal 0 (`ordinal[d]`; TB200_PIN_GPU names the board index for the CPU pinning,
     client_b200/perf/topology.physical_index); without MPS they see every GPU and use ordinal d."""
 
     # per launch (torchrun ranks share MASTER_PORT): a daemon of an earlier run that is still shutting
@@ -691,7 +691,7 @@ class LoopbackBox:
         visible = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
         phys = visible[d] if d < len(visible) else str(d)
         tag = "%s_g%d" % (self._TAG, d)
-        return dict(os.environ, CUDA_VISIBLE_DEVICES=phys, CUDA_MPS_PIPE_DIRECTORY="/tmp/tb200_mps_pipe_" + tag,
+        return dict(os.environ, CUDA_VISIBLE_DEVICES=phys, TB200_PIN_GPU=phys, CUDA_MPS_PIPE_DIRECTORY="/tmp/tb200_mps_pipe_" + tag,
                     CUDA_MPS_LOG_DIRECTORY="/tmp/tb200_mps_log_" + tag)
 
     def _start_mps(self, d):
@@ -700,7 +700,9 @@ class LoopbackBox:
             os.makedirs(env[key], exist_ok=True)
         subprocess.run(["nvidia-cuda-mps-control", "-d"], env=env, timeout=30, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         self._daemons.append(env)
-        self.envs[d], self.ordinal[d] = env, 0
+        # a client's CUDA_VISIBLE_DEVICES counts in the devices its MPS daemon exposes -- the one GPU, ordinal 0;
+        # which GPU that is on the board (for the CPU pinning) travels in TB200_PIN_GPU
+        self.envs[d], self.ordinal[d] = dict(env, CUDA_VISIBLE_DEVICES="0"), 0
 
     def _stop_mps(self):
         for env in self._daemons:
@@ -835,7 +837,7 @@ def host_loops(box, impl, nproc, seconds, data_mode, sync=None):
     ready, go, q = ctx.Barrier(nproc + 1), ctx.Event(), ctx.Queue()
     devs = box.devices
     procs = []
-    keys = ("CUDA_VISIBLE_DEVICES", "CUDA_MPS_PIPE_DIRECTORY", "CUDA_MPS_LOG_DIRECTORY")
+    keys = ("CUDA_VISIBLE_DEVICES", "TB200_PIN_GPU", "CUDA_MPS_PIPE_DIRECTORY", "CUDA_MPS_LOG_DIRECTORY")
     saved = {k: os.environ.get(k) for k in keys}
     try:
         for i in range(nproc):

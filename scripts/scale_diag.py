@@ -32,12 +32,17 @@ def run_pair(boxes, devs, label, seconds=1.0):
 
 
 def main():
+    quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    nproc, secs = (4, 0.5) if quick else (32, 2.0)
     with bench.LoopbackBox([0, 1]) as box:  # one MPS daemon per GPU
+        print("mps", box.mps, "ordinals", box.ordinal, flush=True)
         run_pair({0: box, 1: box}, [(0, 0), (1, 1)], "warm", 0.3)
-        run_pair({0: box, 1: box}, [(0, 0), (1, 1)], "generators, both GPUs ")
-        run_pair({0: box}, [(0, 0)], "generator, GPU0 only   ")
-        hosts(box, [0, 1], "drop-in API device loops, both GPUs")
-        hosts(box, [0], "drop-in API device loops, GPU0 only")
+        run_pair({0: box, 1: box}, [(0, 0), (1, 1)], "generators, both GPUs ", 0.3 if quick else 1.0)
+        if not quick:
+            run_pair({0: box}, [(0, 0)], "generator, GPU0 only   ")
+        hosts(box, [0, 1], "drop-in API device loops, both GPUs", nproc, secs)
+        if not quick:
+            hosts(box, [0], "drop-in API device loops, GPU0 only", nproc, secs)
 
 
 def hosts(box, devs, label, nproc=32, seconds=2.0):

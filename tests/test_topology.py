@@ -53,6 +53,7 @@ def test_physical_index_follows_cuda_visible_devices(monkeypatch):
     from client_b200.perf import topology
 
     monkeypatch.delenv("CUDA_VISIBLE_DEVICES", raising=False)
+    monkeypatch.delenv("TB200_PIN_GPU", raising=False)
     assert topology.physical_index(3) == 3
     monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "5")
     assert topology.physical_index(0) == 5
@@ -61,6 +62,9 @@ def test_physical_index_follows_cuda_visible_devices(monkeypatch):
     assert topology.physical_index(4) == 4  # out of range: left alone
     monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "GPU-8f6c1e2a")
     assert topology.physical_index(0) == 0
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "0")  # a client of an MPS daemon that owns GPU 6
+    monkeypatch.setenv("TB200_PIN_GPU", "6")
+    assert topology.physical_index(0) == 6
 
 
 def test_loopback_rendezvous_waits_for_go(tmp_path):
