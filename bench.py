@@ -423,23 +423,10 @@ def run_b200(args):
             ("e2e", lambda sync: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "device", sync=sync)),
             ("e2e_host", lambda sync: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "per-request", sync=sync)),
             ("e2e_once", lambda sync: host_loops(box, "b200", nproc_rank, HOST_LOOP_SECONDS, "once", sync=sync))]
-    # every rank walks the same list and meets the others at exactly two barriers per entry, whatever happened:
-    # the one inside the entry (or its stand-in here) and the one after it
-    for name, fn in plan:
-        met = [False]
-
-        def sync_once():
-            if not met[0]:
-                met[0] = True
-                rep.barrier()
-
-        if box is not None and lb_error is None:
-            try:
-                lb[name] = fn(sync_once)
-            except Exception as ex:
-                lb_error = "%s: %s: %s" % (name, type(ex).__name__, ex)
-        sync_once()
-        rep.barrier()
+    # every rank walks the same list and meets the others at exactly two barriers per entry, whatever happened
+    walked, walk_error = rep.walk(plan, enabled=box is not None and lb_error is None)
+    lb.update(walked)
+    lb_error = lb_error or walk_error
     if box is not None and lb_error is None and world == 1 and not args.no_loopback:
         extras = {}
         for key, conc, extra in (("c1", 1, ()), ("c256", 256, ()), ("c64_one_pass_at_a_time", 64, ("--device-pipeline", "1")),

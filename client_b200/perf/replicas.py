@@ -66,6 +66,30 @@ class Replicas:
         """Whole-job throughput: all units of all ranks / the slowest rank's time."""
         return self.sum(local_units) / self.max(local_seconds)
 
+    def walk(self, plan, enabled=True):
+        """Run ``plan`` -- [(name, fn(sync))] -- on every rank in step: each entry meets the other ranks at
+        exactly two barriers whatever happens on this rank, the one ``fn`` calls through ``sync`` (between "my
+        instance is warm" and "time now"; made up for here when ``fn`` fails before it, or is skipped) and one
+        after the entry.  After the first failure the remaining entries are skipped, the barriers are not.
+        Returns ({name: result}, error string or None)."""
+        results, error = {}, None
+        for name, fn in plan:
+            met = [False]
+
+            def sync_once():
+                if not met[0]:
+                    met[0] = True
+                    self.barrier()
+
+            if enabled and error is None:
+                try:
+                    results[name] = fn(sync_once)
+                except Exception as ex:
+                    error = "%s: %s: %s" % (name, type(ex).__name__, ex)
+            sync_once()
+            self.barrier()
+        return results, error
+
     def close(self):
         if self._dist is not None and self._dist.is_initialized():
             self._dist.destroy_process_group()
