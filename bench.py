@@ -678,7 +678,8 @@ class LoopbackBox:
         visible = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
         phys = visible[d] if d < len(visible) else str(d)
         tag = "%s_g%d" % (self._TAG, d)
-        return dict(os.environ, CUDA_VISIBLE_DEVICES=phys, TB200_PIN_GPU=phys, CUDA_MPS_PIPE_DIRECTORY="/tmp/tb200_mps_pipe_" + tag,
+        board = phys if phys.isdigit() else str(d)  # UUID entries: the position in the list is the best guess for the pinning
+        return dict(os.environ, CUDA_VISIBLE_DEVICES=phys, TB200_PIN_GPU=board, CUDA_MPS_PIPE_DIRECTORY="/tmp/tb200_mps_pipe_" + tag,
                     CUDA_MPS_LOG_DIRECTORY="/tmp/tb200_mps_log_" + tag)
 
     def _start_mps(self, d):

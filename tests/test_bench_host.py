@@ -40,6 +40,15 @@ def test_per_gpu_daemon_environment(monkeypatch):
     assert len(quits) == 2 and {q[1]["CUDA_MPS_PIPE_DIRECTORY"] for q in quits} == {c[1]["CUDA_MPS_PIPE_DIRECTORY"] for c in calls[:2]}
 
 
+def test_uuid_device_lists_keep_the_daemon_on_its_gpu(monkeypatch):
+    import shutil
+
+    monkeypatch.setattr(shutil, "which", lambda name: "/usr/bin/" + name)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "GPU-aaaa,GPU-bbbb")
+    env = bench.LoopbackBox([0, 1])._mps_env(1)
+    assert env["CUDA_VISIBLE_DEVICES"] == "GPU-bbbb" and env["TB200_PIN_GPU"] == "1"
+
+
 def test_without_the_mps_binary_processes_see_every_gpu(monkeypatch):
     import shutil
 
